@@ -1,0 +1,220 @@
+// ctx.cu -- contexts: reference-layout twiddle tables, Shoup companions and per-limb constants in HBM, plus the
+// host-buffer (end-to-end) transform pipeline.  Replaces the parameter/table set-up every reference driver
+// repeats by hand (demo.cu:62-196: q_bit/mu computation, fillTablePsi128 per limb, cudaMemcpy per limb,
+// cudaMemcpyToSymbol into six 16-entry __constant__ tables).
+#include "internal.h"
+
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+using namespace nttb200;
+typedef unsigned __int128 u128;
+
+static u64 h_modpow(u64 a, u64 e, u64 m)
+{
+    u64 r = 1 % m;
+    a %= m;
+    while (e) { if (e & 1) r = (u64)((u128)r * a % m); a = (u64)((u128)a * a % m); e >>= 1; }
+    return r;
+}
+static unsigned h_bitrev(unsigned x, unsigned bits)
+{
+    unsigned r = 0;
+    for (unsigned i = 0; i < bits; i++) { r = (r << 1) | (x & 1); x >>= 1; }
+    return r;
+}
+static u64 h_shoup(u64 w, u64 q) { return (u64)(((u128)w << 64) / q); }
+
+static int ctx_finish(nttb200_ctx *c, const u64 *psi_h, const u64 *psiinv_h)
+{
+    const size_t tot = (size_t)c->limbs * c->n;
+    std::vector<u64> ps(tot), pis(tot);
+    std::vector<LimbConst> lc(c->limbs);
+    c->mu.resize(c->limbs); c->qbit.resize(c->limbs);
+    for (unsigned l = 0; l < c->limbs; l++) {
+        const u64 q = c->q[l];
+        for (size_t i = 0; i < c->n; i++) {
+            ps[l * (size_t)c->n + i] = h_shoup(psi_h[l * (size_t)c->n + i], q);
+            pis[l * (size_t)c->n + i] = h_shoup(psiinv_h[l * (size_t)c->n + i], q);
+        }
+        const unsigned qbit = (unsigned)(log2((double)q) + 1);            // demo.cu:69
+        const u64 mu = 2 * qbit < 128 ? (u64)(((u128)1 << (2 * qbit)) / q) : 0;   // demo.cu:157-165
+        c->mu[l] = mu; c->qbit[l] = qbit;
+        const u64 ninv = h_modpow(c->n % q, q - 2, q);
+        const u64 w1 = psiinv_h[l * (size_t)c->n + 1];
+        const u64 w1n = (u64)((u128)w1 * ninv % q);
+        LimbConst &k = lc[l];
+        k.q = q; k.twoq = 2 * q; k.mu = mu; k.qbit = qbit; k.pad = 0;
+        k.ninv = ninv; k.ninv_s = h_shoup(ninv, q);
+        k.w1ninv = w1n; k.w1ninv_s = h_shoup(w1n, q);
+    }
+    NTTB200_CHECK(cudaGetDevice(&c->device));
+    NTTB200_CHECK(cudaMalloc(&c->psi, tot * 8));
+    NTTB200_CHECK(cudaMalloc(&c->psiinv, tot * 8));
+    NTTB200_CHECK(cudaMalloc(&c->psi_s, tot * 8));
+    NTTB200_CHECK(cudaMalloc(&c->psiinv_s, tot * 8));
+    NTTB200_CHECK(cudaMalloc(&c->lc, sizeof(LimbConst) * c->limbs));
+    NTTB200_CHECK(cudaMalloc(&c->q_dev, 8 * c->limbs));
+    NTTB200_CHECK(cudaMalloc(&c->mu_dev, 8 * c->limbs));
+    NTTB200_CHECK(cudaMalloc(&c->qbit_dev, 4 * c->limbs));
+    NTTB200_CHECK(cudaMemcpy(c->psi, psi_h, tot * 8, cudaMemcpyHostToDevice));
+    NTTB200_CHECK(cudaMemcpy(c->psiinv, psiinv_h, tot * 8, cudaMemcpyHostToDevice));
+    NTTB200_CHECK(cudaMemcpy(c->psi_s, ps.data(), tot * 8, cudaMemcpyHostToDevice));
+    NTTB200_CHECK(cudaMemcpy(c->psiinv_s, pis.data(), tot * 8, cudaMemcpyHostToDevice));
+    NTTB200_CHECK(cudaMemcpy(c->lc, lc.data(), sizeof(LimbConst) * c->limbs, cudaMemcpyHostToDevice));
+    NTTB200_CHECK(cudaMemcpy(c->q_dev, c->q.data(), 8 * c->limbs, cudaMemcpyHostToDevice));
+    NTTB200_CHECK(cudaMemcpy(c->mu_dev, c->mu.data(), 8 * c->limbs, cudaMemcpyHostToDevice));
+    NTTB200_CHECK(cudaMemcpy(c->qbit_dev, c->qbit.data(), 4 * c->limbs, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static int ctx_alloc(nttb200_ctx **out, unsigned n, unsigned limbs, const u64 *q)
+{
+    if (!out || !q || limbs == 0 || limbs > NTTB200_MAX_LIMBS || (n & (n - 1)) || n < 2048 || n > 131072) return NTTB200_EINVAL;
+    for (unsigned l = 0; l < limbs; l++)
+        if (q[l] < 3 || (q[l] >> 62) || ((q[l] - 1) % (2ull * n))) return NTTB200_EINVAL;   // q < 2^62, q = 1 mod 2n
+    nttb200_ctx *c = new nttb200_ctx();
+    c->n = n; c->limbs = limbs;
+    while ((1u << c->logn) < n) c->logn++;
+    c->q.assign(q, q + limbs);
+    c->use_tma = get_tma_default();
+    *out = c;
+    return 0;
+}
+
+extern "C" {
+
+int nttb200_version(void) { return 100; }
+
+const char *nttb200_error_string(int code)
+{
+    if (code == 0) return "success";
+    if (code == NTTB200_EINVAL) return "nttb200: invalid argument (unsupported n / limbs / modulus, or null pointer)";
+    if (code == NTTB200_ENOTMA) return "nttb200: cuTensorMapEncodeTiled unavailable or failed";
+    return cudaGetErrorString((cudaError_t)code);
+}
+
+int nttb200_ctx_create(nttb200_ctx **ctx, unsigned n, unsigned limbs, const nttb200_u64 *q, const nttb200_u64 *psi_roots)
+{
+    if (!psi_roots) return NTTB200_EINVAL;
+    int r = ctx_alloc(ctx, n, limbs, q);
+    if (r) return r;
+    nttb200_ctx *c = *ctx;
+    const size_t tot = (size_t)limbs * n;
+    std::vector<u64> psi(tot), psiinv(tot);
+    for (unsigned l = 0; l < limbs; l++) {
+        // parameter.h:5-12: table[i] = root^bitrev(i); filled by walking the exponents in natural order
+        const u64 ql = q[l], root = psi_roots[l] % ql, rootinv = h_modpow(root, ql - 2, ql);
+        if (h_modpow(root, n, ql) != ql - 1) { delete c; *ctx = nullptr; return NTTB200_EINVAL; }   // psi^n = -1
+        u64 p = 1, pi = 1;
+        for (unsigned e = 0; e < n; e++) {
+            const unsigned i = h_bitrev(e, c->logn);
+            psi[l * (size_t)n + i] = p;
+            psiinv[l * (size_t)n + i] = pi;
+            p = (u64)((u128)p * root % ql);
+            pi = (u64)((u128)pi * rootinv % ql);
+        }
+    }
+    r = ctx_finish(c, psi.data(), psiinv.data());
+    if (r) { nttb200_ctx_destroy(c); *ctx = nullptr; }
+    return r;
+}
+
+int nttb200_ctx_create_from_tables(nttb200_ctx **ctx, unsigned n, unsigned limbs, const nttb200_u64 *q,
+                                   const nttb200_u64 *psi_tables_host, const nttb200_u64 *psiinv_tables_host)
+{
+    if (!psi_tables_host || !psiinv_tables_host) return NTTB200_EINVAL;
+    int r = ctx_alloc(ctx, n, limbs, q);
+    if (r) return r;
+    r = ctx_finish(*ctx, psi_tables_host, psiinv_tables_host);
+    if (r) { nttb200_ctx_destroy(*ctx); *ctx = nullptr; }
+    return r;
+}
+
+void nttb200_ctx_destroy(nttb200_ctx *c)
+{
+    if (!c) return;
+    cudaFree(c->psi); cudaFree(c->psiinv); cudaFree(c->psi_s); cudaFree(c->psiinv_s);
+    cudaFree(c->lc); cudaFree(c->q_dev); cudaFree(c->mu_dev); cudaFree(c->qbit_dev);
+    for (int i = 0; i < nttb200_ctx::kStages; i++) {
+        if (c->stage_dev[i]) cudaFree(c->stage_dev[i]);
+        if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
+    }
+    delete c;
+}
+
+int nttb200_ctx_tables(const nttb200_ctx *c, const nttb200_u64 **psi, const nttb200_u64 **psiinv)
+{
+    if (!c) return NTTB200_EINVAL;
+    if (psi) *psi = c->psi;
+    if (psiinv) *psiinv = c->psiinv;
+    return 0;
+}
+int nttb200_ctx_consts(const nttb200_ctx *c, const nttb200_u64 **q, const nttb200_u64 **mu, const unsigned **qbit)
+{
+    if (!c) return NTTB200_EINVAL;
+    if (q) *q = c->q_dev;
+    if (mu) *mu = c->mu_dev;
+    if (qbit) *qbit = c->qbit_dev;
+    return 0;
+}
+int nttb200_download(void *dst_host, const void *src_dev, size_t bytes)
+{
+    NTTB200_CHECK(cudaMemcpy(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int nttb200_upload(void *dst_dev, const void *src_host, size_t bytes)
+{
+    NTTB200_CHECK(cudaMemcpy(dst_dev, src_host, bytes, cudaMemcpyHostToDevice));
+    return 0;
+}
+int nttb200_ctx_set_tma(nttb200_ctx *c, int enable)
+{
+    if (!c) return NTTB200_EINVAL;
+    c->use_tma = enable ? 1 : 0;
+    return 0;
+}
+
+// ---- host-buffer transforms: H2D / kernels / D2H of successive chunks overlap on kStages streams ------------------
+static int host_pipeline(nttb200_ctx *c, bool inverse, const u64 *in, u64 *out, unsigned num, unsigned division)
+{
+    if (!c || !in || !out || division == 0 || division > c->limbs) return NTTB200_EINVAL;
+    if (num == 0) return 0;
+    // chunk = a multiple of `division` polynomials, about 16 MiB
+    size_t per = ((size_t)16 << 20) / ((size_t)c->n * 8);
+    per = per / division * division;
+    if (per == 0) per = division;
+    const size_t bytes = per * c->n * 8;
+    if (c->stage_bytes < bytes) {
+        for (int i = 0; i < nttb200_ctx::kStages; i++) {
+            if (c->stage_dev[i]) { cudaFree(c->stage_dev[i]); c->stage_dev[i] = nullptr; }
+            NTTB200_CHECK(cudaMalloc(&c->stage_dev[i], bytes));
+            if (!c->streams[i]) NTTB200_CHECK(cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking));
+        }
+        c->stage_bytes = bytes;
+    }
+    int k = 0;
+    for (size_t p0 = 0; p0 < num; p0 += per, k = (k + 1) % nttb200_ctx::kStages) {
+        const unsigned cnt = (unsigned)((num - p0) < per ? (num - p0) : per);
+        cudaStream_t st = c->streams[k];
+        u64 *d = c->stage_dev[k];
+        NTTB200_CHECK(cudaMemcpyAsync(d, in + p0 * c->n, (size_t)cnt * c->n * 8, cudaMemcpyHostToDevice, st));
+        int r = inverse ? nttb200_inverse_ntt_batch(c, d, cnt, division, st) : nttb200_forward_ntt_batch(c, d, cnt, division, st);
+        if (r) return r;
+        NTTB200_CHECK(cudaMemcpyAsync(out + p0 * c->n, d, (size_t)cnt * c->n * 8, cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < nttb200_ctx::kStages; i++) NTTB200_CHECK(cudaStreamSynchronize(c->streams[i]));
+    return 0;
+}
+
+int nttb200_forward_ntt_batch_host(nttb200_ctx *c, const nttb200_u64 *in, nttb200_u64 *out, unsigned num, unsigned division)
+{
+    return host_pipeline(c, false, in, out, num, division);
+}
+int nttb200_inverse_ntt_batch_host(nttb200_ctx *c, const nttb200_u64 *in, nttb200_u64 *out, unsigned num, unsigned division)
+{
+    return host_pipeline(c, true, in, out, num, division);
+}
+
+}  // extern "C"

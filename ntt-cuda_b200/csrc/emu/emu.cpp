@@ -1,0 +1,102 @@
+// emu.cpp -- CPU execution of the CUDA kernel sources (compiled with -DNTTB200_EMU).  TEST INFRASTRUCTURE.
+#include "emu_rt.h"
+
+#include "../ntt_kernels.cuh"
+
+thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
+thread_local unsigned char *emu_dyn_smem = nullptr;
+thread_local EmuCta *emu_cta = nullptr;
+
+void __syncthreads() { emu_cta->block_bar->arrive_and_wait(); }
+void __syncwarp() { emu_cta->warp_bars[threadIdx.x / 32]->arrive_and_wait(); }
+
+float emu_normcdfinvf(float x)
+{
+    // Beasley-Springer-Moro style via bisection on erfc: slow but only used on tiny emulator inputs
+    double lo = -40, hi = 40;
+    for (int i = 0; i < 200; i++) {
+        double mid = 0.5 * (lo + hi);
+        if (0.5 * std::erfc(-mid / std::sqrt(2.0)) < (double)x) lo = mid; else hi = mid;
+    }
+    return (float)(0.5 * (lo + hi));
+}
+
+// ---- functional TMA model ------------------------------------------------------------------------------------------
+static void emu_tma(bool load, const TensorMap *m, void *smem, const int *c)
+{
+    const EmuTmapDesc *d = reinterpret_cast<const EmuTmapDesc *>(m->opaque);
+    const size_t es = d->strides[0];
+    uint32_t b0 = d->box[0], b1 = d->rank > 1 ? d->box[1] : 1, b2 = d->rank > 2 ? d->box[2] : 1;
+    unsigned char *s = (unsigned char *)smem;
+    if (d->swizzle128 && ((uintptr_t)s & 1023)) abort();   // hardware requirement
+    size_t lin = 0;
+    for (uint32_t k = 0; k < b2; k++)
+        for (uint32_t j = 0; j < b1; j++)
+            for (uint32_t i = 0; i < b0; i++, lin += es) {
+                size_t goff = (size_t)(c[0] + i) * d->strides[0];
+                if (d->rank > 1) goff += (size_t)(c[1] + j) * d->strides[1];
+                if (d->rank > 2) goff += (size_t)(c[2] + k) * d->strides[2];
+                size_t soff = lin;
+                if (d->swizzle128) soff ^= ((soff >> 7) & 7) << 4;
+                if (load) memcpy(s + soff, d->base + goff, es); else memcpy(d->base + goff, s + soff, es);
+            }
+}
+void emu_tma_2d(bool load, const TensorMap *m, void *smem, int c0, int c1) { int c[3] = {c0, c1, 0}; emu_tma(load, m, smem, c); }
+void emu_tma_3d(bool load, const TensorMap *m, void *smem, int c0, int c1, int c2) { int c[3] = {c0, c1, c2}; emu_tma(load, m, smem, c); }
+
+using namespace nttb200;
+
+template <class P, int LOGN, bool INV>
+static void run_one(const NttArgs &A)
+{
+    using SC = Sched<LOGN>;
+    constexpr int R = 1 << SC::K1;
+    const size_t n = (size_t)1 << LOGN;
+    TensorMap ms, mc;
+    EmuTmapDesc ds{}, dc{};
+    ds.base = (unsigned char *)A.a; ds.rank = 3;
+    ds.dims[0] = n >> SC::K1; ds.dims[1] = R; ds.dims[2] = A.num;
+    ds.strides[0] = 8; ds.strides[1] = (n >> SC::K1) * 8; ds.strides[2] = n * 8;
+    ds.box[0] = 16; ds.box[1] = R > 256 ? 256 : R; ds.box[2] = 1; ds.swizzle128 = 0;
+    dc.base = (unsigned char *)A.a; dc.rank = 2;
+    dc.dims[0] = 16; dc.dims[1] = ((size_t)A.num << LOGN) >> 4;
+    dc.strides[0] = 8; dc.strides[1] = 128;
+    dc.box[0] = 16; dc.box[1] = kContigRows; dc.swizzle128 = 1;
+    memcpy(ms.opaque, &ds, sizeof ds);
+    memcpy(mc.opaque, &dc, sizeof dc);
+    emu_dim3 gs, gc;
+    gs.x = (unsigned)(((n >> SC::K1) >> 4) / SC::NT); gs.y = A.num;
+    gc.x = (unsigned)((((size_t)A.num << LOGN) >> 4) / kContigRows);
+    const size_t smem_s = (size_t)SC::NT * R * 128 + 1024 + 16, smem_c = (size_t)kContigRows * 128 + 1024 + 16;
+    auto strided = [&] { emu_launch(gs, R * SC::NT, smem_s, [&] { ntt_strided_pass<P, LOGN, INV>(ms, A); }); };
+    auto contig = [&] { emu_launch(gc, kContigRows, smem_c, [&] { ntt_contig_pass<P, LOGN, INV>(mc, A); }); };
+    if (!INV) { strided(); contig(); } else { contig(); strided(); }
+}
+
+template <class P, bool INV>
+static int run_logn(int logn, const NttArgs &A)
+{
+    switch (logn) {
+    case 11: run_one<P, 11, INV>(A); return 0;
+    case 12: run_one<P, 12, INV>(A); return 0;
+    case 13: run_one<P, 13, INV>(A); return 0;
+    case 14: run_one<P, 14, INV>(A); return 0;
+    case 15: run_one<P, 15, INV>(A); return 0;
+    case 16: run_one<P, 16, INV>(A); return 0;
+    case 17: run_one<P, 17, INV>(A); return 0;
+    }
+    return 1;
+}
+
+extern "C" __attribute__((visibility("default")))
+int emu_ntt(int inverse, int barrett, int use_tma, int logn, u64 *a, const u64 *tw, const u64 *tws, const LimbConst *lc,
+            const u64 *qv, const u64 *muv, const u32 *qbitv, unsigned num, unsigned division)
+{
+    NttArgs A{};
+    A.a = a; A.tw = tw; A.tws = tws; A.lc = lc; A.qv = qv; A.muv = muv; A.qbitv = qbitv;
+    A.num = num; A.division = division; A.use_tma = (u32)use_tma;
+    if (!barrett) return inverse ? run_logn<ShoupPolicy, true>(logn, A) : run_logn<ShoupPolicy, false>(logn, A);
+    return inverse ? run_logn<BarrettPolicy, true>(logn, A) : run_logn<BarrettPolicy, false>(logn, A);
+}
+
+extern "C" __attribute__((visibility("default"))) unsigned emu_sizeof_limbconst() { return (unsigned)sizeof(LimbConst); }

@@ -1,0 +1,55 @@
+// internal.h -- host-side structures shared by the translation units of libnttb200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <vector>
+
+#include "../../include/nttb200.h"
+#include "modarith.cuh"
+
+#define NTTB200_CHECK(expr)                          \
+    do {                                             \
+        cudaError_t e__ = (expr);                    \
+        if (e__ != cudaSuccess) return (int)e__;     \
+    } while (0)
+
+struct nttb200_ctx {
+    unsigned n = 0, logn = 0, limbs = 0;
+    int device = 0;
+    int use_tma = 1;
+    // reference-layout tables [limbs][n] and Shoup companions, device
+    u64 *psi = nullptr, *psiinv = nullptr, *psi_s = nullptr, *psiinv_s = nullptr;
+    nttb200::LimbConst *lc = nullptr;      // [limbs] device
+    u64 *q_dev = nullptr, *mu_dev = nullptr;   // [limbs] device (reference-style constant arrays)
+    unsigned *qbit_dev = nullptr;
+    std::vector<u64> q, mu;
+    std::vector<unsigned> qbit;
+    // host-buffer (e2e) pipeline resources, created lazily
+    static constexpr int kStages = 3;
+    cudaStream_t streams[kStages] = {nullptr, nullptr, nullptr};
+    u64 *stage_dev[kStages] = {nullptr, nullptr, nullptr};
+    size_t stage_bytes = 0;
+};
+
+namespace nttb200 {
+
+// dir: 0 = forward, 1 = inverse.  policy: 0 = Shoup (ctx tables), 1 = Barrett (reference constants).
+struct NttArgsHost;
+int launch_ntt(bool inverse, bool barrett, unsigned logn, const NttArgsHost &h, cudaStream_t stream);
+int launch_ntt_pass(bool inverse, bool barrett, unsigned logn, const NttArgsHost &h, int which, cudaStream_t stream);
+
+struct NttArgsHost {
+    u64 *a;
+    const u64 *tw, *tws;
+    const LimbConst *lc;
+    const u64 *qv, *muv;
+    const unsigned *qbitv;
+    u64 q, mu;
+    unsigned qbit;
+    unsigned num, division;
+    int use_tma;
+};
+
+int get_tma_default();
+
+}  // namespace nttb200

@@ -1,0 +1,73 @@
+// modarith.cuh -- 64-bit modular arithmetic for the B200 integer pipe.
+//
+// Replaces the reference's device arithmetic layer: uint128.h:343-373 (mul64 = 9 x 32-bit mul/mad with
+// carries, sub128) and ntt_60bit.cuh:44-61 (singleBarrett on the emulated 128-bit type).  Here a
+// 64x64 product is `mul.lo.u64` + `mul.hi.u64` (IMAD.WIDE.U32 chains), and the NTT butterflies use
+// Shoup/Harvey lazy multiplication by a precomputed twiddle companion (1 mul.hi + 2 mul.lo).
+//
+// Two arithmetic flavours are provided:
+//   * shoup_mul / lazy [0,4q) butterflies   -- the fast path (context owns companion tables)
+//   * barrett_ref                           -- bit-for-bit the reference's Barrett sequence, for the
+//                                              pointwise kernels and the stateless drop-in NTT path
+#pragma once
+#include "compat.cuh"
+
+namespace nttb200 {
+
+// Per-limb constants kept in device global memory by a context (see nttb200.cu: build_limb_consts).
+struct LimbConst {
+    u64 q;          // modulus (< 2^62)
+    u64 twoq;       // 2q
+    u64 mu;         // floor(2^(2*qbit) / q)            (demo.cu:157-165)
+    u64 ninv;       // n^-1 mod q
+    u64 ninv_s;     // floor(ninv * 2^64 / q)
+    u64 w1ninv;     // psiinv[1] * n^-1 mod q           (last inverse stage with the scaling folded in)
+    u64 w1ninv_s;   // its Shoup companion
+    u32 qbit;       // floor(log2 q) + 1                (demo.cu:69)
+    u32 pad;
+};
+
+// high 64 bits of the 128-bit product (mul.hi.u64 on the device)
+__host__ __device__ __forceinline__ u64 mulhi64(u64 a, u64 b)
+{
+#if defined(__CUDA_ARCH__)
+    return __umul64hi(a, b);
+#else
+    return (u64)(((unsigned __int128)a * b) >> 64);
+#endif
+}
+
+// x in [0, 2m) -> [0, m)
+__host__ __device__ __forceinline__ u64 csub(u64 x, u64 m) { return x >= m ? x - m : x; }
+
+// Shoup multiplication: y arbitrary 64-bit, w < q, ws = floor(w * 2^64 / q).  Result in [0, 2q).
+__host__ __device__ __forceinline__ u64 shoup_mul(u64 y, u64 w, u64 ws, u64 q)
+{
+    u64 qhat = mulhi64(y, ws);
+    return y * w - qhat * q;
+}
+
+// low 64 bits of ((hi:lo) >> s), 0 <= s <= 64
+__host__ __device__ __forceinline__ u64 shr128_lo(u64 hi, u64 lo, int s)
+{
+    if (s <= 0) return lo;
+    if (s >= 64) return s >= 128 ? 0 : hi >> (s - 64);
+    return (lo >> s) | (hi << (64 - s));
+}
+
+// The reference's Barrett reduction of the 128-bit product a*b, operation for operation
+// (ntt_60bit.cuh:44-61; same sequence inlined at poly_arithmetic.cuh:16-33).  Canonical for a*b < 2^(2*qbit).
+__host__ __device__ __forceinline__ u64 barrett_ref(u64 a, u64 b, u64 q, u64 mu, int qbit)
+{
+    u64 lo = a * b, hi = mulhi64(a, b);
+    u64 x1 = shr128_lo(hi, lo, qbit - 2);
+    u64 plo = x1 * mu, phi = mulhi64(x1, mu);
+    u64 x2 = shr128_lo(phi, plo, qbit + 2);
+    u64 r = lo - x2 * q;
+    return r >= q ? r - q : r;
+}
+
+// (x * 2^-1) mod q for canonical x, as the reference does after every inverse stage (ntt_60bit.cuh:165, 494-513)
+__host__ __device__ __forceinline__ u64 half_mod(u64 x, u64 q2) { return (x >> 1) + (q2 & (0 - (x & 1))); }
+
+}  // namespace nttb200

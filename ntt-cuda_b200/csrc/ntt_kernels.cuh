@@ -1,0 +1,440 @@
+// ntt_kernels.cuh -- batched negacyclic NTT / INTT for sm_100a in TWO HBM passes.
+//
+// Replaces ntt_60bit.cuh:63-265, 388-606 (CTBasedNTTInner[Single][_batch], GSBasedINTTInner[Single][_batch]:
+// one butterfly per thread per stage, 4-5 HBM passes at n = 32768) and the launch schedules :267-386, 608-697.
+// Same transform, same tables, same layout: natural-order in -> bit-reversed out (forward), the mirror for the
+// inverse, stage `length = m` uses table entries [m, 2m)  (psi^bitrev(i), parameter.h:5-12).
+//
+// Structure (forward; the inverse runs the same two kernels mirrored):
+//   pass 1  "strided"  : the first K1 stages.  View the polynomial as [R = 2^K1 rows][n/R cols]; stage j pairs
+//                        rows that differ in bit K1-1-j and all columns share the twiddle, so a CTA takes a
+//                        [R][16]-column tile (128-byte rows, fetched by ONE 3-D TMA box), and every thread keeps
+//                        16 coefficients in registers for 3-4 stages at a time (radix-16 / radix-8x2 rounds),
+//                        exchanging through shared memory between rounds.
+//   pass 2  "contig"   : the last K2 = 7|8 stages on contiguous 2^K2-element blocks.  A CTA takes 128 rows of
+//                        16 coefficients (2-D TMA box, 128-byte swizzle); a block is owned by 8|16 lanes of ONE
+//                        warp, so the only synchronisation between its two register rounds is __syncwarp().
+// Butterflies are Harvey lazy butterflies in [0,4q) (forward) / [0,2q) (inverse) on Shoup twiddle companions
+// (1 mul.hi.u64 + 2 mul.lo.u64 per modular multiplication); the n^-1 scaling of the inverse is folded into its
+// last stage instead of one halving per stage (ntt_60bit.cuh:165,175) -- all results are canonical residues,
+// hence bit-identical to the reference's.
+#pragma once
+#include "modarith.cuh"
+#include "tile_io.cuh"
+
+#ifdef NTTB200_EMU
+struct TensorMap { unsigned char opaque[128]; };
+void emu_tma_2d(bool load, const TensorMap *m, void *smem, int c0, int c1);
+void emu_tma_3d(bool load, const TensorMap *m, void *smem, int c0, int c1, int c2);
+#else
+#include <cuda.h>
+typedef CUtensorMap TensorMap;
+#endif
+
+namespace nttb200 {
+
+struct NttArgs {
+    u64 *a;               // [num][n] coefficients, in place
+    const u64 *tw;        // psi (forward) / psiinv (inverse) tables, [limbs][n]
+    const u64 *tws;       // Shoup companions floor(tw * 2^64 / q), [limbs][n]        (ShoupPolicy)
+    const LimbConst *lc;  // [limbs]                                                  (ShoupPolicy)
+    const u64 *qv;        // BarrettPolicy: device arrays q / mu / qbit per limb (the reference's q_cons,
+    const u64 *muv;       //   mu_cons, q_bit_cons symbols, ntt_60bit.cuh:8-10) or NULL -> scalars below
+    const u32 *qbitv;
+    u64 q, mu;
+    u32 qbit;
+    u32 num, division;    // poly p uses limb p % division  (ntt_60bit.cuh:391)
+    u32 use_tma;
+};
+
+// ---- stage split per ring degree: K1 = S1+S2+S3 strided stages (rounds of 3 or 4), K2 contiguous stages -------
+template <int LOGN> struct Sched;
+#define NTTB200_SCHED(L, s1, s2, s3, k2, nt)                                             \
+    template <> struct Sched<L> {                                                        \
+        static constexpr int S1 = s1, S2 = s2, S3 = s3, K1 = s1 + s2 + s3, K2 = k2;      \
+        static constexpr int NT = nt; /* 16-column tiles per CTA in the strided pass */  \
+        static_assert(K1 + K2 == L, "bad split");                                        \
+    };
+NTTB200_SCHED(11, 4, 0, 0, 7, 8)
+NTTB200_SCHED(12, 4, 0, 0, 8, 8)
+NTTB200_SCHED(13, 3, 3, 0, 7, 2)
+NTTB200_SCHED(14, 4, 3, 0, 7, 1)
+NTTB200_SCHED(15, 4, 4, 0, 7, 1)
+NTTB200_SCHED(16, 4, 4, 0, 8, 1)
+NTTB200_SCHED(17, 3, 3, 3, 8, 1)
+#undef NTTB200_SCHED
+
+constexpr int kContigRows = 128;  // rows (of 16 coefficients) per CTA in the contiguous pass
+
+// ---- arithmetic policies ------------------------------------------------------------------------------------
+struct ShoupPolicy {
+    u64 q, twoq;
+    const u64 *w, *ws;
+    const LimbConst *l;
+    struct Tw { u64 w, ws; };
+    __device__ __forceinline__ void init(const NttArgs &A, u32 limb, u32 n)
+    {
+        l = A.lc + limb;
+        q = l->q; twoq = l->twoq;
+        w = A.tw + (size_t)limb * n; ws = A.tws + (size_t)limb * n;
+    }
+    __device__ __forceinline__ Tw load(u32 i) const { Tw t; t.w = __ldg(w + i); t.ws = __ldg(ws + i); return t; }
+    __device__ __forceinline__ void load2(u32 i, Tw &t0, Tw &t1) const
+    {
+        ulonglong2 a = __ldg(reinterpret_cast<const ulonglong2 *>(w + i));
+        ulonglong2 b = __ldg(reinterpret_cast<const ulonglong2 *>(ws + i));
+        t0.w = a.x; t1.w = a.y; t0.ws = b.x; t1.ws = b.y;
+    }
+    // forward (Cooley-Tukey), X,Y in [0,4q) -> [0,4q)
+    __device__ __forceinline__ void ct(u64 &X, u64 &Y, const Tw &t) const
+    {
+        u64 x = csub(X, twoq);
+        u64 T = shoup_mul(Y, t.w, t.ws, q);
+        X = x + T;
+        Y = x - T + twoq;
+    }
+    __device__ __forceinline__ u64 fwd_final(u64 x) const { return csub(csub(x, twoq), q); }
+    // inverse (Gentleman-Sande), U,V in [0,2q) -> [0,2q)
+    __device__ __forceinline__ void gs(u64 &U, u64 &V, const Tw &t) const
+    {
+        u64 s = U + V, d = U - V + twoq;
+        U = csub(s, twoq);
+        V = shoup_mul(d, t.w, t.ws, q);
+    }
+    // last inverse stage (length = 1) with n^-1 folded in; canonical outputs
+    __device__ __forceinline__ void gs_last(u64 &U, u64 &V) const
+    {
+        u64 s = U + V, d = U - V + twoq;
+        U = csub(shoup_mul(s, l->ninv, l->ninv_s, q), q);
+        V = csub(shoup_mul(d, l->w1ninv, l->w1ninv_s, q), q);
+    }
+};
+
+// The reference's own arithmetic, operation for operation (ntt_60bit.cuh:424-440 forward, :494-513 inverse):
+// canonical values, Barrett with the driver's (q, mu, qbit), one halving per inverse stage.  Needs nothing but
+// the reference's tables and constants, so the header drop-in can call it statelessly.
+struct BarrettPolicy {
+    u64 q, mu, q2;
+    int qbit;
+    const u64 *w;
+    struct Tw { u64 w; };
+    __device__ __forceinline__ void init(const NttArgs &A, u32 limb, u32 n)
+    {
+        if (A.qv) { q = __ldg(A.qv + limb); mu = __ldg(A.muv + limb); qbit = (int)__ldg(A.qbitv + limb); }
+        else { q = A.q; mu = A.mu; qbit = (int)A.qbit; }
+        q2 = (q + 1) >> 1;
+        w = A.tw + (size_t)limb * n;
+    }
+    __device__ __forceinline__ Tw load(u32 i) const { Tw t; t.w = __ldg(w + i); return t; }
+    __device__ __forceinline__ void load2(u32 i, Tw &t0, Tw &t1) const
+    {
+        ulonglong2 a = __ldg(reinterpret_cast<const ulonglong2 *>(w + i));
+        t0.w = a.x; t1.w = a.y;
+    }
+    __device__ __forceinline__ void ct(u64 &X, u64 &Y, const Tw &t) const
+    {
+        u64 u = X;
+        u64 v = barrett_ref(Y, t.w, q, mu, qbit);
+        u64 s = u + v;
+        s -= q * (u64)(s >= q);
+        X = s;
+        u += q * (u64)(u < v);
+        Y = u - v;
+    }
+    __device__ __forceinline__ u64 fwd_final(u64 x) const { return x; }
+    __device__ __forceinline__ void gs(u64 &U, u64 &V, const Tw &t) const
+    {
+        u64 u = U, v = V;
+        u64 s = u + v;
+        s -= q * (u64)(s >= q);
+        U = (s >> 1) + q2 * (s & 1);
+        u += q * (u64)(u < v);
+        u64 d = barrett_ref(u - v, t.w, q, mu, qbit);
+        V = (d >> 1) + q2 * (d & 1);
+    }
+    __device__ __forceinline__ void gs_last(u64 &U, u64 &V) const { gs(U, V, load(1)); }
+};
+
+// ---- S consecutive stages on 16 registers laid out [2^S rows][NC = 16 >> S cols] -------------------------------
+// Stage s of the round pairs rows i and i + 2^(S-1-s); block b = i >> (S-s) uses table entry (twbase << s) + b,
+// where twbase = m0 + g0 (m0 = `length` of the round's first stage, g0 = this thread's group index there).
+template <int S, int NC, int s, bool GS, bool LAST, class P>
+__device__ __forceinline__ void one_stage(u64 (&v)[16], u32 twbase, const P &pol)
+{
+    constexpr int half = 1 << (S - 1 - s);
+    const u32 base = twbase << s;
+    if constexpr (s == 0) {
+        if constexpr (GS && LAST) {
+            NTT_UNROLL
+            for (int k = 0; k < half; k++) {
+                NTT_UNROLL
+                for (int c = 0; c < NC; c++) pol.gs_last(v[k * NC + c], v[(k + half) * NC + c]);
+            }
+        } else {
+            typename P::Tw t = pol.load(base);
+            NTT_UNROLL
+            for (int k = 0; k < half; k++) {
+                NTT_UNROLL
+                for (int c = 0; c < NC; c++) {
+                    if constexpr (GS) pol.gs(v[k * NC + c], v[(k + half) * NC + c], t);
+                    else pol.ct(v[k * NC + c], v[(k + half) * NC + c], t);
+                }
+            }
+        }
+    } else {
+        NTT_UNROLL
+        for (int b = 0; b < (1 << s); b += 2) {
+            typename P::Tw t0, t1;
+            pol.load2(base + b, t0, t1);
+            NTT_UNROLL
+            for (int k = 0; k < half; k++) {
+                const int i = (b << (S - s)) + k, j = ((b + 1) << (S - s)) + k;
+                NTT_UNROLL
+                for (int c = 0; c < NC; c++) {
+                    if constexpr (GS) {
+                        pol.gs(v[i * NC + c], v[(i + half) * NC + c], t0);
+                        pol.gs(v[j * NC + c], v[(j + half) * NC + c], t1);
+                    } else {
+                        pol.ct(v[i * NC + c], v[(i + half) * NC + c], t0);
+                        pol.ct(v[j * NC + c], v[(j + half) * NC + c], t1);
+                    }
+                }
+            }
+        }
+    }
+}
+template <int S, int NC, int s, class P>
+__device__ __forceinline__ void ct_from(u64 (&v)[16], u32 twbase, const P &pol)
+{
+    if constexpr (s < S) {
+        one_stage<S, NC, s, false, false>(v, twbase, pol);
+        ct_from<S, NC, s + 1>(v, twbase, pol);
+    }
+}
+template <int S, int NC, int s, bool LAST, class P>
+__device__ __forceinline__ void gs_from(u64 (&v)[16], u32 twbase, const P &pol)
+{
+    if constexpr (s >= 0) {
+        one_stage<S, NC, s, true, LAST>(v, twbase, pol);
+        gs_from<S, NC, s - 1, LAST>(v, twbase, pol);
+    }
+}
+template <int S, int NC, class P>
+__device__ __forceinline__ void ct_stages(u64 (&v)[16], u32 twbase, const P &pol) { ct_from<S, NC, 0>(v, twbase, pol); }
+template <int S, int NC, bool LAST, class P>
+__device__ __forceinline__ void gs_stages(u64 (&v)[16], u32 twbase, const P &pol) { gs_from<S, NC, S - 1, LAST>(v, twbase, pol); }
+
+// ---- register <-> tile moves ----------------------------------------------------------------------------------
+// 2^S rows (rbase + (i << rsh)) x NC adjacent columns starting at col0
+template <int S, bool SWZ, bool LOAD>
+__device__ __forceinline__ void regs_rows(u64 *tile, u32 rbase, u32 rsh, u32 col0, u64 (&v)[16])
+{
+    constexpr int NC = 16 >> S;
+    static_assert(NC == 1 || NC == 2, "rounds are radix-16 (1 col) or radix-8 (2 cols)");
+    NTT_UNROLL
+    for (int i = 0; i < (1 << S); i++) {
+        const u32 row = rbase + ((u32)i << rsh);
+        if (NC == 1) {
+            u64 *p = tile + tile_off<SWZ>(row, col0);
+            if (LOAD) v[i] = *p; else *p = v[i];
+        } else {
+            ulonglong2 *p = reinterpret_cast<ulonglong2 *>(tile + tile_off<SWZ>(row, col0));
+            if (LOAD) { ulonglong2 t = *p; v[2 * i] = t.x; v[2 * i + 1] = t.y; }
+            else *p = make_ulonglong2(v[2 * i], v[2 * i + 1]);
+        }
+    }
+}
+// one whole row (16 contiguous coefficients)
+template <bool SWZ, bool LOAD>
+__device__ __forceinline__ void regs_row(u64 *tile, u32 row, u64 (&v)[16])
+{
+    NTT_UNROLL
+    for (int c = 0; c < 8; c++) {
+        ulonglong2 *p = reinterpret_cast<ulonglong2 *>(tile + tile_off<SWZ>(row, 2 * c));
+        if (LOAD) { ulonglong2 t = *p; v[2 * c] = t.x; v[2 * c + 1] = t.y; }
+        else *p = make_ulonglong2(v[2 * c], v[2 * c + 1]);
+    }
+}
+
+// One round of the strided pass: stages [J0, J0+S) of K1 on thread-in-tile index u in [0, 2^K1).
+template <class P, int K1, int J0, int S, bool INV>
+__device__ __forceinline__ void strided_round(u64 *tile, u32 u, const P &pol)
+{
+    constexpr int NC = 16 >> S;
+    constexpr int LOB = K1 - J0 - S;  // row bits below the round's bits
+    const u32 cg = u & ((1u << S) - 1u);
+    const u32 rest = u >> S;
+    const u32 lo = rest & ((1u << LOB) - 1u), hi = rest >> LOB;
+    const u32 rbase = (hi << (K1 - J0)) + lo;
+    u64 v[16];
+    regs_rows<S, false, true>(tile, rbase, LOB, cg * NC, v);
+    if (!INV) ct_stages<S, NC>(v, (1u << J0) + hi, pol);
+    else gs_stages<S, NC, J0 == 0>(v, (1u << J0) + hi, pol);
+    regs_rows<S, false, false>(tile, rbase, LOB, cg * NC, v);
+}
+
+// Dynamic shared memory is only guaranteed 16-byte aligned; the swizzled TMA image needs 1024.  The pad is added
+// to the __shared__ array itself so the compiler keeps the shared address space (LDS/STS, not generic LD/ST).
+__device__ __forceinline__ u64 *align_1024(unsigned char *p)
+{
+#ifdef NTTB200_EMU
+    return reinterpret_cast<u64 *>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023);
+#else
+    const u32 pad = (1024u - ((u32)__cvta_generic_to_shared(p) & 1023u)) & 1023u;
+    return reinterpret_cast<u64 *>(p + pad);
+#endif
+}
+
+// ---- pass "strided": grid (n / 2^K1 / 16 / NT, num), 2^K1 * NT threads ------------------------------------------
+template <class P, int LOGN, bool INV>
+__global__ void __launch_bounds__((1 << Sched<LOGN>::K1) * Sched<LOGN>::NT)
+ntt_strided_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
+{
+    using SC = Sched<LOGN>;
+    constexpr int K1 = SC::K1, R = 1 << K1, NT = SC::NT, THREADS = R * NT;
+    constexpr u32 n = 1u << LOGN, C = n >> K1;          // C columns per row
+    constexpr int RB = R > 256 ? 256 : R;               // TMA box rows (box dims are capped at 256)
+    NTT_DYN_SMEM(raw);
+    u64 *tiles = align_1024(raw);
+    u64 *bar = tiles + (size_t)NT * R * 16;
+    const u32 tid = threadIdx.x, p = blockIdx.y;
+    const u32 col0 = blockIdx.x * (NT * 16);
+    P pol;
+    pol.init(A, p % A.division, n);
+    u64 *g = A.a + (size_t)p * n + col0;
+
+    if (A.use_tma) {
+#ifdef NTTB200_EMU
+        if (tid == 0)
+            for (int k = 0; k < NT; k++)
+                for (int rc = 0; rc < R / RB; rc++)
+                    emu_tma_3d(true, &tmap, tiles + ((size_t)k * R + rc * RB) * 16, (int)col0 + k * 16, rc * RB, (int)p);
+        __syncthreads();
+#else
+        if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(bar, (u32)(NT * R * 128));
+            for (int k = 0; k < NT; k++)
+                for (int rc = 0; rc < R / RB; rc++)
+                    tma_load_3d(tiles + ((size_t)k * R + rc * RB) * 16, &tmap, bar, (int)col0 + k * 16, rc * RB, (int)p);
+        }
+        mbar_wait(bar, 0);
+#endif
+    } else {
+        for (int k = 0; k < NT; k++) tile_copy_coop<false, true>(tiles + (size_t)k * R * 16, g + k * 16, C, R, tid, THREADS);
+        __syncthreads();
+    }
+
+    u64 *tile = tiles + (size_t)(tid >> K1) * R * 16;
+    const u32 u = tid & (R - 1);
+    if (!INV) {
+        strided_round<P, K1, 0, SC::S1, false>(tile, u, pol);
+        if constexpr (SC::S2 != 0) { __syncthreads(); strided_round<P, K1, SC::S1, SC::S2, false>(tile, u, pol); }
+        if constexpr (SC::S3 != 0) { __syncthreads(); strided_round<P, K1, SC::S1 + SC::S2, SC::S3, false>(tile, u, pol); }
+    } else {
+        if constexpr (SC::S3 != 0) { strided_round<P, K1, SC::S1 + SC::S2, SC::S3, true>(tile, u, pol); __syncthreads(); }
+        if constexpr (SC::S2 != 0) { strided_round<P, K1, SC::S1, SC::S2, true>(tile, u, pol); __syncthreads(); }
+        strided_round<P, K1, 0, SC::S1, true>(tile, u, pol);
+    }
+
+    if (A.use_tma) {
+#ifdef NTTB200_EMU
+        __syncthreads();
+        if (tid == 0)
+            for (int k = 0; k < NT; k++)
+                for (int rc = 0; rc < R / RB; rc++)
+                    emu_tma_3d(false, &tmap, tiles + ((size_t)k * R + rc * RB) * 16, (int)col0 + k * 16, rc * RB, (int)p);
+#else
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            for (int k = 0; k < NT; k++)
+                for (int rc = 0; rc < R / RB; rc++)
+                    tma_store_3d(&tmap, tiles + ((size_t)k * R + rc * RB) * 16, (int)col0 + k * 16, rc * RB, (int)p);
+            tma_store_commit();
+            tma_store_wait_read();
+        }
+#endif
+    } else {
+        __syncthreads();
+        for (int k = 0; k < NT; k++) tile_copy_coop<false, false>(tiles + (size_t)k * R * 16, g + k * 16, C, R, tid, THREADS);
+    }
+    (void)bar;
+}
+
+// ---- pass "contig": grid (num * n / 16 / 128), 128 threads ------------------------------------------------------
+template <class P, int LOGN, bool INV>
+__global__ void __launch_bounds__(kContigRows)
+ntt_contig_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
+{
+    using SC = Sched<LOGN>;
+    constexpr int K1 = SC::K1, K2 = SC::K2, SA = K2 - 4, NC = 16 >> SA, RT = kContigRows;
+    constexpr u32 n = 1u << LOGN;
+    NTT_DYN_SMEM(raw);
+    u64 *tile = align_1024(raw);
+    u64 *bar = tile + (size_t)RT * 16;
+    const u32 tid = threadIdx.x;
+    const u32 row0 = blockIdx.x * RT;                    // flat row of 16 coefficients
+    const u32 p = row0 >> (LOGN - 4);
+    const u32 rip0 = row0 & ((n >> 4) - 1u);             // row inside the polynomial
+    P pol;
+    pol.init(A, p % A.division, n);
+    u64 *g = A.a + (size_t)row0 * 16;
+
+    if (A.use_tma) {
+#ifdef NTTB200_EMU
+        if (tid == 0) emu_tma_2d(true, &tmap, tile, 0, (int)row0);
+        __syncthreads();
+#else
+        if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+        __syncthreads();
+        if (tid == 0) { mbar_expect_tx(bar, (u32)(RT * 128)); tma_load_2d(tile, &tmap, bar, 0, (int)row0); }
+        mbar_wait(bar, 0);
+#endif
+    } else {
+        tile_copy_coop<true, true>(tile, g, 16, RT, tid, RT);
+        __syncthreads();
+    }
+
+    const u32 t = tid & ((1u << SA) - 1u), bl = tid >> SA;     // lane-in-block, block-in-tile
+    const u32 twA = (1u << K1) + (rip0 >> SA) + bl;            // block index inside the polynomial
+    const u32 twB = (n >> 4) + rip0 + tid;                     // row index inside the polynomial
+    u64 v[16];
+    if (!INV) {
+        regs_rows<SA, true, true>(tile, bl << SA, 0, t * NC, v);
+        ct_stages<SA, NC>(v, twA, pol);
+        regs_rows<SA, true, false>(tile, bl << SA, 0, t * NC, v);
+        __syncwarp();
+        regs_row<true, true>(tile, tid, v);
+        ct_stages<4, 1>(v, twB, pol);
+        NTT_UNROLL
+        for (int i = 0; i < 16; i++) v[i] = pol.fwd_final(v[i]);
+        regs_row<true, false>(tile, tid, v);
+    } else {
+        regs_row<true, true>(tile, tid, v);
+        gs_stages<4, 1, false>(v, twB, pol);
+        regs_row<true, false>(tile, tid, v);
+        __syncwarp();
+        regs_rows<SA, true, true>(tile, bl << SA, 0, t * NC, v);
+        gs_stages<SA, NC, false>(v, twA, pol);
+        regs_rows<SA, true, false>(tile, bl << SA, 0, t * NC, v);
+    }
+
+    if (A.use_tma) {
+#ifdef NTTB200_EMU
+        __syncthreads();
+        if (tid == 0) emu_tma_2d(false, &tmap, tile, 0, (int)row0);
+#else
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) { tma_store_2d(&tmap, tile, 0, (int)row0); tma_store_commit(); tma_store_wait_read(); }
+#endif
+    } else {
+        __syncthreads();
+        tile_copy_coop<true, false>(tile, g, 16, RT, tid, RT);
+    }
+    (void)bar;
+}
+
+}  // namespace nttb200

@@ -1,0 +1,207 @@
+// ntt_launch.cu -- kernel instantiations, TMA tensor maps and launch schedules for the NTT / INTT.
+// Replaces the host schedulers forwardNTT / inverseNTT / *_batch (ntt_60bit.cuh:267-386, 608-697): instead of
+// log2(n)-11 single-stage global passes plus one shared-memory pass, every size runs exactly two kernels.
+#include "internal.h"
+#include "ntt_kernels.cuh"
+
+#include <cstdlib>
+#include <mutex>
+
+namespace nttb200 {
+
+// ---- cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda link dependency) ------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode()
+{
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    });
+    return fn;
+}
+
+int get_tma_default()
+{
+    const char *e = getenv("NTTB200_NO_TMA");
+    return (e && e[0] == '1') ? 0 : 1;
+}
+
+// [num][R = 2^K1][C = n/R] u64, box [1][min(R,256)][16], no swizzle
+static int make_tmap_strided(CUtensorMap *m, u64 *a, unsigned logn, unsigned k1, unsigned num)
+{
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return NTTB200_ENOTMA;
+    const cuuint64_t n = 1ull << logn, R = 1ull << k1, C = n >> k1;
+    cuuint64_t dims[3] = {C, R, num};
+    cuuint64_t strides[2] = {C * 8, n * 8};
+    cuuint32_t box[3] = {16, (cuuint32_t)(R > 256 ? 256 : R), 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, a, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : NTTB200_ENOTMA;
+}
+// [rows = num*n/16][16] u64, box [128][16], 128-byte swizzle
+static int make_tmap_contig(CUtensorMap *m, u64 *a, unsigned logn, unsigned num)
+{
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return NTTB200_ENOTMA;
+    cuuint64_t dims[2] = {16, ((cuuint64_t)num << logn) >> 4};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {16, (cuuint32_t)kContigRows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, a, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : NTTB200_ENOTMA;
+}
+
+template <class P, int LOGN, bool INV>
+static int launch_one(const NttArgs &A, int which, unsigned cnt, const CUtensorMap &ms, const CUtensorMap &mc, cudaStream_t st)
+{
+    using SC = Sched<LOGN>;
+    constexpr int R = 1 << SC::K1;
+    constexpr size_t smem_s = (size_t)SC::NT * R * 128 + 1024 + 16;
+    constexpr size_t smem_c = (size_t)kContigRows * 128 + 1024 + 16;
+    static bool attr_done = false;   // per (P, LOGN, INV) instantiation
+    if (!attr_done) {
+        NTTB200_CHECK(cudaFuncSetAttribute(ntt_strided_pass<P, LOGN, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+        NTTB200_CHECK(cudaFuncSetAttribute(ntt_contig_pass<P, LOGN, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+        attr_done = true;
+    }
+    const dim3 gs((((1u << LOGN) >> SC::K1) >> 4) / SC::NT, cnt);
+    const dim3 gc((unsigned)(((size_t)cnt << LOGN) >> 4) / kContigRows);
+    // which: -1 = whole transform, 0 / 1 = only the first / second kernel in execution order (profiling hook)
+    const bool do_strided = which < 0 || (which == 0) == !INV;
+    const bool do_contig = which < 0 || (which == 1) == !INV;
+    if (!INV) {
+        if (do_strided) ntt_strided_pass<P, LOGN, INV><<<gs, R * SC::NT, smem_s, st>>>(ms, A);
+        if (do_contig) ntt_contig_pass<P, LOGN, INV><<<gc, kContigRows, smem_c, st>>>(mc, A);
+    } else {
+        if (do_contig) ntt_contig_pass<P, LOGN, INV><<<gc, kContigRows, smem_c, st>>>(mc, A);
+        if (do_strided) ntt_strided_pass<P, LOGN, INV><<<gs, R * SC::NT, smem_s, st>>>(ms, A);
+    }
+    return (int)cudaGetLastError();
+}
+
+template <class P, bool INV>
+static int launch_logn(unsigned logn, const NttArgs &A, int p0, unsigned cnt, const CUtensorMap &ms, const CUtensorMap &mc,
+                       cudaStream_t st)
+{
+    switch (logn) {
+    case 11: return launch_one<P, 11, INV>(A, p0, cnt, ms, mc, st);
+    case 12: return launch_one<P, 12, INV>(A, p0, cnt, ms, mc, st);
+    case 13: return launch_one<P, 13, INV>(A, p0, cnt, ms, mc, st);
+    case 14: return launch_one<P, 14, INV>(A, p0, cnt, ms, mc, st);
+    case 15: return launch_one<P, 15, INV>(A, p0, cnt, ms, mc, st);
+    case 16: return launch_one<P, 16, INV>(A, p0, cnt, ms, mc, st);
+    case 17: return launch_one<P, 17, INV>(A, p0, cnt, ms, mc, st);
+    default: return NTTB200_EINVAL;
+    }
+}
+
+static unsigned sched_k1(unsigned logn)
+{
+    switch (logn) {
+    case 11: return Sched<11>::K1; case 12: return Sched<12>::K1; case 13: return Sched<13>::K1; case 14: return Sched<14>::K1;
+    case 15: return Sched<15>::K1; case 16: return Sched<16>::K1; case 17: return Sched<17>::K1;
+    default: return 0;
+    }
+}
+
+int launch_ntt(bool inverse, bool barrett, unsigned logn, const NttArgsHost &h, cudaStream_t st) { return launch_ntt_pass(inverse, barrett, logn, h, -1, st); }
+
+int launch_ntt_pass(bool inverse, bool barrett, unsigned logn, const NttArgsHost &h, int which, cudaStream_t st)
+{
+    if (logn < 11 || logn > 17 || !h.a || !h.tw || h.division == 0) return NTTB200_EINVAL;
+    if (h.num == 0) return 0;
+    // gridDim.y caps one launch at 65535 polynomials; the limb phase (p % division) must be kept per chunk.
+    if (h.division > 65535u) return NTTB200_EINVAL;
+    const unsigned max_chunk = (65535u / h.division) * h.division;
+    for (unsigned p0 = 0; p0 < h.num; p0 += max_chunk) {
+        const unsigned cnt = (h.num - p0) < max_chunk ? (h.num - p0) : max_chunk;
+        NttArgs A;
+        A.a = h.a + ((size_t)p0 << logn);
+        A.tw = h.tw; A.tws = h.tws; A.lc = h.lc;
+        A.qv = h.qv; A.muv = h.muv; A.qbitv = h.qbitv;
+        A.q = h.q; A.mu = h.mu; A.qbit = h.qbit;
+        A.num = cnt; A.division = h.division; A.use_tma = (u32)h.use_tma;
+        CUtensorMap ms, mc;
+        if (h.use_tma) {
+            int r = make_tmap_strided(&ms, A.a, logn, sched_k1(logn), cnt);
+            if (r) return r;
+            r = make_tmap_contig(&mc, A.a, logn, cnt);
+            if (r) return r;
+        } else {
+            memset(&ms, 0, sizeof ms); memset(&mc, 0, sizeof mc);
+        }
+        int r;
+        if (!barrett) r = inverse ? launch_logn<ShoupPolicy, true>(logn, A, which, cnt, ms, mc, st) : launch_logn<ShoupPolicy, false>(logn, A, which, cnt, ms, mc, st);
+        else r = inverse ? launch_logn<BarrettPolicy, true>(logn, A, which, cnt, ms, mc, st) : launch_logn<BarrettPolicy, false>(logn, A, which, cnt, ms, mc, st);
+        if (r) return r;
+    }
+    return 0;
+}
+
+}  // namespace nttb200
+
+using namespace nttb200;
+
+static unsigned ilog2u(unsigned n) { unsigned l = 0; while ((1u << l) < n) l++; return l; }
+
+extern "C" {
+
+int nttb200_forward_ntt_batch(const nttb200_ctx *ctx, nttb200_u64 *a, unsigned num, unsigned division, void *stream)
+{
+    if (!ctx || division == 0 || division > ctx->limbs) return NTTB200_EINVAL;
+    NttArgsHost h{a, ctx->psi, ctx->psi_s, ctx->lc, nullptr, nullptr, nullptr, 0, 0, 0, num, division, ctx->use_tma};
+    return launch_ntt(false, false, ctx->logn, h, (cudaStream_t)stream);
+}
+int nttb200_inverse_ntt_batch(const nttb200_ctx *ctx, nttb200_u64 *a, unsigned num, unsigned division, void *stream)
+{
+    if (!ctx || division == 0 || division > ctx->limbs) return NTTB200_EINVAL;
+    NttArgsHost h{a, ctx->psiinv, ctx->psiinv_s, ctx->lc, nullptr, nullptr, nullptr, 0, 0, 0, num, division, ctx->use_tma};
+    return launch_ntt(true, false, ctx->logn, h, (cudaStream_t)stream);
+}
+
+int nttb200_ntt_pass(const nttb200_ctx *ctx, nttb200_u64 *a, unsigned num, unsigned division, int inverse, int which, void *stream)
+{
+    if (!ctx || division == 0 || division > ctx->limbs || which < 0 || which > 1) return NTTB200_EINVAL;
+    NttArgsHost h{a, inverse ? ctx->psiinv : ctx->psi, inverse ? ctx->psiinv_s : ctx->psi_s, ctx->lc, nullptr, nullptr, nullptr, 0, 0, 0,
+                  num, division, ctx->use_tma};
+    return launch_ntt_pass(inverse != 0, false, ctx->logn, h, which, (cudaStream_t)stream);
+}
+
+int nttb200_ref_forward_ntt_batch(nttb200_u64 *a, unsigned n, const nttb200_u64 *psi_powers, unsigned num, unsigned division,
+                                  const nttb200_u64 *q_dev, const nttb200_u64 *mu_dev, const unsigned *qbit_dev, void *stream)
+{
+    if (!q_dev || !mu_dev || !qbit_dev || (n & (n - 1))) return NTTB200_EINVAL;
+    NttArgsHost h{a, psi_powers, nullptr, nullptr, q_dev, mu_dev, qbit_dev, 0, 0, 0, num, division, get_tma_default()};
+    return launch_ntt(false, true, ilog2u(n), h, (cudaStream_t)stream);
+}
+int nttb200_ref_inverse_ntt_batch(nttb200_u64 *a, unsigned n, const nttb200_u64 *psiinv_powers, unsigned num, unsigned division,
+                                  const nttb200_u64 *q_dev, const nttb200_u64 *mu_dev, const unsigned *qbit_dev, void *stream)
+{
+    if (!q_dev || !mu_dev || !qbit_dev || (n & (n - 1))) return NTTB200_EINVAL;
+    NttArgsHost h{a, psiinv_powers, nullptr, nullptr, q_dev, mu_dev, qbit_dev, 0, 0, 0, num, division, get_tma_default()};
+    return launch_ntt(true, true, ilog2u(n), h, (cudaStream_t)stream);
+}
+int nttb200_ref_forward_ntt(nttb200_u64 *a, unsigned n, void *stream, nttb200_u64 q, nttb200_u64 mu, int qbit, const nttb200_u64 *psi_powers)
+{
+    if (n & (n - 1)) return NTTB200_EINVAL;
+    NttArgsHost h{a, psi_powers, nullptr, nullptr, nullptr, nullptr, nullptr, q, mu, (unsigned)qbit, 1, 1, get_tma_default()};
+    return launch_ntt(false, true, ilog2u(n), h, (cudaStream_t)stream);
+}
+int nttb200_ref_inverse_ntt(nttb200_u64 *a, unsigned n, void *stream, nttb200_u64 q, nttb200_u64 mu, int qbit, const nttb200_u64 *psiinv_powers)
+{
+    if (n & (n - 1)) return NTTB200_EINVAL;
+    NttArgsHost h{a, psiinv_powers, nullptr, nullptr, nullptr, nullptr, nullptr, q, mu, (unsigned)qbit, 1, 1, get_tma_default()};
+    return launch_ntt(true, true, ilog2u(n), h, (cudaStream_t)stream);
+}
+
+}  // extern "C"

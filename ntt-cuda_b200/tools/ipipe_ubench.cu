@@ -1,0 +1,92 @@
+// ipipe_ubench.cu -- measures the integer-pipe peaks the NTT roofline is quoted against (SURVEY.md 8d:
+// "integer-pipe peak is not in MEASURED_PEAKS.json -- measure it").  Prints one JSON object.
+// Each kernel runs ILP independent dependency chains per thread, 1024 threads x 2 CTAs per SM, and reports
+// thread-instructions per clock per SM from clock64() deltas (max over CTAs) and from wall time.
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+typedef unsigned long long u64;
+typedef unsigned int u32;
+#define ITERS 4096
+#define ILP 8
+
+template <int OP>
+__global__ void __launch_bounds__(1024) k(u64 *out, u32 a0, u32 b0, long long *cyc)
+{
+    u32 x[ILP], y[ILP];
+    u64 w[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; i++) { x[i] = a0 + threadIdx.x * 7 + i; y[i] = b0 + i * 3; w[i] = ((u64)x[i] << 32) | y[i]; }
+    long long t0 = clock64();
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int i = 0; i < ILP; i++) {
+            if (OP == 0) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(y[i]), "r"(b0));                 // IMAD
+            if (OP == 1) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(x[i]), "r"(y[i]));               // IMAD.WIDE.U32
+            if (OP == 2) asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(y[i]), "r"(b0));                 // IMAD.HI.U32
+            if (OP == 3) asm volatile("add.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(y[i]));                                  // IADD3
+            if (OP == 4) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(y[i]), "r"(b0));              // LOP3
+            if (OP == 5) asm volatile("mul.hi.u64 %0, %0, %1;" : "+l"(w[i]) : "l"(w[(i + 1) % ILP] | 1));              // mul.hi.u64
+            if (OP == 6) asm volatile("mul.lo.u64 %0, %0, %1;" : "+l"(w[i]) : "l"(w[(i + 1) % ILP] | 1));              // mul.lo.u64
+            if (OP == 7) { // Shoup modmul + Harvey CT butterfly on (w[i], w[i^1]) as compiled from C
+                u64 q = 0x7fffffd8001ull | ((u64)b0 << 40), tw = w[i] | 1, tws = w[(i + 3) % ILP];
+                u64 X = w[i], Y = w[(i + 1) % ILP];
+                u64 x2 = X >= 2 * q ? X - 2 * q : X;
+                u64 T = Y * tw - __umul64hi(Y, tws) * q;
+                w[i] = x2 + T; w[(i + 1) % ILP] = x2 - T + 2 * q;
+            }
+        }
+    }
+    long long t1 = clock64();
+    u64 acc = 0;
+#pragma unroll
+    for (int i = 0; i < ILP; i++) acc += x[i] + y[i] + w[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+    if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
+template <int OP>
+static void run(const char *name, int sms, int clk_khz, bool last)
+{
+    int blocks = sms * 2;
+    u64 *out; long long *cyc;
+    cudaMalloc(&out, (size_t)blocks * 1024 * 8);
+    cudaMalloc(&cyc, blocks * 8);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    k<OP><<<blocks, 1024>>>(out, 3, 5, cyc);
+    cudaDeviceSynchronize();
+    cudaEventRecord(e0);
+    k<OP><<<blocks, 1024>>>(out, 3, 5, cyc);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    long long *h = (long long *)malloc(blocks * 8);
+    cudaMemcpy(h, cyc, blocks * 8, cudaMemcpyDeviceToHost);
+    long long mx = 0; for (int i = 0; i < blocks; i++) if (h[i] > mx) mx = h[i];
+    double ops_per_sm = 2.0 * 1024 * ILP * (double)ITERS;      // thread-ops per SM (2 CTAs)
+    double per_clk = ops_per_sm / (double)mx;
+    double total_ops = ops_per_sm * sms;
+    printf("  \"%s\": {\"per_clk_per_sm\": %.2f, \"Gops_wall\": %.1f, \"ms\": %.4f, \"cycles\": %lld}%s\n", name, per_clk,
+           total_ops / (ms * 1e6), ms, mx, last ? "" : ",");
+    (void)clk_khz;
+    cudaFree(out); cudaFree(cyc); free(h);
+}
+
+int main()
+{
+    cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
+    int clk = 0; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
+    printf("{\n  \"device\": \"%s\", \"sms\": %d, \"clock_khz_attr\": %d,\n", p.name, p.multiProcessorCount, clk);
+    int s = p.multiProcessorCount;
+    run<0>("imad_lo32", s, clk, false);
+    run<1>("imad_wide_u32", s, clk, false);
+    run<2>("imad_hi_u32", s, clk, false);
+    run<3>("iadd3", s, clk, false);
+    run<4>("lop3", s, clk, false);
+    run<5>("mul_hi_u64", s, clk, false);
+    run<6>("mul_lo_u64", s, clk, false);
+    run<7>("shoup_ct_butterfly_c", s, clk, true);
+    printf("}\n");
+    return 0;
+}

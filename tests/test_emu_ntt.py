@@ -1,0 +1,74 @@
+"""Runs the *CUDA kernel sources* on the CPU (thread-per-CUDA-thread emulator, csrc/emu) and checks them bit-exactly
+against the oracle: index maths, round schedules, twiddle indexing, the 128-byte swizzle and both arithmetic
+policies are validated before any GPU time is spent.  (The PTX for TMA/mbarrier itself is only exercised on the GPU.)"""
+import numpy as np
+import pytest
+
+from nttb200 import params
+from tests import emu
+
+
+def _ring(oracle, logn, limbs):
+    n = 1 << logn
+    if n in params.GET_PARAMS and limbs == 1:
+        q, psi = params.GET_PARAMS[n][:2]
+        qs, roots = [q], [psi]
+    elif n == 32768:
+        _, qs, roots = params.RNS_SETS["32k_16q"]
+        qs, roots = qs[:limbs], roots[:limbs]
+    elif n == 8192:
+        _, qs, roots = params.RNS_SETS["8k_3q"]
+        qs, roots = qs[:limbs], roots[:limbs]
+    else:
+        qs, roots = params.find_ntt_primes(60, n, limbs)
+    tabs = [oracle.fill_psi_tables(r, q, n) for q, r in zip(qs, roots)]
+    psi = np.stack([t[0] for t in tabs])
+    psiinv = np.stack([t[1] for t in tabs])
+    return n, qs, psi, psiinv
+
+
+def _expect(oracle, a, n, qs, psi, psiinv, num, division, inverse):
+    out = a.copy().reshape(num, n)
+    for pidx in range(num):
+        l = pidx % division
+        out[pidx] = (oracle.inverse_ntt_fast(out[pidx], qs[l], psiinv[l]) if inverse
+                     else oracle.forward_ntt_fast(out[pidx], qs[l], psi[l]))
+    return out.reshape(-1)
+
+
+CASES = [
+    # logn, limbs(division), num, barrett, use_tma
+    (11, 1, 2, 0, 1), (11, 1, 1, 1, 0),
+    (12, 1, 2, 0, 0), (12, 1, 1, 1, 1),
+    (13, 3, 4, 0, 1), (13, 3, 3, 1, 0),
+    (14, 2, 2, 0, 0), (14, 1, 1, 1, 1),
+    (15, 3, 4, 0, 1), (15, 2, 2, 1, 1), (15, 1, 1, 0, 0),
+    (16, 2, 2, 0, 1), (16, 1, 1, 1, 0),
+    (17, 1, 1, 0, 1), (17, 1, 1, 1, 0),
+]
+
+
+@pytest.mark.parametrize("logn,limbs,num,barrett,use_tma", CASES)
+def test_emu_forward_inverse(oracle, logn, limbs, num, barrett, use_tma):
+    n, qs, psi, psiinv = _ring(oracle, logn, limbs)
+    a = np.concatenate([oracle.fill_uniform(n, qs[pidx % limbs], 0x5EED0000 + pidx) for pidx in range(num)])
+    # edge values: 0, 1, q-1 in the first polynomial
+    a[0], a[1], a[2] = 0, 1, qs[0] - 1
+    fwd = emu.ntt(a, n, qs, psi, psiinv, num, limbs, inverse=False, barrett=barrett, use_tma=use_tma)
+    assert np.array_equal(fwd, _expect(oracle, a, n, qs, psi, psiinv, num, limbs, False))
+    inv = emu.ntt(fwd, n, qs, psi, psiinv, num, limbs, inverse=True, barrett=barrett, use_tma=use_tma)
+    assert np.array_equal(inv, a)
+
+
+def test_emu_barrett_matches_reference_on_noncanonical_input(oracle):
+    """The stateless (Barrett) path is the reference's arithmetic operation for operation, so it must agree with
+    the oracle's literal restatement even for inputs >= q (e.g. the value q left behind by the `>` quirk)."""
+    n, qs, psi, psiinv = _ring(oracle, 11, 1)
+    q = qs[0]
+    a = oracle.fill_uniform(n, q, 99)
+    a[5] = q
+    a[17] = q + 3
+    got = emu.ntt(a, n, qs, psi, psiinv, 1, 1, inverse=False, barrett=1, use_tma=0)
+    assert np.array_equal(got, oracle.forward_ntt(a, q, psi[0]))
+    got = emu.ntt(a, n, qs, psi, psiinv, 1, 1, inverse=True, barrett=1, use_tma=0)
+    assert np.array_equal(got, oracle.inverse_ntt(a, q, psiinv[0]))

@@ -1,0 +1,140 @@
+"""GPU parity of the NTT / INTT through the C ABI (libnttb200.so) against the CPU oracle.  Bit-exact: integer work."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from nttb200 import params  # noqa: E402
+
+
+def _ring(oracle, logn, limbs):
+    n = 1 << logn
+    if n in params.GET_PARAMS and limbs == 1:
+        q, psi = params.GET_PARAMS[n][:2]
+        return n, [q], [psi]
+    for name in ("32k_16q", "16k_9q", "8k_4q", "4k_3q"):
+        nn, qs, roots = params.RNS_SETS[name]
+        if nn == n and limbs <= len(qs):
+            return n, qs[:limbs], roots[:limbs]
+    qs, roots = params.find_ntt_primes(60, n, limbs)
+    return n, qs, roots
+
+
+def _tables(oracle, n, qs, roots):
+    tabs = [oracle.fill_psi_tables(r, q, n) for q, r in zip(qs, roots)]
+    return np.stack([t[0] for t in tabs]), np.stack([t[1] for t in tabs])
+
+
+def _expect(oracle, a, n, qs, psi, psiinv, num, division, inverse):
+    out = a.copy().reshape(num, n)
+    for p in range(num):
+        l = p % division
+        out[p] = oracle.inverse_ntt_fast(out[p], qs[l], psiinv[l]) if inverse else oracle.forward_ntt_fast(out[p], qs[l], psi[l])
+    return out.reshape(-1)
+
+
+@pytest.mark.parametrize("tma", [1, 0])
+@pytest.mark.parametrize("logn,limbs,num", [(11, 1, 3), (12, 3, 5), (13, 1, 2), (14, 9, 11), (15, 16, 40), (16, 3, 4), (17, 2, 3)])
+def test_ctx_forward_inverse_vs_oracle(oracle, logn, limbs, num, tma):
+    import nttb200
+    from tests.gpu_util import to_dev, to_host
+    n, qs, roots = _ring(oracle, logn, limbs)
+    psi, psiinv = _tables(oracle, n, qs, roots)
+    ctx = nttb200.Context(n, qs, roots)
+    ctx.set_tma(bool(tma))
+    a = np.concatenate([oracle.fill_uniform(n, qs[p % limbs], 0x5EED0000 + p) for p in range(num)])
+    a[0], a[1], a[2] = 0, 1, qs[0] - 1
+    d = to_dev(a)
+    ctx.forward_ntt_batch(d, num, limbs)
+    fwd = to_host(d)
+    assert np.array_equal(fwd, _expect(oracle, a, n, qs, psi, psiinv, num, limbs, False))
+    ctx.inverse_ntt_batch(d, num, limbs)
+    assert np.array_equal(to_host(d), a)
+    ctx.close()
+
+
+def test_ctx_tables_match_reference_layout(oracle):
+    """Context tables generated on the library side == parameter.h:5-12 fillTablePsi128 (oracle restatement)."""
+    import nttb200
+    n, qs, roots = params.RNS_SETS["8k_3q"]
+    psi, psiinv = _tables(oracle, n, qs, roots)
+    ctx = nttb200.Context(n, qs, roots)
+    assert np.array_equal(nttb200.download(ctx.psi_table, 3 * n).reshape(3, n), psi)
+    assert np.array_equal(nttb200.download(ctx.psiinv_table, 3 * n).reshape(3, n), psiinv)
+    ctx.close()
+
+
+@pytest.mark.parametrize("logn,limbs,num", [(11, 1, 1), (12, 3, 6), (13, 3, 3), (15, 9, 18), (16, 2, 2)])
+def test_stateless_reference_contract_path(oracle, logn, limbs, num):
+    """forwardNTT_batch / inverseNTT_batch given nothing but the reference's tables and q/mu/qbit device arrays."""
+    import nttb200
+    from tests.gpu_util import to_dev, to_host
+    n, qs, roots = _ring(oracle, logn, limbs)
+    psi, psiinv = _tables(oracle, n, qs, roots)
+    qd = to_dev(np.array(qs, dtype=np.uint64))
+    mud = to_dev(np.array([oracle.mu(q) for q in qs], dtype=np.uint64))
+    qbd = to_dev(np.array([oracle.qbit(q) for q in qs], dtype=np.uint32))
+    psid, psiinvd = to_dev(psi.reshape(-1)), to_dev(psiinv.reshape(-1))
+    a = np.concatenate([oracle.fill_uniform(n, qs[p % limbs], 77 + p) for p in range(num)])
+    d = to_dev(a)
+    nttb200.forwardNTT_batch(d, n, psid, num, limbs, qd, mud, qbd)
+    assert np.array_equal(to_host(d), _expect(oracle, a, n, qs, psi, psiinv, num, limbs, False))
+    nttb200.inverseNTT_batch(d, n, psiinvd, num, limbs, qd, mud, qbd)
+    assert np.array_equal(to_host(d), a)
+    # single-polynomial API with explicit constants (forwardNTT / inverseNTT)
+    d1 = to_dev(a[:n])
+    nttb200.forwardNTT(d1, n, None, qs[0], oracle.mu(qs[0]), oracle.qbit(qs[0]), psid)
+    assert np.array_equal(to_host(d1), oracle.forward_ntt(a[:n], qs[0], psi[0]))
+    nttb200.inverseNTT(d1, n, None, qs[0], oracle.mu(qs[0]), oracle.qbit(qs[0]), psiinvd)
+    assert np.array_equal(to_host(d1), a[:n])
+
+
+def test_full_size_c2_properties(oracle):
+    """BASELINE config 2: 1024 polynomials, N = 2^15, 16 limbs.  Size-independent checks: INTT(NTT(a)) == a,
+    linearity NTT(a + b) == NTT(a) + NTT(b) (mod q), and a sample of polynomials against the oracle."""
+    import torch
+    import nttb200
+    from tests.gpu_util import to_dev, to_host
+    n, qs, roots = params.RNS_SETS["32k_16q"]
+    L, num = 16, 1024
+    ctx = nttb200.Context(n, qs, roots)
+    psi, psiinv = _tables(oracle, n, qs, roots)
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    qv = torch.tensor(qs, dtype=torch.int64, device="cuda").repeat(num // L).view(num, 1)
+    a = torch.randint(0, 2**62, (num, n), dtype=torch.int64, device="cuda", generator=g) % qv
+    b = torch.randint(0, 2**62, (num, n), dtype=torch.int64, device="cuda", generator=g) % qv
+    s = (a + b) % qv
+    fa, fb, fs = a.clone(), b.clone(), s.clone()
+    for t in (fa, fb, fs):
+        ctx.forward_ntt_batch(t, num, L)
+    assert torch.equal((fa + fb) % qv, fs)
+    for p in (0, 17, 1023):
+        assert np.array_equal(to_host(fa[p]), oracle.forward_ntt_fast(to_host(a[p]), qs[p % L], psi[p % L]))
+    ctx.inverse_ntt_batch(fa, num, L)
+    assert torch.equal(fa, a)
+    ctx.close()
+
+
+def test_host_buffer_entry_point(oracle):
+    import nttb200
+    n, qs, roots = params.RNS_SETS["8k_3q"]
+    psi, psiinv = _tables(oracle, n, qs, roots)
+    num = 300   # several pipeline chunks, not a multiple of the chunk size
+    ctx = nttb200.Context(n, qs, roots)
+    a = np.concatenate([oracle.fill_uniform(n, qs[p % 3], 5 + p) for p in range(num)])
+    out = np.empty_like(a)
+    ctx.forward_ntt_batch_host(a, out, num, 3)
+    for p in (0, 1, 149, 299):
+        assert np.array_equal(out[p * n:(p + 1) * n], oracle.forward_ntt_fast(a[p * n:(p + 1) * n], qs[p % 3], psi[p % 3]))
+    back = np.empty_like(a)
+    ctx.inverse_ntt_batch_host(out, back, num, 3)
+    assert np.array_equal(back, a)
+    ctx.close()
+
+
+def test_invalid_arguments_fail_loudly():
+    import nttb200
+    with pytest.raises(nttb200.NttB200Error):
+        nttb200.Context(1024, [12289], [7])          # n below 2^11
+    with pytest.raises(nttb200.NttB200Error):
+        nttb200.Context(2048, [137438691329], [5])   # not a primitive 2n-th root
