@@ -95,7 +95,8 @@ int emu_ntt(int inverse, int barrett, int use_tma, int logn, u64 *a, const u64 *
     NttArgs A{};
     A.a = a; A.tw = tw; A.tws = tws; A.lc = lc; A.qv = qv; A.muv = muv; A.qbitv = qbitv;
     A.num = num; A.division = division; A.use_tma = (u32)use_tma;
-    if (!barrett) return inverse ? run_logn<ShoupPolicy, true>(logn, A) : run_logn<ShoupPolicy, false>(logn, A);
+    if (barrett == 2 && !inverse) return run_logn<ShoupLazyPolicy, false>(logn, A);
+    if (barrett != 1) return inverse ? run_logn<ShoupPolicy, true>(logn, A) : run_logn<ShoupPolicy, false>(logn, A);
     return inverse ? run_logn<BarrettPolicy, true>(logn, A) : run_logn<BarrettPolicy, false>(logn, A);
 }
 

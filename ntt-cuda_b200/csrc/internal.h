@@ -17,6 +17,7 @@ struct nttb200_ctx {
     unsigned n = 0, logn = 0, limbs = 0;
     int device = 0;
     int use_tma = 1;
+    int lazy_ok = 1;      // every modulus < 2^58: the forward transform may run without intermediate corrections
     // reference-layout tables [limbs][n] and Shoup companions, device
     u64 *psi = nullptr, *psiinv = nullptr, *psi_s = nullptr, *psiinv_s = nullptr;
     nttb200::LimbConst *lc = nullptr;      // [limbs] device
@@ -35,8 +36,10 @@ namespace nttb200 {
 
 // dir: 0 = forward, 1 = inverse.  policy: 0 = Shoup (ctx tables), 1 = Barrett (reference constants).
 struct NttArgsHost;
-int launch_ntt(bool inverse, bool barrett, unsigned logn, const NttArgsHost &h, cudaStream_t stream);
-int launch_ntt_pass(bool inverse, bool barrett, unsigned logn, const NttArgsHost &h, int which, cudaStream_t stream);
+// policy: 0 = Shoup/Harvey (q < 2^62), 1 = reference Barrett (stateless), 2 = Shoup without intermediate corrections (q < 2^58)
+enum { kPolicyShoup = 0, kPolicyBarrett = 1, kPolicyShoupLazy = 2 };
+int launch_ntt(bool inverse, int policy, unsigned logn, const NttArgsHost &h, cudaStream_t stream);
+int launch_ntt_pass(bool inverse, int policy, unsigned logn, const NttArgsHost &h, int which, cudaStream_t stream);
 
 struct NttArgsHost {
     u64 *a;

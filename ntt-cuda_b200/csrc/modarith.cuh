@@ -23,6 +23,8 @@ struct LimbConst {
     u64 ninv_s;     // floor(ninv * 2^64 / q)
     u64 w1ninv;     // psiinv[1] * n^-1 mod q           (last inverse stage with the scaling folded in)
     u64 w1ninv_s;   // its Shoup companion
+    u64 ratio;      // floor(2^64 / q)                  (final reduction of the lazy forward transform)
+    u64 negq;       // 2^64 - q
     u32 qbit;       // floor(log2 q) + 1                (demo.cu:69)
     u32 pad;
 };
@@ -45,6 +47,42 @@ __host__ __device__ __forceinline__ u64 shoup_mul(u64 y, u64 w, u64 ws, u64 q)
 {
     u64 qhat = mulhi64(y, ws);
     return y * w - qhat * q;
+}
+
+// low 64 bits of a*b + c*d as ONE accumulation chain: 2 IMAD.WIDE.U32 + 4 IMAD and no carry/negate fix-ups
+// (nvcc's own code for `a*b - c*q` is 10 instructions: two separate 64-bit products, a negation and an add).
+__host__ __device__ __forceinline__ u64 mullo_sum2(u64 a, u64 b, u64 c, u64 d)
+{
+#if defined(__CUDA_ARCH__)
+    u64 r;
+    asm("{\n\t"
+        ".reg .u32 al, ah, bl, bh, cl, ch, dl, dh, rl, rh;\n\t"
+        ".reg .u64 acc;\n\t"
+        "mov.b64 {al, ah}, %1;\n\t"
+        "mov.b64 {bl, bh}, %2;\n\t"
+        "mov.b64 {cl, ch}, %3;\n\t"
+        "mov.b64 {dl, dh}, %4;\n\t"
+        "mul.wide.u32 acc, al, bl;\n\t"
+        "mad.wide.u32 acc, cl, dl, acc;\n\t"
+        "mov.b64 {rl, rh}, acc;\n\t"
+        "mad.lo.u32 rh, al, bh, rh;\n\t"
+        "mad.lo.u32 rh, ah, bl, rh;\n\t"
+        "mad.lo.u32 rh, cl, dh, rh;\n\t"
+        "mad.lo.u32 rh, ch, dl, rh;\n\t"
+        "mov.b64 %0, {rl, rh};\n\t"
+        "}"
+        : "=l"(r)
+        : "l"(a), "l"(b), "l"(c), "l"(d));
+    return r;
+#else
+    return a * b + c * d;
+#endif
+}
+
+// Shoup multiplication on the fused chain: negq = 2^64 - q.  Result in [0, 2q).
+__host__ __device__ __forceinline__ u64 shoup_mul_n(u64 y, u64 w, u64 ws, u64 negq)
+{
+    return mullo_sum2(y, w, mulhi64(y, ws), negq);
 }
 
 // low 64 bits of ((hi:lo) >> s), 0 <= s <= 64

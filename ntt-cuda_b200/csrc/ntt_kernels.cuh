@@ -68,14 +68,14 @@ constexpr int kContigRows = 128;  // rows (of 16 coefficients) per CTA in the co
 
 // ---- arithmetic policies ------------------------------------------------------------------------------------
 struct ShoupPolicy {
-    u64 q, twoq;
+    u64 q, twoq, nq;
     const u64 *w, *ws;
     const LimbConst *l;
     struct Tw { u64 w, ws; };
     __device__ __forceinline__ void init(const NttArgs &A, u32 limb, u32 n)
     {
         l = A.lc + limb;
-        q = l->q; twoq = l->twoq;
+        q = l->q; twoq = l->twoq; nq = l->negq;
         w = A.tw + (size_t)limb * n; ws = A.tws + (size_t)limb * n;
     }
     __device__ __forceinline__ Tw load(u32 i) const { Tw t; t.w = __ldg(w + i); t.ws = __ldg(ws + i); return t; }
@@ -89,7 +89,7 @@ struct ShoupPolicy {
     __device__ __forceinline__ void ct(u64 &X, u64 &Y, const Tw &t) const
     {
         u64 x = csub(X, twoq);
-        u64 T = shoup_mul(Y, t.w, t.ws, q);
+        u64 T = shoup_mul_n(Y, t.w, t.ws, nq);
         X = x + T;
         Y = x - T + twoq;
     }
@@ -99,14 +99,39 @@ struct ShoupPolicy {
     {
         u64 s = U + V, d = U - V + twoq;
         U = csub(s, twoq);
-        V = shoup_mul(d, t.w, t.ws, q);
+        V = shoup_mul_n(d, t.w, t.ws, nq);
     }
     // last inverse stage (length = 1) with n^-1 folded in; canonical outputs
     __device__ __forceinline__ void gs_last(u64 &U, u64 &V) const
     {
         u64 s = U + V, d = U - V + twoq;
-        U = csub(shoup_mul(s, l->ninv, l->ninv_s, q), q);
-        V = csub(shoup_mul(d, l->w1ninv, l->w1ninv_s, q), q);
+        U = csub(shoup_mul_n(s, l->ninv, l->ninv_s, nq), q);
+        V = csub(shoup_mul_n(d, l->w1ninv, l->w1ninv_s, nq), q);
+    }
+};
+
+// Forward transform for q < 2^58: no conditional subtraction at all inside the transform.  Every Shoup product is
+// < 2q whatever its input, so X' = X + T and Y' = X - T + 2q stay non-negative and grow by at most 2q per stage:
+// canonical inputs end below (2 log2(n) + 1) q <= 35 q < 2^64.  One Barrett-style reduction by floor(2^64/q) at the
+// very end brings the outputs to [0, q).  The inverse transform is ShoupPolicy's.
+struct ShoupLazyPolicy : ShoupPolicy {
+    u64 ratio;
+    __device__ __forceinline__ void init(const NttArgs &A, u32 limb, u32 n)
+    {
+        ShoupPolicy::init(A, limb, n);
+        ratio = l->ratio;
+    }
+    __device__ __forceinline__ void ct(u64 &X, u64 &Y, const Tw &t) const
+    {
+        u64 T = shoup_mul_n(Y, t.w, t.ws, nq);
+        u64 x = X;
+        X = x + T;
+        Y = x - T + twoq;
+    }
+    __device__ __forceinline__ u64 fwd_final(u64 x) const
+    {
+        u64 r = x + mulhi64(x, ratio) * nq;     // x - floor(x * ratio / 2^64) * q  in [0, 2q)
+        return csub(r, q);
     }
 };
 

@@ -114,9 +114,9 @@ static unsigned sched_k1(unsigned logn)
     }
 }
 
-int launch_ntt(bool inverse, bool barrett, unsigned logn, const NttArgsHost &h, cudaStream_t st) { return launch_ntt_pass(inverse, barrett, logn, h, -1, st); }
+int launch_ntt(bool inverse, int policy, unsigned logn, const NttArgsHost &h, cudaStream_t st) { return launch_ntt_pass(inverse, policy, logn, h, -1, st); }
 
-int launch_ntt_pass(bool inverse, bool barrett, unsigned logn, const NttArgsHost &h, int which, cudaStream_t st)
+int launch_ntt_pass(bool inverse, int policy, unsigned logn, const NttArgsHost &h, int which, cudaStream_t st)
 {
     if (logn < 11 || logn > 17 || !h.a || !h.tw || h.division == 0) return NTTB200_EINVAL;
     if (h.num == 0) return 0;
@@ -141,7 +141,8 @@ int launch_ntt_pass(bool inverse, bool barrett, unsigned logn, const NttArgsHost
             memset(&ms, 0, sizeof ms); memset(&mc, 0, sizeof mc);
         }
         int r;
-        if (!barrett) r = inverse ? launch_logn<ShoupPolicy, true>(logn, A, which, cnt, ms, mc, st) : launch_logn<ShoupPolicy, false>(logn, A, which, cnt, ms, mc, st);
+        if (policy == kPolicyShoupLazy && !inverse) r = launch_logn<ShoupLazyPolicy, false>(logn, A, which, cnt, ms, mc, st);
+        else if (policy != kPolicyBarrett) r = inverse ? launch_logn<ShoupPolicy, true>(logn, A, which, cnt, ms, mc, st) : launch_logn<ShoupPolicy, false>(logn, A, which, cnt, ms, mc, st);
         else r = inverse ? launch_logn<BarrettPolicy, true>(logn, A, which, cnt, ms, mc, st) : launch_logn<BarrettPolicy, false>(logn, A, which, cnt, ms, mc, st);
         if (r) return r;
     }
@@ -160,13 +161,13 @@ int nttb200_forward_ntt_batch(const nttb200_ctx *ctx, nttb200_u64 *a, unsigned n
 {
     if (!ctx || division == 0 || division > ctx->limbs) return NTTB200_EINVAL;
     NttArgsHost h{a, ctx->psi, ctx->psi_s, ctx->lc, nullptr, nullptr, nullptr, 0, 0, 0, num, division, ctx->use_tma};
-    return launch_ntt(false, false, ctx->logn, h, (cudaStream_t)stream);
+    return launch_ntt(false, ctx->lazy_ok ? kPolicyShoupLazy : kPolicyShoup, ctx->logn, h, (cudaStream_t)stream);
 }
 int nttb200_inverse_ntt_batch(const nttb200_ctx *ctx, nttb200_u64 *a, unsigned num, unsigned division, void *stream)
 {
     if (!ctx || division == 0 || division > ctx->limbs) return NTTB200_EINVAL;
     NttArgsHost h{a, ctx->psiinv, ctx->psiinv_s, ctx->lc, nullptr, nullptr, nullptr, 0, 0, 0, num, division, ctx->use_tma};
-    return launch_ntt(true, false, ctx->logn, h, (cudaStream_t)stream);
+    return launch_ntt(true, kPolicyShoup, ctx->logn, h, (cudaStream_t)stream);
 }
 
 int nttb200_ntt_pass(const nttb200_ctx *ctx, nttb200_u64 *a, unsigned num, unsigned division, int inverse, int which, void *stream)
@@ -174,7 +175,7 @@ int nttb200_ntt_pass(const nttb200_ctx *ctx, nttb200_u64 *a, unsigned num, unsig
     if (!ctx || division == 0 || division > ctx->limbs || which < 0 || which > 1) return NTTB200_EINVAL;
     NttArgsHost h{a, inverse ? ctx->psiinv : ctx->psi, inverse ? ctx->psiinv_s : ctx->psi_s, ctx->lc, nullptr, nullptr, nullptr, 0, 0, 0,
                   num, division, ctx->use_tma};
-    return launch_ntt_pass(inverse != 0, false, ctx->logn, h, which, (cudaStream_t)stream);
+    return launch_ntt_pass(inverse != 0, (ctx->lazy_ok && !inverse) ? kPolicyShoupLazy : kPolicyShoup, ctx->logn, h, which, (cudaStream_t)stream);
 }
 
 int nttb200_ref_forward_ntt_batch(nttb200_u64 *a, unsigned n, const nttb200_u64 *psi_powers, unsigned num, unsigned division,
@@ -182,26 +183,26 @@ int nttb200_ref_forward_ntt_batch(nttb200_u64 *a, unsigned n, const nttb200_u64 
 {
     if (!q_dev || !mu_dev || !qbit_dev || (n & (n - 1))) return NTTB200_EINVAL;
     NttArgsHost h{a, psi_powers, nullptr, nullptr, q_dev, mu_dev, qbit_dev, 0, 0, 0, num, division, get_tma_default()};
-    return launch_ntt(false, true, ilog2u(n), h, (cudaStream_t)stream);
+    return launch_ntt(false, kPolicyBarrett, ilog2u(n), h, (cudaStream_t)stream);
 }
 int nttb200_ref_inverse_ntt_batch(nttb200_u64 *a, unsigned n, const nttb200_u64 *psiinv_powers, unsigned num, unsigned division,
                                   const nttb200_u64 *q_dev, const nttb200_u64 *mu_dev, const unsigned *qbit_dev, void *stream)
 {
     if (!q_dev || !mu_dev || !qbit_dev || (n & (n - 1))) return NTTB200_EINVAL;
     NttArgsHost h{a, psiinv_powers, nullptr, nullptr, q_dev, mu_dev, qbit_dev, 0, 0, 0, num, division, get_tma_default()};
-    return launch_ntt(true, true, ilog2u(n), h, (cudaStream_t)stream);
+    return launch_ntt(true, kPolicyBarrett, ilog2u(n), h, (cudaStream_t)stream);
 }
 int nttb200_ref_forward_ntt(nttb200_u64 *a, unsigned n, void *stream, nttb200_u64 q, nttb200_u64 mu, int qbit, const nttb200_u64 *psi_powers)
 {
     if (n & (n - 1)) return NTTB200_EINVAL;
     NttArgsHost h{a, psi_powers, nullptr, nullptr, nullptr, nullptr, nullptr, q, mu, (unsigned)qbit, 1, 1, get_tma_default()};
-    return launch_ntt(false, true, ilog2u(n), h, (cudaStream_t)stream);
+    return launch_ntt(false, kPolicyBarrett, ilog2u(n), h, (cudaStream_t)stream);
 }
 int nttb200_ref_inverse_ntt(nttb200_u64 *a, unsigned n, void *stream, nttb200_u64 q, nttb200_u64 mu, int qbit, const nttb200_u64 *psiinv_powers)
 {
     if (n & (n - 1)) return NTTB200_EINVAL;
     NttArgsHost h{a, psiinv_powers, nullptr, nullptr, nullptr, nullptr, nullptr, q, mu, (unsigned)qbit, 1, 1, get_tma_default()};
-    return launch_ntt(true, true, ilog2u(n), h, (cudaStream_t)stream);
+    return launch_ntt(true, kPolicyBarrett, ilog2u(n), h, (cudaStream_t)stream);
 }
 
 }  // extern "C"

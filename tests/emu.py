@@ -21,7 +21,7 @@ def lib():
             subprocess.check_call(["g++", "-std=c++20", "-O2", "-DNTTB200_EMU", "-fPIC", "-shared", "-pthread", "-o", LIB,
                                    os.path.join(EMU_DIR, "emu.cpp")])
         _lib = C.CDLL(LIB)
-        assert _lib.emu_sizeof_limbconst() == 64
+        assert _lib.emu_sizeof_limbconst() == 80
     return _lib
 
 
@@ -31,14 +31,14 @@ def shoup(w, q):
 
 def limb_consts(qs, n, psiinv_tables):
     """LimbConst[limbs] as laid out in csrc/modarith.cuh (64 bytes each)."""
-    out = np.zeros((len(qs), 8), dtype=np.uint64)
+    out = np.zeros((len(qs), 10), dtype=np.uint64)
     for l, q in enumerate(qs):
         q = int(q)
         qbit = q.bit_length()
         mu = (1 << (2 * qbit)) // q
         ninv = pow(n, q - 2, q)
         w1n = int(psiinv_tables[l][1]) * ninv % q
-        out[l] = [q, 2 * q, mu, ninv, (ninv << 64) // q, w1n, (w1n << 64) // q, qbit]
+        out[l] = [q, 2 * q, mu, ninv, (ninv << 64) // q, w1n, (w1n << 64) // q, (1 << 64) // q, (1 << 64) - q, qbit]
     return out
 
 
@@ -53,7 +53,7 @@ def ntt(a, n, qs, psi_tables, psiinv_tables, num, division, inverse, barrett, us
     tw = np.ascontiguousarray(psiinv_tables if inverse else psi_tables, dtype=np.uint64)
     limbs = len(qs)
     u64p = C.c_ulonglong
-    if barrett:
+    if barrett == 1:
         qv = np.array([int(q) for q in qs], dtype=np.uint64)
         muv = np.array([(1 << (2 * int(q).bit_length())) // int(q) for q in qs], dtype=np.uint64)
         qb = np.array([int(q).bit_length() for q in qs], dtype=np.uint32)
@@ -62,7 +62,7 @@ def ntt(a, n, qs, psi_tables, psiinv_tables, num, division, inverse, barrett, us
     else:
         tws = np.ascontiguousarray(np.stack([shoup(tw[l], int(qs[l])) for l in range(limbs)]))
         lc = limb_consts(qs, n, psiinv_tables)
-        r = lib().emu_ntt(int(inverse), 0, int(use_tma), logn, p(a, u64p), p(tw, u64p), p(tws, u64p), lc.ctypes.data_as(C.c_void_p),
+        r = lib().emu_ntt(int(inverse), int(barrett), int(use_tma), logn, p(a, u64p), p(tw, u64p), p(tws, u64p), lc.ctypes.data_as(C.c_void_p),
                           None, None, None, num, division)
     assert r == 0
     return a

@@ -45,6 +45,8 @@ CASES = [
     (15, 3, 4, 0, 1), (15, 2, 2, 1, 1), (15, 1, 1, 0, 0),
     (16, 2, 2, 0, 1), (16, 1, 1, 1, 0),
     (17, 1, 1, 0, 1), (17, 1, 1, 1, 0),
+    # policy 2 = lazy forward (no intermediate corrections, q < 2^58); the 60-bit primes above stay on policy 0
+    (11, 1, 2, 2, 1), (13, 3, 3, 2, 0), (15, 3, 3, 2, 1),
 ]
 
 
@@ -72,3 +74,20 @@ def test_emu_barrett_matches_reference_on_noncanonical_input(oracle):
     assert np.array_equal(got, oracle.forward_ntt(a, q, psi[0]))
     got = emu.ntt(a, n, qs, psi, psiinv, 1, 1, inverse=True, barrett=1, use_tma=0)
     assert np.array_equal(got, oracle.inverse_ntt(a, q, psiinv[0]))
+
+
+def test_emu_barrett_reproduces_reference_barrett_glitch(oracle):
+    """Found on the first GPU run: for q = 68719230977 (4k_3q limb 1, frac(2^72/q) = 0.879) the reference's single-
+    correction Barrett (ntt_60bit.cuh:44-61) returns a value in [q, 2q) on this input, so the REFERENCE's INTT(NTT(a))
+    != a.  The stateless path reproduces the reference bit for bit (garbage included); the Shoup path is exact."""
+    n, qs, roots = params.RNS_SETS["4k_3q"]
+    q, r = qs[1], roots[1]
+    psi, psiinv = oracle.fill_psi_tables(r, q, n)
+    a = oracle.fill_uniform(n, q, 78)
+    f = oracle.forward_ntt_fast(a, q, psi)
+    lit = oracle.inverse_ntt(f, q, psiinv)
+    assert not np.array_equal(lit, a) and int(lit.max()) >= q          # the reference glitches here
+    got = emu.ntt(f, n, [q], psi[None], psiinv[None], 1, 1, inverse=True, barrett=1, use_tma=1)
+    assert np.array_equal(got, lit)
+    got = emu.ntt(f, n, [q], psi[None], psiinv[None], 1, 1, inverse=True, barrett=0, use_tma=1)
+    assert np.array_equal(got, a)
