@@ -26,23 +26,30 @@ static void emu_tma(bool load, const TensorMap *m, void *smem, const int *c)
 {
     const EmuTmapDesc *d = reinterpret_cast<const EmuTmapDesc *>(m->opaque);
     const size_t es = d->strides[0];
-    uint32_t b0 = d->box[0], b1 = d->rank > 1 ? d->box[1] : 1, b2 = d->rank > 2 ? d->box[2] : 1;
+    uint32_t b0 = d->box[0], b1 = d->rank > 1 ? d->box[1] : 1, b2 = d->rank > 2 ? d->box[2] : 1, b3 = d->rank > 3 ? d->box[3] : 1;
     unsigned char *s = (unsigned char *)smem;
     if (d->swizzle128 && ((uintptr_t)s & 1023)) abort();   // hardware requirement
     size_t lin = 0;
+    for (uint32_t m3 = 0; m3 < b3; m3++)
     for (uint32_t k = 0; k < b2; k++)
         for (uint32_t j = 0; j < b1; j++)
             for (uint32_t i = 0; i < b0; i++, lin += es) {
                 size_t goff = (size_t)(c[0] + i) * d->strides[0];
                 if (d->rank > 1) goff += (size_t)(c[1] + j) * d->strides[1];
                 if (d->rank > 2) goff += (size_t)(c[2] + k) * d->strides[2];
+                if (d->rank > 3) goff += (size_t)(c[3] + m3) * d->strides[3];
+                for (int dd = 0; dd < d->rank; dd++) {   // out-of-bounds boxes would be a bug in the kernels
+                    uint64_t cc = (uint64_t)c[dd] + (dd == 0 ? i : dd == 1 ? j : dd == 2 ? k : m3);
+                    if (cc >= d->dims[dd]) abort();
+                }
                 size_t soff = lin;
                 if (d->swizzle128) soff ^= ((soff >> 7) & 7) << 4;
                 if (load) memcpy(s + soff, d->base + goff, es); else memcpy(d->base + goff, s + soff, es);
             }
 }
-void emu_tma_2d(bool load, const TensorMap *m, void *smem, int c0, int c1) { int c[3] = {c0, c1, 0}; emu_tma(load, m, smem, c); }
-void emu_tma_3d(bool load, const TensorMap *m, void *smem, int c0, int c1, int c2) { int c[3] = {c0, c1, c2}; emu_tma(load, m, smem, c); }
+void emu_tma_2d(bool load, const TensorMap *m, void *smem, int c0, int c1) { int c[4] = {c0, c1, 0, 0}; emu_tma(load, m, smem, c); }
+void emu_tma_3d(bool load, const TensorMap *m, void *smem, int c0, int c1, int c2) { int c[4] = {c0, c1, c2, 0}; emu_tma(load, m, smem, c); }
+void emu_tma_4d(bool load, const TensorMap *m, void *smem, int c0, int c1, int c2, int c3) { int c[4] = {c0, c1, c2, c3}; emu_tma(load, m, smem, c); }
 
 using namespace nttb200;
 
@@ -52,22 +59,30 @@ static void run_one(const NttArgs &A)
     using SC = Sched<LOGN>;
     constexpr int R = 1 << SC::K1;
     const size_t n = (size_t)1 << LOGN;
+    const unsigned groups = (A.num + A.group_polys - 1) / A.group_polys;
     TensorMap ms, mc;
     EmuTmapDesc ds{}, dc{};
-    ds.base = (unsigned char *)A.a; ds.rank = 3;
-    ds.dims[0] = n >> SC::K1; ds.dims[1] = R; ds.dims[2] = A.num;
-    ds.strides[0] = 8; ds.strides[1] = (n >> SC::K1) * 8; ds.strides[2] = n * 8;
-    ds.box[0] = 16; ds.box[1] = R > 256 ? 256 : R; ds.box[2] = 1; ds.swizzle128 = 0;
-    dc.base = (unsigned char *)A.a; dc.rank = 2;
-    dc.dims[0] = 16; dc.dims[1] = ((size_t)A.num << LOGN) >> 4;
-    dc.strides[0] = 8; dc.strides[1] = 128;
-    dc.box[0] = 16; dc.box[1] = kContigRows; dc.swizzle128 = 1;
+    ds.base = (unsigned char *)A.a; ds.rank = 4;
+    ds.dims[0] = n >> SC::K1; ds.dims[1] = R; ds.dims[2] = A.group_polys; ds.dims[3] = groups;
+    ds.strides[0] = 8; ds.strides[1] = (n >> SC::K1) * 8; ds.strides[2] = n * 8; ds.strides[3] = A.group_stride * 8;
+    ds.box[0] = 16; ds.box[1] = R > 256 ? 256 : R; ds.box[2] = 1; ds.box[3] = 1; ds.swizzle128 = 0;
+    dc.base = (unsigned char *)A.a; dc.rank = 3;
+    dc.dims[0] = 16; dc.dims[1] = ((size_t)A.group_polys << LOGN) >> 4; dc.dims[2] = groups;
+    dc.strides[0] = 8; dc.strides[1] = 128; dc.strides[2] = A.group_stride * 8;
+    dc.box[0] = 16; dc.box[1] = kContigRows; dc.box[2] = 1; dc.swizzle128 = 1;
+    static_assert(sizeof(EmuTmapDesc) <= sizeof(TensorMap), "descriptor stub too small");
     memcpy(ms.opaque, &ds, sizeof ds);
     memcpy(mc.opaque, &dc, sizeof dc);
+    const unsigned tiles_s = (unsigned)(((n >> SC::K1) >> 4) / SC::NT), tiles_c = (unsigned)((n >> 4) / kContigRows);
+    const unsigned per_class = (A.num + A.division - 1) / A.division;
+    unsigned G = (per_class + 2) / 3;            // about 3 pipelined polynomials per CTA
+    if (G == 0) G = 1;
     emu_dim3 gs, gc;
-    gs.x = (unsigned)(((n >> SC::K1) >> 4) / SC::NT); gs.y = A.num;
-    gc.x = (unsigned)((((size_t)A.num << LOGN) >> 4) / kContigRows);
-    const size_t smem_s = (size_t)SC::NT * R * 128 + 1024 + 16, smem_c = (size_t)kContigRows * 128 + 1024 + 16;
+    gs.x = A.division * tiles_s * G;
+    gc.x = A.division * tiles_c * G;
+    constexpr size_t buf_s = (size_t)SC::NT * R * 128;
+    constexpr int nbuf_s = (buf_s * kStages <= 200 * 1024) ? kStages : 2;
+    const size_t smem_s = buf_s * nbuf_s + 1024 + 64, smem_c = (size_t)kContigRows * 128 * kStages + 1024 + 64;
     auto strided = [&] { emu_launch(gs, R * SC::NT, smem_s, [&] { ntt_strided_pass<P, LOGN, INV>(ms, A); }); };
     auto contig = [&] { emu_launch(gc, kContigRows, smem_c, [&] { ntt_contig_pass<P, LOGN, INV>(mc, A); }); };
     if (!INV) { strided(); contig(); } else { contig(); strided(); }
@@ -90,9 +105,11 @@ static int run_logn(int logn, const NttArgs &A)
 
 extern "C" __attribute__((visibility("default")))
 int emu_ntt(int inverse, int barrett, int use_tma, int logn, u64 *a, const u64 *tw, const u64 *tws, const LimbConst *lc,
-            const u64 *qv, const u64 *muv, const u32 *qbitv, unsigned num, unsigned division)
+            const u64 *qv, const u64 *muv, const u32 *qbitv, unsigned num, unsigned division, unsigned group_polys, size_t group_stride)
 {
     NttArgs A{};
+    A.group_polys = group_polys ? group_polys : num;
+    A.group_stride = group_polys ? group_stride : ((size_t)num << logn);
     A.a = a; A.tw = tw; A.tws = tws; A.lc = lc; A.qv = qv; A.muv = muv; A.qbitv = qbitv;
     A.num = num; A.division = division; A.use_tma = (u32)use_tma;
     if (barrett == 2 && !inverse) return run_logn<ShoupLazyPolicy, false>(logn, A);

@@ -16,9 +16,9 @@
 struct EmuTmapDesc {          // stored inside the opaque TensorMap bytes
     unsigned char *base;
     int rank;
-    uint64_t dims[3];
-    uint64_t strides[3];      // bytes; strides[0] = element size
-    uint32_t box[3];
+    uint64_t dims[4];
+    uint64_t strides[4];      // bytes; strides[0] = element size
+    uint32_t box[4];
     int swizzle128;
 };
 

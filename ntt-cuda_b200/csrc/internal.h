@@ -51,6 +51,8 @@ struct NttArgsHost {
     unsigned qbit;
     unsigned num, division;
     int use_tma;
+    unsigned group_polys = 0;   // 0 = one contiguous [num][n] array
+    size_t group_stride = 0;    // elements between groups
 };
 
 int get_tma_default();

@@ -33,32 +33,55 @@ int get_tma_default()
     return (e && e[0] == '1') ? 0 : 1;
 }
 
-// [num][R = 2^K1][C = n/R] u64, box [1][min(R,256)][16], no swizzle
-static int make_tmap_strided(CUtensorMap *m, u64 *a, unsigned logn, unsigned k1, unsigned num)
+// groups x [group_polys][R = 2^K1][C = n/R] u64, box [1][1][min(R,256)][16], no swizzle
+static int make_tmap_strided(CUtensorMap *m, u64 *a, unsigned logn, unsigned k1, unsigned group_polys, size_t group_stride, unsigned groups)
 {
     EncodeTiledFn enc = get_encode();
     if (!enc) return NTTB200_ENOTMA;
     const cuuint64_t n = 1ull << logn, R = 1ull << k1, C = n >> k1;
-    cuuint64_t dims[3] = {C, R, num};
-    cuuint64_t strides[2] = {C * 8, n * 8};
-    cuuint32_t box[3] = {16, (cuuint32_t)(R > 256 ? 256 : R), 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, a, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    cuuint64_t dims[4] = {C, R, group_polys, groups};
+    cuuint64_t strides[3] = {C * 8, n * 8, (cuuint64_t)group_stride * 8};
+    cuuint32_t box[4] = {16, (cuuint32_t)(R > 256 ? 256 : R), 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, a, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : NTTB200_ENOTMA;
 }
-// [rows = num*n/16][16] u64, box [128][16], 128-byte swizzle
-static int make_tmap_contig(CUtensorMap *m, u64 *a, unsigned logn, unsigned num)
+// groups x [rows = group_polys*n/16][16] u64, box [1][128][16], 128-byte swizzle
+static int make_tmap_contig(CUtensorMap *m, u64 *a, unsigned logn, unsigned group_polys, size_t group_stride, unsigned groups)
 {
     EncodeTiledFn enc = get_encode();
     if (!enc) return NTTB200_ENOTMA;
-    cuuint64_t dims[2] = {16, ((cuuint64_t)num << logn) >> 4};
-    cuuint64_t strides[1] = {128};
-    cuuint32_t box[2] = {16, (cuuint32_t)kContigRows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, a, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    cuuint64_t dims[3] = {16, ((cuuint64_t)group_polys << logn) >> 4, groups};
+    cuuint64_t strides[2] = {128, (cuuint64_t)group_stride * 8};
+    cuuint32_t box[3] = {16, (cuuint32_t)kContigRows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, a, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : NTTB200_ENOTMA;
+}
+
+// Number of CTAs per (limb class, tile): enough CTAs to fill the machine a few times over while every CTA still
+// pipelines several polynomials (NTTB200_ITERS overrides the target polynomials per CTA).
+static unsigned pick_groups(unsigned num, unsigned division, unsigned tiles)
+{
+    static int iters_env = -1, sms = 0;
+    if (iters_env < 0) {
+        const char *e = getenv("NTTB200_ITERS");
+        iters_env = e ? atoi(e) : 0;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    const unsigned per_class = (num + division - 1) / division;       // polynomials per limb class
+    unsigned target_iters = iters_env > 0 ? (unsigned)iters_env : 4;
+    unsigned G = (per_class + target_iters - 1) / target_iters;
+    // never fewer CTAs than ~2 per SM when the batch allows it
+    const unsigned want = 2u * (unsigned)sms;
+    if ((size_t)G * division * tiles < want) G = (want + division * tiles - 1) / (division * tiles);
+    if (G > per_class) G = per_class;
+    return G ? G : 1;
 }
 
 template <class P, int LOGN, bool INV>
@@ -66,16 +89,19 @@ static int launch_one(const NttArgs &A, int which, unsigned cnt, const CUtensorM
 {
     using SC = Sched<LOGN>;
     constexpr int R = 1 << SC::K1;
-    constexpr size_t smem_s = (size_t)SC::NT * R * 128 + 1024 + 16;
-    constexpr size_t smem_c = (size_t)kContigRows * 128 + 1024 + 16;
+    constexpr size_t buf_s = (size_t)SC::NT * R * 128;
+    constexpr int nbuf_s = (buf_s * kStages <= 200 * 1024) ? kStages : 2;
+    constexpr size_t smem_s = buf_s * nbuf_s + 1024 + 64;
+    constexpr size_t smem_c = (size_t)kContigRows * 128 * kStages + 1024 + 64;
     static bool attr_done = false;   // per (P, LOGN, INV) instantiation
     if (!attr_done) {
         NTTB200_CHECK(cudaFuncSetAttribute(ntt_strided_pass<P, LOGN, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
         NTTB200_CHECK(cudaFuncSetAttribute(ntt_contig_pass<P, LOGN, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
         attr_done = true;
     }
-    const dim3 gs((((1u << LOGN) >> SC::K1) >> 4) / SC::NT, cnt);
-    const dim3 gc((unsigned)(((size_t)cnt << LOGN) >> 4) / kContigRows);
+    const unsigned tiles_s = (((1u << LOGN) >> SC::K1) >> 4) / SC::NT, tiles_c = ((1u << LOGN) >> 4) / kContigRows;
+    const dim3 gs(A.division * tiles_s * pick_groups(cnt, A.division, tiles_s));
+    const dim3 gc(A.division * tiles_c * pick_groups(cnt, A.division, tiles_c));
     // which: -1 = whole transform, 0 / 1 = only the first / second kernel in execution order (profiling hook)
     const bool do_strided = which < 0 || (which == 0) == !INV;
     const bool do_contig = which < 0 || (which == 1) == !INV;
@@ -120,32 +146,31 @@ int launch_ntt_pass(bool inverse, int policy, unsigned logn, const NttArgsHost &
 {
     if (logn < 11 || logn > 17 || !h.a || !h.tw || h.division == 0) return NTTB200_EINVAL;
     if (h.num == 0) return 0;
-    // gridDim.y caps one launch at 65535 polynomials; the limb phase (p % division) must be kept per chunk.
-    if (h.division > 65535u) return NTTB200_EINVAL;
-    const unsigned max_chunk = (65535u / h.division) * h.division;
-    for (unsigned p0 = 0; p0 < h.num; p0 += max_chunk) {
-        const unsigned cnt = (h.num - p0) < max_chunk ? (h.num - p0) : max_chunk;
-        NttArgs A;
-        A.a = h.a + ((size_t)p0 << logn);
-        A.tw = h.tw; A.tws = h.tws; A.lc = h.lc;
-        A.qv = h.qv; A.muv = h.muv; A.qbitv = h.qbitv;
-        A.q = h.q; A.mu = h.mu; A.qbit = h.qbit;
-        A.num = cnt; A.division = h.division; A.use_tma = (u32)h.use_tma;
-        CUtensorMap ms, mc;
-        if (h.use_tma) {
-            int r = make_tmap_strided(&ms, A.a, logn, sched_k1(logn), cnt);
-            if (r) return r;
-            r = make_tmap_contig(&mc, A.a, logn, cnt);
-            if (r) return r;
-        } else {
-            memset(&ms, 0, sizeof ms); memset(&mc, 0, sizeof mc);
-        }
-        int r;
-        if (policy == kPolicyShoupLazy && !inverse) r = launch_logn<ShoupLazyPolicy, false>(logn, A, which, cnt, ms, mc, st);
-        else if (policy != kPolicyBarrett) r = inverse ? launch_logn<ShoupPolicy, true>(logn, A, which, cnt, ms, mc, st) : launch_logn<ShoupPolicy, false>(logn, A, which, cnt, ms, mc, st);
-        else r = inverse ? launch_logn<BarrettPolicy, true>(logn, A, which, cnt, ms, mc, st) : launch_logn<BarrettPolicy, false>(logn, A, which, cnt, ms, mc, st);
+    if (h.division > h.num && h.num) { /* fewer polynomials than limbs: classes beyond num are simply empty */ }
+    NttArgs A;
+    A.a = h.a;
+    A.tw = h.tw; A.tws = h.tws; A.lc = h.lc;
+    A.qv = h.qv; A.muv = h.muv; A.qbitv = h.qbitv;
+    A.q = h.q; A.mu = h.mu; A.qbit = h.qbit;
+    A.num = h.num; A.division = h.division; A.use_tma = (u32)h.use_tma;
+    A.group_polys = h.group_polys ? h.group_polys : h.num;
+    A.group_stride = h.group_polys ? h.group_stride : ((size_t)h.num << logn);
+    const unsigned groups = (h.num + A.group_polys - 1) / A.group_polys;
+    CUtensorMap ms, mc;
+    if (h.use_tma) {
+        int r = make_tmap_strided(&ms, A.a, logn, sched_k1(logn), A.group_polys, A.group_stride, groups);
         if (r) return r;
+        r = make_tmap_contig(&mc, A.a, logn, A.group_polys, A.group_stride, groups);
+        if (r) return r;
+    } else {
+        memset(&ms, 0, sizeof ms); memset(&mc, 0, sizeof mc);
     }
+    const unsigned cnt = h.num;
+    int r;
+    if (policy == kPolicyShoupLazy && !inverse) r = launch_logn<ShoupLazyPolicy, false>(logn, A, which, cnt, ms, mc, st);
+    else if (policy != kPolicyBarrett) r = inverse ? launch_logn<ShoupPolicy, true>(logn, A, which, cnt, ms, mc, st) : launch_logn<ShoupPolicy, false>(logn, A, which, cnt, ms, mc, st);
+    else r = inverse ? launch_logn<BarrettPolicy, true>(logn, A, which, cnt, ms, mc, st) : launch_logn<BarrettPolicy, false>(logn, A, which, cnt, ms, mc, st);
+    if (r) return r;
     return 0;
 }
 

@@ -46,7 +46,7 @@ def p(a, t):
     return a.ctypes.data_as(C.POINTER(t))
 
 
-def ntt(a, n, qs, psi_tables, psiinv_tables, num, division, inverse, barrett, use_tma):
+def ntt(a, n, qs, psi_tables, psiinv_tables, num, division, inverse, barrett, use_tma, group_polys=0, group_stride=0):
     """a: flat uint64 [num*n]; tables [limbs][n]."""
     logn = n.bit_length() - 1
     a = np.ascontiguousarray(a, dtype=np.uint64).copy()
@@ -58,11 +58,11 @@ def ntt(a, n, qs, psi_tables, psiinv_tables, num, division, inverse, barrett, us
         muv = np.array([(1 << (2 * int(q).bit_length())) // int(q) for q in qs], dtype=np.uint64)
         qb = np.array([int(q).bit_length() for q in qs], dtype=np.uint32)
         r = lib().emu_ntt(int(inverse), 1, int(use_tma), logn, p(a, u64p), p(tw, u64p), None, None, p(qv, u64p), p(muv, u64p),
-                          p(qb, C.c_uint), num, division)
+                          p(qb, C.c_uint), num, division, group_polys, C.c_size_t(group_stride))
     else:
         tws = np.ascontiguousarray(np.stack([shoup(tw[l], int(qs[l])) for l in range(limbs)]))
         lc = limb_consts(qs, n, psiinv_tables)
         r = lib().emu_ntt(int(inverse), int(barrett), int(use_tma), logn, p(a, u64p), p(tw, u64p), p(tws, u64p), lc.ctypes.data_as(C.c_void_p),
-                          None, None, None, num, division)
+                          None, None, None, num, division, group_polys, C.c_size_t(group_stride))
     assert r == 0
     return a
