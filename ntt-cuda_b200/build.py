@@ -35,6 +35,20 @@ def _compile(src, force):
     return obj
 
 
+def build_variant(name, defines):
+    """Experimental variant: libnttb200_<name>.so compiled with extra -D flags (selected at run time by NTTB200_LIB)."""
+    objdir = os.path.join(OBJ, name)
+    os.makedirs(objdir, exist_ok=True)
+    objs = []
+    for src in _sources():
+        obj = os.path.join(objdir, src[:-3] + ".o")
+        subprocess.check_call([NVCC] + FLAGS + ["-D" + d for d in defines] + ["-c", os.path.join(CSRC, src), "-o", obj])
+        objs.append(obj)
+    out = os.path.join(HERE, "nttb200", "libnttb200_%s.so" % name)
+    subprocess.check_call([NVCC, "-shared", "-o", out] + objs + ["-cudart", "static", "-Xlinker", "--no-undefined", "-lpthread", "-ldl", "-lrt"])
+    return out
+
+
 def build(force=False, jobs=8):
     os.makedirs(OBJ, exist_ok=True)
     with cf.ThreadPoolExecutor(jobs) as ex:
@@ -45,4 +59,8 @@ def build(force=False, jobs=8):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv))
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    else:
+        print(build(force="--force" in sys.argv))

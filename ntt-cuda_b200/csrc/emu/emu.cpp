@@ -74,15 +74,10 @@ static void run_one(const NttArgs &A)
     memcpy(ms.opaque, &ds, sizeof ds);
     memcpy(mc.opaque, &dc, sizeof dc);
     const unsigned tiles_s = (unsigned)(((n >> SC::K1) >> 4) / SC::NT), tiles_c = (unsigned)((n >> 4) / kContigRows);
-    const unsigned per_class = (A.num + A.division - 1) / A.division;
-    unsigned G = (per_class + 2) / 3;            // about 3 pipelined polynomials per CTA
-    if (G == 0) G = 1;
     emu_dim3 gs, gc;
-    gs.x = A.division * tiles_s * G;
-    gc.x = A.division * tiles_c * G;
-    constexpr size_t buf_s = (size_t)SC::NT * R * 128;
-    constexpr int nbuf_s = (buf_s * kStages <= 200 * 1024) ? kStages : 2;
-    const size_t smem_s = buf_s * nbuf_s + 1024 + 64, smem_c = (size_t)kContigRows * 128 * kStages + 1024 + 64;
+    gs.x = A.num * tiles_s;
+    gc.x = A.num * tiles_c;
+    const size_t smem_s = (size_t)SC::NT * R * 128 + 1024 + 16, smem_c = (size_t)kContigRows * 128 + 1024 + 16;
     auto strided = [&] { emu_launch(gs, R * SC::NT, smem_s, [&] { ntt_strided_pass<P, LOGN, INV>(ms, A); }); };
     auto contig = [&] { emu_launch(gc, kContigRows, smem_c, [&] { ntt_contig_pass<P, LOGN, INV>(mc, A); }); };
     if (!INV) { strided(); contig(); } else { contig(); strided(); }

@@ -49,8 +49,9 @@ __host__ __device__ __forceinline__ u64 shoup_mul(u64 y, u64 w, u64 ws, u64 q)
     return y * w - qhat * q;
 }
 
-// low 64 bits of a*b + c*d as ONE accumulation chain: 2 IMAD.WIDE.U32 + 4 IMAD and no carry/negate fix-ups
-// (nvcc's own code for `a*b - c*q` is 10 instructions: two separate 64-bit products, a negation and an add).
+// low 64 bits of a*b + c*d as one accumulation chain: 2 IMAD.WIDE.U32 + 4 IMAD, no carry / negate fix-ups (nvcc's own
+// code for `a*b - c*q` is 10 instructions).  The a*b part (1 wide + 2 lo) is issued first and does not depend on c, so
+// in a Shoup product it overlaps the mul.hi that produces c; only 1 wide + 2 lo remain on the critical path after it.
 __host__ __device__ __forceinline__ u64 mullo_sum2(u64 a, u64 b, u64 c, u64 d)
 {
 #if defined(__CUDA_ARCH__)
@@ -63,10 +64,12 @@ __host__ __device__ __forceinline__ u64 mullo_sum2(u64 a, u64 b, u64 c, u64 d)
         "mov.b64 {cl, ch}, %3;\n\t"
         "mov.b64 {dl, dh}, %4;\n\t"
         "mul.wide.u32 acc, al, bl;\n\t"
-        "mad.wide.u32 acc, cl, dl, acc;\n\t"
         "mov.b64 {rl, rh}, acc;\n\t"
         "mad.lo.u32 rh, al, bh, rh;\n\t"
         "mad.lo.u32 rh, ah, bl, rh;\n\t"
+        "mov.b64 acc, {rl, rh};\n\t"
+        "mad.wide.u32 acc, cl, dl, acc;\n\t"
+        "mov.b64 {rl, rh}, acc;\n\t"
         "mad.lo.u32 rh, cl, dh, rh;\n\t"
         "mad.lo.u32 rh, ch, dl, rh;\n\t"
         "mov.b64 %0, {rl, rh};\n\t"

@@ -68,6 +68,14 @@ NTTB200_SCHED(17, 3, 3, 3, 8, 1)
 #undef NTTB200_SCHED
 
 constexpr int kContigRows = 128;  // rows (of 16 coefficients) per CTA in the contiguous pass
+// Minimum resident CTAs per SM the register allocator must leave room for (occupancy vs. per-thread ILP trade-off,
+// tuned on the B200: see DESIGN.md "occupancy sweep").
+#ifndef NTT_MINB_S
+#define NTT_MINB_S 3
+#endif
+#ifndef NTT_MINB_C
+#define NTT_MINB_C 6
+#endif
 
 // ---- arithmetic policies ------------------------------------------------------------------------------------
 struct ShoupPolicy {
@@ -313,263 +321,160 @@ __device__ __forceinline__ u64 *align_1024(unsigned char *p)
 #endif
 }
 
-// ---- work distribution ---------------------------------------------------------------------------------------------
-// A CTA owns one (limb class, tile) pair and walks the polynomials of that class: p = cls + division * (g + G * k).
-// All of them use the same twiddles, which therefore stay in L1 (the data itself goes HBM -> smem by TMA and never
-// touches L1), and consecutive polynomials are software-pipelined through kStages shared-memory buffers:
-// the TMA load of item i+2 and the TMA store of item i-1 are in flight while item i is being computed.
-constexpr int kStages = 3;
-
-struct WorkList {
-    u32 tile, first, step, count;   // tile index inside a polynomial; polynomials first, first+step, ... (count of them)
-};
-__device__ __forceinline__ WorkList work_list(const NttArgs &A, u32 tiles)
-{
-    WorkList w;
-    const u32 cta = blockIdx.x;
-    w.tile = cta % tiles;
-    const u32 rest = cta / tiles;
-    const u32 cls = rest % A.division, g = rest / A.division, G = gridDim.x / (tiles * A.division);
-    w.first = cls + A.division * g;
-    w.step = A.division * G;
-    w.count = w.first < A.num ? (A.num - w.first + w.step - 1) / w.step : 0;
-    return w;
-}
-// polynomial p lives at a + (p / group_polys) * group_stride + (p % group_polys) * n
-__device__ __forceinline__ size_t poly_offset(const NttArgs &A, u32 p, u32 logn)
-{
-    const u32 grp = p / A.group_polys, idx = p - grp * A.group_polys;
-    return (size_t)grp * A.group_stride + ((size_t)idx << logn);
-}
-
-// ---- pass "strided": grid (division * tiles * G), 2^K1 * NT threads, tiles = n / 2^K1 / 16 / NT -------------------
+// ---- pass "strided": grid (num * tiles), tiles = n / 2^K1 / 16 / NT column tiles per polynomial; 2^K1 * NT threads ------------------------------------------
 template <class P, int LOGN, bool INV>
-__global__ void __launch_bounds__((1 << Sched<LOGN>::K1) * Sched<LOGN>::NT)
+__global__ void __launch_bounds__((1 << Sched<LOGN>::K1) * Sched<LOGN>::NT, ((1 << Sched<LOGN>::K1) * Sched<LOGN>::NT) > 256 ? 1 : NTT_MINB_S)
 ntt_strided_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
 {
     using SC = Sched<LOGN>;
     constexpr int K1 = SC::K1, R = 1 << K1, NT = SC::NT, THREADS = R * NT;
     constexpr u32 n = 1u << LOGN, C = n >> K1;          // C columns per row
     constexpr int RB = R > 256 ? 256 : R;               // TMA box rows (box dims are capped at 256)
-    constexpr size_t BUF = (size_t)NT * R * 16;         // u64 per pipeline buffer
-    constexpr int NBUF = (BUF * 8 * kStages <= 200 * 1024) ? kStages : 2;
     NTT_DYN_SMEM(raw);
-    u64 *bufs = align_1024(raw);
-    u64 *bar = bufs + BUF * NBUF;                       // NBUF mbarriers
-    const u32 tid = threadIdx.x;
-    const WorkList wl = work_list(A, (C >> 4) / NT);
-    if (wl.count == 0) return;
-    const u32 col0 = wl.tile * (NT * 16);
+    u64 *tiles = align_1024(raw);
+    u64 *bar = tiles + (size_t)NT * R * 16;
+    constexpr u32 TILES = (C >> 4) / NT;
+    const u32 tid = threadIdx.x, p = blockIdx.x / TILES;
+    const u32 col0 = (blockIdx.x % TILES) * (NT * 16);
+    const u32 grp = p / A.group_polys, idx = p - grp * A.group_polys;   // polynomial idx of group grp
     P pol;
-    pol.init(A, wl.first % A.division, n);
-
-    auto tma_item = [&](bool load, u32 item, u64 *buf, u64 *b) {
-        const u32 p = wl.first + item * wl.step;
-        const u32 grp = p / A.group_polys, idx = p - grp * A.group_polys;
-        for (int k = 0; k < NT; k++)
-            for (int rc = 0; rc < R / RB; rc++) {
-                u64 *dst = buf + ((size_t)k * R + rc * RB) * 16;
-#ifdef NTTB200_EMU
-                (void)b;
-                emu_tma_4d(load, &tmap, dst, (int)col0 + k * 16, rc * RB, (int)idx, (int)grp);
-#else
-                if (load) tma_load_4d(dst, &tmap, b, (int)col0 + k * 16, rc * RB, (int)idx, (int)grp);
-                else tma_store_4d(&tmap, dst, (int)col0 + k * 16, rc * RB, (int)idx, (int)grp);
-#endif
-            }
-    };
+    pol.init(A, p % A.division, n);
+    u64 *g = A.a + (size_t)grp * A.group_stride + ((size_t)idx << LOGN) + col0;
 
     if (A.use_tma) {
-#ifndef NTTB200_EMU
-        if (tid == 0) {
-            for (int s = 0; s < NBUF; s++) mbar_init(bar + s, 1);
-            fence_mbar_init();
-        }
-        __syncthreads();
-#endif
-        if (tid == 0)
-            for (u32 s = 0; s < (u32)(NBUF - 1) && s < wl.count; s++) {
-#ifndef NTTB200_EMU
-                mbar_expect_tx(bar + s, (u32)(BUF * 8));
-#endif
-                tma_item(true, s, bufs + BUF * s, bar + s);
-            }
-    }
-
-    const u32 u = tid & (R - 1);
-    for (u32 it = 0; it < wl.count; it++) {
-        const u32 b = A.use_tma ? it % NBUF : 0;
-        u64 *buf = bufs + BUF * b;
-        u64 *g = A.a + poly_offset(A, wl.first + it * wl.step, LOGN) + col0;
-        if (A.use_tma) {
 #ifdef NTTB200_EMU
-            __syncthreads();
+        if (tid == 0)
+            for (int k = 0; k < NT; k++)
+                for (int rc = 0; rc < R / RB; rc++)
+                    emu_tma_4d(true, &tmap, tiles + ((size_t)k * R + rc * RB) * 16, (int)col0 + k * 16, rc * RB, (int)idx, (int)grp);
+        __syncthreads();
 #else
-            mbar_wait(bar + b, (it / NBUF) & 1u);
-#endif
-        } else {
-            for (int k = 0; k < NT; k++) tile_copy_coop<false, true>(buf + (size_t)k * R * 16, g + k * 16, C, R, tid, THREADS);
-            __syncthreads();
+        if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(bar, (u32)(NT * R * 128));
+            for (int k = 0; k < NT; k++)
+                for (int rc = 0; rc < R / RB; rc++)
+                    tma_load_4d(tiles + ((size_t)k * R + rc * RB) * 16, &tmap, bar, (int)col0 + k * 16, rc * RB, (int)idx, (int)grp);
         }
-
-        u64 *tile = buf + (size_t)(tid >> K1) * R * 16;
-        if (!INV) {
-            strided_round<P, K1, 0, SC::S1, false>(tile, u, pol);
-            if constexpr (SC::S2 != 0) { __syncthreads(); strided_round<P, K1, SC::S1, SC::S2, false>(tile, u, pol); }
-            if constexpr (SC::S3 != 0) { __syncthreads(); strided_round<P, K1, SC::S1 + SC::S2, SC::S3, false>(tile, u, pol); }
-        } else {
-            if constexpr (SC::S3 != 0) { strided_round<P, K1, SC::S1 + SC::S2, SC::S3, true>(tile, u, pol); __syncthreads(); }
-            if constexpr (SC::S2 != 0) { strided_round<P, K1, SC::S1, SC::S2, true>(tile, u, pol); __syncthreads(); }
-            strided_round<P, K1, 0, SC::S1, true>(tile, u, pol);
-        }
-
-        if (A.use_tma) {
-#ifndef NTTB200_EMU
-            fence_proxy_async();
+        mbar_wait(bar, 0);
 #endif
-            __syncthreads();
-            if (tid == 0) {
-                tma_item(false, it, buf, nullptr);
-#ifndef NTTB200_EMU
-                tma_store_commit();
-#endif
-                const u32 nxt = it + NBUF - 1;              // goes into the buffer item it-1 was stored from
-                if (nxt < wl.count) {
-#ifndef NTTB200_EMU
-                    tma_store_wait_read<1>();
-                    mbar_expect_tx(bar + nxt % NBUF, (u32)(BUF * 8));
-#endif
-                    tma_item(true, nxt, bufs + BUF * (nxt % NBUF), bar + nxt % NBUF);
-                }
-            }
-        } else {
-            __syncthreads();
-            for (int k = 0; k < NT; k++) tile_copy_coop<false, false>(buf + (size_t)k * R * 16, g + k * 16, C, R, tid, THREADS);
-            __syncthreads();
-        }
+    } else {
+        for (int k = 0; k < NT; k++) tile_copy_coop<false, true>(tiles + (size_t)k * R * 16, g + k * 16, C, R, tid, THREADS);
+        __syncthreads();
     }
-#ifndef NTTB200_EMU
-    if (A.use_tma && tid == 0) tma_store_wait_read<0>();
+
+    u64 *tile = tiles + (size_t)(tid >> K1) * R * 16;
+    const u32 u = tid & (R - 1);
+    if (!INV) {
+        strided_round<P, K1, 0, SC::S1, false>(tile, u, pol);
+        if constexpr (SC::S2 != 0) { __syncthreads(); strided_round<P, K1, SC::S1, SC::S2, false>(tile, u, pol); }
+        if constexpr (SC::S3 != 0) { __syncthreads(); strided_round<P, K1, SC::S1 + SC::S2, SC::S3, false>(tile, u, pol); }
+    } else {
+        if constexpr (SC::S3 != 0) { strided_round<P, K1, SC::S1 + SC::S2, SC::S3, true>(tile, u, pol); __syncthreads(); }
+        if constexpr (SC::S2 != 0) { strided_round<P, K1, SC::S1, SC::S2, true>(tile, u, pol); __syncthreads(); }
+        strided_round<P, K1, 0, SC::S1, true>(tile, u, pol);
+    }
+
+    if (A.use_tma) {
+#ifdef NTTB200_EMU
+        __syncthreads();
+        if (tid == 0)
+            for (int k = 0; k < NT; k++)
+                for (int rc = 0; rc < R / RB; rc++)
+                    emu_tma_4d(false, &tmap, tiles + ((size_t)k * R + rc * RB) * 16, (int)col0 + k * 16, rc * RB, (int)idx, (int)grp);
+#else
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            for (int k = 0; k < NT; k++)
+                for (int rc = 0; rc < R / RB; rc++)
+                    tma_store_4d(&tmap, tiles + ((size_t)k * R + rc * RB) * 16, (int)col0 + k * 16, rc * RB, (int)idx, (int)grp);
+            tma_store_commit();
+            tma_store_wait_read<0>();
+        }
 #endif
+    } else {
+        __syncthreads();
+        for (int k = 0; k < NT; k++) tile_copy_coop<false, false>(tiles + (size_t)k * R * 16, g + k * 16, C, R, tid, THREADS);
+    }
+    (void)bar;
 }
 
-// ---- pass "contig": grid (division * tiles * G), 128 threads, tiles = n / 16 / 128 -----------------------------------
+// ---- pass "contig": grid (num * n / 16 / 128), 128 threads; CTA = 128 consecutive rows of one polynomial ------------------------------------------------------
 template <class P, int LOGN, bool INV>
-__global__ void __launch_bounds__(kContigRows)
+__global__ void __launch_bounds__(kContigRows, NTT_MINB_C)
 ntt_contig_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
 {
     using SC = Sched<LOGN>;
     constexpr int K1 = SC::K1, K2 = SC::K2, SA = K2 - 4, NC = 16 >> SA, RT = kContigRows;
     constexpr u32 n = 1u << LOGN;
-    constexpr size_t BUF = (size_t)RT * 16;
-    constexpr int NBUF = kStages;
     NTT_DYN_SMEM(raw);
-    u64 *bufs = align_1024(raw);
-    u64 *bar = bufs + BUF * NBUF;
+    u64 *tile = align_1024(raw);
+    u64 *bar = tile + (size_t)RT * 16;
     const u32 tid = threadIdx.x;
-    const WorkList wl = work_list(A, (n >> 4) / RT);
-    if (wl.count == 0) return;
-    const u32 rip0 = wl.tile * RT;                       // first row (of 16 coefficients) inside the polynomial
+    constexpr u32 TILES = (n >> 4) / RT;
+    const u32 p = blockIdx.x / TILES;
+    const u32 rip0 = (blockIdx.x % TILES) * RT;          // first row (of 16 coefficients) inside the polynomial
+    const u32 grp = p / A.group_polys, idx = p - grp * A.group_polys;
+    const int grow = (int)(idx * (n >> 4) + rip0);       // row inside the group
     P pol;
-    pol.init(A, wl.first % A.division, n);
-
-    auto tma_item = [&](bool load, u32 item, u64 *buf, u64 *b) {
-        const u32 p = wl.first + item * wl.step;
-        const u32 grp = p / A.group_polys, idx = p - grp * A.group_polys;
-        const int row = (int)(idx * (n >> 4) + rip0);    // row inside the group
-#ifdef NTTB200_EMU
-        (void)b;
-        emu_tma_3d(load, &tmap, buf, 0, row, (int)grp);
-#else
-        if (load) tma_load_3d(buf, &tmap, b, 0, row, (int)grp);
-        else tma_store_3d(&tmap, buf, 0, row, (int)grp);
-#endif
-    };
+    pol.init(A, p % A.division, n);
+    u64 *g = A.a + (size_t)grp * A.group_stride + ((size_t)idx << LOGN) + (size_t)rip0 * 16;
 
     if (A.use_tma) {
-#ifndef NTTB200_EMU
-        if (tid == 0) {
-            for (int s = 0; s < NBUF; s++) mbar_init(bar + s, 1);
-            fence_mbar_init();
-        }
+#ifdef NTTB200_EMU
+        if (tid == 0) emu_tma_3d(true, &tmap, tile, 0, grow, (int)grp);
         __syncthreads();
+#else
+        if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+        __syncthreads();
+        if (tid == 0) { mbar_expect_tx(bar, (u32)(RT * 128)); tma_load_3d(tile, &tmap, bar, 0, grow, (int)grp); }
+        mbar_wait(bar, 0);
 #endif
-        if (tid == 0)
-            for (u32 s = 0; s < (u32)(NBUF - 1) && s < wl.count; s++) {
-#ifndef NTTB200_EMU
-                mbar_expect_tx(bar + s, (u32)(BUF * 8));
-#endif
-                tma_item(true, s, bufs + BUF * s, bar + s);
-            }
+    } else {
+        tile_copy_coop<true, true>(tile, g, 16, RT, tid, RT);
+        __syncthreads();
     }
 
     const u32 t = tid & ((1u << SA) - 1u), bl = tid >> SA;     // lane-in-block, block-in-tile
     const u32 twA = (1u << K1) + (rip0 >> SA) + bl;            // block index inside the polynomial
     const u32 twB = (n >> 4) + rip0 + tid;                     // row index inside the polynomial
-    for (u32 it = 0; it < wl.count; it++) {
-        const u32 b = A.use_tma ? it % NBUF : 0;
-        u64 *tile = bufs + BUF * b;
-        u64 *g = A.a + poly_offset(A, wl.first + it * wl.step, LOGN) + (size_t)rip0 * 16;
-        if (A.use_tma) {
-#ifdef NTTB200_EMU
-            __syncthreads();
-#else
-            mbar_wait(bar + b, (it / NBUF) & 1u);
-#endif
-        } else {
-            tile_copy_coop<true, true>(tile, g, 16, RT, tid, RT);
-            __syncthreads();
-        }
-
-        u64 v[16];
-        if (!INV) {
-            regs_rows<SA, true, true>(tile, bl << SA, 0, t * NC, v);
-            ct_stages<SA, NC>(v, twA, pol);
-            regs_rows<SA, true, false>(tile, bl << SA, 0, t * NC, v);
-            __syncwarp();
-            regs_row<true, true>(tile, tid, v);
-            ct_stages<4, 1>(v, twB, pol);
-            NTT_UNROLL
-            for (int i = 0; i < 16; i++) v[i] = pol.fwd_final(v[i]);
-            regs_row<true, false>(tile, tid, v);
-        } else {
-            regs_row<true, true>(tile, tid, v);
-            gs_stages<4, 1, false>(v, twB, pol);
-            regs_row<true, false>(tile, tid, v);
-            __syncwarp();
-            regs_rows<SA, true, true>(tile, bl << SA, 0, t * NC, v);
-            gs_stages<SA, NC, false>(v, twA, pol);
-            regs_rows<SA, true, false>(tile, bl << SA, 0, t * NC, v);
-        }
-
-        if (A.use_tma) {
-#ifndef NTTB200_EMU
-            fence_proxy_async();
-#endif
-            __syncthreads();
-            if (tid == 0) {
-                tma_item(false, it, tile, nullptr);
-#ifndef NTTB200_EMU
-                tma_store_commit();
-#endif
-                const u32 nxt = it + NBUF - 1;
-                if (nxt < wl.count) {
-#ifndef NTTB200_EMU
-                    tma_store_wait_read<1>();
-                    mbar_expect_tx(bar + nxt % NBUF, (u32)(BUF * 8));
-#endif
-                    tma_item(true, nxt, bufs + BUF * (nxt % NBUF), bar + nxt % NBUF);
-                }
-            }
-        } else {
-            __syncthreads();
-            tile_copy_coop<true, false>(tile, g, 16, RT, tid, RT);
-            __syncthreads();
-        }
+    u64 v[16];
+    if (!INV) {
+        regs_rows<SA, true, true>(tile, bl << SA, 0, t * NC, v);
+        ct_stages<SA, NC>(v, twA, pol);
+        regs_rows<SA, true, false>(tile, bl << SA, 0, t * NC, v);
+        __syncwarp();
+        regs_row<true, true>(tile, tid, v);
+        ct_stages<4, 1>(v, twB, pol);
+        NTT_UNROLL
+        for (int i = 0; i < 16; i++) v[i] = pol.fwd_final(v[i]);
+        regs_row<true, false>(tile, tid, v);
+    } else {
+        regs_row<true, true>(tile, tid, v);
+        gs_stages<4, 1, false>(v, twB, pol);
+        regs_row<true, false>(tile, tid, v);
+        __syncwarp();
+        regs_rows<SA, true, true>(tile, bl << SA, 0, t * NC, v);
+        gs_stages<SA, NC, false>(v, twA, pol);
+        regs_rows<SA, true, false>(tile, bl << SA, 0, t * NC, v);
     }
-#ifndef NTTB200_EMU
-    if (A.use_tma && tid == 0) tma_store_wait_read<0>();
+
+    if (A.use_tma) {
+#ifdef NTTB200_EMU
+        __syncthreads();
+        if (tid == 0) emu_tma_3d(false, &tmap, tile, 0, grow, (int)grp);
+#else
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) { tma_store_3d(&tmap, tile, 0, grow, (int)grp); tma_store_commit(); tma_store_wait_read<0>(); }
 #endif
+    } else {
+        __syncthreads();
+        tile_copy_coop<true, false>(tile, g, 16, RT, tid, RT);
+    }
+    (void)bar;
 }
 
 }  // namespace nttb200

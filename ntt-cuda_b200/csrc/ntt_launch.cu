@@ -61,38 +61,13 @@ static int make_tmap_contig(CUtensorMap *m, u64 *a, unsigned logn, unsigned grou
     return r == CUDA_SUCCESS ? 0 : NTTB200_ENOTMA;
 }
 
-// Number of CTAs per (limb class, tile): enough CTAs to fill the machine a few times over while every CTA still
-// pipelines several polynomials (NTTB200_ITERS overrides the target polynomials per CTA).
-static unsigned pick_groups(unsigned num, unsigned division, unsigned tiles)
-{
-    static int iters_env = -1, sms = 0;
-    if (iters_env < 0) {
-        const char *e = getenv("NTTB200_ITERS");
-        iters_env = e ? atoi(e) : 0;
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-    }
-    const unsigned per_class = (num + division - 1) / division;       // polynomials per limb class
-    unsigned target_iters = iters_env > 0 ? (unsigned)iters_env : 4;
-    unsigned G = (per_class + target_iters - 1) / target_iters;
-    // never fewer CTAs than ~2 per SM when the batch allows it
-    const unsigned want = 2u * (unsigned)sms;
-    if ((size_t)G * division * tiles < want) G = (want + division * tiles - 1) / (division * tiles);
-    if (G > per_class) G = per_class;
-    return G ? G : 1;
-}
-
 template <class P, int LOGN, bool INV>
 static int launch_one(const NttArgs &A, int which, unsigned cnt, const CUtensorMap &ms, const CUtensorMap &mc, cudaStream_t st)
 {
     using SC = Sched<LOGN>;
     constexpr int R = 1 << SC::K1;
-    constexpr size_t buf_s = (size_t)SC::NT * R * 128;
-    constexpr int nbuf_s = (buf_s * kStages <= 200 * 1024) ? kStages : 2;
-    constexpr size_t smem_s = buf_s * nbuf_s + 1024 + 64;
-    constexpr size_t smem_c = (size_t)kContigRows * 128 * kStages + 1024 + 64;
+    constexpr size_t smem_s = (size_t)SC::NT * R * 128 + 1024 + 16;
+    constexpr size_t smem_c = (size_t)kContigRows * 128 + 1024 + 16;
     static bool attr_done = false;   // per (P, LOGN, INV) instantiation
     if (!attr_done) {
         NTTB200_CHECK(cudaFuncSetAttribute(ntt_strided_pass<P, LOGN, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
@@ -100,8 +75,9 @@ static int launch_one(const NttArgs &A, int which, unsigned cnt, const CUtensorM
         attr_done = true;
     }
     const unsigned tiles_s = (((1u << LOGN) >> SC::K1) >> 4) / SC::NT, tiles_c = ((1u << LOGN) >> 4) / kContigRows;
-    const dim3 gs(A.division * tiles_s * pick_groups(cnt, A.division, tiles_s));
-    const dim3 gc(A.division * tiles_c * pick_groups(cnt, A.division, tiles_c));
+    if ((size_t)cnt * tiles_c >= (1ull << 31)) return NTTB200_EINVAL;
+    const dim3 gs(cnt * tiles_s);
+    const dim3 gc(cnt * tiles_c);
     // which: -1 = whole transform, 0 / 1 = only the first / second kernel in execution order (profiling hook)
     const bool do_strided = which < 0 || (which == 0) == !INV;
     const bool do_contig = which < 0 || (which == 1) == !INV;

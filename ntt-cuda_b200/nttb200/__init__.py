@@ -15,7 +15,7 @@ import os
 from . import params  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnttb200.so")
+LIB_PATH = os.environ.get("NTTB200_LIB") or os.path.join(_HERE, "libnttb200.so")   # NTTB200_LIB: tuning variants
 
 _lib = None
 u64 = C.c_ulonglong
