@@ -93,6 +93,103 @@ NTTB200_API int nttb200_ref_forward_ntt(nttb200_u64 *a, unsigned n, void *stream
 NTTB200_API int nttb200_ref_inverse_ntt(nttb200_u64 *a, unsigned n, void *stream, nttb200_u64 q, nttb200_u64 mu, int qbit,
                                         const nttb200_u64 *psiinv_powers);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Coefficient-wise kernels (poly_arithmetic.cuh).  Reference semantics quirk for quirk: poly_add*
+ * subtract q only if the sum is > q, poly_sub never subtracts b, mod_t / fast_convert_t use a 32-bit mask.
+ * ------------------------------------------------------------------------------------------------- */
+/* barrett<<<n/256,256>>> poly_arithmetic.cuh:9 (a *= b) and the 3-operand form c = a*b */
+NTTB200_API int nttb200_barrett(nttb200_u64 *a, const nttb200_u64 *b, unsigned n, nttb200_u64 q, nttb200_u64 mu, int qbit, void *stream);
+NTTB200_API int nttb200_barrett_3param(nttb200_u64 *c, const nttb200_u64 *a, const nttb200_u64 *b, unsigned n, nttb200_u64 q, nttb200_u64 mu,
+                                       int qbit, void *stream);
+/* barrett_batch :36, barrett_batch_3param :68 (limb = poly % division; constants from device arrays) */
+NTTB200_API int nttb200_barrett_batch(nttb200_u64 *a, const nttb200_u64 *b, unsigned n, unsigned polys, unsigned division,
+                                      const nttb200_u64 *q_dev, const nttb200_u64 *mu_dev, const unsigned *qbit_dev, void *stream);
+NTTB200_API int nttb200_barrett_batch_3param(nttb200_u64 *c, const nttb200_u64 *a, const nttb200_u64 *b, unsigned n, unsigned polys,
+                                             unsigned division, const nttb200_u64 *q_dev, const nttb200_u64 *mu_dev, const unsigned *qbit_dev,
+                                             void *stream);
+/* poly_mul_int :317 (barrett_int :100), poly_mul_int_t :322 (mod_t :128) */
+NTTB200_API int nttb200_barrett_int(nttb200_u64 *a, nttb200_u64 b, unsigned n, nttb200_u64 q, nttb200_u64 mu, int qbit, void *stream);
+NTTB200_API int nttb200_mod_t(nttb200_u64 *a, nttb200_u64 b, unsigned n, nttb200_u64 t, void *stream);
+/* poly_add_device :312, poly_add_integer_device :345, poly_sub_device :327, poly_negate_device :340 */
+NTTB200_API int nttb200_poly_add(nttb200_u64 *a, const nttb200_u64 *b, unsigned n, nttb200_u64 q, void *stream);
+NTTB200_API int nttb200_poly_add_integer(nttb200_u64 *a, nttb200_u64 b, unsigned n, nttb200_u64 q, void *stream);
+NTTB200_API int nttb200_poly_sub(nttb200_u64 *a, const nttb200_u64 *b, unsigned n, nttb200_u64 q, void *stream);
+NTTB200_API int nttb200_poly_negate(nttb200_u64 *a, unsigned n, nttb200_u64 q, void *stream);
+/* divide_and_round_q_last_inplace_loop :180 */
+NTTB200_API int nttb200_divide_and_round_q_last_inplace_loop(nttb200_u64 *input_poly, const nttb200_u64 *rns_poly_minus1, unsigned n,
+                                                             nttb200_u64 base_q_i, nttb200_u64 half_mod, nttb200_u64 inv_q_last_mod_q_i,
+                                                             nttb200_u64 mu, int qbit, void *stream);
+/* fast_convert_array_kernels :270 (result_poly[0:n] mod t, [n:2n] mod gamma; both on `stream`), dec_round :265 */
+NTTB200_API int nttb200_fast_convert_array(const nttb200_u64 *input_poly, nttb200_u64 *result_poly, nttb200_u64 t, const nttb200_u64 *bcm_dev,
+                                           unsigned q_amount, nttb200_u64 gamma, int gamma_bits, nttb200_u64 mu_gamma, unsigned n, void *stream);
+NTTB200_API int nttb200_dec_round(const nttb200_u64 *input_poly, nttb200_u64 *result_poly, nttb200_u64 t, nttb200_u64 gamma,
+                                  nttb200_u64 gamma_div_2, unsigned n, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Sampling (distributions.cuh, salsa_common.h): Salsa20/20 keystream + distribution converters.
+ * ------------------------------------------------------------------------------------------------- */
+/* generate_random_default :249 (key 32 x 0x01), generate_random :220 (key 0x4D in bytes 0..23, tail = process state) */
+NTTB200_API int nttb200_generate_random_default(unsigned char *a, unsigned nbytes, void *stream);
+NTTB200_API int nttb200_generate_random(unsigned char *a, unsigned nbytes, void *stream);
+/* explicit key; `streams` keystreams of blocks_per_stream 64-byte blocks, stream s = nonce0 + s at out + s*stream_stride */
+NTTB200_API int nttb200_salsa20_keystream(unsigned char *out, nttb200_u64 blocks_per_stream, nttb200_u64 streams, size_t stream_stride,
+                                          const unsigned char key[32], nttb200_u64 nonce0, void *stream);
+/* gaussian_dist :278, uniform_dist :285, ternary_dist :292 */
+NTTB200_API int nttb200_gaussian_dist(const unsigned *in, nttb200_u64 *out, unsigned n, void *stream, nttb200_u64 q);
+NTTB200_API int nttb200_uniform_dist(const nttb200_u64 *in, nttb200_u64 *out, unsigned n, void *stream, nttb200_u64 q);
+NTTB200_API int nttb200_ternary_dist(const unsigned char *in, nttb200_u64 *out, unsigned n, void *stream, nttb200_u64 q);
+/* ternary_dist_xq bfv_keygen.cuh:14, uniform_dist_xq :33, gaussian_dist_xq :47, poly_add_negate_xq :81,
+ * convert_ternary_gaussian_x2 bfv_encryption.cuh:17 */
+NTTB200_API int nttb200_ternary_dist_xq(const unsigned char *in, nttb200_u64 *sk, unsigned n, unsigned q_amount, const nttb200_u64 *q_dev, void *stream);
+NTTB200_API int nttb200_uniform_dist_xq(const unsigned char *in, nttb200_u64 *pk, unsigned n, unsigned q_amount, const nttb200_u64 *q_dev, void *stream);
+NTTB200_API int nttb200_gaussian_dist_xq(const unsigned char *in, nttb200_u64 *temp, unsigned n, unsigned q_amount, const nttb200_u64 *q_dev, void *stream);
+NTTB200_API int nttb200_poly_add_negate_xq(nttb200_u64 *a, const nttb200_u64 *b, unsigned n, unsigned q_amount, const nttb200_u64 *q_dev, void *stream);
+NTTB200_API int nttb200_convert_ternary_gaussian_x2(const unsigned char *in, nttb200_u64 *c, nttb200_u64 *e, unsigned n, unsigned q_amount,
+                                                    const nttb200_u64 *q_dev, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * BFV pipelines, context-based and BATCHED.  Layouts per item (the reference's):
+ *   sk[r][n] (NTT domain) . pk[2][r][n] = [pk0 | pk1 = a] (NTT domain) . c[2][r][n] with limb r-1 of each half
+ *   left as padding after encryption . m[n] (< t).  Item k samples from Salsa20 nonce nonce0 + k; nonce0 = 0,
+ *   batch = 1 reproduces the reference call bit for bit.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct nttb200_bfv nttb200_bfv;
+/* derives every constant of demo.cu:62-264 (qbit, mu, inv_q_last_mod_q, q_i/t, t*gamma mod q_i, punctured inverses,
+ * base-change matrix, -q^-1 mod {t, gamma}, mu_gamma) and the twiddle tables */
+NTTB200_API int nttb200_bfv_create(nttb200_bfv **bfv, unsigned n, unsigned limbs, const nttb200_u64 *q, const nttb200_u64 *psi_roots,
+                                   nttb200_u64 t, nttb200_u64 gamma);
+NTTB200_API void nttb200_bfv_destroy(nttb200_bfv *bfv);
+NTTB200_API nttb200_ctx *nttb200_bfv_ctx(nttb200_bfv *bfv);
+/* pre-sizes the internal keystream scratch so that later calls never allocate */
+NTTB200_API int nttb200_bfv_reserve(nttb200_bfv *bfv, unsigned batch);
+/* keygen_rns bfv_keygen.cuh:95 */
+NTTB200_API int nttb200_bfv_keygen(nttb200_bfv *bfv, nttb200_u64 *sk, nttb200_u64 *pk, unsigned batch, nttb200_u64 nonce0, void *stream);
+/* encryption_rns bfv_encryption.cuh:223; pk_per_item = 0: one public key for the batch */
+NTTB200_API int nttb200_bfv_encrypt(nttb200_bfv *bfv, nttb200_u64 *c, const nttb200_u64 *pk, int pk_per_item, const nttb200_u64 *m,
+                                    unsigned batch, nttb200_u64 nonce0, void *stream);
+/* decryption_rns bfv_decryption.cuh:76; m_out[batch][n]; c1 of every item is overwritten (as in the reference) */
+NTTB200_API int nttb200_bfv_decrypt(nttb200_bfv *bfv, nttb200_u64 *m_out, nttb200_u64 *c, const nttb200_u64 *sk, int sk_per_item,
+                                    unsigned batch, void *stream);
+
+/* The reference's single-item calls, stateless (tables and constant arrays are the caller's device buffers;
+ * unused reference parameters are dropped).  Scratch: `in` as in the reference; the first n (keygen) / 2n (encrypt)
+ * 32-bit words of `temp` / `e` receive the signed gaussian draws instead of r*n residues. */
+NTTB200_API int nttb200_ref_keygen_rns(unsigned char *in, unsigned q_amount, unsigned n, nttb200_u64 *secret_key, nttb200_u64 *public_key,
+                                       nttb200_u64 *temp, const nttb200_u64 *psi_table, const nttb200_u64 *psiinv_table,
+                                       const nttb200_u64 *q_dev, const nttb200_u64 *mu_dev, const unsigned *qbit_dev, void *stream);
+NTTB200_API int nttb200_ref_encryption_rns(nttb200_u64 *c, const nttb200_u64 *public_key, unsigned char *in, nttb200_u64 *e, unsigned n,
+                                           const nttb200_u64 *psi_table, const nttb200_u64 *psiinv_table, const nttb200_u64 *m_poly,
+                                           const nttb200_u64 *qi_div_t_dev, nttb200_u64 t, unsigned q_amount, const nttb200_u64 *q_dev,
+                                           const nttb200_u64 *mu_dev, const unsigned *qbit_dev, const nttb200_u64 *inv_q_last_mod_q_dev,
+                                           void *stream);
+/* q_amount = limbs after the drop; the plaintext lands at c + n*(q_amount-1) as in the reference (demo.cu:299) */
+NTTB200_API int nttb200_ref_decryption_rns(nttb200_u64 *c, const nttb200_u64 *secret_key, const nttb200_u64 *psi_table,
+                                           const nttb200_u64 *psiinv_table, unsigned n, unsigned q_amount,
+                                           const nttb200_u64 *base_change_matrix_dev, nttb200_u64 t, nttb200_u64 gamma, nttb200_u64 mu_gamma,
+                                           int gamma_bits, nttb200_u64 neg_inv_t, nttb200_u64 neg_inv_gamma, nttb200_u64 gamma_div_2,
+                                           const nttb200_u64 *q_dev, const nttb200_u64 *mu_dev, const unsigned *qbit_dev,
+                                           const nttb200_u64 *inv_punctured_q_dev, const nttb200_u64 *prod_t_gamma_mod_q_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,294 @@
+// bfv.cu -- BFV keygen / encrypt / decrypt orchestration (replaces bfv_keygen.cuh:95-151 keygen_rns,
+// bfv_encryption.cuh:223-290 encryption_rns, bfv_decryption.cuh:76-138 decryption_rns and the constant derivation
+// every reference driver repeats, demo.cu:62-264).
+//
+// One implementation serves two front ends:
+//   * nttb200_bfv_*      : context-based and BATCHED (item k = Salsa20 nonce nonce0 + k), Shoup NTT on context tables;
+//   * nttb200_ref_*_rns  : the reference's single-item calls with the reference's own tables / constant arrays,
+//                          stateless Barrett NTT (what include/dropin/bfv_*.cuh forwards to).
+// Launch counts (any batch size): keygen 10, encrypt 9, decrypt 6 kernels on ONE stream -- the reference issues
+// 13 / 16 / 18 per item, creates r streams and mallocs inside decryption_rns, and races dec_round against mod_t.
+#include "internal.h"
+#include "bfv_kernels.cuh"
+
+#include <cmath>
+
+using namespace nttb200;
+typedef unsigned __int128 u128;
+
+namespace nttb200 {
+dim3 grid_for(size_t total, int threads);
+SalsaKey default_key();
+}
+
+struct nttb200_bfv {
+    nttb200_ctx *ctx = nullptr;
+    unsigned n = 0, r = 0;            // all limbs; rp = r - 1 after the modulus switch
+    u64 t = 0, gamma = 0, mu_gamma = 0, gamma_div_2 = 0, neg_inv_t = 0, neg_inv_gamma = 0;
+    int gamma_bits = 0;
+    // device constant arrays
+    u64 *inv_q_last_mod_q = nullptr, *qi_div_t = nullptr, *prod_t_gamma_mod_q = nullptr, *inv_punctured_q = nullptr, *bcm = nullptr;
+    // grow-only scratch: keystream and gaussian draws
+    unsigned char *ks = nullptr; size_t ks_bytes = 0;
+    int *es = nullptr; size_t es_count = 0;
+};
+
+static u64 h_modpow(u64 a, u64 e, u64 m)
+{
+    u64 r = 1 % m; a %= m;
+    while (e) { if (e & 1) r = (u64)((u128)r * a % m); a = (u64)((u128)a * a % m); e >>= 1; }
+    return r;
+}
+// the reference's modinv128(a, m) = a^(m-2) mod m (helper.h:52-56), also applied to the non-prime t (demo.cu:109)
+static u64 h_modinv_fermat(u64 a, u64 m) { return h_modpow(a, m - 2, m); }
+
+struct Pipe {                 // everything one pipeline run needs, independent of the front end
+    unsigned n, logn, r;
+    LimbArrays L;
+    const u64 *qi_div_t;
+    // NTT flavour
+    int policy_fwd, policy_inv;
+    const u64 *psi, *psiinv, *psi_s, *psiinv_s;
+    const LimbConst *lc;
+    int use_tma;
+    cudaStream_t st;
+};
+
+static int pipe_ntt(const Pipe &P, bool inverse, u64 *a, unsigned num, unsigned division, unsigned group_polys, size_t group_stride)
+{
+    NttArgsHost h{a, inverse ? P.psiinv : P.psi, inverse ? P.psiinv_s : P.psi_s, P.lc, P.L.q, P.L.mu, P.L.qbit, 0, 0, 0, num, division, P.use_tma,
+                  group_polys, group_stride};
+    const int pol = inverse ? P.policy_inv : P.policy_fwd;
+    if (pol != kPolicyBarrett) { h.qv = nullptr; h.muv = nullptr; h.qbitv = nullptr; }
+    return launch_ntt(inverse, pol, P.logn, h, P.st);
+}
+
+#define KCHECK() do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return (int)e__; } while (0)
+#define NTTB200_TRY(x) do { int r__ = (x); if (r__) return r__; } while (0)
+
+// keygen: in = keystream scratch ([batch] streams of in_stride bytes), es = n ints per item
+static int run_keygen(const Pipe &P, unsigned char *in, size_t in_stride, int *es, u64 *sk, u64 *pk, unsigned batch, u64 nonce0)
+{
+    const unsigned n = P.n, r = P.r;
+    const size_t rn = (size_t)r * n;
+    const u64 nblk = (9 * rn + 4 * (size_t)n) / 64;                                   // bfv_keygen.cuh:99
+    k_salsa20_keystream<<<grid_for(nblk * batch, 256), 256, 0, P.st>>>(in, nblk, (u64)batch, in_stride, default_key(), nonce0);
+    k_keygen_sample<<<grid_for((size_t)batch * n, 256), 256, 0, P.st>>>(in, in_stride, sk, pk, es, n, r, batch, P.L.q);   // :120-122
+    KCHECK();
+    NTTB200_TRY(pipe_ntt(P, false, sk, batch * r, r, 0, 0));                               // :129
+    k_keygen_mul<<<grid_for((size_t)batch * rn, 256), 256, 0, P.st>>>(pk, sk, n, r, batch, P.L);                      // :132
+    KCHECK();
+    NTTB200_TRY(pipe_ntt(P, true, pk, batch * r, r, r, 2 * rn));                           // :133
+    k_keygen_add_negate<<<grid_for((size_t)batch * rn, 256), 256, 0, P.st>>>(pk, es, n, r, batch, P.L);               // :144
+    KCHECK();
+    NTTB200_TRY(pipe_ntt(P, false, pk, batch * r, r, r, 2 * rn));                          // :145
+    return 0;
+}
+
+static int run_encrypt(const Pipe &P, unsigned char *in, size_t in_stride, int *es, u64 *c, const u64 *pk, size_t pk_stride, const u64 *m,
+                       size_t m_stride, u64 t, unsigned batch, u64 nonce0)
+{
+    const unsigned n = P.n, r = P.r;
+    const size_t rn = (size_t)r * n;
+    const u64 nblk = (9 * (size_t)n) / 64;                                                // bfv_encryption.cuh:228
+    k_salsa20_keystream<<<grid_for(nblk * batch, 256), 256, 0, P.st>>>(in, nblk, (u64)batch, in_stride, default_key(), nonce0);
+    k_encrypt_sample<<<grid_for((size_t)batch * n, 256), 256, 0, P.st>>>(in, in_stride, c, es, n, r, batch, P.L.q);       // :247
+    KCHECK();
+    NTTB200_TRY(pipe_ntt(P, false, c, batch * r, r, r, 2 * rn));                           // :268 (once, not twice)
+    k_encrypt_mul<<<grid_for((size_t)batch * rn, 256), 256, 0, P.st>>>(c, pk, pk_stride, n, r, batch, P.L);              // :270
+    KCHECK();
+    NTTB200_TRY(pipe_ntt(P, true, c, batch * 2 * r, r, 0, 0));                             // :271
+    k_encrypt_epilogue<<<grid_for((size_t)batch * 2 * n, 256), 256, 0, P.st>>>(c, es, m, m_stride, n, r, batch, t, P.qi_div_t, P.L);   // :280-289
+    KCHECK();
+    return 0;
+}
+
+// c: items of [2][rp+1][n]; the plaintext of item k goes to out + k*out_stride
+static int run_decrypt(const Pipe &P, u64 *c, const u64 *sk, size_t sk_stride, u64 *out, size_t out_stride, const DecryptConsts &D, unsigned batch)
+{
+    const unsigned n = P.n, rp = D.rp;
+    const size_t item = (size_t)2 * (rp + 1) * n, c1_off = (size_t)(rp + 1) * n;
+    NTTB200_TRY(pipe_ntt(P, false, c + c1_off, batch * rp, rp, rp, item));                 // bfv_decryption.cuh:98
+    k_decrypt_mul<<<grid_for((size_t)batch * rp * n, 256), 256, 0, P.st>>>(c, item, c1_off, sk, sk_stride, n, rp, batch, P.L);   // :100
+    KCHECK();
+    NTTB200_TRY(pipe_ntt(P, true, c + c1_off, batch * rp, rp, rp, item));                  // :101
+    k_decrypt_epilogue<<<grid_for((size_t)batch * n, 256), 256, 0, P.st>>>(c, item, c1_off, out, out_stride, n, batch, D, P.L);   // :103-137
+    KCHECK();
+    return 0;
+}
+
+static unsigned ilog2u(unsigned n) { unsigned l = 0; while ((1u << l) < n) l++; return l; }
+
+static Pipe pipe_from_bfv(const nttb200_bfv *b, cudaStream_t st)
+{
+    const nttb200_ctx *c = b->ctx;
+    Pipe P;
+    P.n = b->n; P.logn = c->logn; P.r = b->r;
+    P.L = LimbArrays{c->q_dev, c->mu_dev, c->qbit_dev, b->inv_q_last_mod_q, b->inv_punctured_q, b->prod_t_gamma_mod_q};
+    P.qi_div_t = b->qi_div_t;
+    P.policy_fwd = c->lazy_ok ? kPolicyShoupLazy : kPolicyShoup; P.policy_inv = kPolicyShoup;
+    P.psi = c->psi; P.psiinv = c->psiinv; P.psi_s = c->psi_s; P.psiinv_s = c->psiinv_s; P.lc = c->lc;
+    P.use_tma = c->use_tma; P.st = st;
+    return P;
+}
+
+static int ensure_scratch(nttb200_bfv *b, size_t ks_bytes, size_t es_count)
+{
+    if (b->ks_bytes < ks_bytes) {
+        if (b->ks) cudaFree(b->ks);
+        b->ks = nullptr; b->ks_bytes = 0;
+        NTTB200_CHECK(cudaMalloc(&b->ks, ks_bytes));
+        b->ks_bytes = ks_bytes;
+    }
+    if (b->es_count < es_count) {
+        if (b->es) cudaFree(b->es);
+        b->es = nullptr; b->es_count = 0;
+        NTTB200_CHECK(cudaMalloc(&b->es, es_count * sizeof(int)));
+        b->es_count = es_count;
+    }
+    return 0;
+}
+
+extern "C" {
+
+int nttb200_bfv_create(nttb200_bfv **out, unsigned n, unsigned limbs, const nttb200_u64 *q, const nttb200_u64 *psi_roots, nttb200_u64 t,
+                       nttb200_u64 gamma)
+{
+    if (!out || limbs < 2 || t == 0 || (t & (t - 1)) || gamma < 3) return NTTB200_EINVAL;
+    nttb200_ctx *ctx = nullptr;
+    int rc = nttb200_ctx_create(&ctx, n, limbs, q, psi_roots);
+    if (rc) return rc;
+    nttb200_bfv *b = new nttb200_bfv();
+    b->ctx = ctx; b->n = n; b->r = limbs; b->t = t; b->gamma = gamma;
+    const unsigned r = limbs, rp = r - 1;
+    b->gamma_bits = (int)(log2((double)gamma) + 1);                                     // demo.cu:100 uses {10, 61}
+    b->gamma_div_2 = gamma >> 1;
+    b->mu_gamma = (u64)(((u128)1 << (2 * b->gamma_bits)) / gamma);                      // demo.cu:221-226
+    std::vector<u64> iql(rp), qdt(r), ptg(rp), ipq(rp), bcm(2 * rp);
+    for (unsigned i = 0; i < r; i++) qdt[i] = q[i] / t;                                 // :84-88
+    for (unsigned i = 0; i < rp; i++) iql[i] = h_modinv_fermat(q[r - 1] % q[i], q[i]);  // :75-79
+    u64 mult_t = 1, mult_g = 1;
+    for (unsigned i = 0; i < rp; i++) { mult_t = (u64)((u128)mult_t * q[i] % t); mult_g = (u64)((u128)mult_g * q[i] % gamma); }   // :103-108
+    b->neg_inv_t = t - h_modinv_fermat(mult_t, t);                                      // :109 (Fermat on t = 2^k: exact only because q_i = 1 mod t)
+    b->neg_inv_gamma = gamma - h_modinv_fermat(mult_g, gamma);                          // :110
+    for (unsigned i = 0; i < rp; i++) ptg[i] = (u64)((u128)t * gamma % q[i]);           // :118-123
+    for (unsigned i = 0; i < rp; i++) {                                                 // :229-243
+        u64 tmp = 1;
+        for (unsigned j = 0; j < rp; j++) if (j != i) tmp = (u64)((u128)tmp * q[j] % q[i]);
+        ipq[i] = h_modinv_fermat(tmp, q[i]);
+    }
+    const u64 base[2] = {t, gamma};
+    for (unsigned k = 0; k < 2; k++)                                                    // :248-264
+        for (unsigned j = 0; j < rp; j++) {
+            u64 tmp = 1;
+            for (unsigned i = 0; i < rp; i++) if (i != j) tmp = (u64)((u128)tmp * q[i] % base[k]);
+            bcm[k * rp + j] = tmp;
+        }
+    auto up = [](u64 **d, const std::vector<u64> &h) -> int {
+        NTTB200_CHECK(cudaMalloc(d, h.size() * 8));
+        NTTB200_CHECK(cudaMemcpy(*d, h.data(), h.size() * 8, cudaMemcpyHostToDevice));
+        return 0;
+    };
+    rc = up(&b->inv_q_last_mod_q, iql); if (!rc) rc = up(&b->qi_div_t, qdt); if (!rc) rc = up(&b->prod_t_gamma_mod_q, ptg);
+    if (!rc) rc = up(&b->inv_punctured_q, ipq); if (!rc) rc = up(&b->bcm, bcm);
+    if (rc) { nttb200_bfv_destroy(b); return rc; }
+    *out = b;
+    return 0;
+}
+
+void nttb200_bfv_destroy(nttb200_bfv *b)
+{
+    if (!b) return;
+    cudaFree(b->inv_q_last_mod_q); cudaFree(b->qi_div_t); cudaFree(b->prod_t_gamma_mod_q); cudaFree(b->inv_punctured_q); cudaFree(b->bcm);
+    if (b->ks) cudaFree(b->ks);
+    if (b->es) cudaFree(b->es);
+    nttb200_ctx_destroy(b->ctx);
+    delete b;
+}
+
+nttb200_ctx *nttb200_bfv_ctx(nttb200_bfv *b) { return b ? b->ctx : nullptr; }
+
+int nttb200_bfv_reserve(nttb200_bfv *b, unsigned batch)
+{
+    if (!b || !batch) return NTTB200_EINVAL;
+    const size_t rn = (size_t)b->r * b->n;
+    return ensure_scratch(b, (9 * rn + 4 * (size_t)b->n) * batch, (size_t)2 * b->n * batch);
+}
+
+int nttb200_bfv_keygen(nttb200_bfv *b, nttb200_u64 *sk, nttb200_u64 *pk, unsigned batch, nttb200_u64 nonce0, void *stream)
+{
+    if (!b || !sk || !pk || !batch) return NTTB200_EINVAL;
+    NTTB200_TRY(nttb200_bfv_reserve(b, batch));
+    const size_t rn = (size_t)b->r * b->n;
+    Pipe P = pipe_from_bfv(b, (cudaStream_t)stream);
+    return run_keygen(P, b->ks, 9 * rn + 4 * (size_t)b->n, b->es, sk, pk, batch, nonce0);
+}
+
+int nttb200_bfv_encrypt(nttb200_bfv *b, nttb200_u64 *c, const nttb200_u64 *pk, int pk_per_item, const nttb200_u64 *m, unsigned batch,
+                        nttb200_u64 nonce0, void *stream)
+{
+    if (!b || !c || !pk || !m || !batch) return NTTB200_EINVAL;
+    NTTB200_TRY(nttb200_bfv_reserve(b, batch));
+    const size_t rn = (size_t)b->r * b->n;
+    Pipe P = pipe_from_bfv(b, (cudaStream_t)stream);
+    return run_encrypt(P, b->ks, 9 * (size_t)b->n, b->es, c, pk, pk_per_item ? 2 * rn : 0, m, b->n, b->t, batch, nonce0);
+}
+
+int nttb200_bfv_decrypt(nttb200_bfv *b, nttb200_u64 *m_out, nttb200_u64 *c, const nttb200_u64 *sk, int sk_per_item, unsigned batch, void *stream)
+{
+    if (!b || !c || !sk || !m_out || !batch) return NTTB200_EINVAL;
+    Pipe P = pipe_from_bfv(b, (cudaStream_t)stream);
+    DecryptConsts D{b->t, b->gamma, b->mu_gamma, b->gamma_div_2, b->neg_inv_t, b->neg_inv_gamma, b->gamma_bits, b->r - 1, b->bcm};
+    return run_decrypt(P, c, sk, sk_per_item ? (size_t)b->r * b->n : 0, m_out, b->n, D, batch);
+}
+
+// ---- the reference's single-item calls (stateless; constants come from the caller's device arrays) -------------------
+static Pipe pipe_ref(unsigned n, unsigned r, const nttb200_u64 *psi, const nttb200_u64 *psiinv, const nttb200_u64 *q_dev, const nttb200_u64 *mu_dev,
+                     const unsigned *qbit_dev, const nttb200_u64 *inv_q_last, const nttb200_u64 *inv_punct, const nttb200_u64 *ptg,
+                     const nttb200_u64 *qi_div_t, cudaStream_t st)
+{
+    Pipe P;
+    P.n = n; P.logn = ilog2u(n); P.r = r;
+    P.L = LimbArrays{q_dev, mu_dev, qbit_dev, inv_q_last, inv_punct, ptg};
+    P.qi_div_t = qi_div_t;
+    P.policy_fwd = P.policy_inv = kPolicyBarrett;
+    P.psi = psi; P.psiinv = psiinv; P.psi_s = P.psiinv_s = nullptr; P.lc = nullptr;
+    P.use_tma = get_tma_default(); P.st = st;
+    return P;
+}
+
+// keygen_rns bfv_keygen.cuh:95.  `in`: 9*r*n + 4*n bytes; `temp`: r*n u64 (its first n*4 bytes receive the gaussian draws).
+int nttb200_ref_keygen_rns(unsigned char *in, unsigned q_amount, unsigned n, nttb200_u64 *secret_key, nttb200_u64 *public_key, nttb200_u64 *temp,
+                           const nttb200_u64 *psi_table, const nttb200_u64 *psiinv_table, const nttb200_u64 *q_dev, const nttb200_u64 *mu_dev,
+                           const unsigned *qbit_dev, void *stream)
+{
+    if (!in || !secret_key || !public_key || !temp || !q_amount || (n & (n - 1))) return NTTB200_EINVAL;
+    Pipe P = pipe_ref(n, q_amount, psi_table, psiinv_table, q_dev, mu_dev, qbit_dev, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+    return run_keygen(P, in, 0, reinterpret_cast<int *>(temp), secret_key, public_key, 1, 0);
+}
+// encryption_rns bfv_encryption.cuh:223.  `in`: 9*n bytes; `e`: 2*r*n u64 (its first 2*n*4 bytes receive the draws).
+int nttb200_ref_encryption_rns(nttb200_u64 *c, const nttb200_u64 *public_key, unsigned char *in, nttb200_u64 *e, unsigned n,
+                               const nttb200_u64 *psi_table, const nttb200_u64 *psiinv_table, const nttb200_u64 *m_poly,
+                               const nttb200_u64 *qi_div_t_dev, nttb200_u64 t, unsigned q_amount, const nttb200_u64 *q_dev,
+                               const nttb200_u64 *mu_dev, const unsigned *qbit_dev, const nttb200_u64 *inv_q_last_mod_q_dev, void *stream)
+{
+    if (!c || !public_key || !in || !e || !m_poly || q_amount < 2 || (n & (n - 1))) return NTTB200_EINVAL;
+    Pipe P = pipe_ref(n, q_amount, psi_table, psiinv_table, q_dev, mu_dev, qbit_dev, inv_q_last_mod_q_dev, nullptr, nullptr, qi_div_t_dev,
+                      (cudaStream_t)stream);
+    return run_encrypt(P, in, 0, reinterpret_cast<int *>(e), c, public_key, 0, m_poly, 0, t, 1, 0);
+}
+// decryption_rns bfv_decryption.cuh:76.  q_amount = limbs after the drop; plaintext lands at c + n*(q_amount-1) (demo.cu:299).
+int nttb200_ref_decryption_rns(nttb200_u64 *c, const nttb200_u64 *secret_key, const nttb200_u64 *psi_table, const nttb200_u64 *psiinv_table,
+                               unsigned n, unsigned q_amount, const nttb200_u64 *base_change_matrix_dev, nttb200_u64 t, nttb200_u64 gamma,
+                               nttb200_u64 mu_gamma, int gamma_bits, nttb200_u64 neg_inv_t, nttb200_u64 neg_inv_gamma, nttb200_u64 gamma_div_2,
+                               const nttb200_u64 *q_dev, const nttb200_u64 *mu_dev, const unsigned *qbit_dev,
+                               const nttb200_u64 *inv_punctured_q_dev, const nttb200_u64 *prod_t_gamma_mod_q_dev, void *stream)
+{
+    if (!c || !secret_key || !q_amount || (n & (n - 1))) return NTTB200_EINVAL;
+    Pipe P = pipe_ref(n, q_amount + 1, psi_table, psiinv_table, q_dev, mu_dev, qbit_dev, nullptr, inv_punctured_q_dev, prod_t_gamma_mod_q_dev,
+                      nullptr, (cudaStream_t)stream);
+    DecryptConsts D{t, gamma, mu_gamma, gamma_div_2, neg_inv_t, neg_inv_gamma, gamma_bits, q_amount, base_change_matrix_dev};
+    return run_decrypt(P, c, secret_key, 0, c + (size_t)n * (q_amount - 1), 0, D, 1);
+}
+
+}  // extern "C"

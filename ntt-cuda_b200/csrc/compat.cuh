@@ -33,11 +33,13 @@ struct uint4 { u32 x, y, z, w; };
 float emu_normcdfinvf(float x);   // double-precision stand-in; GPU parity for this op is pinned on the GPU
 #define normcdfinvf emu_normcdfinvf
 #define NTT_DYN_SMEM(name) unsigned char *name = emu_dyn_smem
+#define NTT_KERNEL static
 #define NTT_UNROLL _Pragma("GCC unroll 32")
 #else
 // ---------------------------------------------------------------------------------------------
 #include <cuda_runtime.h>
 #define NTT_RESTRICT __restrict__
 #define NTT_DYN_SMEM(name) extern __shared__ __align__(1024) unsigned char name[]
+#define NTT_KERNEL static __global__   /* header-defined kernels: internal linkage per translation unit */
 #define NTT_UNROLL _Pragma("unroll")
 #endif

@@ -113,3 +113,101 @@ int emu_ntt(int inverse, int barrett, int use_tma, int logn, u64 *a, const u64 *
 }
 
 extern "C" __attribute__((visibility("default"))) unsigned emu_sizeof_limbconst() { return (unsigned)sizeof(LimbConst); }
+
+// ---- BFV pipelines on the emulator: same kernels, same order as csrc/bfv.cu ---------------------------------------------
+#include "../bfv_kernels.cuh"
+
+namespace {
+struct EmuRing {
+    unsigned n, logn, r;
+    const u64 *q, *mu; const u32 *qbit;
+    const u64 *psi, *psiinv, *psi_s, *psiinv_s; const LimbConst *lc;
+    int barrett;    // 1: stateless Barrett NTT, 0: Shoup (lazy forward)
+};
+template <class F> void ew(F &&f) { emu_dim3 g; g.x = 3; emu_launch(g, 64, 0, f); }
+int ring_ntt(const EmuRing &R, bool inv, u64 *a, unsigned num, unsigned division, unsigned gp, size_t gs)
+{
+    return emu_ntt(inv, R.barrett ? 1 : (inv ? 0 : 2), 1, (int)R.logn, a, inv ? R.psiinv : R.psi, inv ? R.psiinv_s : R.psi_s, R.lc, R.q, R.mu, R.qbit,
+                   num, division, gp, gs);
+}
+}  // namespace
+
+#define EXPORT extern "C" __attribute__((visibility("default")))
+
+EXPORT int emu_bfv(int op, unsigned n, unsigned r, const u64 *q, const u64 *mu, const u32 *qbit, const u64 *psi, const u64 *psiinv,
+                   const u64 *psi_s, const u64 *psiinv_s, const LimbConst *lc, int barrett,
+                   // buffers
+                   unsigned char *in, int *es, u64 *sk, u64 *pk, u64 *c, const u64 *m, u64 *out, unsigned batch, u64 nonce0,
+                   // constants
+                   const u64 *inv_q_last, const u64 *qi_div_t, const u64 *ptg, const u64 *ipq, const u64 *bcm, u64 t, u64 gamma, u64 mu_gamma,
+                   int gamma_bits, u64 neg_inv_t, u64 neg_inv_gamma, int per_item_keys)
+{
+    EmuRing R{n, 0, r, q, mu, qbit, psi, psiinv, psi_s, psiinv_s, lc, barrett};
+    while ((1u << R.logn) < n) R.logn++;
+    LimbArrays L{q, mu, qbit, inv_q_last, ipq, ptg};
+    const size_t rn = (size_t)r * n;
+    SalsaKey key; for (int i = 0; i < 8; i++) key.k[i] = 0x01010101u;
+    if (op == 0) {          // keygen
+        const size_t stride = 9 * rn + 4 * (size_t)n; const u64 nblk = stride / 64;
+        ew([&] { k_salsa20_keystream(in, nblk, (u64)batch, stride, key, nonce0); });
+        ew([&] { k_keygen_sample(in, stride, sk, pk, es, n, r, batch, q); });
+        ring_ntt(R, false, sk, batch * r, r, 0, 0);
+        ew([&] { k_keygen_mul(pk, sk, n, r, batch, L); });
+        ring_ntt(R, true, pk, batch * r, r, r, 2 * rn);
+        ew([&] { k_keygen_add_negate(pk, es, n, r, batch, L); });
+        ring_ntt(R, false, pk, batch * r, r, r, 2 * rn);
+    } else if (op == 1) {   // encrypt
+        const size_t stride = 9 * (size_t)n; const u64 nblk = stride / 64;
+        ew([&] { k_salsa20_keystream(in, nblk, (u64)batch, stride, key, nonce0); });
+        ew([&] { k_encrypt_sample(in, stride, c, es, n, r, batch, q); });
+        ring_ntt(R, false, c, batch * r, r, r, 2 * rn);
+        ew([&] { k_encrypt_mul(c, pk, per_item_keys ? 2 * rn : 0, n, r, batch, L); });
+        ring_ntt(R, true, c, batch * 2 * r, r, 0, 0);
+        ew([&] { k_encrypt_epilogue(c, es, m, (size_t)n, n, r, batch, t, qi_div_t, L); });
+    } else {                // decrypt (r = all limbs)
+        const unsigned rp = r - 1;
+        const size_t item = 2 * rn, c1_off = rn;
+        DecryptConsts D{t, gamma, mu_gamma, gamma >> 1, neg_inv_t, neg_inv_gamma, gamma_bits, rp, bcm};
+        ring_ntt(R, false, c + c1_off, batch * rp, rp, rp, item);
+        ew([&] { k_decrypt_mul(c, item, c1_off, sk, per_item_keys ? rn : 0, n, rp, batch, L); });
+        ring_ntt(R, true, c + c1_off, batch * rp, rp, rp, item);
+        ew([&] { k_decrypt_epilogue(c, item, c1_off, out, (size_t)n, n, batch, D, L); });
+    }
+    return 0;
+}
+
+// stand-alone kernels: op codes in tests/emu.py
+EXPORT int emu_pointwise(int op, u64 *a, const u64 *b, u64 *c, size_t n, u64 s0, u64 s1, u64 s2, int i0, unsigned u0, unsigned u1,
+                         const u64 *qv, const u64 *muv, const u32 *qbitv, const u64 *aux)
+{
+    LimbArrays L{qv, muv, qbitv, aux, aux, aux};
+    switch (op) {
+    case 0: ew([&] { k_barrett(c, a, b, n, s0, s1, i0); }); break;
+    case 1: ew([&] { k_barrett_int(a, s2, n, s0, s1, i0); }); break;
+    case 2: ew([&] { k_mod_t(a, s2, n, s0); }); break;
+    case 3: ew([&] { k_poly_add(a, b, n, s0); }); break;
+    case 4: ew([&] { k_poly_add_integer(a, s2, n, s0); }); break;
+    case 5: ew([&] { k_poly_sub(a, b, n, s0); }); break;
+    case 6: ew([&] { k_poly_negate(a, n, s0); }); break;
+    case 7: ew([&] { k_barrett_batch(c, a, b, u0, n, u1, L); }); break;
+    case 8: ew([&] { k_fast_convert_t(a, c, s0, b, u0, n); }); ew([&] { k_fast_convert_gamma(a, c, s1, b, u0, i0, s2, n); }); break;
+    case 9: ew([&] { k_dec_round(a, c, s0, s1, s2, n); }); break;
+    case 10: ew([&] { k_divide_and_round_q_last_inplace_loop(a, b, n, s0, s2, aux[0], s1, i0); }); break;
+    case 11: ew([&] { k_poly_add_negate_xq(a, b, u0, n, L); }); break;
+    default: return 1;
+    }
+    return 0;
+}
+EXPORT int emu_sampling(int op, const unsigned char *in, u64 *out, u64 *out2, size_t n, unsigned u0, const u64 *q, u64 nonce, size_t stride)
+{
+    SalsaKey key; for (int i = 0; i < 8; i++) key.k[i] = 0x01010101u;
+    switch (op) {
+    case 0: ew([&] { k_salsa20_keystream((unsigned char *)out, (u64)n, (u64)u0, stride, key, nonce); }); break;
+    case 1: ew([&] { k_ternary_dist_xq(in, out, u0, n, q); }); break;
+    case 2: ew([&] { k_uniform_dist_xq(in, out, u0, n, q); }); break;
+    case 3: ew([&] { k_convert_ternary(in, out, n, q[0]); }); break;
+    case 4: ew([&] { k_convert_range((const u64 *)in, out, n, q[0]); }); break;
+    default: return 1;
+    }
+    return 0;
+}

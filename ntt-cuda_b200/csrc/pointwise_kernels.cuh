@@ -24,43 +24,43 @@ struct LimbArrays {
 
 // ---- single-limb kernels (explicit q, mu, qbit) ---------------------------------------------------------------------
 // barrett poly_arithmetic.cuh:9-34 (c == a), barrett_3param (c != a)
-__global__ void k_barrett(u64 *c, const u64 *a, const u64 *b, size_t n, u64 q, u64 mu, int qbit)
+NTT_KERNEL void k_barrett(u64 *c, const u64 *a, const u64 *b, size_t n, u64 q, u64 mu, int qbit)
 {
     NTT_GRID_STRIDE(i, n) c[i] = barrett_ref(a[i], b[i], q, mu, qbit);
 }
 // barrett_int poly_arithmetic.cuh:100-126
-__global__ void k_barrett_int(u64 *a, u64 b, size_t n, u64 q, u64 mu, int qbit)
+NTT_KERNEL void k_barrett_int(u64 *a, u64 b, size_t n, u64 q, u64 mu, int qbit)
 {
     NTT_GRID_STRIDE(i, n) a[i] = barrett_ref(a[i], b, q, mu, qbit);
 }
 // mod_t poly_arithmetic.cuh:128-141 (the mask is a 32-bit unsigned, :139)
-__global__ void k_mod_t(u64 *a, u64 b, size_t n, u64 t)
+NTT_KERNEL void k_mod_t(u64 *a, u64 b, size_t n, u64 t)
 {
     const u32 mask = (u32)(t - 1);
     NTT_GRID_STRIDE(i, n) a[i] = (a[i] * b) & (u64)mask;
 }
 // poly_add poly_arithmetic.cuh:143-153
-__global__ void k_poly_add(u64 *a, const u64 *b, size_t n, u64 q)
+NTT_KERNEL void k_poly_add(u64 *a, const u64 *b, size_t n, u64 q)
 {
     NTT_GRID_STRIDE(i, n) { u64 r = a[i] + b[i]; if (r > q) r -= q; a[i] = r; }
 }
 // poly_add_integer poly_arithmetic.cuh:155-165
-__global__ void k_poly_add_integer(u64 *a, u64 b, size_t n, u64 q)
+NTT_KERNEL void k_poly_add_integer(u64 *a, u64 b, size_t n, u64 q)
 {
     NTT_GRID_STRIDE(i, n) { u64 r = a[i] + b; if (r > q) r -= q; a[i] = r; }
 }
 // poly_sub poly_arithmetic.cuh:167-178: adds q when a < b and never subtracts b (reference behaviour, kept)
-__global__ void k_poly_sub(u64 *a, const u64 *b, size_t n, u64 q)
+NTT_KERNEL void k_poly_sub(u64 *a, const u64 *b, size_t n, u64 q)
 {
     NTT_GRID_STRIDE(i, n) { u64 r = a[i]; if (r < b[i]) r += q; a[i] = r; }
 }
 // poly_negate poly_arithmetic.cuh:332-338
-__global__ void k_poly_negate(u64 *a, size_t n, u64 q)
+NTT_KERNEL void k_poly_negate(u64 *a, size_t n, u64 q)
 {
     NTT_GRID_STRIDE(i, n) { u64 r = q - a[i]; a[i] = r * (u64)(r != q); }
 }
 // divide_and_round_q_last_inplace_loop poly_arithmetic.cuh:180-214
-__global__ void k_divide_and_round_q_last_inplace_loop(u64 *input_poly, const u64 *rns_poly_minus1, size_t n, u64 base_q_i, u64 half_mod,
+NTT_KERNEL void k_divide_and_round_q_last_inplace_loop(u64 *input_poly, const u64 *rns_poly_minus1, size_t n, u64 base_q_i, u64 half_mod,
                                                        u64 inv_q_last_mod_q_i, u64 mu, int qbit)
 {
     NTT_GRID_STRIDE(i, n) {
@@ -74,7 +74,7 @@ __global__ void k_divide_and_round_q_last_inplace_loop(u64 *input_poly, const u6
     }
 }
 // fast_convert_array_kernel_t poly_arithmetic.cuh:217-234
-__global__ void k_fast_convert_t(const u64 *input_poly, u64 *result_poly, u64 t, const u64 *bcm, unsigned q_amount, size_t n)
+NTT_KERNEL void k_fast_convert_t(const u64 *input_poly, u64 *result_poly, u64 t, const u64 *bcm, unsigned q_amount, size_t n)
 {
     const u32 mask = (u32)(t - 1);
     NTT_GRID_STRIDE(k, n) {
@@ -84,7 +84,7 @@ __global__ void k_fast_convert_t(const u64 *input_poly, u64 *result_poly, u64 t,
     }
 }
 // fast_convert_array_kernel_gamma poly_arithmetic.cuh:237-251 (writes result_poly[k + n])
-__global__ void k_fast_convert_gamma(const u64 *input_poly, u64 *result_poly, u64 gamma, const u64 *bcm, unsigned q_amount, int gamma_bits,
+NTT_KERNEL void k_fast_convert_gamma(const u64 *input_poly, u64 *result_poly, u64 gamma, const u64 *bcm, unsigned q_amount, int gamma_bits,
                                      u64 mu_gamma, size_t n)
 {
     NTT_GRID_STRIDE(k, n) {
@@ -97,7 +97,7 @@ __global__ void k_fast_convert_gamma(const u64 *input_poly, u64 *result_poly, u6
     }
 }
 // dec_round_kernel poly_arithmetic.cuh:253-263
-__global__ void k_dec_round(const u64 *input_poly, u64 *result_poly, u64 t, u64 gamma, u64 gamma_div_2, size_t n)
+NTT_KERNEL void k_dec_round(const u64 *input_poly, u64 *result_poly, u64 t, u64 gamma, u64 gamma_div_2, size_t n)
 {
     const u64 mask = t - 1;
     NTT_GRID_STRIDE(i, n) {
@@ -108,7 +108,7 @@ __global__ void k_dec_round(const u64 *input_poly, u64 *result_poly, u64 t, u64 
 
 // ---- multi-limb kernels: element i of a [polys][n] array belongs to limb (i / n) % division ----------------------
 // barrett_batch poly_arithmetic.cuh:36-66 (c == a) / barrett_batch_3param :68-98
-__global__ void k_barrett_batch(u64 *c, const u64 *a, const u64 *b, unsigned n, size_t total, unsigned division, LimbArrays L)
+NTT_KERNEL void k_barrett_batch(u64 *c, const u64 *a, const u64 *b, unsigned n, size_t total, unsigned division, LimbArrays L)
 {
     NTT_GRID_STRIDE(i, total) {
         const unsigned l = (unsigned)((i / n) % division);
@@ -116,7 +116,7 @@ __global__ void k_barrett_batch(u64 *c, const u64 *a, const u64 *b, unsigned n, 
     }
 }
 // poly_add_negate_xq bfv_keygen.cuh:81-93: a = -(a + b) mod q   (limb = i / n)
-__global__ void k_poly_add_negate_xq(u64 *a, const u64 *b, unsigned n, size_t total, LimbArrays L)
+NTT_KERNEL void k_poly_add_negate_xq(u64 *a, const u64 *b, unsigned n, size_t total, LimbArrays L)
 {
     NTT_GRID_STRIDE(i, total) {
         const u64 q = L.q[i / n];
@@ -127,7 +127,7 @@ __global__ void k_poly_add_negate_xq(u64 *a, const u64 *b, unsigned n, size_t to
     }
 }
 // poly_add_xq bfv_encryption.cuh:180-191: c += e on both halves ([2][q_amount][n]); `>` quirk
-__global__ void k_poly_add_xq(u64 *c, const u64 *e, unsigned n, unsigned q_amount, LimbArrays L)
+NTT_KERNEL void k_poly_add_xq(u64 *c, const u64 *e, unsigned n, unsigned q_amount, LimbArrays L)
 {
     const size_t half = (size_t)n * q_amount;
     NTT_GRID_STRIDE(i, 2 * half) {
@@ -138,7 +138,7 @@ __global__ void k_poly_add_xq(u64 *c, const u64 *e, unsigned n, unsigned q_amoun
     }
 }
 // divide_and_round_q_last_inplace_add_x2 bfv_encryption.cuh:111-125: last limb of c0 and c1 += floor(q_last / 2)
-__global__ void k_divide_and_round_q_last_inplace_add_x2(u64 *c, unsigned n, unsigned q_amount, LimbArrays L)
+NTT_KERNEL void k_divide_and_round_q_last_inplace_add_x2(u64 *c, unsigned n, unsigned q_amount, LimbArrays L)
 {
     const u64 last = L.q[q_amount - 1], half = last >> 1;
     NTT_GRID_STRIDE(i, (size_t)2 * n) {
@@ -149,7 +149,7 @@ __global__ void k_divide_and_round_q_last_inplace_add_x2(u64 *c, unsigned n, uns
     }
 }
 // divide_and_round_q_last_inplace_loop_xq bfv_encryption.cuh:127-178: limbs i < r-1 of c0 and c1
-__global__ void k_divide_and_round_q_last_inplace_loop_xq(u64 *c, unsigned q_amount, unsigned n, LimbArrays L)
+NTT_KERNEL void k_divide_and_round_q_last_inplace_loop_xq(u64 *c, unsigned q_amount, unsigned n, LimbArrays L)
 {
     const u64 half_last = L.q[q_amount - 1] >> 1;
     const size_t per = (size_t)n * (q_amount - 1);
@@ -171,7 +171,7 @@ __global__ void k_divide_and_round_q_last_inplace_loop_xq(u64 *c, unsigned q_amo
     }
 }
 // weird_m_stuff bfv_encryption.cuh:193-212: c0_i += m * floor(q_i / t) + round-fix, i < r-1
-__global__ void k_weird_m_stuff(const u64 *m_poly, u64 *c0, u64 t, const u64 *qi_div_t, const u64 *q_array, unsigned q_amount, unsigned n)
+NTT_KERNEL void k_weird_m_stuff(const u64 *m_poly, u64 *c0, u64 t, const u64 *qi_div_t, const u64 *q_array, unsigned q_amount, unsigned n)
 {
     NTT_GRID_STRIDE(j, (size_t)n) {
         const u64 m = m_poly[j];
@@ -183,7 +183,7 @@ __global__ void k_weird_m_stuff(const u64 *m_poly, u64 *c0, u64 t, const u64 *qi
     }
 }
 // poly_add_xq_d bfv_decryption.cuh:13-23: c1_i += c0_i (c1 at c + n * q_amount_plus1), `>` quirk
-__global__ void k_poly_add_xq_d(u64 *c, unsigned n, unsigned rp, unsigned q_amount_plus1, LimbArrays L)
+NTT_KERNEL void k_poly_add_xq_d(u64 *c, unsigned n, unsigned rp, unsigned q_amount_plus1, LimbArrays L)
 {
     NTT_GRID_STRIDE(i, (size_t)n * rp) {
         const u64 q = L.q[i / n];
@@ -193,7 +193,7 @@ __global__ void k_poly_add_xq_d(u64 *c, unsigned n, unsigned rp, unsigned q_amou
     }
 }
 // poly_mul_int_xq_prodtgamma / _invpq bfv_decryption.cuh:25-57: c_i *= k_i  (k = prod_t_gamma_mod_q or inv_punctured_q)
-__global__ void k_poly_mul_int_xq(u64 *c, unsigned n, size_t total, const u64 *k, LimbArrays L)
+NTT_KERNEL void k_poly_mul_int_xq(u64 *c, unsigned n, size_t total, const u64 *k, LimbArrays L)
 {
     NTT_GRID_STRIDE(i, total) {
         const unsigned l = (unsigned)(i / n);

@@ -157,3 +157,171 @@ def inverseNTT(device_a, n, stream, q, mu, bit_length, psiinv_powers):
     """ntt_60bit.cuh:350"""
     check(lib().nttb200_ref_inverse_ntt(vp(ptr(device_a)), C.c_uint(n), vp(_stream(stream)), u64(q), u64(mu), C.c_int(bit_length),
                                         vp(ptr(psiinv_powers))))
+
+
+# ---- coefficient-wise kernels (poly_arithmetic.cuh) ------------------------------------------------------------------------
+def _call(name, *args):
+    check(getattr(lib(), name)(*args))
+
+
+def barrett(a, b, n, q, mu, qbit, stream=None):
+    """barrett<<<n/256,256>>>(a, b, q, mu, qbit), poly_arithmetic.cuh:9"""
+    _call("nttb200_barrett", vp(ptr(a)), vp(ptr(b)), C.c_uint(n), u64(q), u64(mu), C.c_int(qbit), vp(_stream(stream)))
+
+
+def barrett_batch(a, b, n, polys, division, q_cons, mu_cons, q_bit_cons, stream=None):
+    _call("nttb200_barrett_batch", vp(ptr(a)), vp(ptr(b)), C.c_uint(n), C.c_uint(polys), C.c_uint(division), vp(ptr(q_cons)), vp(ptr(mu_cons)),
+          vp(ptr(q_bit_cons)), vp(_stream(stream)))
+
+
+def barrett_batch_3param(c, a, b, n, polys, division, q_cons, mu_cons, q_bit_cons, stream=None):
+    _call("nttb200_barrett_batch_3param", vp(ptr(c)), vp(ptr(a)), vp(ptr(b)), C.c_uint(n), C.c_uint(polys), C.c_uint(division), vp(ptr(q_cons)),
+          vp(ptr(mu_cons)), vp(ptr(q_bit_cons)), vp(_stream(stream)))
+
+
+def poly_mul_int(a, b, n, stream, q, mu, bit_length):
+    _call("nttb200_barrett_int", vp(ptr(a)), u64(b), C.c_uint(n), u64(q), u64(mu), C.c_int(bit_length), vp(_stream(stream)))
+
+
+def poly_mul_int_t(a, b, n, stream, t):
+    _call("nttb200_mod_t", vp(ptr(a)), u64(b), C.c_uint(n), u64(t), vp(_stream(stream)))
+
+
+def poly_add_device(a, b, n, stream, q):
+    _call("nttb200_poly_add", vp(ptr(a)), vp(ptr(b)), C.c_uint(n), u64(q), vp(_stream(stream)))
+
+
+def poly_add_integer_device(a, b, n, stream, q):
+    _call("nttb200_poly_add_integer", vp(ptr(a)), u64(b), C.c_uint(n), u64(q), vp(_stream(stream)))
+
+
+def poly_sub_device(a, b, n, stream, q):
+    _call("nttb200_poly_sub", vp(ptr(a)), vp(ptr(b)), C.c_uint(n), u64(q), vp(_stream(stream)))
+
+
+def poly_negate_device(a, n, stream, q):
+    _call("nttb200_poly_negate", vp(ptr(a)), C.c_uint(n), u64(q), vp(_stream(stream)))
+
+
+def divide_and_round_q_last_inplace_loop(input_poly, rns_poly_minus1, n, base_q_i, half_mod, inv_q_last_mod_q_i, mu, qbit, stream=None):
+    _call("nttb200_divide_and_round_q_last_inplace_loop", vp(ptr(input_poly)), vp(ptr(rns_poly_minus1)), C.c_uint(n), u64(base_q_i), u64(half_mod),
+          u64(inv_q_last_mod_q_i), u64(mu), C.c_int(qbit), vp(_stream(stream)))
+
+
+def fast_convert_array_kernels(input_poly, result_poly, t, bcm, q_amount, gamma, gamma_bits, mu_gamma, n, stream=None):
+    _call("nttb200_fast_convert_array", vp(ptr(input_poly)), vp(ptr(result_poly)), u64(t), vp(ptr(bcm)), C.c_uint(q_amount), u64(gamma),
+          C.c_int(gamma_bits), u64(mu_gamma), C.c_uint(n), vp(_stream(stream)))
+
+
+def dec_round(input_poly, result_poly, t, gamma, gamma_div_2, n, stream=None):
+    _call("nttb200_dec_round", vp(ptr(input_poly)), vp(ptr(result_poly)), u64(t), u64(gamma), u64(gamma_div_2), C.c_uint(n), vp(_stream(stream)))
+
+
+# ---- sampling (distributions.cuh) ---------------------------------------------------------------------------------------
+def generate_random_default(a, nbytes, stream=None):
+    _call("nttb200_generate_random_default", vp(ptr(a)), C.c_uint(nbytes), vp(_stream(stream)))
+
+
+def generate_random(a, nbytes, stream=None):
+    _call("nttb200_generate_random", vp(ptr(a)), C.c_uint(nbytes), vp(_stream(stream)))
+
+
+def salsa20_keystream(out, blocks_per_stream, streams, stream_stride, key: bytes, nonce0, stream=None):
+    kb = (C.c_ubyte * 32).from_buffer_copy(key)
+    _call("nttb200_salsa20_keystream", vp(ptr(out)), u64(blocks_per_stream), u64(streams), C.c_size_t(stream_stride), kb, u64(nonce0),
+          vp(_stream(stream)))
+
+
+def gaussian_dist(inp, out, n, stream, q):
+    _call("nttb200_gaussian_dist", vp(ptr(inp)), vp(ptr(out)), C.c_uint(n), vp(_stream(stream)), u64(q))
+
+
+def uniform_dist(inp, out, n, stream, q):
+    _call("nttb200_uniform_dist", vp(ptr(inp)), vp(ptr(out)), C.c_uint(n), vp(_stream(stream)), u64(q))
+
+
+def ternary_dist(inp, out, n, stream, q):
+    _call("nttb200_ternary_dist", vp(ptr(inp)), vp(ptr(out)), C.c_uint(n), vp(_stream(stream)), u64(q))
+
+
+def ternary_dist_xq(inp, sk, n, q_amount, q_cons, stream=None):
+    _call("nttb200_ternary_dist_xq", vp(ptr(inp)), vp(ptr(sk)), C.c_uint(n), C.c_uint(q_amount), vp(ptr(q_cons)), vp(_stream(stream)))
+
+
+def uniform_dist_xq(inp, pk, n, q_amount, q_cons, stream=None):
+    _call("nttb200_uniform_dist_xq", vp(ptr(inp)), vp(ptr(pk)), C.c_uint(n), C.c_uint(q_amount), vp(ptr(q_cons)), vp(_stream(stream)))
+
+
+def gaussian_dist_xq(inp, temp, n, q_amount, q_cons, stream=None):
+    _call("nttb200_gaussian_dist_xq", vp(ptr(inp)), vp(ptr(temp)), C.c_uint(n), C.c_uint(q_amount), vp(ptr(q_cons)), vp(_stream(stream)))
+
+
+def poly_add_negate_xq(a, b, n, q_amount, q_cons, stream=None):
+    _call("nttb200_poly_add_negate_xq", vp(ptr(a)), vp(ptr(b)), C.c_uint(n), C.c_uint(q_amount), vp(ptr(q_cons)), vp(_stream(stream)))
+
+
+def convert_ternary_gaussian_x2(inp, c, e, n, q_amount, q_cons, stream=None):
+    _call("nttb200_convert_ternary_gaussian_x2", vp(ptr(inp)), vp(ptr(c)), vp(ptr(e)), C.c_uint(n), C.c_uint(q_amount), vp(ptr(q_cons)),
+          vp(_stream(stream)))
+
+
+# ---- BFV pipelines -------------------------------------------------------------------------------------------------------
+class Bfv:
+    """Batched BFV keygen / encrypt / decrypt on one ring (replaces the per-driver set-up of demo.cu:62-272 and the
+    single-item keygen_rns / encryption_rns / decryption_rns calls).  Layouts are the reference's."""
+
+    def __init__(self, n, q, psi_roots, t=params.T, gamma=params.GAMMA):
+        self.n, self.q, self.r, self.t, self.gamma = int(n), [int(v) for v in q], len(q), int(t), int(gamma)
+        self._h = vp()
+        check(lib().nttb200_bfv_create(C.byref(self._h), C.c_uint(self.n), C.c_uint(self.r), _arr64(self.q), _arr64(psi_roots), u64(t), u64(gamma)))
+
+    def close(self):
+        if self._h:
+            lib().nttb200_bfv_destroy(self._h)
+            self._h = vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reserve(self, batch):
+        check(lib().nttb200_bfv_reserve(self._h, C.c_uint(batch)))
+
+    def keygen(self, sk, pk, batch=1, nonce0=0, stream=None):
+        """sk[batch][r][n], pk[batch][2][r][n] (bfv_keygen.cuh:95)"""
+        check(lib().nttb200_bfv_keygen(self._h, vp(ptr(sk)), vp(ptr(pk)), C.c_uint(batch), u64(nonce0), vp(_stream(stream))))
+
+    def encrypt(self, c, pk, m, batch=1, nonce0=0, pk_per_item=False, stream=None):
+        """c[batch][2][r][n], m[batch][n] (bfv_encryption.cuh:223)"""
+        check(lib().nttb200_bfv_encrypt(self._h, vp(ptr(c)), vp(ptr(pk)), C.c_int(int(pk_per_item)), vp(ptr(m)), C.c_uint(batch), u64(nonce0),
+                                        vp(_stream(stream))))
+
+    def decrypt(self, m_out, c, sk, batch=1, sk_per_item=False, stream=None):
+        """m_out[batch][n] (bfv_decryption.cuh:76)"""
+        check(lib().nttb200_bfv_decrypt(self._h, vp(ptr(m_out)), vp(ptr(c)), vp(ptr(sk)), C.c_int(int(sk_per_item)), C.c_uint(batch),
+                                        vp(_stream(stream))))
+
+
+def keygen_rns(inp, q_amount, n, secret_key, public_key, temp, psi_table, psiinv_table, q_cons, mu_cons, q_bit_cons, stream=None):
+    """bfv_keygen.cuh:95 (the unused reference parameters q, streams, mu_array, q_bit_lengths are dropped)"""
+    _call("nttb200_ref_keygen_rns", vp(ptr(inp)), C.c_uint(q_amount), C.c_uint(n), vp(ptr(secret_key)), vp(ptr(public_key)), vp(ptr(temp)),
+          vp(ptr(psi_table)), vp(ptr(psiinv_table)), vp(ptr(q_cons)), vp(ptr(mu_cons)), vp(ptr(q_bit_cons)), vp(_stream(stream)))
+
+
+def encryption_rns(c, public_key, inp, e, n, psi_table, psiinv_table, m_poly, qi_div_t, t, q_amount, q_cons, mu_cons, q_bit_cons,
+                   inv_q_last_mod_q_cons, stream=None):
+    """bfv_encryption.cuh:223"""
+    _call("nttb200_ref_encryption_rns", vp(ptr(c)), vp(ptr(public_key)), vp(ptr(inp)), vp(ptr(e)), C.c_uint(n), vp(ptr(psi_table)),
+          vp(ptr(psiinv_table)), vp(ptr(m_poly)), vp(ptr(qi_div_t)), u64(t), C.c_uint(q_amount), vp(ptr(q_cons)), vp(ptr(mu_cons)),
+          vp(ptr(q_bit_cons)), vp(ptr(inv_q_last_mod_q_cons)), vp(_stream(stream)))
+
+
+def decryption_rns(c, secret_key, psi_table, psiinv_table, n, q_amount, base_change_matrix, t, gamma, mu_gamma, gamma_bits, neg_inv_t,
+                   neg_inv_gamma, gamma_div_2, q_cons, mu_cons, q_bit_cons, inv_punctured_q_cons, prod_t_gamma_mod_q_cons, stream=None):
+    """bfv_decryption.cuh:76 (q_amount = limbs after the drop; plaintext at c + n*(q_amount-1))"""
+    _call("nttb200_ref_decryption_rns", vp(ptr(c)), vp(ptr(secret_key)), vp(ptr(psi_table)), vp(ptr(psiinv_table)), C.c_uint(n),
+          C.c_uint(q_amount), vp(ptr(base_change_matrix)), u64(t), u64(gamma), u64(mu_gamma), C.c_int(gamma_bits), u64(neg_inv_t),
+          u64(neg_inv_gamma), u64(gamma_div_2), vp(ptr(q_cons)), vp(ptr(mu_cons)), vp(ptr(q_bit_cons)), vp(ptr(inv_punctured_q_cons)),
+          vp(ptr(prod_t_gamma_mod_q_cons)), vp(_stream(stream)))

@@ -362,11 +362,14 @@ ORC_API void orc_salsa20_keystream(unsigned char *out, size_t nbytes, const unsi
     size_t nblk = nbytes / 64;
     for (size_t b = 0; b < nblk; b++) salsa20_block(out + 64 * b, key, nonce, b);
 }
-/* distributions.cuh:249-276 generate_random_default: key = 32 x 0x01, nonce 0 */
+/* distributions.cuh:249-276 generate_random_default: key = 32 x 0x01, nonce 0.  (orc_set_nonce lets the tests restate
+ * the batched pipelines, where item k draws from nonce k; the reference itself always uses 0.) */
+static u64 g_nonce = 0;
+ORC_API void orc_set_nonce(u64 nonce) { g_nonce = nonce; }
 ORC_API void orc_generate_random_default(unsigned char *out, unsigned nbytes)
 {
     unsigned char key[32]; memset(key, 1, 32);
-    orc_salsa20_keystream(out, nbytes, key, 0);
+    orc_salsa20_keystream(out, nbytes, key, g_nonce);
 }
 /* distributions.cuh:220-247 generate_random: key = 0x4D but only the first 24 bytes are uploaded (:235);
  * bytes 24..31 keep whatever the `key` symbol held before (`prev_key_tail`: zeros on a fresh context,

@@ -309,6 +309,11 @@ def salsa20_keystream(nbytes, key: bytes, nonce=0):
     return out
 
 
+def set_nonce(nonce):
+    """Batched pipelines: item k uses Salsa20 nonce k (0 = the reference)."""
+    lib().orc_set_nonce(u64(nonce))
+
+
 def generate_random_default(nbytes):
     out = np.zeros(nbytes, dtype=np.uint8)
     lib().orc_generate_random_default(_p8(out), C.c_uint(nbytes))

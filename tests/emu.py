@@ -66,3 +66,71 @@ def ntt(a, n, qs, psi_tables, psiinv_tables, num, division, inverse, barrett, us
                           None, None, None, num, division, group_polys, C.c_size_t(group_stride))
     assert r == 0
     return a
+
+
+# ---- BFV pipelines / pointwise / sampling on the emulator ---------------------------------------------------------------
+class EmuRing:
+    """Device-side view of an oracle.Ring for the emulator (tables, Shoup companions, LimbConst)."""
+
+    def __init__(self, ring):
+        self.ring = ring
+        self.psi = np.ascontiguousarray(ring.psi)
+        self.psiinv = np.ascontiguousarray(ring.psiinv)
+        qs = [int(x) for x in ring.q]
+        self.psi_s = np.ascontiguousarray(np.stack([shoup(self.psi[l], qs[l]) for l in range(ring.r)]))
+        self.psiinv_s = np.ascontiguousarray(np.stack([shoup(self.psiinv[l], qs[l]) for l in range(ring.r)]))
+        self.lc = limb_consts(qs, ring.n, self.psiinv)
+
+
+def bfv(op, er: EmuRing, barrett, batch=1, nonce0=0, sk=None, pk=None, c=None, m=None, per_item_keys=0):
+    """op 0 keygen -> (sk, pk, es); 1 encrypt -> (c, es); 2 decrypt -> (out, c)."""
+    R = er.ring
+    n, r = R.n, R.r
+    rn = r * n
+    u = C.c_ulonglong
+    inb = np.zeros(batch * (9 * rn + 4 * n), dtype=np.uint8)
+    es = np.zeros(batch * 2 * n, dtype=np.int32)
+    sk = np.zeros(batch * rn, dtype=np.uint64) if sk is None else np.ascontiguousarray(sk, dtype=np.uint64).copy()
+    pk = np.zeros(batch * 2 * rn, dtype=np.uint64) if pk is None else np.ascontiguousarray(pk, dtype=np.uint64).copy()
+    c = np.zeros(batch * 2 * rn, dtype=np.uint64) if c is None else np.ascontiguousarray(c, dtype=np.uint64).copy()
+    m = np.zeros(batch * n, dtype=np.uint64) if m is None else np.ascontiguousarray(m, dtype=np.uint64)
+    out = np.zeros(batch * n, dtype=np.uint64)
+    rc = lib().emu_bfv(op, n, r, p(R.qa, u), p(R.mu, u), p(R.qbit, C.c_uint), p(er.psi, u), p(er.psiinv, u), p(er.psi_s, u), p(er.psiinv_s, u),
+                       er.lc.ctypes.data_as(C.c_void_p), int(barrett),
+                       p(inb, C.c_ubyte), p(es, C.c_int), p(sk, u), p(pk, u), p(c, u), p(m, u), p(out, u), batch, u(nonce0),
+                       p(R.inv_q_last_mod_q, u), p(R.qi_div_t, u), p(R.prod_t_gamma_mod_q, u), p(R.inv_punctured_q, u), p(R.bcm, u),
+                       u(R.t), u(R.gamma), u(R.mu_gamma), int(R.gamma_bits), u(int(R.neg_inv[0])), u(int(R.neg_inv[1])), int(per_item_keys))
+    assert rc == 0
+    if op == 0:
+        return sk, pk, es[:batch * n].reshape(batch, n)
+    if op == 1:
+        return c, es.reshape(batch, 2, n)
+    return out.reshape(batch, n), c
+
+
+def pointwise(op, a, b=None, n=None, s0=0, s1=0, s2=0, i0=0, u0=0, u1=0, qv=None, muv=None, qbitv=None, aux=None, out_size=None):
+    u = C.c_ulonglong
+    a = np.ascontiguousarray(a, dtype=np.uint64).copy()
+    b = np.zeros(1, dtype=np.uint64) if b is None else np.ascontiguousarray(b, dtype=np.uint64)
+    n = a.size if n is None else n
+    c = np.zeros(out_size or a.size, dtype=np.uint64)
+    z = np.zeros(1, dtype=np.uint64)
+    zq = np.zeros(1, dtype=np.uint32)
+    qv = z if qv is None else np.ascontiguousarray(qv, dtype=np.uint64)
+    muv = z if muv is None else np.ascontiguousarray(muv, dtype=np.uint64)
+    qbitv = zq if qbitv is None else np.ascontiguousarray(qbitv, dtype=np.uint32)
+    aux = z if aux is None else np.ascontiguousarray(aux, dtype=np.uint64)
+    rc = lib().emu_pointwise(op, p(a, u), p(b, u), p(c, u), C.c_size_t(n), u(s0), u(s1), u(s2), int(i0), int(u0), int(u1), p(qv, u), p(muv, u),
+                             p(qbitv, C.c_uint), p(aux, u))
+    assert rc == 0
+    return a, c
+
+
+def sampling(op, inb, n, u0=0, q=None, nonce=0, stride=0, out_size=None):
+    u = C.c_ulonglong
+    inb = np.zeros(8, dtype=np.uint8) if inb is None else np.ascontiguousarray(inb).view(np.uint8)
+    out = np.zeros(out_size if out_size else n, dtype=np.uint64)
+    q = np.zeros(1, dtype=np.uint64) if q is None else np.ascontiguousarray(q, dtype=np.uint64)
+    rc = lib().emu_sampling(op, p(inb, C.c_ubyte), p(out, u), None, C.c_size_t(n), int(u0), p(q, u), u(nonce), C.c_size_t(stride))
+    assert rc == 0
+    return out
