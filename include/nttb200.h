@@ -171,6 +171,15 @@ NTTB200_API int nttb200_bfv_encrypt(nttb200_bfv *bfv, nttb200_u64 *c, const nttb
 NTTB200_API int nttb200_bfv_decrypt(nttb200_bfv *bfv, nttb200_u64 *m_out, nttb200_u64 *c, const nttb200_u64 *sk, int sk_per_item,
                                     unsigned batch, void *stream);
 
+/* Limb-sharded decryption across GPUs.  Each GPU holds limbs [first_limb, first_limb + limb_count) of
+ * every ciphertext as a compact shard c_shard[batch][2][limb_count][n] (c0 limbs, then c1 limbs) and the same limbs of the
+ * secret key.  _partial runs NTT / (.)sk / INTT / scaling on the shard and writes the partial base-conversion sums
+ * partial[batch][2][n]; the caller all-reduces (SUM, 64-bit) `partial` over the GPUs -- the path's only collective -- and
+ * _finish rounds to the plaintext m_out[batch][n].  Bit-identical to nttb200_bfv_decrypt on one GPU. */
+NTTB200_API int nttb200_bfv_decrypt_partial(nttb200_bfv *bfv, nttb200_u64 *partial, nttb200_u64 *c_shard, const nttb200_u64 *sk_shard,
+                                            int sk_per_item, unsigned first_limb, unsigned limb_count, unsigned batch, void *stream);
+NTTB200_API int nttb200_bfv_decrypt_finish(nttb200_bfv *bfv, nttb200_u64 *m_out, const nttb200_u64 *partial_sum, unsigned batch, void *stream);
+
 /* The reference's single-item calls, stateless (tables and constant arrays are the caller's device buffers;
  * unused reference parameters are dropped).  Scratch: `in` as in the reference; the first n (keygen) / 2n (encrypt)
  * 32-bit words of `temp` / `e` receive the signed gaussian draws instead of r*n residues. */

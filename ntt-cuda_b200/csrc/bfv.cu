@@ -242,6 +242,41 @@ int nttb200_bfv_decrypt(nttb200_bfv *b, nttb200_u64 *m_out, nttb200_u64 *c, cons
     return run_decrypt(P, c, sk, sk_per_item ? (size_t)b->r * b->n : 0, m_out, b->n, D, batch);
 }
 
+// ---- limb-sharded decryption: this GPU's share up to the cross-limb reduction, and the step after the all-reduce -------
+// c_shard: items of [2][count][n] holding limbs [first, first+count) of c0 then of c1; sk_shard[count][n] (or per item).
+int nttb200_bfv_decrypt_partial(nttb200_bfv *b, nttb200_u64 *partial, nttb200_u64 *c_shard, const nttb200_u64 *sk_shard, int sk_per_item,
+                                unsigned first_limb, unsigned limb_count, unsigned batch, void *stream)
+{
+    if (!b || !partial || !c_shard || !sk_shard || !batch || !limb_count || first_limb + limb_count > b->r - 1) return NTTB200_EINVAL;
+    const unsigned n = b->n;
+    const nttb200_ctx *c = b->ctx;
+    Pipe P = pipe_from_bfv(b, (cudaStream_t)stream);
+    // the transform sees only this shard: tables / constants start at the first owned limb, local limb = poly % count
+    const size_t toff = (size_t)first_limb * n;
+    P.psi = c->psi + toff; P.psiinv = c->psiinv + toff; P.psi_s = c->psi_s + toff; P.psiinv_s = c->psiinv_s + toff; P.lc = c->lc + first_limb;
+    LimbArrays Lloc{c->q_dev + first_limb, c->mu_dev + first_limb, c->qbit_dev + first_limb, nullptr, nullptr, nullptr};
+    const LimbArrays Lglob = P.L;
+    P.L = Lloc;
+    const size_t item = (size_t)2 * limb_count * n, c1_off = (size_t)limb_count * n;
+    NTTB200_TRY(pipe_ntt(P, false, c_shard + c1_off, batch * limb_count, limb_count, limb_count, item));
+    k_decrypt_mul<<<grid_for((size_t)batch * limb_count * n, 256), 256, 0, P.st>>>(c_shard, item, c1_off, sk_shard,
+                                                                                 sk_per_item ? (size_t)limb_count * n : 0, n, limb_count, batch, Lloc);
+    KCHECK();
+    NTTB200_TRY(pipe_ntt(P, true, c_shard + c1_off, batch * limb_count, limb_count, limb_count, item));
+    DecryptConsts D{b->t, b->gamma, b->mu_gamma, b->gamma_div_2, b->neg_inv_t, b->neg_inv_gamma, b->gamma_bits, b->r - 1, b->bcm};
+    k_decrypt_partial<<<grid_for((size_t)batch * n, 256), 256, 0, P.st>>>(c_shard, item, c1_off, partial, n, batch, first_limb, limb_count, D, Lglob);
+    KCHECK();
+    return 0;
+}
+int nttb200_bfv_decrypt_finish(nttb200_bfv *b, nttb200_u64 *m_out, const nttb200_u64 *partial_sum, unsigned batch, void *stream)
+{
+    if (!b || !m_out || !partial_sum || !batch) return NTTB200_EINVAL;
+    DecryptConsts D{b->t, b->gamma, b->mu_gamma, b->gamma_div_2, b->neg_inv_t, b->neg_inv_gamma, b->gamma_bits, b->r - 1, b->bcm};
+    k_decrypt_finish<<<grid_for((size_t)batch * b->n, 256), 256, 0, (cudaStream_t)stream>>>(partial_sum, m_out, b->n, b->n, batch, D);
+    KCHECK();
+    return 0;
+}
+
 // ---- the reference's single-item calls (stateless; constants come from the caller's device arrays) -------------------
 static Pipe pipe_ref(unsigned n, unsigned r, const nttb200_u64 *psi, const nttb200_u64 *psiinv, const nttb200_u64 *q_dev, const nttb200_u64 *mu_dev,
                      const unsigned *qbit_dev, const nttb200_u64 *inv_q_last, const nttb200_u64 *inv_punct, const nttb200_u64 *ptg,

@@ -303,4 +303,47 @@ NTT_KERNEL void k_decrypt_epilogue(const u64 *c, size_t item_stride, size_t c1_o
     }
 }
 
+// ---- limb-sharded decryption (multi-GPU): the same arithmetic split at its only cross-limb reduction -------------------
+// Each GPU owns `count` limbs [first, first+count) of every ciphertext as a compact shard c[item][2][count][n] and
+// produces partial base-conversion sums  part[item][0][j] = sum (v_l * bcm_t[l] & mask)  (mod 2^64 wrap-around, masked at the end)
+// and part[item][1][j] = sum Barrett_gamma(v_l * bcm_g[l]) mod gamma.  One all-reduce(SUM) of `part` across the GPUs
+// (at most 8 addends < 2^61: no 64-bit overflow) followed by k_decrypt_finish reproduces k_decrypt_epilogue exactly:
+// the reference's running `(acc + v) % gamma` and the plain modular sum are the same residue.
+NTT_KERNEL void k_decrypt_partial(const u64 *c, size_t item_stride, size_t c1_off, u64 *part, unsigned n, unsigned batch, unsigned first,
+                                  unsigned count, DecryptConsts D, LimbArrays L)
+{
+    const u32 mask32 = (u32)(D.t - 1);
+    NTT_GRID_STRIDE(i, (size_t)batch * n) {
+        const size_t k = i / n, j = i - k * n;
+        const u64 *c0 = c + k * item_stride, *c1 = c0 + c1_off;
+        u64 acc_t = 0, acc_g = 0;
+        for (unsigned ll = 0; ll < count; ll++) {
+            const unsigned l = first + ll;                 // global limb: constants are indexed globally, data locally
+            const u64 q = L.q[l], mu = L.mu[l];
+            const int qb = (int)L.qbit[l];
+            u64 v = c1[(size_t)ll * n + j] + c0[(size_t)ll * n + j];
+            if (v > q) v -= q;
+            v = barrett_ref(v, L.prod_t_gamma_mod_q[l], q, mu, qb);
+            v = barrett_ref(v, L.inv_punctured_q[l], q, mu, qb);
+            acc_t += (v * D.bcm[l]) & (u64)mask32;
+            acc_g = (acc_g + barrett_ref(v, D.bcm[l + D.rp], D.gamma, D.mu_gamma, D.gamma_bits)) % D.gamma;
+        }
+        part[k * 2 * n + j] = acc_t;
+        part[k * 2 * n + n + j] = acc_g;
+    }
+}
+NTT_KERNEL void k_decrypt_finish(const u64 *part_sum, u64 *out, size_t out_stride, unsigned n, unsigned batch, DecryptConsts D)
+{
+    const u32 mask32 = (u32)(D.t - 1);
+    NTT_GRID_STRIDE(i, (size_t)batch * n) {
+        const size_t k = i / n, j = i - k * n;
+        u64 mt = part_sum[k * 2 * n + j] & (u64)mask32;
+        u64 mg = part_sum[k * 2 * n + n + j] % D.gamma;
+        mt = (mt * D.neg_inv_t) & (u64)mask32;
+        mg = barrett_ref(mg, D.neg_inv_gamma, D.gamma, D.mu_gamma, D.gamma_bits);
+        const u64 tmask = D.t - 1;
+        out[k * out_stride + j] = mg > D.gamma_div_2 ? ((mt + (D.gamma - mg)) & tmask) : ((mt - mg) & tmask);
+    }
+}
+
 }  // namespace nttb200

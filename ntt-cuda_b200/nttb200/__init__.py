@@ -304,6 +304,15 @@ class Bfv:
                                         vp(_stream(stream))))
 
 
+    def decrypt_partial(self, partial, c_shard, sk_shard, first_limb, limb_count, batch=1, sk_per_item=False, stream=None):
+        """Limb-sharded decryption, this GPU's share: partial[batch][2][n] (all-reduce SUM it, then decrypt_finish)."""
+        check(lib().nttb200_bfv_decrypt_partial(self._h, vp(ptr(partial)), vp(ptr(c_shard)), vp(ptr(sk_shard)), C.c_int(int(sk_per_item)),
+                                                C.c_uint(first_limb), C.c_uint(limb_count), C.c_uint(batch), vp(_stream(stream))))
+
+    def decrypt_finish(self, m_out, partial_sum, batch=1, stream=None):
+        check(lib().nttb200_bfv_decrypt_finish(self._h, vp(ptr(m_out)), vp(ptr(partial_sum)), C.c_uint(batch), vp(_stream(stream))))
+
+
 def keygen_rns(inp, q_amount, n, secret_key, public_key, temp, psi_table, psiinv_table, q_cons, mu_cons, q_bit_cons, stream=None):
     """bfv_keygen.cuh:95 (the unused reference parameters q, streams, mu_array, q_bit_lengths are dropped)"""
     _call("nttb200_ref_keygen_rns", vp(ptr(inp)), C.c_uint(q_amount), C.c_uint(n), vp(ptr(secret_key)), vp(ptr(public_key)), vp(ptr(temp)),

@@ -1,0 +1,64 @@
+"""Multi-GPU orchestration: one process per GPU, torch.distributed (NCCL over NVLink) for the plumbing.
+
+The hot path shards with NO data-path collective for NTT / INTT / pointwise / keygen / encryption (units = (batch item,
+limb) are independent) and with exactly ONE collective for decryption: the cross-limb base-conversion sum.
+
+  * shard_batch(total, world, rank)             -> the contiguous slice of batch items a rank owns (batch sharding)
+  * shard_limbs(rp, world, rank)                -> the contiguous limb range a rank owns (limb sharding)
+  * scatter_ciphertext_limbs / decrypt_limb_sharded : limb-sharded decryption, all-reduce(SUM) of [batch][2][n] u64 partials
+
+`backend` hooks let the CPU test-suite (gloo, world_size 2) drive the identical control flow with the emulator build of
+the kernels in place of the GPU library.
+"""
+from __future__ import annotations
+
+
+def shard_batch(total: int, world: int, rank: int):
+    """Contiguous, balanced split: the first (total % world) ranks get one extra item.  Returns (first, count)."""
+    base, extra = divmod(total, world)
+    first = rank * base + min(rank, extra)
+    return first, base + (1 if rank < extra else 0)
+
+
+def shard_limbs(rp: int, world: int, rank: int):
+    """Limb-major blocks of ceil(rp / world) limbs.  Ranks beyond the last limb own nothing."""
+    per = -(-rp // world)
+    first = min(rank * per, rp)
+    return first, max(0, min(per, rp - first))
+
+
+def ciphertext_limb_shard(c, n: int, r: int, first: int, count: int, batch: int = 1):
+    """Slices a reference-layout ciphertext array c[batch][2][r][n] (numpy or torch, flat or shaped) into the compact
+    shard [batch][2][count][n] of limbs [first, first+count)."""
+    v = c.reshape(batch, 2, r, n)
+    s = v[:, :, first:first + count, :]
+    return s.contiguous().reshape(-1) if hasattr(s, "contiguous") else s.copy().reshape(-1)
+
+
+def decrypt_limb_sharded(bfv, c_shard, sk_shard, first: int, count: int, batch: int, all_reduce_sum, new_u64, sk_per_item=False):
+    """Limb-sharded decryption on this rank.
+
+    bfv            object with decrypt_partial / decrypt_finish (nttb200.Bfv on the GPU)
+    all_reduce_sum callable(buffer) -> None, in-place 64-bit SUM over all ranks (torch.distributed.all_reduce on the
+                   int64 view: two's-complement wrap-around is exactly the u64 sum the kernels need)
+    new_u64        callable(count) -> zero-initialised device buffer of `count` 64-bit words
+    Returns the plaintext buffer m_out[batch][n] (identical on every rank)."""
+    n = bfv.n
+    partial = new_u64(batch * 2 * n)
+    if count > 0:
+        bfv.decrypt_partial(partial, c_shard, sk_shard, first, count, batch=batch, sk_per_item=sk_per_item)
+    all_reduce_sum(partial)                      # the path's only collective: batch * 2 * n * 8 bytes
+    out = new_u64(batch * n)
+    bfv.decrypt_finish(out, partial, batch=batch)
+    return out
+
+
+def torch_all_reduce_sum(t):
+    import torch.distributed as dist
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+
+def torch_new_u64(count, device="cuda"):
+    import torch
+    return torch.zeros(count, dtype=torch.int64, device=device)

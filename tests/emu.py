@@ -134,3 +134,28 @@ def sampling(op, inb, n, u0=0, q=None, nonce=0, stride=0, out_size=None):
     rc = lib().emu_sampling(op, p(inb, C.c_ubyte), p(out, u), None, C.c_size_t(n), int(u0), p(q, u), u(nonce), C.c_size_t(stride))
     assert rc == 0
     return out
+
+
+class EmuBfv:
+    """Adapter with the nttb200.Bfv decrypt_partial / decrypt_finish interface, backed by the emulator (CPU tests of the
+    multi-GPU control flow)."""
+
+    def __init__(self, er: EmuRing):
+        self.er, self.n, self.r = er, er.ring.n, er.ring.r
+
+    def _call(self, op, c_shard, sk_shard, part, out, batch, first, count):
+        R, er, u = self.er.ring, self.er, C.c_ulonglong
+        z = np.zeros(1, dtype=np.uint64)
+        rc = lib().emu_bfv_sharded(op, R.n, R.r, p(R.qa, u), p(R.mu, u), p(R.qbit, C.c_uint), p(er.psi, u), p(er.psiinv, u), p(er.psi_s, u),
+                                   p(er.psiinv_s, u), er.lc.ctypes.data_as(C.c_void_p), p(c_shard if c_shard is not None else z, u),
+                                   p(sk_shard if sk_shard is not None else z, u), p(part, u), p(out if out is not None else z, u), batch, first,
+                                   count, p(R.prod_t_gamma_mod_q, u), p(R.inv_punctured_q, u), p(R.bcm, u), u(R.t), u(R.gamma), u(R.mu_gamma),
+                                   int(R.gamma_bits), u(int(R.neg_inv[0])), u(int(R.neg_inv[1])))
+        assert rc == 0
+
+    def decrypt_partial(self, partial, c_shard, sk_shard, first, count, batch=1, sk_per_item=False):
+        assert not sk_per_item
+        self._call(0, c_shard, sk_shard, partial, None, batch, first, count)
+
+    def decrypt_finish(self, m_out, partial_sum, batch=1):
+        self._call(1, None, None, partial_sum, m_out, batch, 0, 0)
