@@ -153,6 +153,71 @@ class ClockSampler:
         return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bfv_throughput(nttb200, params, torch, world, dist, batch=64, reps=5):
+    """BFV encrypt + decrypt ops/s (whole job): each rank encrypts and decrypts its own batch (batch sharding, no
+    collective).  Decryption overwrites c1, so every repetition decrypts a fresh device copy (copy time subtracted)."""
+    n, qs, roots = params.RNS_SETS["32k_16q"]
+    rn = len(qs) * n
+    bfv = nttb200.Bfv(n, qs, roots)
+    bfv.reserve(batch)
+    sk = torch.zeros(rn, dtype=torch.int64, device="cuda")
+    pk = torch.zeros(2 * rn, dtype=torch.int64, device="cuda")
+    bfv.keygen(sk, pk)
+    m = torch.randint(0, params.T, (batch * n,), dtype=torch.int64, device="cuda")
+    c = torch.zeros(batch * 2 * rn, dtype=torch.int64, device="cuda")
+    keep = torch.zeros_like(c)
+    out = torch.zeros(batch * n, dtype=torch.int64, device="cuda")
+
+    def timed(fn):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    enc = timed(lambda: bfv.encrypt(c, pk, m, batch=batch))
+    keep.copy_(c)
+
+    def dec():
+        c.copy_(keep)
+        bfv.decrypt(out, c, sk, batch=batch)
+
+    dec_ms = timed(dec) - timed(lambda: c.copy_(keep))
+    ok = bool(torch.equal(out, m))
+    bfv.close()
+    if not ok:
+        raise SystemExit("bench.py: BFV round trip failed")
+    return {"workload": "BFV encrypt + decrypt, n=32768, 16-limb q (demo.cu), t=1024, batch %d per GPU" % batch,
+            "enc_plus_dec_per_s": world * batch / ((enc + dec_ms) * 1e-3), "encrypt_per_s": world * batch / (enc * 1e-3),
+            "decrypt_per_s": world * batch / (dec_ms * 1e-3), "unit": "ops/s", "roundtrip_ok": ok}
+
+
+def reference_gpu_rebuilt():
+    """The reference's own kernels rebuilt for sm_100a (oracle/_ref/ref_dump), same batch, same GPU,
+    in a separate process.  Reported baseline only; absent when the binary was not built."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_dump")
+    if not os.path.exists(exe):
+        return None
+    try:
+        out = subprocess.run([exe, "bench", "32k_16q", str(POLYS), "20"], capture_output=True, text=True, timeout=300).stdout
+        d = json.loads(out.strip().splitlines()[-1])
+        return {"fwd_ntt_per_s": d["fwd_ntt_per_s"], "inv_ntt_per_s": d["inv_ntt_per_s"], "keygen_us": d["keygen_us"],
+                "encrypt_us": d["encrypt_us"], "decrypt_us": d["decrypt_us"],
+                "note": "forwardNTT_batch / inverseNTT_batch num=1024 and single-item keygen/encryption/decryption_rns loops, CUDA events"}
+    except Exception as e:  # pragma: no cover
+        return {"error": str(e)[:200]}
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -255,6 +320,11 @@ def run_ours(args):
     if not torch.equal(chk.cpu(), hout[:2]):
         raise SystemExit("bench.py: host-buffer path disagrees with the device path")
 
+    # ---- secondary metric of BASELINE.json ("BFV enc+dec ops/s"): batched context API, demo.cu's (32768, 16 primes) set
+    bfv_line = None
+    if not args.no_bfv:
+        bfv_line = bfv_throughput(nttb200, params, torch, world, dist)
+
     if rank == 0:
         peak, peak_src = peaks()
         alg_bytes = 16.0 * n * POLYS                     # per launch: every coefficient read once + written once
@@ -283,6 +353,8 @@ def run_ours(args):
             "butterflies_per_s": butterflies * args.steps / (ms_total * 1e-3) * world,
             "inverse": {"value": world * POLYS / (inv_ms * 1e-3), "unit": "INTT/s", "ms_per_step": inv_ms},
             "cpu_baseline": cb,
+            "bfv": bfv_line,
+            "reference_gpu_rebuilt": reference_gpu_rebuilt() if world == 1 and not args.no_cpu_baseline else None,
         }
         print(json.dumps(line))
     ctx.close()
@@ -297,6 +369,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-bfv", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
