@@ -47,7 +47,7 @@ static int ctx_finish(nttb200_ctx *c, const u64 *psi_h, const u64 *psiinv_h)
         LimbConst &k = lc[l];
         k.q = q; k.twoq = 2 * q; k.mu = mu; k.qbit = qbit; k.pad = 0;
         k.ratio = (u64)((((u128)1) << 64) / q); k.negq = 0 - q;
-        if (qbit > 58) c->lazy_ok = 0;
+        if (qbit > 57) c->lazy_ok = 0;   // 69 q < 2^64
         k.ninv = ninv; k.ninv_s = h_shoup(ninv, q);
         k.w1ninv = w1n; k.w1ninv_s = h_shoup(w1n, q);
     }

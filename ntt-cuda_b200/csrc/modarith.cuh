@@ -82,6 +82,44 @@ __host__ __device__ __forceinline__ u64 mullo_sum2(u64 a, u64 b, u64 c, u64 d)
 #endif
 }
 
+// Approximate high product: drops lo*lo and the carries out of the low words, so the result is in {exact-2 .. exact}.
+// 3 IMAD.WIDE.U32 + 3 IADD3 (the exact mul.hi.u64 is 4 + 3).  The C fallback computes the identical value.
+__host__ __device__ __forceinline__ u64 mulhi64_approx(u64 y, u64 s)
+{
+#if defined(__CUDA_ARCH__)
+    u64 r;
+    asm("{\n\t"
+        ".reg .u32 yl, yh, sl, sh, a1, b1, rl, rh, dm;\n\t"
+        ".reg .u64 t1, t2, t3;\n\t"
+        "mov.b64 {yl, yh}, %1;\n\t"
+        "mov.b64 {sl, sh}, %2;\n\t"
+        "mul.wide.u32 t1, yh, sl;\n\t"
+        "mul.wide.u32 t2, yl, sh;\n\t"
+        "mul.wide.u32 t3, yh, sh;\n\t"
+        "mov.b64 {dm, a1}, t1;\n\t"
+        "mov.b64 {dm, b1}, t2;\n\t"
+        "mov.b64 {rl, rh}, t3;\n\t"
+        "add.cc.u32 rl, rl, a1;\n\t"
+        "addc.u32 rh, rh, 0;\n\t"
+        "add.cc.u32 rl, rl, b1;\n\t"
+        "addc.u32 rh, rh, 0;\n\t"
+        "mov.b64 %0, {rl, rh};\n\t"
+        "}"
+        : "=l"(r)
+        : "l"(y), "l"(s));
+    return r;
+#else
+    const u64 yl = (u32)y, yh = y >> 32, sl = (u32)s, sh = s >> 32;
+    return yh * sh + ((yh * sl) >> 32) + ((yl * sh) >> 32);
+#endif
+}
+
+// Shoup multiplication with the approximate quotient: result in [0, 4q) for any 64-bit y.
+__host__ __device__ __forceinline__ u64 shoup_mul_a(u64 y, u64 w, u64 ws, u64 negq)
+{
+    return mullo_sum2(y, w, mulhi64_approx(y, ws), negq);
+}
+
 // Shoup multiplication on the fused chain: negq = 2^64 - q.  Result in [0, 2q).
 __host__ __device__ __forceinline__ u64 shoup_mul_n(u64 y, u64 w, u64 ws, u64 negq)
 {

@@ -77,6 +77,22 @@ constexpr int kContigRows = 128;  // rows (of 16 coefficients) per CTA in the co
 #define NTT_MINB_C 6
 #endif
 
+__device__ __forceinline__ void prefetch_l1(const void *p)
+{
+#ifndef NTTB200_EMU
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+// Twiddles of a round of S stages starting at table index twbase: stage s uses entries [(twbase << s), +2^s).
+template <int S, class P>
+__device__ __forceinline__ void prefetch_round(const P &pol, u32 twbase)
+{
+    NTT_UNROLL
+    for (int s = 0; s < S; s++) pol.prefetch(twbase << s);      // 2^s * 8 bytes <= 64: one line per stage and table
+}
+
 // ---- arithmetic policies ------------------------------------------------------------------------------------
 struct ShoupPolicy {
     u64 q, twoq, nq;
@@ -96,6 +112,8 @@ struct ShoupPolicy {
         ulonglong2 b = __ldg(reinterpret_cast<const ulonglong2 *>(ws + i));
         t0.w = a.x; t1.w = a.y; t0.ws = b.x; t1.ws = b.y;
     }
+    // pull the line holding table entry i into L1 (no destination register: can be issued long before the use)
+    __device__ __forceinline__ void prefetch(u32 i) const { prefetch_l1(w + i); prefetch_l1(ws + i); }
     // forward (Cooley-Tukey), X,Y in [0,4q) -> [0,4q)
     __device__ __forceinline__ void ct(u64 &X, u64 &Y, const Tw &t) const
     {
@@ -121,23 +139,25 @@ struct ShoupPolicy {
     }
 };
 
-// Forward transform for q < 2^58: no conditional subtraction at all inside the transform.  Every Shoup product is
-// < 2q whatever its input, so X' = X + T and Y' = X - T + 2q stay non-negative and grow by at most 2q per stage:
-// canonical inputs end below (2 log2(n) + 1) q <= 35 q < 2^64.  One Barrett-style reduction by floor(2^64/q) at the
-// very end brings the outputs to [0, q).  The inverse transform is ShoupPolicy's.
+// Forward transform for q < 2^57: no conditional subtraction at all inside the transform, and an approximate Shoup
+// quotient (3 wide multiplies instead of 4).  The approximate product is < 4q whatever its input, so X' = X + T and
+// Y' = X - T + 4q stay non-negative and grow by at most 4q per stage: canonical inputs end below
+// (4 log2(n) + 1) q <= 69 q < 2^64.  One reduction by floor(2^64/q) at the very end brings the outputs to [0, q).
+// The inverse transform is ShoupPolicy's.
 struct ShoupLazyPolicy : ShoupPolicy {
-    u64 ratio;
+    u64 ratio, fourq;
     __device__ __forceinline__ void init(const NttArgs &A, u32 limb, u32 n)
     {
         ShoupPolicy::init(A, limb, n);
         ratio = l->ratio;
+        fourq = twoq + twoq;
     }
     __device__ __forceinline__ void ct(u64 &X, u64 &Y, const Tw &t) const
     {
-        u64 T = shoup_mul_n(Y, t.w, t.ws, nq);
+        u64 T = shoup_mul_a(Y, t.w, t.ws, nq);
         u64 x = X;
         X = x + T;
-        Y = x - T + twoq;
+        Y = x - T + fourq;
     }
     __device__ __forceinline__ u64 fwd_final(u64 x) const
     {
@@ -167,6 +187,7 @@ struct BarrettPolicy {
         ulonglong2 a = __ldg(reinterpret_cast<const ulonglong2 *>(w + i));
         t0.w = a.x; t1.w = a.y;
     }
+    __device__ __forceinline__ void prefetch(u32 i) const { prefetch_l1(w + i); }
     __device__ __forceinline__ void ct(u64 &X, u64 &Y, const Tw &t) const
     {
         u64 u = X;
@@ -340,6 +361,12 @@ ntt_strided_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
     P pol;
     pol.init(A, p % A.division, n);
     u64 *g = A.a + (size_t)grp * A.group_stride + ((size_t)idx << LOGN) + col0;
+    {   // twiddle lines of every round of this thread, requested before the tile wait so they arrive under it
+        const u32 uu = tid & (R - 1);
+        if constexpr (SC::S2 != 0) prefetch_round<SC::S2>(pol, (1u << SC::S1) + ((uu >> SC::S2) >> (K1 - SC::S1 - SC::S2)));
+        if constexpr (SC::S3 != 0) prefetch_round<SC::S3>(pol, (1u << (SC::S1 + SC::S2)) + (uu >> SC::S3));
+        if (uu < 32) prefetch_round<SC::S1>(pol, 1u);
+    }
 
     if (A.use_tma) {
 #ifdef NTTB200_EMU
@@ -421,6 +448,8 @@ ntt_contig_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
     P pol;
     pol.init(A, p % A.division, n);
     u64 *g = A.a + (size_t)grp * A.group_stride + ((size_t)idx << LOGN) + (size_t)rip0 * 16;
+    prefetch_round<4>(pol, (n >> 4) + rip0 + tid);
+    prefetch_round<SA>(pol, (1u << K1) + (rip0 >> SA) + (tid >> SA));
 
     if (A.use_tma) {
 #ifdef NTTB200_EMU

@@ -40,6 +40,12 @@ __global__ void __launch_bounds__(1024) k(u64 *out, u32 a0, u32 b0, long long *c
                 u64 T = nttb200::shoup_mul_n(Y, tw, tws, 0 - q);
                 w[i] = X + T; w[(i + 1) % ILP] = X - T + 2 * q;
             }
+            if (OP == 9) { // same with the approximate quotient (3 wide multiplies)
+                u64 q = 0x7fffffd8001ull | ((u64)b0 << 40), tw = w[i] | 1, tws = w[(i + 3) % ILP];
+                u64 X = w[i], Y = w[(i + 1) % ILP];
+                u64 T = nttb200::shoup_mul_a(Y, tw, tws, 0 - q);
+                w[i] = X + T; w[(i + 1) % ILP] = X - T + 4 * q;
+            }
         }
     }
     long long t1 = clock64();
@@ -92,7 +98,8 @@ int main()
     run<5>("mul_hi_u64", s, clk, false);
     run<6>("mul_lo_u64", s, clk, false);
     run<7>("shoup_ct_butterfly_c", s, clk, false);
-    run<8>("shoup_ct_butterfly_lazy_ptx", s, clk, true);
+    run<8>("shoup_ct_butterfly_lazy_ptx", s, clk, false);
+    run<9>("shoup_ct_butterfly_lazy_approx_ptx", s, clk, true);
     printf("}\n");
     return 0;
 }

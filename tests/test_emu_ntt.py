@@ -109,3 +109,18 @@ def test_emu_grouped_layout(oracle):
             if off + n <= exp.size:
                 exp[off:off + n] = oracle.forward_ntt_fast(view[it, 1, l], qs[l], psi[l])
     assert np.array_equal(got, exp)
+
+
+def test_emu_lazy_policy_at_its_bound(oracle):
+    """Lazy forward policy at the edge of its range: the largest 57-bit prime, n = 2^17 (17 stages, values up to 69 q),
+    inputs at q - 1 everywhere (the worst case for growth) plus random ones."""
+    n = 1 << 17
+    qs, roots = params.find_ntt_primes(57, n, 1)
+    assert qs[0].bit_length() == 57
+    psi, psiinv = oracle.fill_psi_tables(roots[0], qs[0], n)
+    worst = np.full(n, qs[0] - 1, dtype=np.uint64)
+    rnd = oracle.fill_uniform(n, qs[0], 4242)
+    a = np.concatenate([worst, rnd])
+    got = emu.ntt(a, n, qs, psi[None], psiinv[None], 2, 1, inverse=False, barrett=2, use_tma=1)
+    assert np.array_equal(got[:n], oracle.forward_ntt_fast(worst, qs[0], psi))
+    assert np.array_equal(got[n:], oracle.forward_ntt_fast(rnd, qs[0], psi))
