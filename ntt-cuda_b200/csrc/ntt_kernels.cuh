@@ -47,7 +47,7 @@ struct NttArgs {
     u32 num, division;    // poly p uses limb p % division  (ntt_60bit.cuh:391)
     u32 group_polys;      // polynomial p starts at a + (p / group_polys) * group_stride + (p % group_polys) * n;
     size_t group_stride;  //   group_polys = num for one contiguous [num][n] array (the reference's layout)
-    u32 use_tma;
+    u32 use_tma;          // bit 0: TMA tile movement; bits 1/2 (profiling only): skip the butterflies / skip the tile traffic
 };
 
 // ---- stage split per ring degree: K1 = S1+S2+S3 strided stages (rounds of 3 or 4), K2 contiguous stages -------
@@ -368,7 +368,10 @@ ntt_strided_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
         if (uu < 32) prefetch_round<SC::S1>(pol, 1u);
     }
 
-    if (A.use_tma) {
+    const bool dbg_nocompute = (A.use_tma & 2u) != 0, dbg_nomem = (A.use_tma & 4u) != 0;
+    if (dbg_nomem) {
+        __syncthreads();
+    } else if (A.use_tma & 1u) {
 #ifdef NTTB200_EMU
         if (tid == 0)
             for (int k = 0; k < NT; k++)
@@ -393,7 +396,8 @@ ntt_strided_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
 
     u64 *tile = tiles + (size_t)(tid >> K1) * R * 16;
     const u32 u = tid & (R - 1);
-    if (!INV) {
+    if (dbg_nocompute) {
+    } else if (!INV) {
         strided_round<P, K1, 0, SC::S1, false>(tile, u, pol);
         if constexpr (SC::S2 != 0) { __syncthreads(); strided_round<P, K1, SC::S1, SC::S2, false>(tile, u, pol); }
         if constexpr (SC::S3 != 0) { __syncthreads(); strided_round<P, K1, SC::S1 + SC::S2, SC::S3, false>(tile, u, pol); }
@@ -403,7 +407,8 @@ ntt_strided_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
         strided_round<P, K1, 0, SC::S1, true>(tile, u, pol);
     }
 
-    if (A.use_tma) {
+    if (dbg_nomem) {
+    } else if (A.use_tma & 1u) {
 #ifdef NTTB200_EMU
         __syncthreads();
         if (tid == 0)
@@ -451,7 +456,10 @@ ntt_contig_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
     prefetch_round<4>(pol, (n >> 4) + rip0 + tid);
     prefetch_round<SA>(pol, (1u << K1) + (rip0 >> SA) + (tid >> SA));
 
-    if (A.use_tma) {
+    const bool dbg_nocompute = (A.use_tma & 2u) != 0, dbg_nomem = (A.use_tma & 4u) != 0;
+    if (dbg_nomem) {
+        __syncthreads();
+    } else if (A.use_tma & 1u) {
 #ifdef NTTB200_EMU
         if (tid == 0) emu_tma_3d(true, &tmap, tile, 0, grow, (int)grp);
         __syncthreads();
@@ -470,7 +478,8 @@ ntt_contig_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
     const u32 twA = (1u << K1) + (rip0 >> SA) + bl;            // block index inside the polynomial
     const u32 twB = (n >> 4) + rip0 + tid;                     // row index inside the polynomial
     u64 v[16];
-    if (!INV) {
+    if (dbg_nocompute) {
+    } else if (!INV) {
         regs_rows<SA, true, true>(tile, bl << SA, 0, t * NC, v);
         ct_stages<SA, NC>(v, twA, pol);
         regs_rows<SA, true, false>(tile, bl << SA, 0, t * NC, v);
@@ -490,7 +499,8 @@ ntt_contig_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
         regs_rows<SA, true, false>(tile, bl << SA, 0, t * NC, v);
     }
 
-    if (A.use_tma) {
+    if (dbg_nomem) {
+    } else if (A.use_tma & 1u) {
 #ifdef NTTB200_EMU
         __syncthreads();
         if (tid == 0) emu_tma_3d(false, &tmap, tile, 0, grow, (int)grp);

@@ -30,7 +30,10 @@ static EncodeTiledFn get_encode()
 int get_tma_default()
 {
     const char *e = getenv("NTTB200_NO_TMA");
-    return (e && e[0] == '1') ? 0 : 1;
+    int v = (e && e[0] == '1') ? 0 : 1;
+    const char *d = getenv("NTTB200_DEBUG_SKIP");        // profiling only: 1 = skip butterflies, 2 = skip tile traffic
+    if (d) v |= (atoi(d) & 3) << 1;
+    return v;
 }
 
 // groups x [group_polys][R = 2^K1][C = n/R] u64, box [1][1][min(R,256)][16], no swizzle
@@ -133,7 +136,7 @@ int launch_ntt_pass(bool inverse, int policy, unsigned logn, const NttArgsHost &
     A.group_stride = h.group_polys ? h.group_stride : ((size_t)h.num << logn);
     const unsigned groups = (h.num + A.group_polys - 1) / A.group_polys;
     CUtensorMap ms, mc;
-    if (h.use_tma) {
+    if (h.use_tma & 1) {
         int r = make_tmap_strided(&ms, A.a, logn, sched_k1(logn), A.group_polys, A.group_stride, groups);
         if (r) return r;
         r = make_tmap_contig(&mc, A.a, logn, A.group_polys, A.group_stride, groups);

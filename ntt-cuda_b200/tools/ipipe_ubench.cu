@@ -40,6 +40,37 @@ __global__ void __launch_bounds__(1024) k(u64 *out, u32 a0, u32 b0, long long *c
                 u64 T = nttb200::shoup_mul_n(Y, tw, tws, 0 - q);
                 w[i] = X + T; w[(i + 1) % ILP] = X - T + 2 * q;
             }
+            if (OP == 10) { // 1:1 mix of independent IMAD (fma pipe) and LOP3 (alu pipe): do the two half-rate pipes co-issue?
+                asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(y[i]), "r"(b0));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(y[i]) : "r"(a0), "r"(b0));
+            }
+            if (OP == 11) { // 1:1 mix of IMAD.WIDE and 64-bit add (IADD3 + IADD3.X)
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(x[i]), "r"(y[i]));
+                asm volatile("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, %1, %3;" : "+r"(x[i]), "+r"(y[i]) : "r"(a0), "r"(b0));
+            }
+            if (OP == 12) { // 64-bit add as add.cc / addc (IADD3 with carry-out predicate + IADD3.X)
+                asm volatile("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, %1, %3;" : "+r"(x[i]), "+r"(y[i]) : "r"(a0), "r"(b0));
+            }
+            if (OP == 13) { // 64-bit a + b - c as nvcc compiles it (3-input IADD3 with two carries + IADD3.X)
+                w[i] = w[i] + w[(i + 1) % ILP] - w[(i + 2) % ILP];
+            }
+            if (OP == 14) { // carry-free 64-bit add: IMAD.WIDE(lo, 1, acc) then a plain 32-bit add into the high word
+                u32 tl = y[i], th = x[i];
+                asm volatile("{\n\t.reg .u32 l, h;\n\tmad.wide.u32 %0, %1, 1, %0;\n\tmov.b64 {l, h}, %0;\n\tadd.u32 h, h, %2;\n\tmov.b64 %0, {l, h};\n\t}"
+                             : "+l"(w[i]) : "r"(tl), "r"(th));
+            }
+            if (OP == 15) { // INDEPENDENT streams: IMAD.WIDE chain on w[i], 64-bit add.cc/addc chain on (x[i], y[i])
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(a0), "r"(b0));
+                asm volatile("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, %1, %3;" : "+r"(x[i]), "+r"(y[i]) : "r"(a0), "r"(b0));
+            }
+            if (OP == 16) { // INDEPENDENT streams: IMAD.WIDE chain + two plain 32-bit adds (no carry)
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(a0), "r"(b0));
+                asm volatile("add.u32 %0, %0, %2;\n\tadd.u32 %1, %1, %3;" : "+r"(x[i]), "+r"(y[i]) : "r"(a0), "r"(b0));
+            }
+            if (OP == 17) { // INDEPENDENT streams: IMAD (lo) + IMAD.WIDE: both on the fma pipe
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(a0), "r"(b0));
+                asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(a0), "r"(b0));
+            }
             if (OP == 9) { // same with the approximate quotient (3 wide multiplies)
                 u64 q = 0x7fffffd8001ull | ((u64)b0 << 40), tw = w[i] | 1, tws = w[(i + 3) % ILP];
                 u64 X = w[i], Y = w[(i + 1) % ILP];
@@ -99,7 +130,15 @@ int main()
     run<6>("mul_lo_u64", s, clk, false);
     run<7>("shoup_ct_butterfly_c", s, clk, false);
     run<8>("shoup_ct_butterfly_lazy_ptx", s, clk, false);
-    run<9>("shoup_ct_butterfly_lazy_approx_ptx", s, clk, true);
+    run<9>("shoup_ct_butterfly_lazy_approx_ptx", s, clk, false);
+    run<10>("mix_imad_lop3_pairs", s, clk, false);
+    run<11>("mix_imadwide_add64_triples", s, clk, false);
+    run<12>("add64_cc_pairs", s, clk, false);
+    run<13>("add64_3input_c", s, clk, false);
+    run<14>("add64_via_imad_wide", s, clk, false);
+    run<15>("indep_imadwide_plus_add64cc", s, clk, false);
+    run<16>("indep_imadwide_plus_2add32", s, clk, false);
+    run<17>("indep_imadwide_plus_imad", s, clk, true);
     printf("}\n");
     return 0;
 }
