@@ -126,7 +126,7 @@ static Pipe pipe_from_bfv(const nttb200_bfv *b, cudaStream_t st)
     P.n = b->n; P.logn = c->logn; P.r = b->r;
     P.L = LimbArrays{c->q_dev, c->mu_dev, c->qbit_dev, b->inv_q_last_mod_q, b->inv_punctured_q, b->prod_t_gamma_mod_q};
     P.qi_div_t = b->qi_div_t;
-    P.policy_fwd = c->lazy_ok ? kPolicyShoupLazy : kPolicyShoup; P.policy_inv = kPolicyShoup;
+    P.policy_fwd = P.policy_inv = c->lazy_ok ? kPolicyShoupLazy : kPolicyShoup;
     P.psi = c->psi; P.psiinv = c->psiinv; P.psi_s = c->psi_s; P.psiinv_s = c->psiinv_s; P.lc = c->lc;
     P.use_tma = c->use_tma; P.st = st;
     return P;

@@ -108,6 +108,7 @@ int emu_ntt(int inverse, int barrett, int use_tma, int logn, u64 *a, const u64 *
     A.a = a; A.tw = tw; A.tws = tws; A.lc = lc; A.qv = qv; A.muv = muv; A.qbitv = qbitv;
     A.num = num; A.division = division; A.use_tma = (u32)use_tma;
     if (barrett == 2 && !inverse) return run_logn<ShoupLazyPolicy, false>(logn, A);
+    if (barrett == 2 && inverse) return run_logn<ShoupLazyInvPolicy, true>(logn, A);
     if (barrett != 1) return inverse ? run_logn<ShoupPolicy, true>(logn, A) : run_logn<ShoupPolicy, false>(logn, A);
     return inverse ? run_logn<BarrettPolicy, true>(logn, A) : run_logn<BarrettPolicy, false>(logn, A);
 }
@@ -127,7 +128,7 @@ struct EmuRing {
 template <class F> void ew(F &&f) { emu_dim3 g; g.x = 3; emu_launch(g, 64, 0, f); }
 int ring_ntt(const EmuRing &R, bool inv, u64 *a, unsigned num, unsigned division, unsigned gp, size_t gs)
 {
-    return emu_ntt(inv, R.barrett ? 1 : (inv ? 0 : 2), 1, (int)R.logn, a, inv ? R.psiinv : R.psi, inv ? R.psiinv_s : R.psi_s, R.lc, R.q, R.mu, R.qbit,
+    return emu_ntt(inv, R.barrett ? 1 : 2, 1, (int)R.logn, a, inv ? R.psiinv : R.psi, inv ? R.psiinv_s : R.psi_s, R.lc, R.q, R.mu, R.qbit,
                    num, division, gp, gs);
 }
 }  // namespace

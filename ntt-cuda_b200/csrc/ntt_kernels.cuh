@@ -95,6 +95,7 @@ __device__ __forceinline__ void prefetch_round(const P &pol, u32 twbase)
 
 // ---- arithmetic policies ------------------------------------------------------------------------------------
 struct ShoupPolicy {
+    static constexpr bool kLazyGS = false;
     u64 q, twoq, nq;
     const u64 *w, *ws;
     const LimbConst *l;
@@ -166,10 +167,50 @@ struct ShoupLazyPolicy : ShoupPolicy {
     }
 };
 
+// Inverse transform for q < 2^57: approximate quotient and NO per-butterfly correction inside a register round.
+// With B = 4q (the bound of every approximate Shoup product), a Gentleman-Sande butterfly on U < bB, V < bB gives
+// U' = U + V < 2bB and V' = ((U - V + bB) * w) < B.  Starting a round of S <= 4 stages from values < B, the bound of
+// register row p after k stages is B * 2^(k - bitlength(p)) -- a fixed pattern known at compile time -- so the bias of
+// every subtraction is a constant shift of 4q and each row is brought back below B once, at the end of the round, by a
+// ladder of (S - bitlength(p)) conditional subtractions: 15 per 32 butterflies instead of 32.  Largest intermediate:
+// 16 B = 64 q < 2^63.  The last stage of the transform (n^-1 folded in) uses the exact quotient and canonicalises.
+struct ShoupLazyInvPolicy : ShoupPolicy {
+    static constexpr bool kLazyGS = true;
+    u64 fourq;
+    __device__ __forceinline__ void init(const NttArgs &A, u32 limb, u32 n)
+    {
+        ShoupPolicy::init(A, limb, n);
+        fourq = twoq + twoq;
+    }
+    // e: log2 of the common bound multiplier of U and V (compile-time after unrolling)
+    __device__ __forceinline__ void gs_lazy(u64 &U, u64 &V, const Tw &t, int e) const
+    {
+        const u64 s = U + V, d = U - V + (fourq << e);
+        U = s;
+        V = shoup_mul_a(d, t.w, t.ws, nq);
+    }
+    // x < 2^e * B  ->  x < B
+    __device__ __forceinline__ u64 reduce_to_B(u64 x, int e) const
+    {
+        NTT_UNROLL
+        for (int k = 4; k >= 1; k--)
+            if (k <= e) x = csub(x, fourq << (k - 1));
+        return x;
+    }
+    // last stage: U, V < 2^e * B; canonical outputs
+    __device__ __forceinline__ void gs_last_lazy(u64 &U, u64 &V, int e) const
+    {
+        const u64 s = U + V, d = U - V + (fourq << e);
+        U = csub(shoup_mul_n(s, l->ninv, l->ninv_s, nq), q);
+        V = csub(shoup_mul_n(d, l->w1ninv, l->w1ninv_s, nq), q);
+    }
+};
+
 // The reference's own arithmetic, operation for operation (ntt_60bit.cuh:424-440 forward, :494-513 inverse):
 // canonical values, Barrett with the driver's (q, mu, qbit), one halving per inverse stage.  Needs nothing but
 // the reference's tables and constants, so the header drop-in can call it statelessly.
 struct BarrettPolicy {
+    static constexpr bool kLazyGS = false;
     u64 q, mu, q2;
     int qbit;
     const u64 *w;
@@ -220,12 +261,18 @@ __device__ __forceinline__ void one_stage(u64 (&v)[16], u32 twbase, const P &pol
 {
     constexpr int half = 1 << (S - 1 - s);
     const u32 base = twbase << s;
+    // lazy inverse rounds: stages already done in this round = S-1-s, pair position k < half = 2^(S-1-s):
+    // common bound exponent of the pair = (S-1-s) - bitlength(k)
+    [[maybe_unused]] auto bexp = [](int k) { int bl = 0; while ((k >> bl) != 0) bl++; return (S - 1 - s) - bl; };
     if constexpr (s == 0) {
         if constexpr (GS && LAST) {
             NTT_UNROLL
             for (int k = 0; k < half; k++) {
                 NTT_UNROLL
-                for (int c = 0; c < NC; c++) pol.gs_last(v[k * NC + c], v[(k + half) * NC + c]);
+                for (int c = 0; c < NC; c++) {
+                    if constexpr (P::kLazyGS) pol.gs_last_lazy(v[k * NC + c], v[(k + half) * NC + c], bexp(k));
+                    else pol.gs_last(v[k * NC + c], v[(k + half) * NC + c]);
+                }
             }
         } else {
             typename P::Tw t = pol.load(base);
@@ -233,7 +280,8 @@ __device__ __forceinline__ void one_stage(u64 (&v)[16], u32 twbase, const P &pol
             for (int k = 0; k < half; k++) {
                 NTT_UNROLL
                 for (int c = 0; c < NC; c++) {
-                    if constexpr (GS) pol.gs(v[k * NC + c], v[(k + half) * NC + c], t);
+                    if constexpr (GS && P::kLazyGS) pol.gs_lazy(v[k * NC + c], v[(k + half) * NC + c], t, bexp(k));
+                    else if constexpr (GS) pol.gs(v[k * NC + c], v[(k + half) * NC + c], t);
                     else pol.ct(v[k * NC + c], v[(k + half) * NC + c], t);
                 }
             }
@@ -248,7 +296,10 @@ __device__ __forceinline__ void one_stage(u64 (&v)[16], u32 twbase, const P &pol
                 const int i = (b << (S - s)) + k, j = ((b + 1) << (S - s)) + k;
                 NTT_UNROLL
                 for (int c = 0; c < NC; c++) {
-                    if constexpr (GS) {
+                    if constexpr (GS && P::kLazyGS) {
+                        pol.gs_lazy(v[i * NC + c], v[(i + half) * NC + c], t0, bexp(k));
+                        pol.gs_lazy(v[j * NC + c], v[(j + half) * NC + c], t1, bexp(k));
+                    } else if constexpr (GS) {
                         pol.gs(v[i * NC + c], v[(i + half) * NC + c], t0);
                         pol.gs(v[j * NC + c], v[(j + half) * NC + c], t1);
                     } else {
@@ -279,7 +330,20 @@ __device__ __forceinline__ void gs_from(u64 (&v)[16], u32 twbase, const P &pol)
 template <int S, int NC, class P>
 __device__ __forceinline__ void ct_stages(u64 (&v)[16], u32 twbase, const P &pol) { ct_from<S, NC, 0>(v, twbase, pol); }
 template <int S, int NC, bool LAST, class P>
-__device__ __forceinline__ void gs_stages(u64 (&v)[16], u32 twbase, const P &pol) { gs_from<S, NC, S - 1, LAST>(v, twbase, pol); }
+__device__ __forceinline__ void gs_stages(u64 (&v)[16], u32 twbase, const P &pol)
+{
+    gs_from<S, NC, S - 1, LAST>(v, twbase, pol);
+    if constexpr (P::kLazyGS && !LAST) {
+        // row p of the round ends below B * 2^(S - bitlength(p)): bring every row back below B
+        NTT_UNROLL
+        for (int p = 0; p < (1 << S); p++) {
+            int bl = 0;
+            while ((p >> bl) != 0) bl++;
+            NTT_UNROLL
+            for (int c = 0; c < NC; c++) v[p * NC + c] = pol.reduce_to_B(v[p * NC + c], S - bl);
+        }
+    }
+}
 
 // ---- register <-> tile moves ----------------------------------------------------------------------------------
 // 2^S rows (rbase + (i << rsh)) x NC adjacent columns starting at col0

@@ -147,6 +147,7 @@ int launch_ntt_pass(bool inverse, int policy, unsigned logn, const NttArgsHost &
     const unsigned cnt = h.num;
     int r;
     if (policy == kPolicyShoupLazy && !inverse) r = launch_logn<ShoupLazyPolicy, false>(logn, A, which, cnt, ms, mc, st);
+    else if (policy == kPolicyShoupLazy && inverse) r = launch_logn<ShoupLazyInvPolicy, true>(logn, A, which, cnt, ms, mc, st);
     else if (policy != kPolicyBarrett) r = inverse ? launch_logn<ShoupPolicy, true>(logn, A, which, cnt, ms, mc, st) : launch_logn<ShoupPolicy, false>(logn, A, which, cnt, ms, mc, st);
     else r = inverse ? launch_logn<BarrettPolicy, true>(logn, A, which, cnt, ms, mc, st) : launch_logn<BarrettPolicy, false>(logn, A, which, cnt, ms, mc, st);
     if (r) return r;
@@ -171,7 +172,7 @@ int nttb200_inverse_ntt_batch(const nttb200_ctx *ctx, nttb200_u64 *a, unsigned n
 {
     if (!ctx || division == 0 || division > ctx->limbs) return NTTB200_EINVAL;
     NttArgsHost h{a, ctx->psiinv, ctx->psiinv_s, ctx->lc, nullptr, nullptr, nullptr, 0, 0, 0, num, division, ctx->use_tma};
-    return launch_ntt(true, kPolicyShoup, ctx->logn, h, (cudaStream_t)stream);
+    return launch_ntt(true, ctx->lazy_ok ? kPolicyShoupLazy : kPolicyShoup, ctx->logn, h, (cudaStream_t)stream);
 }
 
 int nttb200_ntt_pass(const nttb200_ctx *ctx, nttb200_u64 *a, unsigned num, unsigned division, int inverse, int which, void *stream)
@@ -179,7 +180,7 @@ int nttb200_ntt_pass(const nttb200_ctx *ctx, nttb200_u64 *a, unsigned num, unsig
     if (!ctx || division == 0 || division > ctx->limbs || which < 0 || which > 1) return NTTB200_EINVAL;
     NttArgsHost h{a, inverse ? ctx->psiinv : ctx->psi, inverse ? ctx->psiinv_s : ctx->psi_s, ctx->lc, nullptr, nullptr, nullptr, 0, 0, 0,
                   num, division, ctx->use_tma};
-    return launch_ntt_pass(inverse != 0, (ctx->lazy_ok && !inverse) ? kPolicyShoupLazy : kPolicyShoup, ctx->logn, h, which, (cudaStream_t)stream);
+    return launch_ntt_pass(inverse != 0, ctx->lazy_ok ? kPolicyShoupLazy : kPolicyShoup, ctx->logn, h, which, (cudaStream_t)stream);
 }
 
 int nttb200_ref_forward_ntt_batch(nttb200_u64 *a, unsigned n, const nttb200_u64 *psi_powers, unsigned num, unsigned division,

@@ -124,3 +124,10 @@ def test_emu_lazy_policy_at_its_bound(oracle):
     got = emu.ntt(a, n, qs, psi[None], psiinv[None], 2, 1, inverse=False, barrett=2, use_tma=1)
     assert np.array_equal(got[:n], oracle.forward_ntt_fast(worst, qs[0], psi))
     assert np.array_equal(got[n:], oracle.forward_ntt_fast(rnd, qs[0], psi))
+    # the lazy inverse (bound-tracked rounds, intermediates up to 64 q) on the same worst cases
+    inv = emu.ntt(a, n, qs, psi[None], psiinv[None], 2, 1, inverse=True, barrett=2, use_tma=1)
+    assert np.array_equal(inv[:n], oracle.inverse_ntt_fast(worst, qs[0], psiinv))
+    assert np.array_equal(inv[n:], oracle.inverse_ntt_fast(rnd, qs[0], psiinv))
+    alt = np.where(np.arange(n) % 2 == 0, qs[0] - 1, 0).astype(np.uint64)      # maximises |U - V| in the first stage
+    assert np.array_equal(emu.ntt(alt, n, qs, psi[None], psiinv[None], 1, 1, inverse=True, barrett=2, use_tma=0),
+                          oracle.inverse_ntt_fast(alt, qs[0], psiinv))
