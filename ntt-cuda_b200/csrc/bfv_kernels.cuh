@@ -14,6 +14,8 @@
 #include "modarith.cuh"
 #include "pointwise_kernels.cuh"
 
+#define NTTB200_MAX_LIMBS_INTERNAL 64
+
 namespace nttb200 {
 
 // ---- Salsa20/20 -------------------------------------------------------------------------------------------------------
@@ -145,126 +147,200 @@ NTT_KERNEL void k_convert_ternary_gaussian_x2(const unsigned char *in, u64 *c, u
 // keygen  (bfv_keygen.cuh:120-122):  bytes [0,n) ternary | u64 at n + 8*(l*n + j) uniform | u32 at n + 8rn + 4j gaussian
 // encrypt (bfv_encryption.cuh:23,49,79): bytes [0,n) ternary u | u32 at n + 4j -> e0 | u32 at 5n + 4j -> e1
 
-// keygen sampling: sk = ternary (all limbs), pk1 = uniform, es[k][j] = gaussian draw (signed)
+// Launch geometry of the fused kernels: blockIdx.x strides over coefficient PAIRS (16-byte accesses), blockIdx.y / .z carry
+// the limb / half / item, so no thread ever divides by n or r.  Per-limb constants (and the few 64-bit divisions they
+// need) are computed once per CTA into shared memory.
+#define NTT_PAIR_STRIDE(j, n) \
+    for (u32 j = (blockIdx.x * blockDim.x + threadIdx.x) * 2u; j < (n); j += gridDim.x * blockDim.x * 2u)
+
+constexpr int kMaxLimbs = NTTB200_MAX_LIMBS_INTERNAL;
+
+// exact x mod q for any 64-bit x, ratio = floor(2^64 / q): x - floor(x * ratio / 2^64) * q is in [0, 2q).  The remainder
+// is unique, so this is bit-identical to the reference's `%` (bfv_encryption.cuh:146,209; poly_arithmetic.cuh:248).
+__host__ __device__ __forceinline__ u64 mod_exact(u64 x, u64 q, u64 ratio) { return csub(x - mulhi64(x, ratio) * q, q); }
+__host__ __device__ __forceinline__ u64 ratio_of(u64 q) { return ~0ull / q; }   // = floor(2^64 / q) for odd q > 1
+
+__device__ __forceinline__ ulonglong2 ld2(const u64 *p) { return *reinterpret_cast<const ulonglong2 *>(p); }
+__device__ __forceinline__ void st2(u64 *p, u64 a, u64 b) { *reinterpret_cast<ulonglong2 *>(p) = make_ulonglong2(a, b); }
+
+// keygen sampling: sk = ternary (all limbs), pk1 = uniform, es[k][j] = gaussian draw (signed).  grid (x, batch)
 NTT_KERNEL void k_keygen_sample(const unsigned char *in, size_t in_stride, u64 *sk, u64 *pk, int *es, unsigned n, unsigned r,
                                 unsigned batch, const u64 *q)
 {
-    const size_t rn = (size_t)r * n;
-    NTT_GRID_STRIDE(i, (size_t)batch * n) {
-        const size_t k = i / n, j = i - k * n;
-        const unsigned char *s = in + k * in_stride;
-        const unsigned char byte = s[j];
-        es[i] = gaussian_value(reinterpret_cast<const u32 *>(s + n + 8 * rn)[j]);
+    (void)batch;
+    const size_t rn = (size_t)r * n, k = blockIdx.y;
+    const unsigned char *s = in + k * in_stride;
+    NTT_PAIR_STRIDE(j, n) {
+        const unsigned char b0 = s[j], b1 = s[j + 1];
+        const u32 *g = reinterpret_cast<const u32 *>(s + n + 8 * rn) + j;
+        es[k * n + j] = gaussian_value(g[0]);
+        es[k * n + j + 1] = gaussian_value(g[1]);
         for (unsigned l = 0; l < r; l++) {
             const u64 ql = q[l];
-            sk[k * rn + (size_t)l * n + j] = ternary_value(byte, ql);
-            pk[k * 2 * rn + rn + (size_t)l * n + j] = uniform_value(reinterpret_cast<const u64 *>(s + n)[(size_t)l * n + j], ql);
+            st2(sk + k * rn + (size_t)l * n + j, ternary_value(b0, ql), ternary_value(b1, ql));
+            const ulonglong2 u = ld2(reinterpret_cast<const u64 *>(s + n) + (size_t)l * n + j);
+            st2(pk + k * 2 * rn + rn + (size_t)l * n + j, uniform_value(u.x, ql), uniform_value(u.y, ql));
         }
     }
 }
-// pk0 = pk1 (.) sk   (barrett_batch_3param, bfv_keygen.cuh:132)
+// pk0 = pk1 (.) sk   (barrett_batch_3param, bfv_keygen.cuh:132).  grid (x, r, batch)
 NTT_KERNEL void k_keygen_mul(u64 *pk, const u64 *sk, unsigned n, unsigned r, unsigned batch, LimbArrays L)
 {
-    const size_t rn = (size_t)r * n;
-    NTT_GRID_STRIDE(i, (size_t)batch * rn) {
-        const size_t k = i / rn, rem = i - k * rn;
-        const unsigned l = (unsigned)(rem / n);
-        pk[k * 2 * rn + rem] = barrett_ref(pk[k * 2 * rn + rn + rem], sk[i], L.q[l], L.mu[l], (int)L.qbit[l]);
+    (void)batch;
+    const unsigned l = blockIdx.y;
+    const size_t rn = (size_t)r * n, k = blockIdx.z;
+    const u64 q = L.q[l], mu = L.mu[l];
+    const int qb = (int)L.qbit[l];
+    u64 *p0 = pk + k * 2 * rn + (size_t)l * n;
+    const u64 *p1 = p0 + rn, *s = sk + k * rn + (size_t)l * n;
+    NTT_PAIR_STRIDE(j, n) {
+        const ulonglong2 a = ld2(p1 + j), b = ld2(s + j);
+        st2(p0 + j, barrett_ref(a.x, b.x, q, mu, qb), barrett_ref(a.y, b.y, q, mu, qb));
     }
 }
-// pk0 = -(pk0 + e)   (gaussian_dist_xq + poly_add_negate_xq, bfv_keygen.cuh:47-93)
+// pk0 = -(pk0 + e)   (gaussian_dist_xq + poly_add_negate_xq, bfv_keygen.cuh:47-93).  grid (x, r, batch)
 NTT_KERNEL void k_keygen_add_negate(u64 *pk, const int *es, unsigned n, unsigned r, unsigned batch, LimbArrays L)
 {
-    const size_t rn = (size_t)r * n;
-    NTT_GRID_STRIDE(i, (size_t)batch * rn) {
-        const size_t k = i / rn, rem = i - k * rn;
-        const unsigned l = (unsigned)(rem / n);
-        const u64 q = L.q[l];
-        u64 ra = pk[k * 2 * rn + rem] + signed_to_residue(es[k * n + rem % n], q);
-        if (ra >= q) ra -= q;
-        ra = q - ra;
-        pk[k * 2 * rn + rem] = ra * (u64)(ra != q);
+    (void)batch;
+    const unsigned l = blockIdx.y;
+    const size_t rn = (size_t)r * n, k = blockIdx.z;
+    const u64 q = L.q[l];
+    u64 *p0 = pk + k * 2 * rn + (size_t)l * n;
+    const int *e = es + k * n;
+    NTT_PAIR_STRIDE(j, n) {
+        const ulonglong2 a = ld2(p0 + j);
+        u64 r0 = a.x + signed_to_residue(e[j], q), r1 = a.y + signed_to_residue(e[j + 1], q);
+        if (r0 >= q) r0 -= q;
+        if (r1 >= q) r1 -= q;
+        r0 = q - r0; r1 = q - r1;
+        st2(p0 + j, r0 * (u64)(r0 != q), r1 * (u64)(r1 != q));
     }
 }
 
 // encryption sampling: u (ternary) into half 0 of c for every limb; es[k][0][j], es[k][1][j] = the two gaussian draws
+// grid (x, batch)
 NTT_KERNEL void k_encrypt_sample(const unsigned char *in, size_t in_stride, u64 *c, int *es, unsigned n, unsigned r, unsigned batch,
                                  const u64 *q)
 {
-    const size_t rn = (size_t)r * n;
-    NTT_GRID_STRIDE(i, (size_t)batch * n) {
-        const size_t k = i / n, j = i - k * n;
-        const unsigned char *s = in + k * in_stride;
-        const unsigned char byte = s[j];
-        es[k * 2 * n + j] = gaussian_value(reinterpret_cast<const u32 *>(s + n)[j]);
-        es[k * 2 * n + n + j] = gaussian_value(reinterpret_cast<const u32 *>(s + (size_t)n * 5)[j]);
-        for (unsigned l = 0; l < r; l++) c[k * 2 * rn + (size_t)l * n + j] = ternary_value(byte, q[l]);
+    (void)batch;
+    const size_t rn = (size_t)r * n, k = blockIdx.y;
+    const unsigned char *s = in + k * in_stride;
+    NTT_PAIR_STRIDE(j, n) {
+        const unsigned char b0 = s[j], b1 = s[j + 1];
+        const u32 *g0 = reinterpret_cast<const u32 *>(s + n) + j, *g1 = reinterpret_cast<const u32 *>(s + (size_t)n * 5) + j;
+        int *e = es + k * 2 * n;
+        e[j] = gaussian_value(g0[0]); e[j + 1] = gaussian_value(g0[1]);
+        e[n + j] = gaussian_value(g1[0]); e[n + j + 1] = gaussian_value(g1[1]);
+        for (unsigned l = 0; l < r; l++) {
+            const u64 ql = q[l];
+            st2(c + k * 2 * rn + (size_t)l * n + j, ternary_value(b0, ql), ternary_value(b1, ql));
+        }
     }
 }
 // c0 = NTT(u) (.) pk0, c1 = NTT(u) (.) pk1 -- the reference transforms u twice; here NTT(u) sits in
-// half 0 and is read once.  pk_stride = 0: one public key for the whole batch.
+// half 0 and is read once.  pk_stride = 0: one public key for the whole batch.  grid (x, r, batch)
 NTT_KERNEL void k_encrypt_mul(u64 *c, const u64 *pk, size_t pk_stride, unsigned n, unsigned r, unsigned batch, LimbArrays L)
 {
-    const size_t rn = (size_t)r * n;
-    NTT_GRID_STRIDE(i, (size_t)batch * rn) {
-        const size_t k = i / rn, rem = i - k * rn;
-        const unsigned l = (unsigned)(rem / n);
-        const u64 q = L.q[l], mu = L.mu[l];
-        const int qb = (int)L.qbit[l];
-        const u64 *pkk = pk + k * pk_stride;
-        const u64 uh = c[k * 2 * rn + rem];
-        c[k * 2 * rn + rem] = barrett_ref(uh, pkk[rem], q, mu, qb);
-        c[k * 2 * rn + rn + rem] = barrett_ref(uh, pkk[rn + rem], q, mu, qb);
+    (void)batch;
+    const unsigned l = blockIdx.y;
+    const size_t rn = (size_t)r * n, k = blockIdx.z;
+    const u64 q = L.q[l], mu = L.mu[l];
+    const int qb = (int)L.qbit[l];
+    u64 *c0 = c + k * 2 * rn + (size_t)l * n, *c1 = c0 + rn;
+    const u64 *p0 = pk + k * pk_stride + (size_t)l * n, *p1 = p0 + rn;
+    NTT_PAIR_STRIDE(j, n) {
+        const ulonglong2 uh = ld2(c0 + j), a = ld2(p0 + j), b = ld2(p1 + j);
+        st2(c0 + j, barrett_ref(uh.x, a.x, q, mu, qb), barrett_ref(uh.y, a.y, q, mu, qb));
+        st2(c1 + j, barrett_ref(uh.x, b.x, q, mu, qb), barrett_ref(uh.y, b.y, q, mu, qb));
     }
 }
+
+struct EncLimb { u64 q, mu, ratio, half_mod, inv_q_last, qdt; int qbit, pad; };
 // poly_add_xq + divide_and_round_q_last_inplace_add_x2 + ..._loop_xq + weird_m_stuff (bfv_encryption.cuh:111-212)
-// in one pass; thread = (item, half, coefficient).  The dropped limb r-1 keeps the value the reference leaves there.
+// in one pass.  grid (x, 2 halves, batch).  The dropped limb r-1 keeps the value the reference leaves there.
 NTT_KERNEL void k_encrypt_epilogue(u64 *c, const int *es, const u64 *m_poly, size_t m_stride, unsigned n, unsigned r, unsigned batch, u64 t,
                                    const u64 *qi_div_t, LimbArrays L)
 {
-    const size_t rn = (size_t)r * n;
+    (void)batch;
+    NTT_SHARED EncLimb K[kMaxLimbs];
     const u64 last = L.q[r - 1], half_last = last >> 1;
-    NTT_GRID_STRIDE(i, (size_t)batch * 2 * n) {
-        const size_t k = i / (2 * (size_t)n), rem = i - k * 2 * n;
-        const unsigned h = (unsigned)(rem / n);
-        const size_t j = rem - (size_t)h * n;
-        u64 *ch = c + k * 2 * rn + (size_t)h * rn;
-        const int dd = es[k * 2 * n + (size_t)h * n + j];
+    if (threadIdx.x + 1 < r) {
+        const unsigned l = threadIdx.x;
+        EncLimb e;
+        e.q = L.q[l]; e.mu = L.mu[l]; e.qbit = (int)L.qbit[l]; e.pad = 0;
+        e.ratio = ratio_of(e.q);
+        e.half_mod = half_last % e.q;
+        e.inv_q_last = L.inv_q_last_mod_q[l];
+        e.qdt = qi_div_t[l];
+        K[l] = e;
+    }
+    __syncthreads();
+    const unsigned h = blockIdx.y;
+    const size_t rn = (size_t)r * n, k = blockIdx.z;
+    u64 *ch = c + k * 2 * rn + (size_t)h * rn;
+    const int *e = es + k * 2 * n + (size_t)h * n;
+    const u64 *mp = m_poly + k * m_stride;
+    const u64 tfix = (t + 1) >> 1;
+    // t is a power of two in every reference parameter set; keep the general division for anything else
+    const bool tpow2 = (t & (t - 1)) == 0;
+    int tsh = 0;
+    while (tpow2 && (1ull << tsh) < t) tsh++;
+    NTT_PAIR_STRIDE(j, n) {
+        const int d0 = e[j], d1 = e[j + 1];
         // last limb: += e (`>` quirk, :187), += floor(q_last / 2) mod q_last (:121-124)
-        u64 cl = ch[(size_t)(r - 1) * n + j] + signed_to_residue(dd, last);
-        if (cl > last) cl -= last;
-        cl += half_last;
-        if (cl >= last) cl -= last;
-        ch[(size_t)(r - 1) * n + j] = cl;
-        u64 m = 0, fix = 0;
-        if (h == 0) { m = m_poly[k * m_stride + j]; fix = (m + ((t + 1) >> 1)) / t; }
+        const ulonglong2 lv = ld2(ch + (size_t)(r - 1) * n + j);
+        u64 cl0 = lv.x + signed_to_residue(d0, last), cl1 = lv.y + signed_to_residue(d1, last);
+        if (cl0 > last) cl0 -= last;
+        if (cl1 > last) cl1 -= last;
+        cl0 += half_last; cl1 += half_last;
+        if (cl0 >= last) cl0 -= last;
+        if (cl1 >= last) cl1 -= last;
+        st2(ch + (size_t)(r - 1) * n + j, cl0, cl1);
+        u64 m0 = 0, m1 = 0, f0 = 0, f1 = 0;
+        if (h == 0) {
+            const ulonglong2 mv = ld2(mp + j);
+            m0 = mv.x; m1 = mv.y;
+            f0 = tpow2 ? (m0 + tfix) >> tsh : (m0 + tfix) / t;
+            f1 = tpow2 ? (m1 + tfix) >> tsh : (m1 + tfix) / t;
+        }
         for (unsigned l = 0; l + 1 < r; l++) {
-            const u64 q = L.q[l];
-            u64 x = ch[(size_t)l * n + j] + signed_to_residue(dd, q);
-            if (x > q) x -= q;
-            const u64 half_mod = half_last % q;
-            u64 tp = cl % q;
-            if (tp < half_mod) tp += q;
-            tp -= half_mod;
-            if (x < tp) x += q;
-            x -= tp;
-            x = barrett_ref(x, L.inv_q_last_mod_q[l], q, L.mu[l], (int)L.qbit[l]);
-            if (h == 0) x = (x + ((m * qi_div_t[l]) + fix)) % q;
-            ch[(size_t)l * n + j] = x;
+            const EncLimb &P = K[l];
+            const ulonglong2 xv = ld2(ch + (size_t)l * n + j);
+            u64 x0 = xv.x + signed_to_residue(d0, P.q), x1 = xv.y + signed_to_residue(d1, P.q);
+            if (x0 > P.q) x0 -= P.q;
+            if (x1 > P.q) x1 -= P.q;
+            u64 t0 = mod_exact(cl0, P.q, P.ratio), t1 = mod_exact(cl1, P.q, P.ratio);
+            if (t0 < P.half_mod) t0 += P.q;
+            if (t1 < P.half_mod) t1 += P.q;
+            t0 -= P.half_mod; t1 -= P.half_mod;
+            if (x0 < t0) x0 += P.q;
+            if (x1 < t1) x1 += P.q;
+            x0 -= t0; x1 -= t1;
+            x0 = barrett_ref(x0, P.inv_q_last, P.q, P.mu, P.qbit);
+            x1 = barrett_ref(x1, P.inv_q_last, P.q, P.mu, P.qbit);
+            if (h == 0) {
+                x0 = mod_exact(x0 + ((m0 * P.qdt) + f0), P.q, P.ratio);
+                x1 = mod_exact(x1 + ((m1 * P.qdt) + f1), P.q, P.ratio);
+            }
+            st2(ch + (size_t)l * n + j, x0, x1);
         }
     }
 }
 
-// c1 = NTT(c1) (.) sk    (barrett_batch, bfv_decryption.cuh:100).  c1 of item k = c + k*item_stride + c1_off.
+// c1 = NTT(c1) (.) sk    (barrett_batch, bfv_decryption.cuh:100).  c1 of item k = c + k*item_stride + c1_off.  grid (x, rp, batch)
 NTT_KERNEL void k_decrypt_mul(u64 *c, size_t item_stride, size_t c1_off, const u64 *sk, size_t sk_stride, unsigned n, unsigned rp,
                               unsigned batch, LimbArrays L)
 {
-    const size_t rn = (size_t)rp * n;
-    NTT_GRID_STRIDE(i, (size_t)batch * rn) {
-        const size_t k = i / rn, rem = i - k * rn;
-        const unsigned l = (unsigned)(rem / n);
-        u64 *p = c + k * item_stride + c1_off + rem;
-        *p = barrett_ref(*p, sk[k * sk_stride + rem], L.q[l], L.mu[l], (int)L.qbit[l]);
+    (void)batch; (void)rp;
+    const unsigned l = blockIdx.y;
+    const size_t k = blockIdx.z;
+    const u64 q = L.q[l], mu = L.mu[l];
+    const int qb = (int)L.qbit[l];
+    u64 *p = c + k * item_stride + c1_off + (size_t)l * n;
+    const u64 *s = sk + k * sk_stride + (size_t)l * n;
+    NTT_PAIR_STRIDE(j, n) {
+        const ulonglong2 a = ld2(p + j), b = ld2(s + j);
+        st2(p + j, barrett_ref(a.x, b.x, q, mu, qb), barrett_ref(a.y, b.y, q, mu, qb));
     }
 }
 struct DecryptConsts {
@@ -273,33 +349,67 @@ struct DecryptConsts {
     unsigned rp;          // limbs after the drop (the driver's q_amount after q_amount--)
     const u64 *bcm;       // [2][rp]: prod_{i != j} q_i mod t | mod gamma   (demo.cu:248-264)
 };
+struct DecLimb { u64 q, mu, ptg, ipq, bt, bg; int qbit, pad; };
+// (acc + v) mod gamma for acc < gamma and v < 2*gamma (the reference's Barrett may leave v in [gamma, 2 gamma)): the sum is
+// below 3*gamma, so two conditional subtractions are the exact remainder the reference's `%` computes.
+__host__ __device__ __forceinline__ u64 add_mod_gamma(u64 acc, u64 v, u64 gamma)
+{
+    u64 s = acc + v;
+    if (s >= gamma) s -= gamma;
+    if (s >= gamma) s -= gamma;
+    return s;
+}
+__device__ __forceinline__ void dec_stage_limbs(DecLimb *K, unsigned first, unsigned count, const DecryptConsts &D, const LimbArrays &L)
+{
+    if (threadIdx.x < count) {
+        const unsigned l = first + threadIdx.x;
+        DecLimb e;
+        e.q = L.q[l]; e.mu = L.mu[l]; e.qbit = (int)L.qbit[l]; e.pad = 0;
+        e.ptg = L.prod_t_gamma_mod_q[l]; e.ipq = L.inv_punctured_q[l];
+        e.bt = D.bcm[l]; e.bg = D.bcm[l + D.rp];
+        K[threadIdx.x] = e;
+    }
+    __syncthreads();
+}
+// one limb's contribution: c1 += c0 (`>` quirk), *= t*gamma, *= punctured inverse, accumulate both base conversions
+__device__ __forceinline__ void dec_accumulate(const DecLimb &P, u64 a1, u64 a0, u32 mask32, const DecryptConsts &D, u64 &acc_t, u64 &acc_g)
+{
+    u64 v = a1 + a0;
+    if (v > P.q) v -= P.q;
+    v = barrett_ref(v, P.ptg, P.q, P.mu, P.qbit);
+    v = barrett_ref(v, P.ipq, P.q, P.mu, P.qbit);
+    acc_t += (v * P.bt) & (u64)mask32;
+    acc_g = add_mod_gamma(acc_g, barrett_ref(v, P.bg, D.gamma, D.mu_gamma, D.gamma_bits), D.gamma);
+}
+__device__ __forceinline__ u64 dec_finish_one(u64 acc_t, u64 acc_g, u32 mask32, const DecryptConsts &D)
+{
+    u64 mt = acc_t & (u64)mask32;
+    u64 mg = acc_g >= D.gamma ? acc_g % D.gamma : acc_g;
+    mt = (mt * D.neg_inv_t) & (u64)mask32;                                       // mod_t
+    mg = barrett_ref(mg, D.neg_inv_gamma, D.gamma, D.mu_gamma, D.gamma_bits);       // barrett_int
+    const u64 tmask = D.t - 1;
+    return mg > D.gamma_div_2 ? ((mt + (D.gamma - mg)) & tmask) : ((mt - mg) & tmask);
+}
 // poly_add_xq_d, poly_mul_int_xq_prodtgamma, poly_mul_int_xq_invpq (bfv_decryption.cuh:13-57), fast_convert_array_kernel_t,
 // _gamma (poly_arithmetic.cuh:217-251), mod_t, barrett_int, dec_round_kernel (:128-141, :100-126, :253-263) in one pass.
-// Writes n plaintext coefficients per item to out + k*out_stride.
+// Writes n plaintext coefficients per item to out + k*out_stride.  grid (x, batch)
 NTT_KERNEL void k_decrypt_epilogue(const u64 *c, size_t item_stride, size_t c1_off, u64 *out, size_t out_stride, unsigned n, unsigned batch,
                                    DecryptConsts D, LimbArrays L)
 {
+    (void)batch;
+    NTT_SHARED DecLimb K[kMaxLimbs];
+    dec_stage_limbs(K, 0, D.rp, D, L);
     const u32 mask32 = (u32)(D.t - 1);
-    NTT_GRID_STRIDE(i, (size_t)batch * n) {
-        const size_t k = i / n, j = i - k * n;
-        const u64 *c0 = c + k * item_stride, *c1 = c0 + c1_off;
-        u64 acc_t = 0, acc_g = 0;
+    const size_t k = blockIdx.y;
+    const u64 *c0 = c + k * item_stride, *c1 = c0 + c1_off;
+    NTT_PAIR_STRIDE(j, n) {
+        u64 at0 = 0, at1 = 0, ag0 = 0, ag1 = 0;
         for (unsigned l = 0; l < D.rp; l++) {
-            const u64 q = L.q[l], mu = L.mu[l];
-            const int qb = (int)L.qbit[l];
-            u64 v = c1[(size_t)l * n + j] + c0[(size_t)l * n + j];
-            if (v > q) v -= q;
-            v = barrett_ref(v, L.prod_t_gamma_mod_q[l], q, mu, qb);
-            v = barrett_ref(v, L.inv_punctured_q[l], q, mu, qb);
-            acc_t += (v * D.bcm[l]) & (u64)mask32;
-            acc_g = (acc_g + barrett_ref(v, D.bcm[l + D.rp], D.gamma, D.mu_gamma, D.gamma_bits)) % D.gamma;
+            const ulonglong2 a1 = ld2(c1 + (size_t)l * n + j), a0 = ld2(c0 + (size_t)l * n + j);
+            dec_accumulate(K[l], a1.x, a0.x, mask32, D, at0, ag0);
+            dec_accumulate(K[l], a1.y, a0.y, mask32, D, at1, ag1);
         }
-        u64 mt = acc_t & (u64)mask32;
-        u64 mg = acc_g % D.gamma;
-        mt = (mt * D.neg_inv_t) & (u64)mask32;                                   // mod_t
-        mg = barrett_ref(mg, D.neg_inv_gamma, D.gamma, D.mu_gamma, D.gamma_bits);   // barrett_int
-        const u64 tmask = D.t - 1;
-        out[k * out_stride + j] = mg > D.gamma_div_2 ? ((mt + (D.gamma - mg)) & tmask) : ((mt - mg) & tmask);
+        st2(out + k * out_stride + j, dec_finish_one(at0, ag0, mask32, D), dec_finish_one(at1, ag1, mask32, D));
     }
 }
 
@@ -312,37 +422,31 @@ NTT_KERNEL void k_decrypt_epilogue(const u64 *c, size_t item_stride, size_t c1_o
 NTT_KERNEL void k_decrypt_partial(const u64 *c, size_t item_stride, size_t c1_off, u64 *part, unsigned n, unsigned batch, unsigned first,
                                   unsigned count, DecryptConsts D, LimbArrays L)
 {
+    (void)batch;
+    NTT_SHARED DecLimb K[kMaxLimbs];
+    dec_stage_limbs(K, first, count, D, L);          // constants are indexed by the global limb, data by the local one
     const u32 mask32 = (u32)(D.t - 1);
-    NTT_GRID_STRIDE(i, (size_t)batch * n) {
-        const size_t k = i / n, j = i - k * n;
-        const u64 *c0 = c + k * item_stride, *c1 = c0 + c1_off;
-        u64 acc_t = 0, acc_g = 0;
+    const size_t k = blockIdx.y;
+    const u64 *c0 = c + k * item_stride, *c1 = c0 + c1_off;
+    NTT_PAIR_STRIDE(j, n) {
+        u64 at0 = 0, at1 = 0, ag0 = 0, ag1 = 0;
         for (unsigned ll = 0; ll < count; ll++) {
-            const unsigned l = first + ll;                 // global limb: constants are indexed globally, data locally
-            const u64 q = L.q[l], mu = L.mu[l];
-            const int qb = (int)L.qbit[l];
-            u64 v = c1[(size_t)ll * n + j] + c0[(size_t)ll * n + j];
-            if (v > q) v -= q;
-            v = barrett_ref(v, L.prod_t_gamma_mod_q[l], q, mu, qb);
-            v = barrett_ref(v, L.inv_punctured_q[l], q, mu, qb);
-            acc_t += (v * D.bcm[l]) & (u64)mask32;
-            acc_g = (acc_g + barrett_ref(v, D.bcm[l + D.rp], D.gamma, D.mu_gamma, D.gamma_bits)) % D.gamma;
+            const ulonglong2 a1 = ld2(c1 + (size_t)ll * n + j), a0 = ld2(c0 + (size_t)ll * n + j);
+            dec_accumulate(K[ll], a1.x, a0.x, mask32, D, at0, ag0);
+            dec_accumulate(K[ll], a1.y, a0.y, mask32, D, at1, ag1);
         }
-        part[k * 2 * n + j] = acc_t;
-        part[k * 2 * n + n + j] = acc_g;
+        st2(part + k * 2 * n + j, at0, at1);
+        st2(part + k * 2 * n + n + j, ag0, ag1);
     }
 }
 NTT_KERNEL void k_decrypt_finish(const u64 *part_sum, u64 *out, size_t out_stride, unsigned n, unsigned batch, DecryptConsts D)
 {
+    (void)batch;
     const u32 mask32 = (u32)(D.t - 1);
-    NTT_GRID_STRIDE(i, (size_t)batch * n) {
-        const size_t k = i / n, j = i - k * n;
-        u64 mt = part_sum[k * 2 * n + j] & (u64)mask32;
-        u64 mg = part_sum[k * 2 * n + n + j] % D.gamma;
-        mt = (mt * D.neg_inv_t) & (u64)mask32;
-        mg = barrett_ref(mg, D.neg_inv_gamma, D.gamma, D.mu_gamma, D.gamma_bits);
-        const u64 tmask = D.t - 1;
-        out[k * out_stride + j] = mg > D.gamma_div_2 ? ((mt + (D.gamma - mg)) & tmask) : ((mt - mg) & tmask);
+    const size_t k = blockIdx.y;
+    NTT_PAIR_STRIDE(j, n) {
+        const ulonglong2 pt = ld2(part_sum + k * 2 * n + j), pg = ld2(part_sum + k * 2 * n + n + j);
+        st2(out + k * out_stride + j, dec_finish_one(pt.x, pg.x % D.gamma, mask32, D), dec_finish_one(pt.y, pg.y % D.gamma, mask32, D));
     }
 }
 

@@ -34,6 +34,7 @@ float emu_normcdfinvf(float x);   // double-precision stand-in; GPU parity for t
 #define normcdfinvf emu_normcdfinvf
 #define NTT_DYN_SMEM(name) unsigned char *name = emu_dyn_smem
 #define NTT_KERNEL static
+#define NTT_SHARED static          /* the emulator runs one CTA at a time: a function-local static is CTA-shared */
 #define NTT_UNROLL _Pragma("GCC unroll 32")
 #else
 // ---------------------------------------------------------------------------------------------
@@ -41,5 +42,6 @@ float emu_normcdfinvf(float x);   // double-precision stand-in; GPU parity for t
 #define NTT_RESTRICT __restrict__
 #define NTT_DYN_SMEM(name) extern __shared__ __align__(1024) unsigned char name[]
 #define NTT_KERNEL static __global__   /* header-defined kernels: internal linkage per translation unit */
+#define NTT_SHARED __shared__
 #define NTT_UNROLL _Pragma("unroll")
 #endif

@@ -126,6 +126,7 @@ struct EmuRing {
     int barrett;    // 1: stateless Barrett NTT, 0: Shoup (lazy forward)
 };
 template <class F> void ew(F &&f) { emu_dim3 g; g.x = 3; emu_launch(g, 64, 0, f); }
+template <class F> void ew3(unsigned y, unsigned z, F &&f) { emu_dim3 g; g.x = 2; g.y = y; g.z = z; emu_launch(g, 64, 0, f); }
 int ring_ntt(const EmuRing &R, bool inv, u64 *a, unsigned num, unsigned division, unsigned gp, size_t gs)
 {
     return emu_ntt(inv, R.barrett ? 1 : 2, 1, (int)R.logn, a, inv ? R.psiinv : R.psi, inv ? R.psiinv_s : R.psi_s, R.lc, R.q, R.mu, R.qbit,
@@ -151,28 +152,28 @@ EXPORT int emu_bfv(int op, unsigned n, unsigned r, const u64 *q, const u64 *mu, 
     if (op == 0) {          // keygen
         const size_t stride = 9 * rn + 4 * (size_t)n; const u64 nblk = stride / 64;
         ew([&] { k_salsa20_keystream(in, nblk, (u64)batch, stride, key, nonce0); });
-        ew([&] { k_keygen_sample(in, stride, sk, pk, es, n, r, batch, q); });
+        ew3(batch, 1, [&] { k_keygen_sample(in, stride, sk, pk, es, n, r, batch, q); });
         ring_ntt(R, false, sk, batch * r, r, 0, 0);
-        ew([&] { k_keygen_mul(pk, sk, n, r, batch, L); });
+        ew3(r, batch, [&] { k_keygen_mul(pk, sk, n, r, batch, L); });
         ring_ntt(R, true, pk, batch * r, r, r, 2 * rn);
-        ew([&] { k_keygen_add_negate(pk, es, n, r, batch, L); });
+        ew3(r, batch, [&] { k_keygen_add_negate(pk, es, n, r, batch, L); });
         ring_ntt(R, false, pk, batch * r, r, r, 2 * rn);
     } else if (op == 1) {   // encrypt
         const size_t stride = 9 * (size_t)n; const u64 nblk = stride / 64;
         ew([&] { k_salsa20_keystream(in, nblk, (u64)batch, stride, key, nonce0); });
-        ew([&] { k_encrypt_sample(in, stride, c, es, n, r, batch, q); });
+        ew3(batch, 1, [&] { k_encrypt_sample(in, stride, c, es, n, r, batch, q); });
         ring_ntt(R, false, c, batch * r, r, r, 2 * rn);
-        ew([&] { k_encrypt_mul(c, pk, per_item_keys ? 2 * rn : 0, n, r, batch, L); });
+        ew3(r, batch, [&] { k_encrypt_mul(c, pk, per_item_keys ? 2 * rn : 0, n, r, batch, L); });
         ring_ntt(R, true, c, batch * 2 * r, r, 0, 0);
-        ew([&] { k_encrypt_epilogue(c, es, m, (size_t)n, n, r, batch, t, qi_div_t, L); });
+        ew3(2, batch, [&] { k_encrypt_epilogue(c, es, m, (size_t)n, n, r, batch, t, qi_div_t, L); });
     } else {                // decrypt (r = all limbs)
         const unsigned rp = r - 1;
         const size_t item = 2 * rn, c1_off = rn;
         DecryptConsts D{t, gamma, mu_gamma, gamma >> 1, neg_inv_t, neg_inv_gamma, gamma_bits, rp, bcm};
         ring_ntt(R, false, c + c1_off, batch * rp, rp, rp, item);
-        ew([&] { k_decrypt_mul(c, item, c1_off, sk, per_item_keys ? rn : 0, n, rp, batch, L); });
+        ew3(rp, batch, [&] { k_decrypt_mul(c, item, c1_off, sk, per_item_keys ? rn : 0, n, rp, batch, L); });
         ring_ntt(R, true, c + c1_off, batch * rp, rp, rp, item);
-        ew([&] { k_decrypt_epilogue(c, item, c1_off, out, (size_t)n, n, batch, D, L); });
+        ew3(batch, 1, [&] { k_decrypt_epilogue(c, item, c1_off, out, (size_t)n, n, batch, D, L); });
     }
     return 0;
 }
@@ -229,11 +230,11 @@ EXPORT int emu_bfv_sharded(int op, unsigned n, unsigned r, const u64 *q, const u
         LimbArrays Lglob{q, mu, qbit, nullptr, ipq, ptg};
         const size_t item = (size_t)2 * count * n, c1_off = (size_t)count * n;
         ring_ntt(R, false, c_shard + c1_off, batch * count, count, count, item);
-        ew([&] { k_decrypt_mul(c_shard, item, c1_off, sk_shard, 0, n, count, batch, Lloc); });
+        ew3(count, batch, [&] { k_decrypt_mul(c_shard, item, c1_off, sk_shard, 0, n, count, batch, Lloc); });
         ring_ntt(R, true, c_shard + c1_off, batch * count, count, count, item);
-        ew([&] { k_decrypt_partial(c_shard, item, c1_off, part, n, batch, first, count, D, Lglob); });
+        ew3(batch, 1, [&] { k_decrypt_partial(c_shard, item, c1_off, part, n, batch, first, count, D, Lglob); });
     } else {
-        ew([&] { k_decrypt_finish(part, out, (size_t)n, n, batch, D); });
+        ew3(batch, 1, [&] { k_decrypt_finish(part, out, (size_t)n, n, batch, D); });
     }
     return 0;
 }

@@ -31,6 +31,7 @@ extern thread_local EmuCta *emu_cta;
 template <class F>
 void emu_launch(emu_dim3 grid, unsigned block, size_t smem_bytes, F &&body)
 {
+    for (unsigned bz = 0; bz < grid.z; bz++)
     for (unsigned by = 0; by < grid.y; by++)
         for (unsigned bx = 0; bx < grid.x; bx++) {
             std::vector<unsigned char> smem(smem_bytes + 16);
@@ -44,7 +45,7 @@ void emu_launch(emu_dim3 grid, unsigned block, size_t smem_bytes, F &&body)
             th.reserve(block);
             for (unsigned t = 0; t < block; t++)
                 th.emplace_back([&, t] {
-                    threadIdx.x = t; blockIdx.x = bx; blockIdx.y = by;
+                    threadIdx.x = t; blockIdx.x = bx; blockIdx.y = by; blockIdx.z = bz;
                     blockDim.x = block; gridDim = grid;
                     emu_dyn_smem = smem.data();
                     emu_cta = &cta;

@@ -499,7 +499,7 @@ ntt_strided_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
 
 // ---- pass "contig": grid (num * n / 16 / 128), 128 threads; CTA = 128 consecutive rows of one polynomial ------------------------------------------------------
 template <class P, int LOGN, bool INV>
-__global__ void __launch_bounds__(kContigRows, NTT_MINB_C)
+__global__ void __launch_bounds__(kContigRows, Sched<LOGN>::K2 == 8 ? 4 : NTT_MINB_C)   // radix-16 first round needs > 80 registers
 ntt_contig_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
 {
     using SC = Sched<LOGN>;
