@@ -160,6 +160,23 @@ constexpr int kMaxLimbs = NTTB200_MAX_LIMBS_INTERNAL;
 __host__ __device__ __forceinline__ u64 mod_exact(u64 x, u64 q, u64 ratio) { return csub(x - mulhi64(x, ratio) * q, q); }
 __host__ __device__ __forceinline__ u64 ratio_of(u64 q) { return ~0ull / q; }   // = floor(2^64 / q) for odd q > 1
 
+// The reference's Barrett (one correction) is exact for every product a*b < 2^(2*qbit) iff its quotient estimate is never 2
+// short; that is guaranteed when delta = frac(2^(2*qbit) / q) < 1/2 (estimate error < delta + 1/2 + frac).
+// For such moduli any exact modular multiplication returns the reference's bits, so multiplications by per-limb CONSTANTS
+// use a Shoup product (mul.hi + 2 mul.lo) instead of the 30-instruction Barrett sequence.  Moduli with delta >= 1/2
+// (68719230977 and 274877202433 among the reference's) keep the literal sequence so even their glitches reproduce.
+__host__ __device__ __forceinline__ bool barrett_is_exact(u64 q, u64 mu, int qbit)
+{
+    const u64 rem = (2 * qbit >= 64 ? 0ull : (1ull << (2 * qbit))) - mu * q;     // 2^(2 qbit) mod q (mod 2^64 arithmetic, rem < q)
+    return qbit >= 3 && qbit <= 61 && rem < q && rem * 2 < q;
+}
+__host__ __device__ __forceinline__ u64 shoup_companion(u64 c, u64 q) { return (u64)((((unsigned __int128)c) << 64) / q); }
+// v * c mod q, canonical, for a constant c < q with companion cs; `fast` as decided by barrett_is_exact
+__host__ __device__ __forceinline__ u64 mul_const(u64 v, u64 c, u64 cs, bool fast, u64 q, u64 mu, int qbit)
+{
+    return fast ? csub(shoup_mul(v, c, cs, q), q) : barrett_ref(v, c, q, mu, qbit);
+}
+
 __device__ __forceinline__ ulonglong2 ld2(const u64 *p) { return *reinterpret_cast<const ulonglong2 *>(p); }
 __device__ __forceinline__ void st2(u64 *p, u64 a, u64 b) { *reinterpret_cast<ulonglong2 *>(p) = make_ulonglong2(a, b); }
 
@@ -255,7 +272,7 @@ NTT_KERNEL void k_encrypt_mul(u64 *c, const u64 *pk, size_t pk_stride, unsigned 
     }
 }
 
-struct EncLimb { u64 q, mu, ratio, half_mod, inv_q_last, qdt; int qbit, pad; };
+struct EncLimb { u64 q, mu, ratio, half_mod, inv_q_last, inv_q_last_s, qdt; int qbit, fast; };
 // poly_add_xq + divide_and_round_q_last_inplace_add_x2 + ..._loop_xq + weird_m_stuff (bfv_encryption.cuh:111-212)
 // in one pass.  grid (x, 2 halves, batch).  The dropped limb r-1 keeps the value the reference leaves there.
 NTT_KERNEL void k_encrypt_epilogue(u64 *c, const int *es, const u64 *m_poly, size_t m_stride, unsigned n, unsigned r, unsigned batch, u64 t,
@@ -267,10 +284,12 @@ NTT_KERNEL void k_encrypt_epilogue(u64 *c, const int *es, const u64 *m_poly, siz
     if (threadIdx.x + 1 < r) {
         const unsigned l = threadIdx.x;
         EncLimb e;
-        e.q = L.q[l]; e.mu = L.mu[l]; e.qbit = (int)L.qbit[l]; e.pad = 0;
+        e.q = L.q[l]; e.mu = L.mu[l]; e.qbit = (int)L.qbit[l];
         e.ratio = ratio_of(e.q);
         e.half_mod = half_last % e.q;
         e.inv_q_last = L.inv_q_last_mod_q[l];
+        e.fast = barrett_is_exact(e.q, e.mu, e.qbit) && e.inv_q_last < e.q;
+        e.inv_q_last_s = e.fast ? shoup_companion(e.inv_q_last, e.q) : 0;
         e.qdt = qi_div_t[l];
         K[l] = e;
     }
@@ -316,8 +335,8 @@ NTT_KERNEL void k_encrypt_epilogue(u64 *c, const int *es, const u64 *m_poly, siz
             if (x0 < t0) x0 += P.q;
             if (x1 < t1) x1 += P.q;
             x0 -= t0; x1 -= t1;
-            x0 = barrett_ref(x0, P.inv_q_last, P.q, P.mu, P.qbit);
-            x1 = barrett_ref(x1, P.inv_q_last, P.q, P.mu, P.qbit);
+            x0 = mul_const(x0, P.inv_q_last, P.inv_q_last_s, P.fast != 0, P.q, P.mu, P.qbit);
+            x1 = mul_const(x1, P.inv_q_last, P.inv_q_last_s, P.fast != 0, P.q, P.mu, P.qbit);
             if (h == 0) {
                 x0 = mod_exact(x0 + ((m0 * P.qdt) + f0), P.q, P.ratio);
                 x1 = mod_exact(x1 + ((m1 * P.qdt) + f1), P.q, P.ratio);
@@ -349,7 +368,7 @@ struct DecryptConsts {
     unsigned rp;          // limbs after the drop (the driver's q_amount after q_amount--)
     const u64 *bcm;       // [2][rp]: prod_{i != j} q_i mod t | mod gamma   (demo.cu:248-264)
 };
-struct DecLimb { u64 q, mu, ptg, ipq, bt, bg; int qbit, pad; };
+struct DecLimb { u64 q, mu, ptg, ipq, c12, c12_s, bt, bg, bg_s; int qbit, fast; };   // c12 = ptg * ipq mod q
 // (acc + v) mod gamma for acc < gamma and v < 2*gamma (the reference's Barrett may leave v in [gamma, 2 gamma)): the sum is
 // below 3*gamma, so two conditional subtractions are the exact remainder the reference's `%` computes.
 __host__ __device__ __forceinline__ u64 add_mod_gamma(u64 acc, u64 v, u64 gamma)
@@ -364,9 +383,15 @@ __device__ __forceinline__ void dec_stage_limbs(DecLimb *K, unsigned first, unsi
     if (threadIdx.x < count) {
         const unsigned l = first + threadIdx.x;
         DecLimb e;
-        e.q = L.q[l]; e.mu = L.mu[l]; e.qbit = (int)L.qbit[l]; e.pad = 0;
+        e.q = L.q[l]; e.mu = L.mu[l]; e.qbit = (int)L.qbit[l];
         e.ptg = L.prod_t_gamma_mod_q[l]; e.ipq = L.inv_punctured_q[l];
         e.bt = D.bcm[l]; e.bg = D.bcm[l + D.rp];
+        // fast: both the limb's and gamma's Barrett are provably exact -> two Shoup products replace three Barrett sequences
+        e.fast = barrett_is_exact(e.q, e.mu, e.qbit) && barrett_is_exact(D.gamma, D.mu_gamma, D.gamma_bits) && e.ptg < e.q && e.ipq < e.q &&
+                 e.bg < D.gamma;
+        e.c12 = e.fast ? (u64)((unsigned __int128)e.ptg * e.ipq % e.q) : 0;
+        e.c12_s = e.fast ? shoup_companion(e.c12, e.q) : 0;
+        e.bg_s = e.fast ? shoup_companion(e.bg, D.gamma) : 0;
         K[threadIdx.x] = e;
     }
     __syncthreads();
@@ -376,10 +401,17 @@ __device__ __forceinline__ void dec_accumulate(const DecLimb &P, u64 a1, u64 a0,
 {
     u64 v = a1 + a0;
     if (v > P.q) v -= P.q;
-    v = barrett_ref(v, P.ptg, P.q, P.mu, P.qbit);
-    v = barrett_ref(v, P.ipq, P.q, P.mu, P.qbit);
+    u64 g;
+    if (P.fast) {
+        v = csub(shoup_mul(v, P.c12, P.c12_s, P.q), P.q);                  // (v * t*gamma) * punctured inverse, canonical
+        g = csub(shoup_mul(v, P.bg, P.bg_s, D.gamma), D.gamma);
+    } else {
+        v = barrett_ref(v, P.ptg, P.q, P.mu, P.qbit);
+        v = barrett_ref(v, P.ipq, P.q, P.mu, P.qbit);
+        g = barrett_ref(v, P.bg, D.gamma, D.mu_gamma, D.gamma_bits);
+    }
     acc_t += (v * P.bt) & (u64)mask32;
-    acc_g = add_mod_gamma(acc_g, barrett_ref(v, P.bg, D.gamma, D.mu_gamma, D.gamma_bits), D.gamma);
+    acc_g = add_mod_gamma(acc_g, g, D.gamma);
 }
 __device__ __forceinline__ u64 dec_finish_one(u64 acc_t, u64 acc_g, u32 mask32, const DecryptConsts &D)
 {

@@ -137,3 +137,35 @@ def test_keygen_encrypt_decrypt_roundtrip(oracle, name):
     a_s = oracle.barrett(pk[r * n: r * n + n], sk[:n], q[0])
     lhs = oracle.inverse_ntt((pk[:n] + a_s) % np.uint64(q[0]), q[0], ring.psiinv[0])
     assert np.array_equal((lhs + temp[:n]) % np.uint64(q[0]), np.zeros(n, dtype=np.uint64))
+
+
+def test_reference_barrett_exactness_criterion(oracle):
+    """the reference's one-correction Barrett is exact for all a, b < q when frac(2^(2 qbit)/q) < 1/2 (the fused
+    kernels rely on this to replace it by Shoup products) and can be 1*q off otherwise (a witness is kept for 68719230977)."""
+    rng = np.random.default_rng(5)
+    for name in ("32k_16q", "16k_5q", "8k_4q", "8k_3q", "4k_3q"):
+        for q in params.RNS_SETS[name][1]:
+            qb, m = oracle.qbit(q), oracle.mu(q)
+            delta = ((1 << (2 * qb)) % q) / q
+            if delta >= 0.5:
+                continue
+            # adversarial operands: products just above a multiple of q (small true remainder) and near 2^(2 qbit)
+            xs = [q - 1, q - 2, (q - 1) // 2, 1 << (qb - 1)] + [int(v) % q for v in rng.integers(1, 2**63, 300)]
+            for a in xs[:40]:
+                inv = pow(a, q - 2, q)
+                for r in (0, 1, 2, 3, q - 1):
+                    b = inv * r % q                      # a * b = r (mod q)
+                    assert int(oracle.lib().orc_barrett_mul(a, b, q, m, qb)) == r
+            for a, b in zip(xs[4:], xs[5:]):
+                assert int(oracle.lib().orc_barrett_mul(a, b, q, m, qb)) == a * b % q
+    # a witness of the glitch for the delta = 0.879 prime: result in [q, 2q)
+    q = 68719230977
+    qb, m = oracle.qbit(q), oracle.mu(q)
+    assert ((1 << (2 * qb)) % q) / q > 0.75
+    found = False
+    for a in range(q - 1, q - 4000, -1):
+        b = q - 1
+        if int(oracle.lib().orc_barrett_mul(a, b, q, m, qb)) != a * b % q:
+            found = True
+            break
+    assert found
