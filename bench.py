@@ -62,8 +62,7 @@ def cpu_ntt_rate(budget_s=12.0, threads=None):
     t0 = time.perf_counter()
     orc.forward_ntt_fast_range(a, n, psi, LIMBS, qa, 0, 1)
     one = time.perf_counter() - t0
-    reps = max(1, int(budget_s / max(one * per_thread, 1e-6)))
-    reps = min(reps, 64)
+    reps = max(1, int(budget_s / max(one * per_thread, 1e-6)))       # ~budget_s seconds of CPU work per thread
 
     def work(t):
         for _ in range(reps):
