@@ -328,6 +328,9 @@ def run_ours(args):
         peak, peak_src = peaks()
         alg_bytes = 16.0 * n * POLYS                     # per launch: every coefficient read once + written once
         dom, dom_ms = ("ntt_strided_pass", p1) if p1 >= p2 else ("ntt_contig_pass", p2)
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this workload
+        # (profiles/r01h_ncu_full_summary.md); below the algorithmic 536.9 MB because write-back still sits in L2 at kernel end
+        ncu_traffic = {"ntt_strided_pass": 484.5e6, "ntt_contig_pass": 493.4e6}[dom]
         ach = alg_bytes / (dom_ms * 1e-3) / 1e9
         butterflies = POLYS * (n // 2) * 15
         cb = None
@@ -345,7 +348,7 @@ def run_ours(args):
                     "steps": e2e_steps, "api": "nttb200_forward_ntt_batch_host (pinned host buffers, 3-stage stream pipeline)"},
             "gpu_launches": 2 * args.steps,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": ncu_traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": dom_ms},
             "kernels_ms": {"ntt_strided_pass": p1, "ntt_contig_pass": p2},
             "hbm_gbs_whole_step": 2 * alg_bytes / ((p1 + p2) * 1e-3) / 1e9,
@@ -364,7 +367,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
