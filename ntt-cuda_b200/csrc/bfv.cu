@@ -6,7 +6,7 @@
 //   * nttb200_bfv_*      : context-based and BATCHED (item k = Salsa20 nonce nonce0 + k), Shoup NTT on context tables;
 //   * nttb200_ref_*_rns  : the reference's single-item calls with the reference's own tables / constant arrays,
 //                          stateless Barrett NTT (what include/dropin/bfv_*.cuh forwards to).
-// Launch counts (any batch size): keygen 10, encrypt 9, decrypt 6 kernels on ONE stream -- the reference issues
+// Launch counts (any batch size): keygen 10, encrypt 8, decrypt 6 kernels on ONE stream -- the reference issues
 // 13 / 16 / 18 per item, creates r streams and mallocs inside decryption_rns, and races dec_round against mod_t.
 #include "internal.h"
 #include "bfv_kernels.cuh"
