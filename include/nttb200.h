@@ -171,13 +171,20 @@ NTTB200_API int nttb200_bfv_encrypt(nttb200_bfv *bfv, nttb200_u64 *c, const nttb
 NTTB200_API int nttb200_bfv_decrypt(nttb200_bfv *bfv, nttb200_u64 *m_out, nttb200_u64 *c, const nttb200_u64 *sk, int sk_per_item,
                                     unsigned batch, void *stream);
 
-/* Limb-sharded decryption across GPUs.  Each GPU holds limbs [first_limb, first_limb + limb_count) of
- * every ciphertext as a compact shard c_shard[batch][2][limb_count][n] (c0 limbs, then c1 limbs) and the same limbs of the
- * secret key.  _partial runs NTT / (.)sk / INTT / scaling on the shard and writes the partial base-conversion sums
+/* Limb-sharded encryption needs no extra entry point: create a context for the sub-ring {owned limbs..., last limb}
+ * and call nttb200_bfv_encrypt on it -- a limb of the ciphertext depends only on itself, the dropped last limb and the
+ * nonce-addressed randomness (whose layout does not depend on the limb count), so the shard equals the same limbs of the
+ * full ciphertext bit for bit (nttb200/distributed.py: encrypt_limb_sharded).
+ *
+ * Limb-sharded decryption across GPUs.  Each GPU holds limbs [first_limb, first_limb + limb_count) of
+ * every ciphertext as a shard c_shard[batch][2][shard_half_limbs][n] (per half: the owned limbs first; shard_half_limbs =
+ * limb_count for a compact shard, limb_count + 1 for the output of a sub-ring encryption, 0 = compact) and the same limbs
+ * of the secret key.  _partial runs NTT / (.)sk / INTT / scaling on the shard and writes the partial base-conversion sums
  * partial[batch][2][n]; the caller all-reduces (SUM, 64-bit) `partial` over the GPUs -- the path's only collective -- and
  * _finish rounds to the plaintext m_out[batch][n].  Bit-identical to nttb200_bfv_decrypt on one GPU. */
 NTTB200_API int nttb200_bfv_decrypt_partial(nttb200_bfv *bfv, nttb200_u64 *partial, nttb200_u64 *c_shard, const nttb200_u64 *sk_shard,
-                                            int sk_per_item, unsigned first_limb, unsigned limb_count, unsigned batch, void *stream);
+                                            int sk_per_item, unsigned first_limb, unsigned limb_count, unsigned shard_half_limbs,
+                                            unsigned batch, void *stream);
 NTTB200_API int nttb200_bfv_decrypt_finish(nttb200_bfv *bfv, nttb200_u64 *m_out, const nttb200_u64 *partial_sum, unsigned batch, void *stream);
 
 /* The reference's single-item calls, stateless (tables and constant arrays are the caller's device buffers;

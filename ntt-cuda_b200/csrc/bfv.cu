@@ -256,9 +256,11 @@ int nttb200_bfv_decrypt(nttb200_bfv *b, nttb200_u64 *m_out, nttb200_u64 *c, cons
 // ---- limb-sharded decryption: this GPU's share up to the cross-limb reduction, and the step after the all-reduce -------
 // c_shard: items of [2][count][n] holding limbs [first, first+count) of c0 then of c1; sk_shard[count][n] (or per item).
 int nttb200_bfv_decrypt_partial(nttb200_bfv *b, nttb200_u64 *partial, nttb200_u64 *c_shard, const nttb200_u64 *sk_shard, int sk_per_item,
-                                unsigned first_limb, unsigned limb_count, unsigned batch, void *stream)
+                                unsigned first_limb, unsigned limb_count, unsigned shard_half_limbs, unsigned batch, void *stream)
 {
     if (!b || !partial || !c_shard || !sk_shard || !batch || !limb_count || first_limb + limb_count > b->r - 1) return NTTB200_EINVAL;
+    if (shard_half_limbs == 0) shard_half_limbs = limb_count;
+    if (shard_half_limbs < limb_count || batch > 65535) return NTTB200_EINVAL;
     const unsigned n = b->n;
     const nttb200_ctx *c = b->ctx;
     Pipe P = pipe_from_bfv(b, (cudaStream_t)stream);
@@ -268,7 +270,7 @@ int nttb200_bfv_decrypt_partial(nttb200_bfv *b, nttb200_u64 *partial, nttb200_u6
     LimbArrays Lloc{c->q_dev + first_limb, c->mu_dev + first_limb, c->qbit_dev + first_limb, nullptr, nullptr, nullptr};
     const LimbArrays Lglob = P.L;
     P.L = Lloc;
-    const size_t item = (size_t)2 * limb_count * n, c1_off = (size_t)limb_count * n;
+    const size_t item = (size_t)2 * shard_half_limbs * n, c1_off = (size_t)shard_half_limbs * n;
     NTTB200_TRY(pipe_ntt(P, false, c_shard + c1_off, batch * limb_count, limb_count, limb_count, item));
     k_decrypt_mul<<<pair_grid(n, limb_count, batch), 256, 0, P.st>>>(c_shard, item, c1_off, sk_shard,
                                                                                  sk_per_item ? (size_t)limb_count * n : 0, n, limb_count, batch, Lloc);

@@ -218,7 +218,7 @@ EXPORT int emu_sampling(int op, const unsigned char *in, u64 *out, u64 *out2, si
 EXPORT int emu_bfv_sharded(int op, unsigned n, unsigned r, const u64 *q, const u64 *mu, const u32 *qbit, const u64 *psi, const u64 *psiinv,
                            const u64 *psi_s, const u64 *psiinv_s, const LimbConst *lc, u64 *c_shard, const u64 *sk_shard, u64 *part, u64 *out,
                            unsigned batch, unsigned first, unsigned count, const u64 *ptg, const u64 *ipq, const u64 *bcm, u64 t, u64 gamma,
-                           u64 mu_gamma, int gamma_bits, u64 neg_inv_t, u64 neg_inv_gamma)
+                           u64 mu_gamma, int gamma_bits, u64 neg_inv_t, u64 neg_inv_gamma, unsigned shard_half_limbs)
 {
     const unsigned rp = r - 1;
     DecryptConsts D{t, gamma, mu_gamma, gamma >> 1, neg_inv_t, neg_inv_gamma, gamma_bits, rp, bcm};
@@ -228,7 +228,8 @@ EXPORT int emu_bfv_sharded(int op, unsigned n, unsigned r, const u64 *q, const u
         while ((1u << R.logn) < n) R.logn++;
         LimbArrays Lloc{q + first, mu + first, qbit + first, nullptr, nullptr, nullptr};
         LimbArrays Lglob{q, mu, qbit, nullptr, ipq, ptg};
-        const size_t item = (size_t)2 * count * n, c1_off = (size_t)count * n;
+        if (shard_half_limbs == 0) shard_half_limbs = count;
+        const size_t item = (size_t)2 * shard_half_limbs * n, c1_off = (size_t)shard_half_limbs * n;
         ring_ntt(R, false, c_shard + c1_off, batch * count, count, count, item);
         ew3(count, batch, [&] { k_decrypt_mul(c_shard, item, c1_off, sk_shard, 0, n, count, batch, Lloc); });
         ring_ntt(R, true, c_shard + c1_off, batch * count, count, count, item);

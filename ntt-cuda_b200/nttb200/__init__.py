@@ -304,10 +304,13 @@ class Bfv:
                                         vp(_stream(stream))))
 
 
-    def decrypt_partial(self, partial, c_shard, sk_shard, first_limb, limb_count, batch=1, sk_per_item=False, stream=None):
-        """Limb-sharded decryption, this GPU's share: partial[batch][2][n] (all-reduce SUM it, then decrypt_finish)."""
+    def decrypt_partial(self, partial, c_shard, sk_shard, first_limb, limb_count, batch=1, sk_per_item=False, shard_half_limbs=0,
+                        stream=None):
+        """Limb-sharded decryption, this GPU's share: partial[batch][2][n] (all-reduce SUM it, then decrypt_finish).
+        c_shard[batch][2][shard_half_limbs][n]; shard_half_limbs = 0 means compact (= limb_count)."""
         check(lib().nttb200_bfv_decrypt_partial(self._h, vp(ptr(partial)), vp(ptr(c_shard)), vp(ptr(sk_shard)), C.c_int(int(sk_per_item)),
-                                                C.c_uint(first_limb), C.c_uint(limb_count), C.c_uint(batch), vp(_stream(stream))))
+                                                C.c_uint(first_limb), C.c_uint(limb_count), C.c_uint(shard_half_limbs), C.c_uint(batch),
+                                                vp(_stream(stream))))
 
     def decrypt_finish(self, m_out, partial_sum, batch=1, stream=None):
         check(lib().nttb200_bfv_decrypt_finish(self._h, vp(ptr(m_out)), vp(ptr(partial_sum)), C.c_uint(batch), vp(_stream(stream))))

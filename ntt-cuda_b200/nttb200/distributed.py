@@ -35,7 +35,31 @@ def ciphertext_limb_shard(c, n: int, r: int, first: int, count: int, batch: int 
     return s.contiguous().reshape(-1) if hasattr(s, "contiguous") else s.copy().reshape(-1)
 
 
-def decrypt_limb_sharded(bfv, c_shard, sk_shard, first: int, count: int, batch: int, all_reduce_sum, new_u64, sk_per_item=False):
+def sub_ring(q, psi_roots, first: int, count: int):
+    """Moduli / roots of the sub-ring a rank encrypts on: its owned limbs followed by the last limb (which the modulus
+    switch drops).  A ciphertext limb depends only on itself, on the last limb and on randomness whose keystream layout
+    (9n bytes, bfv_encryption.cuh:228) is independent of the limb count."""
+    q, psi_roots = list(q), list(psi_roots)
+    return q[first:first + count] + [q[-1]], psi_roots[first:first + count] + [psi_roots[-1]]
+
+
+def public_key_limb_shard(pk, n: int, r: int, first: int, count: int):
+    """pk[2][r][n] -> [2][count+1][n]: owned limbs then the last limb, per half."""
+    v = pk.reshape(2, r, n)
+    idx = list(range(first, first + count)) + [r - 1]
+    s = v[:, idx, :]
+    return s.contiguous().reshape(-1) if hasattr(s, "contiguous") else s.copy().reshape(-1)
+
+
+def encrypt_limb_sharded(sub_bfv, c_shard, pk_shard, m, batch: int, nonce0: int = 0):
+    """Limb-sharded encryption on this rank, no communication: `sub_bfv` is a Bfv on sub_ring(...); c_shard[batch][2][count+1][n]
+    receives the owned limbs of every ciphertext (slot `count` of each half is the padding limb)."""
+    sub_bfv.encrypt(c_shard, pk_shard, m, batch=batch, nonce0=nonce0)
+    return c_shard
+
+
+def decrypt_limb_sharded(bfv, c_shard, sk_shard, first: int, count: int, batch: int, all_reduce_sum, new_u64, sk_per_item=False,
+                         shard_half_limbs: int = 0):
     """Limb-sharded decryption on this rank.
 
     bfv            object with decrypt_partial / decrypt_finish (nttb200.Bfv on the GPU)
@@ -46,7 +70,7 @@ def decrypt_limb_sharded(bfv, c_shard, sk_shard, first: int, count: int, batch: 
     n = bfv.n
     partial = new_u64(batch * 2 * n)
     if count > 0:
-        bfv.decrypt_partial(partial, c_shard, sk_shard, first, count, batch=batch, sk_per_item=sk_per_item)
+        bfv.decrypt_partial(partial, c_shard, sk_shard, first, count, batch=batch, sk_per_item=sk_per_item, shard_half_limbs=shard_half_limbs)
     all_reduce_sum(partial)                      # the path's only collective: batch * 2 * n * 8 bytes
     out = new_u64(batch * n)
     bfv.decrypt_finish(out, partial, batch=batch)

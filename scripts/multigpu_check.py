@@ -14,8 +14,8 @@ import torch.distributed as dist  # noqa: E402
 
 import nttb200  # noqa: E402
 from nttb200 import params  # noqa: E402
-from nttb200.distributed import (ciphertext_limb_shard, decrypt_limb_sharded, shard_batch, shard_limbs, torch_all_reduce_sum,  # noqa: E402
-                                 torch_new_u64)
+from nttb200.distributed import (ciphertext_limb_shard, decrypt_limb_sharded, encrypt_limb_sharded, public_key_limb_shard,  # noqa: E402
+                                 shard_batch, shard_limbs, sub_ring, torch_all_reduce_sum, torch_new_u64)
 
 
 def main():
@@ -58,17 +58,32 @@ def main():
     ms = torch.tensor([e0.elapsed_time(e1) / reps], device="cuda", dtype=torch.float64)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ok_limb = bool(torch.equal(out, ref)) and bool(torch.equal(out, m))
+    # limb-sharded ENCRYPTION on the sub-ring {owned limbs, last limb}: no communication; must equal the same limbs of c,
+    # and its (count+1)-limb shard must feed the limb-sharded decryption directly
+    ok_enc = True
+    if count > 0:
+        q_sub, roots_sub = sub_ring(qs, roots, first, count)
+        sub = nttb200.Bfv(n, q_sub, roots_sub)
+        c_enc = torch.zeros(B * 2 * (count + 1) * n, dtype=torch.int64, device="cuda")
+        encrypt_limb_sharded(sub, c_enc, public_key_limb_shard(pk, n, r, first, count), m, B)
+        ok_enc = bool(torch.equal(c_enc.view(B, 2, count + 1, n)[:, :, :count, :], c.view(B, 2, r, n)[:, :, first:first + count, :]))
+        out2 = decrypt_limb_sharded(bfv, c_enc, sk_shard, first, count, B, torch_all_reduce_sum, torch_new_u64, shard_half_limbs=count + 1)
+        sub.close()
+    else:
+        out2 = decrypt_limb_sharded(bfv, None, None, first, count, B, torch_all_reduce_sum, torch_new_u64)
+    ok_enc = ok_enc and bool(torch.equal(out2, m))
     # batch-sharded decryption: no collective at all
     f, cnt = shard_batch(B, world, rank)
     outb = torch.zeros(max(cnt, 1) * n, dtype=torch.int64, device="cuda")
     if cnt:
         bfv.decrypt(outb, c[f * 2 * rn:(f + cnt) * 2 * rn].clone(), sk, batch=cnt)
     ok_batch = cnt == 0 or bool(torch.equal(outb[:cnt * n], m[f * n:(f + cnt) * n]))
-    flags = torch.tensor([int(ok_limb), int(ok_batch)], device="cuda")
+    flags = torch.tensor([int(ok_limb), int(ok_batch), int(ok_enc)], device="cuda")
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(json.dumps({"world": world, "set": name, "batch": B, "limb_sharded_decrypt_ok": bool(flags[0].item()),
-                          "batch_sharded_decrypt_ok": bool(flags[1].item()), "limb_sharded_decrypt_ms": float(ms.item()),
+                          "batch_sharded_decrypt_ok": bool(flags[1].item()), "limb_sharded_encrypt_then_decrypt_ok": bool(flags[2].item()),
+                          "limb_sharded_decrypt_ms": float(ms.item()),
                           "limb_sharded_decrypt_per_s": B / (float(ms.item()) * 1e-3), "allreduce_bytes": B * 2 * n * 8,
                           "limbs_per_rank": [shard_limbs(rp, world, k)[1] for k in range(world)]}))
     bfv.close()

@@ -143,19 +143,24 @@ class EmuBfv:
     def __init__(self, er: EmuRing):
         self.er, self.n, self.r = er, er.ring.n, er.ring.r
 
-    def _call(self, op, c_shard, sk_shard, part, out, batch, first, count):
+    def _call(self, op, c_shard, sk_shard, part, out, batch, first, count, half=0):
         R, er, u = self.er.ring, self.er, C.c_ulonglong
         z = np.zeros(1, dtype=np.uint64)
         rc = lib().emu_bfv_sharded(op, R.n, R.r, p(R.qa, u), p(R.mu, u), p(R.qbit, C.c_uint), p(er.psi, u), p(er.psiinv, u), p(er.psi_s, u),
                                    p(er.psiinv_s, u), er.lc.ctypes.data_as(C.c_void_p), p(c_shard if c_shard is not None else z, u),
                                    p(sk_shard if sk_shard is not None else z, u), p(part, u), p(out if out is not None else z, u), batch, first,
                                    count, p(R.prod_t_gamma_mod_q, u), p(R.inv_punctured_q, u), p(R.bcm, u), u(R.t), u(R.gamma), u(R.mu_gamma),
-                                   int(R.gamma_bits), u(int(R.neg_inv[0])), u(int(R.neg_inv[1])))
+                                   int(R.gamma_bits), u(int(R.neg_inv[0])), u(int(R.neg_inv[1])), int(half))
         assert rc == 0
 
-    def decrypt_partial(self, partial, c_shard, sk_shard, first, count, batch=1, sk_per_item=False):
+    def decrypt_partial(self, partial, c_shard, sk_shard, first, count, batch=1, sk_per_item=False, shard_half_limbs=0):
         assert not sk_per_item
-        self._call(0, c_shard, sk_shard, partial, None, batch, first, count)
+        self._call(0, c_shard, sk_shard, partial, None, batch, first, count, shard_half_limbs)
+
+    def encrypt(self, c, pk, m, batch=1, nonce0=0):
+        """nttb200.Bfv.encrypt interface on the emulator (in place into the numpy array c)."""
+        out, _ = bfv(1, self.er, 0, batch=batch, nonce0=nonce0, pk=pk, m=m)
+        c[:] = out
 
     def decrypt_finish(self, m_out, partial_sum, batch=1):
         self._call(1, None, None, partial_sum, m_out, batch, 0, 0)

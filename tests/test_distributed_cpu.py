@@ -70,6 +70,26 @@ def _worker(rank, world, port, q):
 
         out = decrypt_limb_sharded(bfv, c_shard, sk_shard, first, count, B, all_reduce_sum, lambda cnt: np.zeros(cnt, dtype=np.uint64))
         ok = all(np.array_equal(out[k * n:(k + 1) * n], ms[k]) for k in range(B))
+        # limb-sharded ENCRYPTION on the sub-ring {owned limbs, last limb}: no communication, same bits as the full ciphertext
+        from nttb200.distributed import encrypt_limb_sharded, public_key_limb_shard, sub_ring
+        if count > 0:
+            q_sub, roots_sub = sub_ring(qs, roots, first, count)
+            sub = emu.EmuBfv(emu.EmuRing(orc.Ring(n, q_sub, roots_sub)))
+            c_enc = np.zeros(B * 2 * (count + 1) * n, dtype=np.uint64)
+            # item k of the full run used nonce k: encrypt item by item with the same nonces
+            for k in range(B):
+                one = np.zeros(2 * (count + 1) * n, dtype=np.uint64)
+                encrypt_limb_sharded(sub, one, public_key_limb_shard(pk, n, r, first, count), ms[k], 1, nonce0=k)
+                c_enc[k * one.size:(k + 1) * one.size] = one
+            full = c_all.reshape(B, 2, r, n)
+            mine = c_enc.reshape(B, 2, count + 1, n)
+            ok = ok and np.array_equal(mine[:, :, :count, :], full[:, :, first:first + count, :])
+            # ... and that shard feeds limb-sharded decryption directly (shard_half_limbs = count + 1)
+            out2 = decrypt_limb_sharded(bfv, c_enc, sk_shard, first, count, B, all_reduce_sum, lambda cnt: np.zeros(cnt, dtype=np.uint64),
+                                        shard_half_limbs=count + 1)
+        else:
+            out2 = decrypt_limb_sharded(bfv, None, None, first, count, B, all_reduce_sum, lambda cnt: np.zeros(cnt, dtype=np.uint64))
+        ok = ok and all(np.array_equal(out2[k * n:(k + 1) * n], ms[k]) for k in range(B))
         # and identical to the single-device oracle decryption
         for k in range(B):
             plain, _ = orc.decryption_rns(R, cs[k], sk)
