@@ -86,7 +86,7 @@ def run_reference(args):
     if rank != 0:
         return
     per_step_budget = max(2.0, min(20.0, 60.0 / max(args.steps + args.warmup, 1)))
-    vals, samples = [], []
+    vals = []
     last = None
     for i in range(args.warmup + args.steps):
         cb, dt, done = cpu_ntt_rate(budget_s=per_step_budget)

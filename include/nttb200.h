@@ -10,6 +10,8 @@
  * `_host`; `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); every function
  * returns 0 on success or a cudaError_t / NTTB200_E* code (nttb200_error_string()).  Calls are
  * asynchronous with respect to the host unless stated.  Nothing allocates on the hot path.
+ * Threading: like the reference (global rng / nonce / __constant__ state), one host thread per context; the
+ * Salsa20 key state mirrored for generate_random() is per process.
  */
 #ifndef NTTB200_H
 #define NTTB200_H

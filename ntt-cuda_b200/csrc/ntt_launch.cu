@@ -71,11 +71,14 @@ static int launch_one(const NttArgs &A, int which, unsigned cnt, const CUtensorM
     constexpr int R = 1 << SC::K1;
     constexpr size_t smem_s = (size_t)SC::NT * R * 128 + 1024 + 16;
     constexpr size_t smem_c = (size_t)kContigRows * 128 + 1024 + 16;
-    static bool attr_done = false;   // per (P, LOGN, INV) instantiation
-    if (!attr_done) {
+    // the dynamic shared-memory opt-in is a per-device function attribute: remember it per (instantiation, device)
+    static bool attr_done[64] = {false};
+    int dev = 0;
+    NTTB200_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
         NTTB200_CHECK(cudaFuncSetAttribute(ntt_strided_pass<P, LOGN, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
         NTTB200_CHECK(cudaFuncSetAttribute(ntt_contig_pass<P, LOGN, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
-        attr_done = true;
+        if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
     const unsigned tiles_s = (((1u << LOGN) >> SC::K1) >> 4) / SC::NT, tiles_c = ((1u << LOGN) >> 4) / kContigRows;
     if ((size_t)cnt * tiles_c >= (1ull << 31)) return NTTB200_EINVAL;

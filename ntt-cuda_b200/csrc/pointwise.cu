@@ -11,7 +11,7 @@ namespace nttb200 {
 // grid-stride launch geometry: enough CTAs to fill the machine (multiple of the SM count), never more than the work
 dim3 grid_for(size_t total, int threads)
 {
-    static int sms = 0;
+    static int sms = 0;      // one process drives GPUs of one kind: the SM count is read once
     if (!sms) {
         int dev = 0;
         cudaGetDevice(&dev);
