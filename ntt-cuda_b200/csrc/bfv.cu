@@ -22,10 +22,19 @@ SalsaKey default_key();
 }
 // grid of the fused kernels: x strides over coefficient pairs (256 threads x 2 coefficients per CTA step), y / z carry
 // limb or half / batch item; x is trimmed so the whole grid stays around 8 CTAs per SM
-static dim3 pair_grid(unsigned n, unsigned y, unsigned z)
+// threads per CTA of the fused kernels: 256, or 64 when the whole problem would not even give two 256-thread CTAs per SM
+// (single-item calls are latency-bound: many small CTAs spread over all SMs beat few large ones)
+static unsigned pair_block(unsigned n, unsigned y, unsigned z)
 {
     const unsigned cap = grid_for((size_t)1 << 40, 256).x;          // = 8 * SM count
-    unsigned x = (n + 511) / 512;
+    const unsigned long long ctas256 = (unsigned long long)((n + 511) / 512) * y * z;
+    return ctas256 * 4 < cap ? 64u : 256u;
+}
+static dim3 pair_grid(unsigned n, unsigned y, unsigned z)
+{
+    const unsigned cap = grid_for((size_t)1 << 40, 256).x;
+    const unsigned per_cta = 2 * pair_block(n, y, z);
+    unsigned x = (n + per_cta - 1) / per_cta;
     const unsigned long long yz = (unsigned long long)y * z;
     unsigned lim = (unsigned)(yz >= cap ? 1 : cap / yz);
     if (x > lim) x = lim;
@@ -84,13 +93,13 @@ static int run_keygen(const Pipe &P, unsigned char *in, size_t in_stride, int *e
     const size_t rn = (size_t)r * n;
     const u64 nblk = (9 * rn + 4 * (size_t)n) / 64;                                   // bfv_keygen.cuh:99
     k_salsa20_keystream<<<grid_for(nblk * batch, 256), 256, 0, P.st>>>(in, nblk, (u64)batch, in_stride, default_key(), nonce0);
-    k_keygen_sample<<<pair_grid(n, batch, 1), 256, 0, P.st>>>(in, in_stride, sk, pk, es, n, r, batch, P.L.q);   // :120-122
+    k_keygen_sample<<<pair_grid(n, batch, 1), pair_block(n, batch, 1), 0, P.st>>>(in, in_stride, sk, pk, es, n, r, batch, P.L.q);   // :120-122
     KCHECK();
     NTTB200_TRY(pipe_ntt(P, false, sk, batch * r, r, 0, 0));                               // :129
-    k_keygen_mul<<<pair_grid(n, r, batch), 256, 0, P.st>>>(pk, sk, n, r, batch, P.L);                      // :132
+    k_keygen_mul<<<pair_grid(n, r, batch), pair_block(n, r, batch), 0, P.st>>>(pk, sk, n, r, batch, P.L);                      // :132
     KCHECK();
     NTTB200_TRY(pipe_ntt(P, true, pk, batch * r, r, r, 2 * rn));                           // :133
-    k_keygen_add_negate<<<pair_grid(n, r, batch), 256, 0, P.st>>>(pk, es, n, r, batch, P.L);               // :144
+    k_keygen_add_negate<<<pair_grid(n, r, batch), pair_block(n, r, batch), 0, P.st>>>(pk, es, n, r, batch, P.L);               // :144
     KCHECK();
     NTTB200_TRY(pipe_ntt(P, false, pk, batch * r, r, r, 2 * rn));                          // :145
     return 0;
@@ -103,13 +112,13 @@ static int run_encrypt(const Pipe &P, unsigned char *in, size_t in_stride, int *
     const size_t rn = (size_t)r * n;
     const u64 nblk = (9 * (size_t)n) / 64;                                                // bfv_encryption.cuh:228
     k_salsa20_keystream<<<grid_for(nblk * batch, 256), 256, 0, P.st>>>(in, nblk, (u64)batch, in_stride, default_key(), nonce0);
-    k_encrypt_sample<<<pair_grid(n, batch, 1), 256, 0, P.st>>>(in, in_stride, c, es, n, r, batch, P.L.q);       // :247
+    k_encrypt_sample<<<pair_grid(n, batch, 1), pair_block(n, batch, 1), 0, P.st>>>(in, in_stride, c, es, n, r, batch, P.L.q);       // :247
     KCHECK();
     NTTB200_TRY(pipe_ntt(P, false, c, batch * r, r, r, 2 * rn));                           // :268 (once, not twice)
-    k_encrypt_mul<<<pair_grid(n, r, batch), 256, 0, P.st>>>(c, pk, pk_stride, n, r, batch, P.L);              // :270
+    k_encrypt_mul<<<pair_grid(n, r, batch), pair_block(n, r, batch), 0, P.st>>>(c, pk, pk_stride, n, r, batch, P.L);              // :270
     KCHECK();
     NTTB200_TRY(pipe_ntt(P, true, c, batch * 2 * r, r, 0, 0));                             // :271
-    k_encrypt_epilogue<<<pair_grid(n, 2, batch), 256, 0, P.st>>>(c, es, m, m_stride, n, r, batch, t, P.qi_div_t, P.L);   // :280-289
+    k_encrypt_epilogue<<<pair_grid(n, 2, batch), pair_block(n, 2, batch), 0, P.st>>>(c, es, m, m_stride, n, r, batch, t, P.qi_div_t, P.L);   // :280-289
     KCHECK();
     return 0;
 }
@@ -120,10 +129,10 @@ static int run_decrypt(const Pipe &P, u64 *c, const u64 *sk, size_t sk_stride, u
     const unsigned n = P.n, rp = D.rp;
     const size_t item = (size_t)2 * (rp + 1) * n, c1_off = (size_t)(rp + 1) * n;
     NTTB200_TRY(pipe_ntt(P, false, c + c1_off, batch * rp, rp, rp, item));                 // bfv_decryption.cuh:98
-    k_decrypt_mul<<<pair_grid(n, rp, batch), 256, 0, P.st>>>(c, item, c1_off, sk, sk_stride, n, rp, batch, P.L);   // :100
+    k_decrypt_mul<<<pair_grid(n, rp, batch), pair_block(n, rp, batch), 0, P.st>>>(c, item, c1_off, sk, sk_stride, n, rp, batch, P.L);   // :100
     KCHECK();
     NTTB200_TRY(pipe_ntt(P, true, c + c1_off, batch * rp, rp, rp, item));                  // :101
-    k_decrypt_epilogue<<<pair_grid(n, batch, 1), 256, 0, P.st>>>(c, item, c1_off, out, out_stride, n, batch, D, P.L);   // :103-137
+    k_decrypt_epilogue<<<pair_grid(n, batch, 1), pair_block(n, batch, 1), 0, P.st>>>(c, item, c1_off, out, out_stride, n, batch, D, P.L);   // :103-137
     KCHECK();
     return 0;
 }
@@ -272,12 +281,12 @@ int nttb200_bfv_decrypt_partial(nttb200_bfv *b, nttb200_u64 *partial, nttb200_u6
     P.L = Lloc;
     const size_t item = (size_t)2 * shard_half_limbs * n, c1_off = (size_t)shard_half_limbs * n;
     NTTB200_TRY(pipe_ntt(P, false, c_shard + c1_off, batch * limb_count, limb_count, limb_count, item));
-    k_decrypt_mul<<<pair_grid(n, limb_count, batch), 256, 0, P.st>>>(c_shard, item, c1_off, sk_shard,
+    k_decrypt_mul<<<pair_grid(n, limb_count, batch), pair_block(n, limb_count, batch), 0, P.st>>>(c_shard, item, c1_off, sk_shard,
                                                                                  sk_per_item ? (size_t)limb_count * n : 0, n, limb_count, batch, Lloc);
     KCHECK();
     NTTB200_TRY(pipe_ntt(P, true, c_shard + c1_off, batch * limb_count, limb_count, limb_count, item));
     DecryptConsts D{b->t, b->gamma, b->mu_gamma, b->gamma_div_2, b->neg_inv_t, b->neg_inv_gamma, b->gamma_bits, b->r - 1, b->bcm};
-    k_decrypt_partial<<<pair_grid(n, batch, 1), 256, 0, P.st>>>(c_shard, item, c1_off, partial, n, batch, first_limb, limb_count, D, Lglob);
+    k_decrypt_partial<<<pair_grid(n, batch, 1), pair_block(n, batch, 1), 0, P.st>>>(c_shard, item, c1_off, partial, n, batch, first_limb, limb_count, D, Lglob);
     KCHECK();
     return 0;
 }
@@ -285,7 +294,7 @@ int nttb200_bfv_decrypt_finish(nttb200_bfv *b, nttb200_u64 *m_out, const nttb200
 {
     if (!b || !m_out || !partial_sum || !batch) return NTTB200_EINVAL;
     DecryptConsts D{b->t, b->gamma, b->mu_gamma, b->gamma_div_2, b->neg_inv_t, b->neg_inv_gamma, b->gamma_bits, b->r - 1, b->bcm};
-    k_decrypt_finish<<<pair_grid(b->n, batch, 1), 256, 0, (cudaStream_t)stream>>>(partial_sum, m_out, b->n, b->n, batch, D);
+    k_decrypt_finish<<<pair_grid(b->n, batch, 1), pair_block(b->n, batch, 1), 0, (cudaStream_t)stream>>>(partial_sum, m_out, b->n, b->n, batch, D);
     KCHECK();
     return 0;
 }

@@ -209,3 +209,39 @@ def test_batched_context_pipelines(oracle):
     bfv.decrypt(out, c2, sk[:rn], batch=B)
     assert np.array_equal(to_host(out), m)
     bfv.close()
+
+
+def test_pipelines_are_cuda_graph_capturable(oracle):
+    """Single-item calls are launch-bound; after reserve() nothing on the path allocates or synchronises, so the whole
+    encrypt / decrypt call captures into a CUDA graph and replays to the same bits."""
+    import torch
+    import nttb200
+    from tests.gpu_util import to_dev, to_host
+    n, qs, roots = params.RNS_SETS["16k_5q"]
+    r = len(qs)
+    rn = r * n
+    bfv = nttb200.Bfv(n, qs, roots)
+    bfv.reserve(1)
+    sk = torch.zeros(rn, dtype=torch.int64, device="cuda")
+    pk = torch.zeros(2 * rn, dtype=torch.int64, device="cuda")
+    bfv.keygen(sk, pk)
+    m = to_dev(oracle.fill_uniform(n, params.T, 31337))
+    c_ref = torch.zeros(2 * rn, dtype=torch.int64, device="cuda")
+    bfv.encrypt(c_ref, pk, m)                      # eager (also warms up attributes / tensor-map entry point)
+    out_ref = torch.zeros(n, dtype=torch.int64, device="cuda")
+    bfv.decrypt(out_ref, c_ref.clone(), sk)
+    c = torch.zeros(2 * rn, dtype=torch.int64, device="cuda")
+    out = torch.zeros(n, dtype=torch.int64, device="cuda")
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g, stream=s):
+            bfv.encrypt(c, pk, m, stream=s)
+            bfv.decrypt(out, c, sk, stream=s)
+    for _ in range(3):
+        c.zero_()
+        out.zero_()
+        g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, m) and torch.equal(out, out_ref)
+    bfv.close()
