@@ -183,8 +183,10 @@ static int host_pipeline(nttb200_ctx *c, bool inverse, const u64 *in, u64 *out, 
 {
     if (!c || !in || !out || division == 0 || division > c->limbs) return NTTB200_EINVAL;
     if (num == 0) return 0;
-    // chunk = a multiple of `division` polynomials, about 16 MiB
-    size_t per = ((size_t)16 << 20) / ((size_t)c->n * 8);
+    // chunk = a multiple of `division` polynomials, about 16 MiB (NTTB200_E2E_CHUNK_MB overrides, for tuning)
+    static size_t chunk_mb = 0;
+    if (!chunk_mb) { const char *e = getenv("NTTB200_E2E_CHUNK_MB"); chunk_mb = e && atoi(e) > 0 ? (size_t)atoi(e) : 16; }
+    size_t per = (chunk_mb << 20) / ((size_t)c->n * 8);
     per = per / division * division;
     if (per == 0) per = division;
     const size_t bytes = per * c->n * 8;

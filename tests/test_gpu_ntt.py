@@ -147,3 +147,31 @@ def test_invalid_arguments_fail_loudly():
         nttb200.Context(1024, [12289], [7])          # n below 2^11
     with pytest.raises(nttb200.NttB200Error):
         nttb200.Context(2048, [137438691329], [5])   # not a primitive 2n-th root
+
+
+@pytest.mark.parametrize("logn,limbs,num", [(16, 20, 40), (17, 16, 32)])
+def test_c5_large_rings_many_limbs(oracle, logn, limbs, num):
+    """BASELINE config 5: N = 2^16 .. 2^17 with 16+ RNS limbs (the reference stops at 32768 and at 16 limbs).  New 57-bit
+    primes q = 1 mod 2N (nttb200.params.find_ntt_primes).  Oracle parity on a sample, round trip + linearity on everything."""
+    import torch
+    import nttb200
+    from tests.gpu_util import to_host
+    n = 1 << logn
+    qs, roots = params.find_ntt_primes(57, n, limbs)
+    ctx = nttb200.Context(n, qs, roots)
+    g = torch.Generator(device="cuda").manual_seed(99)
+    reps = -(-num // limbs)
+    qv = torch.tensor(qs, dtype=torch.int64, device="cuda").repeat(reps)[:num].view(num, 1)
+    a = torch.randint(0, 2**62, (num, n), dtype=torch.int64, device="cuda", generator=g) % qv
+    b = torch.randint(0, 2**62, (num, n), dtype=torch.int64, device="cuda", generator=g) % qv
+    fa, fb, fs = a.clone(), b.clone(), (a + b) % qv
+    for t in (fa, fb, fs):
+        ctx.forward_ntt_batch(t, num, limbs)
+    assert torch.equal((fa + fb) % qv, fs)
+    for p in (0, limbs - 1, num - 1):
+        l = p % limbs
+        psi, _ = oracle.fill_psi_tables(roots[l], qs[l], n)
+        assert np.array_equal(to_host(fa[p]), oracle.forward_ntt_fast(to_host(a[p]), qs[l], psi))
+    ctx.inverse_ntt_batch(fa, num, limbs)
+    assert torch.equal(fa, a)
+    ctx.close()
