@@ -408,7 +408,7 @@ __device__ __forceinline__ u64 *align_1024(unsigned char *p)
 
 // ---- pass "strided": grid (num * tiles), tiles = n / 2^K1 / 16 / NT column tiles per polynomial; 2^K1 * NT threads ------------------------------------------
 template <class P, int LOGN, bool INV>
-__global__ void __launch_bounds__((1 << Sched<LOGN>::K1) * Sched<LOGN>::NT, ((1 << Sched<LOGN>::K1) * Sched<LOGN>::NT) > 256 ? 1 : NTT_MINB_S)
+__global__ void __launch_bounds__((1 << Sched<LOGN>::K1) * Sched<LOGN>::NT, ((1 << Sched<LOGN>::K1) * Sched<LOGN>::NT) > 256 ? 2 : NTT_MINB_S)
 ntt_strided_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
 {
     using SC = Sched<LOGN>;
