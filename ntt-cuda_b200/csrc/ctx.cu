@@ -3,6 +3,7 @@
 // repeats by hand (demo.cu:62-196: q_bit/mu computation, fillTablePsi128 per limb, cudaMemcpy per limb,
 // cudaMemcpyToSymbol into six 16-entry __constant__ tables).
 #include "internal.h"
+#include "table_kernels.cuh"
 
 #include <cmath>
 #include <cstdlib>
@@ -18,31 +19,30 @@ static u64 h_modpow(u64 a, u64 e, u64 m)
     while (e) { if (e & 1) r = (u64)((u128)r * a % m); a = (u64)((u128)a * a % m); e >>= 1; }
     return r;
 }
-static unsigned h_bitrev(unsigned x, unsigned bits)
-{
-    unsigned r = 0;
-    for (unsigned i = 0; i < bits; i++) { r = (r << 1) | (x & 1); x >>= 1; }
-    return r;
-}
 static u64 h_shoup(u64 w, u64 q) { return (u64)(((u128)w << 64) / q); }
 
-static int ctx_finish(nttb200_ctx *c, const u64 *psi_h, const u64 *psiinv_h)
+// Allocates the device state, fills the per-limb constants and produces the tables: from the roots on the device
+// (psi_h == nullptr) or from caller-supplied host tables (companions still computed on the device).
+static int ctx_finish(nttb200_ctx *c, const u64 *roots, const u64 *psi_h, const u64 *psiinv_h)
 {
     const size_t tot = (size_t)c->limbs * c->n;
-    std::vector<u64> ps(tot), pis(tot);
     std::vector<LimbConst> lc(c->limbs);
+    std::vector<u64> roots_v(c->limbs, 0), rootsinv_v(c->limbs, 0);
     c->mu.resize(c->limbs); c->qbit.resize(c->limbs);
     for (unsigned l = 0; l < c->limbs; l++) {
         const u64 q = c->q[l];
-        for (size_t i = 0; i < c->n; i++) {
-            ps[l * (size_t)c->n + i] = h_shoup(psi_h[l * (size_t)c->n + i], q);
-            pis[l * (size_t)c->n + i] = h_shoup(psiinv_h[l * (size_t)c->n + i], q);
-        }
         const unsigned qbit = (unsigned)(log2((double)q) + 1);            // demo.cu:69
         const u64 mu = 2 * qbit < 128 ? (u64)(((u128)1 << (2 * qbit)) / q) : 0;   // demo.cu:157-165
         c->mu[l] = mu; c->qbit[l] = qbit;
         const u64 ninv = h_modpow(c->n % q, q - 2, q);
-        const u64 w1 = psiinv_h[l * (size_t)c->n + 1];
+        u64 w1;                                                          // psiinv[1] = psiinv^(n/2)
+        if (roots) {
+            roots_v[l] = roots[l] % q;
+            rootsinv_v[l] = h_modpow(roots_v[l], q - 2, q);              // demo.cu:96-97
+            w1 = h_modpow(rootsinv_v[l], c->n / 2, q);
+        } else {
+            w1 = psiinv_h[l * (size_t)c->n + 1];
+        }
         const u64 w1n = (u64)((u128)w1 * ninv % q);
         LimbConst &k = lc[l];
         k.q = q; k.twoq = 2 * q; k.mu = mu; k.qbit = qbit; k.pad = 0;
@@ -60,14 +60,26 @@ static int ctx_finish(nttb200_ctx *c, const u64 *psi_h, const u64 *psiinv_h)
     NTTB200_CHECK(cudaMalloc(&c->q_dev, 8 * c->limbs));
     NTTB200_CHECK(cudaMalloc(&c->mu_dev, 8 * c->limbs));
     NTTB200_CHECK(cudaMalloc(&c->qbit_dev, 4 * c->limbs));
-    NTTB200_CHECK(cudaMemcpy(c->psi, psi_h, tot * 8, cudaMemcpyHostToDevice));
-    NTTB200_CHECK(cudaMemcpy(c->psiinv, psiinv_h, tot * 8, cudaMemcpyHostToDevice));
-    NTTB200_CHECK(cudaMemcpy(c->psi_s, ps.data(), tot * 8, cudaMemcpyHostToDevice));
-    NTTB200_CHECK(cudaMemcpy(c->psiinv_s, pis.data(), tot * 8, cudaMemcpyHostToDevice));
     NTTB200_CHECK(cudaMemcpy(c->lc, lc.data(), sizeof(LimbConst) * c->limbs, cudaMemcpyHostToDevice));
     NTTB200_CHECK(cudaMemcpy(c->q_dev, c->q.data(), 8 * c->limbs, cudaMemcpyHostToDevice));
     NTTB200_CHECK(cudaMemcpy(c->mu_dev, c->mu.data(), 8 * c->limbs, cudaMemcpyHostToDevice));
     NTTB200_CHECK(cudaMemcpy(c->qbit_dev, c->qbit.data(), 4 * c->limbs, cudaMemcpyHostToDevice));
+    if (roots) {
+        u64 *rd = nullptr;                                               // [roots | inverse roots]
+        NTTB200_CHECK(cudaMalloc(&rd, 16 * c->limbs));
+        NTTB200_CHECK(cudaMemcpy(rd, roots_v.data(), 8 * c->limbs, cudaMemcpyHostToDevice));
+        NTTB200_CHECK(cudaMemcpy(rd + c->limbs, rootsinv_v.data(), 8 * c->limbs, cudaMemcpyHostToDevice));
+        k_build_tables<<<dim3(c->limbs, 2), 1024>>>(c->psi, c->psi_s, c->psiinv, c->psiinv_s, c->q_dev, rd, rd + c->limbs, c->logn);
+        cudaError_t e = cudaDeviceSynchronize();
+        cudaFree(rd);
+        if (e != cudaSuccess) return (int)e;
+    } else {
+        NTTB200_CHECK(cudaMemcpy(c->psi, psi_h, tot * 8, cudaMemcpyHostToDevice));
+        NTTB200_CHECK(cudaMemcpy(c->psiinv, psiinv_h, tot * 8, cudaMemcpyHostToDevice));
+        k_build_companions<<<1184, 256>>>(c->psi, c->psi_s, c->q_dev, c->logn, c->limbs);
+        k_build_companions<<<1184, 256>>>(c->psiinv, c->psiinv_s, c->q_dev, c->logn, c->limbs);
+        NTTB200_CHECK(cudaDeviceSynchronize());
+    }
     return 0;
 }
 
@@ -103,22 +115,9 @@ int nttb200_ctx_create(nttb200_ctx **ctx, unsigned n, unsigned limbs, const nttb
     int r = ctx_alloc(ctx, n, limbs, q);
     if (r) return r;
     nttb200_ctx *c = *ctx;
-    const size_t tot = (size_t)limbs * n;
-    std::vector<u64> psi(tot), psiinv(tot);
-    for (unsigned l = 0; l < limbs; l++) {
-        // parameter.h:5-12: table[i] = root^bitrev(i); filled by walking the exponents in natural order
-        const u64 ql = q[l], root = psi_roots[l] % ql, rootinv = h_modpow(root, ql - 2, ql);
-        if (h_modpow(root, n, ql) != ql - 1) { delete c; *ctx = nullptr; return NTTB200_EINVAL; }   // psi^n = -1
-        u64 p = 1, pi = 1;
-        for (unsigned e = 0; e < n; e++) {
-            const unsigned i = h_bitrev(e, c->logn);
-            psi[l * (size_t)n + i] = p;
-            psiinv[l * (size_t)n + i] = pi;
-            p = (u64)((u128)p * root % ql);
-            pi = (u64)((u128)pi * rootinv % ql);
-        }
-    }
-    r = ctx_finish(c, psi.data(), psiinv.data());
+    for (unsigned l = 0; l < limbs; l++)                               // psi must be a primitive 2n-th root: psi^n = -1
+        if (h_modpow(psi_roots[l] % q[l], n, q[l]) != q[l] - 1) { delete c; *ctx = nullptr; return NTTB200_EINVAL; }
+    r = ctx_finish(c, psi_roots, nullptr, nullptr);                     // tables + companions generated on the device
     if (r) { nttb200_ctx_destroy(c); *ctx = nullptr; }
     return r;
 }
@@ -129,7 +128,7 @@ int nttb200_ctx_create_from_tables(nttb200_ctx **ctx, unsigned n, unsigned limbs
     if (!psi_tables_host || !psiinv_tables_host) return NTTB200_EINVAL;
     int r = ctx_alloc(ctx, n, limbs, q);
     if (r) return r;
-    r = ctx_finish(*ctx, psi_tables_host, psiinv_tables_host);
+    r = ctx_finish(*ctx, nullptr, psi_tables_host, psiinv_tables_host);
     if (r) { nttb200_ctx_destroy(*ctx); *ctx = nullptr; }
     return r;
 }

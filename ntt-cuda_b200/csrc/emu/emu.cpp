@@ -239,3 +239,13 @@ EXPORT int emu_bfv_sharded(int op, unsigned n, unsigned r, const u64 *q, const u
     }
     return 0;
 }
+
+// device-side table generation on the emulator
+#include "../table_kernels.cuh"
+EXPORT int emu_build_tables(u64 *psi, u64 *psi_s, u64 *psiinv, u64 *psiinv_s, const u64 *q, const u64 *roots, const u64 *roots_inv,
+                            unsigned logn, unsigned limbs)
+{
+    emu_dim3 g; g.x = limbs; g.y = 2;
+    emu_launch(g, 128, 0, [&] { k_build_tables(psi, psi_s, psiinv, psiinv_s, q, roots, roots_inv, logn); });
+    return 0;
+}

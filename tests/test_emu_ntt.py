@@ -131,3 +131,22 @@ def test_emu_lazy_policy_at_its_bound(oracle):
     alt = np.where(np.arange(n) % 2 == 0, qs[0] - 1, 0).astype(np.uint64)      # maximises |U - V| in the first stage
     assert np.array_equal(emu.ntt(alt, n, qs, psi[None], psiinv[None], 1, 1, inverse=True, barrett=2, use_tma=0),
                           oracle.inverse_ntt_fast(alt, qs[0], psiinv))
+
+
+def test_emu_device_table_generation(oracle):
+    """csrc/table_kernels.cuh (doubling construction on the device) == parameter.h:5-12 fillTablePsi128, plus companions."""
+    import ctypes as C
+    n, qs, roots = params.RNS_SETS["8k_3q"]
+    logn, L = 13, 3
+    q = np.array(qs, dtype=np.uint64)
+    r = np.array(roots, dtype=np.uint64)
+    ri = np.array([oracle.modinv(x, y) for x, y in zip(roots, qs)], dtype=np.uint64)
+    bufs = [np.zeros(L * n, dtype=np.uint64) for _ in range(4)]
+    u = C.c_ulonglong
+    rc = emu.lib().emu_build_tables(*[emu.p(b, u) for b in bufs], emu.p(q, u), emu.p(r, u), emu.p(ri, u), logn, L)
+    assert rc == 0
+    for l in range(L):
+        psi, psiinv = oracle.fill_psi_tables(roots[l], qs[l], n)
+        assert np.array_equal(bufs[0][l * n:(l + 1) * n], psi) and np.array_equal(bufs[2][l * n:(l + 1) * n], psiinv)
+        assert np.array_equal(bufs[1][l * n:(l + 1) * n], emu.shoup(psi, qs[l]))
+        assert np.array_equal(bufs[3][l * n:(l + 1) * n], emu.shoup(psiinv, qs[l]))
