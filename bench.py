@@ -329,7 +329,7 @@ def run_ours(args):
         alg_bytes = 16.0 * n * POLYS                     # per launch: every coefficient read once + written once
         dom, dom_ms = ("ntt_strided_pass", p1) if p1 >= p2 else ("ntt_contig_pass", p2)
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this workload
-        # (profiles/r01h_ncu_full_summary.md); below the algorithmic 536.9 MB because write-back still sits in L2 at kernel end
+        # (profiles/r01z_ncu_full_summary.md); below the algorithmic 536.9 MB because write-back still sits in L2 at kernel end
         ncu_traffic = {"ntt_strided_pass": 484.5e6, "ntt_contig_pass": 493.4e6}[dom]
         ach = alg_bytes / (dom_ms * 1e-3) / 1e9
         butterflies = POLYS * (n // 2) * 15
