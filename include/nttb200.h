@@ -164,12 +164,17 @@ NTTB200_API void nttb200_bfv_destroy(nttb200_bfv *bfv);
 NTTB200_API nttb200_ctx *nttb200_bfv_ctx(nttb200_bfv *bfv);
 /* pre-sizes the internal keystream scratch so that later calls never allocate */
 NTTB200_API int nttb200_bfv_reserve(nttb200_bfv *bfv, unsigned batch);
+/* Loads a key pair into the context (device pointers; either may be NULL): private copies + Shoup companions.
+ * nttb200_bfv_encrypt(pk = NULL) / nttb200_bfv_decrypt(sk = NULL) then use the loaded key through the FUSED
+ * "NTT (.) key -> INTT" kernel (no canonicalisation of NTT(x), no pointwise pass, two HBM passes fewer); same results. */
+NTTB200_API int nttb200_bfv_load_keys(nttb200_bfv *bfv, const nttb200_u64 *sk, const nttb200_u64 *pk, void *stream);
 /* keygen_rns bfv_keygen.cuh:95 */
 NTTB200_API int nttb200_bfv_keygen(nttb200_bfv *bfv, nttb200_u64 *sk, nttb200_u64 *pk, unsigned batch, nttb200_u64 nonce0, void *stream);
-/* encryption_rns bfv_encryption.cuh:223; pk_per_item = 0: one public key for the batch */
+/* encryption_rns bfv_encryption.cuh:223; pk_per_item = 0: one public key for the batch; pk = NULL: the loaded key */
 NTTB200_API int nttb200_bfv_encrypt(nttb200_bfv *bfv, nttb200_u64 *c, const nttb200_u64 *pk, int pk_per_item, const nttb200_u64 *m,
                                     unsigned batch, nttb200_u64 nonce0, void *stream);
-/* decryption_rns bfv_decryption.cuh:76; m_out[batch][n]; c1 of every item is overwritten (as in the reference) */
+/* decryption_rns bfv_decryption.cuh:76; m_out[batch][n]; c1 of every item is overwritten (as in the reference);
+ * sk = NULL: the loaded key */
 NTTB200_API int nttb200_bfv_decrypt(nttb200_bfv *bfv, nttb200_u64 *m_out, nttb200_u64 *c, const nttb200_u64 *sk, int sk_per_item,
                                     unsigned batch, void *stream);
 

@@ -10,6 +10,7 @@
 // 13 / 16 / 18 per item, creates r streams and mallocs inside decryption_rns, and races dec_round against mod_t.
 #include "internal.h"
 #include "bfv_kernels.cuh"
+#include "table_kernels.cuh"
 
 #include <cmath>
 
@@ -48,6 +49,9 @@ struct nttb200_bfv {
     int gamma_bits = 0;
     // device constant arrays
     u64 *inv_q_last_mod_q = nullptr, *qi_div_t = nullptr, *prod_t_gamma_mod_q = nullptr, *inv_punctured_q = nullptr, *bcm = nullptr;
+    // keys loaded into the context (nttb200_bfv_load_keys): private copies + Shoup companions, enabling the fused
+    // "NTT (.) key -> INTT" kernel; used when encrypt / decrypt are called with a NULL key pointer
+    u64 *sk_l = nullptr, *sk_ls = nullptr, *pk_l = nullptr, *pk_ls = nullptr;
     // grow-only scratch: keystream and gaussian draws
     unsigned char *ks = nullptr; size_t ks_bytes = 0;
     int *es = nullptr; size_t es_count = 0;
@@ -74,6 +78,18 @@ struct Pipe {                 // everything one pipeline run needs, independent 
     cudaStream_t st;
 };
 
+static NttArgsHost pipe_args(const Pipe &P, bool inverse, u64 *a, unsigned num, unsigned division, unsigned group_polys, size_t group_stride)
+{
+    NttArgsHost h{a, inverse ? P.psiinv : P.psi, inverse ? P.psiinv_s : P.psi_s, P.lc, nullptr, nullptr, nullptr, 0, 0, 0, num, division, P.use_tma,
+                  group_polys, group_stride};
+    return h;
+}
+// only the first / second kernel of a transform (execution order), context path
+static int pipe_ntt_pass(const Pipe &P, bool inverse, int which, u64 *a, unsigned num, unsigned division, unsigned group_polys, size_t group_stride)
+{
+    return launch_ntt_pass(inverse, inverse ? P.policy_inv : P.policy_fwd, P.logn, pipe_args(P, inverse, a, num, division, group_polys, group_stride),
+                           which, P.st);
+}
 static int pipe_ntt(const Pipe &P, bool inverse, u64 *a, unsigned num, unsigned division, unsigned group_polys, size_t group_stride)
 {
     NttArgsHost h{a, inverse ? P.psiinv : P.psi, inverse ? P.psiinv_s : P.psi_s, P.lc, P.L.q, P.L.mu, P.L.qbit, 0, 0, 0, num, division, P.use_tma,
@@ -119,6 +135,40 @@ static int run_encrypt(const Pipe &P, unsigned char *in, size_t in_stride, int *
     KCHECK();
     NTTB200_TRY(pipe_ntt(P, true, c, batch * 2 * r, r, 0, 0));                             // :271
     k_encrypt_epilogue<<<pair_grid(n, 2, batch), pair_block(n, 2, batch), 0, P.st>>>(c, es, m, m_stride, n, r, batch, t, P.qi_div_t, P.L);   // :280-289
+    KCHECK();
+    return 0;
+}
+
+// encryption with a key loaded into the context: strided forward pass, ONE fused kernel (contig forward pass, (.) pk0 / pk1 by
+// Shoup companions, contig inverse pass for both halves), strided inverse pass, epilogue.  7 launches.
+static int run_encrypt_fused(const Pipe &P, bool lazy, unsigned char *in, size_t in_stride, int *es, u64 *c, const u64 *pk, const u64 *pk_s,
+                             const u64 *m, size_t m_stride, u64 t, unsigned batch, u64 nonce0)
+{
+    const unsigned n = P.n, r = P.r;
+    const size_t rn = (size_t)r * n;
+    const u64 nblk = (9 * (size_t)n) / 64;
+    k_salsa20_keystream<<<grid_for(nblk * batch, 256), 256, 0, P.st>>>(in, nblk, (u64)batch, in_stride, default_key(), nonce0);
+    k_encrypt_sample<<<pair_grid(n, batch, 1), pair_block(n, batch, 1), 0, P.st>>>(in, in_stride, c, es, n, r, batch, P.L.q);
+    KCHECK();
+    NTTB200_TRY(pipe_ntt_pass(P, false, 0, c, batch * r, r, r, 2 * rn));                   // strided forward pass on NTT input u
+    NTTB200_TRY(launch_fused_mul(lazy, P.logn, pipe_args(P, false, c, batch * 2 * r, r, 2 * r, 2 * rn), P.psiinv, P.psiinv_s, pk, pk_s, 0, rn, r,
+                                 0, 0, r, batch, 2, P.st));
+    NTTB200_TRY(pipe_ntt_pass(P, true, 1, c, batch * 2 * r, r, 0, 0));                     // strided inverse pass on both halves
+    k_encrypt_epilogue<<<pair_grid(n, 2, batch), pair_block(n, 2, batch), 0, P.st>>>(c, es, m, m_stride, n, r, batch, t, P.qi_div_t, P.L);
+    KCHECK();
+    return 0;
+}
+// decryption with a loaded secret key: 4 launches
+static int run_decrypt_fused(const Pipe &P, bool lazy, u64 *c, const u64 *sk, const u64 *sk_s, u64 *out, size_t out_stride, const DecryptConsts &D,
+                             unsigned batch)
+{
+    const unsigned n = P.n, rp = D.rp;
+    const size_t item = (size_t)2 * (rp + 1) * n, c1_off = (size_t)(rp + 1) * n;
+    NTTB200_TRY(pipe_ntt_pass(P, false, 0, c + c1_off, batch * rp, rp, rp, item));
+    NTTB200_TRY(launch_fused_mul(lazy, P.logn, pipe_args(P, false, c, batch * 2 * (rp + 1), rp, 2 * (rp + 1), item), P.psiinv, P.psiinv_s, sk, sk_s,
+                                 0, 0, rp, rp + 1, rp + 1, rp + 1, batch, 1, P.st));
+    NTTB200_TRY(pipe_ntt_pass(P, true, 1, c + c1_off, batch * rp, rp, rp, item));
+    k_decrypt_epilogue<<<pair_grid(n, batch, 1), pair_block(n, batch, 1), 0, P.st>>>(c, item, c1_off, out, out_stride, n, batch, D, P.L);
     KCHECK();
     return 0;
 }
@@ -222,6 +272,7 @@ void nttb200_bfv_destroy(nttb200_bfv *b)
     cudaFree(b->inv_q_last_mod_q); cudaFree(b->qi_div_t); cudaFree(b->prod_t_gamma_mod_q); cudaFree(b->inv_punctured_q); cudaFree(b->bcm);
     if (b->ks) cudaFree(b->ks);
     if (b->es) cudaFree(b->es);
+    cudaFree(b->sk_l); cudaFree(b->sk_ls); cudaFree(b->pk_l); cudaFree(b->pk_ls);
     nttb200_ctx_destroy(b->ctx);
     delete b;
 }
@@ -233,6 +284,27 @@ int nttb200_bfv_reserve(nttb200_bfv *b, unsigned batch)
     if (!b || !batch) return NTTB200_EINVAL;
     const size_t rn = (size_t)b->r * b->n;
     return ensure_scratch(b, (9 * rn + 4 * (size_t)b->n) * batch, (size_t)2 * b->n * batch);
+}
+
+// Copies the keys into the context and builds their Shoup companions (one division per coefficient, once per key).
+int nttb200_bfv_load_keys(nttb200_bfv *b, const nttb200_u64 *sk, const nttb200_u64 *pk, void *stream)
+{
+    if (!b || (!sk && !pk)) return NTTB200_EINVAL;
+    const size_t rn = (size_t)b->r * b->n;
+    const nttb200_ctx *c = b->ctx;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (sk) {
+        if (!b->sk_l) { NTTB200_CHECK(cudaMalloc(&b->sk_l, rn * 8)); NTTB200_CHECK(cudaMalloc(&b->sk_ls, rn * 8)); }
+        NTTB200_CHECK(cudaMemcpyAsync(b->sk_l, sk, rn * 8, cudaMemcpyDeviceToDevice, st));
+        k_build_companions<<<grid_for(rn, 256), 256, 0, st>>>(b->sk_l, b->sk_ls, c->q_dev, c->logn, b->r, b->r);
+    }
+    if (pk) {
+        if (!b->pk_l) { NTTB200_CHECK(cudaMalloc(&b->pk_l, 2 * rn * 8)); NTTB200_CHECK(cudaMalloc(&b->pk_ls, 2 * rn * 8)); }
+        NTTB200_CHECK(cudaMemcpyAsync(b->pk_l, pk, 2 * rn * 8, cudaMemcpyDeviceToDevice, st));
+        k_build_companions<<<grid_for(2 * rn, 256), 256, 0, st>>>(b->pk_l, b->pk_ls, c->q_dev, c->logn, b->r, 2 * b->r);
+    }
+    KCHECK();
+    return 0;
 }
 
 int nttb200_bfv_keygen(nttb200_bfv *b, nttb200_u64 *sk, nttb200_u64 *pk, unsigned batch, nttb200_u64 nonce0, void *stream)
@@ -247,18 +319,20 @@ int nttb200_bfv_keygen(nttb200_bfv *b, nttb200_u64 *sk, nttb200_u64 *pk, unsigne
 int nttb200_bfv_encrypt(nttb200_bfv *b, nttb200_u64 *c, const nttb200_u64 *pk, int pk_per_item, const nttb200_u64 *m, unsigned batch,
                         nttb200_u64 nonce0, void *stream)
 {
-    if (!b || !c || !pk || !m || !batch || batch > 65535) return NTTB200_EINVAL;
+    if (!b || !c || !m || !batch || batch > 65535 || (!pk && !b->pk_l)) return NTTB200_EINVAL;
     NTTB200_TRY(nttb200_bfv_reserve(b, batch));
     const size_t rn = (size_t)b->r * b->n;
     Pipe P = pipe_from_bfv(b, (cudaStream_t)stream);
+    if (!pk) return run_encrypt_fused(P, b->ctx->lazy_ok != 0, b->ks, 9 * (size_t)b->n, b->es, c, b->pk_l, b->pk_ls, m, b->n, b->t, batch, nonce0);
     return run_encrypt(P, b->ks, 9 * (size_t)b->n, b->es, c, pk, pk_per_item ? 2 * rn : 0, m, b->n, b->t, batch, nonce0);
 }
 
 int nttb200_bfv_decrypt(nttb200_bfv *b, nttb200_u64 *m_out, nttb200_u64 *c, const nttb200_u64 *sk, int sk_per_item, unsigned batch, void *stream)
 {
-    if (!b || !c || !sk || !m_out || !batch || batch > 65535) return NTTB200_EINVAL;
+    if (!b || !c || !m_out || !batch || batch > 65535 || (!sk && !b->sk_l)) return NTTB200_EINVAL;
     Pipe P = pipe_from_bfv(b, (cudaStream_t)stream);
     DecryptConsts D{b->t, b->gamma, b->mu_gamma, b->gamma_div_2, b->neg_inv_t, b->neg_inv_gamma, b->gamma_bits, b->r - 1, b->bcm};
+    if (!sk) return run_decrypt_fused(P, b->ctx->lazy_ok != 0, c, b->sk_l, b->sk_ls, m_out, b->n, D, batch);
     return run_decrypt(P, c, sk, sk_per_item ? (size_t)b->r * b->n : 0, m_out, b->n, D, batch);
 }
 

@@ -322,26 +322,34 @@ NTT_KERNEL void k_encrypt_epilogue(u64 *c, const int *es, const u64 *m_poly, siz
             f0 = tpow2 ? (m0 + tfix) >> tsh : (m0 + tfix) / t;
             f1 = tpow2 ? (m1 + tfix) >> tsh : (m1 + tfix) / t;
         }
-        for (unsigned l = 0; l + 1 < r; l++) {
-            const EncLimb &P = K[l];
-            const ulonglong2 xv = ld2(ch + (size_t)l * n + j);
-            u64 x0 = xv.x + signed_to_residue(d0, P.q), x1 = xv.y + signed_to_residue(d1, P.q);
-            if (x0 > P.q) x0 -= P.q;
-            if (x1 > P.q) x1 -= P.q;
-            u64 t0 = mod_exact(cl0, P.q, P.ratio), t1 = mod_exact(cl1, P.q, P.ratio);
-            if (t0 < P.half_mod) t0 += P.q;
-            if (t1 < P.half_mod) t1 += P.q;
-            t0 -= P.half_mod; t1 -= P.half_mod;
-            if (x0 < t0) x0 += P.q;
-            if (x1 < t1) x1 += P.q;
-            x0 -= t0; x1 -= t1;
-            x0 = mul_const(x0, P.inv_q_last, P.inv_q_last_s, P.fast != 0, P.q, P.mu, P.qbit);
-            x1 = mul_const(x1, P.inv_q_last, P.inv_q_last_s, P.fast != 0, P.q, P.mu, P.qbit);
-            if (h == 0) {
-                x0 = mod_exact(x0 + ((m0 * P.qdt) + f0), P.q, P.ratio);
-                x1 = mod_exact(x1 + ((m1 * P.qdt) + f1), P.q, P.ratio);
+        // limbs in chunks of 4 with the loads issued together: one dependent 16-byte load per limb leaves HBM idle
+        for (unsigned l0 = 0; l0 + 1 < r; l0 += 4) {
+            ulonglong2 xv[4];
+            NTT_UNROLL
+            for (unsigned i = 0; i < 4; i++)
+                if (l0 + i + 1 < r) xv[i] = ld2(ch + (size_t)(l0 + i) * n + j);
+            NTT_UNROLL
+            for (unsigned i = 0; i < 4; i++) {
+                if (l0 + i + 1 >= r) break;
+                const EncLimb &P = K[l0 + i];
+                u64 x0 = xv[i].x + signed_to_residue(d0, P.q), x1 = xv[i].y + signed_to_residue(d1, P.q);
+                if (x0 > P.q) x0 -= P.q;
+                if (x1 > P.q) x1 -= P.q;
+                u64 t0 = mod_exact(cl0, P.q, P.ratio), t1 = mod_exact(cl1, P.q, P.ratio);
+                if (t0 < P.half_mod) t0 += P.q;
+                if (t1 < P.half_mod) t1 += P.q;
+                t0 -= P.half_mod; t1 -= P.half_mod;
+                if (x0 < t0) x0 += P.q;
+                if (x1 < t1) x1 += P.q;
+                x0 -= t0; x1 -= t1;
+                x0 = mul_const(x0, P.inv_q_last, P.inv_q_last_s, P.fast != 0, P.q, P.mu, P.qbit);
+                x1 = mul_const(x1, P.inv_q_last, P.inv_q_last_s, P.fast != 0, P.q, P.mu, P.qbit);
+                if (h == 0) {
+                    x0 = mod_exact(x0 + ((m0 * P.qdt) + f0), P.q, P.ratio);
+                    x1 = mod_exact(x1 + ((m1 * P.qdt) + f1), P.q, P.ratio);
+                }
+                st2(ch + (size_t)(l0 + i) * n + j, x0, x1);
             }
-            st2(ch + (size_t)l * n + j, x0, x1);
         }
     }
 }
@@ -413,6 +421,23 @@ __device__ __forceinline__ void dec_accumulate(const DecLimb &P, u64 a1, u64 a0,
     acc_t += (v * P.bt) & (u64)mask32;
     acc_g = add_mod_gamma(acc_g, g, D.gamma);
 }
+// both coefficients of pair j over `count` limbs, four limbs' loads (8 x 16 bytes) in flight at a time
+__device__ __forceinline__ void dec_sum_limbs(const DecLimb *K, const u64 *c0, const u64 *c1, unsigned n, u32 j, unsigned count, u32 mask32,
+                                              const DecryptConsts &D, u64 &at0, u64 &at1, u64 &ag0, u64 &ag1)
+{
+    for (unsigned l0 = 0; l0 < count; l0 += 4) {
+        ulonglong2 a1[4], a0[4];
+        NTT_UNROLL
+        for (unsigned i = 0; i < 4; i++)
+            if (l0 + i < count) { a1[i] = ld2(c1 + (size_t)(l0 + i) * n + j); a0[i] = ld2(c0 + (size_t)(l0 + i) * n + j); }
+        NTT_UNROLL
+        for (unsigned i = 0; i < 4; i++) {
+            if (l0 + i >= count) break;
+            dec_accumulate(K[l0 + i], a1[i].x, a0[i].x, mask32, D, at0, ag0);
+            dec_accumulate(K[l0 + i], a1[i].y, a0[i].y, mask32, D, at1, ag1);
+        }
+    }
+}
 __device__ __forceinline__ u64 dec_finish_one(u64 acc_t, u64 acc_g, u32 mask32, const DecryptConsts &D)
 {
     u64 mt = acc_t & (u64)mask32;
@@ -436,11 +461,7 @@ NTT_KERNEL void k_decrypt_epilogue(const u64 *c, size_t item_stride, size_t c1_o
     const u64 *c0 = c + k * item_stride, *c1 = c0 + c1_off;
     NTT_PAIR_STRIDE(j, n) {
         u64 at0 = 0, at1 = 0, ag0 = 0, ag1 = 0;
-        for (unsigned l = 0; l < D.rp; l++) {
-            const ulonglong2 a1 = ld2(c1 + (size_t)l * n + j), a0 = ld2(c0 + (size_t)l * n + j);
-            dec_accumulate(K[l], a1.x, a0.x, mask32, D, at0, ag0);
-            dec_accumulate(K[l], a1.y, a0.y, mask32, D, at1, ag1);
-        }
+        dec_sum_limbs(K, c0, c1, n, j, D.rp, mask32, D, at0, at1, ag0, ag1);
         st2(out + k * out_stride + j, dec_finish_one(at0, ag0, mask32, D), dec_finish_one(at1, ag1, mask32, D));
     }
 }
@@ -462,11 +483,7 @@ NTT_KERNEL void k_decrypt_partial(const u64 *c, size_t item_stride, size_t c1_of
     const u64 *c0 = c + k * item_stride, *c1 = c0 + c1_off;
     NTT_PAIR_STRIDE(j, n) {
         u64 at0 = 0, at1 = 0, ag0 = 0, ag1 = 0;
-        for (unsigned ll = 0; ll < count; ll++) {
-            const ulonglong2 a1 = ld2(c1 + (size_t)ll * n + j), a0 = ld2(c0 + (size_t)ll * n + j);
-            dec_accumulate(K[ll], a1.x, a0.x, mask32, D, at0, ag0);
-            dec_accumulate(K[ll], a1.y, a0.y, mask32, D, at1, ag1);
-        }
+        dec_sum_limbs(K, c0, c1, n, j, count, mask32, D, at0, at1, ag0, ag1);
         st2(part + k * 2 * n + j, at0, at1);
         st2(part + k * 2 * n + n + j, ag0, ag1);
     }

@@ -76,8 +76,8 @@ static int ctx_finish(nttb200_ctx *c, const u64 *roots, const u64 *psi_h, const 
     } else {
         NTTB200_CHECK(cudaMemcpy(c->psi, psi_h, tot * 8, cudaMemcpyHostToDevice));
         NTTB200_CHECK(cudaMemcpy(c->psiinv, psiinv_h, tot * 8, cudaMemcpyHostToDevice));
-        k_build_companions<<<1184, 256>>>(c->psi, c->psi_s, c->q_dev, c->logn, c->limbs);
-        k_build_companions<<<1184, 256>>>(c->psiinv, c->psiinv_s, c->q_dev, c->logn, c->limbs);
+        k_build_companions<<<1184, 256>>>(c->psi, c->psi_s, c->q_dev, c->logn, c->limbs, c->limbs);
+        k_build_companions<<<1184, 256>>>(c->psiinv, c->psiinv_s, c->q_dev, c->logn, c->limbs, c->limbs);
         NTTB200_CHECK(cudaDeviceSynchronize());
     }
     return 0;

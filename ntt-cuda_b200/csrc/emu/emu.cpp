@@ -53,6 +53,8 @@ void emu_tma_4d(bool load, const TensorMap *m, void *smem, int c0, int c1, int c
 
 using namespace nttb200;
 
+static int g_which = -1;   // -1: whole transform, 0 / 1: only the first / second kernel in execution order
+
 template <class P, int LOGN, bool INV>
 static void run_one(const NttArgs &A)
 {
@@ -80,7 +82,37 @@ static void run_one(const NttArgs &A)
     const size_t smem_s = (size_t)SC::NT * R * 128 + 1024 + 16, smem_c = (size_t)kContigRows * 128 + 1024 + 16;
     auto strided = [&] { emu_launch(gs, R * SC::NT, smem_s, [&] { ntt_strided_pass<P, LOGN, INV>(ms, A); }); };
     auto contig = [&] { emu_launch(gc, kContigRows, smem_c, [&] { ntt_contig_pass<P, LOGN, INV>(mc, A); }); };
-    if (!INV) { strided(); contig(); } else { contig(); strided(); }
+    if (!INV) { if (g_which != 1) strided(); if (g_which != 0) contig(); } else { if (g_which != 1) contig(); if (g_which != 0) strided(); }
+}
+
+template <class PF, class PI, int LOGN, int NOUT>
+static void run_fused_one(const FusedArgs &F)
+{
+    const NttArgs &A = F.A;
+    TensorMap mc;
+    EmuTmapDesc dc{};
+    dc.base = (unsigned char *)A.a; dc.rank = 3;
+    dc.dims[0] = 16; dc.dims[1] = ((size_t)A.group_polys << LOGN) >> 4; dc.dims[2] = F.items;
+    dc.strides[0] = 8; dc.strides[1] = 128; dc.strides[2] = A.group_stride * 8;
+    dc.box[0] = 16; dc.box[1] = kContigRows; dc.box[2] = 1; dc.swizzle128 = 1;
+    memcpy(mc.opaque, &dc, sizeof dc);
+    emu_dim3 g;
+    g.x = F.items * F.r * (unsigned)((((size_t)1 << LOGN) >> 4) / kContigRows);
+    emu_launch(g, kContigRows, (size_t)kContigRows * 128 * NOUT + 1024 + 16, [&] { ntt_contig_fused_mul<PF, PI, LOGN, NOUT>(mc, F); });
+}
+template <class PF, class PI, int NOUT>
+static int run_fused_logn(int logn, const FusedArgs &F)
+{
+    switch (logn) {
+    case 11: run_fused_one<PF, PI, 11, NOUT>(F); return 0;
+    case 12: run_fused_one<PF, PI, 12, NOUT>(F); return 0;
+    case 13: run_fused_one<PF, PI, 13, NOUT>(F); return 0;
+    case 14: run_fused_one<PF, PI, 14, NOUT>(F); return 0;
+    case 15: run_fused_one<PF, PI, 15, NOUT>(F); return 0;
+    case 16: run_fused_one<PF, PI, 16, NOUT>(F); return 0;
+    case 17: run_fused_one<PF, PI, 17, NOUT>(F); return 0;
+    }
+    return 1;
 }
 
 template <class P, bool INV>
@@ -127,14 +159,30 @@ struct EmuRing {
 };
 template <class F> void ew(F &&f) { emu_dim3 g; g.x = 3; emu_launch(g, 64, 0, f); }
 template <class F> void ew3(unsigned y, unsigned z, F &&f) { emu_dim3 g; g.x = 2; g.y = y; g.z = z; emu_launch(g, 64, 0, f); }
-int ring_ntt(const EmuRing &R, bool inv, u64 *a, unsigned num, unsigned division, unsigned gp, size_t gs)
+int ring_ntt(const EmuRing &R, bool inv, u64 *a, unsigned num, unsigned division, unsigned gp, size_t gs, int which = -1)
 {
-    return emu_ntt(inv, R.barrett ? 1 : 2, 1, (int)R.logn, a, inv ? R.psiinv : R.psi, inv ? R.psiinv_s : R.psi_s, R.lc, R.q, R.mu, R.qbit,
+    struct Restore { ~Restore() { g_which = -1; } } restore;
+    g_which = which;
+    return emu_ntt(inv, R.barrett < 0 ? 0 : R.barrett ? 1 : 2, 1, (int)R.logn, a, inv ? R.psiinv : R.psi, inv ? R.psiinv_s : R.psi_s, R.lc, R.q, R.mu, R.qbit,
                    num, division, gp, gs);
+}
+// fused contig-forward (.) key -> contig-inverse, as launch_fused_mul in csrc/ntt_launch.cu; lazy = 0 uses ShoupPolicy both ways
+int ring_fused(const EmuRing &R, bool lazy, u64 *a, unsigned group_polys, size_t group_stride, const u64 *key, const u64 *key_s,
+               size_t key_half_stride, unsigned r, unsigned in_off, unsigned out0, unsigned out1, unsigned items, int nout)
+{
+    FusedArgs F{};
+    F.A.a = a; F.A.tw = R.psi; F.A.tws = R.psi_s; F.A.lc = R.lc; F.A.num = items * r; F.A.division = r; F.A.use_tma = 1;
+    F.A.group_polys = group_polys; F.A.group_stride = group_stride;
+    F.twi = R.psiinv; F.twis = R.psiinv_s; F.key = key; F.key_s = key_s; F.key_item_stride = 0; F.key_half_stride = key_half_stride;
+    F.r = r; F.in_off = in_off; F.out_off[0] = out0; F.out_off[1] = out1; F.items = items;
+    if (lazy) return nout == 2 ? run_fused_logn<ShoupLazyPolicy, ShoupLazyInvPolicy, 2>((int)R.logn, F)
+                               : run_fused_logn<ShoupLazyPolicy, ShoupLazyInvPolicy, 1>((int)R.logn, F);
+    return nout == 2 ? run_fused_logn<ShoupPolicy, ShoupPolicy, 2>((int)R.logn, F) : run_fused_logn<ShoupPolicy, ShoupPolicy, 1>((int)R.logn, F);
 }
 }  // namespace
 
 #define EXPORT extern "C" __attribute__((visibility("default")))
+#include "../table_kernels.cuh"
 
 EXPORT int emu_bfv(int op, unsigned n, unsigned r, const u64 *q, const u64 *mu, const u32 *qbit, const u64 *psi, const u64 *psiinv,
                    const u64 *psi_s, const u64 *psiinv_s, const LimbConst *lc, int barrett,
@@ -166,6 +214,30 @@ EXPORT int emu_bfv(int op, unsigned n, unsigned r, const u64 *q, const u64 *mu, 
         ew3(r, batch, [&] { k_encrypt_mul(c, pk, per_item_keys ? 2 * rn : 0, n, r, batch, L); });
         ring_ntt(R, true, c, batch * 2 * r, r, 0, 0);
         ew3(2, batch, [&] { k_encrypt_epilogue(c, es, m, (size_t)n, n, r, batch, t, qi_div_t, L); });
+    } else if (op == 3 || op == 5) {   // encrypt through the fused kernel, key loaded (op 5: non-lazy policies); companions built here
+        const size_t stride = 9 * (size_t)n; const u64 nblk = stride / 64;
+        u64 *pk_s = new u64[2 * rn];
+        ew([&] { k_build_companions(pk, pk_s, q, R.logn, r, 2 * r); });
+        ew([&] { k_salsa20_keystream(in, nblk, (u64)batch, stride, key, nonce0); });
+        ew3(batch, 1, [&] { k_encrypt_sample(in, stride, c, es, n, r, batch, q); });
+        if (op == 5) R.barrett = -1;
+        ring_ntt(R, false, c, batch * r, r, r, 2 * rn, 0);
+        ring_fused(R, op == 3, c, 2 * r, 2 * rn, pk, pk_s, rn, r, 0, 0, r, batch, 2);
+        ring_ntt(R, true, c, batch * 2 * r, r, 0, 0, 1);
+        ew3(2, batch, [&] { k_encrypt_epilogue(c, es, m, (size_t)n, n, r, batch, t, qi_div_t, L); });
+        delete[] pk_s;
+    } else if (op == 4 || op == 6) {   // decrypt through the fused kernel
+        const unsigned rp = r - 1;
+        const size_t item = 2 * rn, c1_off = rn;
+        u64 *sk_s = new u64[rn];
+        ew([&] { k_build_companions(sk, sk_s, q, R.logn, r, r); });
+        DecryptConsts D{t, gamma, mu_gamma, gamma >> 1, neg_inv_t, neg_inv_gamma, gamma_bits, rp, bcm};
+        if (op == 6) R.barrett = -1;
+        ring_ntt(R, false, c + c1_off, batch * rp, rp, rp, item, 0);
+        ring_fused(R, op == 4, c, 2 * r, item, sk, sk_s, 0, rp, r, r, r, batch, 1);
+        ring_ntt(R, true, c + c1_off, batch * rp, rp, rp, item, 1);
+        ew3(batch, 1, [&] { k_decrypt_epilogue(c, item, c1_off, out, (size_t)n, n, batch, D, L); });
+        delete[] sk_s;
     } else {                // decrypt (r = all limbs)
         const unsigned rp = r - 1;
         const size_t item = 2 * rn, c1_off = rn;
@@ -241,7 +313,6 @@ EXPORT int emu_bfv_sharded(int op, unsigned n, unsigned r, const u64 *q, const u
 }
 
 // device-side table generation on the emulator
-#include "../table_kernels.cuh"
 EXPORT int emu_build_tables(u64 *psi, u64 *psi_s, u64 *psiinv, u64 *psiinv_s, const u64 *q, const u64 *roots, const u64 *roots_inv,
                             unsigned logn, unsigned limbs)
 {

@@ -55,6 +55,10 @@ struct NttArgsHost {
     size_t group_stride = 0;    // elements between groups
 };
 
+int launch_fused_mul(bool lazy, unsigned logn, const NttArgsHost &h, const u64 *twi, const u64 *twis, const u64 *key, const u64 *key_s,
+                     size_t key_item_stride, size_t key_half_stride, unsigned r, unsigned in_off, unsigned out_off0, unsigned out_off1,
+                     unsigned items, int nout, cudaStream_t st);
+
 int get_tma_default();
 
 }  // namespace nttb200

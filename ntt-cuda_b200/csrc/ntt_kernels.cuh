@@ -131,6 +131,8 @@ struct ShoupPolicy {
         U = csub(s, twoq);
         V = shoup_mul_n(d, t.w, t.ws, nq);
     }
+    // lazy product with a key coefficient (companion ks): any 64-bit x -> [0, 2q), a valid inverse-round input
+    __device__ __forceinline__ u64 mul_key(u64 x, u64 k, u64 ks) const { return shoup_mul_n(x, k, ks, nq); }
     // last inverse stage (length = 1) with n^-1 folded in; canonical outputs
     __device__ __forceinline__ void gs_last(u64 &U, u64 &V) const
     {
@@ -182,6 +184,7 @@ struct ShoupLazyInvPolicy : ShoupPolicy {
         ShoupPolicy::init(A, limb, n);
         fourq = twoq + twoq;
     }
+    __device__ __forceinline__ u64 mul_key(u64 x, u64 k, u64 ks) const { return shoup_mul_a(x, k, ks, nq); }   // < B = 4q
     // e: log2 of the common bound multiplier of U and V (compile-time after unrolling)
     __device__ __forceinline__ void gs_lazy(u64 &U, u64 &V, const Tw &t, int e) const
     {
@@ -576,6 +579,125 @@ ntt_contig_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
     } else {
         __syncthreads();
         tile_copy_coop<true, false>(tile, g, 16, RT, tid, RT);
+    }
+    (void)bar;
+}
+
+// ---- fused "contig forward pass  (.) key  ->  contig inverse pass" ----------------------------------------------------
+// BFV never needs NTT(x) itself, only INTT(NTT(x) (.) key).  With the key's Shoup companions in HBM the
+// product is a lazy Shoup multiplication, so the thread that finishes the forward row round multiplies its 16 coefficients
+// in registers and walks straight into the inverse row round: no canonicalisation, no pointwise kernel, no HBM round trip
+// of NTT(x), one shared-memory round trip less.  NOUT = 2 produces both halves of a ciphertext from one NTT(u) (pk0, pk1).
+struct FusedArgs {
+    NttArgs A;                 // data array + FORWARD tables (tw = psi, tws = psi_s); group = one item
+    const u64 *twi, *twis;     // inverse tables
+    const u64 *key, *key_s;    // key polynomials (NTT domain, canonical) and floor(key * 2^64 / q); [item?][NOUT][r][n]
+    size_t key_item_stride;    // 0: one key for every item
+    size_t key_half_stride;    // distance between the two key halves (NOUT = 2)
+    u32 r;                     // polynomials per half = limbs; CTA index = ((item * r) + limb) * tiles + tile
+    u32 in_off, out_off[2];    // polynomial index inside the item's group of the input / outputs for limb 0
+    u32 items;
+};
+
+template <class PF, class PI, int LOGN, int NOUT>
+__global__ void __launch_bounds__(kContigRows, NOUT == 2 ? 3 : 4)
+ntt_contig_fused_mul(const __grid_constant__ TensorMap tmap, FusedArgs F)
+{
+    using SC = Sched<LOGN>;
+    constexpr int K1 = SC::K1, K2 = SC::K2, SA = K2 - 4, NC = 16 >> SA, RT = kContigRows;
+    constexpr u32 n = 1u << LOGN, TILES = (n >> 4) / RT;
+    const NttArgs &A = F.A;
+    NTT_DYN_SMEM(raw);
+    u64 *tile = align_1024(raw);
+    u64 *tile2 = tile + (size_t)RT * 16;                 // second output (NOUT = 2)
+    u64 *bar = tile + (size_t)RT * 16 * NOUT;
+    const u32 tid = threadIdx.x;
+    const u32 pl = blockIdx.x / TILES, rip0 = (blockIdx.x % TILES) * RT;
+    const u32 item = pl / F.r, limb = pl - item * F.r;
+    PF pf;
+    pf.init(A, limb, n);
+    NttArgs Ai = A;
+    Ai.tw = F.twi; Ai.tws = F.twis;
+    PI pi;
+    pi.init(Ai, limb, n);
+    const int row_in = (int)((F.in_off + limb) * (n >> 4) + rip0);
+    const int row_o0 = (int)((F.out_off[0] + limb) * (n >> 4) + rip0);
+    const int row_o1 = (int)((F.out_off[1] + limb) * (n >> 4) + rip0);
+    u64 *gbase = A.a + (size_t)item * A.group_stride;
+
+    if (A.use_tma & 1u) {
+#ifdef NTTB200_EMU
+        if (tid == 0) emu_tma_3d(true, &tmap, tile, 0, row_in, (int)item);
+        __syncthreads();
+#else
+        if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+        __syncthreads();
+        if (tid == 0) { mbar_expect_tx(bar, (u32)(RT * 128)); tma_load_3d(tile, &tmap, bar, 0, row_in, (int)item); }
+        mbar_wait(bar, 0);
+#endif
+    } else {
+        tile_copy_coop<true, true>(tile, gbase + (size_t)row_in * 16, 16, RT, tid, RT);
+        __syncthreads();
+    }
+
+    const u32 t = tid & ((1u << SA) - 1u), bl = tid >> SA;
+    const u32 twA = (1u << K1) + (rip0 >> SA) + bl, twB = (n >> 4) + rip0 + tid;
+    u64 v[16];
+    // forward: column round, row round (values stay lazy)
+    regs_rows<SA, true, true>(tile, bl << SA, 0, t * NC, v);
+    ct_stages<SA, NC>(v, twA, pf);
+    regs_rows<SA, true, false>(tile, bl << SA, 0, t * NC, v);
+    __syncwarp();
+    regs_row<true, true>(tile, tid, v);
+    ct_stages<4, 1>(v, twB, pf);
+    // (.) key, inverse row round, per output
+    const size_t krow = (size_t)item * F.key_item_stride + ((size_t)limb << LOGN) + ((size_t)(rip0 + tid) << 4);
+    NTT_UNROLL
+    for (int o = 0; o < NOUT; o++) {
+        const u64 *kp = F.key + krow + (size_t)o * F.key_half_stride, *ks = F.key_s + krow + (size_t)o * F.key_half_stride;
+        u64 x[16];
+        NTT_UNROLL
+        for (int c = 0; c < 8; c++) {
+            const ulonglong2 kv = __ldg(reinterpret_cast<const ulonglong2 *>(kp) + c), sv = __ldg(reinterpret_cast<const ulonglong2 *>(ks) + c);
+            x[2 * c] = pi.mul_key(v[2 * c], kv.x, sv.x);
+            x[2 * c + 1] = pi.mul_key(v[2 * c + 1], kv.y, sv.y);
+        }
+        gs_stages<4, 1, false>(x, twB, pi);
+        u64 *dst = o == 0 ? tile : tile2;
+        if (NOUT == 2 && o == 0) __syncwarp();            // every lane has read its forward row before rows are overwritten
+        regs_row<true, false>(dst, tid, x);
+    }
+    __syncwarp();
+    // inverse column round on each output tile
+    NTT_UNROLL
+    for (int o = 0; o < NOUT; o++) {
+        u64 *dst = o == 0 ? tile : tile2;
+        regs_rows<SA, true, true>(dst, bl << SA, 0, t * NC, v);
+        gs_stages<SA, NC, false>(v, twA, pi);
+        regs_rows<SA, true, false>(dst, bl << SA, 0, t * NC, v);
+    }
+
+    if (A.use_tma & 1u) {
+#ifdef NTTB200_EMU
+        __syncthreads();
+        if (tid == 0) {
+            emu_tma_3d(false, &tmap, tile, 0, row_o0, (int)item);
+            if (NOUT == 2) emu_tma_3d(false, &tmap, tile2, 0, row_o1, (int)item);
+        }
+#else
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            tma_store_3d(&tmap, tile, 0, row_o0, (int)item);
+            if (NOUT == 2) tma_store_3d(&tmap, tile2, 0, row_o1, (int)item);
+            tma_store_commit();
+            tma_store_wait_read<0>();
+        }
+#endif
+    } else {
+        __syncthreads();
+        tile_copy_coop<true, false>(tile, gbase + (size_t)row_o0 * 16, 16, RT, tid, RT);
+        if (NOUT == 2) tile_copy_coop<true, false>(tile2, gbase + (size_t)row_o1 * 16, 16, RT, tid, RT);
     }
     (void)bar;
 }

@@ -157,6 +157,63 @@ int launch_ntt_pass(bool inverse, int policy, unsigned logn, const NttArgsHost &
     return 0;
 }
 
+// ---- fused contig-forward (.) key -> contig-inverse -------------------------------------------------------------------
+template <class PF, class PI, int LOGN, int NOUT>
+static int launch_fused_one(const FusedArgs &F, const CUtensorMap &mc, cudaStream_t st)
+{
+    constexpr size_t smem = (size_t)kContigRows * 128 * NOUT + 1024 + 16;
+    static bool attr_done[64] = {false};
+    int dev = 0;
+    NTTB200_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+        NTTB200_CHECK(cudaFuncSetAttribute(ntt_contig_fused_mul<PF, PI, LOGN, NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (dev >= 0 && dev < 64) attr_done[dev] = true;
+    }
+    const unsigned tiles = ((1u << LOGN) >> 4) / kContigRows;
+    ntt_contig_fused_mul<PF, PI, LOGN, NOUT><<<F.items * F.r * tiles, kContigRows, smem, st>>>(mc, F);
+    return (int)cudaGetLastError();
+}
+template <class PF, class PI, int NOUT>
+static int launch_fused_logn(unsigned logn, const FusedArgs &F, const CUtensorMap &mc, cudaStream_t st)
+{
+    switch (logn) {
+    case 11: return launch_fused_one<PF, PI, 11, NOUT>(F, mc, st);
+    case 12: return launch_fused_one<PF, PI, 12, NOUT>(F, mc, st);
+    case 13: return launch_fused_one<PF, PI, 13, NOUT>(F, mc, st);
+    case 14: return launch_fused_one<PF, PI, 14, NOUT>(F, mc, st);
+    case 15: return launch_fused_one<PF, PI, 15, NOUT>(F, mc, st);
+    case 16: return launch_fused_one<PF, PI, 16, NOUT>(F, mc, st);
+    case 17: return launch_fused_one<PF, PI, 17, NOUT>(F, mc, st);
+    default: return NTTB200_EINVAL;
+    }
+}
+// h: data array + forward tables + group description (group = one item); lazy: both lazy policies are valid (q < 2^57)
+int launch_fused_mul(bool lazy, unsigned logn, const NttArgsHost &h, const u64 *twi, const u64 *twis, const u64 *key, const u64 *key_s,
+                     size_t key_item_stride, size_t key_half_stride, unsigned r, unsigned in_off, unsigned out_off0, unsigned out_off1,
+                     unsigned items, int nout, cudaStream_t st)
+{
+    if (logn < 11 || logn > 17 || !h.a || !key || !key_s || !items || !r || !h.group_polys) return NTTB200_EINVAL;
+    FusedArgs F;
+    NttArgs &A = F.A;
+    A.a = h.a; A.tw = h.tw; A.tws = h.tws; A.lc = h.lc;
+    A.qv = nullptr; A.muv = nullptr; A.qbitv = nullptr; A.q = 0; A.mu = 0; A.qbit = 0;
+    A.num = items * r; A.division = r; A.use_tma = (u32)h.use_tma;
+    A.group_polys = h.group_polys; A.group_stride = h.group_stride;
+    F.twi = twi; F.twis = twis; F.key = key; F.key_s = key_s;
+    F.key_item_stride = key_item_stride; F.key_half_stride = key_half_stride;
+    F.r = r; F.in_off = in_off; F.out_off[0] = out_off0; F.out_off[1] = out_off1; F.items = items;
+    CUtensorMap mc;
+    if (h.use_tma & 1) {
+        int rc = make_tmap_contig(&mc, A.a, logn, A.group_polys, A.group_stride, items);
+        if (rc) return rc;
+    } else {
+        memset(&mc, 0, sizeof mc);
+    }
+    if (lazy) return nout == 2 ? launch_fused_logn<ShoupLazyPolicy, ShoupLazyInvPolicy, 2>(logn, F, mc, st)
+                               : launch_fused_logn<ShoupLazyPolicy, ShoupLazyInvPolicy, 1>(logn, F, mc, st);
+    return nout == 2 ? launch_fused_logn<ShoupPolicy, ShoupPolicy, 2>(logn, F, mc, st) : launch_fused_logn<ShoupPolicy, ShoupPolicy, 1>(logn, F, mc, st);
+}
+
 }  // namespace nttb200
 
 using namespace nttb200;

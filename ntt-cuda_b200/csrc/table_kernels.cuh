@@ -42,11 +42,11 @@ NTT_KERNEL void k_build_tables(u64 *psi, u64 *psi_s, u64 *psiinv, u64 *psiinv_s,
 }
 
 // companions of caller-supplied tables (nttb200_ctx_create_from_tables): tab_s[i] = floor(tab[i] * 2^64 / q[limb])
-NTT_KERNEL void k_build_companions(const u64 *tab, u64 *tab_s, const u64 *q_arr, unsigned logn, unsigned limbs)
+NTT_KERNEL void k_build_companions(const u64 *tab, u64 *tab_s, const u64 *q_arr, unsigned logn, unsigned limbs, unsigned polys)
 {
-    const size_t total = (size_t)limbs << logn;
+    const size_t total = (size_t)polys << logn;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
-        tab_s[i] = companion_of(tab[i], q_arr[i >> logn]);
+        tab_s[i] = companion_of(tab[i], q_arr[(i >> logn) % limbs]);       // [..][limbs][n] arrays: limb = polynomial index mod limbs
 }
 
 }  // namespace nttb200

@@ -289,6 +289,11 @@ class Bfv:
     def reserve(self, batch):
         check(lib().nttb200_bfv_reserve(self._h, C.c_uint(batch)))
 
+    def load_keys(self, sk=None, pk=None, stream=None):
+        """Keep a key pair (and its Shoup companions) in the context; encrypt(pk=None) / decrypt(sk=None) then run the
+        fused NTT (.) key -> INTT path."""
+        check(lib().nttb200_bfv_load_keys(self._h, vp(ptr(sk)), vp(ptr(pk)), vp(_stream(stream))))
+
     def keygen(self, sk, pk, batch=1, nonce0=0, stream=None):
         """sk[batch][r][n], pk[batch][2][r][n] (bfv_keygen.cuh:95)"""
         check(lib().nttb200_bfv_keygen(self._h, vp(ptr(sk)), vp(ptr(pk)), C.c_uint(batch), u64(nonce0), vp(_stream(stream))))

@@ -49,6 +49,18 @@ def run(setname, batch, iters):
     dec_ms = timed(dec, iters)
     cp_ms = timed(lambda: c.copy_(c_keep), iters)
     ok = bool(torch.equal(out, m))
+    # loaded-key path: fused "NTT (.) key -> INTT" kernel
+    bfv.load_keys(sk[:rn], pk[:2 * rn])
+    enc_f = timed(lambda: bfv.encrypt(c, None, m, batch=batch), iters)
+    ok = ok and bool(torch.equal(c, c_keep))
+
+    def dec_fused():
+        c.copy_(c_keep)
+        bfv.decrypt(out, c, None, batch=batch)
+
+    out.zero_()
+    dec_f = timed(dec_fused, iters)
+    ok = ok and bool(torch.equal(out, m))
     # single-item latency (batch = 1)
     kg1 = timed(lambda: bfv.keygen(sk, pk, batch=1), 50)
     enc1 = timed(lambda: bfv.encrypt(c, pk, m, batch=1), 50)
@@ -76,12 +88,16 @@ def run(setname, batch, iters):
     gk = graph_us(lambda st: bfv.keygen(sk, pk, batch=1, stream=st))
     ge = graph_us(lambda st: bfv.encrypt(c, pk, m, batch=1, stream=st))
     gd = graph_us(lambda st: bfv.decrypt(out, c, sk, batch=1, stream=st))
+    gef = graph_us(lambda st: bfv.encrypt(c, None, m, batch=1, stream=st))
+    gdf = graph_us(lambda st: bfv.decrypt(out, c, None, batch=1, stream=st))
     res = {"set": setname, "n": n, "limbs": r, "batch": batch, "roundtrip_ok": ok,
            "keygen_per_s": batch / (kg * 1e-3), "encrypt_per_s": batch / (enc * 1e-3), "decrypt_per_s": batch / ((dec_ms - cp_ms) * 1e-3),
            "enc_plus_dec_per_s": batch / ((enc + dec_ms - cp_ms) * 1e-3),
+           "fused": {"encrypt_per_s": batch / (enc_f * 1e-3), "decrypt_per_s": batch / ((dec_f - cp_ms) * 1e-3),
+                     "enc_plus_dec_per_s": batch / ((enc_f + dec_f - cp_ms) * 1e-3), "encrypt_ms": enc_f, "decrypt_ms": dec_f - cp_ms},
            "keygen_ms": kg, "encrypt_ms": enc, "decrypt_ms": dec_ms - cp_ms,
            "single_item_us": {"keygen": kg1 * 1e3, "encrypt": enc1 * 1e3, "decrypt": dec1 * 1e3},
-           "single_item_graph_us": {"keygen": gk, "encrypt": ge, "decrypt": gd}}
+           "single_item_graph_us": {"keygen": gk, "encrypt": ge, "decrypt": gd, "encrypt_fused": gef, "decrypt_fused": gdf}}
     bfv.close()
     return res
 

@@ -83,7 +83,8 @@ class EmuRing:
 
 
 def bfv(op, er: EmuRing, barrett, batch=1, nonce0=0, sk=None, pk=None, c=None, m=None, per_item_keys=0):
-    """op 0 keygen -> (sk, pk, es); 1 encrypt -> (c, es); 2 decrypt -> (out, c)."""
+    """op 0 keygen -> (sk, pk, es); 1 encrypt -> (c, es); 2 decrypt -> (out, c); 3 / 4: encrypt / decrypt through the fused
+    NTT (.) key -> INTT kernel with a loaded key (5 / 6: same with the general-modulus policies)."""
     R = er.ring
     n, r = R.n, R.r
     rn = r * n
@@ -103,7 +104,7 @@ def bfv(op, er: EmuRing, barrett, batch=1, nonce0=0, sk=None, pk=None, c=None, m
     assert rc == 0
     if op == 0:
         return sk, pk, es[:batch * n].reshape(batch, n)
-    if op == 1:
+    if op in (1, 3, 5):
         return c, es.reshape(batch, 2, n)
     return out.reshape(batch, n), c
 

@@ -123,3 +123,30 @@ def test_batched_items_use_their_own_nonce(oracle, ring4k):
     c, _ = emu.bfv(1, er, 0, batch=B, nonce0=3, pk=pk, m=m, per_item_keys=1)
     out, _ = emu.bfv(2, er, 0, batch=B, sk=sk, c=c, per_item_keys=1)
     assert np.array_equal(out.reshape(-1), m)
+
+
+@pytest.mark.parametrize("ops", [(3, 4), (5, 6)], ids=["lazy", "general"])
+def test_fused_key_product_matches_oracle(oracle, ring4k, ops):
+    """Loaded-key path: strided pass, ONE fused kernel (contig NTT pass (.) key by Shoup companion, contig INTT pass), strided pass.
+    Same ciphertext / plaintext bits as the oracle (and so as the unfused kernels), batch of 2 sharing the key, plus the KAT."""
+    import os
+    R, er = ring4k
+    n, r = R.n, R.r
+    enc, dec = ops
+    sk, pk, _ = emu.bfv(0, er, 0)
+    B = 2
+    m = np.concatenate([oracle.fill_uniform(n, R.t, 0xF00 + k) for k in range(B)])
+    c, es = emu.bfv(enc, er, 0, batch=B, nonce0=11, pk=pk, m=m)
+    for k in range(B):
+        oracle.set_nonce(11 + k)
+        oc, _ = oracle.encryption_rns(R, pk, m[k * n:(k + 1) * n], e0_samples=np.ascontiguousarray(es[k, 0]),
+                                      e1_samples=np.ascontiguousarray(es[k, 1]))
+        assert np.array_equal(c[k * 2 * r * n:(k + 1) * 2 * r * n], oc)
+    oracle.set_nonce(0)
+    out, _ = emu.bfv(dec, er, 0, batch=B, sk=sk, c=c)
+    assert np.array_equal(out.reshape(-1), m)
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "decryption_kat.npz"))
+    skk = np.zeros(r * n, dtype=np.uint64)
+    skk[:8192] = g["sk_host"]
+    out, _ = emu.bfv(dec, er, 0, sk=skk, c=g["c_host"])
+    assert np.array_equal(out[0], np.arange(4096, dtype=np.uint64) % 10)

@@ -245,3 +245,61 @@ def test_pipelines_are_cuda_graph_capturable(oracle):
     torch.cuda.synchronize()
     assert torch.equal(out, m) and torch.equal(out, out_ref)
     bfv.close()
+
+
+@pytest.mark.parametrize("bits,logn,r", [(57, 11, 3), (38, 12, 3), (57, 13, 4), (57, 14, 3), (50, 15, 5), (57, 16, 2), (57, 17, 2),
+                                         (60, 11, 3), (60, 13, 2), (59, 16, 2)])
+def test_loaded_key_fused_path(oracle, bits, logn, r):
+    """nttb200_bfv_load_keys + NULL key pointers route the key products through the fused "contig NTT pass (.) key -> contig INTT pass"
+    kernel.  Ciphertexts and plaintexts must equal the unfused pipelines' bit for bit (those are pinned to the oracle above), for
+    every schedule 2^11..2^17 and for both arithmetic families (q < 2^57 lazy, q < 2^62 general)."""
+    import torch
+    import nttb200
+    from tests.gpu_util import to_dev, to_host
+    n = 1 << logn
+    qs, roots = params.find_ntt_primes(bits, n, r)
+    rn = r * n
+    B = 3
+    bfv = nttb200.Bfv(n, qs, roots)
+    sk = torch.zeros(rn, dtype=torch.int64, device="cuda")
+    pk = torch.zeros(2 * rn, dtype=torch.int64, device="cuda")
+    bfv.keygen(sk, pk, nonce0=5)
+    bfv.load_keys(sk, pk)
+    m = to_dev(np.concatenate([oracle.fill_uniform(n, params.T, 900 + k) for k in range(B)]))
+    c_plain = torch.zeros(B * 2 * rn, dtype=torch.int64, device="cuda")
+    c_fused = torch.zeros(B * 2 * rn, dtype=torch.int64, device="cuda")
+    bfv.encrypt(c_plain, pk, m, batch=B, nonce0=77)
+    bfv.encrypt(c_fused, None, m, batch=B, nonce0=77)
+    assert torch.equal(c_plain, c_fused)
+    out_plain = torch.zeros(B * n, dtype=torch.int64, device="cuda")
+    out_fused = torch.zeros(B * n, dtype=torch.int64, device="cuda")
+    bfv.decrypt(out_plain, c_plain, sk, batch=B)
+    bfv.decrypt(out_fused, c_fused, None, batch=B)
+    assert torch.equal(out_fused, m) and torch.equal(out_plain, m)
+    assert torch.equal(c_plain, c_fused)          # decryption leaves the same c1 scratch behind in both paths
+    if logn <= 13:                                # and against the oracle directly where it is quick
+        R = oracle.Ring(n, qs, roots)
+        fresh = torch.zeros(2 * rn, dtype=torch.int64, device="cuda")
+        bfv.encrypt(fresh, None, m, batch=1, nonce0=77)
+        oplain, _ = oracle.decryption_rns(R, to_host(fresh), to_host(sk))
+        assert np.array_equal(oplain, to_host(m)[:n])
+    bfv.close()
+
+
+def test_loaded_key_kat(oracle):
+    """The reference's decryption golden vector through the fused path."""
+    import torch
+    import nttb200
+    from tests.gpu_util import to_dev, to_host
+    g = np.load(GOLD)
+    n, qs, roots = params.RNS_SETS["4k_3q"]
+    bfv = nttb200.Bfv(n, qs, roots)
+    sk = np.zeros(3 * n, dtype=np.uint64)
+    sk[:8192] = g["sk_host"]
+    bfv.load_keys(to_dev(sk), None)
+    out = torch.zeros(n, dtype=torch.int64, device="cuda")
+    bfv.decrypt(out, to_dev(g["c_host"]), None)
+    assert np.array_equal(to_host(out), np.arange(4096, dtype=np.uint64) % 10)
+    with pytest.raises(Exception):
+        bfv.encrypt(to_dev(g["c_host"]), None, out)     # no public key loaded: refused, not silently computed
+    bfv.close()
