@@ -209,6 +209,53 @@ struct ShoupLazyInvPolicy : ShoupPolicy {
     }
 };
 
+// Same two policies on the chain formulation of the product (shoup_mul_c: 9 IMAD-class + 3 ALU instead of 9 + 5).
+struct ShoupLazy2Policy : ShoupLazyPolicy {
+    __device__ __forceinline__ void ct(u64 &X, u64 &Y, const Tw &t) const
+    {
+        u64 T = shoup_mul_c(Y, t.w, t.ws, nq);
+        u64 x = X;
+        X = x + T;
+        Y = x - T + fourq;
+    }
+};
+struct ShoupLazyInv2Policy : ShoupLazyInvPolicy {
+    __device__ __forceinline__ u64 mul_key(u64 x, u64 k, u64 ks) const { return shoup_mul_c(x, k, ks, nq); }
+    __device__ __forceinline__ void gs_lazy(u64 &U, u64 &V, const Tw &t, int e) const
+    {
+        const u64 s = U + V, d = U - V + (fourq << e);
+        U = s;
+        V = shoup_mul_c(d, t.w, t.ws, nq);
+    }
+};
+
+struct ShoupLazy3Policy : ShoupLazyPolicy {     // split-carry quotient + chain low product
+    __device__ __forceinline__ void ct(u64 &X, u64 &Y, const Tw &t) const
+    {
+        u64 T = shoup_mul_m(Y, t.w, t.ws, nq);
+        u64 x = X;
+        X = x + T;
+        Y = x - T + fourq;
+    }
+};
+// Half-scale quotient (63-bit companions in tws, values < 2^63): products < 5q, bias 5q per stage.
+struct ShoupLazyHPolicy : ShoupLazyPolicy {
+    u64 n2q, fiveq;
+    __device__ __forceinline__ void init(const NttArgs &A, u32 limb, u32 n)
+    {
+        ShoupLazyPolicy::init(A, limb, n);
+        n2q = nq + nq;
+        fiveq = fourq + q;
+    }
+    __device__ __forceinline__ void ct(u64 &X, u64 &Y, const Tw &t) const
+    {
+        u64 T = shoup_mul_h(Y, t.w, t.ws, n2q);
+        u64 x = X;
+        X = x + T;
+        Y = x - T + fiveq;
+    }
+};
+
 // The reference's own arithmetic, operation for operation (ntt_60bit.cuh:424-440 forward, :494-513 inverse):
 // canonical values, Barrett with the driver's (q, mu, qbit), one halving per inverse stage.  Needs nothing but
 // the reference's tables and constants, so the header drop-in can call it statelessly.
