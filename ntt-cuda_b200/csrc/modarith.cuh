@@ -126,7 +126,6 @@ __host__ __device__ __forceinline__ u64 shoup_mul_n(u64 y, u64 w, u64 ws, u64 ne
     return mullo_sum2(y, w, mulhi64(y, ws), negq);
 }
 
-// ---- second formulation of the lazy Shoup product: everything stays on IMAD accumulate chains ----------------------
 // low 64 bits of a*b + c*d: the four cross terms go to a separate 32-bit accumulator and the two lo*lo products to ONE
 // 64-bit mad.wide chain (an aligned register pair from start to end), joined by a single carry-less 32-bit add.
 // 2 IMAD.WIDE.U32 + 4 IMAD + 1 IADD3 (the split-accumulator version above costs ptxas 2 carry IADD3 more).
@@ -159,77 +158,7 @@ __host__ __device__ __forceinline__ u64 mullo_sum2_x(u64 a, u64 b, u64 c, u64 d)
 #endif
 }
 
-// Approximate high product as one accumulate chain: yh*sl, then yl*sh + hi32(previous), then yh*sh + hi32(previous).
-// Result in {exact-2 .. exact} (it keeps the carry between the two cross products that mulhi64_approx drops, never more).
-// 3 IMAD.WIDE.U32 + 2 register moves for the zero-extended hi words.
-__host__ __device__ __forceinline__ u64 mulhi64_approx_c(u64 y, u64 s)
-{
-#if defined(__CUDA_ARCH__)
-    u64 r;
-    asm("{\n\t"
-        ".reg .u32 yl, yh, sl, sh, t, dm;\n\t"
-        ".reg .u64 acc;\n\t"
-        "mov.b64 {yl, yh}, %1;\n\t"
-        "mov.b64 {sl, sh}, %2;\n\t"
-        "mul.wide.u32 acc, yh, sl;\n\t"
-        "mov.b64 {dm, t}, acc;\n\t"
-        "cvt.u64.u32 acc, t;\n\t"
-        "mad.wide.u32 acc, yl, sh, acc;\n\t"
-        "mov.b64 {dm, t}, acc;\n\t"
-        "cvt.u64.u32 acc, t;\n\t"
-        "mad.wide.u32 acc, yh, sh, acc;\n\t"
-        "mov.b64 %0, acc;\n\t"
-        "}"
-        : "=l"(r)
-        : "l"(y), "l"(s));
-    return r;
-#else
-    const u64 yl = (u32)y, yh = y >> 32, sl = (u32)s, sh = s >> 32;
-    return yh * sh + ((yl * sh + ((yh * sl) >> 32)) >> 32);
-#endif
-}
-
-// Shoup multiplication, chain formulation: result in [0, 4q) for any 64-bit y.
-__host__ __device__ __forceinline__ u64 shoup_mul_c(u64 y, u64 w, u64 ws, u64 negq)
-{
-    return mullo_sum2_x(y, w, mulhi64_approx_c(y, ws), negq);
-}
-
-// Half-scale quotient for Y < 2^63 and a 63-bit companion s = floor(w * 2^63 / q): yh*sl + yl*sh cannot overflow 64 bits,
-// so the two cross products share ONE mad.wide chain and only its high word is added to yh*sh.  Result in
-// {floor(y*s/2^64) - 1, floor(y*s/2^64)}, i.e. y*w/(2q) - 2.5 < result <= y*w/(2q).
-__host__ __device__ __forceinline__ u64 mulhi64_approx_h(u64 y, u64 s)
-{
-#if defined(__CUDA_ARCH__)
-    u64 r;
-    asm("{\n\t"
-        ".reg .u32 yl, yh, sl, sh, t, dm, rl, rh;\n\t"
-        ".reg .u64 acc, p1;\n\t"
-        "mov.b64 {yl, yh}, %1;\n\t"
-        "mov.b64 {sl, sh}, %2;\n\t"
-        "mul.wide.u32 acc, yh, sl;\n\t"
-        "mad.wide.u32 acc, yl, sh, acc;\n\t"
-        "mul.wide.u32 p1, yh, sh;\n\t"
-        "mov.b64 {dm, t}, acc;\n\t"
-        "mov.b64 {rl, rh}, p1;\n\t"
-        "add.cc.u32 rl, rl, t;\n\t"
-        "addc.u32 rh, rh, 0;\n\t"
-        "mov.b64 %0, {rl, rh};\n\t"
-        "}"
-        : "=l"(r)
-        : "l"(y), "l"(s));
-    return r;
-#else
-    const u64 yl = (u32)y, yh = y >> 32, sl = (u32)s, sh = s >> 32;
-    return yh * sh + ((yl * sh + yh * sl) >> 32);
-#endif
-}
-// y < 2^63, ws63 = floor(w * 2^63 / q), neg2q = 2^64 - 2q: result = y*w - 2q*quotient in [0, 5q).
-__host__ __device__ __forceinline__ u64 shoup_mul_h(u64 y, u64 w, u64 ws63, u64 neg2q)
-{
-    return mullo_sum2_x(y, w, mulhi64_approx_h(y, ws63), neg2q);
-}
-// mixed: split-carry quotient (3 ALU) + chain low product (1 ALU)
+// Shoup multiplication with the approximate quotient and the chain low product: result in [0, 4q) for any 64-bit y.
 __host__ __device__ __forceinline__ u64 shoup_mul_m(u64 y, u64 w, u64 ws, u64 negq)
 {
     return mullo_sum2_x(y, w, mulhi64_approx(y, ws), negq);

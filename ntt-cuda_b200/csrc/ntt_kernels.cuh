@@ -48,6 +48,7 @@ struct NttArgs {
     u32 group_polys;      // polynomial p starts at a + (p / group_polys) * group_stride + (p % group_polys) * n;
     size_t group_stride;  //   group_polys = num for one contiguous [num][n] array (the reference's layout)
     u32 use_tma;          // bit 0: TMA tile movement; bits 1/2 (profiling only): skip the butterflies / skip the tile traffic
+    u32 pf_dist;          // > 0: CTA b prefetches the tile of CTA b + pf_dist into L2 (about one wave of resident CTAs ahead)
 };
 
 // ---- stage split per ring degree: K1 = S1+S2+S3 strided stages (rounds of 3 or 4), K2 contiguous stages -------
@@ -62,7 +63,11 @@ NTTB200_SCHED(11, 4, 0, 0, 7, 8)
 NTTB200_SCHED(12, 4, 0, 0, 8, 8)
 NTTB200_SCHED(13, 3, 3, 0, 7, 2)
 NTTB200_SCHED(14, 4, 3, 0, 7, 1)
+#ifdef NTT_SCHED15_438
+NTTB200_SCHED(15, 4, 3, 0, 8, 1)
+#else
 NTTB200_SCHED(15, 4, 4, 0, 7, 1)
+#endif
 NTTB200_SCHED(16, 4, 4, 0, 8, 1)
 NTTB200_SCHED(17, 3, 3, 3, 8, 1)
 #undef NTTB200_SCHED
@@ -106,8 +111,14 @@ struct ShoupPolicy {
         q = l->q; twoq = l->twoq; nq = l->negq;
         w = A.tw + (size_t)limb * n; ws = A.tws + (size_t)limb * n;
     }
+#ifdef NTT_DBG_REGTW   /* profiling only (wrong results): twiddles from registers, no table loads */
+    __device__ __forceinline__ Tw load(u32 i) const { Tw t; t.w = q - 12345u; t.ws = nq; (void)i; return t; }
+    __device__ __forceinline__ void load2(u32 i, Tw &t0, Tw &t1) const { t0 = load(i); t1.w = twoq - q - 777u; t1.ws = nq + 99u; }
+    __device__ __forceinline__ void load2_ldg(u32 i, Tw &t0, Tw &t1) const
+#else
     __device__ __forceinline__ Tw load(u32 i) const { Tw t; t.w = __ldg(w + i); t.ws = __ldg(ws + i); return t; }
     __device__ __forceinline__ void load2(u32 i, Tw &t0, Tw &t1) const
+#endif
     {
         ulonglong2 a = __ldg(reinterpret_cast<const ulonglong2 *>(w + i));
         ulonglong2 b = __ldg(reinterpret_cast<const ulonglong2 *>(ws + i));
@@ -157,13 +168,20 @@ struct ShoupLazyPolicy : ShoupPolicy {
     }
     __device__ __forceinline__ void ct(u64 &X, u64 &Y, const Tw &t) const
     {
-        u64 T = shoup_mul_a(Y, t.w, t.ws, nq);
+        u64 T = shoup_mul_m(Y, t.w, t.ws, nq);
         u64 x = X;
         X = x + T;
         Y = x - T + fourq;
     }
+    // x < 69 q  ->  [0, q).  For q > 2^32 the quotient estimate needs ONE 32x32 multiplication: floor(x / q) is at most 2
+    // above hi32((x >> 32) * ratio) because ratio = floor(2^64 / q) < 2^32 (dropped: x_lo * ratio / 2^64 < 1, x / 2^64 < 1, the floor).
     __device__ __forceinline__ u64 fwd_final(u64 x) const
     {
+        if ((ratio >> 32) == 0) {
+            const u64 qe = ((u64)(u32)(x >> 32) * (u64)(u32)ratio) >> 32;          // 32-bit quotient estimate
+            u64 r = x - ((u64)(u32)qe * (u64)(u32)q + (((u64)(u32)qe * (q >> 32)) << 32));   // x - qe * q  in [0, 3q)
+            return csub(csub(r, twoq), q);
+        }
         u64 r = x + mulhi64(x, ratio) * nq;     // x - floor(x * ratio / 2^64) * q  in [0, 2q)
         return csub(r, q);
     }
@@ -184,13 +202,13 @@ struct ShoupLazyInvPolicy : ShoupPolicy {
         ShoupPolicy::init(A, limb, n);
         fourq = twoq + twoq;
     }
-    __device__ __forceinline__ u64 mul_key(u64 x, u64 k, u64 ks) const { return shoup_mul_a(x, k, ks, nq); }   // < B = 4q
+    __device__ __forceinline__ u64 mul_key(u64 x, u64 k, u64 ks) const { return shoup_mul_m(x, k, ks, nq); }   // < B = 4q
     // e: log2 of the common bound multiplier of U and V (compile-time after unrolling)
     __device__ __forceinline__ void gs_lazy(u64 &U, u64 &V, const Tw &t, int e) const
     {
         const u64 s = U + V, d = U - V + (fourq << e);
         U = s;
-        V = shoup_mul_a(d, t.w, t.ws, nq);
+        V = shoup_mul_m(d, t.w, t.ws, nq);
     }
     // x < 2^e * B  ->  x < B
     __device__ __forceinline__ u64 reduce_to_B(u64 x, int e) const
@@ -206,53 +224,6 @@ struct ShoupLazyInvPolicy : ShoupPolicy {
         const u64 s = U + V, d = U - V + (fourq << e);
         U = csub(shoup_mul_n(s, l->ninv, l->ninv_s, nq), q);
         V = csub(shoup_mul_n(d, l->w1ninv, l->w1ninv_s, nq), q);
-    }
-};
-
-// Same two policies on the chain formulation of the product (shoup_mul_c: 9 IMAD-class + 3 ALU instead of 9 + 5).
-struct ShoupLazy2Policy : ShoupLazyPolicy {
-    __device__ __forceinline__ void ct(u64 &X, u64 &Y, const Tw &t) const
-    {
-        u64 T = shoup_mul_c(Y, t.w, t.ws, nq);
-        u64 x = X;
-        X = x + T;
-        Y = x - T + fourq;
-    }
-};
-struct ShoupLazyInv2Policy : ShoupLazyInvPolicy {
-    __device__ __forceinline__ u64 mul_key(u64 x, u64 k, u64 ks) const { return shoup_mul_c(x, k, ks, nq); }
-    __device__ __forceinline__ void gs_lazy(u64 &U, u64 &V, const Tw &t, int e) const
-    {
-        const u64 s = U + V, d = U - V + (fourq << e);
-        U = s;
-        V = shoup_mul_c(d, t.w, t.ws, nq);
-    }
-};
-
-struct ShoupLazy3Policy : ShoupLazyPolicy {     // split-carry quotient + chain low product
-    __device__ __forceinline__ void ct(u64 &X, u64 &Y, const Tw &t) const
-    {
-        u64 T = shoup_mul_m(Y, t.w, t.ws, nq);
-        u64 x = X;
-        X = x + T;
-        Y = x - T + fourq;
-    }
-};
-// Half-scale quotient (63-bit companions in tws, values < 2^63): products < 5q, bias 5q per stage.
-struct ShoupLazyHPolicy : ShoupLazyPolicy {
-    u64 n2q, fiveq;
-    __device__ __forceinline__ void init(const NttArgs &A, u32 limb, u32 n)
-    {
-        ShoupLazyPolicy::init(A, limb, n);
-        n2q = nq + nq;
-        fiveq = fourq + q;
-    }
-    __device__ __forceinline__ void ct(u64 &X, u64 &Y, const Tw &t) const
-    {
-        u64 T = shoup_mul_h(Y, t.w, t.ws, n2q);
-        u64 x = X;
-        X = x + T;
-        Y = x - T + fiveq;
     }
 };
 
@@ -500,6 +471,13 @@ ntt_strided_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
             for (int k = 0; k < NT; k++)
                 for (int rc = 0; rc < R / RB; rc++)
                     tma_load_4d(tiles + ((size_t)k * R + rc * RB) * 16, &tmap, bar, (int)col0 + k * 16, rc * RB, (int)idx, (int)grp);
+            const u32 fb = blockIdx.x + A.pf_dist;           // the CTA that will run here about one wave later
+            if (A.pf_dist != 0 && fb < gridDim.x) {
+                const u32 fp = fb / TILES, fcol = (fb % TILES) * (NT * 16);
+                const u32 fgrp = fp / A.group_polys, fidx = fp - fgrp * A.group_polys;
+                for (int k = 0; k < NT; k++)
+                    for (int rc = 0; rc < R / RB; rc++) tma_prefetch_4d(&tmap, (int)fcol + k * 16, rc * RB, (int)fidx, (int)fgrp);
+            }
         }
         mbar_wait(bar, 0);
 #endif
@@ -513,7 +491,11 @@ ntt_strided_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
     if (dbg_nocompute) {
     } else if (!INV) {
         strided_round<P, K1, 0, SC::S1, false>(tile, u, pol);
+#ifdef NTT_DBG_NOBAR   /* profiling only (wrong results): no CTA barrier between the rounds */
+        if constexpr (SC::S2 != 0) { __syncwarp(); strided_round<P, K1, SC::S1, SC::S2, false>(tile, u, pol); }
+#else
         if constexpr (SC::S2 != 0) { __syncthreads(); strided_round<P, K1, SC::S1, SC::S2, false>(tile, u, pol); }
+#endif
         if constexpr (SC::S3 != 0) { __syncthreads(); strided_round<P, K1, SC::S1 + SC::S2, SC::S3, false>(tile, u, pol); }
     } else {
         if constexpr (SC::S3 != 0) { strided_round<P, K1, SC::S1 + SC::S2, SC::S3, true>(tile, u, pol); __syncthreads(); }
@@ -580,7 +562,16 @@ ntt_contig_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
 #else
         if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
         __syncthreads();
-        if (tid == 0) { mbar_expect_tx(bar, (u32)(RT * 128)); tma_load_3d(tile, &tmap, bar, 0, grow, (int)grp); }
+        if (tid == 0) {
+            mbar_expect_tx(bar, (u32)(RT * 128));
+            tma_load_3d(tile, &tmap, bar, 0, grow, (int)grp);
+            const u32 fb = blockIdx.x + A.pf_dist;
+            if (A.pf_dist != 0 && fb < gridDim.x) {
+                const u32 fp = fb / TILES, frip = (fb % TILES) * RT;
+                const u32 fgrp = fp / A.group_polys, fidx = fp - fgrp * A.group_polys;
+                tma_prefetch_3d(&tmap, 0, (int)(fidx * (n >> 4) + frip), (int)fgrp);
+            }
+        }
         mbar_wait(bar, 0);
 #endif
     } else {

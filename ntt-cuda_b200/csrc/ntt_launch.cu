@@ -27,6 +27,17 @@ static EncodeTiledFn get_encode()
     return fn;
 }
 
+// L2 prefetch distance in CTAs for a kernel with `resident` CTAs per SM (NTTB200_PF_WAVES: 0 = off; default 1 wave)
+static unsigned pf_dist_for(int dev, int resident)
+{
+    static int sms[64] = {0};
+    static float waves = -1.f;
+    if (waves < 0.f) { const char *e = getenv("NTTB200_PF_WAVES"); waves = e ? (float)atof(e) : 1.0f; }
+    if (dev < 0 || dev >= 64) return 0;
+    if (!sms[dev]) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    return (unsigned)(waves * (float)(sms[dev] * resident));
+}
+
 int get_tma_default()
 {
     const char *e = getenv("NTTB200_NO_TMA");
@@ -87,12 +98,20 @@ static int launch_one(const NttArgs &A, int which, unsigned cnt, const CUtensorM
     // which: -1 = whole transform, 0 / 1 = only the first / second kernel in execution order (profiling hook)
     const bool do_strided = which < 0 || (which == 0) == !INV;
     const bool do_contig = which < 0 || (which == 1) == !INV;
+    static int occ_s[64] = {0}, occ_c[64] = {0};      // resident CTAs per SM of the two kernels (prefetch distance = one wave)
+    if (dev >= 0 && dev < 64 && !occ_s[dev]) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s[dev], ntt_strided_pass<P, LOGN, INV>, R * SC::NT, smem_s);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c[dev], ntt_contig_pass<P, LOGN, INV>, kContigRows, smem_c);
+    }
+    NttArgs As = A, Ac = A;
+    As.pf_dist = (dev >= 0 && dev < 64) ? pf_dist_for(dev, occ_s[dev]) : 0;
+    Ac.pf_dist = (dev >= 0 && dev < 64) ? pf_dist_for(dev, occ_c[dev]) : 0;
     if (!INV) {
-        if (do_strided) ntt_strided_pass<P, LOGN, INV><<<gs, R * SC::NT, smem_s, st>>>(ms, A);
-        if (do_contig) ntt_contig_pass<P, LOGN, INV><<<gc, kContigRows, smem_c, st>>>(mc, A);
+        if (do_strided) ntt_strided_pass<P, LOGN, INV><<<gs, R * SC::NT, smem_s, st>>>(ms, As);
+        if (do_contig) ntt_contig_pass<P, LOGN, INV><<<gc, kContigRows, smem_c, st>>>(mc, Ac);
     } else {
-        if (do_contig) ntt_contig_pass<P, LOGN, INV><<<gc, kContigRows, smem_c, st>>>(mc, A);
-        if (do_strided) ntt_strided_pass<P, LOGN, INV><<<gs, R * SC::NT, smem_s, st>>>(ms, A);
+        if (do_contig) ntt_contig_pass<P, LOGN, INV><<<gc, kContigRows, smem_c, st>>>(mc, Ac);
+        if (do_strided) ntt_strided_pass<P, LOGN, INV><<<gs, R * SC::NT, smem_s, st>>>(ms, As);
     }
     return (int)cudaGetLastError();
 }
@@ -134,7 +153,7 @@ int launch_ntt_pass(bool inverse, int policy, unsigned logn, const NttArgsHost &
     A.tw = h.tw; A.tws = h.tws; A.lc = h.lc;
     A.qv = h.qv; A.muv = h.muv; A.qbitv = h.qbitv;
     A.q = h.q; A.mu = h.mu; A.qbit = h.qbit;
-    A.num = h.num; A.division = h.division; A.use_tma = (u32)h.use_tma;
+    A.num = h.num; A.division = h.division; A.use_tma = (u32)h.use_tma; A.pf_dist = 0;
     A.group_polys = h.group_polys ? h.group_polys : h.num;
     A.group_stride = h.group_polys ? h.group_stride : ((size_t)h.num << logn);
     const unsigned groups = (h.num + A.group_polys - 1) / A.group_polys;
@@ -197,7 +216,7 @@ int launch_fused_mul(bool lazy, unsigned logn, const NttArgsHost &h, const u64 *
     NttArgs &A = F.A;
     A.a = h.a; A.tw = h.tw; A.tws = h.tws; A.lc = h.lc;
     A.qv = nullptr; A.muv = nullptr; A.qbitv = nullptr; A.q = 0; A.mu = 0; A.qbit = 0;
-    A.num = items * r; A.division = r; A.use_tma = (u32)h.use_tma;
+    A.num = items * r; A.division = r; A.use_tma = (u32)h.use_tma; A.pf_dist = 0;
     A.group_polys = h.group_polys; A.group_stride = h.group_stride;
     F.twi = twi; F.twis = twis; F.key = key; F.key_s = key_s;
     F.key_item_stride = key_item_stride; F.key_half_stride = key_half_stride;

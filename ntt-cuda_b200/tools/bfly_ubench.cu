@@ -8,7 +8,7 @@
 #include <cstring>
 #include <vector>
 #include <cuda_runtime.h>
-#include "../csrc/ntt_kernels.cuh"
+#include "bfly_variants.cuh"
 using namespace nttb200;
 
 // twiddles from registers instead of the L1-resident table: isolates the arithmetic from the LDG stream
@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(256, MINB) kern(u64 *data, NttArgs A, int iter
     long long t0 = clock64();
     u32 twbase = 1 + (threadIdx.x & 15);
     for (int it = 0; it < iters; it++) {
-        if (!INV) ct_stages<4, 1>(v, twbase, pol);
+        if constexpr (!INV) ct_stages<4, 1>(v, twbase, pol);
         else gs_stages<4, 1, false>(v, twbase, pol);
         twbase = (twbase * 5 + 3) & 127;
         if (twbase == 0) twbase = 1;
@@ -88,7 +88,7 @@ int main(int argc, char **argv)
     }
     LimbConst lc = {};
     lc.q = q; lc.twoq = 2 * q; lc.negq = 0 - q; lc.ratio = (u64)((((unsigned __int128)1) << 64) / q);
-    lc.ninv = tw[5]; lc.ninv_s = tws[5]; lc.w1ninv = tw[6]; lc.w1ninv_s = tws[6]; lc.qbit = 55;
+    lc.ninv = tw[5]; lc.ninv_s = tws[5]; lc.w1ninv = tw[6]; lc.w1ninv_s = tws[6]; lc.qbit = 55; lc.pad = 0u - 0x43300000u * (u32)lc.negq;
     u64 *dtw, *dtws, *data; LimbConst *dlc;
     size_t elems = (size_t)s * 8 * 256 * 16;
     cudaMalloc(&dtw, n * 8); cudaMalloc(&dtws, n * 8); cudaMalloc(&dlc, sizeof(lc)); cudaMalloc(&data, elems * 8);
@@ -107,14 +107,12 @@ int main(int argc, char **argv)
     run<P, INV, 4>(nm "_4cta", s, A, data, false);
     RUN3(ShoupPolicy, false, "fwd_shoup_exact")
     RUN3(ShoupLazyPolicy, false, "fwd_lazy_approx")
-#ifdef HAVE_V2
     RUN3(ShoupLazy2Policy, false, "fwd_lazy_v2")
-    RUN3(ShoupLazy3Policy, false, "fwd_lazy_v3")
     RUN3(ShoupLazyHPolicy, false, "fwd_lazy_h")
+    RUN3(ShoupLazyFPolicy, false, "fwd_lazy_f")
+    RUN3(RegTw<ShoupLazyFPolicy>, false, "fwd_lazy_f_regtw")
     RUN3(ShoupLazyInv2Policy, true, "inv_lazy_v2")
-#endif
     RUN3(RegTw<ShoupLazyPolicy>, false, "fwd_lazy_approx_regtw")
-    RUN3(RegTw<ShoupLazy3Policy>, false, "fwd_lazy_v3_regtw")
     RUN3(RegTw<ShoupLazyInvPolicy>, true, "inv_lazy_approx_regtw")
     RUN3(ShoupLazyInvPolicy, true, "inv_lazy_approx")
     run<ShoupPolicy, true, 3>("inv_shoup_exact_3cta", s, A, data, true);

@@ -106,6 +106,11 @@ __global__ void __launch_bounds__(256) k(u32 *out, const u32 *in, long long *cyc
                 asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w[i]) : "r"((u32)(w[i] >> 32)), "r"(cparam));
             } else if (OP == 27) {  // IMAD (lo) with a constant-bank multiplicand
                 asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(x[i]) : "r"(x[j]), "r"(cparam));
+            } else if (OP == 28) {  // I2F.F64.U32 (u32 -> double)
+                d[i] = __uint2double_rn(x[i]); x[i] = (u32)__double2loint(d[i]) + (u32)__double2hiint(d[i]);
+            } else if (OP == 29) {  // I2F.F64.U32 + IMAD.WIDE on independent registers
+                d[i] = __uint2double_rn(x[i]); x[i] = (u32)__double2loint(d[i]) + (u32)__double2hiint(d[i]);
+                asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w[i]) : "r"((u32)w[i]), "r"((u32)(w[i] >> 32)));
             } else if (OP == 17) {  // SHF.L.W (funnel shift): alu
                 asm volatile("shf.l.wrap.b32 %0, %0, %1, 7;" : "+r"(x[i]) : "r"(x[j]));
             }
@@ -178,6 +183,8 @@ int main(int argc, char **argv)
     run<24>("imadwide+2iadd3", s, 3, in, false);
     run<22>("dfma_regs", s, 1, in, false);
     run<25>("dfma+imadwide", s, 2, in, false);
+    run<28>("i2f_f64_u32(+iadd3)", s, 2, in, false);
+    run<29>("i2f_f64_u32(+iadd3)+imadwide", s, 3, in, false);
     run<9>("ffma", s, 1, in, false);
     run<10>("ffma+iadd3", s, 2, in, false);
     run<11>("ffma+imad", s, 2, in, false);
