@@ -55,6 +55,7 @@ struct nttb200_bfv {
     // grow-only scratch: keystream and gaussian draws
     unsigned char *ks = nullptr; size_t ks_bytes = 0;
     int *es = nullptr; size_t es_count = 0;
+    bool enc_lazy = false, dec_fast = false;
 };
 
 static u64 h_modpow(u64 a, u64 e, u64 m)
@@ -76,6 +77,7 @@ struct Pipe {                 // everything one pipeline run needs, independent 
     const LimbConst *lc;
     int use_tma;
     cudaStream_t st;
+    bool enc_lazy = false, dec_fast = false;   // host-verified: every limb qualifies for the lazy / Shoup-only epilogues
 };
 
 static NttArgsHost pipe_args(const Pipe &P, bool inverse, u64 *a, unsigned num, unsigned division, unsigned group_polys, size_t group_stride)
@@ -121,6 +123,20 @@ static int run_keygen(const Pipe &P, unsigned char *in, size_t in_stride, int *e
     return 0;
 }
 
+// mod-switch + Delta*m on the limbs below the dropped one (limb-chunked rows), then the dropped limb's padding value
+static int run_encrypt_epilogue(const Pipe &P, u64 *c, const int *es, const u64 *m, size_t m_stride, u64 t, unsigned batch)
+{
+    const unsigned n = P.n, r = P.r;
+    if (r > 1) {
+        const unsigned rows = 2 * ((r - 1 + kEncChunk - 1) / kEncChunk);
+        if (P.enc_lazy) k_encrypt_epilogue<true><<<pair_grid(n, rows, batch), pair_block(n, rows, batch), 0, P.st>>>(c, es, m, m_stride, n, r, batch, t, P.qi_div_t, P.L);
+        else k_encrypt_epilogue<false><<<pair_grid(n, rows, batch), pair_block(n, rows, batch), 0, P.st>>>(c, es, m, m_stride, n, r, batch, t, P.qi_div_t, P.L);
+    }
+    k_encrypt_last_limb<<<pair_grid(n, 2, batch), pair_block(n, 2, batch), 0, P.st>>>(c, es, n, r, batch, P.L);
+    KCHECK();
+    return 0;
+}
+
 static int run_encrypt(const Pipe &P, unsigned char *in, size_t in_stride, int *es, u64 *c, const u64 *pk, size_t pk_stride, const u64 *m,
                        size_t m_stride, u64 t, unsigned batch, u64 nonce0)
 {
@@ -134,7 +150,7 @@ static int run_encrypt(const Pipe &P, unsigned char *in, size_t in_stride, int *
     k_encrypt_mul<<<pair_grid(n, r, batch), pair_block(n, r, batch), 0, P.st>>>(c, pk, pk_stride, n, r, batch, P.L);              // :270
     KCHECK();
     NTTB200_TRY(pipe_ntt(P, true, c, batch * 2 * r, r, 0, 0));                             // :271
-    k_encrypt_epilogue<<<pair_grid(n, 2, batch), pair_block(n, 2, batch), 0, P.st>>>(c, es, m, m_stride, n, r, batch, t, P.qi_div_t, P.L);   // :280-289
+    NTTB200_TRY(run_encrypt_epilogue(P, c, es, m, m_stride, t, batch));                    // :280-289
     KCHECK();
     return 0;
 }
@@ -154,7 +170,7 @@ static int run_encrypt_fused(const Pipe &P, bool lazy, unsigned char *in, size_t
     NTTB200_TRY(launch_fused_mul(lazy, P.logn, pipe_args(P, false, c, batch * 2 * r, r, 2 * r, 2 * rn), P.psiinv, P.psiinv_s, pk, pk_s, 0, rn, r,
                                  0, 0, r, batch, 2, P.st));
     NTTB200_TRY(pipe_ntt_pass(P, true, 1, c, batch * 2 * r, r, 0, 0));                     // strided inverse pass on both halves
-    k_encrypt_epilogue<<<pair_grid(n, 2, batch), pair_block(n, 2, batch), 0, P.st>>>(c, es, m, m_stride, n, r, batch, t, P.qi_div_t, P.L);
+    NTTB200_TRY(run_encrypt_epilogue(P, c, es, m, m_stride, t, batch));
     KCHECK();
     return 0;
 }
@@ -168,7 +184,8 @@ static int run_decrypt_fused(const Pipe &P, bool lazy, u64 *c, const u64 *sk, co
     NTTB200_TRY(launch_fused_mul(lazy, P.logn, pipe_args(P, false, c, batch * 2 * (rp + 1), rp, 2 * (rp + 1), item), P.psiinv, P.psiinv_s, sk, sk_s,
                                  0, 0, rp, rp + 1, rp + 1, rp + 1, batch, 1, P.st));
     NTTB200_TRY(pipe_ntt_pass(P, true, 1, c + c1_off, batch * rp, rp, rp, item));
-    k_decrypt_epilogue<<<pair_grid(n, batch, 1), pair_block(n, batch, 1), 0, P.st>>>(c, item, c1_off, out, out_stride, n, batch, D, P.L);
+    if (P.dec_fast) k_decrypt_epilogue<true><<<pair_grid(n, batch, 1), pair_block(n, batch, 1), 0, P.st>>>(c, item, c1_off, out, out_stride, n, batch, D, P.L);
+    else k_decrypt_epilogue<false><<<pair_grid(n, batch, 1), pair_block(n, batch, 1), 0, P.st>>>(c, item, c1_off, out, out_stride, n, batch, D, P.L);   // :103-137
     KCHECK();
     return 0;
 }
@@ -182,7 +199,8 @@ static int run_decrypt(const Pipe &P, u64 *c, const u64 *sk, size_t sk_stride, u
     k_decrypt_mul<<<pair_grid(n, rp, batch), pair_block(n, rp, batch), 0, P.st>>>(c, item, c1_off, sk, sk_stride, n, rp, batch, P.L);   // :100
     KCHECK();
     NTTB200_TRY(pipe_ntt(P, true, c + c1_off, batch * rp, rp, rp, item));                  // :101
-    k_decrypt_epilogue<<<pair_grid(n, batch, 1), pair_block(n, batch, 1), 0, P.st>>>(c, item, c1_off, out, out_stride, n, batch, D, P.L);   // :103-137
+    if (P.dec_fast) k_decrypt_epilogue<true><<<pair_grid(n, batch, 1), pair_block(n, batch, 1), 0, P.st>>>(c, item, c1_off, out, out_stride, n, batch, D, P.L);
+    else k_decrypt_epilogue<false><<<pair_grid(n, batch, 1), pair_block(n, batch, 1), 0, P.st>>>(c, item, c1_off, out, out_stride, n, batch, D, P.L);   // :103-137
     KCHECK();
     return 0;
 }
@@ -196,6 +214,7 @@ static Pipe pipe_from_bfv(const nttb200_bfv *b, cudaStream_t st)
     P.n = b->n; P.logn = c->logn; P.r = b->r;
     P.L = LimbArrays{c->q_dev, c->mu_dev, c->qbit_dev, b->inv_q_last_mod_q, b->inv_punctured_q, b->prod_t_gamma_mod_q};
     P.qi_div_t = b->qi_div_t;
+    P.enc_lazy = b->enc_lazy; P.dec_fast = b->dec_fast;
     P.policy_fwd = P.policy_inv = c->lazy_ok ? kPolicyShoupLazy : kPolicyShoup;
     P.psi = c->psi; P.psiinv = c->psiinv; P.psi_s = c->psi_s; P.psiinv_s = c->psiinv_s; P.lc = c->lc;
     P.use_tma = c->use_tma; P.st = st;
@@ -259,6 +278,13 @@ int nttb200_bfv_create(nttb200_bfv **out, unsigned n, unsigned limbs, const nttb
         NTTB200_CHECK(cudaMemcpy(*d, h.data(), h.size() * 8, cudaMemcpyHostToDevice));
         return 0;
     };
+    // epilogue flavours (bfv_kernels.cuh): the same predicates the kernels evaluate per limb, checked here for ALL limbs
+    b->enc_lazy = true; b->dec_fast = barrett_is_exact(gamma, b->mu_gamma, b->gamma_bits);
+    for (unsigned i = 0; i < rp; i++) {
+        const bool exact = barrett_is_exact(q[i], ctx->mu[i], (int)ctx->qbit[i]);
+        b->enc_lazy = b->enc_lazy && exact && iql[i] < q[i] && q[r - 1] <= 2 * q[i] && q[i] < (1ull << 60);
+        b->dec_fast = b->dec_fast && exact && ptg[i] < q[i] && ipq[i] < q[i] && bcm[rp + i] < gamma;
+    }
     rc = up(&b->inv_q_last_mod_q, iql); if (!rc) rc = up(&b->qi_div_t, qdt); if (!rc) rc = up(&b->prod_t_gamma_mod_q, ptg);
     if (!rc) rc = up(&b->inv_punctured_q, ipq); if (!rc) rc = up(&b->bcm, bcm);
     if (rc) { nttb200_bfv_destroy(b); return rc; }

@@ -272,17 +272,36 @@ NTT_KERNEL void k_encrypt_mul(u64 *c, const u64 *pk, size_t pk_stride, unsigned 
     }
 }
 
-struct EncLimb { u64 q, mu, ratio, half_mod, inv_q_last, inv_q_last_s, qdt; int qbit, fast; };
-// poly_add_xq + divide_and_round_q_last_inplace_add_x2 + ..._loop_xq + weird_m_stuff (bfv_encryption.cuh:111-212)
-// in one pass.  grid (x, 2 halves, batch).  The dropped limb r-1 keeps the value the reference leaves there.
-NTT_KERNEL void k_encrypt_epilogue(u64 *c, const int *es, const u64 *m_poly, size_t m_stride, unsigned n, unsigned r, unsigned batch, u64 t,
-                                   const u64 *qi_div_t, LimbArrays L)
+struct EncLimb { u64 q, mu, ratio, half_mod, inv_q_last, inv_q_last_s, qdt, bias; int qbit, fast, last_lt_2q, lazy; };
+constexpr unsigned kEncChunk = 4;      // limbs per CTA row of k_encrypt_epilogue
+// last limb of one half: += e (`>` quirk, bfv_encryption.cuh:187), += floor(q_last / 2) mod q_last (:121-124)
+__host__ __device__ __forceinline__ u64 enc_last_limb(u64 v, int d, u64 last, u64 half_last)
+{
+    u64 x = v + signed_to_residue(d, last);
+    if (x > last) x -= last;
+    x += half_last;
+    if (x >= last) x -= last;
+    return x;
+}
+// poly_add_xq + divide_and_round_q_last_inplace_add_x2 + ..._loop_xq + weird_m_stuff (bfv_encryption.cuh:111-212) for the limbs
+// below the dropped one, in one pass.  grid (x, 2 halves * ceil((r-1) / kEncChunk) limb chunks, batch): every CTA row handles
+// kEncChunk limbs of one half, so (r-1)/4 times more 16-byte loads are in flight than with one thread walking all limbs (the
+// single-row version was latency-bound at 3 TB/s).  Every row recomputes the dropped limb's value from the RAW INTT output,
+// which is therefore left untouched here and finalised by k_encrypt_last_limb afterwards.
+// ALL_LAZY (decided on the host for context-owned parameter sets): every limb takes the lazy path, the literal reference
+// sequence is compiled out and the kernel fits four 256-thread CTAs per SM -- the pass is bound by loads in flight.
+template <bool ALL_LAZY>
+NTT_KERNEL void __launch_bounds__(256, ALL_LAZY ? 4 : 2)
+k_encrypt_epilogue(u64 *c, const int *es, const u64 *m_poly, size_t m_stride, unsigned n, unsigned r, unsigned batch, u64 t,
+                   const u64 *qi_div_t, LimbArrays L)
 {
     (void)batch;
-    NTT_SHARED EncLimb K[kMaxLimbs];
+    NTT_SHARED EncLimb K[kEncChunk];
     const u64 last = L.q[r - 1], half_last = last >> 1;
-    if (threadIdx.x + 1 < r) {
-        const unsigned l = threadIdx.x;
+    const unsigned chunks = (r - 1 + kEncChunk - 1) / kEncChunk;
+    const unsigned h = blockIdx.y / chunks, l0 = (blockIdx.y % chunks) * kEncChunk;
+    if (threadIdx.x < kEncChunk && l0 + threadIdx.x + 1 < r) {
+        const unsigned l = l0 + threadIdx.x;
         EncLimb e;
         e.q = L.q[l]; e.mu = L.mu[l]; e.qbit = (int)L.qbit[l];
         e.ratio = ratio_of(e.q);
@@ -291,10 +310,14 @@ NTT_KERNEL void k_encrypt_epilogue(u64 *c, const int *es, const u64 *m_poly, siz
         e.fast = barrett_is_exact(e.q, e.mu, e.qbit) && e.inv_q_last < e.q;
         e.inv_q_last_s = e.fast ? shoup_companion(e.inv_q_last, e.q) : 0;
         e.qdt = qi_div_t[l];
-        K[l] = e;
+        e.last_lt_2q = last <= 2 * e.q;      // c_last < q_last <= 2 q_i: its residue mod q_i is one conditional subtraction
+        // lazy path: every intermediate of the reference is only ever consumed modulo q_i and the value stored is canonical, so
+        // c_i + e - c_last + half_last may be formed as ONE biased sum in [0, 5q) and reduced by the (exact) Shoup product
+        e.lazy = e.fast && e.last_lt_2q && e.q < (1ull << 60);
+        e.bias = e.half_mod + 3 * e.q;
+        K[threadIdx.x] = e;
     }
     __syncthreads();
-    const unsigned h = blockIdx.y;
     const size_t rn = (size_t)r * n, k = blockIdx.z;
     u64 *ch = c + k * 2 * rn + (size_t)h * rn;
     const int *e = es + k * 2 * n + (size_t)h * n;
@@ -305,16 +328,13 @@ NTT_KERNEL void k_encrypt_epilogue(u64 *c, const int *es, const u64 *m_poly, siz
     int tsh = 0;
     while (tpow2 && (1ull << tsh) < t) tsh++;
     NTT_PAIR_STRIDE(j, n) {
+        ulonglong2 xv[kEncChunk];
+        NTT_UNROLL
+        for (unsigned i = 0; i < kEncChunk; i++)
+            if (l0 + i + 1 < r) xv[i] = ld2(ch + (size_t)(l0 + i) * n + j);
         const int d0 = e[j], d1 = e[j + 1];
-        // last limb: += e (`>` quirk, :187), += floor(q_last / 2) mod q_last (:121-124)
         const ulonglong2 lv = ld2(ch + (size_t)(r - 1) * n + j);
-        u64 cl0 = lv.x + signed_to_residue(d0, last), cl1 = lv.y + signed_to_residue(d1, last);
-        if (cl0 > last) cl0 -= last;
-        if (cl1 > last) cl1 -= last;
-        cl0 += half_last; cl1 += half_last;
-        if (cl0 >= last) cl0 -= last;
-        if (cl1 >= last) cl1 -= last;
-        st2(ch + (size_t)(r - 1) * n + j, cl0, cl1);
+        const u64 cl0 = enc_last_limb(lv.x, d0, last, half_last), cl1 = enc_last_limb(lv.y, d1, last, half_last);
         u64 m0 = 0, m1 = 0, f0 = 0, f1 = 0;
         if (h == 0) {
             const ulonglong2 mv = ld2(mp + j);
@@ -322,35 +342,62 @@ NTT_KERNEL void k_encrypt_epilogue(u64 *c, const int *es, const u64 *m_poly, siz
             f0 = tpow2 ? (m0 + tfix) >> tsh : (m0 + tfix) / t;
             f1 = tpow2 ? (m1 + tfix) >> tsh : (m1 + tfix) / t;
         }
-        // limbs in chunks of 4 with the loads issued together: one dependent 16-byte load per limb leaves HBM idle
-        for (unsigned l0 = 0; l0 + 1 < r; l0 += 4) {
-            ulonglong2 xv[4];
-            NTT_UNROLL
-            for (unsigned i = 0; i < 4; i++)
-                if (l0 + i + 1 < r) xv[i] = ld2(ch + (size_t)(l0 + i) * n + j);
-            NTT_UNROLL
-            for (unsigned i = 0; i < 4; i++) {
-                if (l0 + i + 1 >= r) break;
-                const EncLimb &P = K[l0 + i];
-                u64 x0 = xv[i].x + signed_to_residue(d0, P.q), x1 = xv[i].y + signed_to_residue(d1, P.q);
-                if (x0 > P.q) x0 -= P.q;
-                if (x1 > P.q) x1 -= P.q;
-                u64 t0 = mod_exact(cl0, P.q, P.ratio), t1 = mod_exact(cl1, P.q, P.ratio);
-                if (t0 < P.half_mod) t0 += P.q;
-                if (t1 < P.half_mod) t1 += P.q;
-                t0 -= P.half_mod; t1 -= P.half_mod;
-                if (x0 < t0) x0 += P.q;
-                if (x1 < t1) x1 += P.q;
-                x0 -= t0; x1 -= t1;
-                x0 = mul_const(x0, P.inv_q_last, P.inv_q_last_s, P.fast != 0, P.q, P.mu, P.qbit);
-                x1 = mul_const(x1, P.inv_q_last, P.inv_q_last_s, P.fast != 0, P.q, P.mu, P.qbit);
-                if (h == 0) {
-                    x0 = mod_exact(x0 + ((m0 * P.qdt) + f0), P.q, P.ratio);
-                    x1 = mod_exact(x1 + ((m1 * P.qdt) + f1), P.q, P.ratio);
+        NTT_UNROLL
+        for (unsigned i = 0; i < kEncChunk; i++) {
+            if (l0 + i + 1 >= r) break;
+            const EncLimb &P = K[i];
+            if (ALL_LAZY || P.lazy) {
+                // (c_i + e - (c_last - half)) * q_last^-1: sum in (q - 20, 5q), Shoup product in [0, 2q)
+                u64 x0 = shoup_mul(xv[i].x + P.bias + (u64)(long long)d0 - cl0, P.inv_q_last, P.inv_q_last_s, P.q);
+                u64 x1 = shoup_mul(xv[i].y + P.bias + (u64)(long long)d1 - cl1, P.inv_q_last, P.inv_q_last_s, P.q);
+                if (h == 0 && m0 < t && m1 < t) {          // + Delta*m + round-fix < q + 1: below 3q in total
+                    x0 = csub(x0 + ((m0 * P.qdt) + f0), 2 * P.q);
+                    x1 = csub(x1 + ((m1 * P.qdt) + f1), 2 * P.q);
+                } else if (h == 0) {
+                    x0 = mod_exact(csub(x0, P.q) + ((m0 * P.qdt) + f0), P.q, P.ratio);
+                    x1 = mod_exact(csub(x1, P.q) + ((m1 * P.qdt) + f1), P.q, P.ratio);
                 }
-                st2(ch + (size_t)(l0 + i) * n + j, x0, x1);
+                st2(ch + (size_t)(l0 + i) * n + j, csub(x0, P.q), csub(x1, P.q));
+                continue;
             }
+            if (ALL_LAZY) continue;
+            u64 x0 = xv[i].x + signed_to_residue(d0, P.q), x1 = xv[i].y + signed_to_residue(d1, P.q);
+            if (x0 > P.q) x0 -= P.q;
+            if (x1 > P.q) x1 -= P.q;
+            u64 t0, t1;
+            if (P.last_lt_2q) { t0 = csub(cl0, P.q); t1 = csub(cl1, P.q); }
+            else { t0 = mod_exact(cl0, P.q, P.ratio); t1 = mod_exact(cl1, P.q, P.ratio); }
+            if (t0 < P.half_mod) t0 += P.q;
+            if (t1 < P.half_mod) t1 += P.q;
+            t0 -= P.half_mod; t1 -= P.half_mod;
+            if (x0 < t0) x0 += P.q;
+            if (x1 < t1) x1 += P.q;
+            x0 -= t0; x1 -= t1;
+            x0 = mul_const(x0, P.inv_q_last, P.inv_q_last_s, P.fast != 0, P.q, P.mu, P.qbit);
+            x1 = mul_const(x1, P.inv_q_last, P.inv_q_last_s, P.fast != 0, P.q, P.mu, P.qbit);
+            if (h == 0) {
+                // a plaintext coefficient below t gives m * floor(q/t) < q and a round-fix of at most 1: the sum is below 2q
+                // and the reference's `% q` is one conditional subtraction; anything else takes the exact remainder
+                const u64 s0 = x0 + ((m0 * P.qdt) + f0), s1 = x1 + ((m1 * P.qdt) + f1);
+                if (m0 < t && m1 < t) { x0 = csub(s0, P.q); x1 = csub(s1, P.q); }
+                else { x0 = mod_exact(s0, P.q, P.ratio); x1 = mod_exact(s1, P.q, P.ratio); }
+            }
+            st2(ch + (size_t)(l0 + i) * n + j, x0, x1);
         }
+    }
+}
+// the dropped limb r-1 keeps the value the reference leaves there (padding of the ciphertext layout).  grid (x, 2, batch)
+NTT_KERNEL void k_encrypt_last_limb(u64 *c, const int *es, unsigned n, unsigned r, unsigned batch, LimbArrays L)
+{
+    (void)batch;
+    const u64 last = L.q[r - 1], half_last = last >> 1;
+    const unsigned h = blockIdx.y;
+    const size_t rn = (size_t)r * n, k = blockIdx.z;
+    u64 *p = c + k * 2 * rn + (size_t)h * rn + (size_t)(r - 1) * n;
+    const int *e = es + k * 2 * n + (size_t)h * n;
+    NTT_PAIR_STRIDE(j, n) {
+        const ulonglong2 lv = ld2(p + j);
+        st2(p + j, enc_last_limb(lv.x, e[j], last, half_last), enc_last_limb(lv.y, e[j + 1], last, half_last));
     }
 }
 
@@ -405,23 +452,27 @@ __device__ __forceinline__ void dec_stage_limbs(DecLimb *K, unsigned first, unsi
     __syncthreads();
 }
 // one limb's contribution: c1 += c0 (`>` quirk), *= t*gamma, *= punctured inverse, accumulate both base conversions
+template <bool ALL_FAST>
 __device__ __forceinline__ void dec_accumulate(const DecLimb &P, u64 a1, u64 a0, u32 mask32, const DecryptConsts &D, u64 &acc_t, u64 &acc_g)
 {
     u64 v = a1 + a0;
-    if (v > P.q) v -= P.q;
+    if (!ALL_FAST && v > P.q) v -= P.q;        // the `>` quirk only matters to the literal Barrett sequence; the Shoup product takes any input
     u64 g;
-    if (P.fast) {
+    if (ALL_FAST || P.fast) {
         v = csub(shoup_mul(v, P.c12, P.c12_s, P.q), P.q);                  // (v * t*gamma) * punctured inverse, canonical
         g = csub(shoup_mul(v, P.bg, P.bg_s, D.gamma), D.gamma);
-    } else {
+    } else if (!ALL_FAST) {
         v = barrett_ref(v, P.ptg, P.q, P.mu, P.qbit);
         v = barrett_ref(v, P.ipq, P.q, P.mu, P.qbit);
         g = barrett_ref(v, P.bg, D.gamma, D.mu_gamma, D.gamma_bits);
+    } else {
+        g = 0;
     }
     acc_t += (v * P.bt) & (u64)mask32;
     acc_g = add_mod_gamma(acc_g, g, D.gamma);
 }
 // both coefficients of pair j over `count` limbs, four limbs' loads (8 x 16 bytes) in flight at a time
+template <bool ALL_FAST>
 __device__ __forceinline__ void dec_sum_limbs(const DecLimb *K, const u64 *c0, const u64 *c1, unsigned n, u32 j, unsigned count, u32 mask32,
                                               const DecryptConsts &D, u64 &at0, u64 &at1, u64 &ag0, u64 &ag1)
 {
@@ -433,8 +484,8 @@ __device__ __forceinline__ void dec_sum_limbs(const DecLimb *K, const u64 *c0, c
         NTT_UNROLL
         for (unsigned i = 0; i < 4; i++) {
             if (l0 + i >= count) break;
-            dec_accumulate(K[l0 + i], a1[i].x, a0[i].x, mask32, D, at0, ag0);
-            dec_accumulate(K[l0 + i], a1[i].y, a0[i].y, mask32, D, at1, ag1);
+            dec_accumulate<ALL_FAST>(K[l0 + i], a1[i].x, a0[i].x, mask32, D, at0, ag0);
+            dec_accumulate<ALL_FAST>(K[l0 + i], a1[i].y, a0[i].y, mask32, D, at1, ag1);
         }
     }
 }
@@ -450,7 +501,9 @@ __device__ __forceinline__ u64 dec_finish_one(u64 acc_t, u64 acc_g, u32 mask32, 
 // poly_add_xq_d, poly_mul_int_xq_prodtgamma, poly_mul_int_xq_invpq (bfv_decryption.cuh:13-57), fast_convert_array_kernel_t,
 // _gamma (poly_arithmetic.cuh:217-251), mod_t, barrett_int, dec_round_kernel (:128-141, :100-126, :253-263) in one pass.
 // Writes n plaintext coefficients per item to out + k*out_stride.  grid (x, batch)
-NTT_KERNEL void k_decrypt_epilogue(const u64 *c, size_t item_stride, size_t c1_off, u64 *out, size_t out_stride, unsigned n, unsigned batch,
+template <bool ALL_FAST>
+NTT_KERNEL void __launch_bounds__(256, ALL_FAST ? 3 : 2)
+k_decrypt_epilogue(const u64 *c, size_t item_stride, size_t c1_off, u64 *out, size_t out_stride, unsigned n, unsigned batch,
                                    DecryptConsts D, LimbArrays L)
 {
     (void)batch;
@@ -461,7 +514,7 @@ NTT_KERNEL void k_decrypt_epilogue(const u64 *c, size_t item_stride, size_t c1_o
     const u64 *c0 = c + k * item_stride, *c1 = c0 + c1_off;
     NTT_PAIR_STRIDE(j, n) {
         u64 at0 = 0, at1 = 0, ag0 = 0, ag1 = 0;
-        dec_sum_limbs(K, c0, c1, n, j, D.rp, mask32, D, at0, at1, ag0, ag1);
+        dec_sum_limbs<ALL_FAST>(K, c0, c1, n, j, D.rp, mask32, D, at0, at1, ag0, ag1);
         st2(out + k * out_stride + j, dec_finish_one(at0, ag0, mask32, D), dec_finish_one(at1, ag1, mask32, D));
     }
 }
@@ -483,7 +536,7 @@ NTT_KERNEL void k_decrypt_partial(const u64 *c, size_t item_stride, size_t c1_of
     const u64 *c0 = c + k * item_stride, *c1 = c0 + c1_off;
     NTT_PAIR_STRIDE(j, n) {
         u64 at0 = 0, at1 = 0, ag0 = 0, ag1 = 0;
-        dec_sum_limbs(K, c0, c1, n, j, count, mask32, D, at0, at1, ag0, ag1);
+        dec_sum_limbs<false>(K, c0, c1, n, j, count, mask32, D, at0, at1, ag0, ag1);
         st2(part + k * 2 * n + j, at0, at1);
         st2(part + k * 2 * n + n + j, ag0, ag1);
     }

@@ -184,6 +184,10 @@ int ring_fused(const EmuRing &R, bool lazy, u64 *a, unsigned group_polys, size_t
 #define EXPORT extern "C" __attribute__((visibility("default")))
 #include "../table_kernels.cuh"
 
+// epilogue flavour the next emu_bfv calls run: 1 = the ALL_LAZY / ALL_FAST instantiations the host picks for eligible parameter sets
+static int g_epi_fast = 0;
+EXPORT void emu_set_epilogue_fast(int on) { g_epi_fast = on; }
+
 EXPORT int emu_bfv(int op, unsigned n, unsigned r, const u64 *q, const u64 *mu, const u32 *qbit, const u64 *psi, const u64 *psiinv,
                    const u64 *psi_s, const u64 *psiinv_s, const LimbConst *lc, int barrett,
                    // buffers
@@ -213,7 +217,8 @@ EXPORT int emu_bfv(int op, unsigned n, unsigned r, const u64 *q, const u64 *mu, 
         ring_ntt(R, false, c, batch * r, r, r, 2 * rn);
         ew3(r, batch, [&] { k_encrypt_mul(c, pk, per_item_keys ? 2 * rn : 0, n, r, batch, L); });
         ring_ntt(R, true, c, batch * 2 * r, r, 0, 0);
-        ew3(2, batch, [&] { k_encrypt_epilogue(c, es, m, (size_t)n, n, r, batch, t, qi_div_t, L); });
+        if (r > 1) ew3(2 * ((r - 1 + kEncChunk - 1) / kEncChunk), batch, [&] { if (g_epi_fast) k_encrypt_epilogue<true>(c, es, m, (size_t)n, n, r, batch, t, qi_div_t, L); else k_encrypt_epilogue<false>(c, es, m, (size_t)n, n, r, batch, t, qi_div_t, L); });
+        ew3(2, batch, [&] { k_encrypt_last_limb(c, es, n, r, batch, L); });
     } else if (op == 3 || op == 5) {   // encrypt through the fused kernel, key loaded (op 5: non-lazy policies); companions built here
         const size_t stride = 9 * (size_t)n; const u64 nblk = stride / 64;
         u64 *pk_s = new u64[2 * rn];
@@ -224,7 +229,8 @@ EXPORT int emu_bfv(int op, unsigned n, unsigned r, const u64 *q, const u64 *mu, 
         ring_ntt(R, false, c, batch * r, r, r, 2 * rn, 0);
         ring_fused(R, op == 3, c, 2 * r, 2 * rn, pk, pk_s, rn, r, 0, 0, r, batch, 2);
         ring_ntt(R, true, c, batch * 2 * r, r, 0, 0, 1);
-        ew3(2, batch, [&] { k_encrypt_epilogue(c, es, m, (size_t)n, n, r, batch, t, qi_div_t, L); });
+        if (r > 1) ew3(2 * ((r - 1 + kEncChunk - 1) / kEncChunk), batch, [&] { if (g_epi_fast) k_encrypt_epilogue<true>(c, es, m, (size_t)n, n, r, batch, t, qi_div_t, L); else k_encrypt_epilogue<false>(c, es, m, (size_t)n, n, r, batch, t, qi_div_t, L); });
+        ew3(2, batch, [&] { k_encrypt_last_limb(c, es, n, r, batch, L); });
         delete[] pk_s;
     } else if (op == 4 || op == 6) {   // decrypt through the fused kernel
         const unsigned rp = r - 1;
@@ -236,7 +242,7 @@ EXPORT int emu_bfv(int op, unsigned n, unsigned r, const u64 *q, const u64 *mu, 
         ring_ntt(R, false, c + c1_off, batch * rp, rp, rp, item, 0);
         ring_fused(R, op == 4, c, 2 * r, item, sk, sk_s, 0, rp, r, r, r, batch, 1);
         ring_ntt(R, true, c + c1_off, batch * rp, rp, rp, item, 1);
-        ew3(batch, 1, [&] { k_decrypt_epilogue(c, item, c1_off, out, (size_t)n, n, batch, D, L); });
+        ew3(batch, 1, [&] { if (g_epi_fast) k_decrypt_epilogue<true>(c, item, c1_off, out, (size_t)n, n, batch, D, L); else k_decrypt_epilogue<false>(c, item, c1_off, out, (size_t)n, n, batch, D, L); });
         delete[] sk_s;
     } else {                // decrypt (r = all limbs)
         const unsigned rp = r - 1;
@@ -245,7 +251,7 @@ EXPORT int emu_bfv(int op, unsigned n, unsigned r, const u64 *q, const u64 *mu, 
         ring_ntt(R, false, c + c1_off, batch * rp, rp, rp, item);
         ew3(rp, batch, [&] { k_decrypt_mul(c, item, c1_off, sk, per_item_keys ? rn : 0, n, rp, batch, L); });
         ring_ntt(R, true, c + c1_off, batch * rp, rp, rp, item);
-        ew3(batch, 1, [&] { k_decrypt_epilogue(c, item, c1_off, out, (size_t)n, n, batch, D, L); });
+        ew3(batch, 1, [&] { if (g_epi_fast) k_decrypt_epilogue<true>(c, item, c1_off, out, (size_t)n, n, batch, D, L); else k_decrypt_epilogue<false>(c, item, c1_off, out, (size_t)n, n, batch, D, L); });
     }
     return 0;
 }

@@ -150,3 +150,25 @@ def test_fused_key_product_matches_oracle(oracle, ring4k, ops):
     skk[:8192] = g["sk_host"]
     out, _ = emu.bfv(dec, er, 0, sk=skk, c=g["c_host"])
     assert np.array_equal(out[0], np.arange(4096, dtype=np.uint64) % 10)
+
+
+def test_all_lazy_epilogues_match_oracle(oracle):
+    """The ALL_LAZY encryption epilogue / ALL_FAST decryption epilogue (the instantiations nttb200_bfv_create selects when every
+    limb's Barrett is provably exact and q_last <= 2 q_i) against the oracle on a parameter set that qualifies (8k_4q), both
+    the unfused and the fused-key pipelines; message coefficients at the extremes 0 and t-1 included."""
+    n, q, roots = params.RNS_SETS["8k_4q"]
+    R = oracle.Ring(n, q, roots)
+    er = emu.EmuRing(R)
+    sk, pk, _ = emu.bfv(0, er, 0)
+    m = oracle.fill_uniform(n, R.t, 0xFA57)
+    m[:4] = [0, R.t - 1, 1, R.t - 1]
+    emu.lib().emu_set_epilogue_fast(1)
+    try:
+        for enc, dec in ((1, 2), (3, 4)):
+            c, es2 = emu.bfv(enc, er, 0, pk=pk, m=m)
+            oc, _ = oracle.encryption_rns(R, pk, m, e0_samples=np.ascontiguousarray(es2[0, 0]), e1_samples=np.ascontiguousarray(es2[0, 1]))
+            assert np.array_equal(c, oc)
+            out, _ = emu.bfv(dec, er, 0, sk=sk, c=c)
+            assert np.array_equal(out[0], m)
+    finally:
+        emu.lib().emu_set_epilogue_fast(0)
