@@ -73,6 +73,16 @@ NTTB200_API int nttb200_inverse_ntt_batch(const nttb200_ctx *ctx, nttb200_u64 *a
  * execution order (forward: strided pass then contiguous pass; inverse: the mirror).  bench.py times each with events. */
 NTTB200_API int nttb200_ntt_pass(const nttb200_ctx *ctx, nttb200_u64 *a, unsigned num, unsigned division, int inverse, int which,
                                  void *stream);
+/* a <- a * b in Z_q[X]/(X^n + 1), polynomial p modulo limb p % division: full_poly_mul_device / half_poly_mul_device,
+ * poly_arithmetic.cuh:296-310 (forwardNTTdouble, barrett, inverseNTT: 7 kernels, 7.5 HBM passes) as 4 launches / 4.5 passes:
+ * the contiguous forward passes of both operands, the coefficient-wise product and the contiguous inverse pass are one kernel.
+ * b is clobbered (the reference leaves NTT(b) there; here it holds b after its strided pass). */
+NTTB200_API int nttb200_poly_mul_batch(const nttb200_ctx *ctx, nttb200_u64 *a, nttb200_u64 *b, unsigned num, unsigned division, void *stream);
+/* a <- INTT(a (.) b) for two operands already in the NTT domain (canonical residues, the layout forward_ntt_batch leaves):
+ * barrett_batch + inverseNTT_batch (poly_arithmetic.cuh:36, ntt_60bit.cuh:652) with the product fused into the first inverse
+ * kernel.  b is only read. */
+NTTB200_API int nttb200_ntt_domain_mul_inverse_batch(const nttb200_ctx *ctx, nttb200_u64 *a, const nttb200_u64 *b, unsigned num,
+                                                     unsigned division, void *stream);
 /* same through HOST buffers: chunked H2D -> transform -> D2H on internal streams; synchronous. */
 NTTB200_API int nttb200_forward_ntt_batch_host(nttb200_ctx *ctx, const nttb200_u64 *in_host, nttb200_u64 *out_host, unsigned num,
                                                unsigned division);

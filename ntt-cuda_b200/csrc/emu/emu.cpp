@@ -145,6 +145,65 @@ int emu_ntt(int inverse, int barrett, int use_tma, int logn, u64 *a, const u64 *
     return inverse ? run_logn<BarrettPolicy, true>(logn, A) : run_logn<BarrettPolicy, false>(logn, A);
 }
 
+template <class PF, class PI, int LOGN, bool FWD>
+static void run_polymul_one(const PolymulArgs &F)
+{
+    const NttArgs &A = F.A;
+    TensorMap ma, mb;
+    EmuTmapDesc da{}, db{};
+    da.base = (unsigned char *)A.a; da.rank = 3;
+    da.dims[0] = 16; da.dims[1] = ((size_t)A.group_polys << LOGN) >> 4; da.dims[2] = (A.num + A.group_polys - 1) / A.group_polys;
+    da.strides[0] = 8; da.strides[1] = 128; da.strides[2] = A.group_stride * 8;
+    da.box[0] = 16; da.box[1] = kContigRows; da.box[2] = 1; da.swizzle128 = 1;
+    db = da;
+    db.base = (unsigned char *)F.b; db.dims[1] = ((size_t)F.b_group_polys << LOGN) >> 4; db.dims[2] = (A.num + F.b_group_polys - 1) / F.b_group_polys;
+    db.strides[2] = F.b_group_stride * 8;
+    memcpy(ma.opaque, &da, sizeof da);
+    memcpy(mb.opaque, &db, sizeof db);
+    emu_dim3 g;
+    g.x = A.num * (unsigned)((((size_t)1 << LOGN) >> 4) / kContigRows);
+    emu_launch(g, kContigRows, (size_t)kContigRows * 128 * 2 + 1024 + 16, [&] { ntt_contig_polymul<PF, PI, LOGN, FWD, FWD>(ma, mb, F); });
+}
+template <class PF, class PI, bool FWD>
+static int run_polymul_logn(int logn, const PolymulArgs &F)
+{
+    switch (logn) {
+    case 11: run_polymul_one<PF, PI, 11, FWD>(F); return 0;
+    case 12: run_polymul_one<PF, PI, 12, FWD>(F); return 0;
+    case 13: run_polymul_one<PF, PI, 13, FWD>(F); return 0;
+    case 14: run_polymul_one<PF, PI, 14, FWD>(F); return 0;
+    case 15: run_polymul_one<PF, PI, 15, FWD>(F); return 0;
+    case 16: run_polymul_one<PF, PI, 16, FWD>(F); return 0;
+    case 17: run_polymul_one<PF, PI, 17, FWD>(F); return 0;
+    }
+    return 1;
+}
+// nttb200_poly_mul_batch (fwd = 1) / nttb200_ntt_domain_mul_inverse_batch (fwd = 0) on the emulator, same launch order
+extern "C" __attribute__((visibility("default")))
+int emu_polymul(int fwd, int lazy, int logn, u64 *a, u64 *b, const u64 *psi, const u64 *psi_s, const u64 *psiinv, const u64 *psiinv_s,
+                const LimbConst *lc, unsigned num, unsigned division)
+{
+    const int pol = lazy ? 2 : 0;
+    if (fwd) {
+        g_which = 0;
+        emu_ntt(0, pol, 1, logn, a, psi, psi_s, lc, nullptr, nullptr, nullptr, num, division, 0, 0);
+        emu_ntt(0, pol, 1, logn, b, psi, psi_s, lc, nullptr, nullptr, nullptr, num, division, 0, 0);
+        g_which = -1;
+    }
+    PolymulArgs F{};
+    F.A.a = a; F.A.tw = psi; F.A.tws = psi_s; F.A.lc = lc; F.A.num = num; F.A.division = division; F.A.use_tma = 1;
+    F.A.group_polys = num; F.A.group_stride = (size_t)num << logn;
+    F.b = b; F.twi = psiinv; F.twis = psiinv_s; F.b_group_polys = num; F.b_group_stride = (size_t)num << logn;
+    int r;
+    if (lazy) r = fwd ? run_polymul_logn<ShoupLazyPolicy, ShoupLazyInvPolicy, true>(logn, F) : run_polymul_logn<ShoupLazyPolicy, ShoupLazyInvPolicy, false>(logn, F);
+    else r = fwd ? run_polymul_logn<ShoupPolicy, ShoupPolicy, true>(logn, F) : run_polymul_logn<ShoupPolicy, ShoupPolicy, false>(logn, F);
+    if (r) return r;
+    g_which = 1;
+    r = emu_ntt(1, pol, 1, logn, a, psiinv, psiinv_s, lc, nullptr, nullptr, nullptr, num, division, 0, 0);
+    g_which = -1;
+    return r;
+}
+
 extern "C" __attribute__((visibility("default"))) unsigned emu_sizeof_limbconst() { return (unsigned)sizeof(LimbConst); }
 
 // ---- BFV pipelines on the emulator: same kernels, same order as csrc/bfv.cu ---------------------------------------------

@@ -59,6 +59,9 @@ int launch_fused_mul(bool lazy, unsigned logn, const NttArgsHost &h, const u64 *
                      size_t key_item_stride, size_t key_half_stride, unsigned r, unsigned in_off, unsigned out_off0, unsigned out_off1,
                      unsigned items, int nout, cudaStream_t st);
 
+int launch_polymul(bool lazy, unsigned logn, const NttArgsHost &ha, const u64 *twi, const u64 *twis, const u64 *b, unsigned b_group_polys,
+                   size_t b_group_stride, bool fwd, cudaStream_t st);
+
 int get_tma_default();
 
 }  // namespace nttb200

@@ -184,6 +184,17 @@ __host__ __device__ __forceinline__ u64 barrett_ref(u64 a, u64 b, u64 q, u64 mu,
     return r >= q ? r - q : r;
 }
 
+// Product of two canonical residues without any precomputed companion: the reference's Barrett quotient estimate (never more
+// than 2 short) without its final correction.  Result in [0, 3q), a*b < 2^(2*qbit).
+__host__ __device__ __forceinline__ u64 barrett_lazy(u64 a, u64 b, u64 q, u64 mu, int qbit)
+{
+    u64 lo = a * b, hi = mulhi64(a, b);
+    u64 x1 = shr128_lo(hi, lo, qbit - 2);
+    u64 plo = x1 * mu, phi = mulhi64(x1, mu);
+    u64 x2 = shr128_lo(phi, plo, qbit + 2);
+    return lo - x2 * q;
+}
+
 // (x * 2^-1) mod q for canonical x, as the reference does after every inverse stage (ntt_60bit.cuh:165, 494-513)
 __host__ __device__ __forceinline__ u64 half_mod(u64 x, u64 q2) { return (x >> 1) + (q2 & (0 - (x & 1))); }
 

@@ -144,6 +144,8 @@ struct ShoupPolicy {
     }
     // lazy product with a key coefficient (companion ks): any 64-bit x -> [0, 2q), a valid inverse-round input
     __device__ __forceinline__ u64 mul_key(u64 x, u64 k, u64 ks) const { return shoup_mul_n(x, k, ks, nq); }
+    // product of two CANONICAL residues with no companion (polynomial products): [0, 2q), a valid inverse-round input
+    __device__ __forceinline__ u64 mul_generic(u64 x, u64 y) const { return csub(barrett_lazy(x, y, q, l->mu, (int)l->qbit), q); }
     // last inverse stage (length = 1) with n^-1 folded in; canonical outputs
     __device__ __forceinline__ void gs_last(u64 &U, u64 &V) const
     {
@@ -203,6 +205,7 @@ struct ShoupLazyInvPolicy : ShoupPolicy {
         fourq = twoq + twoq;
     }
     __device__ __forceinline__ u64 mul_key(u64 x, u64 k, u64 ks) const { return shoup_mul_m(x, k, ks, nq); }   // < B = 4q
+    __device__ __forceinline__ u64 mul_generic(u64 x, u64 y) const { return barrett_lazy(x, y, q, l->mu, (int)l->qbit); }   // < 3q < B
     // e: log2 of the common bound multiplier of U and V (compile-time after unrolling)
     __device__ __forceinline__ void gs_lazy(u64 &U, u64 &V, const Tw &t, int e) const
     {
@@ -736,6 +739,128 @@ ntt_contig_fused_mul(const __grid_constant__ TensorMap tmap, FusedArgs F)
         __syncthreads();
         tile_copy_coop<true, false>(tile, gbase + (size_t)row_o0 * 16, 16, RT, tid, RT);
         if (NOUT == 2) tile_copy_coop<true, false>(tile2, gbase + (size_t)row_o1 * 16, 16, RT, tid, RT);
+    }
+    (void)bar;
+}
+
+// ---- fused polynomial product: "contig forward pass of a and b  (.)  ->  contig inverse pass" ---------------------------------
+// c = a * b in Z_q[X]/(X^n + 1) needs NTT(a), NTT(b) only inside the product (full_poly_mul_device / half_poly_mul_device,
+// poly_arithmetic.cuh:296-310: forwardNTTdouble, barrett, inverseNTT = 7 kernels there).  After the strided forward passes of a
+// and b this kernel takes the same tile of both, finishes the two forward transforms, multiplies coefficient-wise (Barrett on
+// canonical values: neither operand has a Shoup companion) and runs the contiguous inverse pass; the strided inverse pass
+// follows.  A_FWD / B_FWD = false: that operand is already in the NTT domain (bit-reversed order, canonical) and is only read --
+// keygen's  INTT(NTT(s) (.) a)  with both operands transformed is the <false, false> instantiation.
+struct PolymulArgs {
+    NttArgs A;                 // operand a (in place: receives the result); forward tables
+    const u64 *b;              // operand b, [num][n], same polynomial order as a; clobbered when B_FWD
+    const u64 *twi, *twis;     // inverse tables
+    u32 b_group_polys;         // b's own group description (polynomial p of b at (p / gp) * stride + (p % gp) * n)
+    size_t b_group_stride;
+};
+
+template <class PF, class PI, int LOGN, bool A_FWD, bool B_FWD>
+__global__ void __launch_bounds__(kContigRows, 4)
+ntt_contig_polymul(const __grid_constant__ TensorMap tmap_a, const __grid_constant__ TensorMap tmap_b, PolymulArgs F)
+{
+    using SC = Sched<LOGN>;
+    constexpr int K1 = SC::K1, K2 = SC::K2, SA = K2 - 4, NC = 16 >> SA, RT = kContigRows;
+    constexpr u32 n = 1u << LOGN, TILES = (n >> 4) / RT;
+    const NttArgs &A = F.A;
+    NTT_DYN_SMEM(raw);
+    u64 *tile = align_1024(raw);
+    u64 *tile2 = tile + (size_t)RT * 16;
+    u64 *bar = tile + (size_t)RT * 16 * 2;
+    const u32 tid = threadIdx.x;
+    const u32 p = blockIdx.x / TILES, rip0 = (blockIdx.x % TILES) * RT;
+    const u32 grp = p / A.group_polys, idx = p - grp * A.group_polys;
+    const u32 bgrp = p / F.b_group_polys, bidx = p - bgrp * F.b_group_polys;
+    const u32 limb = p % A.division;
+    PF pf;
+    pf.init(A, limb, n);
+    NttArgs Ai = A;
+    Ai.tw = F.twi; Ai.tws = F.twis;
+    PI pi;
+    pi.init(Ai, limb, n);
+    const int row_a = (int)(idx * (n >> 4) + rip0), row_b = (int)(bidx * (n >> 4) + rip0);
+    u64 *ga = A.a + (size_t)grp * A.group_stride + ((size_t)idx << LOGN) + (size_t)rip0 * 16;
+    const u64 *gb = F.b + (size_t)bgrp * F.b_group_stride + ((size_t)bidx << LOGN) + (size_t)rip0 * 16;
+
+    if (A.use_tma & 1u) {
+#ifdef NTTB200_EMU
+        if (tid == 0) { emu_tma_3d(true, &tmap_a, tile, 0, row_a, (int)grp); emu_tma_3d(true, &tmap_b, tile2, 0, row_b, (int)bgrp); }
+        __syncthreads();
+#else
+        if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(bar, (u32)(2 * RT * 128));
+            tma_load_3d(tile, &tmap_a, bar, 0, row_a, (int)grp);
+            tma_load_3d(tile2, &tmap_b, bar, 0, row_b, (int)bgrp);
+        }
+        mbar_wait(bar, 0);
+#endif
+    } else {
+        tile_copy_coop<true, true>(tile, ga, 16, RT, tid, RT);
+        tile_copy_coop<true, true>(tile2, const_cast<u64 *>(gb), 16, RT, tid, RT);
+        __syncthreads();
+    }
+
+    const u32 t = tid & ((1u << SA) - 1u), bl = tid >> SA;
+    const u32 twA = (1u << K1) + (rip0 >> SA) + bl, twB = (n >> 4) + rip0 + tid;
+    u64 v[16];
+    // forward column rounds
+    if constexpr (A_FWD) {
+        regs_rows<SA, true, true>(tile, bl << SA, 0, t * NC, v);
+        ct_stages<SA, NC>(v, twA, pf);
+        regs_rows<SA, true, false>(tile, bl << SA, 0, t * NC, v);
+    }
+    if constexpr (B_FWD) {
+        regs_rows<SA, true, true>(tile2, bl << SA, 0, t * NC, v);
+        ct_stages<SA, NC>(v, twA, pf);
+        regs_rows<SA, true, false>(tile2, bl << SA, 0, t * NC, v);
+    }
+    if constexpr (A_FWD || B_FWD) __syncwarp();
+    // b: forward row round, canonical, parked in its own row of tile2 (only this lane touches the row from here on)
+    if constexpr (B_FWD) {
+        regs_row<true, true>(tile2, tid, v);
+        ct_stages<4, 1>(v, twB, pf);
+        NTT_UNROLL
+        for (int i = 0; i < 16; i++) v[i] = pf.fwd_final(v[i]);
+        regs_row<true, false>(tile2, tid, v);
+    }
+    // a: forward row round, canonical, (.) b, inverse row round
+    regs_row<true, true>(tile, tid, v);
+    if constexpr (A_FWD) {
+        ct_stages<4, 1>(v, twB, pf);
+        NTT_UNROLL
+        for (int i = 0; i < 16; i++) v[i] = pf.fwd_final(v[i]);
+    }
+    NTT_UNROLL
+    for (int c = 0; c < 8; c++) {
+        const ulonglong2 bv = *reinterpret_cast<const ulonglong2 *>(tile2 + tile_off<true>(tid, 2 * c));
+        v[2 * c] = pi.mul_generic(v[2 * c], bv.x);
+        v[2 * c + 1] = pi.mul_generic(v[2 * c + 1], bv.y);
+    }
+    gs_stages<4, 1, false>(v, twB, pi);
+    regs_row<true, false>(tile, tid, v);
+    __syncwarp();
+    // inverse column round
+    regs_rows<SA, true, true>(tile, bl << SA, 0, t * NC, v);
+    gs_stages<SA, NC, false>(v, twA, pi);
+    regs_rows<SA, true, false>(tile, bl << SA, 0, t * NC, v);
+
+    if (A.use_tma & 1u) {
+#ifdef NTTB200_EMU
+        __syncthreads();
+        if (tid == 0) emu_tma_3d(false, &tmap_a, tile, 0, row_a, (int)grp);
+#else
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) { tma_store_3d(&tmap_a, tile, 0, row_a, (int)grp); tma_store_commit(); tma_store_wait_read<0>(); }
+#endif
+    } else {
+        __syncthreads();
+        tile_copy_coop<true, false>(tile, ga, 16, RT, tid, RT);
     }
     (void)bar;
 }

@@ -233,6 +233,68 @@ int launch_fused_mul(bool lazy, unsigned logn, const NttArgsHost &h, const u64 *
     return nout == 2 ? launch_fused_logn<ShoupPolicy, ShoupPolicy, 2>(logn, F, mc, st) : launch_fused_logn<ShoupPolicy, ShoupPolicy, 1>(logn, F, mc, st);
 }
 
+// ---- fused polynomial product ----------------------------------------------------------------------------------------------
+template <class PF, class PI, int LOGN, bool A_FWD, bool B_FWD>
+static int launch_polymul_one(const PolymulArgs &F, const CUtensorMap &ma, const CUtensorMap &mb, cudaStream_t st)
+{
+    constexpr size_t smem = (size_t)kContigRows * 128 * 2 + 1024 + 16;
+    static bool attr_done[64] = {false};
+    int dev = 0;
+    NTTB200_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+        NTTB200_CHECK(cudaFuncSetAttribute(ntt_contig_polymul<PF, PI, LOGN, A_FWD, B_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (dev >= 0 && dev < 64) attr_done[dev] = true;
+    }
+    const unsigned tiles = ((1u << LOGN) >> 4) / kContigRows;
+    if ((size_t)F.A.num * tiles >= (1ull << 31)) return NTTB200_EINVAL;
+    ntt_contig_polymul<PF, PI, LOGN, A_FWD, B_FWD><<<F.A.num * tiles, kContigRows, smem, st>>>(ma, mb, F);
+    return (int)cudaGetLastError();
+}
+template <class PF, class PI, bool A_FWD, bool B_FWD>
+static int launch_polymul_logn(unsigned logn, const PolymulArgs &F, const CUtensorMap &ma, const CUtensorMap &mb, cudaStream_t st)
+{
+    switch (logn) {
+    case 11: return launch_polymul_one<PF, PI, 11, A_FWD, B_FWD>(F, ma, mb, st);
+    case 12: return launch_polymul_one<PF, PI, 12, A_FWD, B_FWD>(F, ma, mb, st);
+    case 13: return launch_polymul_one<PF, PI, 13, A_FWD, B_FWD>(F, ma, mb, st);
+    case 14: return launch_polymul_one<PF, PI, 14, A_FWD, B_FWD>(F, ma, mb, st);
+    case 15: return launch_polymul_one<PF, PI, 15, A_FWD, B_FWD>(F, ma, mb, st);
+    case 16: return launch_polymul_one<PF, PI, 16, A_FWD, B_FWD>(F, ma, mb, st);
+    case 17: return launch_polymul_one<PF, PI, 17, A_FWD, B_FWD>(F, ma, mb, st);
+    default: return NTTB200_EINVAL;
+    }
+}
+// ha: operand a (forward tables, group description); b with its own group description.  a_fwd / b_fwd: the operand still needs
+// its contiguous forward pass (false: it is already in the NTT domain).  Only (true, true) and (false, false) are instantiated.
+int launch_polymul(bool lazy, unsigned logn, const NttArgsHost &ha, const u64 *twi, const u64 *twis, const u64 *b, unsigned b_group_polys,
+                   size_t b_group_stride, bool fwd, cudaStream_t st)
+{
+    if (logn < 11 || logn > 17 || !ha.a || !b || !ha.num || !ha.division) return NTTB200_EINVAL;
+    PolymulArgs F;
+    NttArgs &A = F.A;
+    A.a = ha.a; A.tw = ha.tw; A.tws = ha.tws; A.lc = ha.lc;
+    A.qv = nullptr; A.muv = nullptr; A.qbitv = nullptr; A.q = 0; A.mu = 0; A.qbit = 0;
+    A.num = ha.num; A.division = ha.division; A.use_tma = (u32)ha.use_tma; A.pf_dist = 0;
+    A.group_polys = ha.group_polys ? ha.group_polys : ha.num;
+    A.group_stride = ha.group_polys ? ha.group_stride : ((size_t)ha.num << logn);
+    F.b = b; F.twi = twi; F.twis = twis;
+    F.b_group_polys = b_group_polys ? b_group_polys : ha.num;
+    F.b_group_stride = b_group_polys ? b_group_stride : ((size_t)ha.num << logn);
+    CUtensorMap ma, mb;
+    if (ha.use_tma & 1) {
+        int rc = make_tmap_contig(&ma, A.a, logn, A.group_polys, A.group_stride, (ha.num + A.group_polys - 1) / A.group_polys);
+        if (rc) return rc;
+        rc = make_tmap_contig(&mb, const_cast<u64 *>(b), logn, F.b_group_polys, F.b_group_stride, (ha.num + F.b_group_polys - 1) / F.b_group_polys);
+        if (rc) return rc;
+    } else {
+        memset(&ma, 0, sizeof ma); memset(&mb, 0, sizeof mb);
+    }
+    if (lazy) return fwd ? launch_polymul_logn<ShoupLazyPolicy, ShoupLazyInvPolicy, true, true>(logn, F, ma, mb, st)
+                         : launch_polymul_logn<ShoupLazyPolicy, ShoupLazyInvPolicy, false, false>(logn, F, ma, mb, st);
+    return fwd ? launch_polymul_logn<ShoupPolicy, ShoupPolicy, true, true>(logn, F, ma, mb, st)
+               : launch_polymul_logn<ShoupPolicy, ShoupPolicy, false, false>(logn, F, ma, mb, st);
+}
+
 }  // namespace nttb200
 
 using namespace nttb200;
@@ -260,6 +322,40 @@ int nttb200_ntt_pass(const nttb200_ctx *ctx, nttb200_u64 *a, unsigned num, unsig
     NttArgsHost h{a, inverse ? ctx->psiinv : ctx->psi, inverse ? ctx->psiinv_s : ctx->psi_s, ctx->lc, nullptr, nullptr, nullptr, 0, 0, 0,
                   num, division, ctx->use_tma};
     return launch_ntt_pass(inverse != 0, ctx->lazy_ok ? kPolicyShoupLazy : kPolicyShoup, ctx->logn, h, which, (cudaStream_t)stream);
+}
+
+// a <- a * b in Z_q[X]/(X^n + 1), polynomial p modulo limb p % division; b is clobbered (it holds its half-transformed image).
+// 4 launches: strided forward pass of a and of b, ONE fused kernel (both contiguous forward passes, coefficient-wise product,
+// contiguous inverse pass), strided inverse pass.
+int nttb200_poly_mul_batch(const nttb200_ctx *ctx, nttb200_u64 *a, nttb200_u64 *b, unsigned num, unsigned division, void *stream)
+{
+    if (!ctx || !a || !b || division == 0 || division > ctx->limbs) return NTTB200_EINVAL;
+    if (num == 0) return 0;
+    const int pol = ctx->lazy_ok ? kPolicyShoupLazy : kPolicyShoup;
+    cudaStream_t st = (cudaStream_t)stream;
+    NttArgsHost ha{a, ctx->psi, ctx->psi_s, ctx->lc, nullptr, nullptr, nullptr, 0, 0, 0, num, division, ctx->use_tma};
+    NttArgsHost hb = ha; hb.a = b;
+    int r = launch_ntt_pass(false, pol, ctx->logn, ha, 0, st);
+    if (!r) r = launch_ntt_pass(false, pol, ctx->logn, hb, 0, st);
+    if (!r) r = launch_polymul(ctx->lazy_ok != 0, ctx->logn, ha, ctx->psiinv, ctx->psiinv_s, b, 0, 0, true, st);
+    NttArgsHost hi{a, ctx->psiinv, ctx->psiinv_s, ctx->lc, nullptr, nullptr, nullptr, 0, 0, 0, num, division, ctx->use_tma};
+    if (!r) r = launch_ntt_pass(true, pol, ctx->logn, hi, 1, st);
+    return r;
+}
+// a <- INTT(a (.) b) for operands that are both already in the NTT domain (canonical): coefficient-wise product fused into the
+// contiguous inverse pass, then the strided inverse pass.  b is only read.
+int nttb200_ntt_domain_mul_inverse_batch(const nttb200_ctx *ctx, nttb200_u64 *a, const nttb200_u64 *b, unsigned num, unsigned division,
+                                         void *stream)
+{
+    if (!ctx || !a || !b || division == 0 || division > ctx->limbs) return NTTB200_EINVAL;
+    if (num == 0) return 0;
+    const int pol = ctx->lazy_ok ? kPolicyShoupLazy : kPolicyShoup;
+    cudaStream_t st = (cudaStream_t)stream;
+    NttArgsHost ha{a, ctx->psi, ctx->psi_s, ctx->lc, nullptr, nullptr, nullptr, 0, 0, 0, num, division, ctx->use_tma};
+    int r = launch_polymul(ctx->lazy_ok != 0, ctx->logn, ha, ctx->psiinv, ctx->psiinv_s, b, 0, 0, false, st);
+    NttArgsHost hi{a, ctx->psiinv, ctx->psiinv_s, ctx->lc, nullptr, nullptr, nullptr, 0, 0, 0, num, division, ctx->use_tma};
+    if (!r) r = launch_ntt_pass(true, pol, ctx->logn, hi, 1, st);
+    return r;
 }
 
 int nttb200_ref_forward_ntt_batch(nttb200_u64 *a, unsigned n, const nttb200_u64 *psi_powers, unsigned num, unsigned division,

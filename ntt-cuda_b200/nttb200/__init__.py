@@ -121,6 +121,15 @@ class Context:
     def inverse_ntt_batch(self, a, num: int, division: int, stream=None):
         check(lib().nttb200_inverse_ntt_batch(self._h, vp(ptr(a)), C.c_uint(num), C.c_uint(division), vp(_stream(stream))))
 
+    def poly_mul_batch(self, a, b, num: int, division: int, stream=None):
+        """a <- a * b mod (X^n + 1, q_limb), fused (full_poly_mul_device, poly_arithmetic.cuh:296); b is clobbered."""
+        check(lib().nttb200_poly_mul_batch(self._h, vp(ptr(a)), vp(ptr(b)), C.c_uint(num), C.c_uint(division), vp(_stream(stream))))
+
+    def ntt_domain_mul_inverse_batch(self, a, b, num: int, division: int, stream=None):
+        """a <- INTT(a (.) b), both operands in the NTT domain; b is only read."""
+        check(lib().nttb200_ntt_domain_mul_inverse_batch(self._h, vp(ptr(a)), vp(ptr(b)), C.c_uint(num), C.c_uint(division),
+                                                         vp(_stream(stream))))
+
     def ntt_pass(self, a, num: int, division: int, inverse: bool, which: int, stream=None):
         """Profiling hook: only the first / second kernel of the transform (execution order)."""
         check(lib().nttb200_ntt_pass(self._h, vp(ptr(a)), C.c_uint(num), C.c_uint(division), C.c_int(int(inverse)), C.c_int(which),

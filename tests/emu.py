@@ -68,6 +68,24 @@ def ntt(a, n, qs, psi_tables, psiinv_tables, num, division, inverse, barrett, us
     return a
 
 
+def polymul(a, b, n, qs, psi_tables, psiinv_tables, num, division, fwd=True, lazy=True):
+    """nttb200_poly_mul_batch (fwd) / nttb200_ntt_domain_mul_inverse_batch (not fwd) on the emulator; returns (result, b after the call)."""
+    logn = n.bit_length() - 1
+    a = np.ascontiguousarray(a, dtype=np.uint64).copy()
+    b = np.ascontiguousarray(b, dtype=np.uint64).copy()
+    psi = np.ascontiguousarray(psi_tables, dtype=np.uint64)
+    psiinv = np.ascontiguousarray(psiinv_tables, dtype=np.uint64)
+    limbs = len(qs)
+    psi_s = np.ascontiguousarray(np.stack([shoup(psi[l], int(qs[l])) for l in range(limbs)]))
+    psiinv_s = np.ascontiguousarray(np.stack([shoup(psiinv[l], int(qs[l])) for l in range(limbs)]))
+    lc = limb_consts(qs, n, psiinv)
+    u = C.c_ulonglong
+    r = lib().emu_polymul(int(fwd), int(lazy), logn, p(a, u), p(b, u), p(psi, u), p(psi_s, u), p(psiinv, u), p(psiinv_s, u),
+                          lc.ctypes.data_as(C.c_void_p), num, division)
+    assert r == 0
+    return a, b
+
+
 # ---- BFV pipelines / pointwise / sampling on the emulator ---------------------------------------------------------------
 class EmuRing:
     """Device-side view of an oracle.Ring for the emulator (tables, Shoup companions, LimbConst)."""

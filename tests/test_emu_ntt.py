@@ -150,3 +150,37 @@ def test_emu_device_table_generation(oracle):
         assert np.array_equal(bufs[0][l * n:(l + 1) * n], psi) and np.array_equal(bufs[2][l * n:(l + 1) * n], psiinv)
         assert np.array_equal(bufs[1][l * n:(l + 1) * n], emu.shoup(psi, qs[l]))
         assert np.array_equal(bufs[3][l * n:(l + 1) * n], emu.shoup(psiinv, qs[l]))
+
+
+@pytest.mark.parametrize("logn,limbs,num,lazy", [(11, 1, 2, 1), (12, 1, 1, 0), (13, 3, 3, 1), (15, 2, 2, 1)])
+def test_emu_fused_polynomial_product(oracle, logn, limbs, num, lazy):
+    """nttb200_poly_mul_batch (strided passes + ONE fused contig-forward x2 / product / contig-inverse kernel) against the
+    schoolbook negacyclic product (helper.h:95-126 refPolyMul128, the check of 60bit_ntt_test.cu:85-98) at n = 2^11 and against
+    the oracle's own NTT -> barrett -> INTT chain (poly_arithmetic.cuh:296-310) elsewhere; edge coefficients 0, 1, q-1."""
+    n, qs, psi, psiinv = _ring(oracle, logn, limbs)
+    a = np.concatenate([oracle.fill_uniform(n, qs[i % limbs], 0xA000 + i) for i in range(num)])
+    b = np.concatenate([oracle.fill_uniform(n, qs[i % limbs], 0xB000 + i) for i in range(num)])
+    a[0], a[1], a[2], b[0], b[1], b[2] = 0, 1, qs[0] - 1, qs[0] - 1, 0, qs[0] - 1
+    got, _ = emu.polymul(a, b, n, qs, psi, psiinv, num, limbs, fwd=True, lazy=bool(lazy))
+    for i in range(num):
+        q, l = qs[i % limbs], i % limbs
+        ai, bi = a[i * n:(i + 1) * n], b[i * n:(i + 1) * n]
+        if logn == 11:
+            exp = oracle.ref_poly_mul(ai, bi, q)
+        else:
+            exp = oracle.inverse_ntt_fast(oracle.barrett(oracle.forward_ntt_fast(ai, q, psi[l]), oracle.forward_ntt_fast(bi, q, psi[l]), q), q, psiinv[l])
+        assert np.array_equal(got[i * n:(i + 1) * n], exp), f"polynomial {i}"
+
+
+def test_emu_ntt_domain_product_then_inverse(oracle):
+    """nttb200_ntt_domain_mul_inverse_batch: a <- INTT(a (.) b) with both operands already transformed; b untouched."""
+    n, qs, psi, psiinv = _ring(oracle, 13, 3)
+    num = 3
+    a = np.concatenate([oracle.forward_ntt_fast(oracle.fill_uniform(n, qs[i % 3], 0xC000 + i), qs[i % 3], psi[i % 3]) for i in range(num)])
+    b = np.concatenate([oracle.fill_uniform(n, qs[i % 3], 0xD000 + i) for i in range(num)])
+    got, b_after = emu.polymul(a, b, n, qs, psi, psiinv, num, 3, fwd=False, lazy=True)
+    assert np.array_equal(b_after, b)
+    for i in range(num):
+        q, l = qs[i % 3], i % 3
+        exp = oracle.inverse_ntt_fast(oracle.barrett(a[i * n:(i + 1) * n], b[i * n:(i + 1) * n], q), q, psiinv[l])
+        assert np.array_equal(got[i * n:(i + 1) * n], exp)

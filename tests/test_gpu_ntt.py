@@ -175,3 +175,60 @@ def test_c5_large_rings_many_limbs(oracle, logn, limbs, num):
     ctx.inverse_ntt_batch(fa, num, limbs)
     assert torch.equal(fa, a)
     ctx.close()
+
+
+@pytest.mark.parametrize("logn,limbs,num", [(11, 1, 3), (12, 3, 4), (13, 1, 2), (14, 5, 6), (15, 16, 33), (16, 2, 3), (17, 1, 2)])
+def test_fused_polynomial_product_vs_oracle(oracle, logn, limbs, num):
+    """nttb200_poly_mul_batch (full_poly_mul_device, poly_arithmetic.cuh:296-310) against the schoolbook negacyclic product
+    (helper.h:95-126, the check of 60bit_ntt_test.cu:85-98) at n = 2^11 and the oracle's NTT -> barrett -> INTT elsewhere."""
+    import nttb200
+    from tests.gpu_util import to_dev, to_host
+    n, qs, roots = _ring(oracle, logn, limbs)
+    psi, psiinv = _tables(oracle, n, qs, roots)
+    ctx = nttb200.Context(n, qs, roots)
+    a = np.concatenate([oracle.fill_uniform(n, qs[p % limbs], 0xA000 + p) for p in range(num)])
+    b = np.concatenate([oracle.fill_uniform(n, qs[p % limbs], 0xB000 + p) for p in range(num)])
+    a[0], a[1], a[2], b[0], b[1], b[2] = 0, 1, qs[0] - 1, qs[0] - 1, 0, qs[0] - 1
+    da, db = to_dev(a), to_dev(b)
+    ctx.poly_mul_batch(da, db, num, limbs)
+    got = to_host(da)
+    for p in range(0, num, max(1, num // 5)):
+        q, l = qs[p % limbs], p % limbs
+        ap, bp = a[p * n:(p + 1) * n], b[p * n:(p + 1) * n]
+        if logn == 11:
+            exp = oracle.ref_poly_mul(ap, bp, q)
+        else:
+            exp = oracle.inverse_ntt_fast(oracle.barrett(oracle.forward_ntt_fast(ap, q, psi[l]), oracle.forward_ntt_fast(bp, q, psi[l]), q), q, psiinv[l])
+        assert np.array_equal(got[p * n:(p + 1) * n], exp), f"polynomial {p}"
+    ctx.close()
+
+
+def test_fused_product_full_size_equals_unfused_chain(oracle):
+    """C2 size (1024 x 2^15, 16 limbs): the fused product equals forward_ntt_batch x2 -> coefficient-wise product -> inverse_ntt_batch
+    done with separate calls, and ntt_domain_mul_inverse_batch equals the last two steps; commutativity a*b == b*a."""
+    import torch
+    import nttb200
+    n, qs, roots = params.RNS_SETS["32k_16q"]
+    L, num = 16, 1024
+    ctx = nttb200.Context(n, qs, roots)
+    g = torch.Generator(device="cuda").manual_seed(99)
+    qv = torch.tensor(qs, dtype=torch.int64, device="cuda").repeat(num // L).view(num, 1)
+    a = torch.randint(0, 2**62, (num, n), dtype=torch.int64, device="cuda", generator=g) % qv
+    b = torch.randint(0, 2**62, (num, n), dtype=torch.int64, device="cuda", generator=g) % qv
+    fa, fb = a.clone(), b.clone()
+    ctx.forward_ntt_batch(fa, num, L)
+    ctx.forward_ntt_batch(fb, num, L)
+    prod = fa.clone()
+    nttb200.barrett_batch(prod, fb, n, num, L, ctx.q_dev, ctx.mu_dev, ctx.qbit_dev)
+    ref = prod.clone()
+    ctx.inverse_ntt_batch(ref, num, L)
+    x, y = a.clone(), b.clone()
+    ctx.poly_mul_batch(x, y, num, L)
+    assert torch.equal(x, ref)
+    x2, y2 = b.clone(), a.clone()
+    ctx.poly_mul_batch(x2, y2, num, L)
+    assert torch.equal(x2, ref)
+    z = fa.clone()
+    ctx.ntt_domain_mul_inverse_batch(z, fb, num, L)
+    assert torch.equal(z, ref)
+    ctx.close()
