@@ -55,7 +55,7 @@ struct nttb200_bfv {
     // grow-only scratch: keystream and gaussian draws
     unsigned char *ks = nullptr; size_t ks_bytes = 0;
     int *es = nullptr; size_t es_count = 0;
-    bool enc_lazy = false, dec_fast = false;
+    bool enc_lazy = false, dec_fast = false, all_exact = false;
 };
 
 static u64 h_modpow(u64 a, u64 e, u64 m)
@@ -78,6 +78,7 @@ struct Pipe {                 // everything one pipeline run needs, independent 
     int use_tma;
     cudaStream_t st;
     bool enc_lazy = false, dec_fast = false;   // host-verified: every limb qualifies for the lazy / Shoup-only epilogues
+    bool all_exact = false;                    // host-verified: the reference's Barrett is exact for every limb (any exact product = its bits)
 };
 
 static NttArgsHost pipe_args(const Pipe &P, bool inverse, u64 *a, unsigned num, unsigned division, unsigned group_polys, size_t group_stride)
@@ -114,9 +115,16 @@ static int run_keygen(const Pipe &P, unsigned char *in, size_t in_stride, int *e
     k_keygen_sample<<<pair_grid(n, batch, 1), pair_block(n, batch, 1), 0, P.st>>>(in, in_stride, sk, pk, es, n, r, batch, P.L.q);   // :120-122
     KCHECK();
     NTTB200_TRY(pipe_ntt(P, false, sk, batch * r, r, 0, 0));                               // :129
-    k_keygen_mul<<<pair_grid(n, r, batch), pair_block(n, r, batch), 0, P.st>>>(pk, sk, n, r, batch, P.L);                      // :132
-    KCHECK();
-    NTTB200_TRY(pipe_ntt(P, true, pk, batch * r, r, r, 2 * rn));                           // :133
+    if (P.all_exact && P.policy_inv != kPolicyBarrett) {
+        // pk0 = INTT(a (.) NTT(s)): the product rides in the first inverse kernel (both operands are canonical NTT-domain values)
+        NTTB200_TRY(launch_polymul(P.policy_inv == kPolicyShoupLazy, P.logn, pipe_args(P, false, pk + rn, batch * r, r, r, 2 * rn), P.psiinv,
+                                   P.psiinv_s, sk, 0, 0, false, pk, P.st));                // :132
+        NTTB200_TRY(pipe_ntt_pass(P, true, 1, pk, batch * r, r, r, 2 * rn));               // :133 (second kernel)
+    } else {
+        k_keygen_mul<<<pair_grid(n, r, batch), pair_block(n, r, batch), 0, P.st>>>(pk, sk, n, r, batch, P.L);                  // :132
+        KCHECK();
+        NTTB200_TRY(pipe_ntt(P, true, pk, batch * r, r, r, 2 * rn));                       // :133
+    }
     k_keygen_add_negate<<<pair_grid(n, r, batch), pair_block(n, r, batch), 0, P.st>>>(pk, es, n, r, batch, P.L);               // :144
     KCHECK();
     NTTB200_TRY(pipe_ntt(P, false, pk, batch * r, r, r, 2 * rn));                          // :145
@@ -214,7 +222,7 @@ static Pipe pipe_from_bfv(const nttb200_bfv *b, cudaStream_t st)
     P.n = b->n; P.logn = c->logn; P.r = b->r;
     P.L = LimbArrays{c->q_dev, c->mu_dev, c->qbit_dev, b->inv_q_last_mod_q, b->inv_punctured_q, b->prod_t_gamma_mod_q};
     P.qi_div_t = b->qi_div_t;
-    P.enc_lazy = b->enc_lazy; P.dec_fast = b->dec_fast;
+    P.enc_lazy = b->enc_lazy; P.dec_fast = b->dec_fast; P.all_exact = b->all_exact;
     P.policy_fwd = P.policy_inv = c->lazy_ok ? kPolicyShoupLazy : kPolicyShoup;
     P.psi = c->psi; P.psiinv = c->psiinv; P.psi_s = c->psi_s; P.psiinv_s = c->psiinv_s; P.lc = c->lc;
     P.use_tma = c->use_tma; P.st = st;
@@ -280,6 +288,8 @@ int nttb200_bfv_create(nttb200_bfv **out, unsigned n, unsigned limbs, const nttb
     };
     // epilogue flavours (bfv_kernels.cuh): the same predicates the kernels evaluate per limb, checked here for ALL limbs
     b->enc_lazy = true; b->dec_fast = barrett_is_exact(gamma, b->mu_gamma, b->gamma_bits);
+    b->all_exact = true;
+    for (unsigned i = 0; i < r; i++) b->all_exact = b->all_exact && barrett_is_exact(q[i], ctx->mu[i], (int)ctx->qbit[i]);
     for (unsigned i = 0; i < rp; i++) {
         const bool exact = barrett_is_exact(q[i], ctx->mu[i], (int)ctx->qbit[i]);
         b->enc_lazy = b->enc_lazy && exact && iql[i] < q[i] && q[r - 1] <= 2 * q[i] && q[i] < (1ull << 60);

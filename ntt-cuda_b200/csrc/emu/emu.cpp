@@ -149,8 +149,8 @@ template <class PF, class PI, int LOGN, bool FWD>
 static void run_polymul_one(const PolymulArgs &F)
 {
     const NttArgs &A = F.A;
-    TensorMap ma, mb;
-    EmuTmapDesc da{}, db{};
+    TensorMap ma, mb, mo;
+    EmuTmapDesc da{}, db{}, dout{};
     da.base = (unsigned char *)A.a; da.rank = 3;
     da.dims[0] = 16; da.dims[1] = ((size_t)A.group_polys << LOGN) >> 4; da.dims[2] = (A.num + A.group_polys - 1) / A.group_polys;
     da.strides[0] = 8; da.strides[1] = 128; da.strides[2] = A.group_stride * 8;
@@ -158,11 +158,13 @@ static void run_polymul_one(const PolymulArgs &F)
     db = da;
     db.base = (unsigned char *)F.b; db.dims[1] = ((size_t)F.b_group_polys << LOGN) >> 4; db.dims[2] = (A.num + F.b_group_polys - 1) / F.b_group_polys;
     db.strides[2] = F.b_group_stride * 8;
+    dout = da; dout.base = (unsigned char *)F.out;
     memcpy(ma.opaque, &da, sizeof da);
     memcpy(mb.opaque, &db, sizeof db);
+    memcpy(mo.opaque, &dout, sizeof dout);
     emu_dim3 g;
     g.x = A.num * (unsigned)((((size_t)1 << LOGN) >> 4) / kContigRows);
-    emu_launch(g, kContigRows, (size_t)kContigRows * 128 * 2 + 1024 + 16, [&] { ntt_contig_polymul<PF, PI, LOGN, FWD, FWD>(ma, mb, F); });
+    emu_launch(g, kContigRows, (size_t)kContigRows * 128 * 2 + 1024 + 16, [&] { ntt_contig_polymul<PF, PI, LOGN, FWD, FWD>(ma, mb, mo, F); });
 }
 template <class PF, class PI, bool FWD>
 static int run_polymul_logn(int logn, const PolymulArgs &F)
@@ -193,7 +195,7 @@ int emu_polymul(int fwd, int lazy, int logn, u64 *a, u64 *b, const u64 *psi, con
     PolymulArgs F{};
     F.A.a = a; F.A.tw = psi; F.A.tws = psi_s; F.A.lc = lc; F.A.num = num; F.A.division = division; F.A.use_tma = 1;
     F.A.group_polys = num; F.A.group_stride = (size_t)num << logn;
-    F.b = b; F.twi = psiinv; F.twis = psiinv_s; F.b_group_polys = num; F.b_group_stride = (size_t)num << logn;
+    F.out = a; F.b = b; F.twi = psiinv; F.twis = psiinv_s; F.b_group_polys = num; F.b_group_stride = (size_t)num << logn;
     int r;
     if (lazy) r = fwd ? run_polymul_logn<ShoupLazyPolicy, ShoupLazyInvPolicy, true>(logn, F) : run_polymul_logn<ShoupLazyPolicy, ShoupLazyInvPolicy, false>(logn, F);
     else r = fwd ? run_polymul_logn<ShoupPolicy, ShoupPolicy, true>(logn, F) : run_polymul_logn<ShoupPolicy, ShoupPolicy, false>(logn, F);

@@ -60,7 +60,7 @@ int launch_fused_mul(bool lazy, unsigned logn, const NttArgsHost &h, const u64 *
                      unsigned items, int nout, cudaStream_t st);
 
 int launch_polymul(bool lazy, unsigned logn, const NttArgsHost &ha, const u64 *twi, const u64 *twis, const u64 *b, unsigned b_group_polys,
-                   size_t b_group_stride, bool fwd, cudaStream_t st);
+                   size_t b_group_stride, bool fwd, u64 *out, cudaStream_t st);
 
 int get_tma_default();
 

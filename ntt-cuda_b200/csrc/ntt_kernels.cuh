@@ -751,7 +751,8 @@ ntt_contig_fused_mul(const __grid_constant__ TensorMap tmap, FusedArgs F)
 // follows.  A_FWD / B_FWD = false: that operand is already in the NTT domain (bit-reversed order, canonical) and is only read --
 // keygen's  INTT(NTT(s) (.) a)  with both operands transformed is the <false, false> instantiation.
 struct PolymulArgs {
-    NttArgs A;                 // operand a (in place: receives the result); forward tables
+    NttArgs A;                 // operand a; forward tables
+    u64 *out;                  // result array, a's group description (== A.a: in place)
     const u64 *b;              // operand b, [num][n], same polynomial order as a; clobbered when B_FWD
     const u64 *twi, *twis;     // inverse tables
     u32 b_group_polys;         // b's own group description (polynomial p of b at (p / gp) * stride + (p % gp) * n)
@@ -760,7 +761,8 @@ struct PolymulArgs {
 
 template <class PF, class PI, int LOGN, bool A_FWD, bool B_FWD>
 __global__ void __launch_bounds__(kContigRows, 4)
-ntt_contig_polymul(const __grid_constant__ TensorMap tmap_a, const __grid_constant__ TensorMap tmap_b, PolymulArgs F)
+ntt_contig_polymul(const __grid_constant__ TensorMap tmap_a, const __grid_constant__ TensorMap tmap_b,
+                   const __grid_constant__ TensorMap tmap_out, PolymulArgs F)
 {
     using SC = Sched<LOGN>;
     constexpr int K1 = SC::K1, K2 = SC::K2, SA = K2 - 4, NC = 16 >> SA, RT = kContigRows;
@@ -783,6 +785,7 @@ ntt_contig_polymul(const __grid_constant__ TensorMap tmap_a, const __grid_consta
     pi.init(Ai, limb, n);
     const int row_a = (int)(idx * (n >> 4) + rip0), row_b = (int)(bidx * (n >> 4) + rip0);
     u64 *ga = A.a + (size_t)grp * A.group_stride + ((size_t)idx << LOGN) + (size_t)rip0 * 16;
+    u64 *go = F.out + (size_t)grp * A.group_stride + ((size_t)idx << LOGN) + (size_t)rip0 * 16;
     const u64 *gb = F.b + (size_t)bgrp * F.b_group_stride + ((size_t)bidx << LOGN) + (size_t)rip0 * 16;
 
     if (A.use_tma & 1u) {
@@ -852,15 +855,15 @@ ntt_contig_polymul(const __grid_constant__ TensorMap tmap_a, const __grid_consta
     if (A.use_tma & 1u) {
 #ifdef NTTB200_EMU
         __syncthreads();
-        if (tid == 0) emu_tma_3d(false, &tmap_a, tile, 0, row_a, (int)grp);
+        if (tid == 0) emu_tma_3d(false, &tmap_out, tile, 0, row_a, (int)grp);
 #else
         fence_proxy_async();
         __syncthreads();
-        if (tid == 0) { tma_store_3d(&tmap_a, tile, 0, row_a, (int)grp); tma_store_commit(); tma_store_wait_read<0>(); }
+        if (tid == 0) { tma_store_3d(&tmap_out, tile, 0, row_a, (int)grp); tma_store_commit(); tma_store_wait_read<0>(); }
 #endif
     } else {
         __syncthreads();
-        tile_copy_coop<true, false>(tile, ga, 16, RT, tid, RT);
+        tile_copy_coop<true, false>(tile, go, 16, RT, tid, RT);
     }
     (void)bar;
 }

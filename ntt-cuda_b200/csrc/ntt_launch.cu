@@ -235,7 +235,7 @@ int launch_fused_mul(bool lazy, unsigned logn, const NttArgsHost &h, const u64 *
 
 // ---- fused polynomial product ----------------------------------------------------------------------------------------------
 template <class PF, class PI, int LOGN, bool A_FWD, bool B_FWD>
-static int launch_polymul_one(const PolymulArgs &F, const CUtensorMap &ma, const CUtensorMap &mb, cudaStream_t st)
+static int launch_polymul_one(const PolymulArgs &F, const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mo, cudaStream_t st)
 {
     constexpr size_t smem = (size_t)kContigRows * 128 * 2 + 1024 + 16;
     static bool attr_done[64] = {false};
@@ -247,27 +247,28 @@ static int launch_polymul_one(const PolymulArgs &F, const CUtensorMap &ma, const
     }
     const unsigned tiles = ((1u << LOGN) >> 4) / kContigRows;
     if ((size_t)F.A.num * tiles >= (1ull << 31)) return NTTB200_EINVAL;
-    ntt_contig_polymul<PF, PI, LOGN, A_FWD, B_FWD><<<F.A.num * tiles, kContigRows, smem, st>>>(ma, mb, F);
+    ntt_contig_polymul<PF, PI, LOGN, A_FWD, B_FWD><<<F.A.num * tiles, kContigRows, smem, st>>>(ma, mb, mo, F);
     return (int)cudaGetLastError();
 }
 template <class PF, class PI, bool A_FWD, bool B_FWD>
-static int launch_polymul_logn(unsigned logn, const PolymulArgs &F, const CUtensorMap &ma, const CUtensorMap &mb, cudaStream_t st)
+static int launch_polymul_logn(unsigned logn, const PolymulArgs &F, const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mo,
+                               cudaStream_t st)
 {
     switch (logn) {
-    case 11: return launch_polymul_one<PF, PI, 11, A_FWD, B_FWD>(F, ma, mb, st);
-    case 12: return launch_polymul_one<PF, PI, 12, A_FWD, B_FWD>(F, ma, mb, st);
-    case 13: return launch_polymul_one<PF, PI, 13, A_FWD, B_FWD>(F, ma, mb, st);
-    case 14: return launch_polymul_one<PF, PI, 14, A_FWD, B_FWD>(F, ma, mb, st);
-    case 15: return launch_polymul_one<PF, PI, 15, A_FWD, B_FWD>(F, ma, mb, st);
-    case 16: return launch_polymul_one<PF, PI, 16, A_FWD, B_FWD>(F, ma, mb, st);
-    case 17: return launch_polymul_one<PF, PI, 17, A_FWD, B_FWD>(F, ma, mb, st);
+    case 11: return launch_polymul_one<PF, PI, 11, A_FWD, B_FWD>(F, ma, mb, mo, st);
+    case 12: return launch_polymul_one<PF, PI, 12, A_FWD, B_FWD>(F, ma, mb, mo, st);
+    case 13: return launch_polymul_one<PF, PI, 13, A_FWD, B_FWD>(F, ma, mb, mo, st);
+    case 14: return launch_polymul_one<PF, PI, 14, A_FWD, B_FWD>(F, ma, mb, mo, st);
+    case 15: return launch_polymul_one<PF, PI, 15, A_FWD, B_FWD>(F, ma, mb, mo, st);
+    case 16: return launch_polymul_one<PF, PI, 16, A_FWD, B_FWD>(F, ma, mb, mo, st);
+    case 17: return launch_polymul_one<PF, PI, 17, A_FWD, B_FWD>(F, ma, mb, mo, st);
     default: return NTTB200_EINVAL;
     }
 }
 // ha: operand a (forward tables, group description); b with its own group description.  a_fwd / b_fwd: the operand still needs
 // its contiguous forward pass (false: it is already in the NTT domain).  Only (true, true) and (false, false) are instantiated.
 int launch_polymul(bool lazy, unsigned logn, const NttArgsHost &ha, const u64 *twi, const u64 *twis, const u64 *b, unsigned b_group_polys,
-                   size_t b_group_stride, bool fwd, cudaStream_t st)
+                   size_t b_group_stride, bool fwd, u64 *out, cudaStream_t st)
 {
     if (logn < 11 || logn > 17 || !ha.a || !b || !ha.num || !ha.division) return NTTB200_EINVAL;
     PolymulArgs F;
@@ -277,22 +278,24 @@ int launch_polymul(bool lazy, unsigned logn, const NttArgsHost &ha, const u64 *t
     A.num = ha.num; A.division = ha.division; A.use_tma = (u32)ha.use_tma; A.pf_dist = 0;
     A.group_polys = ha.group_polys ? ha.group_polys : ha.num;
     A.group_stride = ha.group_polys ? ha.group_stride : ((size_t)ha.num << logn);
-    F.b = b; F.twi = twi; F.twis = twis;
+    F.b = b; F.twi = twi; F.twis = twis; F.out = out ? out : A.a;
     F.b_group_polys = b_group_polys ? b_group_polys : ha.num;
     F.b_group_stride = b_group_polys ? b_group_stride : ((size_t)ha.num << logn);
-    CUtensorMap ma, mb;
+    CUtensorMap ma, mb, mo;
     if (ha.use_tma & 1) {
         int rc = make_tmap_contig(&ma, A.a, logn, A.group_polys, A.group_stride, (ha.num + A.group_polys - 1) / A.group_polys);
+        if (rc) return rc;
+        rc = make_tmap_contig(&mo, F.out, logn, A.group_polys, A.group_stride, (ha.num + A.group_polys - 1) / A.group_polys);
         if (rc) return rc;
         rc = make_tmap_contig(&mb, const_cast<u64 *>(b), logn, F.b_group_polys, F.b_group_stride, (ha.num + F.b_group_polys - 1) / F.b_group_polys);
         if (rc) return rc;
     } else {
-        memset(&ma, 0, sizeof ma); memset(&mb, 0, sizeof mb);
+        memset(&ma, 0, sizeof ma); memset(&mb, 0, sizeof mb); memset(&mo, 0, sizeof mo);
     }
-    if (lazy) return fwd ? launch_polymul_logn<ShoupLazyPolicy, ShoupLazyInvPolicy, true, true>(logn, F, ma, mb, st)
-                         : launch_polymul_logn<ShoupLazyPolicy, ShoupLazyInvPolicy, false, false>(logn, F, ma, mb, st);
-    return fwd ? launch_polymul_logn<ShoupPolicy, ShoupPolicy, true, true>(logn, F, ma, mb, st)
-               : launch_polymul_logn<ShoupPolicy, ShoupPolicy, false, false>(logn, F, ma, mb, st);
+    if (lazy) return fwd ? launch_polymul_logn<ShoupLazyPolicy, ShoupLazyInvPolicy, true, true>(logn, F, ma, mb, mo, st)
+                         : launch_polymul_logn<ShoupLazyPolicy, ShoupLazyInvPolicy, false, false>(logn, F, ma, mb, mo, st);
+    return fwd ? launch_polymul_logn<ShoupPolicy, ShoupPolicy, true, true>(logn, F, ma, mb, mo, st)
+               : launch_polymul_logn<ShoupPolicy, ShoupPolicy, false, false>(logn, F, ma, mb, mo, st);
 }
 
 }  // namespace nttb200
@@ -337,7 +340,7 @@ int nttb200_poly_mul_batch(const nttb200_ctx *ctx, nttb200_u64 *a, nttb200_u64 *
     NttArgsHost hb = ha; hb.a = b;
     int r = launch_ntt_pass(false, pol, ctx->logn, ha, 0, st);
     if (!r) r = launch_ntt_pass(false, pol, ctx->logn, hb, 0, st);
-    if (!r) r = launch_polymul(ctx->lazy_ok != 0, ctx->logn, ha, ctx->psiinv, ctx->psiinv_s, b, 0, 0, true, st);
+    if (!r) r = launch_polymul(ctx->lazy_ok != 0, ctx->logn, ha, ctx->psiinv, ctx->psiinv_s, b, 0, 0, true, nullptr, st);
     NttArgsHost hi{a, ctx->psiinv, ctx->psiinv_s, ctx->lc, nullptr, nullptr, nullptr, 0, 0, 0, num, division, ctx->use_tma};
     if (!r) r = launch_ntt_pass(true, pol, ctx->logn, hi, 1, st);
     return r;
@@ -352,7 +355,7 @@ int nttb200_ntt_domain_mul_inverse_batch(const nttb200_ctx *ctx, nttb200_u64 *a,
     const int pol = ctx->lazy_ok ? kPolicyShoupLazy : kPolicyShoup;
     cudaStream_t st = (cudaStream_t)stream;
     NttArgsHost ha{a, ctx->psi, ctx->psi_s, ctx->lc, nullptr, nullptr, nullptr, 0, 0, 0, num, division, ctx->use_tma};
-    int r = launch_polymul(ctx->lazy_ok != 0, ctx->logn, ha, ctx->psiinv, ctx->psiinv_s, b, 0, 0, false, st);
+    int r = launch_polymul(ctx->lazy_ok != 0, ctx->logn, ha, ctx->psiinv, ctx->psiinv_s, b, 0, 0, false, nullptr, st);
     NttArgsHost hi{a, ctx->psiinv, ctx->psiinv_s, ctx->lc, nullptr, nullptr, nullptr, 0, 0, 0, num, division, ctx->use_tma};
     if (!r) r = launch_ntt_pass(true, pol, ctx->logn, hi, 1, st);
     return r;
