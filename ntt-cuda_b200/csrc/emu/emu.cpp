@@ -75,11 +75,12 @@ static void run_one(const NttArgs &A)
     static_assert(sizeof(EmuTmapDesc) <= sizeof(TensorMap), "descriptor stub too small");
     memcpy(ms.opaque, &ds, sizeof ds);
     memcpy(mc.opaque, &dc, sizeof dc);
-    const unsigned tiles_s = (unsigned)(((n >> SC::K1) >> 4) / SC::NT), tiles_c = (unsigned)((n >> 4) / kContigRows);
+    const unsigned tiles_s1 = (unsigned)(((n >> SC::K1) >> 4) / SC::NT), tiles_c1 = (unsigned)((n >> 4) / kContigRows);
+    const int tpc_s = tiles_per_cta(tiles_s1), tpc_c = tiles_per_cta(tiles_c1);
     emu_dim3 gs, gc;
-    gs.x = A.num * tiles_s;
-    gc.x = A.num * tiles_c;
-    const size_t smem_s = (size_t)SC::NT * R * 128 + 1024 + 16, smem_c = (size_t)kContigRows * 128 + 1024 + 16;
+    gs.x = A.num * (tiles_s1 / tpc_s);
+    gc.x = A.num * (tiles_c1 / tpc_c);
+    const size_t smem_s = (size_t)tpc_s * SC::NT * R * 128 + 1024 + 64, smem_c = (size_t)tpc_c * kContigRows * 128 + 1024 + 64;
     auto strided = [&] { emu_launch(gs, R * SC::NT, smem_s, [&] { ntt_strided_pass<P, LOGN, INV>(ms, A); }); };
     auto contig = [&] { emu_launch(gc, kContigRows, smem_c, [&] { ntt_contig_pass<P, LOGN, INV>(mc, A); }); };
     if (!INV) { if (g_which != 1) strided(); if (g_which != 0) contig(); } else { if (g_which != 1) contig(); if (g_which != 0) strided(); }

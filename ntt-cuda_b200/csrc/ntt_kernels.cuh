@@ -430,7 +430,16 @@ __device__ __forceinline__ u64 *align_1024(unsigned char *p)
 #endif
 }
 
-// ---- pass "strided": grid (num * tiles), tiles = n / 2^K1 / 16 / NT column tiles per polynomial; 2^K1 * NT threads ------------------------------------------
+// Tiles a CTA processes back to back, all of the SAME polynomial (same limb constants, same table base), every tile's TMA load
+// issued up front into its own buffer.  Measured on the B200 at n = 2^15 (profiles/r01_experiments.md): 2 tiles per CTA is 7 %
+// SLOWER than 1 -- the doubled shared-memory carve-out (200 KB per SM) leaves ~28 KB of L1 for the twiddle lines, and their
+// misses cost more than the hidden tile latency gains.  Kept as a build-time knob; the product uses 1.
+#ifndef NTT_TPC
+#define NTT_TPC 1
+#endif
+__host__ __device__ constexpr int tiles_per_cta(u32 tiles_per_poly) { return tiles_per_poly % NTT_TPC == 0 ? NTT_TPC : 1; }
+
+// ---- pass "strided": grid (num * tiles / TPC), tiles = n / 2^K1 / 16 / NT column tiles per polynomial; 2^K1 * NT threads ----------------------
 template <class P, int LOGN, bool INV>
 __global__ void __launch_bounds__((1 << Sched<LOGN>::K1) * Sched<LOGN>::NT, ((1 << Sched<LOGN>::K1) * Sched<LOGN>::NT) > 256 ? 2 : NTT_MINB_S)
 ntt_strided_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
@@ -439,16 +448,19 @@ ntt_strided_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
     constexpr int K1 = SC::K1, R = 1 << K1, NT = SC::NT, THREADS = R * NT;
     constexpr u32 n = 1u << LOGN, C = n >> K1;          // C columns per row
     constexpr int RB = R > 256 ? 256 : R;               // TMA box rows (box dims are capped at 256)
-    NTT_DYN_SMEM(raw);
-    u64 *tiles = align_1024(raw);
-    u64 *bar = tiles + (size_t)NT * R * 16;
     constexpr u32 TILES = (C >> 4) / NT;
-    const u32 tid = threadIdx.x, p = blockIdx.x / TILES;
-    const u32 col0 = (blockIdx.x % TILES) * (NT * 16);
+    constexpr int TPC = tiles_per_cta(TILES);
+    constexpr u32 TG = TILES / TPC;                     // CTAs per polynomial
+    constexpr size_t TILE_ELEMS = (size_t)NT * R * 16;
+    NTT_DYN_SMEM(raw);
+    u64 *tiles0 = align_1024(raw);
+    u64 *bar = tiles0 + TPC * TILE_ELEMS;
+    const u32 tid = threadIdx.x, p = blockIdx.x / TG;
+    const u32 colbase = (blockIdx.x % TG) * (TPC * NT * 16);
     const u32 grp = p / A.group_polys, idx = p - grp * A.group_polys;   // polynomial idx of group grp
     P pol;
     pol.init(A, p % A.division, n);
-    u64 *g = A.a + (size_t)grp * A.group_stride + ((size_t)idx << LOGN) + col0;
+    u64 *g = A.a + (size_t)grp * A.group_stride + ((size_t)idx << LOGN) + colbase;
     {   // twiddle lines of every round of this thread, requested before the tile wait so they arrive under it
         const u32 uu = tid & (R - 1);
         if constexpr (SC::S2 != 0) prefetch_round<SC::S2>(pol, (1u << SC::S1) + ((uu >> SC::S2) >> (K1 - SC::S1 - SC::S2)));
@@ -457,82 +469,99 @@ ntt_strided_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
     }
 
     const bool dbg_nocompute = (A.use_tma & 2u) != 0, dbg_nomem = (A.use_tma & 4u) != 0;
+    const bool tma = (A.use_tma & 1u) != 0;
     if (dbg_nomem) {
         __syncthreads();
-    } else if (A.use_tma & 1u) {
+    } else if (tma) {
 #ifdef NTTB200_EMU
         if (tid == 0)
-            for (int k = 0; k < NT; k++)
-                for (int rc = 0; rc < R / RB; rc++)
-                    emu_tma_4d(true, &tmap, tiles + ((size_t)k * R + rc * RB) * 16, (int)col0 + k * 16, rc * RB, (int)idx, (int)grp);
+            for (int tt = 0; tt < TPC; tt++)
+                for (int k = 0; k < NT; k++)
+                    for (int rc = 0; rc < R / RB; rc++)
+                        emu_tma_4d(true, &tmap, tiles0 + tt * TILE_ELEMS + ((size_t)k * R + rc * RB) * 16, (int)colbase + (tt * NT + k) * 16, rc * RB,
+                                   (int)idx, (int)grp);
         __syncthreads();
 #else
-        if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+        if (tid == 0) {
+            for (int tt = 0; tt < TPC; tt++) mbar_init(bar + tt, 1);
+            fence_mbar_init();
+        }
         __syncthreads();
         if (tid == 0) {
-            mbar_expect_tx(bar, (u32)(NT * R * 128));
-            for (int k = 0; k < NT; k++)
-                for (int rc = 0; rc < R / RB; rc++)
-                    tma_load_4d(tiles + ((size_t)k * R + rc * RB) * 16, &tmap, bar, (int)col0 + k * 16, rc * RB, (int)idx, (int)grp);
+            for (int tt = 0; tt < TPC; tt++) {
+                mbar_expect_tx(bar + tt, (u32)(NT * R * 128));
+                for (int k = 0; k < NT; k++)
+                    for (int rc = 0; rc < R / RB; rc++)
+                        tma_load_4d(tiles0 + tt * TILE_ELEMS + ((size_t)k * R + rc * RB) * 16, &tmap, bar + tt, (int)colbase + (tt * NT + k) * 16,
+                                    rc * RB, (int)idx, (int)grp);
+            }
             const u32 fb = blockIdx.x + A.pf_dist;           // the CTA that will run here about one wave later
             if (A.pf_dist != 0 && fb < gridDim.x) {
-                const u32 fp = fb / TILES, fcol = (fb % TILES) * (NT * 16);
+                const u32 fp = fb / TG, fcol = (fb % TG) * (TPC * NT * 16);
                 const u32 fgrp = fp / A.group_polys, fidx = fp - fgrp * A.group_polys;
-                for (int k = 0; k < NT; k++)
+                for (int k = 0; k < TPC * NT; k++)
                     for (int rc = 0; rc < R / RB; rc++) tma_prefetch_4d(&tmap, (int)fcol + k * 16, rc * RB, (int)fidx, (int)fgrp);
             }
         }
-        mbar_wait(bar, 0);
 #endif
     } else {
-        for (int k = 0; k < NT; k++) tile_copy_coop<false, true>(tiles + (size_t)k * R * 16, g + k * 16, C, R, tid, THREADS);
+        for (int k = 0; k < TPC * NT; k++) tile_copy_coop<false, true>(tiles0 + (size_t)k * R * 16, g + k * 16, C, R, tid, THREADS);
         __syncthreads();
     }
 
-    u64 *tile = tiles + (size_t)(tid >> K1) * R * 16;
     const u32 u = tid & (R - 1);
-    if (dbg_nocompute) {
-    } else if (!INV) {
-        strided_round<P, K1, 0, SC::S1, false>(tile, u, pol);
+#pragma unroll 1
+    for (int tt = 0; tt < TPC; tt++) {
+        u64 *tiles = tiles0 + tt * TILE_ELEMS;
+        u64 *tile = tiles + (size_t)(tid >> K1) * R * 16;
+#ifndef NTTB200_EMU
+        if (!dbg_nomem && tma) mbar_wait(bar + tt, 0);
+#endif
+        if (dbg_nocompute) {
+        } else if (!INV) {
+            strided_round<P, K1, 0, SC::S1, false>(tile, u, pol);
 #ifdef NTT_DBG_NOBAR   /* profiling only (wrong results): no CTA barrier between the rounds */
-        if constexpr (SC::S2 != 0) { __syncwarp(); strided_round<P, K1, SC::S1, SC::S2, false>(tile, u, pol); }
+            if constexpr (SC::S2 != 0) { __syncwarp(); strided_round<P, K1, SC::S1, SC::S2, false>(tile, u, pol); }
 #else
-        if constexpr (SC::S2 != 0) { __syncthreads(); strided_round<P, K1, SC::S1, SC::S2, false>(tile, u, pol); }
+            if constexpr (SC::S2 != 0) { __syncthreads(); strided_round<P, K1, SC::S1, SC::S2, false>(tile, u, pol); }
 #endif
-        if constexpr (SC::S3 != 0) { __syncthreads(); strided_round<P, K1, SC::S1 + SC::S2, SC::S3, false>(tile, u, pol); }
-    } else {
-        if constexpr (SC::S3 != 0) { strided_round<P, K1, SC::S1 + SC::S2, SC::S3, true>(tile, u, pol); __syncthreads(); }
-        if constexpr (SC::S2 != 0) { strided_round<P, K1, SC::S1, SC::S2, true>(tile, u, pol); __syncthreads(); }
-        strided_round<P, K1, 0, SC::S1, true>(tile, u, pol);
-    }
-
-    if (dbg_nomem) {
-    } else if (A.use_tma & 1u) {
-#ifdef NTTB200_EMU
-        __syncthreads();
-        if (tid == 0)
-            for (int k = 0; k < NT; k++)
-                for (int rc = 0; rc < R / RB; rc++)
-                    emu_tma_4d(false, &tmap, tiles + ((size_t)k * R + rc * RB) * 16, (int)col0 + k * 16, rc * RB, (int)idx, (int)grp);
-#else
-        fence_proxy_async();
-        __syncthreads();
-        if (tid == 0) {
-            for (int k = 0; k < NT; k++)
-                for (int rc = 0; rc < R / RB; rc++)
-                    tma_store_4d(&tmap, tiles + ((size_t)k * R + rc * RB) * 16, (int)col0 + k * 16, rc * RB, (int)idx, (int)grp);
-            tma_store_commit();
-            tma_store_wait_read<0>();
+            if constexpr (SC::S3 != 0) { __syncthreads(); strided_round<P, K1, SC::S1 + SC::S2, SC::S3, false>(tile, u, pol); }
+        } else {
+            if constexpr (SC::S3 != 0) { strided_round<P, K1, SC::S1 + SC::S2, SC::S3, true>(tile, u, pol); __syncthreads(); }
+            if constexpr (SC::S2 != 0) { strided_round<P, K1, SC::S1, SC::S2, true>(tile, u, pol); __syncthreads(); }
+            strided_round<P, K1, 0, SC::S1, true>(tile, u, pol);
         }
+
+        if (dbg_nomem) {
+        } else if (tma) {
+#ifdef NTTB200_EMU
+            __syncthreads();
+            if (tid == 0)
+                for (int k = 0; k < NT; k++)
+                    for (int rc = 0; rc < R / RB; rc++)
+                        emu_tma_4d(false, &tmap, tiles + ((size_t)k * R + rc * RB) * 16, (int)colbase + (tt * NT + k) * 16, rc * RB, (int)idx, (int)grp);
+#else
+            fence_proxy_async();
+            __syncthreads();
+            if (tid == 0) {
+                for (int k = 0; k < NT; k++)
+                    for (int rc = 0; rc < R / RB; rc++)
+                        tma_store_4d(&tmap, tiles + ((size_t)k * R + rc * RB) * 16, (int)colbase + (tt * NT + k) * 16, rc * RB, (int)idx, (int)grp);
+                tma_store_commit();
+            }
 #endif
-    } else {
-        __syncthreads();
-        for (int k = 0; k < NT; k++) tile_copy_coop<false, false>(tiles + (size_t)k * R * 16, g + k * 16, C, R, tid, THREADS);
+        } else {
+            __syncthreads();
+            for (int k = 0; k < NT; k++) tile_copy_coop<false, false>(tiles + (size_t)k * R * 16, g + (tt * NT + k) * 16, C, R, tid, THREADS);
+        }
     }
+#ifndef NTTB200_EMU
+    if (!dbg_nomem && tma && tid == 0) tma_store_wait_read<0>();
+#endif
     (void)bar;
 }
 
-// ---- pass "contig": grid (num * n / 16 / 128), 128 threads; CTA = 128 consecutive rows of one polynomial ------------------------------------------------------
+// ---- pass "contig": grid (num * n / 16 / 128 / TPC), 128 threads; CTA = TPC x 128 consecutive rows of one polynomial ---------------------------------
 template <class P, int LOGN, bool INV>
 __global__ void __launch_bounds__(kContigRows, Sched<LOGN>::K2 == 8 ? 4 : NTT_MINB_C)   // radix-16 first round needs > 80 registers
 ntt_contig_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
@@ -540,87 +569,111 @@ ntt_contig_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
     using SC = Sched<LOGN>;
     constexpr int K1 = SC::K1, K2 = SC::K2, SA = K2 - 4, NC = 16 >> SA, RT = kContigRows;
     constexpr u32 n = 1u << LOGN;
-    NTT_DYN_SMEM(raw);
-    u64 *tile = align_1024(raw);
-    u64 *bar = tile + (size_t)RT * 16;
-    const u32 tid = threadIdx.x;
     constexpr u32 TILES = (n >> 4) / RT;
-    const u32 p = blockIdx.x / TILES;
-    const u32 rip0 = (blockIdx.x % TILES) * RT;          // first row (of 16 coefficients) inside the polynomial
+    constexpr int TPC = tiles_per_cta(TILES);
+    constexpr u32 TG = TILES / TPC;
+    NTT_DYN_SMEM(raw);
+    u64 *tile0 = align_1024(raw);
+    u64 *bar = tile0 + (size_t)TPC * RT * 16;
+    const u32 tid = threadIdx.x;
+    const u32 p = blockIdx.x / TG;
+    const u32 ripbase = (blockIdx.x % TG) * (TPC * RT);      // first row (of 16 coefficients) inside the polynomial
     const u32 grp = p / A.group_polys, idx = p - grp * A.group_polys;
-    const int grow = (int)(idx * (n >> 4) + rip0);       // row inside the group
+    const int growbase = (int)(idx * (n >> 4) + ripbase);    // row inside the group
     P pol;
     pol.init(A, p % A.division, n);
-    u64 *g = A.a + (size_t)grp * A.group_stride + ((size_t)idx << LOGN) + (size_t)rip0 * 16;
-    prefetch_round<4>(pol, (n >> 4) + rip0 + tid);
-    prefetch_round<SA>(pol, (1u << K1) + (rip0 >> SA) + (tid >> SA));
+    u64 *g = A.a + (size_t)grp * A.group_stride + ((size_t)idx << LOGN) + (size_t)ripbase * 16;
+    prefetch_round<4>(pol, (n >> 4) + ripbase + tid);
+    prefetch_round<SA>(pol, (1u << K1) + (ripbase >> SA) + (tid >> SA));
 
     const bool dbg_nocompute = (A.use_tma & 2u) != 0, dbg_nomem = (A.use_tma & 4u) != 0;
+    const bool tma = (A.use_tma & 1u) != 0;
     if (dbg_nomem) {
         __syncthreads();
-    } else if (A.use_tma & 1u) {
+    } else if (tma) {
 #ifdef NTTB200_EMU
-        if (tid == 0) emu_tma_3d(true, &tmap, tile, 0, grow, (int)grp);
+        if (tid == 0)
+            for (int tt = 0; tt < TPC; tt++) emu_tma_3d(true, &tmap, tile0 + (size_t)tt * RT * 16, 0, growbase + tt * RT, (int)grp);
         __syncthreads();
 #else
-        if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+        if (tid == 0) {
+            for (int tt = 0; tt < TPC; tt++) mbar_init(bar + tt, 1);
+            fence_mbar_init();
+        }
         __syncthreads();
         if (tid == 0) {
-            mbar_expect_tx(bar, (u32)(RT * 128));
-            tma_load_3d(tile, &tmap, bar, 0, grow, (int)grp);
+            for (int tt = 0; tt < TPC; tt++) {
+                mbar_expect_tx(bar + tt, (u32)(RT * 128));
+                tma_load_3d(tile0 + (size_t)tt * RT * 16, &tmap, bar + tt, 0, growbase + tt * RT, (int)grp);
+            }
             const u32 fb = blockIdx.x + A.pf_dist;
             if (A.pf_dist != 0 && fb < gridDim.x) {
-                const u32 fp = fb / TILES, frip = (fb % TILES) * RT;
+                const u32 fp = fb / TG, frip = (fb % TG) * (TPC * RT);
                 const u32 fgrp = fp / A.group_polys, fidx = fp - fgrp * A.group_polys;
-                tma_prefetch_3d(&tmap, 0, (int)(fidx * (n >> 4) + frip), (int)fgrp);
+                for (int tt = 0; tt < TPC; tt++) tma_prefetch_3d(&tmap, 0, (int)(fidx * (n >> 4) + frip) + tt * RT, (int)fgrp);
             }
         }
-        mbar_wait(bar, 0);
 #endif
     } else {
-        tile_copy_coop<true, true>(tile, g, 16, RT, tid, RT);
+        tile_copy_coop<true, true>(tile0, g, 16, TPC * RT, tid, RT);
         __syncthreads();
     }
 
     const u32 t = tid & ((1u << SA) - 1u), bl = tid >> SA;     // lane-in-block, block-in-tile
-    const u32 twA = (1u << K1) + (rip0 >> SA) + bl;            // block index inside the polynomial
-    const u32 twB = (n >> 4) + rip0 + tid;                     // row index inside the polynomial
-    u64 v[16];
-    if (dbg_nocompute) {
-    } else if (!INV) {
-        regs_rows<SA, true, true>(tile, bl << SA, 0, t * NC, v);
-        ct_stages<SA, NC>(v, twA, pol);
-        regs_rows<SA, true, false>(tile, bl << SA, 0, t * NC, v);
-        __syncwarp();
-        regs_row<true, true>(tile, tid, v);
-        ct_stages<4, 1>(v, twB, pol);
-        NTT_UNROLL
-        for (int i = 0; i < 16; i++) v[i] = pol.fwd_final(v[i]);
-        regs_row<true, false>(tile, tid, v);
-    } else {
-        regs_row<true, true>(tile, tid, v);
-        gs_stages<4, 1, false>(v, twB, pol);
-        regs_row<true, false>(tile, tid, v);
-        __syncwarp();
-        regs_rows<SA, true, true>(tile, bl << SA, 0, t * NC, v);
-        gs_stages<SA, NC, false>(v, twA, pol);
-        regs_rows<SA, true, false>(tile, bl << SA, 0, t * NC, v);
-    }
-
-    if (dbg_nomem) {
-    } else if (A.use_tma & 1u) {
-#ifdef NTTB200_EMU
-        __syncthreads();
-        if (tid == 0) emu_tma_3d(false, &tmap, tile, 0, grow, (int)grp);
-#else
-        fence_proxy_async();
-        __syncthreads();
-        if (tid == 0) { tma_store_3d(&tmap, tile, 0, grow, (int)grp); tma_store_commit(); tma_store_wait_read<0>(); }
+#pragma unroll 1
+    for (int tt = 0; tt < TPC; tt++) {
+        u64 *tile = tile0 + (size_t)tt * RT * 16;
+        const u32 rip0 = ripbase + tt * RT;
+        const u32 twA = (1u << K1) + (rip0 >> SA) + bl;            // block index inside the polynomial
+        const u32 twB = (n >> 4) + rip0 + tid;                     // row index inside the polynomial
+        if (tt + 1 < TPC) {                                        // next tile's twiddle lines
+            prefetch_round<4>(pol, twB + RT);
+            prefetch_round<SA>(pol, twA + (RT >> SA));
+        }
+#ifndef NTTB200_EMU
+        if (!dbg_nomem && tma) mbar_wait(bar + tt, 0);
 #endif
-    } else {
-        __syncthreads();
-        tile_copy_coop<true, false>(tile, g, 16, RT, tid, RT);
+        u64 v[16];
+        if (dbg_nocompute) {
+        } else if (!INV) {
+            regs_rows<SA, true, true>(tile, bl << SA, 0, t * NC, v);
+            ct_stages<SA, NC>(v, twA, pol);
+            regs_rows<SA, true, false>(tile, bl << SA, 0, t * NC, v);
+            __syncwarp();
+            regs_row<true, true>(tile, tid, v);
+            ct_stages<4, 1>(v, twB, pol);
+            NTT_UNROLL
+            for (int i = 0; i < 16; i++) v[i] = pol.fwd_final(v[i]);
+            regs_row<true, false>(tile, tid, v);
+        } else {
+            regs_row<true, true>(tile, tid, v);
+            gs_stages<4, 1, false>(v, twB, pol);
+            regs_row<true, false>(tile, tid, v);
+            __syncwarp();
+            regs_rows<SA, true, true>(tile, bl << SA, 0, t * NC, v);
+            gs_stages<SA, NC, false>(v, twA, pol);
+            regs_rows<SA, true, false>(tile, bl << SA, 0, t * NC, v);
+        }
+
+        if (dbg_nomem) {
+        } else if (tma) {
+#ifdef NTTB200_EMU
+            __syncthreads();
+            if (tid == 0) emu_tma_3d(false, &tmap, tile, 0, growbase + tt * RT, (int)grp);
+#else
+            fence_proxy_async();
+            __syncthreads();
+            if (tid == 0) { tma_store_3d(&tmap, tile, 0, growbase + tt * RT, (int)grp); tma_store_commit(); }
+#endif
+        }
     }
+    if (!dbg_nomem && !tma) {
+        __syncthreads();
+        tile_copy_coop<true, false>(tile0, g, 16, TPC * RT, tid, RT);
+    }
+#ifndef NTTB200_EMU
+    if (!dbg_nomem && tma && tid == 0) tma_store_wait_read<0>();
+#endif
     (void)bar;
 }
 

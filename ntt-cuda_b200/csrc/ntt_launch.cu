@@ -80,8 +80,10 @@ static int launch_one(const NttArgs &A, int which, unsigned cnt, const CUtensorM
 {
     using SC = Sched<LOGN>;
     constexpr int R = 1 << SC::K1;
-    constexpr size_t smem_s = (size_t)SC::NT * R * 128 + 1024 + 16;
-    constexpr size_t smem_c = (size_t)kContigRows * 128 + 1024 + 16;
+    constexpr unsigned tiles_s1 = (((1u << LOGN) >> SC::K1) >> 4) / SC::NT, tiles_c1 = ((1u << LOGN) >> 4) / kContigRows;
+    constexpr int tpc_s = tiles_per_cta(tiles_s1), tpc_c = tiles_per_cta(tiles_c1);
+    constexpr size_t smem_s = (size_t)tpc_s * SC::NT * R * 128 + 1024 + 64;
+    constexpr size_t smem_c = (size_t)tpc_c * kContigRows * 128 + 1024 + 64;
     // the dynamic shared-memory opt-in is a per-device function attribute: remember it per (instantiation, device)
     static bool attr_done[64] = {false};
     int dev = 0;
@@ -91,7 +93,7 @@ static int launch_one(const NttArgs &A, int which, unsigned cnt, const CUtensorM
         NTTB200_CHECK(cudaFuncSetAttribute(ntt_contig_pass<P, LOGN, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
         if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
-    const unsigned tiles_s = (((1u << LOGN) >> SC::K1) >> 4) / SC::NT, tiles_c = ((1u << LOGN) >> 4) / kContigRows;
+    const unsigned tiles_s = tiles_s1 / tpc_s, tiles_c = tiles_c1 / tpc_c;       // CTAs per polynomial
     if ((size_t)cnt * tiles_c >= (1ull << 31)) return NTTB200_EINVAL;
     const dim3 gs(cnt * tiles_s);
     const dim3 gc(cnt * tiles_c);
