@@ -191,14 +191,48 @@ def bfv_throughput(nttb200, params, torch, world, dist, batch=64, reps=5):
         c.copy_(keep)
         bfv.decrypt(out, c, sk, batch=batch)
 
-    dec_ms = timed(dec) - timed(lambda: c.copy_(keep))
+    copy_ms = timed(lambda: c.copy_(keep))
+    dec_ms = timed(dec) - copy_ms
     ok = bool(torch.equal(out, m))
+    # keys loaded into the context once (nttb200_bfv_load_keys): the fused NTT (.) key -> INTT kernels
+    bfv.load_keys(sk, pk)
+    enc_l = timed(lambda: bfv.encrypt(c, None, m, batch=batch))
+    keep.copy_(c)
+
+    def dec_loaded():
+        c.copy_(keep)
+        bfv.decrypt(out, c, None, batch=batch)
+
+    dec_l = timed(dec_loaded) - copy_ms
+    ok = ok and bool(torch.equal(out, m))
     bfv.close()
     if not ok:
         raise SystemExit("bench.py: BFV round trip failed")
     return {"workload": "BFV encrypt + decrypt, n=32768, 16-limb q (demo.cu), t=1024, batch %d per GPU" % batch,
+            "loaded_keys": {"enc_plus_dec_per_s": world * batch / ((enc_l + dec_l) * 1e-3), "encrypt_per_s": world * batch / (enc_l * 1e-3),
+                            "decrypt_per_s": world * batch / (dec_l * 1e-3), "api": "nttb200_bfv_load_keys + encrypt / decrypt with NULL key"},
             "enc_plus_dec_per_s": world * batch / ((enc + dec_ms) * 1e-3), "encrypt_per_s": world * batch / (enc * 1e-3),
             "decrypt_per_s": world * batch / (dec_ms * 1e-3), "unit": "ops/s", "roundtrip_ok": ok}
+
+
+def ncu_numbers(kernel):
+    """(dram traffic per launch, fma-heavy pipe record) of `kernel` (forward, C2 workload) from the committed ncu --set full
+    summary profiles/r01_final_pipe_util.json (scripts/ncu_summary.py); fallbacks are the values of the earlier capture."""
+    traffic = {"ntt_strided_pass": 484.5e6, "ntt_contig_pass": 493.4e6}[kernel]
+    rec = None
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r01_final_pipe_util.json")))
+        for name, m in d.items():
+            if kernel in name and "ShoupLazyPolicy" in name and ", 0>" in name.replace("(bool)", ""):
+                traffic = m.get("traffic_bytes", traffic)
+                f = m.get("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed")
+                if f is not None:
+                    rec = {"bound": "fma-heavy (IMAD/IMAD.WIDE) pipe", "frac": f / 100.0,
+                           "metric": "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed", "kernel": kernel,
+                           "source": "profiles/r01_final_ncu_full_summary.md (ncu --set full of this command; not a live number)"}
+    except (OSError, ValueError):
+        pass
+    return traffic, rec
 
 
 def reference_gpu_rebuilt():
@@ -330,7 +364,7 @@ def run_ours(args):
         dom, dom_ms = ("ntt_strided_pass", p1) if p1 >= p2 else ("ntt_contig_pass", p2)
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this workload
         # (profiles/r01z_ncu_full_summary.md); below the algorithmic 536.9 MB because write-back still sits in L2 at kernel end
-        ncu_traffic = {"ntt_strided_pass": 484.5e6, "ntt_contig_pass": 493.4e6}[dom]
+        ncu_traffic, int_pipe = ncu_numbers(dom)
         ach = alg_bytes / (dom_ms * 1e-3) / 1e9
         butterflies = POLYS * (n // 2) * 15
         cb = None
@@ -350,6 +384,9 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": ncu_traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": dom_ms},
+            # the pipe that actually binds these kernels: ncu's own utilisation counter of the fma-heavy
+            # (IMAD / IMAD.WIDE) pipe for the same kernel and workload, from the committed --set full capture (not measured live)
+            "roofline_int_pipe": int_pipe,
             "kernels_ms": {"ntt_strided_pass": p1, "ntt_contig_pass": p2},
             "hbm_gbs_whole_step": 2 * alg_bytes / ((p1 + p2) * 1e-3) / 1e9,
             "butterflies_per_s": butterflies * args.steps / (ms_total * 1e-3) * world,

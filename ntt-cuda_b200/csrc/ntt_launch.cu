@@ -91,6 +91,10 @@ static int launch_one(const NttArgs &A, int which, unsigned cnt, const CUtensorM
     if (dev < 0 || dev >= 64 || !attr_done[dev]) {
         NTTB200_CHECK(cudaFuncSetAttribute(ntt_strided_pass<P, LOGN, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
         NTTB200_CHECK(cudaFuncSetAttribute(ntt_contig_pass<P, LOGN, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+        if (const char *e = getenv("NTTB200_CARVEOUT")) {      // tuning hook: shared-memory carve-out in percent (rest of the 228 KB is L1)
+            cudaFuncSetAttribute(ntt_strided_pass<P, LOGN, INV>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
+            cudaFuncSetAttribute(ntt_contig_pass<P, LOGN, INV>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
+        }
         if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
     const unsigned tiles_s = tiles_s1 / tpc_s, tiles_c = tiles_c1 / tpc_c;       // CTAs per polynomial
