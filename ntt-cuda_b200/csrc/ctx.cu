@@ -182,9 +182,9 @@ static int host_pipeline(nttb200_ctx *c, bool inverse, const u64 *in, u64 *out, 
 {
     if (!c || !in || !out || division == 0 || division > c->limbs) return NTTB200_EINVAL;
     if (num == 0) return 0;
-    // chunk = a multiple of `division` polynomials, about 16 MiB (NTTB200_E2E_CHUNK_MB overrides, for tuning)
+    // chunk = a multiple of `division` polynomials, about 32 MiB (NTTB200_E2E_CHUNK_MB overrides, for tuning)
     static size_t chunk_mb = 0;
-    if (!chunk_mb) { const char *e = getenv("NTTB200_E2E_CHUNK_MB"); chunk_mb = e && atoi(e) > 0 ? (size_t)atoi(e) : 16; }
+    if (!chunk_mb) { const char *e = getenv("NTTB200_E2E_CHUNK_MB"); chunk_mb = e && atoi(e) > 0 ? (size_t)atoi(e) : 32; }
     size_t per = (chunk_mb << 20) / ((size_t)c->n * 8);
     per = per / division * division;
     if (per == 0) per = division;
@@ -197,9 +197,23 @@ static int host_pipeline(nttb200_ctx *c, bool inverse, const u64 *in, u64 *out, 
         }
         c->stage_bytes = bytes;
     }
+    // chunk schedule: full chunks in the middle, a geometric ramp (per/4, per/2) at both ends so that the first H2D and the last
+    // D2H -- the only copies with nothing to overlap -- are short
+    std::vector<size_t> sizes;
+    {
+        size_t left = num;
+        auto rounded = [&](size_t v) { v = v / division * division; return v ? v : (size_t)division; };
+        const size_t ramp[2] = {rounded(per / 4), rounded(per / 2)};
+        std::vector<size_t> head, tail;
+        for (int i = 0; i < 2 && left > 2 * per; i++) { head.push_back(ramp[i]); tail.push_back(ramp[i]); left -= 2 * ramp[i]; }
+        sizes = head;
+        while (left) { const size_t cnt = left < per ? left : per; sizes.push_back(cnt); left -= cnt; }
+        for (size_t i = tail.size(); i-- > 0;) sizes.push_back(tail[i]);
+    }
     int k = 0;
-    for (size_t p0 = 0; p0 < num; p0 += per, k = (k + 1) % nttb200_ctx::kStages) {
-        const unsigned cnt = (unsigned)((num - p0) < per ? (num - p0) : per);
+    size_t p0 = 0;
+    for (size_t ci = 0; ci < sizes.size(); p0 += sizes[ci], ci++, k = (k + 1) % nttb200_ctx::kStages) {
+        const unsigned cnt = (unsigned)sizes[ci];
         cudaStream_t st = c->streams[k];
         u64 *d = c->stage_dev[k];
         NTTB200_CHECK(cudaMemcpyAsync(d, in + p0 * c->n, (size_t)cnt * c->n * 8, cudaMemcpyHostToDevice, st));
