@@ -188,6 +188,13 @@ NTTB200_API int nttb200_bfv_encrypt(nttb200_bfv *bfv, nttb200_u64 *c, const nttb
 NTTB200_API int nttb200_bfv_decrypt(nttb200_bfv *bfv, nttb200_u64 *m_out, nttb200_u64 *c, const nttb200_u64 *sk, int sk_per_item,
                                     unsigned batch, void *stream);
 
+/* Homomorphic operations on ciphertexts in the reference layout (the reference stops at decryption):
+ * c_a <- c_a + c_b  (Dec = m_a + m_b mod t), and  c <- c * p  for a plaintext polynomial p[n] or p[batch][n]
+ * (Dec = m * p mod (X^n + 1, t); coefficients of p are taken mod t and lifted centred).  The padding limb is left alone. */
+NTTB200_API int nttb200_bfv_add(nttb200_bfv *bfv, nttb200_u64 *c_a, const nttb200_u64 *c_b, unsigned batch, void *stream);
+NTTB200_API int nttb200_bfv_mul_plain(nttb200_bfv *bfv, nttb200_u64 *c, const nttb200_u64 *p_poly, int plain_per_item, unsigned batch,
+                                      void *stream);
+
 /* Limb-sharded encryption needs no extra entry point: create a context for the sub-ring {owned limbs..., last limb}
  * and call nttb200_bfv_encrypt on it -- a limb of the ciphertext depends only on itself, the dropped last limb and the
  * nonce-addressed randomness (whose layout does not depend on the limb count), so the shard equals the same limbs of the

@@ -55,6 +55,7 @@ struct nttb200_bfv {
     // grow-only scratch: keystream and gaussian draws
     unsigned char *ks = nullptr; size_t ks_bytes = 0;
     int *es = nullptr; size_t es_count = 0;
+    u64 *pt = nullptr; size_t pt_count = 0;          // lifted + transformed plaintexts of nttb200_bfv_mul_plain
     bool enc_lazy = false, dec_fast = false, all_exact = false;
 };
 
@@ -239,6 +240,7 @@ static int ensure_scratch(nttb200_bfv *b, size_t ks_bytes, size_t es_count)
     }
     if (b->es_count < es_count) {
         if (b->es) cudaFree(b->es);
+    if (b->pt) cudaFree(b->pt);
         b->es = nullptr; b->es_count = 0;
         NTTB200_CHECK(cudaMalloc(&b->es, es_count * sizeof(int)));
         b->es_count = es_count;
@@ -308,6 +310,7 @@ void nttb200_bfv_destroy(nttb200_bfv *b)
     cudaFree(b->inv_q_last_mod_q); cudaFree(b->qi_div_t); cudaFree(b->prod_t_gamma_mod_q); cudaFree(b->inv_punctured_q); cudaFree(b->bcm);
     if (b->ks) cudaFree(b->ks);
     if (b->es) cudaFree(b->es);
+    if (b->pt) cudaFree(b->pt);
     cudaFree(b->sk_l); cudaFree(b->sk_ls); cudaFree(b->pk_l); cudaFree(b->pk_ls);
     nttb200_ctx_destroy(b->ctx);
     delete b;
@@ -370,6 +373,50 @@ int nttb200_bfv_decrypt(nttb200_bfv *b, nttb200_u64 *m_out, nttb200_u64 *c, cons
     DecryptConsts D{b->t, b->gamma, b->mu_gamma, b->gamma_div_2, b->neg_inv_t, b->neg_inv_gamma, b->gamma_bits, b->r - 1, b->bcm};
     if (!sk) return run_decrypt_fused(P, b->ctx->lazy_ok != 0, c, b->sk_l, b->sk_ls, m_out, b->n, D, batch);
     return run_decrypt(P, c, sk, sk_per_item ? (size_t)b->r * b->n : 0, m_out, b->n, D, batch);
+}
+
+// ---- homomorphic add and plaintext multiply (the reference stops at decryption) ------------------------------------
+// c_a <- c_a + c_b: Dec(result) = m_a + m_b mod t.  Ciphertexts in the reference layout c[batch][2][r][n]; the padding limb is left alone.
+int nttb200_bfv_add(nttb200_bfv *b, nttb200_u64 *c_a, const nttb200_u64 *c_b, unsigned batch, void *stream)
+{
+    if (!b || !c_a || !c_b || !batch || 2 * (size_t)batch > 65535) return NTTB200_EINVAL;
+    const unsigned n = b->n, r = b->r;
+    k_ct_add<<<pair_grid(n, r - 1, 2 * batch), pair_block(n, r - 1, 2 * batch), 0, (cudaStream_t)stream>>>(c_a, c_b, n, r, batch, b->ctx->q_dev);
+    KCHECK();
+    return 0;
+}
+// c <- c * p for a plaintext polynomial p (coefficients taken mod t, centred lift): Dec(result) = m * p mod (X^n + 1, t).
+// One plaintext for the whole batch (plain_per_item = 0) or one per item.  Per call: lift, NTT of the plaintext limbs, NTT of both
+// ciphertext halves, the coefficient-wise product fused into the first inverse kernel, strided inverse pass.
+int nttb200_bfv_mul_plain(nttb200_bfv *b, nttb200_u64 *c, const nttb200_u64 *p_poly, int plain_per_item, unsigned batch, void *stream)
+{
+    if (!b || !c || !p_poly || !batch || batch > 32767) return NTTB200_EINVAL;
+    const unsigned n = b->n, r = b->r, rp = r - 1;
+    const size_t rn = (size_t)r * n;
+    const unsigned items = plain_per_item ? batch : 1;
+    const size_t need = (size_t)items * rp * n;
+    if (b->pt_count < need) {
+        if (b->pt) cudaFree(b->pt);
+        b->pt = nullptr; b->pt_count = 0;
+        NTTB200_CHECK(cudaMalloc(&b->pt, need * 8));
+        b->pt_count = need;
+    }
+    Pipe P = pipe_from_bfv(b, (cudaStream_t)stream);
+    k_plain_lift<<<pair_grid(n, items, 1), pair_block(n, items, 1), 0, P.st>>>(p_poly, (size_t)n, b->pt, n, rp, items, b->t, b->ctx->q_dev);
+    KCHECK();
+    NTTB200_TRY(pipe_ntt(P, false, b->pt, items * rp, rp, 0, 0));
+    NTTB200_TRY(pipe_ntt(P, false, c, batch * 2 * rp, rp, rp, rn));              // groups = (item, half): rp limbs every r*n
+    const bool lazy = P.policy_inv == kPolicyShoupLazy;
+    if (!plain_per_item) {
+        NTTB200_TRY(launch_polymul(lazy, P.logn, pipe_args(P, false, c, batch * 2 * rp, rp, rp, rn), P.psiinv, P.psiinv_s, b->pt, rp, 0, false,
+                                   nullptr, P.st));
+    } else {
+        for (unsigned h = 0; h < 2; h++)
+            NTTB200_TRY(launch_polymul(lazy, P.logn, pipe_args(P, false, c + h * rn, batch * rp, rp, rp, 2 * rn), P.psiinv, P.psiinv_s, b->pt, rp,
+                                       (size_t)rp * n, false, nullptr, P.st));
+    }
+    NTTB200_TRY(pipe_ntt_pass(P, true, 1, c, batch * 2 * rp, rp, rp, rn));
+    return 0;
 }
 
 // ---- limb-sharded decryption: this GPU's share up to the cross-limb reduction, and the step after the all-reduce -------

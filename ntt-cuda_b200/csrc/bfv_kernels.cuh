@@ -552,4 +552,33 @@ NTT_KERNEL void k_decrypt_finish(const u64 *part_sum, u64 *out, size_t out_strid
     }
 }
 
+// ---- homomorphic operations on ciphertexts in the reference layout (the next callers of the batched NTT) ----------
+// ca += cb on the limbs below the dropped one, both halves (canonical in, canonical out).  grid (x, r-1, 2*batch)
+NTT_KERNEL void k_ct_add(u64 *ca, const u64 *cb, unsigned n, unsigned r, unsigned batch, const u64 *q)
+{
+    (void)batch;
+    const unsigned l = blockIdx.y;
+    const size_t off = (size_t)blockIdx.z * r * n + (size_t)l * n;       // blockIdx.z = item * 2 + half
+    const u64 ql = q[l];
+    NTT_PAIR_STRIDE(j, n) {
+        const ulonglong2 a = ld2(ca + off + j), b = ld2(cb + off + j);
+        st2(ca + off + j, csub(a.x + b.x, ql), csub(a.y + b.y, ql));
+    }
+}
+// centred lift of a plaintext polynomial (coefficients reduced mod t first) to every limb below the dropped one:
+// P[k][l][j] = m mod q_l for m <= t/2, m - t mod q_l otherwise.  grid (x, items)
+NTT_KERNEL void k_plain_lift(const u64 *m, size_t m_stride, u64 *P, unsigned n, unsigned rp, unsigned items, u64 t, const u64 *q)
+{
+    (void)items;
+    const size_t k = blockIdx.y;
+    NTT_PAIR_STRIDE(j, n) {
+        const ulonglong2 mv = ld2(m + k * m_stride + j);
+        const u64 m0 = mv.x % t, m1 = mv.y % t;
+        for (unsigned l = 0; l < rp; l++) {
+            const u64 ql = q[l];
+            st2(P + (k * rp + l) * n + j, m0 <= t / 2 ? m0 : ql - (t - m0), m1 <= t / 2 ? m1 : ql - (t - m1));
+        }
+    }
+}
+
 }  // namespace nttb200

@@ -318,6 +318,15 @@ class Bfv:
                                         vp(_stream(stream))))
 
 
+    def add(self, c_a, c_b, batch=1, stream=None):
+        """c_a <- c_a + c_b (homomorphic addition: Dec = m_a + m_b mod t)."""
+        check(lib().nttb200_bfv_add(self._h, vp(ptr(c_a)), vp(ptr(c_b)), C.c_uint(batch), vp(_stream(stream))))
+
+    def mul_plain(self, c, p_poly, batch=1, plain_per_item=False, stream=None):
+        """c <- c * p for a plaintext polynomial p[n] (or p[batch][n]): Dec = m * p mod (X^n + 1, t)."""
+        check(lib().nttb200_bfv_mul_plain(self._h, vp(ptr(c)), vp(ptr(p_poly)), C.c_int(int(plain_per_item)), C.c_uint(batch),
+                                          vp(_stream(stream))))
+
     def decrypt_partial(self, partial, c_shard, sk_shard, first_limb, limb_count, batch=1, sk_per_item=False, shard_half_limbs=0,
                         stream=None):
         """Limb-sharded decryption, this GPU's share: partial[batch][2][n] (all-reduce SUM it, then decrypt_finish).

@@ -303,3 +303,65 @@ def test_loaded_key_kat(oracle):
     with pytest.raises(Exception):
         bfv.encrypt(to_dev(g["c_host"]), None, out)     # no public key loaded: refused, not silently computed
     bfv.close()
+
+
+@pytest.mark.parametrize("name,batch", [("4k_3q", 3), ("8k_4q", 2), ("32k_16q", 2)])
+def test_homomorphic_add_and_plain_multiply(oracle, name, batch):
+    """SURVEY.md 8f-4 (the reference stops at decryption): Dec(Enc(m1) + Enc(m2)) == m1 + m2 mod t and
+    Dec(Enc(m) * p) == m * p mod (X^n + 1, t), the latter against the schoolbook negacyclic product of helper.h:95-126 (oracle) and,
+    independently, against the oracle's own decryption of the product ciphertext; shared and per-item plaintext factors."""
+    import torch
+    import nttb200
+    from tests.gpu_util import to_dev, to_host
+    n, qs, roots = params.RNS_SETS[name]
+    R = oracle.Ring(n, qs, roots)
+    t, rn = params.T, len(qs) * n
+    bfv = nttb200.Bfv(n, qs, roots)
+    sk = torch.zeros(rn, dtype=torch.int64, device="cuda")
+    pk = torch.zeros(2 * rn, dtype=torch.int64, device="cuda")
+    bfv.keygen(sk, pk)
+    m1 = np.concatenate([oracle.fill_uniform(n, t, 0x111 + k) for k in range(batch)])
+    m2 = np.concatenate([oracle.fill_uniform(n, t, 0x222 + k) for k in range(batch)])
+    m1[:3] = [0, t - 1, t - 1]
+    m2[:3] = [t - 1, t - 1, 1]
+    c1 = torch.zeros(batch * 2 * rn, dtype=torch.int64, device="cuda")
+    c2 = torch.zeros_like(c1)
+    bfv.encrypt(c1, pk, to_dev(m1), batch=batch, nonce0=5)
+    bfv.encrypt(c2, pk, to_dev(m2), batch=batch, nonce0=50)
+    out = torch.zeros(batch * n, dtype=torch.int64, device="cuda")
+    # addition
+    s = c1.clone()
+    bfv.add(s, c2, batch=batch)
+    bfv.decrypt(out, s.clone(), sk, batch=batch)
+    assert np.array_equal(to_host(out), (m1 + m2) % np.uint64(t))
+    # plaintext multiplication: a sparse factor keeps the schoolbook reference cheap; one shared factor, then one per item
+    def negacyclic_mod_t(a, b):
+        res = np.zeros(n, dtype=np.int64)
+        for i in np.nonzero(b)[0]:
+            v = int(b[i])
+            res[i:] += v * a[:n - i].astype(np.int64)
+            res[:i] -= v * a[n - i:].astype(np.int64)
+        return (res % t).astype(np.uint64)
+    p_shared = np.zeros(n, dtype=np.uint64)
+    p_shared[[0, 1, n // 2, n - 1]] = [3, t - 1, 7, 512]
+    prod = c1.clone()
+    bfv.mul_plain(prod, to_dev(p_shared), batch=batch)
+    host_prod = to_host(prod).copy()
+    bfv.decrypt(out, prod, sk, batch=batch)
+    got = to_host(out)
+    for k in range(batch):
+        assert np.array_equal(got[k * n:(k + 1) * n], negacyclic_mod_t(m1[k * n:(k + 1) * n], p_shared)), f"item {k}"
+    # the oracle's decryption (CPU restatement of decryption_rns) agrees on the product ciphertext
+    plain, _ = oracle.decryption_rns(R, host_prod[:2 * rn], to_host(sk))
+    assert np.array_equal(plain, got[:n])
+    p_items = np.zeros(batch * n, dtype=np.uint64)
+    for k in range(batch):
+        p_items[k * n + k] = 2 + k
+        p_items[k * n + n - 1 - k] = t - 3
+    prod = c2.clone()
+    bfv.mul_plain(prod, to_dev(p_items), batch=batch, plain_per_item=True)
+    bfv.decrypt(out, prod, sk, batch=batch)
+    got = to_host(out)
+    for k in range(batch):
+        assert np.array_equal(got[k * n:(k + 1) * n], negacyclic_mod_t(m2[k * n:(k + 1) * n], p_items[k * n:(k + 1) * n])), f"item {k}"
+    bfv.close()
