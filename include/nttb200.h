@@ -188,6 +188,14 @@ NTTB200_API int nttb200_bfv_encrypt(nttb200_bfv *bfv, nttb200_u64 *c, const nttb
 NTTB200_API int nttb200_bfv_decrypt(nttb200_bfv *bfv, nttb200_u64 *m_out, nttb200_u64 *c, const nttb200_u64 *sk, int sk_per_item,
                                     unsigned batch, void *stream);
 
+/* Compact wire format for ciphertexts (the reference has none beyond the text dump of decryption_test.cu:329-344):
+ * for half in {0,1}, for limb l < r-1: n coefficients as n * qbit_l bits, coefficient j at bit j * qbit_l of the limb's bit string,
+ * little-endian bits in little-endian 64-bit words; the padding limb is dropped.  nttb200_bfv_packed_words() = 2 * n/64 * sum qbit_l
+ * words per ciphertext (32768 x 16 limbs: 6.45 MB instead of 8 MiB).  unpack restores the reference layout with a zeroed padding limb. */
+NTTB200_API size_t nttb200_bfv_packed_words(const nttb200_bfv *bfv);
+NTTB200_API int nttb200_bfv_pack(nttb200_bfv *bfv, nttb200_u64 *packed, const nttb200_u64 *c, unsigned batch, void *stream);
+NTTB200_API int nttb200_bfv_unpack(nttb200_bfv *bfv, nttb200_u64 *c, const nttb200_u64 *packed, unsigned batch, void *stream);
+
 /* Homomorphic operations on ciphertexts in the reference layout (the reference stops at decryption):
  * c_a <- c_a + c_b  (Dec = m_a + m_b mod t), and  c <- c * p  for a plaintext polynomial p[n] or p[batch][n]
  * (Dec = m * p mod (X^n + 1, t); coefficients of p are taken mod t and lifted centred).  The padding limb is left alone. */

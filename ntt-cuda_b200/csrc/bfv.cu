@@ -56,6 +56,7 @@ struct nttb200_bfv {
     unsigned char *ks = nullptr; size_t ks_bytes = 0;
     int *es = nullptr; size_t es_count = 0;
     u64 *pt = nullptr; size_t pt_count = 0;          // lifted + transformed plaintexts of nttb200_bfv_mul_plain
+    unsigned *word_off = nullptr; unsigned half_words = 0;   // compact wire format: first word of each limb inside a half, words per half
     bool enc_lazy = false, dec_fast = false, all_exact = false;
 };
 
@@ -103,8 +104,8 @@ static int pipe_ntt(const Pipe &P, bool inverse, u64 *a, unsigned num, unsigned 
     return launch_ntt(inverse, pol, P.logn, h, P.st);
 }
 
-#define KCHECK() do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return (int)e__; } while (0)
-#define NTTB200_TRY(x) do { int r__ = (x); if (r__) return r__; } while (0)
+#define KCHECK() do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return nttb200_trace_error((int)e__, __FILE__, __LINE__); } while (0)
+#define NTTB200_TRY(x) do { int r__ = (x); if (r__) return nttb200_trace_error(r__, __FILE__, __LINE__); } while (0)
 
 // keygen: in = keystream scratch ([batch] streams of in_stride bytes), es = n ints per item
 static int run_keygen(const Pipe &P, unsigned char *in, size_t in_stride, int *es, u64 *sk, u64 *pk, unsigned batch, u64 nonce0)
@@ -240,7 +241,6 @@ static int ensure_scratch(nttb200_bfv *b, size_t ks_bytes, size_t es_count)
     }
     if (b->es_count < es_count) {
         if (b->es) cudaFree(b->es);
-    if (b->pt) cudaFree(b->pt);
         b->es = nullptr; b->es_count = 0;
         NTTB200_CHECK(cudaMalloc(&b->es, es_count * sizeof(int)));
         b->es_count = es_count;
@@ -297,6 +297,17 @@ int nttb200_bfv_create(nttb200_bfv **out, unsigned n, unsigned limbs, const nttb
         b->enc_lazy = b->enc_lazy && exact && iql[i] < q[i] && q[r - 1] <= 2 * q[i] && q[i] < (1ull << 60);
         b->dec_fast = b->dec_fast && exact && ptg[i] < q[i] && ipq[i] < q[i] && bcm[rp + i] < gamma;
     }
+    {   // wire format offsets (bfv_kernels.cuh: k_ct_pack)
+        std::vector<unsigned> woff(rp);
+        unsigned acc = 0;
+        for (unsigned i = 0; i < rp; i++) { woff[i] = acc; acc += n / 64 * ctx->qbit[i]; }
+        b->half_words = acc;
+        if (cudaMalloc(&b->word_off, rp * sizeof(unsigned)) != cudaSuccess ||
+            cudaMemcpy(b->word_off, woff.data(), rp * sizeof(unsigned), cudaMemcpyHostToDevice) != cudaSuccess) {
+            nttb200_bfv_destroy(b);
+            return (int)cudaErrorMemoryAllocation;
+        }
+    }
     rc = up(&b->inv_q_last_mod_q, iql); if (!rc) rc = up(&b->qi_div_t, qdt); if (!rc) rc = up(&b->prod_t_gamma_mod_q, ptg);
     if (!rc) rc = up(&b->inv_punctured_q, ipq); if (!rc) rc = up(&b->bcm, bcm);
     if (rc) { nttb200_bfv_destroy(b); return rc; }
@@ -311,6 +322,7 @@ void nttb200_bfv_destroy(nttb200_bfv *b)
     if (b->ks) cudaFree(b->ks);
     if (b->es) cudaFree(b->es);
     if (b->pt) cudaFree(b->pt);
+    if (b->word_off) cudaFree(b->word_off);
     cudaFree(b->sk_l); cudaFree(b->sk_ls); cudaFree(b->pk_l); cudaFree(b->pk_ls);
     nttb200_ctx_destroy(b->ctx);
     delete b;
@@ -416,6 +428,30 @@ int nttb200_bfv_mul_plain(nttb200_bfv *b, nttb200_u64 *c, const nttb200_u64 *p_p
                                        (size_t)rp * n, false, nullptr, P.st));
     }
     NTTB200_TRY(pipe_ntt_pass(P, true, 1, c, batch * 2 * rp, rp, rp, rn));
+    return 0;
+}
+
+// ---- compact wire format --------------------------------------------------------------------------------------------
+size_t nttb200_bfv_packed_words(const nttb200_bfv *b) { return b ? 2 * (size_t)b->half_words : 0; }
+int nttb200_bfv_pack(nttb200_bfv *b, nttb200_u64 *packed, const nttb200_u64 *c, unsigned batch, void *stream)
+{
+    if (!b || !packed || !c || !batch || 2 * (size_t)batch > 65535) return NTTB200_EINVAL;
+    const unsigned n = b->n, r = b->r;
+    const unsigned x = (n / 64 + 127) / 128;
+    k_ct_pack<<<dim3(x, r - 1, 2 * batch), 128, 0, (cudaStream_t)stream>>>(c, packed, n, r, batch, b->ctx->qbit_dev, b->word_off, b->half_words);
+    KCHECK();
+    return 0;
+}
+int nttb200_bfv_unpack(nttb200_bfv *b, nttb200_u64 *c, const nttb200_u64 *packed, unsigned batch, void *stream)
+{
+    if (!b || !packed || !c || !batch || 2 * (size_t)batch > 65535) return NTTB200_EINVAL;
+    const unsigned n = b->n, r = b->r;
+    const size_t rn = (size_t)r * n;
+    for (unsigned h = 0; h < 2; h++)      // the padding limb of the reference layout is not stored: zero it
+        NTTB200_CHECK(cudaMemset2DAsync(c + h * rn + (size_t)(r - 1) * n, 2 * rn * 8, 0, (size_t)n * 8, batch, (cudaStream_t)stream));
+    const unsigned x = (n / 64 + 127) / 128;
+    k_ct_unpack<<<dim3(x, r - 1, 2 * batch), 128, 0, (cudaStream_t)stream>>>(packed, c, n, r, batch, b->ctx->qbit_dev, b->word_off, b->half_words);
+    KCHECK();
     return 0;
 }
 

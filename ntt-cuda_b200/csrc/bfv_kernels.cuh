@@ -581,4 +581,61 @@ NTT_KERNEL void k_plain_lift(const u64 *m, size_t m_stride, u64 *P, unsigned n, 
     }
 }
 
+// ---- compact wire format for ciphertexts (the reference has none beyond a text dump, decryption_test.cu:329-344) ----
+// packed ciphertext = for half in {0,1}, for limb l < r-1: the n coefficients as n * qbit_l bits, coefficient j at bit offset
+// j * qbit_l of that limb's bit string, little-endian bits in little-endian 64-bit words (n is a multiple of 64, so every limb is
+// a whole number of words: n / 64 * qbit_l).  The padding limb is not stored.  One thread = 64 coefficients = qbit_l words.
+// grid (x, r-1, 2 * batch); word_off[l] = first word of limb l inside one half; half_words = words per half.
+NTT_KERNEL void k_ct_pack(const u64 *c, u64 *packed, unsigned n, unsigned r, unsigned batch, const u32 *qbit, const u32 *word_off, u32 half_words)
+{
+    (void)batch;
+    const unsigned l = blockIdx.y, qb = qbit[l];
+    const u64 *src = c + (size_t)blockIdx.z * r * n + (size_t)l * n;                 // blockIdx.z = item * 2 + half
+    u64 *dst = packed + (size_t)blockIdx.z * half_words + word_off[l];
+    for (u32 g = blockIdx.x * blockDim.x + threadIdx.x; g < n / 64; g += gridDim.x * blockDim.x) {
+        const u64 *in = src + (size_t)g * 64;
+        u64 *out = dst + (size_t)g * qb;
+        u64 acc = 0;
+        unsigned have = 0;
+        for (unsigned k = 0; k < 64; k++) {
+            const u64 v = in[k];
+            acc |= v << have;
+            if (have + qb >= 64) {
+                *out++ = acc;
+                acc = have ? v >> (64 - have) : 0;
+                have = have + qb - 64;
+            } else {
+                have += qb;
+            }
+        }
+    }
+}
+NTT_KERNEL void k_ct_unpack(const u64 *packed, u64 *c, unsigned n, unsigned r, unsigned batch, const u32 *qbit, const u32 *word_off, u32 half_words)
+{
+    (void)batch;
+    const unsigned l = blockIdx.y, qb = qbit[l];
+    const u64 mask = qb >= 64 ? ~0ull : ((1ull << qb) - 1);
+    u64 *dst = c + (size_t)blockIdx.z * r * n + (size_t)l * n;
+    const u64 *src = packed + (size_t)blockIdx.z * half_words + word_off[l];
+    for (u32 g = blockIdx.x * blockDim.x + threadIdx.x; g < n / 64; g += gridDim.x * blockDim.x) {
+        const u64 *in = src + (size_t)g * qb;
+        u64 *out = dst + (size_t)g * 64;
+        u64 cur = *in++;
+        unsigned have = 64;                                                        // unread bits left in cur
+        for (unsigned k = 0; k < 64; k++) {
+            u64 v;
+            if (have >= qb) {
+                v = cur >> (64 - have);
+                have -= qb;
+            } else {
+                v = have ? cur >> (64 - have) : 0;
+                cur = *in++;
+                v |= cur << have;
+                have = 64 - (qb - have);
+            }
+            out[k] = v & mask;
+        }
+    }
+}
+
 }  // namespace nttb200

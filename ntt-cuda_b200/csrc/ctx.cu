@@ -6,6 +6,7 @@
 #include "table_kernels.cuh"
 
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -95,6 +96,14 @@ static int ctx_alloc(nttb200_ctx **out, unsigned n, unsigned limbs, const u64 *q
     c->use_tma = get_tma_default();
     *out = c;
     return 0;
+}
+
+int nttb200_trace_error(int code, const char *file, int line)
+{
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("NTTB200_DEBUG"); on = (e && e[0] == '1') ? 1 : 0; }
+    if (on) fprintf(stderr, "nttb200: error %d (%s) at %s:%d\n", code, code < 10000 ? cudaGetErrorString((cudaError_t)code) : "nttb200", file, line);
+    return code;
 }
 
 extern "C" {

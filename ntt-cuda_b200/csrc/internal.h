@@ -7,10 +7,12 @@
 #include "../../include/nttb200.h"
 #include "modarith.cuh"
 
-#define NTTB200_CHECK(expr)                          \
-    do {                                             \
-        cudaError_t e__ = (expr);                    \
-        if (e__ != cudaSuccess) return (int)e__;     \
+// NTTB200_DEBUG=1 in the environment: every failing step reports its source line on stderr before the code is returned
+int nttb200_trace_error(int code, const char *file, int line);
+#define NTTB200_CHECK(expr)                                                                      \
+    do {                                                                                         \
+        cudaError_t e__ = (expr);                                                                \
+        if (e__ != cudaSuccess) return nttb200_trace_error((int)e__, __FILE__, __LINE__);        \
     } while (0)
 
 struct nttb200_ctx {

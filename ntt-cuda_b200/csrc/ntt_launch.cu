@@ -119,7 +119,7 @@ static int launch_one(const NttArgs &A, int which, unsigned cnt, const CUtensorM
         if (do_contig) ntt_contig_pass<P, LOGN, INV><<<gc, kContigRows, smem_c, st>>>(mc, Ac);
         if (do_strided) ntt_strided_pass<P, LOGN, INV><<<gs, R * SC::NT, smem_s, st>>>(ms, As);
     }
-    return (int)cudaGetLastError();
+    { const int e__ = (int)cudaGetLastError(); return e__ ? nttb200_trace_error(e__, __FILE__, __LINE__) : 0; }
 }
 
 template <class P, bool INV>
@@ -196,7 +196,7 @@ static int launch_fused_one(const FusedArgs &F, const CUtensorMap &mc, cudaStrea
     }
     const unsigned tiles = ((1u << LOGN) >> 4) / kContigRows;
     ntt_contig_fused_mul<PF, PI, LOGN, NOUT><<<F.items * F.r * tiles, kContigRows, smem, st>>>(mc, F);
-    return (int)cudaGetLastError();
+    { const int e__ = (int)cudaGetLastError(); return e__ ? nttb200_trace_error(e__, __FILE__, __LINE__) : 0; }
 }
 template <class PF, class PI, int NOUT>
 static int launch_fused_logn(unsigned logn, const FusedArgs &F, const CUtensorMap &mc, cudaStream_t st)
@@ -254,7 +254,7 @@ static int launch_polymul_one(const PolymulArgs &F, const CUtensorMap &ma, const
     const unsigned tiles = ((1u << LOGN) >> 4) / kContigRows;
     if ((size_t)F.A.num * tiles >= (1ull << 31)) return NTTB200_EINVAL;
     ntt_contig_polymul<PF, PI, LOGN, A_FWD, B_FWD><<<F.A.num * tiles, kContigRows, smem, st>>>(ma, mb, mo, F);
-    return (int)cudaGetLastError();
+    { const int e__ = (int)cudaGetLastError(); return e__ ? nttb200_trace_error(e__, __FILE__, __LINE__) : 0; }
 }
 template <class PF, class PI, bool A_FWD, bool B_FWD>
 static int launch_polymul_logn(unsigned logn, const PolymulArgs &F, const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mo,

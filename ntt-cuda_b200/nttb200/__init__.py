@@ -318,6 +318,17 @@ class Bfv:
                                         vp(_stream(stream))))
 
 
+    def packed_words(self) -> int:
+        """64-bit words of one ciphertext in the compact wire format."""
+        lib().nttb200_bfv_packed_words.restype = C.c_size_t
+        return int(lib().nttb200_bfv_packed_words(self._h))
+
+    def pack(self, packed, c, batch=1, stream=None):
+        check(lib().nttb200_bfv_pack(self._h, vp(ptr(packed)), vp(ptr(c)), C.c_uint(batch), vp(_stream(stream))))
+
+    def unpack(self, c, packed, batch=1, stream=None):
+        check(lib().nttb200_bfv_unpack(self._h, vp(ptr(c)), vp(ptr(packed)), C.c_uint(batch), vp(_stream(stream))))
+
     def add(self, c_a, c_b, batch=1, stream=None):
         """c_a <- c_a + c_b (homomorphic addition: Dec = m_a + m_b mod t)."""
         check(lib().nttb200_bfv_add(self._h, vp(ptr(c_a)), vp(ptr(c_b)), C.c_uint(batch), vp(_stream(stream))))

@@ -365,3 +365,42 @@ def test_homomorphic_add_and_plain_multiply(oracle, name, batch):
     for k in range(batch):
         assert np.array_equal(got[k * n:(k + 1) * n], negacyclic_mod_t(m2[k * n:(k + 1) * n], p_items[k * n:(k + 1) * n])), f"item {k}"
     bfv.close()
+
+
+@pytest.mark.parametrize("name,batch", [("4k_3q", 2), ("16k_5q", 2), ("32k_16q", 3)])
+def test_wire_format_round_trip(oracle, name, batch):
+    """pack -> bytes match a numpy restatement of the format definition in include/nttb200.h -> unpack restores every
+    stored limb bit for bit (padding limb zeroed) and the unpacked ciphertext still decrypts to the message."""
+    import torch
+    import nttb200
+    from tests.gpu_util import to_dev, to_host
+    n, qs, roots = params.RNS_SETS[name]
+    r, rn, t = len(qs), len(qs) * n, params.T
+    bfv = nttb200.Bfv(n, qs, roots)
+    sk = torch.zeros(rn, dtype=torch.int64, device="cuda")
+    pk = torch.zeros(2 * rn, dtype=torch.int64, device="cuda")
+    bfv.keygen(sk, pk)
+    m = np.concatenate([oracle.fill_uniform(n, t, 0x333 + k) for k in range(batch)])
+    c = torch.zeros(batch * 2 * rn, dtype=torch.int64, device="cuda")
+    bfv.encrypt(c, pk, to_dev(m), batch=batch, nonce0=9)
+    words = bfv.packed_words()
+    qbits = [int(q).bit_length() for q in qs[:-1]]
+    assert words == 2 * (n // 64) * sum(qbits)
+    packed = torch.zeros(batch * words, dtype=torch.int64, device="cuda")
+    bfv.pack(packed, c, batch=batch)
+    hc, hp = to_host(c).reshape(batch, 2, r, n), to_host(packed).reshape(batch, words)
+    for k in range(batch):
+        exp = []
+        for h in range(2):
+            for l, qb in enumerate(qbits):
+                bits = ((hc[k, h, l][:, None] >> np.arange(qb, dtype=np.uint64)[None, :]) & np.uint64(1)).astype(np.uint8).reshape(-1)
+                exp.append(np.packbits(bits, bitorder="little").view(np.uint64))
+        assert np.array_equal(hp[k], np.concatenate(exp)), f"item {k}"
+    back = torch.full_like(c, -1)
+    bfv.unpack(back, packed, batch=batch)
+    hb = to_host(back).reshape(batch, 2, r, n)
+    assert np.array_equal(hb[:, :, :r - 1], hc[:, :, :r - 1]) and not hb[:, :, r - 1].any()
+    out = torch.zeros(batch * n, dtype=torch.int64, device="cuda")
+    bfv.decrypt(out, back, sk, batch=batch)
+    assert np.array_equal(to_host(out), m)
+    bfv.close()
