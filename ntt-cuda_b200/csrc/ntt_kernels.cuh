@@ -458,6 +458,30 @@ ntt_strided_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
     const u32 tid = threadIdx.x, p = blockIdx.x / TG;
     const u32 colbase = (blockIdx.x % TG) * (TPC * NT * 16);
     const u32 grp = p / A.group_polys, idx = p - grp * A.group_polys;   // polynomial idx of group grp
+    const bool dbg_nocompute = (A.use_tma & 2u) != 0, dbg_nomem = (A.use_tma & 4u) != 0;
+    const bool tma = (A.use_tma & 1u) != 0;
+#ifndef NTTB200_EMU
+    // The tile loads are issued FIRST, by the thread that also initialises their barriers (no CTA barrier in between): limb constants,
+    // index arithmetic and twiddle prefetches of everybody else then run under the HBM latency.
+    if (!dbg_nomem && tma && tid == 0) {
+        for (int tt = 0; tt < TPC; tt++) mbar_init(bar + tt, 1);
+        fence_mbar_init();
+        for (int tt = 0; tt < TPC; tt++) {
+            mbar_expect_tx(bar + tt, (u32)(NT * R * 128));
+            for (int k = 0; k < NT; k++)
+                for (int rc = 0; rc < R / RB; rc++)
+                    tma_load_4d(tiles0 + tt * TILE_ELEMS + ((size_t)k * R + rc * RB) * 16, &tmap, bar + tt, (int)colbase + (tt * NT + k) * 16,
+                                rc * RB, (int)idx, (int)grp);
+        }
+        const u32 fb = blockIdx.x + A.pf_dist;           // the CTA that will run here about one wave later
+        if (A.pf_dist != 0 && fb < gridDim.x) {
+            const u32 fp = fb / TG, fcol = (fb % TG) * (TPC * NT * 16);
+            const u32 fgrp = fp / A.group_polys, fidx = fp - fgrp * A.group_polys;
+            for (int k = 0; k < TPC * NT; k++)
+                for (int rc = 0; rc < R / RB; rc++) tma_prefetch_4d(&tmap, (int)fcol + k * 16, rc * RB, (int)fidx, (int)fgrp);
+        }
+    }
+#endif
     P pol;
     pol.init(A, p % A.division, n);
     u64 *g = A.a + (size_t)grp * A.group_stride + ((size_t)idx << LOGN) + colbase;
@@ -468,8 +492,6 @@ ntt_strided_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
         if (uu < 32) prefetch_round<SC::S1>(pol, 1u);
     }
 
-    const bool dbg_nocompute = (A.use_tma & 2u) != 0, dbg_nomem = (A.use_tma & 4u) != 0;
-    const bool tma = (A.use_tma & 1u) != 0;
     if (dbg_nomem) {
         __syncthreads();
     } else if (tma) {
@@ -482,27 +504,7 @@ ntt_strided_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
                                    (int)idx, (int)grp);
         __syncthreads();
 #else
-        if (tid == 0) {
-            for (int tt = 0; tt < TPC; tt++) mbar_init(bar + tt, 1);
-            fence_mbar_init();
-        }
-        __syncthreads();
-        if (tid == 0) {
-            for (int tt = 0; tt < TPC; tt++) {
-                mbar_expect_tx(bar + tt, (u32)(NT * R * 128));
-                for (int k = 0; k < NT; k++)
-                    for (int rc = 0; rc < R / RB; rc++)
-                        tma_load_4d(tiles0 + tt * TILE_ELEMS + ((size_t)k * R + rc * RB) * 16, &tmap, bar + tt, (int)colbase + (tt * NT + k) * 16,
-                                    rc * RB, (int)idx, (int)grp);
-            }
-            const u32 fb = blockIdx.x + A.pf_dist;           // the CTA that will run here about one wave later
-            if (A.pf_dist != 0 && fb < gridDim.x) {
-                const u32 fp = fb / TG, fcol = (fb % TG) * (TPC * NT * 16);
-                const u32 fgrp = fp / A.group_polys, fidx = fp - fgrp * A.group_polys;
-                for (int k = 0; k < TPC * NT; k++)
-                    for (int rc = 0; rc < R / RB; rc++) tma_prefetch_4d(&tmap, (int)fcol + k * 16, rc * RB, (int)fidx, (int)fgrp);
-            }
-        }
+        __syncthreads();                                     // the barriers thread 0 initialised before issuing the loads
 #endif
     } else {
         for (int k = 0; k < TPC * NT; k++) tile_copy_coop<false, true>(tiles0 + (size_t)k * R * 16, g + k * 16, C, R, tid, THREADS);
@@ -580,14 +582,30 @@ ntt_contig_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
     const u32 ripbase = (blockIdx.x % TG) * (TPC * RT);      // first row (of 16 coefficients) inside the polynomial
     const u32 grp = p / A.group_polys, idx = p - grp * A.group_polys;
     const int growbase = (int)(idx * (n >> 4) + ripbase);    // row inside the group
+    const bool dbg_nocompute = (A.use_tma & 2u) != 0, dbg_nomem = (A.use_tma & 4u) != 0;
+    const bool tma = (A.use_tma & 1u) != 0;
+#ifndef NTTB200_EMU
+    if (!dbg_nomem && tma && tid == 0) {                      // loads first (see ntt_strided_pass)
+        for (int tt = 0; tt < TPC; tt++) mbar_init(bar + tt, 1);
+        fence_mbar_init();
+        for (int tt = 0; tt < TPC; tt++) {
+            mbar_expect_tx(bar + tt, (u32)(RT * 128));
+            tma_load_3d(tile0 + (size_t)tt * RT * 16, &tmap, bar + tt, 0, growbase + tt * RT, (int)grp);
+        }
+        const u32 fb = blockIdx.x + A.pf_dist;
+        if (A.pf_dist != 0 && fb < gridDim.x) {
+            const u32 fp = fb / TG, frip = (fb % TG) * (TPC * RT);
+            const u32 fgrp = fp / A.group_polys, fidx = fp - fgrp * A.group_polys;
+            for (int tt = 0; tt < TPC; tt++) tma_prefetch_3d(&tmap, 0, (int)(fidx * (n >> 4) + frip) + tt * RT, (int)fgrp);
+        }
+    }
+#endif
     P pol;
     pol.init(A, p % A.division, n);
     u64 *g = A.a + (size_t)grp * A.group_stride + ((size_t)idx << LOGN) + (size_t)ripbase * 16;
     prefetch_round<4>(pol, (n >> 4) + ripbase + tid);
     prefetch_round<SA>(pol, (1u << K1) + (ripbase >> SA) + (tid >> SA));
 
-    const bool dbg_nocompute = (A.use_tma & 2u) != 0, dbg_nomem = (A.use_tma & 4u) != 0;
-    const bool tma = (A.use_tma & 1u) != 0;
     if (dbg_nomem) {
         __syncthreads();
     } else if (tma) {
@@ -596,23 +614,7 @@ ntt_contig_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
             for (int tt = 0; tt < TPC; tt++) emu_tma_3d(true, &tmap, tile0 + (size_t)tt * RT * 16, 0, growbase + tt * RT, (int)grp);
         __syncthreads();
 #else
-        if (tid == 0) {
-            for (int tt = 0; tt < TPC; tt++) mbar_init(bar + tt, 1);
-            fence_mbar_init();
-        }
-        __syncthreads();
-        if (tid == 0) {
-            for (int tt = 0; tt < TPC; tt++) {
-                mbar_expect_tx(bar + tt, (u32)(RT * 128));
-                tma_load_3d(tile0 + (size_t)tt * RT * 16, &tmap, bar + tt, 0, growbase + tt * RT, (int)grp);
-            }
-            const u32 fb = blockIdx.x + A.pf_dist;
-            if (A.pf_dist != 0 && fb < gridDim.x) {
-                const u32 fp = fb / TG, frip = (fb % TG) * (TPC * RT);
-                const u32 fgrp = fp / A.group_polys, fidx = fp - fgrp * A.group_polys;
-                for (int tt = 0; tt < TPC; tt++) tma_prefetch_3d(&tmap, 0, (int)(fidx * (n >> 4) + frip) + tt * RT, (int)fgrp);
-            }
-        }
+        __syncthreads();                                     // the barriers thread 0 initialised before issuing the loads
 #endif
     } else {
         tile_copy_coop<true, true>(tile0, g, 16, TPC * RT, tid, RT);
@@ -708,15 +710,21 @@ ntt_contig_fused_mul(const __grid_constant__ TensorMap tmap, FusedArgs F)
     const u32 tid = threadIdx.x;
     const u32 pl = blockIdx.x / TILES, rip0 = (blockIdx.x % TILES) * RT;
     const u32 item = pl / F.r, limb = pl - item * F.r;
+    const int row_in = (int)((F.in_off + limb) * (n >> 4) + rip0);
+    const int row_o0 = (int)((F.out_off[0] + limb) * (n >> 4) + rip0);
+    const int row_o1 = (int)((F.out_off[1] + limb) * (n >> 4) + rip0);
+#ifndef NTTB200_EMU
+    if ((A.use_tma & 1u) && tid == 0) {                      // load first: constants and twiddle prefetches run under its latency
+        mbar_init(bar, 1); fence_mbar_init();
+        mbar_expect_tx(bar, (u32)(RT * 128)); tma_load_3d(tile, &tmap, bar, 0, row_in, (int)item);
+    }
+#endif
     PF pf;
     pf.init(A, limb, n);
     NttArgs Ai = A;
     Ai.tw = F.twi; Ai.tws = F.twis;
     PI pi;
     pi.init(Ai, limb, n);
-    const int row_in = (int)((F.in_off + limb) * (n >> 4) + rip0);
-    const int row_o0 = (int)((F.out_off[0] + limb) * (n >> 4) + rip0);
-    const int row_o1 = (int)((F.out_off[1] + limb) * (n >> 4) + rip0);
     u64 *gbase = A.a + (size_t)item * A.group_stride;
 
     if (A.use_tma & 1u) {
@@ -724,9 +732,7 @@ ntt_contig_fused_mul(const __grid_constant__ TensorMap tmap, FusedArgs F)
         if (tid == 0) emu_tma_3d(true, &tmap, tile, 0, row_in, (int)item);
         __syncthreads();
 #else
-        if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
         __syncthreads();
-        if (tid == 0) { mbar_expect_tx(bar, (u32)(RT * 128)); tma_load_3d(tile, &tmap, bar, 0, row_in, (int)item); }
         mbar_wait(bar, 0);
 #endif
     } else {
@@ -830,13 +836,21 @@ ntt_contig_polymul(const __grid_constant__ TensorMap tmap_a, const __grid_consta
     const u32 grp = p / A.group_polys, idx = p - grp * A.group_polys;
     const u32 bgrp = p / F.b_group_polys, bidx = p - bgrp * F.b_group_polys;
     const u32 limb = p % A.division;
+    const int row_a = (int)(idx * (n >> 4) + rip0), row_b = (int)(bidx * (n >> 4) + rip0);
+#ifndef NTTB200_EMU
+    if ((A.use_tma & 1u) && tid == 0) {                      // loads first
+        mbar_init(bar, 1); fence_mbar_init();
+        mbar_expect_tx(bar, (u32)(2 * RT * 128));
+        tma_load_3d(tile, &tmap_a, bar, 0, row_a, (int)grp);
+        tma_load_3d(tile2, &tmap_b, bar, 0, row_b, (int)bgrp);
+    }
+#endif
     PF pf;
     pf.init(A, limb, n);
     NttArgs Ai = A;
     Ai.tw = F.twi; Ai.tws = F.twis;
     PI pi;
     pi.init(Ai, limb, n);
-    const int row_a = (int)(idx * (n >> 4) + rip0), row_b = (int)(bidx * (n >> 4) + rip0);
     u64 *ga = A.a + (size_t)grp * A.group_stride + ((size_t)idx << LOGN) + (size_t)rip0 * 16;
     u64 *go = F.out + (size_t)grp * A.group_stride + ((size_t)idx << LOGN) + (size_t)rip0 * 16;
     const u64 *gb = F.b + (size_t)bgrp * F.b_group_stride + ((size_t)bidx << LOGN) + (size_t)rip0 * 16;
@@ -846,13 +860,7 @@ ntt_contig_polymul(const __grid_constant__ TensorMap tmap_a, const __grid_consta
         if (tid == 0) { emu_tma_3d(true, &tmap_a, tile, 0, row_a, (int)grp); emu_tma_3d(true, &tmap_b, tile2, 0, row_b, (int)bgrp); }
         __syncthreads();
 #else
-        if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
         __syncthreads();
-        if (tid == 0) {
-            mbar_expect_tx(bar, (u32)(2 * RT * 128));
-            tma_load_3d(tile, &tmap_a, bar, 0, row_a, (int)grp);
-            tma_load_3d(tile2, &tmap_b, bar, 0, row_b, (int)bgrp);
-        }
         mbar_wait(bar, 0);
 #endif
     } else {
