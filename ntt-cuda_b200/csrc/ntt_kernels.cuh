@@ -84,7 +84,11 @@ constexpr int kContigRows = 128;  // rows (of 16 coefficients) per CTA in the co
 
 __device__ __forceinline__ void prefetch_l1(const void *p)
 {
-#ifndef NTTB200_EMU
+#if !defined(NTTB200_EMU) && !defined(NTT_PF_HINT)
+    // a real load whose result is discarded: unlike the prefetch.global.L1 hint it is never dropped (contig pass -2 %)
+    u64 sink;
+    asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(sink) : "l"(p));
+#elif !defined(NTTB200_EMU)
     asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 #else
     (void)p;
