@@ -95,6 +95,14 @@ static int pipe_ntt_pass(const Pipe &P, bool inverse, int which, u64 *a, unsigne
     return launch_ntt_pass(inverse, inverse ? P.policy_inv : P.policy_fwd, P.logn, pipe_args(P, inverse, a, num, division, group_polys, group_stride),
                            which, P.st);
 }
+// forward strided pass whose input u is generated from the keystream inside the kernel (context path)
+static int pipe_ntt_gen_pass(const Pipe &P, u64 *a, unsigned num, unsigned division, unsigned group_polys, size_t group_stride,
+                             const unsigned char *in, size_t in_stride)
+{
+    NttArgsHost h = pipe_args(P, false, a, num, division, group_polys, group_stride);
+    h.gen_src = in; h.gen_stride = in_stride;
+    return launch_ntt_pass(false, P.policy_fwd, P.logn, h, 0, P.st);
+}
 static int pipe_ntt(const Pipe &P, bool inverse, u64 *a, unsigned num, unsigned division, unsigned group_polys, size_t group_stride)
 {
     NttArgsHost h{a, inverse ? P.psiinv : P.psi, inverse ? P.psiinv_s : P.psi_s, P.lc, P.L.q, P.L.mu, P.L.qbit, 0, 0, 0, num, division, P.use_tma,
@@ -154,9 +162,16 @@ static int run_encrypt(const Pipe &P, unsigned char *in, size_t in_stride, int *
     const size_t rn = (size_t)r * n;
     const u64 nblk = (9 * (size_t)n) / 64;                                                // bfv_encryption.cuh:228
     k_salsa20_keystream<<<grid_for(nblk * batch, 256), 256, 0, P.st>>>(in, nblk, (u64)batch, in_stride, default_key(), nonce0);
-    k_encrypt_sample<<<pair_grid(n, batch, 1), pair_block(n, batch, 1), 0, P.st>>>(in, in_stride, c, es, n, r, batch, P.L.q);       // :247
-    KCHECK();
-    NTTB200_TRY(pipe_ntt(P, false, c, batch * r, r, r, 2 * rn));                           // :268 (once, not twice)
+    if (P.policy_fwd != kPolicyBarrett) {
+        k_encrypt_gauss<<<pair_grid(n, batch, 1), pair_block(n, batch, 1), 0, P.st>>>(in, in_stride, es, n, batch);               // :247 (e0, e1)
+        KCHECK();
+        NTTB200_TRY(pipe_ntt_gen_pass(P, c, batch * r, r, r, 2 * rn, in, in_stride));      // :247 (u) + :268 (once, not twice), first kernel
+        NTTB200_TRY(pipe_ntt_pass(P, false, 1, c, batch * r, r, r, 2 * rn));
+    } else {
+        k_encrypt_sample<<<pair_grid(n, batch, 1), pair_block(n, batch, 1), 0, P.st>>>(in, in_stride, c, es, n, r, batch, P.L.q);   // :247
+        KCHECK();
+        NTTB200_TRY(pipe_ntt(P, false, c, batch * r, r, r, 2 * rn));                       // :268 (once, not twice)
+    }
     k_encrypt_mul<<<pair_grid(n, r, batch), pair_block(n, r, batch), 0, P.st>>>(c, pk, pk_stride, n, r, batch, P.L);              // :270
     KCHECK();
     NTTB200_TRY(pipe_ntt(P, true, c, batch * 2 * r, r, 0, 0));                             // :271
@@ -174,9 +189,9 @@ static int run_encrypt_fused(const Pipe &P, bool lazy, unsigned char *in, size_t
     const size_t rn = (size_t)r * n;
     const u64 nblk = (9 * (size_t)n) / 64;
     k_salsa20_keystream<<<grid_for(nblk * batch, 256), 256, 0, P.st>>>(in, nblk, (u64)batch, in_stride, default_key(), nonce0);
-    k_encrypt_sample<<<pair_grid(n, batch, 1), pair_block(n, batch, 1), 0, P.st>>>(in, in_stride, c, es, n, r, batch, P.L.q);
+    k_encrypt_gauss<<<pair_grid(n, batch, 1), pair_block(n, batch, 1), 0, P.st>>>(in, in_stride, es, n, batch);
     KCHECK();
-    NTTB200_TRY(pipe_ntt_pass(P, false, 0, c, batch * r, r, r, 2 * rn));                   // strided forward pass on NTT input u
+    NTTB200_TRY(pipe_ntt_gen_pass(P, c, batch * r, r, r, 2 * rn, in, in_stride));          // strided forward pass, u generated in the kernel
     NTTB200_TRY(launch_fused_mul(lazy, P.logn, pipe_args(P, false, c, batch * 2 * r, r, 2 * r, 2 * rn), P.psiinv, P.psiinv_s, pk, pk_s, 0, rn, r,
                                  0, 0, r, batch, 2, P.st));
     NTTB200_TRY(pipe_ntt_pass(P, true, 1, c, batch * 2 * r, r, 0, 0));                     // strided inverse pass on both halves

@@ -63,14 +63,7 @@ NTT_KERNEL void k_salsa20_keystream(unsigned char *out, u64 blocks_per_stream, u
 }
 
 // ---- distribution converters: the reference's formulas -----------------------------------------------------------------
-// bfv_keygen.cuh:18-30 / bfv_encryption.cuh:23-36: int(float(byte) / (255.0f/3)) - 1 in {-1, 0, 1, 2}; negative -> q - 1
-__host__ __device__ __forceinline__ u64 ternary_value(unsigned char byte, u64 q)
-{
-    float d = (float)byte;
-    d /= (255.0f / 3);
-    int b = int(d) - 1;
-    return (u64)(b < 0) * q + (u64)(long long)b;
-}
+// ternary_value(byte, q): modarith.cuh (shared with the NTT pass that generates u on the fly)
 // bfv_keygen.cuh:37-44 / distributions.cuh:195-201
 __host__ __device__ __forceinline__ u64 uniform_value(u64 x, u64 q)
 {
@@ -252,6 +245,20 @@ NTT_KERNEL void k_encrypt_sample(const unsigned char *in, size_t in_stride, u64 
             const u64 ql = q[l];
             st2(c + k * 2 * rn + (size_t)l * n + j, ternary_value(b0, ql), ternary_value(b1, ql));
         }
+    }
+}
+// the two gaussian draws only: u is generated inside the first strided NTT pass straight from the keystream (NttArgs::gen_src),
+// so the r*n ternary residues are never written to and re-read from HBM.  grid (x, batch)
+NTT_KERNEL void k_encrypt_gauss(const unsigned char *in, size_t in_stride, int *es, unsigned n, unsigned batch)
+{
+    (void)batch;
+    const size_t k = blockIdx.y;
+    const unsigned char *s = in + k * in_stride;
+    NTT_PAIR_STRIDE(j, n) {
+        const u32 *g0 = reinterpret_cast<const u32 *>(s + n) + j, *g1 = reinterpret_cast<const u32 *>(s + (size_t)n * 5) + j;
+        int *e = es + k * 2 * n;
+        e[j] = gaussian_value(g0[0]); e[j + 1] = gaussian_value(g0[1]);
+        e[n + j] = gaussian_value(g1[0]); e[n + j + 1] = gaussian_value(g1[1]);
     }
 }
 // c0 = NTT(u) (.) pk0, c1 = NTT(u) (.) pk1 -- the reference transforms u twice; here NTT(u) sits in

@@ -54,6 +54,8 @@ void emu_tma_4d(bool load, const TensorMap *m, void *smem, int c0, int c1, int c
 using namespace nttb200;
 
 static int g_which = -1;   // -1: whole transform, 0 / 1: only the first / second kernel in execution order
+static const unsigned char *g_gen_src = nullptr;   // next forward strided pass generates its input (NttArgs::gen_src)
+static size_t g_gen_stride = 0;
 
 template <class P, int LOGN, bool INV>
 static void run_one(const NttArgs &A)
@@ -140,6 +142,7 @@ int emu_ntt(int inverse, int barrett, int use_tma, int logn, u64 *a, const u64 *
     A.group_stride = group_polys ? group_stride : ((size_t)num << logn);
     A.a = a; A.tw = tw; A.tws = tws; A.lc = lc; A.qv = qv; A.muv = muv; A.qbitv = qbitv;
     A.num = num; A.division = division; A.use_tma = (u32)use_tma;
+    A.gen_src = inverse ? nullptr : g_gen_src; A.gen_stride = g_gen_stride;
     if (barrett == 2 && !inverse) return run_logn<ShoupLazyPolicy, false>(logn, A);
     if (barrett == 2 && inverse) return run_logn<ShoupLazyInvPolicy, true>(logn, A);
     if (barrett != 1) return inverse ? run_logn<ShoupPolicy, true>(logn, A) : run_logn<ShoupPolicy, false>(logn, A);
@@ -275,8 +278,16 @@ EXPORT int emu_bfv(int op, unsigned n, unsigned r, const u64 *q, const u64 *mu, 
     } else if (op == 1) {   // encrypt
         const size_t stride = 9 * (size_t)n; const u64 nblk = stride / 64;
         ew([&] { k_salsa20_keystream(in, nblk, (u64)batch, stride, key, nonce0); });
-        ew3(batch, 1, [&] { k_encrypt_sample(in, stride, c, es, n, r, batch, q); });
-        ring_ntt(R, false, c, batch * r, r, r, 2 * rn);
+        if (R.barrett == 1) {
+            ew3(batch, 1, [&] { k_encrypt_sample(in, stride, c, es, n, r, batch, q); });
+            ring_ntt(R, false, c, batch * r, r, r, 2 * rn);
+        } else {           // context path: u generated inside the first strided pass
+            ew3(batch, 1, [&] { k_encrypt_gauss(in, stride, es, n, batch); });
+            g_gen_src = in; g_gen_stride = stride;
+            ring_ntt(R, false, c, batch * r, r, r, 2 * rn, 0);
+            g_gen_src = nullptr;
+            ring_ntt(R, false, c, batch * r, r, r, 2 * rn, 1);
+        }
         ew3(r, batch, [&] { k_encrypt_mul(c, pk, per_item_keys ? 2 * rn : 0, n, r, batch, L); });
         ring_ntt(R, true, c, batch * 2 * r, r, 0, 0);
         if (r > 1) ew3(2 * ((r - 1 + kEncChunk - 1) / kEncChunk), batch, [&] { if (g_epi_fast) k_encrypt_epilogue<true>(c, es, m, (size_t)n, n, r, batch, t, qi_div_t, L); else k_encrypt_epilogue<false>(c, es, m, (size_t)n, n, r, batch, t, qi_div_t, L); });
@@ -286,9 +297,11 @@ EXPORT int emu_bfv(int op, unsigned n, unsigned r, const u64 *q, const u64 *mu, 
         u64 *pk_s = new u64[2 * rn];
         ew([&] { k_build_companions(pk, pk_s, q, R.logn, r, 2 * r); });
         ew([&] { k_salsa20_keystream(in, nblk, (u64)batch, stride, key, nonce0); });
-        ew3(batch, 1, [&] { k_encrypt_sample(in, stride, c, es, n, r, batch, q); });
+        ew3(batch, 1, [&] { k_encrypt_gauss(in, stride, es, n, batch); });
         if (op == 5) R.barrett = -1;
+        g_gen_src = in; g_gen_stride = stride;
         ring_ntt(R, false, c, batch * r, r, r, 2 * rn, 0);
+        g_gen_src = nullptr;
         ring_fused(R, op == 3, c, 2 * r, 2 * rn, pk, pk_s, rn, r, 0, 0, r, batch, 2);
         ring_ntt(R, true, c, batch * 2 * r, r, 0, 0, 1);
         if (r > 1) ew3(2 * ((r - 1 + kEncChunk - 1) / kEncChunk), batch, [&] { if (g_epi_fast) k_encrypt_epilogue<true>(c, es, m, (size_t)n, n, r, batch, t, qi_div_t, L); else k_encrypt_epilogue<false>(c, es, m, (size_t)n, n, r, batch, t, qi_div_t, L); });

@@ -55,6 +55,8 @@ struct NttArgsHost {
     int use_tma;
     unsigned group_polys = 0;   // 0 = one contiguous [num][n] array
     size_t group_stride = 0;    // elements between groups
+    const unsigned char *gen_src = nullptr;   // forward strided pass: generate the input from keystream bytes (NttArgs::gen_src)
+    size_t gen_stride = 0;
 };
 
 int launch_fused_mul(bool lazy, unsigned logn, const NttArgsHost &h, const u64 *twi, const u64 *twis, const u64 *key, const u64 *key_s,

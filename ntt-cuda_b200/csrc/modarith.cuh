@@ -198,4 +198,13 @@ __host__ __device__ __forceinline__ u64 barrett_lazy(u64 a, u64 b, u64 q, u64 mu
 // (x * 2^-1) mod q for canonical x, as the reference does after every inverse stage (ntt_60bit.cuh:165, 494-513)
 __host__ __device__ __forceinline__ u64 half_mod(u64 x, u64 q2) { return (x >> 1) + (q2 & (0 - (x & 1))); }
 
+// The reference's ternary converter, bfv_keygen.cuh:18-30 / bfv_encryption.cuh:23-36: int(float(byte) / (255.0f/3)) - 1 in {-1, 0, 1, 2}; negative -> q - 1
+__host__ __device__ __forceinline__ u64 ternary_value(unsigned char byte, u64 q)
+{
+    float d = (float)byte;
+    d /= (255.0f / 3);
+    int b = int(d) - 1;
+    return (u64)(b < 0) * q + (u64)(long long)b;
+}
+
 }  // namespace nttb200

@@ -49,6 +49,10 @@ struct NttArgs {
     size_t group_stride;  //   group_polys = num for one contiguous [num][n] array (the reference's layout)
     u32 use_tma;          // bit 0: TMA tile movement; bits 1/2 (profiling only): skip the butterflies / skip the tile traffic
     u32 pf_dist;          // > 0: CTA b prefetches the tile of CTA b + pf_dist into L2 (about one wave of resident CTAs ahead)
+    // forward strided pass only: when set, the input is not read from `a` but GENERATED -- coefficient j of every polynomial of
+    // group g is ternary_value(gen_src[g * gen_stride + j], q_limb)  (encryption's u, bfv_encryption.cuh:23-36)
+    const unsigned char *gen_src;
+    size_t gen_stride;
 };
 
 // ---- stage split per ring degree: K1 = S1+S2+S3 strided stages (rounds of 3 or 4), K2 contiguous stages -------
@@ -467,7 +471,8 @@ ntt_strided_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
 #ifndef NTTB200_EMU
     // The tile loads are issued FIRST, by the thread that also initialises their barriers (no CTA barrier in between): limb constants,
     // index arithmetic and twiddle prefetches of everybody else then run under the HBM latency.
-    if (!dbg_nomem && tma && tid == 0) {
+    const bool gen = !INV && A.gen_src != nullptr;
+    if (!dbg_nomem && tma && !gen && tid == 0) {
         for (int tt = 0; tt < TPC; tt++) mbar_init(bar + tt, 1);
         fence_mbar_init();
         for (int tt = 0; tt < TPC; tt++) {
@@ -485,6 +490,8 @@ ntt_strided_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
                 for (int rc = 0; rc < R / RB; rc++) tma_prefetch_4d(&tmap, (int)fcol + k * 16, rc * RB, (int)fidx, (int)fgrp);
         }
     }
+#else
+    const bool gen = !INV && A.gen_src != nullptr;
 #endif
     P pol;
     pol.init(A, p % A.division, n);
@@ -497,6 +504,23 @@ ntt_strided_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
     }
 
     if (dbg_nomem) {
+        __syncthreads();
+    } else if (gen) {
+        // one 16-byte load per (tile, row): the 16 keystream bytes of that row segment become its 16 coefficients (the row stores of
+        // neighbouring lanes conflict on banks, which costs LSU wavefronts but no issue slots: 4 KB of input per CTA instead of 32 KB)
+        const unsigned char *src = A.gen_src + (size_t)grp * A.gen_stride + colbase;
+        for (u32 e = tid; e < (u32)(TPC * NT) * R; e += THREADS) {
+            const u32 k = e / R, row = e % R;
+            const uint4 b16 = *reinterpret_cast<const uint4 *>(src + (size_t)row * C + k * 16);
+            const u32 w[4] = {b16.x, b16.y, b16.z, b16.w};
+            u64 *dst = tiles0 + (size_t)e * 16;
+            NTT_UNROLL
+            for (u32 c = 0; c < 8; c++) {                              // chunk c = coefficients 2c, 2c+1 = bytes 2c, 2c+1
+                const u32 word = w[c >> 1] >> ((c & 1u) * 16u);
+                *reinterpret_cast<ulonglong2 *>(dst + 2 * c) =
+                    make_ulonglong2(ternary_value((unsigned char)(word & 0xffu), pol.q), ternary_value((unsigned char)((word >> 8) & 0xffu), pol.q));
+            }
+        }
         __syncthreads();
     } else if (tma) {
 #ifdef NTTB200_EMU
@@ -521,7 +545,7 @@ ntt_strided_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
         u64 *tiles = tiles0 + tt * TILE_ELEMS;
         u64 *tile = tiles + (size_t)(tid >> K1) * R * 16;
 #ifndef NTTB200_EMU
-        if (!dbg_nomem && tma) mbar_wait(bar + tt, 0);
+        if (!dbg_nomem && tma && !gen) mbar_wait(bar + tt, 0);
 #endif
         if (dbg_nocompute) {
         } else if (!INV) {

@@ -160,6 +160,7 @@ int launch_ntt_pass(bool inverse, int policy, unsigned logn, const NttArgsHost &
     A.qv = h.qv; A.muv = h.muv; A.qbitv = h.qbitv;
     A.q = h.q; A.mu = h.mu; A.qbit = h.qbit;
     A.num = h.num; A.division = h.division; A.use_tma = (u32)h.use_tma; A.pf_dist = 0;
+    A.gen_src = h.gen_src; A.gen_stride = h.gen_stride;
     A.group_polys = h.group_polys ? h.group_polys : h.num;
     A.group_stride = h.group_polys ? h.group_stride : ((size_t)h.num << logn);
     const unsigned groups = (h.num + A.group_polys - 1) / A.group_polys;
@@ -222,7 +223,7 @@ int launch_fused_mul(bool lazy, unsigned logn, const NttArgsHost &h, const u64 *
     NttArgs &A = F.A;
     A.a = h.a; A.tw = h.tw; A.tws = h.tws; A.lc = h.lc;
     A.qv = nullptr; A.muv = nullptr; A.qbitv = nullptr; A.q = 0; A.mu = 0; A.qbit = 0;
-    A.num = items * r; A.division = r; A.use_tma = (u32)h.use_tma; A.pf_dist = 0;
+    A.num = items * r; A.division = r; A.use_tma = (u32)h.use_tma; A.pf_dist = 0; A.gen_src = nullptr; A.gen_stride = 0;
     A.group_polys = h.group_polys; A.group_stride = h.group_stride;
     F.twi = twi; F.twis = twis; F.key = key; F.key_s = key_s;
     F.key_item_stride = key_item_stride; F.key_half_stride = key_half_stride;
@@ -281,7 +282,7 @@ int launch_polymul(bool lazy, unsigned logn, const NttArgsHost &ha, const u64 *t
     NttArgs &A = F.A;
     A.a = ha.a; A.tw = ha.tw; A.tws = ha.tws; A.lc = ha.lc;
     A.qv = nullptr; A.muv = nullptr; A.qbitv = nullptr; A.q = 0; A.mu = 0; A.qbit = 0;
-    A.num = ha.num; A.division = ha.division; A.use_tma = (u32)ha.use_tma; A.pf_dist = 0;
+    A.num = ha.num; A.division = ha.division; A.use_tma = (u32)ha.use_tma; A.pf_dist = 0; A.gen_src = nullptr; A.gen_stride = 0;
     A.group_polys = ha.group_polys ? ha.group_polys : ha.num;
     A.group_stride = ha.group_polys ? ha.group_stride : ((size_t)ha.num << logn);
     F.b = b; F.twi = twi; F.twis = twis; F.out = out ? out : A.a;
