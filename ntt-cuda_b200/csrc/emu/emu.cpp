@@ -393,6 +393,21 @@ EXPORT int emu_bfv_sharded(int op, unsigned n, unsigned r, const u64 *q, const u
     return 0;
 }
 
+// wire format + homomorphic helper kernels on the emulator (op 0: pack, 1: unpack, 2: ct add, 3: plaintext lift)
+EXPORT int emu_ct_ops(int op, u64 *c, u64 *other, unsigned n, unsigned r, unsigned batch, const u64 *q, const u32 *qbit, const u32 *word_off,
+                      u32 half_words, u64 t)
+{
+    emu_dim3 g; g.x = 2; g.y = r - 1; g.z = 2 * batch;
+    switch (op) {
+    case 0: emu_launch(g, 64, 0, [&] { k_ct_pack(c, other, n, r, batch, qbit, word_off, half_words); }); break;
+    case 1: emu_launch(g, 64, 0, [&] { k_ct_unpack(other, c, n, r, batch, qbit, word_off, half_words); }); break;
+    case 2: emu_launch(g, 64, 0, [&] { k_ct_add(c, other, n, r, batch, q); }); break;
+    case 3: { emu_dim3 g2; g2.x = 2; g2.y = batch; emu_launch(g2, 64, 0, [&] { k_plain_lift(other, (size_t)n, c, n, r - 1, batch, t, q); }); break; }
+    default: return 1;
+    }
+    return 0;
+}
+
 // device-side table generation on the emulator
 EXPORT int emu_build_tables(u64 *psi, u64 *psi_s, u64 *psiinv, u64 *psiinv_s, const u64 *q, const u64 *roots, const u64 *roots_inv,
                             unsigned logn, unsigned limbs)

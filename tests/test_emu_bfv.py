@@ -172,3 +172,49 @@ def test_all_lazy_epilogues_match_oracle(oracle):
             assert np.array_equal(out[0], m)
     finally:
         emu.lib().emu_set_epilogue_fast(0)
+
+
+def test_wire_format_and_homomorphic_helper_kernels_on_emulator(oracle):
+    """k_ct_pack / k_ct_unpack (format definition in include/nttb200.h, restated here with numpy), k_ct_add and k_plain_lift."""
+    import ctypes as C
+    n, qs, _ = params.RNS_SETS["4k_3q"]
+    r, batch, t = len(qs), 2, params.T
+    qa = np.array(qs, dtype=np.uint64)
+    qbit = np.array([int(q).bit_length() for q in qs], dtype=np.uint32)
+    woff = np.zeros(r - 1, dtype=np.uint32)
+    for l in range(1, r - 1):
+        woff[l] = woff[l - 1] + n // 64 * qbit[l - 1]
+    half_words = int(woff[-1] + n // 64 * qbit[r - 2])
+    c = np.concatenate([oracle.fill_uniform(n, qs[l], 0x77 + 10 * k + l) for k in range(batch * 2) for l in range(r)])
+    c[0], c[1] = 0, qs[0] - 1
+    packed = np.zeros(batch * 2 * half_words, dtype=np.uint64)
+    u, u32 = C.c_ulonglong, C.c_uint
+    lib = emu.lib()
+    assert lib.emu_ct_ops(0, emu.p(c, u), emu.p(packed, u), n, r, batch, emu.p(qa, u), emu.p(qbit, u32), emu.p(woff, u32), half_words, C.c_ulonglong(t)) == 0
+    hc = c.reshape(batch * 2, r, n)
+    exp = []
+    for kh in range(batch * 2):
+        for l in range(r - 1):
+            bits = ((hc[kh, l][:, None] >> np.arange(int(qbit[l]), dtype=np.uint64)[None, :]) & np.uint64(1)).astype(np.uint8).reshape(-1)
+            exp.append(np.packbits(bits, bitorder="little").view(np.uint64))
+    assert np.array_equal(packed, np.concatenate(exp))
+    back = np.full_like(c, 0xFFFFFFFFFFFFFFFF)
+    assert lib.emu_ct_ops(1, emu.p(back, u), emu.p(packed, u), n, r, batch, emu.p(qa, u), emu.p(qbit, u32), emu.p(woff, u32), half_words, C.c_ulonglong(t)) == 0
+    hb = back.reshape(batch * 2, r, n)
+    assert np.array_equal(hb[:, :r - 1], hc[:, :r - 1]) and (hb[:, r - 1] == np.uint64(0xFFFFFFFFFFFFFFFF)).all()   # padding limb is the caller's
+    # limb-wise addition on the stored limbs
+    d = np.concatenate([oracle.fill_uniform(n, qs[l], 0x99 + 10 * k + l) for k in range(batch * 2) for l in range(r)])
+    s = c.copy()
+    assert lib.emu_ct_ops(2, emu.p(s, u), emu.p(d, u), n, r, batch, emu.p(qa, u), emu.p(qbit, u32), emu.p(woff, u32), half_words, C.c_ulonglong(t)) == 0
+    hs, hd = s.reshape(batch * 2, r, n), d.reshape(batch * 2, r, n)
+    for l in range(r - 1):
+        assert np.array_equal(hs[:, l], (hc[:, l] + hd[:, l]) % np.uint64(qs[l]))
+    assert np.array_equal(hs[:, r - 1], hc[:, r - 1])
+    # centred plaintext lift
+    m = oracle.fill_uniform(batch * n, 1 << 20, 0x4242)                      # deliberately not reduced mod t
+    P = np.zeros(batch * (r - 1) * n, dtype=np.uint64)
+    assert lib.emu_ct_ops(3, emu.p(P, u), emu.p(m, u), n, r, batch, emu.p(qa, u), emu.p(qbit, u32), emu.p(woff, u32), half_words, C.c_ulonglong(t)) == 0
+    mm = (m % np.uint64(t)).reshape(batch, n).astype(np.int64)
+    cen = np.where(mm <= t // 2, mm, mm - t)
+    for l in range(r - 1):
+        assert np.array_equal(P.reshape(batch, r - 1, n)[:, l], (cen % qs[l]).astype(np.uint64))
