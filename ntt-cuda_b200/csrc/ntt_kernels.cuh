@@ -591,81 +591,6 @@ ntt_strided_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
     (void)bar;
 }
 
-// ---- EXPERIMENT: persistent, double-buffered strided pass (TMA path only, schedules with at least two rounds) ----------------------
-// A CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the load of the next tile is issued between the rounds of the current
-// one into the other buffer, so no tile wait is exposed after the first.
-#ifndef NTTB200_EMU
-template <class P, int LOGN, bool INV>
-__global__ void __launch_bounds__((1 << Sched<LOGN>::K1) * Sched<LOGN>::NT, ((1 << Sched<LOGN>::K1) * Sched<LOGN>::NT) > 256 ? 2 : NTT_MINB_S)
-ntt_strided_persist(const __grid_constant__ TensorMap tmap, NttArgs A, u32 total)
-{
-    using SC = Sched<LOGN>;
-    constexpr int K1 = SC::K1, R = 1 << K1, NT = SC::NT;
-    constexpr u32 n = 1u << LOGN, C = n >> K1;
-    constexpr int RB = R > 256 ? 256 : R;
-    constexpr u32 TG = (C >> 4) / NT;                   // tiles per polynomial
-    constexpr size_t TILE_ELEMS = (size_t)NT * R * 16;
-    static_assert(SC::S2 != 0, "needs two rounds");
-    NTT_DYN_SMEM(raw);
-    u64 *buf = align_1024(raw);
-    u64 *bar = buf + 2 * TILE_ELEMS;
-    const u32 tid = threadIdx.x, u = tid & (R - 1);
-    u32 w = blockIdx.x;
-    if (w >= total) return;
-    auto issue = [&](u32 ww, u32 b) {
-        const u32 p = ww / TG, colbase = (ww % TG) * (NT * 16);
-        const u32 grp = p / A.group_polys, idx = p - grp * A.group_polys;
-        mbar_expect_tx(bar + b, (u32)(NT * R * 128));
-        for (int k = 0; k < NT; k++)
-            for (int rc = 0; rc < R / RB; rc++)
-                tma_load_4d(buf + b * TILE_ELEMS + ((size_t)k * R + rc * RB) * 16, &tmap, bar + b, (int)colbase + k * 16, rc * RB, (int)idx, (int)grp);
-    };
-    if (tid == 0) {
-        mbar_init(bar, 1); mbar_init(bar + 1, 1);
-        fence_mbar_init();
-        issue(w, 0);
-    }
-    __syncthreads();
-    for (u32 i = 0; w < total; i++, w += gridDim.x) {
-        const u32 b = i & 1u;
-        const u32 p = w / TG, colbase = (w % TG) * (NT * 16);
-        const u32 grp = p / A.group_polys, idx = p - grp * A.group_polys;
-        P pol;
-        pol.init(A, p % A.division, n);
-        prefetch_round<SC::S2>(pol, (1u << SC::S1) + ((u >> SC::S2) >> (K1 - SC::S1 - SC::S2)));
-        if constexpr (SC::S3 != 0) prefetch_round<SC::S3>(pol, (1u << (SC::S1 + SC::S2)) + (u >> SC::S3));
-        if (u < 32) prefetch_round<SC::S1>(pol, 1u);
-        u64 *tiles = buf + b * TILE_ELEMS;
-        u64 *tile = tiles + (size_t)(tid >> K1) * R * 16;
-        mbar_wait(bar + b, (i >> 1) & 1u);
-        if (!INV) strided_round<P, K1, 0, SC::S1, false>(tile, u, pol);
-        else if constexpr (SC::S3 != 0) strided_round<P, K1, SC::S1 + SC::S2, SC::S3, true>(tile, u, pol);
-        else strided_round<P, K1, SC::S1, SC::S2, true>(tile, u, pol);
-        if (tid == 0) {                                   // next tile into the other buffer (its previous store had a whole round to drain)
-            const u32 wn = w + gridDim.x;
-            if (wn < total) { tma_store_wait_read<0>(); issue(wn, b ^ 1u); }
-        }
-        __syncthreads();
-        if (!INV) {
-            strided_round<P, K1, SC::S1, SC::S2, false>(tile, u, pol);
-            if constexpr (SC::S3 != 0) { __syncthreads(); strided_round<P, K1, SC::S1 + SC::S2, SC::S3, false>(tile, u, pol); }
-        } else {
-            if constexpr (SC::S3 != 0) { strided_round<P, K1, SC::S1, SC::S2, true>(tile, u, pol); __syncthreads(); }
-            strided_round<P, K1, 0, SC::S1, true>(tile, u, pol);
-        }
-        fence_proxy_async();
-        __syncthreads();
-        if (tid == 0) {
-            for (int k = 0; k < NT; k++)
-                for (int rc = 0; rc < R / RB; rc++)
-                    tma_store_4d(&tmap, tiles + ((size_t)k * R + rc * RB) * 16, (int)colbase + k * 16, rc * RB, (int)idx, (int)grp);
-            tma_store_commit();
-        }
-    }
-    if (tid == 0) tma_store_wait_read<0>();
-}
-#endif
-
 // ---- pass "contig": grid (num * n / 16 / 128 / TPC), 128 threads; CTA = TPC x 128 consecutive rows of one polynomial ---------------------------------
 template <class P, int LOGN, bool INV>
 __global__ void __launch_bounds__(kContigRows, Sched<LOGN>::K2 == 8 ? 4 : NTT_MINB_C)   // radix-16 first round needs > 80 registers

@@ -5,7 +5,6 @@
 #include "ntt_kernels.cuh"
 
 #include <cstdlib>
-#include <type_traits>
 #include <mutex>
 
 namespace nttb200 {
@@ -113,28 +112,6 @@ static int launch_one(const NttArgs &A, int which, unsigned cnt, const CUtensorM
     NttArgs As = A, Ac = A;
     As.pf_dist = (dev >= 0 && dev < 64) ? pf_dist_for(dev, occ_s[dev]) : 0;
     Ac.pf_dist = (dev >= 0 && dev < 64) ? pf_dist_for(dev, occ_c[dev]) : 0;
-    // EXPERIMENT (NTTB200_PERSIST=1): persistent double-buffered strided pass
-    static int persist = -1;
-    if (persist < 0) { const char *e = getenv("NTTB200_PERSIST"); persist = (e && e[0] == '1') ? 1 : 0; }
-    if constexpr (SC::S2 != 0 && !std::is_same<P, BarrettPolicy>::value) {
-        if (persist && do_strided && (A.use_tma == 1u) && !A.gen_src) {
-            constexpr size_t smem_p = (size_t)2 * SC::NT * R * 128 + 1024 + 64;
-            static int occ_p = 0;
-            if (!occ_p) {
-                NTTB200_CHECK(cudaFuncSetAttribute(ntt_strided_persist<P, LOGN, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, ntt_strided_persist<P, LOGN, INV>, R * SC::NT, smem_p);
-            }
-            int sms = 0;
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            const unsigned total = cnt * tiles_s;
-            unsigned grid = (unsigned)(occ_p * sms);
-            if (grid > total) grid = total;
-            if (INV && do_contig) ntt_contig_pass<P, LOGN, INV><<<gc, kContigRows, smem_c, st>>>(mc, Ac);
-            ntt_strided_persist<P, LOGN, INV><<<grid, R * SC::NT, smem_p, st>>>(ms, As, total);
-            if (!INV && do_contig) ntt_contig_pass<P, LOGN, INV><<<gc, kContigRows, smem_c, st>>>(mc, Ac);
-            { const int e__ = (int)cudaGetLastError(); return e__ ? nttb200_trace_error(e__, __FILE__, __LINE__) : 0; }
-        }
-    }
     if (!INV) {
         if (do_strided) ntt_strided_pass<P, LOGN, INV><<<gs, R * SC::NT, smem_s, st>>>(ms, As);
         if (do_contig) ntt_contig_pass<P, LOGN, INV><<<gc, kContigRows, smem_c, st>>>(mc, Ac);
