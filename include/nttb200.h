@@ -200,6 +200,8 @@ NTTB200_API int nttb200_bfv_unpack(nttb200_bfv *bfv, nttb200_u64 *c, const nttb2
  * c_a <- c_a + c_b  (Dec = m_a + m_b mod t), and  c <- c * p  for a plaintext polynomial p[n] or p[batch][n]
  * (Dec = m * p mod (X^n + 1, t); coefficients of p are taken mod t and lifted centred).  The padding limb is left alone. */
 NTTB200_API int nttb200_bfv_add(nttb200_bfv *bfv, nttb200_u64 *c_a, const nttb200_u64 *c_b, unsigned batch, void *stream);
+NTTB200_API int nttb200_bfv_add_plain(nttb200_bfv *bfv, nttb200_u64 *c, const nttb200_u64 *m_poly, int plain_per_item, unsigned batch,
+                                      void *stream);   /* Dec = m_c + m mod t (the Delta*m scaling of bfv_encryption.cuh:193-212) */
 NTTB200_API int nttb200_bfv_mul_plain(nttb200_bfv *bfv, nttb200_u64 *c, const nttb200_u64 *p_poly, int plain_per_item, unsigned batch,
                                       void *stream);
 

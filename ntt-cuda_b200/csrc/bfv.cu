@@ -412,6 +412,16 @@ int nttb200_bfv_add(nttb200_bfv *b, nttb200_u64 *c_a, const nttb200_u64 *c_b, un
     KCHECK();
     return 0;
 }
+// c <- c + m for a plaintext polynomial m (one per item, or one for the whole batch): Dec(result) = m_c + m mod t.
+int nttb200_bfv_add_plain(nttb200_bfv *b, nttb200_u64 *c, const nttb200_u64 *m_poly, int plain_per_item, unsigned batch, void *stream)
+{
+    if (!b || !c || !m_poly || !batch || batch > 65535) return NTTB200_EINVAL;
+    const unsigned n = b->n, r = b->r;
+    k_ct_add_plain<<<pair_grid(n, r - 1, batch), pair_block(n, r - 1, batch), 0, (cudaStream_t)stream>>>(c, m_poly, plain_per_item ? (size_t)n : 0, n, r,
+                                                                                                 batch, b->t, b->ctx->q_dev, b->qi_div_t);
+    KCHECK();
+    return 0;
+}
 // c <- c * p for a plaintext polynomial p (coefficients taken mod t, centred lift): Dec(result) = m * p mod (X^n + 1, t).
 // One plaintext for the whole batch (plain_per_item = 0) or one per item.  Per call: lift, NTT of the plaintext limbs, NTT of both
 // ciphertext halves, the coefficient-wise product fused into the first inverse kernel, strided inverse pass.

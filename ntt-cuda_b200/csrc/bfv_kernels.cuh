@@ -572,6 +572,22 @@ NTT_KERNEL void k_ct_add(u64 *ca, const u64 *cb, unsigned n, unsigned r, unsigne
         st2(ca + off + j, csub(a.x + b.x, ql), csub(a.y + b.y, ql));
     }
 }
+// c0 += Delta * m + round-fix on the limbs below the dropped one: the scaling encryption applies to its message (weird_m_stuff,
+// bfv_encryption.cuh:193-212), so Dec(c + plain m) = m_c + m mod t.  Message coefficients are taken mod t.  grid (x, r-1, batch)
+NTT_KERNEL void k_ct_add_plain(u64 *c, const u64 *m, size_t m_stride, unsigned n, unsigned r, unsigned batch, u64 t, const u64 *q,
+                               const u64 *qi_div_t)
+{
+    (void)batch;
+    const unsigned l = blockIdx.y;
+    const size_t k = blockIdx.z;
+    const u64 ql = q[l], qdt = qi_div_t[l], tfix = (t + 1) >> 1;
+    u64 *c0 = c + k * 2 * r * n + (size_t)l * n;
+    NTT_PAIR_STRIDE(j, n) {
+        const ulonglong2 a = ld2(c0 + j), mv = ld2(m + k * m_stride + j);
+        const u64 m0 = mv.x % t, m1 = mv.y % t;
+        st2(c0 + j, csub(a.x + m0 * qdt + (m0 + tfix) / t, ql), csub(a.y + m1 * qdt + (m1 + tfix) / t, ql));
+    }
+}
 // centred lift of a plaintext polynomial (coefficients reduced mod t first) to every limb below the dropped one:
 // P[k][l][j] = m mod q_l for m <= t/2, m - t mod q_l otherwise.  grid (x, items)
 NTT_KERNEL void k_plain_lift(const u64 *m, size_t m_stride, u64 *P, unsigned n, unsigned rp, unsigned items, u64 t, const u64 *q)

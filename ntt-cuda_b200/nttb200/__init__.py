@@ -333,6 +333,11 @@ class Bfv:
         """c_a <- c_a + c_b (homomorphic addition: Dec = m_a + m_b mod t)."""
         check(lib().nttb200_bfv_add(self._h, vp(ptr(c_a)), vp(ptr(c_b)), C.c_uint(batch), vp(_stream(stream))))
 
+    def add_plain(self, c, m_poly, batch=1, plain_per_item=False, stream=None):
+        """c <- c + m for a plaintext polynomial m[n] (or m[batch][n]): Dec = m_c + m mod t."""
+        check(lib().nttb200_bfv_add_plain(self._h, vp(ptr(c)), vp(ptr(m_poly)), C.c_int(int(plain_per_item)), C.c_uint(batch),
+                                          vp(_stream(stream))))
+
     def mul_plain(self, c, p_poly, batch=1, plain_per_item=False, stream=None):
         """c <- c * p for a plaintext polynomial p[n] (or p[batch][n]): Dec = m * p mod (X^n + 1, t)."""
         check(lib().nttb200_bfv_mul_plain(self._h, vp(ptr(c)), vp(ptr(p_poly)), C.c_int(int(plain_per_item)), C.c_uint(batch),

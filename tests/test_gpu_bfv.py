@@ -334,6 +334,15 @@ def test_homomorphic_add_and_plain_multiply(oracle, name, batch):
     bfv.add(s, c2, batch=batch)
     bfv.decrypt(out, s.clone(), sk, batch=batch)
     assert np.array_equal(to_host(out), (m1 + m2) % np.uint64(t))
+    # plaintext addition (shared plaintext, then one per item)
+    s = c1.clone()
+    bfv.add_plain(s, to_dev(m2[:n]), batch=batch)
+    bfv.decrypt(out, s, sk, batch=batch)
+    assert np.array_equal(to_host(out), (m1 + np.tile(m2[:n], batch)) % np.uint64(t))
+    s = c1.clone()
+    bfv.add_plain(s, to_dev(m2), batch=batch, plain_per_item=True)
+    bfv.decrypt(out, s, sk, batch=batch)
+    assert np.array_equal(to_host(out), (m1 + m2) % np.uint64(t))
     # plaintext multiplication: a sparse factor keeps the schoolbook reference cheap; one shared factor, then one per item
     def negacyclic_mod_t(a, b):
         res = np.zeros(n, dtype=np.int64)

@@ -126,3 +126,12 @@ def test_bfv_gpu_vs_reference_pipelines(name):
     assert np.array_equal(to_host(outp), u64v("plain")) and np.array_equal(to_host(outp), m)
     bfv.close()
     ctx_psi.close()
+
+
+def test_native_cpp_example_runs():
+    """examples/bfv_batched.cpp: the C ABI used from plain C++ (keygen, load_keys, batched encrypt, wire format, homomorphic add, decrypt)."""
+    exe = os.path.join(ROOT, "ntt-cuda_b200", "build", "example_bfv_batched")
+    if not os.path.exists(exe):
+        pytest.skip("example not built (python -c 'import __graft_entry__ as g; g.build()')")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr
