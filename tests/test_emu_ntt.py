@@ -47,6 +47,8 @@ CASES = [
     (17, 1, 1, 0, 1), (17, 1, 1, 1, 0),
     # policy 2 = lazy forward (no intermediate corrections, q < 2^58); the 60-bit primes above stay on policy 0
     (11, 1, 2, 2, 1), (13, 3, 3, 2, 0), (15, 3, 3, 2, 1),
+    # getParams(4096) is a 25-bit prime: floor(2^64/q) does not fit 32 bits, so the lazy forward transform takes the general final reduction
+    (12, 1, 2, 2, 1),
 ]
 
 
