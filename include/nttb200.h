@@ -198,7 +198,9 @@ NTTB200_API int nttb200_bfv_unpack(nttb200_bfv *bfv, nttb200_u64 *c, const nttb2
 
 /* Homomorphic operations on ciphertexts in the reference layout (the reference stops at decryption):
  * c_a <- c_a + c_b  (Dec = m_a + m_b mod t), and  c <- c * p  for a plaintext polynomial p[n] or p[batch][n]
- * (Dec = m * p mod (X^n + 1, t); coefficients of p are taken mod t and lifted centred).  The padding limb is left alone. */
+ * (Dec = m * p mod (X^n + 1, t); coefficients of p are taken mod t and lifted centred).  The padding limb is left alone.
+ * nttb200_bfv_mul_plain keeps a grow-only device scratch for the transformed plaintext limbs: the first call (or a larger batch)
+ * allocates, so warm it up before capturing it into a CUDA graph. */
 NTTB200_API int nttb200_bfv_add(nttb200_bfv *bfv, nttb200_u64 *c_a, const nttb200_u64 *c_b, unsigned batch, void *stream);
 NTTB200_API int nttb200_bfv_add_plain(nttb200_bfv *bfv, nttb200_u64 *c, const nttb200_u64 *m_poly, int plain_per_item, unsigned batch,
                                       void *stream);   /* Dec = m_c + m mod t (the Delta*m scaling of bfv_encryption.cuh:193-212) */
