@@ -143,6 +143,11 @@ struct ShoupPolicy {
         Y = x - T + twoq;
     }
     __device__ __forceinline__ u64 fwd_final(u64 x) const { return csub(csub(x, twoq), q); }
+    __device__ __forceinline__ void fwd_final_all(u64 (&v)[16]) const
+    {
+        NTT_UNROLL
+        for (int i = 0; i < 16; i++) v[i] = fwd_final(v[i]);
+    }
     // inverse (Gentleman-Sande), U,V in [0,2q) -> [0,2q)
     __device__ __forceinline__ void gs(u64 &U, u64 &V, const Tw &t) const
     {
@@ -170,11 +175,17 @@ struct ShoupPolicy {
 // The inverse transform is ShoupPolicy's.
 struct ShoupLazyPolicy : ShoupPolicy {
     u64 ratio, fourq;
+    u32 pm_delta, pm_bits;      // q = 2^pm_bits - pm_delta with 69 * pm_delta < q (pm_bits = 0: not of that form)
     __device__ __forceinline__ void init(const NttArgs &A, u32 limb, u32 n)
     {
         ShoupPolicy::init(A, limb, n);
         ratio = l->ratio;
         fourq = twoq + twoq;
+        const u32 b = l->qbit;
+        const u64 d = (1ull << b) - q;                       // qbit <= 57 under this policy
+        const bool ok = d < (1ull << 32) && d * 69 < q;
+        pm_delta = (u32)d;
+        pm_bits = ok ? b : 0u;
     }
     __device__ __forceinline__ void ct(u64 &X, u64 &Y, const Tw &t) const
     {
@@ -183,17 +194,47 @@ struct ShoupLazyPolicy : ShoupPolicy {
         X = x + T;
         Y = x - T + fourq;
     }
-    // x < 69 q  ->  [0, q).  For q > 2^32 the quotient estimate needs ONE 32x32 multiplication: floor(x / q) is at most 2
-    // above hi32((x >> 32) * ratio) because ratio = floor(2^64 / q) < 2^32 (dropped: x_lo * ratio / 2^64 < 1, x / 2^64 < 1, the floor).
-    __device__ __forceinline__ u64 fwd_final(u64 x) const
+    // x < 69 q  ->  [0, q).
+    //  * q = 2^b - delta with a small delta (every prime of the reference's parameter sets: NTT primes are picked just below a
+    //    power of two): x = hi * 2^b + lo gives x - hi * q = lo + hi * delta < q + 69 delta < 2q -- a shift, a mask, one 32x32
+    //    multiplication and one conditional subtraction.  Measured: the general path below costs 14 % of the contiguous pass.
+    //  * otherwise, for q > 2^32: floor(x / q) is at most 2 above hi32((x >> 32) * ratio) because ratio = floor(2^64 / q) < 2^32
+    //    (dropped: x_lo * ratio / 2^64 < 1, x / 2^64 < 1, the floor).
+    __device__ __forceinline__ u64 final_pm(u64 x) const
     {
-        if ((ratio >> 32) == 0) {
-            const u64 qe = ((u64)(u32)(x >> 32) * (u64)(u32)ratio) >> 32;          // 32-bit quotient estimate
-            u64 r = x - ((u64)(u32)qe * (u64)(u32)q + (((u64)(u32)qe * (q >> 32)) << 32));   // x - qe * q  in [0, 3q)
-            return csub(csub(r, twoq), q);
-        }
+        const u32 hi = (u32)(x >> pm_bits);                  // x < 69 q < 2^(b + 7)
+        const u64 r = (x & ((1ull << pm_bits) - 1)) + (u64)hi * (u64)pm_delta;
+        return csub(r, q);
+    }
+    __device__ __forceinline__ u64 final_q32(u64 x) const
+    {
+        const u64 qe = ((u64)(u32)(x >> 32) * (u64)(u32)ratio) >> 32;          // 32-bit quotient estimate
+        u64 r = x - ((u64)(u32)qe * (u64)(u32)q + (((u64)(u32)qe * (q >> 32)) << 32));   // x - qe * q  in [0, 3q)
+        return csub(csub(r, twoq), q);
+    }
+    __device__ __forceinline__ u64 final_any(u64 x) const
+    {
         u64 r = x + mulhi64(x, ratio) * nq;     // x - floor(x * ratio / 2^64) * q  in [0, 2q)
         return csub(r, q);
+    }
+    __device__ __forceinline__ u64 fwd_final(u64 x) const
+    {
+        return pm_bits != 0 ? final_pm(x) : (ratio >> 32) == 0 ? final_q32(x) : final_any(x);
+    }
+    // the (CTA-uniform) choice is made ONCE for the 16 coefficients of a thread: each arm is then straight-line code with 16
+    // independent reductions (with the choice inside the loop ptxas emitted 16 branchy, serial blocks and the cheap arm bought nothing)
+    __device__ __forceinline__ void fwd_final_all(u64 (&v)[16]) const
+    {
+        if (pm_bits != 0) {
+            NTT_UNROLL
+            for (int i = 0; i < 16; i++) v[i] = final_pm(v[i]);
+        } else if ((ratio >> 32) == 0) {
+            NTT_UNROLL
+            for (int i = 0; i < 16; i++) v[i] = final_q32(v[i]);
+        } else {
+            NTT_UNROLL
+            for (int i = 0; i < 16; i++) v[i] = final_any(v[i]);
+        }
     }
 };
 
@@ -272,6 +313,7 @@ struct BarrettPolicy {
         Y = u - v;
     }
     __device__ __forceinline__ u64 fwd_final(u64 x) const { return x; }
+    __device__ __forceinline__ void fwd_final_all(u64 (&)[16]) const {}
     __device__ __forceinline__ void gs(u64 &U, u64 &V, const Tw &t) const
     {
         u64 u = U, v = V;
@@ -672,8 +714,9 @@ ntt_contig_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
             __syncwarp();
             regs_row<true, true>(tile, tid, v);
             ct_stages<4, 1>(v, twB, pol);
-            NTT_UNROLL
-            for (int i = 0; i < 16; i++) v[i] = pol.fwd_final(v[i]);
+#ifndef NTT_DBG_NOFINAL   /* profiling only (non-canonical results): what the final reduction costs */
+            pol.fwd_final_all(v);
+#endif
             regs_row<true, false>(tile, tid, v);
         } else {
             regs_row<true, true>(tile, tid, v);
@@ -916,16 +959,14 @@ ntt_contig_polymul(const __grid_constant__ TensorMap tmap_a, const __grid_consta
     if constexpr (B_FWD) {
         regs_row<true, true>(tile2, tid, v);
         ct_stages<4, 1>(v, twB, pf);
-        NTT_UNROLL
-        for (int i = 0; i < 16; i++) v[i] = pf.fwd_final(v[i]);
+        pf.fwd_final_all(v);
         regs_row<true, false>(tile2, tid, v);
     }
     // a: forward row round, canonical, (.) b, inverse row round
     regs_row<true, true>(tile, tid, v);
     if constexpr (A_FWD) {
         ct_stages<4, 1>(v, twB, pf);
-        NTT_UNROLL
-        for (int i = 0; i < 16; i++) v[i] = pf.fwd_final(v[i]);
+        pf.fwd_final_all(v);
     }
     NTT_UNROLL
     for (int c = 0; c < 8; c++) {
