@@ -408,6 +408,14 @@ EXPORT int emu_ct_ops(int op, u64 *c, u64 *other, unsigned n, unsigned r, unsign
     return 0;
 }
 
+// both ternary formulas for one byte (exhaustive equivalence test)
+EXPORT int emu_ternary(int which, unsigned byte)
+{
+    if (which == 0) return ternary_float_formula((unsigned char)byte);
+    const u64 v = ternary_value((unsigned char)byte, 1000);
+    return v == 999 ? -1 : (int)v;
+}
+
 // device-side table generation on the emulator
 EXPORT int emu_build_tables(u64 *psi, u64 *psi_s, u64 *psiinv, u64 *psiinv_s, const u64 *q, const u64 *roots, const u64 *roots_inv,
                             unsigned logn, unsigned limbs)

@@ -198,13 +198,22 @@ __host__ __device__ __forceinline__ u64 barrett_lazy(u64 a, u64 b, u64 q, u64 mu
 // (x * 2^-1) mod q for canonical x, as the reference does after every inverse stage (ntt_60bit.cuh:165, 494-513)
 __host__ __device__ __forceinline__ u64 half_mod(u64 x, u64 q2) { return (x >> 1) + (q2 & (0 - (x & 1))); }
 
-// The reference's ternary converter, bfv_keygen.cuh:18-30 / bfv_encryption.cuh:23-36: int(float(byte) / (255.0f/3)) - 1 in {-1, 0, 1, 2}; negative -> q - 1
+// The reference's ternary converter, bfv_keygen.cuh:18-30 / bfv_encryption.cuh:23-36: int(float(byte) / (255.0f/3)) - 1 in {-1, 0, 1, 2};
+// negative -> q - 1.  255.0f/3 is exactly 85.0f and byte/85.0f crosses an integer only AT 85, 170 and 255 (84/85, 169/85, 254/85 are
+// nowhere near one), so the float expression equals the threshold count below for all 256 bytes
+// (tests/test_oracle_golden.py::test_ternary_thresholds_equal_the_float_formula checks all of them against the float formula):
+// three compares instead of an IEEE division with its slow-path call.
 __host__ __device__ __forceinline__ u64 ternary_value(unsigned char byte, u64 q)
+{
+    const int b = (int)(byte >= 85) + (int)(byte >= 170) + (int)(byte == 255) - 1;
+    return (u64)(b < 0) * q + (u64)(long long)b;
+}
+// the literal float formula (kept for the exhaustive equivalence test and the emulator export)
+__host__ __device__ __forceinline__ int ternary_float_formula(unsigned char byte)
 {
     float d = (float)byte;
     d /= (255.0f / 3);
-    int b = int(d) - 1;
-    return (u64)(b < 0) * q + (u64)(long long)b;
+    return int(d) - 1;
 }
 
 }  // namespace nttb200

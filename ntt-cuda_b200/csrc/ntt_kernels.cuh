@@ -767,6 +767,8 @@ struct FusedArgs {
 };
 
 template <class PF, class PI, int LOGN, int NOUT>
+// two outputs: 168 registers and three CTAs per SM; parking the forward row in shared memory to reach 128 registers / four CTAs
+// spilled and measured 3 % slower (profiles/r01_experiments.md)
 __global__ void __launch_bounds__(kContigRows, NOUT == 2 ? 3 : 4)
 ntt_contig_fused_mul(const __grid_constant__ TensorMap tmap, FusedArgs F)
 {
@@ -826,8 +828,7 @@ ntt_contig_fused_mul(const __grid_constant__ TensorMap tmap, FusedArgs F)
     NTT_UNROLL
     for (int o = 0; o < NOUT; o++) {
         const u64 *kp = F.key + krow + (size_t)o * F.key_half_stride, *ks = F.key_s + krow + (size_t)o * F.key_half_stride;
-        u64 x[16];
-        NTT_UNROLL
+        u64 x[16];        NTT_UNROLL
         for (int c = 0; c < 8; c++) {
             const ulonglong2 kv = __ldg(reinterpret_cast<const ulonglong2 *>(kp) + c), sv = __ldg(reinterpret_cast<const ulonglong2 *>(ks) + c);
             x[2 * c] = pi.mul_key(v[2 * c], kv.x, sv.x);

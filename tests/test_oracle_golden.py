@@ -226,3 +226,20 @@ def test_oracle_bfv_matches_reference_gpu_outputs(oracle, name):
     assert _sha(c) == rec["c_sha256"] and _sha(ee) == rec["e_sha256"]
     plain, _ = oracle.decryption_rns(R, c, sk)
     assert _sha(plain) == rec["plain_sha256"] and np.array_equal(plain, m)
+
+
+def test_ternary_thresholds_equal_the_float_formula(oracle):
+    """csrc/modarith.cuh: ternary_value() counts thresholds (85, 170, 255) instead of evaluating int(float(b) / (255.0f/3)) - 1
+    (bfv_keygen.cuh:18-30).  All 256 bytes: the kernel source's two formulas (compiled for the CPU emulator), numpy float32, and the
+    oracle's converter agree."""
+    from tests import emu
+    lib = emu.lib()
+    b = np.arange(256, dtype=np.uint8)
+    f32 = (b.astype(np.float32) / (np.float32(255.0) / np.float32(3))).astype(np.int32) - 1
+    got_float = np.array([lib.emu_ternary(0, int(x)) for x in b])
+    got_thr = np.array([lib.emu_ternary(1, int(x)) for x in b])
+    assert np.array_equal(got_float, f32) and np.array_equal(got_thr, f32)
+    q = 1000
+    orc = oracle.ternary_dist_xq(b, 256, [q]).astype(np.int64)      # the _xq formula (the legacy convert_ternary differs: distributions.cuh:204)
+    assert np.array_equal(np.where(orc == q - 1, -1, orc), f32)
+    assert sorted(set(f32.tolist())) == [-1, 0, 1, 2] and f32[255] == 2 and f32[254] == 1 and f32[85] == 0 and f32[84] == -1
