@@ -475,7 +475,7 @@ __device__ __forceinline__ void dec_accumulate(const DecLimb &P, u64 a1, u64 a0,
     } else {
         g = 0;
     }
-    acc_t += (v * P.bt) & (u64)mask32;
+    acc_t += (u64)(((u32)v * (u32)P.bt) & mask32);     // only the low 32 bits survive the mask: one 32-bit multiply (bt < t)
     acc_g = add_mod_gamma(acc_g, g, D.gamma);
 }
 // both coefficients of pair j over `count` limbs, four limbs' loads (8 x 16 bytes) in flight at a time
