@@ -186,3 +186,23 @@ def test_emu_ntt_domain_product_then_inverse(oracle):
         q, l = qs[i % 3], i % 3
         exp = oracle.inverse_ntt_fast(oracle.barrett(a[i * n:(i + 1) * n], b[i * n:(i + 1) * n], q), q, psiinv[l])
         assert np.array_equal(got[i * n:(i + 1) * n], exp)
+
+
+def test_emu_final_reduction_arms(oracle):
+    """The lazy forward transform ends with one of three canonicalisations (ShoupLazyPolicy::fwd_final_all): q = 2^b - delta with a
+    small delta (every reference prime), q > 2^32 elsewhere, and q < 2^32.  Primes around 3 * 2^(b-2) exercise the middle arm, which
+    no parameter set of the reference reaches; one limb of each kind in the same batch."""
+    n = 1 << 11
+    q_mid, r_mid = params.find_ntt_primes(55, n, 1, below=3 << 53)
+    q_pm, r_pm = params.find_ntt_primes(55, n, 1)
+    q_small, r_small = params.find_ntt_primes(30, n, 1)
+    qs, roots = q_mid + q_pm + q_small, r_mid + r_pm + r_small
+    assert 69 * ((1 << qs[0].bit_length()) - qs[0]) > qs[0] and 69 * ((1 << 55) - qs[1]) < qs[1] and qs[2] < (1 << 32)
+    tabs = [oracle.fill_psi_tables(r, q, n) for q, r in zip(qs, roots)]
+    psi, psiinv = np.stack([t[0] for t in tabs]), np.stack([t[1] for t in tabs])
+    num = 6
+    a = np.concatenate([oracle.fill_uniform(n, qs[i % 3], 0xF1A7 + i) for i in range(num)])
+    a[:3] = [0, 1, qs[0] - 1]
+    fwd = emu.ntt(a, n, qs, psi, psiinv, num, 3, inverse=False, barrett=2, use_tma=1)
+    assert np.array_equal(fwd, _expect(oracle, a, n, qs, psi, psiinv, num, 3, False))
+    assert np.array_equal(emu.ntt(fwd, n, qs, psi, psiinv, num, 3, inverse=True, barrett=2, use_tma=1), a)

@@ -232,3 +232,35 @@ def test_fused_product_full_size_equals_unfused_chain(oracle):
     ctx.ntt_domain_mul_inverse_batch(z, fb, num, L)
     assert torch.equal(z, ref)
     ctx.close()
+
+
+@pytest.mark.parametrize("logn", [11, 15])
+def test_final_reduction_arms_on_gpu(oracle, logn):
+    """All three canonicalisation arms of the lazy forward transform in one batch (see tests/test_emu_ntt.py): a prime around
+    3 * 2^53 (general 32-bit quotient arm), one just under 2^55 (pseudo-Mersenne arm), one below 2^32 (64-bit quotient arm)."""
+    import nttb200
+    from tests.gpu_util import to_dev, to_host
+    n = 1 << logn
+    q_mid, r_mid = params.find_ntt_primes(55, n, 1, below=3 << 53)
+    q_pm, r_pm = params.find_ntt_primes(55, n, 1)
+    q_small, r_small = params.find_ntt_primes(30, n, 1)
+    qs, roots = q_mid + q_pm + q_small, r_mid + r_pm + r_small
+    psi, psiinv = _tables(oracle, n, qs, roots)
+    num = 9
+    a = np.concatenate([oracle.fill_uniform(n, qs[i % 3], 0xF1A7 + i) for i in range(num)])
+    ctx = nttb200.Context(n, qs, roots)
+    d = to_dev(a)
+    ctx.forward_ntt_batch(d, num, 3)
+    assert np.array_equal(to_host(d), _expect(oracle, a, n, qs, psi, psiinv, num, 3, False))
+    ctx.inverse_ntt_batch(d, num, 3)
+    assert np.array_equal(to_host(d), a)
+    b = np.concatenate([oracle.fill_uniform(n, qs[i % 3], 0xBEE5 + i) for i in range(num)])
+    da, db = to_dev(a), to_dev(b)
+    ctx.poly_mul_batch(da, db, num, 3)
+    got = to_host(da)
+    for i in (0, 1, 2):
+        q, l = qs[i % 3], i % 3
+        exp = oracle.inverse_ntt_fast(oracle.barrett(oracle.forward_ntt_fast(a[i * n:(i + 1) * n], q, psi[l]),
+                                                     oracle.forward_ntt_fast(b[i * n:(i + 1) * n], q, psi[l]), q), q, psiinv[l])
+        assert np.array_equal(got[i * n:(i + 1) * n], exp)
+    ctx.close()
