@@ -122,9 +122,16 @@ static int run_keygen(const Pipe &P, unsigned char *in, size_t in_stride, int *e
     const size_t rn = (size_t)r * n;
     const u64 nblk = (9 * rn + 4 * (size_t)n) / 64;                                   // bfv_keygen.cuh:99
     k_salsa20_keystream<<<grid_for(nblk * batch, 256), 256, 0, P.st>>>(in, nblk, (u64)batch, in_stride, default_key(), nonce0);
-    k_keygen_sample<<<pair_grid(n, batch, 1), pair_block(n, batch, 1), 0, P.st>>>(in, in_stride, sk, pk, es, n, r, batch, P.L.q);   // :120-122
-    KCHECK();
-    NTTB200_TRY(pipe_ntt(P, false, sk, batch * r, r, 0, 0));                               // :129
+    if (P.policy_fwd != kPolicyBarrett) {      // context path: the ternary secret is generated inside the first strided pass
+        k_keygen_sample<<<pair_grid(n, batch, 1), pair_block(n, batch, 1), 0, P.st>>>(in, in_stride, nullptr, pk, es, n, r, batch, P.L.q);   // :121-122
+        KCHECK();
+        NTTB200_TRY(pipe_ntt_gen_pass(P, sk, batch * r, r, r, rn, in, in_stride));         // :120 + :129, first kernel
+        NTTB200_TRY(pipe_ntt_pass(P, false, 1, sk, batch * r, r, r, rn));
+    } else {
+        k_keygen_sample<<<pair_grid(n, batch, 1), pair_block(n, batch, 1), 0, P.st>>>(in, in_stride, sk, pk, es, n, r, batch, P.L.q);   // :120-122
+        KCHECK();
+        NTTB200_TRY(pipe_ntt(P, false, sk, batch * r, r, 0, 0));                           // :129
+    }
     if (P.all_exact && P.policy_inv != kPolicyBarrett) {
         // pk0 = INTT(a (.) NTT(s)): the product rides in the first inverse kernel (both operands are canonical NTT-domain values)
         NTTB200_TRY(launch_polymul(P.policy_inv == kPolicyShoupLazy, P.logn, pipe_args(P, false, pk + rn, batch * r, r, r, 2 * rn), P.psiinv,

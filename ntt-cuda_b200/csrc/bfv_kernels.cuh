@@ -174,6 +174,7 @@ __device__ __forceinline__ ulonglong2 ld2(const u64 *p) { return *reinterpret_ca
 __device__ __forceinline__ void st2(u64 *p, u64 a, u64 b) { *reinterpret_cast<ulonglong2 *>(p) = make_ulonglong2(a, b); }
 
 // keygen sampling: sk = ternary (all limbs), pk1 = uniform, es[k][j] = gaussian draw (signed).  grid (x, batch)
+// sk == nullptr: the ternary secret is generated inside the first strided NTT pass instead (NttArgs::gen_src)
 NTT_KERNEL void k_keygen_sample(const unsigned char *in, size_t in_stride, u64 *sk, u64 *pk, int *es, unsigned n, unsigned r,
                                 unsigned batch, const u64 *q)
 {
@@ -187,7 +188,7 @@ NTT_KERNEL void k_keygen_sample(const unsigned char *in, size_t in_stride, u64 *
         es[k * n + j + 1] = gaussian_value(g[1]);
         for (unsigned l = 0; l < r; l++) {
             const u64 ql = q[l];
-            st2(sk + k * rn + (size_t)l * n + j, ternary_value(b0, ql), ternary_value(b1, ql));
+            if (sk) st2(sk + k * rn + (size_t)l * n + j, ternary_value(b0, ql), ternary_value(b1, ql));
             const ulonglong2 u = ld2(reinterpret_cast<const u64 *>(s + n) + (size_t)l * n + j);
             st2(pk + k * 2 * rn + rn + (size_t)l * n + j, uniform_value(u.x, ql), uniform_value(u.y, ql));
         }

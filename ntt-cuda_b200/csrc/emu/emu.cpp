@@ -269,8 +269,16 @@ EXPORT int emu_bfv(int op, unsigned n, unsigned r, const u64 *q, const u64 *mu, 
     if (op == 0) {          // keygen
         const size_t stride = 9 * rn + 4 * (size_t)n; const u64 nblk = stride / 64;
         ew([&] { k_salsa20_keystream(in, nblk, (u64)batch, stride, key, nonce0); });
-        ew3(batch, 1, [&] { k_keygen_sample(in, stride, sk, pk, es, n, r, batch, q); });
-        ring_ntt(R, false, sk, batch * r, r, 0, 0);
+        if (R.barrett == 1) {
+            ew3(batch, 1, [&] { k_keygen_sample(in, stride, sk, pk, es, n, r, batch, q); });
+            ring_ntt(R, false, sk, batch * r, r, 0, 0);
+        } else {           // context path: the ternary secret is generated inside the first strided pass
+            ew3(batch, 1, [&] { k_keygen_sample(in, stride, (u64 *)nullptr, pk, es, n, r, batch, q); });
+            g_gen_src = in; g_gen_stride = stride;
+            ring_ntt(R, false, sk, batch * r, r, r, rn, 0);
+            g_gen_src = nullptr;
+            ring_ntt(R, false, sk, batch * r, r, r, rn, 1);
+        }
         ew3(r, batch, [&] { k_keygen_mul(pk, sk, n, r, batch, L); });
         ring_ntt(R, true, pk, batch * r, r, r, 2 * rn);
         ew3(r, batch, [&] { k_keygen_add_negate(pk, es, n, r, batch, L); });
