@@ -307,7 +307,17 @@ def run_ours(args):
         ev[k][2].record()
     t_end.record()
     barrier()
+    # the timed region is only a few milliseconds long (nvidia-smi samples every 100 ms): keep the SAME launches running for another
+    # 0.4 s, untimed, so that the clock / throttle record really is one taken under this load
+    t_hold = time.perf_counter()
+    while time.perf_counter() - t_hold < 0.4:
+        for _ in range(50):
+            ctx.ntt_pass(a, POLYS, LIMBS, False, 0)
+            ctx.ntt_pass(a, POLYS, LIMBS, False, 1)
+        torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["window"] = "timed region + 0.4 s untimed continuation of the same launches"
     ms_total = t_start.elapsed_time(t_end)
     p1 = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
     p2 = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
