@@ -7,6 +7,15 @@ One "step" = one forward NTT over a batch of 1024 polynomials x 32768 coefficien
 (pinned host memory, H2D + D2H inside the timed region).  N > 1: one process per GPU, each rank transforms its own
 batch (weak scaling, no collective on the data path), time = max over ranks.
 
+Extra blocks on the same JSON line (BASELINE.json's other configs; none of them changes `value`):
+  value_sustained      the same launches kept running for >= 1 s, timed with events, own clock record
+  bfv                  enc+dec ops/s (batch 64 per GPU, 32768 x 16 limbs) + `e2e` through nttb200_bfv_encrypt_host / _decrypt_host
+  bfv_limb_sharded     config 4: 4096 ciphertexts, LIMB-sharded over the N GPUs through nttb200_bfv_encrypt_sharded /
+                       _decrypt_sharded (NCCL inside the library), strong scaling, bit-identity re-checked every run
+  ntt_limb_sharded     config 5: N = 2^16 / 2^17, 16 limbs, each rank owns its limbs' tables only, strong scaling
+  keygen_c3            config 3: 8192 x 3 limbs, 256 keys per call
+  latency_c1           config 1: one N = 4096 transform (58-bit prime), ours vs the rebuilt reference
+
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 --impl reference times the CPU restatement of the reference's transform (oracle/, all host threads) on a bounded
@@ -30,6 +39,15 @@ LIMBS = 16
 WORKLOAD = "batched 60-bit NTT, N=2^15, 1024 polynomials, 16 RNS limbs (demo.cu 32k_16q primes)"
 METRIC = "60-bit NTT/s at N=2^15 batched"
 UNIT = "NTT/s"
+SMSP = 148 * 4                      # SM sub-partitions of a B200
+FLOOR_CYCLES = 28.0                 # fma-heavy issue cycles of one warp-butterfly: 5 IMAD.WIDE x 4 + 4 IMAD x 2
+
+
+def config(world):
+    """One config dict for both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "polys_per_gpu": POLYS, "n": N, "limbs": LIMBS,
+            "l2": "batch is 256 MiB per GPU (> 126 MB L2): every step streams from HBM, no flush needed",
+            "parallelism": f"batch-sharded x{world}, no collective"}
 
 
 def peaks():
@@ -85,6 +103,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     per_step_budget = max(2.0, min(20.0, 60.0 / max(args.steps + args.warmup, 1)))
     vals = []
     last = None
@@ -100,7 +119,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "CPU arm: bounded sample per step, all host threads"},
+            "config": config(world),
+            "note": "CPU arm: each step is a bounded sample of the workload on all host threads (the reference has no CPU NTT; oracle port)",
             "cpu_baseline": last,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -152,7 +172,36 @@ class ClockSampler:
         return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def bfv_throughput(nttb200, params, torch, world, dist, batch=64, reps=5):
+class Timer:
+    """CUDA-event timing of a callable on torch's current stream, max over ranks."""
+
+    def __init__(self, torch, dist, world):
+        self.torch, self.dist, self.world = torch, dist, world
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def ms(self, fn, reps=5, warm=2):
+        torch = self.torch
+        for _ in range(warm):
+            fn()
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def bfv_throughput(nttb200, params, torch, T, world, batch=64, reps=5):
     """BFV encrypt + decrypt ops/s (whole job): each rank encrypts and decrypts its own batch (batch sharding, no
     collective).  Decryption overwrites c1, so every repetition decrypts a fresh device copy (copy time subtracted)."""
     n, qs, roots = params.RNS_SETS["32k_16q"]
@@ -167,72 +216,266 @@ def bfv_throughput(nttb200, params, torch, world, dist, batch=64, reps=5):
     keep = torch.zeros_like(c)
     out = torch.zeros(batch * n, dtype=torch.int64, device="cuda")
 
-    def timed(fn):
-        for _ in range(2):
-            fn()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    enc = timed(lambda: bfv.encrypt(c, pk, m, batch=batch))
+    enc = T.ms(lambda: bfv.encrypt(c, pk, m, batch=batch), reps)
     keep.copy_(c)
 
     def dec():
         c.copy_(keep)
         bfv.decrypt(out, c, sk, batch=batch)
 
-    copy_ms = timed(lambda: c.copy_(keep))
-    dec_ms = timed(dec) - copy_ms
+    copy_ms = T.ms(lambda: c.copy_(keep), reps)
+    dec_ms = T.ms(dec, reps) - copy_ms
     ok = bool(torch.equal(out, m))
-    # keys loaded into the context once (nttb200_bfv_load_keys): the fused NTT (.) key -> INTT kernels
+    # keys loaded into the context once (nttb200_bfv_load_keys): fused NTT (.) key -> INTT kernels, epilogue in the last inverse kernel
     bfv.load_keys(sk, pk)
-    enc_l = timed(lambda: bfv.encrypt(c, None, m, batch=batch))
+    enc_l = T.ms(lambda: bfv.encrypt(c, None, m, batch=batch), reps)
+    same = bool(torch.equal(c, keep))
     keep.copy_(c)
 
     def dec_loaded():
         c.copy_(keep)
         bfv.decrypt(out, c, None, batch=batch)
 
-    dec_l = timed(dec_loaded) - copy_ms
-    ok = ok and bool(torch.equal(out, m))
+    dec_l = T.ms(dec_loaded, reps) - copy_ms
+    ok = ok and same and bool(torch.equal(out, m))
+    bfv.set_fused_epilogue(False)
+    enc_l_sep = T.ms(lambda: bfv.encrypt(c, None, m, batch=batch), reps)
+    bfv.set_fused_epilogue(True)
+    # end to end through host buffers: m (pinned) -> H2D -> encrypt -> pack -> D2H ciphertexts; ciphertexts -> H2D -> unpack -> decrypt -> D2H m
+    pw = bfv.packed_words()
+    mh = torch.empty(batch * n, dtype=torch.int64).pin_memory()
+    mh.copy_(m.cpu())
+    ch = torch.empty(batch * pw, dtype=torch.int64).pin_memory()
+    oh = torch.empty(batch * n, dtype=torch.int64).pin_memory()
+    for _ in range(2):
+        bfv.encrypt_host(ch, mh, batch, packed=True)
+        bfv.decrypt_host(oh, ch, batch, packed=True)
+    T.barrier()
+    e2e_reps = 3
+    t0 = time.perf_counter()
+    for _ in range(e2e_reps):
+        bfv.encrypt_host(ch, mh, batch, packed=True)
+        bfv.decrypt_host(oh, ch, batch, packed=True)
+    e2e_s = (time.perf_counter() - t0) / e2e_reps
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        T.dist.all_reduce(te, op=T.dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    ok = ok and bool(torch.equal(oh, mh))
     bfv.close()
     if not ok:
         raise SystemExit("bench.py: BFV round trip failed")
     return {"workload": "BFV encrypt + decrypt, n=32768, 16-limb q (demo.cu), t=1024, batch %d per GPU" % batch,
             "loaded_keys": {"enc_plus_dec_per_s": world * batch / ((enc_l + dec_l) * 1e-3), "encrypt_per_s": world * batch / (enc_l * 1e-3),
-                            "decrypt_per_s": world * batch / (dec_l * 1e-3), "api": "nttb200_bfv_load_keys + encrypt / decrypt with NULL key"},
+                            "decrypt_per_s": world * batch / (dec_l * 1e-3),
+                            "encrypt_per_s_separate_epilogue": world * batch / (enc_l_sep * 1e-3),
+                            "api": "nttb200_bfv_load_keys + encrypt / decrypt with NULL key (5 / 4 launches)"},
             "enc_plus_dec_per_s": world * batch / ((enc + dec_ms) * 1e-3), "encrypt_per_s": world * batch / (enc * 1e-3),
-            "decrypt_per_s": world * batch / (dec_ms * 1e-3), "unit": "ops/s", "roundtrip_ok": ok}
+            "decrypt_per_s": world * batch / (dec_ms * 1e-3), "unit": "ops/s", "roundtrip_ok": ok,
+            "e2e": {"value": world * batch / e2e_s, "unit": "enc+dec ops/s", "h2d_bytes_per_step": batch * (n * 8 + pw * 8),
+                    "d2h_bytes_per_step": batch * (pw * 8 + n * 8),
+                    "api": "nttb200_bfv_encrypt_host + nttb200_bfv_decrypt_host, pinned host buffers, ciphertexts in the compact wire format "
+                           "(%.2f MB each instead of %.2f)" % (pw * 8 / 1e6, 2 * rn * 8 / 1e6)}}
 
 
-def ncu_numbers(kernel):
-    """(dram traffic per launch, fma-heavy pipe record) of `kernel` (forward, C2 workload) from the committed ncu --set full
-    summary profiles/r01_final_pipe_util.json (scripts/ncu_summary.py); fallbacks are the values of the earlier capture."""
-    traffic = {"ntt_strided_pass": 484.5e6, "ntt_contig_pass": 493.4e6}[kernel]
-    rec = None
+def bfv_limb_sharded(nttb200, params, torch, T, world, rank, total=4096):
+    """BASELINE config 4: `total` ciphertexts, limb-sharded over the N GPUs (strong scaling).  Same library calls at N = 1."""
+    out = {"ciphertexts": total, "scaling": "strong",
+           "api": "nttb200_bfv_encrypt_sharded / nttb200_bfv_decrypt_sharded (collectives inside libnttb200.so, NCCL bound at run time)",
+           "sets": {}}
+    comm = nttb200.Comm.from_torch()
+    for name in ("32k_16q", "16k_9q"):
+        n, qs, roots = params.RNS_SETS[name]
+        r = len(qs)
+        rn = r * n
+        bfv = nttb200.Bfv(n, qs, roots)
+        sk = torch.zeros(rn, dtype=torch.int64, device="cuda")
+        pk = torch.zeros(2 * rn, dtype=torch.int64, device="cuda")
+        bfv.keygen(sk, pk)                       # same key on every rank (nonce-addressed sampling)
+        bfv.load_keys(sk, pk)
+        g = torch.Generator(device="cuda").manual_seed(0xC4)
+        m = torch.randint(0, params.T, (total * n,), dtype=torch.int64, device="cuda", generator=g)
+        words = bfv.shard_words(comm, total)
+        shard = torch.zeros(max(words, 1), dtype=torch.int64, device="cuda")
+        res = torch.zeros(total * n, dtype=torch.int64, device="cuda")
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        for _ in range(2):
+            bfv.encrypt_sharded(comm, shard, m, total)
+            bfv.decrypt_sharded(comm, res, shard, total)
+        T.barrier()
+        reps, te, td = 3, 0.0, 0.0
+        for _ in range(reps):
+            ev[0].record()
+            bfv.encrypt_sharded(comm, shard, m, total)
+            ev[1].record()
+            bfv.decrypt_sharded(comm, res, shard, total)
+            ev[2].record()
+            torch.cuda.synchronize()
+            te += ev[0].elapsed_time(ev[1]) / reps
+            td += ev[1].elapsed_time(ev[2]) / reps
+        t = torch.tensor([te, td, te + td], dtype=torch.float64, device="cuda")
+        if world > 1:
+            T.dist.all_reduce(t, op=T.dist.ReduceOp.MAX)
+        ok = bool(torch.equal(res, m))
+        # bit-identity with the single-GPU call on a sample: the first 2 items of every block this rank holds tiles of
+        bfv.encrypt_sharded(comm, shard, m, total)
+        plan, _ = nttb200.shard_plan(r - 1, n, total, world, rank)
+        for (it, items, f, cnt, off) in plan:
+            if not cnt:
+                continue
+            one = torch.zeros(2 * 2 * rn, dtype=torch.int64, device="cuda")
+            bfv.encrypt(one, None, m[it * n:(it + 2) * n], batch=2, nonce0=it)
+            tile = shard[off:off + 2 * 2 * cnt * n].view(2, 2, cnt, n)
+            ok = ok and bool(torch.equal(tile, one.view(2, 2, r, n)[:, :, f:f + cnt, :]))
+        flag = torch.tensor([int(ok)], device="cuda")
+        if world > 1:
+            T.dist.all_reduce(flag, op=T.dist.ReduceOp.MIN)
+        if not bool(flag.item()):
+            raise SystemExit(f"bench.py: limb-sharded BFV ({name}) is not bit-identical to the single-GPU result")
+        out["sets"][name] = {"n": n, "limbs": r, "enc_plus_dec_per_s": total / (float(t[2]) * 1e-3), "encrypt_ms": float(t[0]),
+                             "decrypt_ms": float(t[1]), "bit_identical_to_one_gpu": True,
+                             "tiles_per_rank": sum(b[3] for b in plan), "shard_bytes_per_rank": words * 8}
+        bfv.close()
+        del shard, res, m
+        torch.cuda.empty_cache()
+    comm.close()
+    out["value"] = out["sets"]["32k_16q"]["enc_plus_dec_per_s"]
+    out["unit"] = "enc+dec ops/s (N=32768, 16 limbs, 4096 ciphertexts, whole job)"
+    return out
+
+
+def ntt_limb_sharded(nttb200, params, torch, T, world, rank):
+    """BASELINE config 5: N = 2^16 / 2^17 with 16 new 55-bit primes; rank g owns limbs [16 g / N, 16 (g+1) / N) and creates a context
+    with ONLY those primes (its tables never leave the GPU, no collective); 64 polynomials per limb; strong scaling."""
+    out = {"scaling": "strong", "limbs": 16, "polys_per_limb": 64, "sizes": {}}
+    for logn in (16, 17):
+        n = 1 << logn
+        qs, roots = params.find_ntt_primes(55, n, 16)
+        per = -(-16 // world)
+        mine = list(range(min(rank * per, 16), min((rank + 1) * per, 16)))
+        polys = 64 * len(mine)
+        ms = 0.0
+        if mine:
+            ctx = nttb200.Context(n, [qs[l] for l in mine], [roots[l] for l in mine])
+            g = torch.Generator(device="cuda").manual_seed(0xC5 + rank)
+            qv = torch.tensor([qs[l] for l in mine], dtype=torch.int64, device="cuda").repeat(64).view(polys, 1)
+            a = torch.randint(0, 2**62, (polys, n), dtype=torch.int64, device="cuda", generator=g) % qv
+            a0 = a.clone()
+            ctx.forward_ntt_batch(a, polys, len(mine))
+            ctx.inverse_ntt_batch(a, polys, len(mine))
+            if not torch.equal(a, a0):
+                raise SystemExit("bench.py: limb-sharded NTT round trip failed")
+        T.barrier()
+        if mine:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for _ in range(3):
+                ctx.forward_ntt_batch(a, polys, len(mine))
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(10):
+                ctx.forward_ntt_batch(a, polys, len(mine))
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            ctx.close()
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            T.dist.all_reduce(t, op=T.dist.ReduceOp.MAX)
+        out["sizes"][f"2^{logn}"] = {"ntt_per_s": 16 * 64 / (float(t.item()) * 1e-3), "ms_per_step": float(t.item()),
+                                     "limbs_per_rank": per, "table_bytes_per_rank": per * 4 * n * 8}
+    return out
+
+
+def keygen_c3(nttb200, params, torch, T, world):
+    n, qs, roots = params.RNS_SETS["8k_3q"]
+    rn = len(qs) * n
+    B = 256
+    bfv = nttb200.Bfv(n, qs, roots)
+    bfv.reserve(B)
+    sk = torch.zeros(B * rn, dtype=torch.int64, device="cuda")
+    pk = torch.zeros(B * 2 * rn, dtype=torch.int64, device="cuda")
+    ms = T.ms(lambda: bfv.keygen(sk, pk, batch=B), reps=10)
+    bfv.close()
+    return {"workload": "BFV keygen, N=8192, 3-limb q (demo.cu 8k_3q), 256 keys per call, per GPU", "keys_per_s": world * B / (ms * 1e-3),
+            "ms_per_call": ms, "us_per_key": 1e3 * ms / B}
+
+
+def latency_c1(nttb200, params, torch):
+    """BASELINE config 1: ONE polynomial, N = 4096, 58-bit prime: microseconds per call (back-to-back launches, CUDA events)."""
+    n = 4096
+    q, psi = params.GET_PARAMS_4096_58BIT[:2]
+    ctx = nttb200.Context(n, [q], [psi])
+    a = torch.randint(0, q, (n,), dtype=torch.int64, device="cuda")
+    b = a.clone()
+    qbit = q.bit_length()
+    mu = (1 << (2 * qbit)) // q
+    psi_t, psiinv_t = ctx.psi_table, ctx.psiinv_table
+
+    def timed(fn, iters=200):
+        for _ in range(10):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return 1e3 * e0.elapsed_time(e1) / iters
+
+    st = torch.cuda.current_stream().cuda_stream
+    res = {"workload": "one N=4096 transform, q = 288230376135196673 (parameter.h:43-47)",
+           "stateless_fwd_us": timed(lambda: nttb200.forwardNTT(a, n, st, q, mu, qbit, psi_t)),
+           "stateless_inv_us": timed(lambda: nttb200.inverseNTT(a, n, st, q, mu, qbit, psiinv_t)),
+           "context_fwd_us": timed(lambda: ctx.forward_ntt_batch(a, 1, 1)),
+           "context_inv_us": timed(lambda: ctx.inverse_ntt_batch(a, 1, 1))}
+
+    def polymul():
+        nttb200.forwardNTT(a, n, st, q, mu, qbit, psi_t)
+        nttb200.forwardNTT(b, n, st, q, mu, qbit, psi_t)
+        nttb200.barrett(a, b, n, q, mu, qbit)
+        nttb200.inverseNTT(a, n, st, q, mu, qbit, psiinv_t)
+
+    res["stateless_polymul_us"] = timed(polymul)
+    # the same flow replayed from a CUDA graph (launch overhead off the critical path)
+    gstream = torch.cuda.Stream()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(gstream):
+        gs = gstream.cuda_stream
+
+        def polymul_g():
+            nttb200.forwardNTT(a, n, gs, q, mu, qbit, psi_t)
+            nttb200.forwardNTT(b, n, gs, q, mu, qbit, psi_t)
+            nttb200.barrett(a, b, n, q, mu, qbit, stream=gs)
+            nttb200.inverseNTT(a, n, gs, q, mu, qbit, psiinv_t)
+        polymul_g()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(graph, stream=gstream):
+            polymul_g()
+    res["graph_polymul_us"] = timed(graph.replay)
+    ctx.close()
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_dump")
+    if os.path.exists(exe):
+        try:
+            o = subprocess.run([exe, "c1", "200"], capture_output=True, text=True, timeout=120).stdout
+            res["reference_gpu_rebuilt"] = json.loads(o.strip().splitlines()[-1])
+        except Exception as e:  # pragma: no cover
+            res["reference_gpu_rebuilt"] = {"error": str(e)[:200]}
+    res["paper_v100_us"] = {"fwd": 22.5, "inv": 15.5}
+    return res
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` (forward, C2 workload) from THIS round's committed
+    ncu --set full capture (profiles/r02_pipe_util.json, scripts/ncu_summary.py); None when no capture of this build exists."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r01_final_pipe_util.json")))
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02_pipe_util.json")))
         for name, m in d.items():
-            if kernel in name and "ShoupLazyPolicy" in name and ", 0>" in name.replace("(bool)", ""):
-                traffic = m.get("traffic_bytes", traffic)
-                f = m.get("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed")
-                if f is not None:
-                    rec = {"bound": "fma-heavy (IMAD/IMAD.WIDE) pipe", "frac": f / 100.0,
-                           "metric": "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed", "kernel": kernel,
-                           "source": "profiles/r01_final_ncu_full_summary.md (ncu --set full of this command; not a live number)"}
+            if kernel in name and "ShoupLazyPolicy" in name and ", 0" in name.replace("(bool)", ""):
+                return m.get("traffic_bytes")
     except (OSError, ValueError):
         pass
-    return traffic, rec
+    return None
 
 
 def reference_gpu_rebuilt():
@@ -244,15 +487,18 @@ def reference_gpu_rebuilt():
     try:
         out = subprocess.run([exe, "bench", "32k_16q", str(POLYS), "20"], capture_output=True, text=True, timeout=300).stdout
         d = json.loads(out.strip().splitlines()[-1])
-        return {"fwd_ntt_per_s": d["fwd_ntt_per_s"], "inv_ntt_per_s": d["inv_ntt_per_s"], "keygen_us": d["keygen_us"],
-                "encrypt_us": d["encrypt_us"], "decrypt_us": d["decrypt_us"],
-                "note": "forwardNTT_batch / inverseNTT_batch num=1024 and single-item keygen/encryption/decryption_rns loops, CUDA events"}
+        res = {"fwd_ntt_per_s": d["fwd_ntt_per_s"], "inv_ntt_per_s": d["inv_ntt_per_s"], "keygen_us": d["keygen_us"],
+               "encrypt_us": d["encrypt_us"], "decrypt_us": d["decrypt_us"],
+               "note": "forwardNTT_batch / inverseNTT_batch num=1024 and single-item keygen/encryption/decryption_rns loops, CUDA events"}
+        out = subprocess.run([exe, "bench", "8k_3q", "256", "20"], capture_output=True, text=True, timeout=300).stdout
+        d = json.loads(out.strip().splitlines()[-1])
+        res["c3_8k_3q"] = {"keygen_us": d["keygen_us"], "encrypt_us": d["encrypt_us"], "decrypt_us": d["decrypt_us"]}
+        return res
     except Exception as e:  # pragma: no cover
         return {"error": str(e)[:200]}
 
 
 def run_ours(args):
-    import numpy as np
     import torch
     import torch.distributed as dist
     import nttb200
@@ -266,6 +512,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    T = Timer(torch, dist, world)
 
     n, qs, roots = params.RNS_SETS["32k_16q"]
     ctx = nttb200.Context(n, qs, roots)
@@ -274,12 +521,7 @@ def run_ours(args):
     qv = torch.tensor(qs, dtype=torch.int64, device="cuda").repeat(POLYS // LIMBS).view(POLYS, 1)
     a = torch.randint(0, 2**62, (POLYS, n), dtype=torch.int64, device="cuda", generator=g) % qv
     a0 = a.clone()
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    barrier = T.barrier
 
     # ---- correctness gate before timing: INTT(NTT(a)) == a on the device (oracle parity is tests/'s job)
     ctx.forward_ntt_batch(a, POLYS, LIMBS)
@@ -307,37 +549,35 @@ def run_ours(args):
         ev[k][2].record()
     t_end.record()
     barrier()
-    # the timed region is only a few milliseconds long (nvidia-smi samples every 100 ms): keep the SAME launches running for another
-    # 0.4 s, untimed, so that the clock / throttle record really is one taken under this load
+    ms_total = t_start.elapsed_time(t_end)
+    # ---- sustained: the SAME launches (whole transform per step) for at least 1 s, timed; this is also the window the clock /
+    # throttle record is taken over (nvidia-smi samples every 100 ms; the K-step region above is only milliseconds long)
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sus_steps = 0
+    s0.record()
     t_hold = time.perf_counter()
-    while time.perf_counter() - t_hold < 0.4:
-        for _ in range(50):
-            ctx.ntt_pass(a, POLYS, LIMBS, False, 0)
-            ctx.ntt_pass(a, POLYS, LIMBS, False, 1)
+    while time.perf_counter() - t_hold < 1.2:
+        for _ in range(100):
+            ctx.forward_ntt_batch(a, POLYS, LIMBS)
+        sus_steps += 100
         torch.cuda.synchronize()
+    s1.record()
+    torch.cuda.synchronize()
+    sus_ms = s0.elapsed_time(s1)
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:
-        clocks["window"] = "timed region + 0.4 s untimed continuation of the same launches"
-    ms_total = t_start.elapsed_time(t_end)
+        clocks["window"] = "timed region + the >= 1.2 s sustained continuation of the same launches"
     p1 = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
     p2 = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
-    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms_total, sus_ms / sus_steps], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+    ms_total, sus_step_ms = float(t[0]), float(t[1])
     value = world * POLYS * args.steps / (ms_total * 1e-3)
+    value_sustained = world * POLYS / (sus_step_ms * 1e-3)
 
     # ---- inverse transform, same protocol (reported as an extra)
-    for _ in range(2):
-        ctx.inverse_ntt_batch(a, POLYS, LIMBS)
-    barrier()
-    i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    i0.record()
-    for _ in range(args.steps):
-        ctx.inverse_ntt_batch(a, POLYS, LIMBS)
-    i1.record()
-    barrier()
-    inv_ms = i0.elapsed_time(i1) / args.steps
+    inv_ms = T.ms(lambda: ctx.inverse_ntt_batch(a, POLYS, LIMBS), reps=args.steps)
 
     # ---- end to end through the host-buffer C-ABI entry point (pinned host memory)
     hin = torch.empty((POLYS, n), dtype=torch.int64, pin_memory=True)
@@ -362,21 +602,38 @@ def run_ours(args):
     ctx.forward_ntt_batch(chk, 2, LIMBS)
     if not torch.equal(chk.cpu(), hout[:2]):
         raise SystemExit("bench.py: host-buffer path disagrees with the device path")
+    del hin, hout, a, a0
+    ctx.close()
+    torch.cuda.empty_cache()
 
-    # ---- secondary metric of BASELINE.json ("BFV enc+dec ops/s"): batched context API, demo.cu's (32768, 16 primes) set
-    bfv_line = None
+    # ---- BASELINE.json's other configs
+    extras = {}
     if not args.no_bfv:
-        bfv_line = bfv_throughput(nttb200, params, torch, world, dist)
+        extras["bfv"] = bfv_throughput(nttb200, params, torch, T, world)
+        extras["bfv_limb_sharded"] = bfv_limb_sharded(nttb200, params, torch, T, world, rank, total=args.sharded_total)
+        extras["ntt_limb_sharded"] = ntt_limb_sharded(nttb200, params, torch, T, world, rank)
+        extras["keygen_c3"] = keygen_c3(nttb200, params, torch, T, world)
+        if rank == 0 and world == 1:
+            extras["latency_c1"] = latency_c1(nttb200, params, torch)
 
     if rank == 0:
         peak, peak_src = peaks()
         alg_bytes = 16.0 * n * POLYS                     # per launch: every coefficient read once + written once
         dom, dom_ms = ("ntt_strided_pass", p1) if p1 >= p2 else ("ntt_contig_pass", p2)
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this workload
-        # (profiles/r01z_ncu_full_summary.md); below the algorithmic 536.9 MB because write-back still sits in L2 at kernel end
-        ncu_traffic, int_pipe = ncu_numbers(dom)
         ach = alg_bytes / (dom_ms * 1e-3) / 1e9
         butterflies = POLYS * (n // 2) * 15
+        # integer (fma-heavy) pipe: floor issue cycles per warp-butterfly / measured cycles per warp-butterfly, per kernel, from the
+        # live kernel times and the SM clock sampled under this load
+        stages = {"ntt_strided_pass": 8, "ntt_contig_pass": 7}
+        int_pipe = None
+        if clocks and clocks.get("sm_mhz"):
+            int_pipe = {"bound": "fma-heavy (IMAD / IMAD.WIDE) issue", "floor_cycles_per_warp_butterfly": FLOOR_CYCLES, "sm_mhz": clocks["sm_mhz"],
+                        "kernels": {}}
+            for kname, kms in (("ntt_strided_pass", p1), ("ntt_contig_pass", p2)):
+                wb = POLYS * (n // 2) * stages[kname] / 32.0
+                cyc = kms * 1e-3 * clocks["sm_mhz"] * 1e6 * SMSP / wb
+                int_pipe["kernels"][kname] = {"cycles_per_warp_butterfly": cyc, "frac": FLOOR_CYCLES / cyc}
+            int_pipe["frac"] = int_pipe["kernels"][dom]["frac"]
         cb = None
         if world == 1 and not args.no_cpu_baseline:
             cb, _, _ = cpu_ntt_rate(budget_s=12.0)
@@ -384,29 +641,26 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "polys_per_gpu": POLYS, "n": n, "limbs": LIMBS,
-                       "l2": "batch is 256 MiB per GPU (> 126 MB L2): every step streams from HBM, no flush needed",
-                       "parallelism": f"batch-sharded x{world}, no collective"},
+            "config": config(world),
             "clocks": clocks,
+            "value_sustained": {"value": value_sustained, "unit": UNIT, "steps": sus_steps, "ms_per_step": sus_step_ms,
+                                "note": "same launches for >= 1.2 s, CUDA events; the clock record covers this window"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": POLYS * n * 8, "d2h_bytes_per_step": POLYS * n * 8,
                     "steps": e2e_steps, "api": "nttb200_forward_ntt_batch_host (pinned host buffers, 3-stage stream pipeline)"},
             "gpu_launches": 2 * args.steps,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": ncu_traffic, "peak_source": peak_src,
+                         "traffic": ncu_traffic(dom), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": dom_ms},
-            # the pipe that actually binds these kernels: ncu's own utilisation counter of the fma-heavy
-            # (IMAD / IMAD.WIDE) pipe for the same kernel and workload, from the committed --set full capture (not measured live)
             "roofline_int_pipe": int_pipe,
             "kernels_ms": {"ntt_strided_pass": p1, "ntt_contig_pass": p2},
             "hbm_gbs_whole_step": 2 * alg_bytes / ((p1 + p2) * 1e-3) / 1e9,
             "butterflies_per_s": butterflies * args.steps / (ms_total * 1e-3) * world,
             "inverse": {"value": world * POLYS / (inv_ms * 1e-3), "unit": "INTT/s", "ms_per_step": inv_ms},
             "cpu_baseline": cb,
-            "bfv": bfv_line,
             "reference_gpu_rebuilt": reference_gpu_rebuilt() if world == 1 and not args.no_cpu_baseline else None,
         }
+        line.update(extras)
         print(json.dumps(line))
-    ctx.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -419,6 +673,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bfv", action="store_true")
+    ap.add_argument("--sharded-total", type=int, default=4096, help="ciphertexts of the limb-sharded BFV block (config 4: 4096)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

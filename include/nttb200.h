@@ -34,6 +34,7 @@ typedef struct nttb200_ctx nttb200_ctx;
 
 #define NTTB200_EINVAL 10001  /* unsupported n / limbs / null pointer */
 #define NTTB200_ENOTMA 10002  /* cuTensorMapEncodeTiled unavailable or failed */
+#define NTTB200_ENCCL 10003   /* NCCL not loadable, or a collective failed */
 #define NTTB200_MAX_LIMBS 64  /* the reference caps at 16 (__constant__ tables, ntt_60bit.cuh:8-13) */
 
 NTTB200_API int nttb200_version(void);
@@ -172,6 +173,27 @@ NTTB200_API int nttb200_bfv_create(nttb200_bfv **bfv, unsigned n, unsigned limbs
                                    nttb200_u64 t, nttb200_u64 gamma);
 NTTB200_API void nttb200_bfv_destroy(nttb200_bfv *bfv);
 NTTB200_API nttb200_ctx *nttb200_bfv_ctx(nttb200_bfv *bfv);
+/* Creation validates what the scheme, as the reference implements it, silently assumes: t a power of two <= 2^32 (32-bit masks,
+ * poly_arithmetic.cuh:139,222), every q_i = 1 (mod t) (floor(q_i/t) stands for floor(q/t) mod q_i, bfv_encryption.cuh:193-212; the Fermat
+ * "inverse" mod t of demo.cu:109), gamma an odd prime < 2^62 different from every q_i (demo.cu:110) with gamma = 1 (mod t) (dec_round,
+ * poly_arithmetic.cuh:253-263, omits the multiplication by gamma^-1 mod t: the reference's gamma is 1 mod 2^11 only, so with it
+ * t <= 2048).  Anything else: NTTB200_EINVAL.
+ *
+ * Limits of the batched calls: batch <= 65535 items per call (nttb200_bfv_add / _pack / _unpack / _mul_plain: 32767), a grid dimension.
+ *
+ * Threading / streams: a context owns grow-only scratch (keystream, gaussian draws, transformed plaintexts) that every keygen /
+ * encrypt / mul_plain call uses on the CALLER's stream: a context serves one stream (and one host thread) at a time -- use one
+ * context per stream, or order calls on different streams with events.
+ *
+ * Randomness: Salsa20/20 keystream under the context's sampling key, item k of a call draws nonce nonce0 + k.  The DEFAULT key is the
+ * reference's (32 x 0x01, distributions.cuh:249) and keygen / encryption read the same stream layout, exactly as in the reference, so
+ * that nonce0 = 0 reproduces its outputs bit for bit: that default is for parity tests only -- anyone can regenerate such keys.  A
+ * deployment sets its own 32-byte key with nttb200_bfv_set_sampling_key and keeps the nonce ranges of key generation and of
+ * encryption disjoint (e.g. bit 63 set for encryption). */
+NTTB200_API int nttb200_bfv_set_sampling_key(nttb200_bfv *bfv, const unsigned char key[32]);
+/* A/B knob (default 1): encryption with a loaded key on a lazy-policy ring fuses `+ e`, the modulus switch and Delta*m into the store
+ * of the last inverse NTT kernel (5 launches, c written once); 0 keeps the separate epilogue kernels (7 launches).  Same bits. */
+NTTB200_API int nttb200_bfv_set_fused_epilogue(nttb200_bfv *bfv, int enable);
 /* pre-sizes the internal keystream scratch so that later calls never allocate */
 NTTB200_API int nttb200_bfv_reserve(nttb200_bfv *bfv, unsigned batch);
 /* Loads a key pair into the context (device pointers; either may be NULL): private copies + Shoup companions.
@@ -195,6 +217,21 @@ NTTB200_API int nttb200_bfv_decrypt(nttb200_bfv *bfv, nttb200_u64 *m_out, nttb20
 NTTB200_API size_t nttb200_bfv_packed_words(const nttb200_bfv *bfv);
 NTTB200_API int nttb200_bfv_pack(nttb200_bfv *bfv, nttb200_u64 *packed, const nttb200_u64 *c, unsigned batch, void *stream);
 NTTB200_API int nttb200_bfv_unpack(nttb200_bfv *bfv, nttb200_u64 *c, const nttb200_u64 *packed, unsigned batch, void *stream);
+
+/* Keys in the same bit-packed format, ALL r limbs (NTT-domain residues below q_l): polys = r for sk[batch][r][n], 2r for
+ * pk[batch][2][r][n]; nttb200_bfv_key_packed_words(bfv, polys) words per key. */
+NTTB200_API size_t nttb200_bfv_key_packed_words(const nttb200_bfv *bfv, unsigned polys);
+NTTB200_API int nttb200_bfv_pack_key(nttb200_bfv *bfv, nttb200_u64 *packed, const nttb200_u64 *key, unsigned polys, unsigned batch, void *stream);
+NTTB200_API int nttb200_bfv_unpack_key(nttb200_bfv *bfv, nttb200_u64 *key, const nttb200_u64 *packed, unsigned polys, unsigned batch, void *stream);
+/* device ciphertexts <-> packed HOST buffer (the disk / wire side of the format); synchronous */
+NTTB200_API int nttb200_bfv_pack_host(nttb200_bfv *bfv, nttb200_u64 *packed_host, const nttb200_u64 *c, unsigned batch, void *stream);
+NTTB200_API int nttb200_bfv_unpack_host(nttb200_bfv *bfv, nttb200_u64 *c, const nttb200_u64 *packed_host, unsigned batch, void *stream);
+/* BFV through HOST buffers (what demo.cu:275-299 times end to end): m_host[batch][n] -> ciphertexts in c_host, and back.  packed != 0:
+ * ciphertexts cross PCIe in the wire format above (batch * nttb200_bfv_packed_words() words), else as c[batch][2][r][n].  Loaded keys
+ * (nttb200_bfv_load_keys).  H2D, kernels and D2H of successive chunks overlap on three internal streams; synchronous. */
+NTTB200_API int nttb200_bfv_encrypt_host(nttb200_bfv *bfv, nttb200_u64 *c_host, int packed, const nttb200_u64 *m_host, unsigned batch,
+                                         nttb200_u64 nonce0);
+NTTB200_API int nttb200_bfv_decrypt_host(nttb200_bfv *bfv, nttb200_u64 *m_host, const nttb200_u64 *c_host, int packed, unsigned batch);
 
 /* Homomorphic operations on ciphertexts in the reference layout (the reference stops at decryption):
  * c_a <- c_a + c_b  (Dec = m_a + m_b mod t), and  c <- c * p  for a plaintext polynomial p[n] or p[batch][n]
@@ -222,6 +259,60 @@ NTTB200_API int nttb200_bfv_decrypt_partial(nttb200_bfv *bfv, nttb200_u64 *parti
                                             int sk_per_item, unsigned first_limb, unsigned limb_count, unsigned shard_half_limbs,
                                             unsigned batch, void *stream);
 NTTB200_API int nttb200_bfv_decrypt_finish(nttb200_bfv *bfv, nttb200_u64 *m_out, const nttb200_u64 *partial_sum, unsigned batch, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Limb-sharded BFV across the GPUs of one box, one process per GPU (BASELINE configs 4-5).
+ * The collectives live in the library: NCCL is bound at run time (the libnccl already loaded in the process, e.g.
+ * PyTorch's, else libnccl.so.2), so libnttb200.so has no NCCL link dependency.
+ *
+ * Partition: the batch (a multiple of the world size) is cut into `world` item blocks; block j's plaintext and
+ * dropped limb belong to rank j.  Unit (limb l < r-1, block j) has flat index l * world + j; rank g owns
+ * [g * (r-1), (g+1) * (r-1)): r-1 tiles on every rank (15 limbs on 8 GPUs balance), and for one block the limbs of a
+ * rank are contiguous.  A rank's shard buffer is, block after block, c[items][2][limb_count][n].
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct nttb200_comm nttb200_comm;
+typedef struct nttb200_shard_block {
+    unsigned first_item, items;        /* the block's items */
+    unsigned first_limb, limb_count;   /* limbs of this block held by the calling rank (limb_count may be 0) */
+    size_t offset;                     /* word offset of the block's tile inside the rank's shard buffer */
+} nttb200_shard_block;
+/* host-only: fills blocks[world] for `rank`; rp = limbs - 1; *shard_words = size of the rank's shard buffer */
+NTTB200_API int nttb200_shard_plan(unsigned rp, unsigned n, unsigned batch, unsigned world, unsigned rank, nttb200_shard_block *blocks,
+                                   size_t *shard_words);
+/* communicator: created from a 128-byte NCCL unique id (rank 0 calls nttb200_comm_unique_id and ships it to the others by its own
+ * means), or adopted from an existing ncclComm_t (not destroyed by nttb200_comm_destroy).  world = 1 needs no NCCL at all. */
+NTTB200_API int nttb200_comm_unique_id(unsigned char id[128]);
+NTTB200_API int nttb200_comm_create(nttb200_comm **comm, const unsigned char id[128], int world, int rank);
+NTTB200_API int nttb200_comm_adopt(nttb200_comm **comm, void *nccl_comm, int world, int rank);
+NTTB200_API void nttb200_comm_destroy(nttb200_comm *comm);
+NTTB200_API int nttb200_comm_world(const nttb200_comm *comm);
+NTTB200_API int nttb200_comm_rank(const nttb200_comm *comm);
+/* encryption_rns bfv_encryption.cuh:223, limb-sharded: every rank passes the same m[batch][n] and nonce0 and receives its tiles of
+ * the ciphertexts in c_shard (bit-identical to the same limbs of nttb200_bfv_encrypt's output).  Uses the loaded public key.
+ * Collective: one all-gather of the finished dropped limbs (and of the signed-byte gaussian draws), overlapped with the transforms. */
+NTTB200_API int nttb200_bfv_encrypt_sharded(nttb200_bfv *bfv, nttb200_comm *comm, nttb200_u64 *c_shard, const nttb200_u64 *m, unsigned batch,
+                                            nttb200_u64 nonce0, void *stream);
+/* decryption_rns bfv_decryption.cuh:76, limb-sharded: c_shard is consumed; m_out[batch][n] is complete on every rank.  Uses the
+ * loaded secret key.  Collectives: per item block, the partial base-conversion sums (poly_arithmetic.cuh:217-251) packed to 10 bytes
+ * per coefficient go to the block's owner (ncclReduce; mode 1: chunked ncclReduceScatter) while the next block's transforms run;
+ * the owner rounds (dec_round :253-263) and ONE all-gather of 16-bit plaintext words ends the call. */
+NTTB200_API int nttb200_bfv_decrypt_sharded(nttb200_bfv *bfv, nttb200_comm *comm, nttb200_u64 *m_out, nttb200_u64 *c_shard, unsigned batch,
+                                            void *stream);
+/* Building blocks for callers that run their own collectives: one (limb window, item block) tile of the plan through the fused
+ * NTT (.) sk -> INTT kernel up to the partial sums (packed = 1: partial[batch][n + n/4] = gamma sums then four 16-bit t sums per word,
+ * needs (r-1)(t-1) < 2^16; packed = 0: partial[batch][2][n]); SUM-reduce (64-bit) over the windows, then _finish_tile rounds
+ * (out16 = 1: unsigned short m_out[batch][n], t <= 2^16). */
+NTTB200_API int nttb200_bfv_decrypt_partial_tile(nttb200_bfv *bfv, nttb200_u64 *partial, int packed, nttb200_u64 *c_tile, unsigned first_limb,
+                                                 unsigned limb_count, unsigned batch, void *stream);
+NTTB200_API int nttb200_bfv_decrypt_finish_tile(nttb200_bfv *bfv, void *m_out, int out16, const nttb200_u64 *partial_sum, int packed,
+                                                unsigned batch, void *stream);
+/* mode 0 (default): per-block ncclReduce; mode 1: `chunks` ncclReduceScatter calls.  Env NTTB200_SHARD_MODE / NTTB200_SHARD_CHUNKS. */
+NTTB200_API int nttb200_bfv_shard_config(nttb200_bfv *bfv, int mode, unsigned chunks);
+/* device-local conversion between the reference layout c[batch][2][r][n] and the calling rank's shard */
+NTTB200_API int nttb200_bfv_shard_from_full(nttb200_bfv *bfv, unsigned world, unsigned rank, nttb200_u64 *c_shard, const nttb200_u64 *c_full,
+                                            unsigned batch, void *stream);
+NTTB200_API int nttb200_bfv_shard_to_full(nttb200_bfv *bfv, unsigned world, unsigned rank, nttb200_u64 *c_full, const nttb200_u64 *c_shard,
+                                          unsigned batch, void *stream);
 
 /* The reference's single-item calls, stateless (tables and constant arrays are the caller's device buffers;
  * unused reference parameters are dropped).  Scratch: `in` as in the reference; the first n (keygen) / 2n (encrypt)

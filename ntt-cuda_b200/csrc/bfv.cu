@@ -10,9 +10,12 @@
 // 13 / 16 / 18 per item, creates r streams and mallocs inside decryption_rns, and races dec_round against mod_t.
 #include "internal.h"
 #include "bfv_kernels.cuh"
+#include "epi.cuh"
 #include "table_kernels.cuh"
+#include "bfv_internal.h"
 
 #include <cmath>
+#include <cstring>
 
 using namespace nttb200;
 typedef unsigned __int128 u128;
@@ -42,46 +45,32 @@ static dim3 pair_grid(unsigned n, unsigned y, unsigned z)
     return dim3(x ? x : 1, y, z);
 }
 
-struct nttb200_bfv {
-    nttb200_ctx *ctx = nullptr;
-    unsigned n = 0, r = 0;            // all limbs; rp = r - 1 after the modulus switch
-    u64 t = 0, gamma = 0, mu_gamma = 0, gamma_div_2 = 0, neg_inv_t = 0, neg_inv_gamma = 0;
-    int gamma_bits = 0;
-    // device constant arrays
-    u64 *inv_q_last_mod_q = nullptr, *qi_div_t = nullptr, *prod_t_gamma_mod_q = nullptr, *inv_punctured_q = nullptr, *bcm = nullptr;
-    // keys loaded into the context (nttb200_bfv_load_keys): private copies + Shoup companions, enabling the fused
-    // "NTT (.) key -> INTT" kernel; used when encrypt / decrypt are called with a NULL key pointer
-    u64 *sk_l = nullptr, *sk_ls = nullptr, *pk_l = nullptr, *pk_ls = nullptr;
-    // grow-only scratch: keystream and gaussian draws
-    unsigned char *ks = nullptr; size_t ks_bytes = 0;
-    int *es = nullptr; size_t es_count = 0;
-    u64 *pt = nullptr; size_t pt_count = 0;          // lifted + transformed plaintexts of nttb200_bfv_mul_plain
-    unsigned *word_off = nullptr; unsigned half_words = 0;   // compact wire format: first word of each limb inside a half, words per half
-    bool enc_lazy = false, dec_fast = false, all_exact = false;
-};
-
 static u64 h_modpow(u64 a, u64 e, u64 m)
 {
     u64 r = 1 % m; a %= m;
     while (e) { if (e & 1) r = (u64)((u128)r * a % m); a = (u64)((u128)a * a % m); e >>= 1; }
     return r;
 }
+// deterministic Miller-Rabin for 64-bit integers
+static bool h_is_prime(u64 m)
+{
+    if (m < 2) return false;
+    for (u64 p : {2ull, 3ull, 5ull, 7ull, 11ull, 13ull, 17ull, 19ull, 23ull, 29ull, 31ull, 37ull}) {
+        if (m % p == 0) return m == p;
+    }
+    u64 d = m - 1; int sft = 0;
+    while (!(d & 1)) { d >>= 1; sft++; }
+    for (u64 a : {2ull, 3ull, 5ull, 7ull, 11ull, 13ull, 17ull, 19ull, 23ull, 29ull, 31ull, 37ull}) {
+        u64 x = h_modpow(a, d, m);
+        if (x == 1 || x == m - 1) continue;
+        bool comp = true;
+        for (int i = 1; i < sft && comp; i++) { x = (u64)((u128)x * x % m); if (x == m - 1) comp = false; }
+        if (comp) return false;
+    }
+    return true;
+}
 // the reference's modinv128(a, m) = a^(m-2) mod m (helper.h:52-56), also applied to the non-prime t (demo.cu:109)
 static u64 h_modinv_fermat(u64 a, u64 m) { return h_modpow(a, m - 2, m); }
-
-struct Pipe {                 // everything one pipeline run needs, independent of the front end
-    unsigned n, logn, r;
-    LimbArrays L;
-    const u64 *qi_div_t;
-    // NTT flavour
-    int policy_fwd, policy_inv;
-    const u64 *psi, *psiinv, *psi_s, *psiinv_s;
-    const LimbConst *lc;
-    int use_tma;
-    cudaStream_t st;
-    bool enc_lazy = false, dec_fast = false;   // host-verified: every limb qualifies for the lazy / Shoup-only epilogues
-    bool all_exact = false;                    // host-verified: the reference's Barrett is exact for every limb (any exact product = its bits)
-};
 
 static NttArgsHost pipe_args(const Pipe &P, bool inverse, u64 *a, unsigned num, unsigned division, unsigned group_polys, size_t group_stride)
 {
@@ -112,8 +101,6 @@ static int pipe_ntt(const Pipe &P, bool inverse, u64 *a, unsigned num, unsigned 
     return launch_ntt(inverse, pol, P.logn, h, P.st);
 }
 
-#define KCHECK() do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return nttb200_trace_error((int)e__, __FILE__, __LINE__); } while (0)
-#define NTTB200_TRY(x) do { int r__ = (x); if (r__) return nttb200_trace_error(r__, __FILE__, __LINE__); } while (0)
 
 // keygen: in = keystream scratch ([batch] streams of in_stride bytes), es = n ints per item
 static int run_keygen(const Pipe &P, unsigned char *in, size_t in_stride, int *es, u64 *sk, u64 *pk, unsigned batch, u64 nonce0)
@@ -121,7 +108,7 @@ static int run_keygen(const Pipe &P, unsigned char *in, size_t in_stride, int *e
     const unsigned n = P.n, r = P.r;
     const size_t rn = (size_t)r * n;
     const u64 nblk = (9 * rn + 4 * (size_t)n) / 64;                                   // bfv_keygen.cuh:99
-    k_salsa20_keystream<<<grid_for(nblk * batch, 256), 256, 0, P.st>>>(in, nblk, (u64)batch, in_stride, default_key(), nonce0);
+    k_salsa20_keystream<<<grid_for(nblk * batch, 256), 256, 0, P.st>>>(in, nblk, (u64)batch, in_stride, P.key, nonce0);
     if (P.policy_fwd != kPolicyBarrett) {      // context path: the ternary secret is generated inside the first strided pass
         k_keygen_sample<<<pair_grid(n, batch, 1), pair_block(n, batch, 1), 0, P.st>>>(in, in_stride, nullptr, pk, es, n, r, batch, P.L.q);   // :121-122
         KCHECK();
@@ -168,9 +155,9 @@ static int run_encrypt(const Pipe &P, unsigned char *in, size_t in_stride, int *
     const unsigned n = P.n, r = P.r;
     const size_t rn = (size_t)r * n;
     const u64 nblk = (9 * (size_t)n) / 64;                                                // bfv_encryption.cuh:228
-    k_salsa20_keystream<<<grid_for(nblk * batch, 256), 256, 0, P.st>>>(in, nblk, (u64)batch, in_stride, default_key(), nonce0);
+    k_salsa20_keystream<<<grid_for(nblk * batch, 256), 256, 0, P.st>>>(in, nblk, (u64)batch, in_stride, P.key, nonce0);
     if (P.policy_fwd != kPolicyBarrett) {
-        k_encrypt_gauss<<<pair_grid(n, batch, 1), pair_block(n, batch, 1), 0, P.st>>>(in, in_stride, es, n, batch);               // :247 (e0, e1)
+        k_encrypt_gauss<<<pair_grid(n, batch, 1), pair_block(n, batch, 1), 0, P.st>>>(in, in_stride, es, n, batch, (size_t)n);               // :247 (e0, e1)
         KCHECK();
         NTTB200_TRY(pipe_ntt_gen_pass(P, c, batch * r, r, r, 2 * rn, in, in_stride));      // :247 (u) + :268 (once, not twice), first kernel
         NTTB200_TRY(pipe_ntt_pass(P, false, 1, c, batch * r, r, r, 2 * rn));
@@ -195,8 +182,8 @@ static int run_encrypt_fused(const Pipe &P, bool lazy, unsigned char *in, size_t
     const unsigned n = P.n, r = P.r;
     const size_t rn = (size_t)r * n;
     const u64 nblk = (9 * (size_t)n) / 64;
-    k_salsa20_keystream<<<grid_for(nblk * batch, 256), 256, 0, P.st>>>(in, nblk, (u64)batch, in_stride, default_key(), nonce0);
-    k_encrypt_gauss<<<pair_grid(n, batch, 1), pair_block(n, batch, 1), 0, P.st>>>(in, in_stride, es, n, batch);
+    k_salsa20_keystream<<<grid_for(nblk * batch, 256), 256, 0, P.st>>>(in, nblk, (u64)batch, in_stride, P.key, nonce0);
+    k_encrypt_gauss<<<pair_grid(n, batch, 1), pair_block(n, batch, 1), 0, P.st>>>(in, in_stride, es, n, batch, (size_t)n);
     KCHECK();
     NTTB200_TRY(pipe_ntt_gen_pass(P, c, batch * r, r, r, 2 * rn, in, in_stride));          // strided forward pass, u generated in the kernel
     NTTB200_TRY(launch_fused_mul(lazy, P.logn, pipe_args(P, false, c, batch * 2 * r, r, 2 * r, 2 * rn), P.psiinv, P.psiinv_s, pk, pk_s, 0, rn, r,
@@ -204,6 +191,23 @@ static int run_encrypt_fused(const Pipe &P, bool lazy, unsigned char *in, size_t
     NTTB200_TRY(pipe_ntt_pass(P, true, 1, c, batch * 2 * r, r, 0, 0));                     // strided inverse pass on both halves
     NTTB200_TRY(run_encrypt_epilogue(P, c, es, m, m_stride, t, batch));
     KCHECK();
+    return 0;
+}
+// encryption with a loaded key on a lazy-policy ring, 5 launches: sampling (u bytes + signed-byte gaussian draws), strided forward
+// pass generating u, fused contig forward (.) pk0 | pk1 -> contig inverse, strided inverse pass of the dropped limb (+ e, rounding
+// offset in its store), strided inverse pass of the other limbs with mod-switch + Delta*m in its store.  c is written once.
+static int run_encrypt_v2(nttb200_bfv *b, const Pipe &P, u64 *c, const u64 *m, unsigned batch, u64 nonce0)
+{
+    const unsigned n = P.n, r = P.r;
+    const size_t rn = (size_t)r * n;
+    NTTB200_TRY(ensure_enc_scratch(b, (size_t)batch * n, (size_t)batch * 2 * n));
+    const u64 per = 9 * (u64)n / 64;
+    k_encrypt_sample_fused<<<grid_for(per * batch, 128), 128, 0, P.st>>>(b->ub, b->es8, n, (u64)batch, P.key, nonce0, 1, 1);
+    KCHECK();
+    NTTB200_TRY(enc_front(b, P, c, r, 0, r, batch, b->ub));
+    u64 *cl = c + (size_t)(r - 1) * n;
+    NTTB200_TRY(enc_finish_last(b, P, cl, 2 * rn, rn, b->es8, batch));
+    NTTB200_TRY(enc_finish_limbs(b, P, c, r, 0, r - 1, batch, cl, 2 * rn, rn, b->es8, m, (size_t)n));
     return 0;
 }
 // decryption with a loaded secret key: 4 launches
@@ -239,7 +243,8 @@ static int run_decrypt(const Pipe &P, u64 *c, const u64 *sk, size_t sk_stride, u
 
 static unsigned ilog2u(unsigned n) { unsigned l = 0; while ((1u << l) < n) l++; return l; }
 
-static Pipe pipe_from_bfv(const nttb200_bfv *b, cudaStream_t st)
+namespace nttb200 {
+Pipe pipe_from_bfv(const nttb200_bfv *b, cudaStream_t st)
 {
     const nttb200_ctx *c = b->ctx;
     Pipe P;
@@ -250,8 +255,117 @@ static Pipe pipe_from_bfv(const nttb200_bfv *b, cudaStream_t st)
     P.policy_fwd = P.policy_inv = c->lazy_ok ? kPolicyShoupLazy : kPolicyShoup;
     P.psi = c->psi; P.psiinv = c->psiinv; P.psi_s = c->psi_s; P.psiinv_s = c->psiinv_s; P.lc = c->lc;
     P.use_tma = c->use_tma; P.st = st;
+    P.key = bfv_salsa_key(b);
     return P;
 }
+Pipe pipe_limb_window(const Pipe &P0, const nttb200_ctx *c, unsigned first)
+{
+    Pipe P = P0;
+    const size_t toff = (size_t)first * P.n;
+    P.psi = c->psi + toff; P.psiinv = c->psiinv + toff; P.psi_s = c->psi_s + toff; P.psiinv_s = c->psiinv_s + toff; P.lc = c->lc + first;
+    return P;
+}
+SalsaKey key_from_bytes(const unsigned char *b);
+SalsaKey bfv_salsa_key(const nttb200_bfv *b) { return key_from_bytes(b->salsa_key); }
+
+int ensure_enc_scratch(nttb200_bfv *b, size_t ub_bytes, size_t es8_bytes)
+{
+    if (b->ub_bytes < ub_bytes) {
+        if (b->ub) cudaFree(b->ub);
+        b->ub = nullptr; b->ub_bytes = 0;
+        NTTB200_CHECK(cudaMalloc(&b->ub, ub_bytes));
+        b->ub_bytes = ub_bytes;
+    }
+    if (b->es8_bytes < es8_bytes) {
+        if (b->es8) cudaFree(b->es8);
+        b->es8 = nullptr; b->es8_bytes = 0;
+        NTTB200_CHECK(cudaMalloc(&b->es8, es8_bytes));
+        b->es8_bytes = es8_bytes;
+    }
+    return 0;
+}
+
+// ---- fused-epilogue encryption building blocks (see bfv_internal.h) ---------------------------------------------------------------
+int enc_front(const nttb200_bfv *b, const Pipe &P0, u64 *c, unsigned slots, unsigned first, unsigned count, unsigned items, const unsigned char *ub)
+{
+    const unsigned n = P0.n;
+    const size_t rn = (size_t)b->r * n, item = (size_t)2 * slots * n;
+    Pipe P = pipe_limb_window(P0, b->ctx, first);
+    NTTB200_TRY(pipe_ntt_gen_pass(P, c, items * count, count, count, item, ub, (size_t)n));      // half 0, slots [0, count)
+    NTTB200_TRY(launch_fused_mul(true, P.logn, pipe_args(P, false, c, items * 2 * slots, count, 2 * slots, item), P.psiinv, P.psiinv_s,
+                                 b->pk_l + (size_t)first * n, b->pk_ls + (size_t)first * n, 0, rn, count, 0, 0, slots, items, 2, P.st));
+    return 0;
+}
+static EpiArgs epi_args(const nttb200_bfv *b, const signed char *es8)
+{
+    EpiArgs E{};
+    E.es = es8; E.K = b->enc_epi;
+    E.last = b->ctx->q[b->r - 1]; E.half_last = E.last >> 1;
+    E.t = b->t; E.tfix = (b->t + 1) >> 1; E.tsh = b->tsh;
+    return E;
+}
+int enc_finish_last(const nttb200_bfv *b, const Pipe &P0, u64 *cl, size_t cl_item_stride, size_t cl_half_stride, const signed char *es8, unsigned items)
+{
+    if (cl_item_stride != 2 * cl_half_stride) return NTTB200_EINVAL;
+    Pipe P = pipe_limb_window(P0, b->ctx, b->r - 1);
+    EpiArgs E = epi_args(b, es8);
+    return launch_strided_inv_epi(P.logn, pipe_args(P, true, cl, items * 2, 1, 1, cl_half_stride), kEpiEncLast, E, P.st);
+}
+int enc_finish_limbs(const nttb200_bfv *b, const Pipe &P0, u64 *c, unsigned slots, unsigned first, unsigned count, unsigned items, const u64 *cl,
+                     size_t cl_item_stride, size_t cl_half_stride, const signed char *es8, const u64 *m, size_t m_stride)
+{
+    Pipe P = pipe_limb_window(P0, b->ctx, first);
+    EpiArgs E = epi_args(b, es8);
+    E.cl = cl; E.cl_item_stride = cl_item_stride; E.cl_half_stride = cl_half_stride;
+    E.m = m; E.m_stride = m_stride; E.first_limb = first;
+    return launch_strided_inv_epi(P.logn, pipe_args(P, true, c, items * 2 * count, count, count, (size_t)slots * P.n), kEpiEncLimb, E, P.st);
+}
+int dec_partial(const nttb200_bfv *b, const Pipe &P0, u64 *partial, int packed, u64 *c_shard, unsigned slots, unsigned first, unsigned count,
+                unsigned items)
+{
+    const unsigned n = P0.n;
+    const size_t item = (size_t)2 * slots * n, c1_off = (size_t)slots * n;
+    Pipe P = pipe_limb_window(P0, b->ctx, first);
+    NTTB200_TRY(pipe_ntt_pass(P, false, 0, c_shard + c1_off, items * count, count, count, item));
+    NTTB200_TRY(launch_fused_mul(b->ctx->lazy_ok != 0, P.logn, pipe_args(P, false, c_shard, items * 2 * slots, count, 2 * slots, item), P.psiinv,
+                                 P.psiinv_s, b->sk_l + (size_t)first * n, b->sk_ls + (size_t)first * n, 0, 0, count, slots, slots, slots, items, 1, P.st));
+    NTTB200_TRY(pipe_ntt_pass(P, true, 1, c_shard + c1_off, items * count, count, count, item));
+    DecryptConsts D{b->t, b->gamma, b->mu_gamma, b->gamma_div_2, b->neg_inv_t, b->neg_inv_gamma, b->gamma_bits, b->r - 1, b->bcm};
+    if (packed) k_decrypt_partial<true><<<pair_grid(n, items, 1), pair_block(n, items, 1), 0, P.st>>>(c_shard, item, c1_off, partial, n, items, first, count, D, P0.L);
+    else k_decrypt_partial<false><<<pair_grid(n, items, 1), pair_block(n, items, 1), 0, P.st>>>(c_shard, item, c1_off, partial, n, items, first, count, D, P0.L);
+    KCHECK();
+    return 0;
+}
+// partial sums -> plaintext (16-bit words or u64 coefficients); expansion of gathered 16-bit plaintexts
+int dec_finish(const nttb200_bfv *b, void *out, int out16, const u64 *partial_sum, int packed, unsigned items, cudaStream_t st)
+{
+    DecryptConsts D{b->t, b->gamma, b->mu_gamma, b->gamma_div_2, b->neg_inv_t, b->neg_inv_gamma, b->gamma_bits, b->r - 1, b->bcm};
+    const unsigned n = b->n;
+    const dim3 g = pair_grid(n, items, 1);
+    const unsigned tb = pair_block(n, items, 1);
+    if (packed && out16) k_decrypt_finish<true, true><<<g, tb, 0, st>>>(partial_sum, out, (size_t)n, n, items, D);
+    else if (packed) k_decrypt_finish<true, false><<<g, tb, 0, st>>>(partial_sum, out, (size_t)n, n, items, D);
+    else if (out16) k_decrypt_finish<false, true><<<g, tb, 0, st>>>(partial_sum, out, (size_t)n, n, items, D);
+    else k_decrypt_finish<false, false><<<g, tb, 0, st>>>(partial_sum, out, (size_t)n, n, items, D);
+    KCHECK();
+    return 0;
+}
+int dec_expand16(const unsigned short *in, u64 *out, size_t total, cudaStream_t st)
+{
+    k_expand16<<<grid_for(total / 2, 256), 256, 0, st>>>(in, out, total);
+    KCHECK();
+    return 0;
+}
+// u bytes for `items` items (want_u) and / or signed-byte gaussian draws (want_e), nonce = nonce0 + item
+int enc_sample(const nttb200_bfv *b, unsigned char *ub, signed char *es8, unsigned items, u64 nonce0, int want_u, int want_e, cudaStream_t st)
+{
+    const u64 per = (want_u ? (u64)b->n / 64 : 0) + (want_e ? 8 * (u64)b->n / 64 : 0);
+    if (!per || !items) return 0;
+    k_encrypt_sample_fused<<<grid_for(per * items, 128), 128, 0, st>>>(ub, es8, b->n, (u64)items, bfv_salsa_key(b), nonce0, want_u, want_e);
+    KCHECK();
+    return 0;
+}
+}  // namespace nttb200
 
 static int ensure_scratch(nttb200_bfv *b, size_t ks_bytes, size_t es_count)
 {
@@ -275,7 +389,15 @@ extern "C" {
 int nttb200_bfv_create(nttb200_bfv **out, unsigned n, unsigned limbs, const nttb200_u64 *q, const nttb200_u64 *psi_roots, nttb200_u64 t,
                        nttb200_u64 gamma)
 {
-    if (!out || limbs < 2 || t == 0 || (t & (t - 1)) || gamma < 3) return NTTB200_EINVAL;
+    if (!out || !q || limbs < 2 || t < 2 || (t & (t - 1)) || gamma < 3) return NTTB200_EINVAL;
+    // The scheme as the reference implements it needs: t a power of two below 2^32 (32-bit masks in mod_t / fast_convert, poly_arithmetic.cuh:139,222);
+    // every q_i = 1 (mod t) (floor(q_i / t) stands in for floor(q / t) mod q_i, bfv_encryption.cuh:193-212, and the Fermat "inverse" mod t of
+    // demo.cu:109 is only an inverse then); gamma an odd prime below 2^62 coprime to every q_i (Fermat inverse demo.cu:110, 2 * gamma_bits <= 124).
+    // gamma = 1 (mod t): dec_round (poly_arithmetic.cuh:253-263) omits BEHZ's multiplication by gamma^-1 mod t -- the reference's
+    // gamma = 2^61 - 10239 is 1 mod 2^11, so its own scheme is only correct for t <= 2048.
+    if (t > (1ull << 32) || gamma >= (1ull << 62) || !(gamma & 1) || !h_is_prime(gamma) || gamma % t != 1) return NTTB200_EINVAL;
+    for (unsigned i = 0; i < limbs; i++)
+        if (q[i] % t != 1 || q[i] == gamma) return NTTB200_EINVAL;
     nttb200_ctx *ctx = nullptr;
     int rc = nttb200_ctx_create(&ctx, n, limbs, q, psi_roots);
     if (rc) return rc;
@@ -324,8 +446,29 @@ int nttb200_bfv_create(nttb200_bfv **out, unsigned n, unsigned limbs, const nttb
         unsigned acc = 0;
         for (unsigned i = 0; i < rp; i++) { woff[i] = acc; acc += n / 64 * ctx->qbit[i]; }
         b->half_words = acc;
+        std::vector<unsigned> koff(r);
+        acc = 0;
+        for (unsigned i = 0; i < r; i++) { koff[i] = acc; acc += n / 64 * ctx->qbit[i]; }
+        b->key_half_words = acc;
         if (cudaMalloc(&b->word_off, rp * sizeof(unsigned)) != cudaSuccess ||
-            cudaMemcpy(b->word_off, woff.data(), rp * sizeof(unsigned), cudaMemcpyHostToDevice) != cudaSuccess) {
+            cudaMemcpy(b->word_off, woff.data(), rp * sizeof(unsigned), cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMalloc(&b->key_word_off, r * sizeof(unsigned)) != cudaSuccess ||
+            cudaMemcpy(b->key_word_off, koff.data(), r * sizeof(unsigned), cudaMemcpyHostToDevice) != cudaSuccess) {
+            nttb200_bfv_destroy(b);
+            return (int)cudaErrorMemoryAllocation;
+        }
+    }
+    memset(b->salsa_key, 1, 32);                                                        // distributions.cuh:249 generate_random_default
+    while ((1ull << b->tsh) < t) b->tsh++;
+    {   // per-limb constants of the epilogue fused into the last inverse kernel (epi.cuh)
+        std::vector<EncEpiLimb> ek(rp);
+        for (unsigned i = 0; i < rp; i++) {
+            EncEpiLimb &e = ek[i];
+            e.q = q[i]; e.twoq = 2 * q[i]; e.inv_q_last = iql[i]; e.inv_q_last_s = shoup_companion(iql[i], q[i]);
+            e.qdt = qdt[i]; e.bias = (q[r - 1] >> 1) % q[i] + 3 * q[i]; e.ratio = ratio_of(q[i]); e.pad = 0;
+        }
+        if (cudaMalloc(&b->enc_epi, rp * sizeof(EncEpiLimb)) != cudaSuccess ||
+            cudaMemcpy(b->enc_epi, ek.data(), rp * sizeof(EncEpiLimb), cudaMemcpyHostToDevice) != cudaSuccess) {
             nttb200_bfv_destroy(b);
             return (int)cudaErrorMemoryAllocation;
         }
@@ -345,12 +488,31 @@ void nttb200_bfv_destroy(nttb200_bfv *b)
     if (b->es) cudaFree(b->es);
     if (b->pt) cudaFree(b->pt);
     if (b->word_off) cudaFree(b->word_off);
+    if (b->key_word_off) cudaFree(b->key_word_off);
+    nttb200_host_state_destroy(b->host);
+    if (b->ub) cudaFree(b->ub);
+    if (b->es8) cudaFree(b->es8);
+    if (b->enc_epi) cudaFree(b->enc_epi);
+    nttb200_shard_state_destroy(b->shard);
     cudaFree(b->sk_l); cudaFree(b->sk_ls); cudaFree(b->pk_l); cudaFree(b->pk_ls);
     nttb200_ctx_destroy(b->ctx);
     delete b;
 }
 
 nttb200_ctx *nttb200_bfv_ctx(nttb200_bfv *b) { return b ? b->ctx : nullptr; }
+
+int nttb200_bfv_set_sampling_key(nttb200_bfv *b, const unsigned char key[32])
+{
+    if (!b || !key) return NTTB200_EINVAL;
+    memcpy(b->salsa_key, key, 32);
+    return 0;
+}
+int nttb200_bfv_set_fused_epilogue(nttb200_bfv *b, int enable)
+{
+    if (!b) return NTTB200_EINVAL;
+    b->no_fused_epilogue = !enable;
+    return 0;
+}
 
 int nttb200_bfv_reserve(nttb200_bfv *b, unsigned batch)
 {
@@ -393,9 +555,11 @@ int nttb200_bfv_encrypt(nttb200_bfv *b, nttb200_u64 *c, const nttb200_u64 *pk, i
                         nttb200_u64 nonce0, void *stream)
 {
     if (!b || !c || !m || !batch || batch > 65535 || (!pk && !b->pk_l)) return NTTB200_EINVAL;
-    NTTB200_TRY(nttb200_bfv_reserve(b, batch));
+    const bool v2 = !pk && b->ctx->lazy_ok && b->enc_lazy && !b->no_fused_epilogue;
+    if (!v2) NTTB200_TRY(ensure_scratch(b, 9 * (size_t)b->n * batch, (size_t)2 * b->n * batch));      // encryption draws 9n bytes per item
     const size_t rn = (size_t)b->r * b->n;
     Pipe P = pipe_from_bfv(b, (cudaStream_t)stream);
+    if (!pk && b->ctx->lazy_ok && b->enc_lazy && !b->no_fused_epilogue) return run_encrypt_v2(b, P, c, m, batch, nonce0);
     if (!pk) return run_encrypt_fused(P, b->ctx->lazy_ok != 0, b->ks, 9 * (size_t)b->n, b->es, c, b->pk_l, b->pk_ls, m, b->n, b->t, batch, nonce0);
     return run_encrypt(P, b->ks, 9 * (size_t)b->n, b->es, c, pk, pk_per_item ? 2 * rn : 0, m, b->n, b->t, batch, nonce0);
 }
@@ -487,6 +651,52 @@ int nttb200_bfv_unpack(nttb200_bfv *b, nttb200_u64 *c, const nttb200_u64 *packed
     return 0;
 }
 
+// keys: sk[batch][r][n] (polys = r) or pk[batch][2][r][n] (polys = 2r), all r limbs packed
+int nttb200_bfv_pack_key(nttb200_bfv *b, nttb200_u64 *packed, const nttb200_u64 *key, unsigned polys, unsigned batch, void *stream)
+{
+    if (!b || !packed || !key || !batch || (polys != b->r && polys != 2 * b->r) || (size_t)batch * 2 > 65535) return NTTB200_EINVAL;
+    const unsigned n = b->n, r = b->r, groups = polys / r * batch;
+    const unsigned x = (n / 64 + 127) / 128;
+    // the kernel packs limbs [0, gridDim.y) of groups of `r + 1` polynomials when told r + 1: here every limb of a group of r is stored
+    k_ct_pack<<<dim3(x, r, groups), 128, 0, (cudaStream_t)stream>>>(key, packed, n, r, batch, b->ctx->qbit_dev, b->key_word_off, b->key_half_words);
+    KCHECK();
+    return 0;
+}
+int nttb200_bfv_unpack_key(nttb200_bfv *b, nttb200_u64 *key, const nttb200_u64 *packed, unsigned polys, unsigned batch, void *stream)
+{
+    if (!b || !packed || !key || !batch || (polys != b->r && polys != 2 * b->r) || (size_t)batch * 2 > 65535) return NTTB200_EINVAL;
+    const unsigned n = b->n, r = b->r, groups = polys / r * batch;
+    const unsigned x = (n / 64 + 127) / 128;
+    k_ct_unpack<<<dim3(x, r, groups), 128, 0, (cudaStream_t)stream>>>(packed, key, n, r, batch, b->ctx->qbit_dev, b->key_word_off, b->key_half_words);
+    KCHECK();
+    return 0;
+}
+// device ciphertexts <-> packed HOST bytes (synchronous; a staging buffer is allocated per call: not a hot-path entry)
+int nttb200_bfv_pack_host(nttb200_bfv *b, nttb200_u64 *packed_host, const nttb200_u64 *c, unsigned batch, void *stream)
+{
+    if (!b || !packed_host || !c || !batch) return NTTB200_EINVAL;
+    const size_t words = (size_t)batch * 2 * b->half_words;
+    u64 *tmp = nullptr;
+    NTTB200_CHECK(cudaMalloc(&tmp, words * 8));
+    int rc = nttb200_bfv_pack(b, tmp, c, batch, stream);
+    if (!rc) rc = (int)cudaMemcpyAsync(packed_host, tmp, words * 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (!rc) rc = (int)cudaStreamSynchronize((cudaStream_t)stream);
+    cudaFree(tmp);
+    return rc;
+}
+int nttb200_bfv_unpack_host(nttb200_bfv *b, nttb200_u64 *c, const nttb200_u64 *packed_host, unsigned batch, void *stream)
+{
+    if (!b || !packed_host || !c || !batch) return NTTB200_EINVAL;
+    const size_t words = (size_t)batch * 2 * b->half_words;
+    u64 *tmp = nullptr;
+    NTTB200_CHECK(cudaMalloc(&tmp, words * 8));
+    int rc = (int)cudaMemcpyAsync(tmp, packed_host, words * 8, cudaMemcpyHostToDevice, (cudaStream_t)stream);
+    if (!rc) rc = nttb200_bfv_unpack(b, c, tmp, batch, stream);
+    if (!rc) rc = (int)cudaStreamSynchronize((cudaStream_t)stream);
+    cudaFree(tmp);
+    return rc;
+}
+
 // ---- limb-sharded decryption: this GPU's share up to the cross-limb reduction, and the step after the all-reduce -------
 // c_shard: items of [2][count][n] holding limbs [first, first+count) of c0 then of c1; sk_shard[count][n] (or per item).
 int nttb200_bfv_decrypt_partial(nttb200_bfv *b, nttb200_u64 *partial, nttb200_u64 *c_shard, const nttb200_u64 *sk_shard, int sk_per_item,
@@ -511,7 +721,7 @@ int nttb200_bfv_decrypt_partial(nttb200_bfv *b, nttb200_u64 *partial, nttb200_u6
     KCHECK();
     NTTB200_TRY(pipe_ntt(P, true, c_shard + c1_off, batch * limb_count, limb_count, limb_count, item));
     DecryptConsts D{b->t, b->gamma, b->mu_gamma, b->gamma_div_2, b->neg_inv_t, b->neg_inv_gamma, b->gamma_bits, b->r - 1, b->bcm};
-    k_decrypt_partial<<<pair_grid(n, batch, 1), pair_block(n, batch, 1), 0, P.st>>>(c_shard, item, c1_off, partial, n, batch, first_limb, limb_count, D, Lglob);
+    k_decrypt_partial<false><<<pair_grid(n, batch, 1), pair_block(n, batch, 1), 0, P.st>>>(c_shard, item, c1_off, partial, n, batch, first_limb, limb_count, D, Lglob);
     KCHECK();
     return 0;
 }
@@ -519,7 +729,7 @@ int nttb200_bfv_decrypt_finish(nttb200_bfv *b, nttb200_u64 *m_out, const nttb200
 {
     if (!b || !m_out || !partial_sum || !batch) return NTTB200_EINVAL;
     DecryptConsts D{b->t, b->gamma, b->mu_gamma, b->gamma_div_2, b->neg_inv_t, b->neg_inv_gamma, b->gamma_bits, b->r - 1, b->bcm};
-    k_decrypt_finish<<<pair_grid(b->n, batch, 1), pair_block(b->n, batch, 1), 0, (cudaStream_t)stream>>>(partial_sum, m_out, b->n, b->n, batch, D);
+    k_decrypt_finish<false, false><<<pair_grid(b->n, batch, 1), pair_block(b->n, batch, 1), 0, (cudaStream_t)stream>>>(partial_sum, m_out, b->n, b->n, batch, D);
     KCHECK();
     return 0;
 }
@@ -536,6 +746,7 @@ static Pipe pipe_ref(unsigned n, unsigned r, const nttb200_u64 *psi, const nttb2
     P.policy_fwd = P.policy_inv = kPolicyBarrett;
     P.psi = psi; P.psiinv = psiinv; P.psi_s = P.psiinv_s = nullptr; P.lc = nullptr;
     P.use_tma = get_tma_default(); P.st = st;
+    P.key = default_key();
     return P;
 }
 

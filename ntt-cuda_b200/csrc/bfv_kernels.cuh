@@ -50,12 +50,15 @@ __host__ __device__ __forceinline__ void salsa20_block(u32 (&o)[16], const Salsa
 
 // VecCrypt distributions.cuh:48-155 on a zeroed buffer == the raw keystream.  `streams` independent streams of
 // blocks_per_stream blocks each; stream s uses nonce0 + s and starts at out + s * stream_stride (bytes).
-NTT_KERNEL void k_salsa20_keystream(unsigned char *out, u64 blocks_per_stream, u64 streams, size_t stream_stride, SalsaKey key, u64 nonce0)
+// blk0: first block of every stream that is generated (out + s * stream_stride receives block blk0 first) -- the sharded pipelines
+// draw only the part of an item's keystream they consume (Salsa20 is counter-addressable).
+NTT_KERNEL void k_salsa20_keystream(unsigned char *out, u64 blocks_per_stream, u64 streams, size_t stream_stride, SalsaKey key, u64 nonce0,
+                                    u64 blk0 = 0)
 {
     NTT_GRID_STRIDE(i, blocks_per_stream * streams) {
         const u64 s = i / blocks_per_stream, b = i - s * blocks_per_stream;
         u32 o[16];
-        salsa20_block(o, key, nonce0 + s, b);
+        salsa20_block(o, key, nonce0 + s, blk0 + b);
         uint4 *dst = reinterpret_cast<uint4 *>(out + s * stream_stride + b * 64);
         NTT_UNROLL
         for (int v = 0; v < 4; v++) { uint4 t; t.x = o[4 * v]; t.y = o[4 * v + 1]; t.z = o[4 * v + 2]; t.w = o[4 * v + 3]; dst[v] = t; }
@@ -250,16 +253,50 @@ NTT_KERNEL void k_encrypt_sample(const unsigned char *in, size_t in_stride, u64 
 }
 // the two gaussian draws only: u is generated inside the first strided NTT pass straight from the keystream (NttArgs::gen_src),
 // so the r*n ternary residues are never written to and re-read from HBM.  grid (x, batch)
-NTT_KERNEL void k_encrypt_gauss(const unsigned char *in, size_t in_stride, int *es, unsigned n, unsigned batch)
+// e_off: byte offset of the e0 words inside an item's stream (n for the full 9n-byte stream; 0 when only blocks [n/64, 9n/64) were drawn)
+NTT_KERNEL void k_encrypt_gauss(const unsigned char *in, size_t in_stride, int *es, unsigned n, unsigned batch, size_t e_off)
 {
     (void)batch;
     const size_t k = blockIdx.y;
     const unsigned char *s = in + k * in_stride;
     NTT_PAIR_STRIDE(j, n) {
-        const u32 *g0 = reinterpret_cast<const u32 *>(s + n) + j, *g1 = reinterpret_cast<const u32 *>(s + (size_t)n * 5) + j;
+        const u32 *g0 = reinterpret_cast<const u32 *>(s + e_off) + j, *g1 = reinterpret_cast<const u32 *>(s + e_off + (size_t)n * 4) + j;
         int *e = es + k * 2 * n;
         e[j] = gaussian_value(g0[0]); e[j + 1] = gaussian_value(g0[1]);
         e[n + j] = gaussian_value(g1[0]); e[n + j + 1] = gaussian_value(g1[1]);
+    }
+}
+// Sampling of the fused-epilogue encryption path: one launch, one thread per 64-byte Salsa20 block of an item's keystream
+// (bfv_encryption.cuh:228: 9n bytes).  Blocks [0, n/64) are the ternary source of u and are stored as they are (n bytes per
+// item, read by the first strided NTT pass); blocks [n/64, 9n/64) are 2n 32-bit words that become the gaussian draws e0 | e1,
+// stored as signed bytes (|e| <= 19).  The 8n keystream bytes of e and the 8n bytes of 32-bit draws never reach HBM.
+// item0 / items: the items of the batch that get their e part (sharded runs draw e only for the items they finish);
+// every item gets its u part when `ub` is given.
+NTT_KERNEL void k_encrypt_sample_fused(unsigned char *ub, signed char *es8, unsigned n, u64 items, SalsaKey key, u64 nonce0, int want_u, int want_e)
+{
+    const u64 ublk = n / 64, eblk = 8 * (u64)n / 64;
+    const u64 per = (want_u ? ublk : 0) + (want_e ? eblk : 0);
+    NTT_GRID_STRIDE(i, per * items) {
+        const u64 k = i / per;
+        u64 b = i - k * per;
+        if (!want_u) b += ublk;
+        u32 o[16];
+        salsa20_block(o, key, nonce0 + k, b);
+        if (b < ublk) {
+            uint4 *dst = reinterpret_cast<uint4 *>(ub + k * n + b * 64);
+            NTT_UNROLL
+            for (int v = 0; v < 4; v++) { uint4 t; t.x = o[4 * v]; t.y = o[4 * v + 1]; t.z = o[4 * v + 2]; t.w = o[4 * v + 3]; dst[v] = t; }
+        } else {
+            u32 w[4];
+            NTT_UNROLL
+            for (int v = 0; v < 4; v++) {
+                w[v] = 0;
+                NTT_UNROLL
+                for (int e = 0; e < 4; e++) w[v] |= ((u32)(gaussian_value(o[4 * v + e]) & 0xff)) << (8 * e);
+            }
+            uint4 t; t.x = w[0]; t.y = w[1]; t.z = w[2]; t.w = w[3];
+            *reinterpret_cast<uint4 *>(es8 + k * 2 * (u64)n + (b - ublk) * 16) = t;
+        }
     }
 }
 // c0 = NTT(u) (.) pk0, c1 = NTT(u) (.) pk1 -- the reference transforms u twice; here NTT(u) sits in
@@ -533,6 +570,9 @@ k_decrypt_epilogue(const u64 *c, size_t item_stride, size_t c1_off, u64 *out, si
 // and part[item][1][j] = sum Barrett_gamma(v_l * bcm_g[l]) mod gamma.  One all-reduce(SUM) of `part` across the GPUs
 // (at most 8 addends < 2^61: no 64-bit overflow) followed by k_decrypt_finish reproduces k_decrypt_epilogue exactly:
 // the reference's running `(acc + v) % gamma` and the plain modular sum are the same residue.
+// PACKED (requires rp * (t - 1) < 2^16): per item [gamma sums: n u64][t sums: n 16-bit fields, four per u64] = 1.25 n words instead of
+// 2 n -- the fields cannot carry into each other under a 64-bit SUM reduction, so the collective moves 10 bytes per coefficient, not 16.
+template <bool PACKED>
 NTT_KERNEL void k_decrypt_partial(const u64 *c, size_t item_stride, size_t c1_off, u64 *part, unsigned n, unsigned batch, unsigned first,
                                   unsigned count, DecryptConsts D, LimbArrays L)
 {
@@ -545,18 +585,47 @@ NTT_KERNEL void k_decrypt_partial(const u64 *c, size_t item_stride, size_t c1_of
     NTT_PAIR_STRIDE(j, n) {
         u64 at0 = 0, at1 = 0, ag0 = 0, ag1 = 0;
         dec_sum_limbs<false>(K, c0, c1, n, j, count, mask32, D, at0, at1, ag0, ag1);
-        st2(part + k * 2 * n + j, at0, at1);
-        st2(part + k * 2 * n + n + j, ag0, ag1);
+        if (PACKED) {
+            u64 *p = part + k * (size_t)(n + n / 4);
+            st2(p + j, ag0, ag1);
+            reinterpret_cast<u32 *>(p + n)[j >> 1] = (u32)at0 | ((u32)at1 << 16);
+        } else {
+            st2(part + k * 2 * n + j, at0, at1);
+            st2(part + k * 2 * n + n + j, ag0, ag1);
+        }
     }
 }
-NTT_KERNEL void k_decrypt_finish(const u64 *part_sum, u64 *out, size_t out_stride, unsigned n, unsigned batch, DecryptConsts D)
+// OUT16: plaintext coefficients as 16-bit words (t <= 2^16; what the final gather of a sharded decryption moves)
+template <bool PACKED, bool OUT16>
+NTT_KERNEL void k_decrypt_finish(const u64 *part_sum, void *out, size_t out_stride, unsigned n, unsigned batch, DecryptConsts D)
 {
     (void)batch;
     const u32 mask32 = (u32)(D.t - 1);
     const size_t k = blockIdx.y;
     NTT_PAIR_STRIDE(j, n) {
-        const ulonglong2 pt = ld2(part_sum + k * 2 * n + j), pg = ld2(part_sum + k * 2 * n + n + j);
-        st2(out + k * out_stride + j, dec_finish_one(pt.x, pg.x % D.gamma, mask32, D), dec_finish_one(pt.y, pg.y % D.gamma, mask32, D));
+        u64 t0, t1;
+        ulonglong2 pg;
+        if (PACKED) {
+            const u64 *p = part_sum + k * (size_t)(n + n / 4);
+            pg = ld2(p + j);
+            const u32 w = reinterpret_cast<const u32 *>(p + n)[j >> 1];
+            t0 = w & 0xffffu; t1 = w >> 16;
+        } else {
+            const ulonglong2 pt = ld2(part_sum + k * 2 * n + j);
+            pg = ld2(part_sum + k * 2 * n + n + j);
+            t0 = pt.x; t1 = pt.y;
+        }
+        const u64 r0 = dec_finish_one(t0, pg.x % D.gamma, mask32, D), r1 = dec_finish_one(t1, pg.y % D.gamma, mask32, D);
+        if (OUT16) reinterpret_cast<u32 *>(reinterpret_cast<unsigned short *>(out) + k * out_stride)[j >> 1] = (u32)r0 | ((u32)r1 << 16);
+        else st2(reinterpret_cast<u64 *>(out) + k * out_stride + j, r0, r1);
+    }
+}
+// 16-bit plaintext words -> the u64 coefficients of the reference layout
+NTT_KERNEL void k_expand16(const unsigned short *in, u64 *out, size_t total)
+{
+    NTT_GRID_STRIDE(i, total / 2) {
+        const u32 w = reinterpret_cast<const u32 *>(in)[i];
+        st2(out + 2 * i, (u64)(w & 0xffffu), (u64)(w >> 16));
     }
 }
 

@@ -108,13 +108,14 @@ int nttb200_trace_error(int code, const char *file, int line)
 
 extern "C" {
 
-int nttb200_version(void) { return 100; }
+int nttb200_version(void) { return 200; }
 
 const char *nttb200_error_string(int code)
 {
     if (code == 0) return "success";
     if (code == NTTB200_EINVAL) return "nttb200: invalid argument (unsupported n / limbs / modulus, or null pointer)";
     if (code == NTTB200_ENOTMA) return "nttb200: cuTensorMapEncodeTiled unavailable or failed";
+    if (code == NTTB200_ENCCL) return "nttb200: NCCL unavailable (libnccl.so.2 not loadable) or a collective failed (NTTB200_DEBUG=1 prints the NCCL error)";
     return cudaGetErrorString((cudaError_t)code);
 }
 

@@ -83,7 +83,7 @@ static void run_one(const NttArgs &A)
     gs.x = A.num * (tiles_s1 / tpc_s);
     gc.x = A.num * (tiles_c1 / tpc_c);
     const size_t smem_s = (size_t)tpc_s * SC::NT * R * 128 + 1024 + 64, smem_c = (size_t)tpc_c * kContigRows * 128 + 1024 + 64;
-    auto strided = [&] { emu_launch(gs, R * SC::NT, smem_s, [&] { ntt_strided_pass<P, LOGN, INV>(ms, A); }); };
+    auto strided = [&] { emu_launch(gs, R * SC::NT, smem_s, [&] { ntt_strided_pass<P, LOGN, INV>(ms, A, EpiArgs{}); }); };
     auto contig = [&] { emu_launch(gc, kContigRows, smem_c, [&] { ntt_contig_pass<P, LOGN, INV>(mc, A); }); };
     if (!INV) { if (g_which != 1) strided(); if (g_which != 0) contig(); } else { if (g_which != 1) contig(); if (g_which != 0) strided(); }
 }
@@ -290,7 +290,7 @@ EXPORT int emu_bfv(int op, unsigned n, unsigned r, const u64 *q, const u64 *mu, 
             ew3(batch, 1, [&] { k_encrypt_sample(in, stride, c, es, n, r, batch, q); });
             ring_ntt(R, false, c, batch * r, r, r, 2 * rn);
         } else {           // context path: u generated inside the first strided pass
-            ew3(batch, 1, [&] { k_encrypt_gauss(in, stride, es, n, batch); });
+            ew3(batch, 1, [&] { k_encrypt_gauss(in, stride, es, n, batch, (size_t)n); });
             g_gen_src = in; g_gen_stride = stride;
             ring_ntt(R, false, c, batch * r, r, r, 2 * rn, 0);
             g_gen_src = nullptr;
@@ -305,7 +305,7 @@ EXPORT int emu_bfv(int op, unsigned n, unsigned r, const u64 *q, const u64 *mu, 
         u64 *pk_s = new u64[2 * rn];
         ew([&] { k_build_companions(pk, pk_s, q, R.logn, r, 2 * r); });
         ew([&] { k_salsa20_keystream(in, nblk, (u64)batch, stride, key, nonce0); });
-        ew3(batch, 1, [&] { k_encrypt_gauss(in, stride, es, n, batch); });
+        ew3(batch, 1, [&] { k_encrypt_gauss(in, stride, es, n, batch, (size_t)n); });
         if (op == 5) R.barrett = -1;
         g_gen_src = in; g_gen_stride = stride;
         ring_ntt(R, false, c, batch * r, r, r, 2 * rn, 0);
@@ -394,12 +394,134 @@ EXPORT int emu_bfv_sharded(int op, unsigned n, unsigned r, const u64 *q, const u
         ring_ntt(R, false, c_shard + c1_off, batch * count, count, count, item);
         ew3(count, batch, [&] { k_decrypt_mul(c_shard, item, c1_off, sk_shard, 0, n, count, batch, Lloc); });
         ring_ntt(R, true, c_shard + c1_off, batch * count, count, count, item);
-        ew3(batch, 1, [&] { k_decrypt_partial(c_shard, item, c1_off, part, n, batch, first, count, D, Lglob); });
+        ew3(batch, 1, [&] { k_decrypt_partial<false>(c_shard, item, c1_off, part, n, batch, first, count, D, Lglob); });
     } else {
-        ew3(batch, 1, [&] { k_decrypt_finish(part, out, (size_t)n, n, batch, D); });
+        ew3(batch, 1, [&] { k_decrypt_finish<false, false>(part, out, (size_t)n, n, batch, D); });
     }
     return 0;
 }
+
+
+// ---- fused-epilogue encryption / fused sharded decryption building blocks on the emulator (mirror csrc/bfv.cu: enc_sample, enc_front,
+// enc_finish_last, enc_finish_limbs, dec_partial, dec_finish, dec_expand16) -----------------------------------------------------------
+template <int LOGN, class EPI>
+static void run_strided_inv_epi_one(const NttArgs &A, const EpiArgs &E)
+{
+    using SC = Sched<LOGN>;
+    using P = ShoupLazyInvPolicy;
+    constexpr int R = 1 << SC::K1;
+    const size_t n = (size_t)1 << LOGN;
+    const unsigned groups = (A.num + A.group_polys - 1) / A.group_polys;
+    TensorMap ms;
+    EmuTmapDesc ds{};
+    ds.base = (unsigned char *)A.a; ds.rank = 4;
+    ds.dims[0] = n >> SC::K1; ds.dims[1] = R; ds.dims[2] = A.group_polys; ds.dims[3] = groups;
+    ds.strides[0] = 8; ds.strides[1] = (n >> SC::K1) * 8; ds.strides[2] = n * 8; ds.strides[3] = A.group_stride * 8;
+    ds.box[0] = 16; ds.box[1] = R > 256 ? 256 : R; ds.box[2] = 1; ds.box[3] = 1; ds.swizzle128 = 0;
+    memcpy(ms.opaque, &ds, sizeof ds);
+    const unsigned tiles_s1 = (unsigned)(((n >> SC::K1) >> 4) / SC::NT);
+    const int tpc_s = tiles_per_cta(tiles_s1);
+    emu_dim3 gs;
+    gs.x = A.num * (tiles_s1 / tpc_s);
+    emu_launch(gs, R * SC::NT, (size_t)tpc_s * SC::NT * R * 128 + 1024 + 64, [&] { ntt_strided_pass<P, LOGN, true, EPI>(ms, A, E); });
+}
+template <class EPI>
+static int run_strided_inv_epi(int logn, const NttArgs &A, const EpiArgs &E)
+{
+    switch (logn) {
+    case 11: run_strided_inv_epi_one<11, EPI>(A, E); return 0;
+    case 12: run_strided_inv_epi_one<12, EPI>(A, E); return 0;
+    case 13: run_strided_inv_epi_one<13, EPI>(A, E); return 0;
+    case 14: run_strided_inv_epi_one<14, EPI>(A, E); return 0;
+    case 15: run_strided_inv_epi_one<15, EPI>(A, E); return 0;
+    case 16: run_strided_inv_epi_one<16, EPI>(A, E); return 0;
+    case 17: run_strided_inv_epi_one<17, EPI>(A, E); return 0;
+    }
+    return 1;
+}
+namespace {
+EmuRing ring_window(const EmuRing &R, unsigned first, unsigned count)
+{
+    EmuRing W = R;
+    const size_t toff = (size_t)first * R.n;
+    W.r = count; W.q = R.q + first; W.mu = R.mu + first; W.qbit = R.qbit + first;
+    W.psi = R.psi + toff; W.psiinv = R.psiinv + toff; W.psi_s = R.psi_s + toff; W.psiinv_s = R.psiinv_s + toff; W.lc = R.lc + first;
+    return W;
+}
+}  // namespace
+
+// op 0: sample (want_u = i0, want_e = i1; items, nonce0) | 1: front | 2: finish_last | 3: finish_limbs
+EXPORT int emu_enc_blocks(int op, unsigned n, unsigned r, const u64 *q, const u64 *mu, const u32 *qbit, const u64 *psi, const u64 *psiinv,
+                          const u64 *psi_s, const u64 *psiinv_s, const LimbConst *lc, unsigned first, unsigned count, unsigned slots, unsigned items,
+                          u64 *c, unsigned char *ub, signed char *es8, const u64 *pk, const u64 *pk_s, u64 *cl, size_t cl_item_stride,
+                          size_t cl_half_stride, const u64 *m, const EncEpiLimb *K, u64 t, unsigned tsh, u64 nonce0, int i0, int i1)
+{
+    EmuRing R{n, 0, r, q, mu, qbit, psi, psiinv, psi_s, psiinv_s, lc, 0};
+    while ((1u << R.logn) < n) R.logn++;
+    const size_t rn = (size_t)r * n;
+    SalsaKey key; for (int i = 0; i < 8; i++) key.k[i] = 0x01010101u;
+    EpiArgs E{};
+    E.es = es8; E.K = K; E.last = q[r - 1]; E.half_last = E.last >> 1; E.t = t; E.tfix = (t + 1) >> 1; E.tsh = tsh;
+    if (op == 0) {
+        ew([&] { k_encrypt_sample_fused(ub, es8, n, (u64)items, key, nonce0, i0, i1); });
+    } else if (op == 1) {
+        EmuRing W = ring_window(R, first, count);
+        const size_t item = (size_t)2 * slots * n;
+        g_gen_src = ub; g_gen_stride = n;
+        ring_ntt(W, false, c, items * count, count, count, item, 0);
+        g_gen_src = nullptr;
+        ring_fused(W, true, c, 2 * slots, item, pk + (size_t)first * n, pk_s + (size_t)first * n, rn, count, 0, 0, slots, items, 2);
+    } else if (op == 2) {
+        EmuRing W = ring_window(R, r - 1, 1);
+        NttArgs A{};
+        A.a = cl; A.tw = W.psiinv; A.tws = W.psiinv_s; A.lc = W.lc; A.num = items * 2; A.division = 1; A.use_tma = 1;
+        A.group_polys = 1; A.group_stride = cl_half_stride;
+        if (cl_item_stride != 2 * cl_half_stride) return 2;
+        return run_strided_inv_epi<EncLastEpi>((int)R.logn, A, E);
+    } else if (op == 3) {
+        EmuRing W = ring_window(R, first, count);
+        NttArgs A{};
+        A.a = c; A.tw = W.psiinv; A.tws = W.psiinv_s; A.lc = W.lc; A.num = items * 2 * count; A.division = count; A.use_tma = 1;
+        A.group_polys = count; A.group_stride = (size_t)slots * n;
+        E.cl = cl; E.cl_item_stride = cl_item_stride; E.cl_half_stride = cl_half_stride; E.m = m; E.m_stride = n; E.first_limb = first;
+        return run_strided_inv_epi<EncLimbEpi>((int)R.logn, A, E);
+    } else {
+        return 1;
+    }
+    return 0;
+}
+
+// op 0: partial sums of limbs [first, first+count) through the fused kernel (loaded key) | 1: finish | 2: expand 16-bit plaintexts
+EXPORT int emu_dec_blocks(int op, unsigned n, unsigned r, const u64 *q, const u64 *mu, const u32 *qbit, const u64 *psi, const u64 *psiinv,
+                          const u64 *psi_s, const u64 *psiinv_s, const LimbConst *lc, unsigned first, unsigned count, unsigned slots, unsigned items,
+                          u64 *c_shard, const u64 *sk, const u64 *sk_s, u64 *part, void *out, int packed, int out16, const u64 *ptg, const u64 *ipq,
+                          const u64 *bcm, u64 t, u64 gamma, u64 mu_gamma, int gamma_bits, u64 neg_inv_t, u64 neg_inv_gamma)
+{
+    EmuRing R{n, 0, r, q, mu, qbit, psi, psiinv, psi_s, psiinv_s, lc, 0};
+    while ((1u << R.logn) < n) R.logn++;
+    DecryptConsts D{t, gamma, mu_gamma, gamma >> 1, neg_inv_t, neg_inv_gamma, gamma_bits, r - 1, bcm};
+    LimbArrays Lglob{q, mu, qbit, nullptr, ipq, ptg};
+    if (op == 0) {
+        EmuRing W = ring_window(R, first, count);
+        const size_t item = (size_t)2 * slots * n, c1_off = (size_t)slots * n;
+        ring_ntt(W, false, c_shard + c1_off, items * count, count, count, item, 0);
+        ring_fused(W, true, c_shard, 2 * slots, item, sk + (size_t)first * n, sk_s + (size_t)first * n, 0, count, slots, slots, slots, items, 1);
+        ring_ntt(W, true, c_shard + c1_off, items * count, count, count, item, 1);
+        if (packed) ew3(items, 1, [&] { k_decrypt_partial<true>(c_shard, item, c1_off, part, n, items, first, count, D, Lglob); });
+        else ew3(items, 1, [&] { k_decrypt_partial<false>(c_shard, item, c1_off, part, n, items, first, count, D, Lglob); });
+    } else if (op == 1) {
+        if (packed && out16) ew3(items, 1, [&] { k_decrypt_finish<true, true>(part, out, (size_t)n, n, items, D); });
+        else if (packed) ew3(items, 1, [&] { k_decrypt_finish<true, false>(part, out, (size_t)n, n, items, D); });
+        else if (out16) ew3(items, 1, [&] { k_decrypt_finish<false, true>(part, out, (size_t)n, n, items, D); });
+        else ew3(items, 1, [&] { k_decrypt_finish<false, false>(part, out, (size_t)n, n, items, D); });
+    } else if (op == 2) {
+        ew([&] { k_expand16((const unsigned short *)part, (u64 *)out, (size_t)items * n); });
+    } else {
+        return 1;
+    }
+    return 0;
+}
+EXPORT unsigned emu_sizeof_encepilimb() { return (unsigned)sizeof(EncEpiLimb); }
 
 // wire format + homomorphic helper kernels on the emulator (op 0: pack, 1: unpack, 2: ct add, 3: plaintext lift)
 EXPORT int emu_ct_ops(int op, u64 *c, u64 *other, unsigned n, unsigned r, unsigned batch, const u64 *q, const u32 *qbit, const u32 *word_off,

@@ -15,6 +15,9 @@ int nttb200_trace_error(int code, const char *file, int line);
         if (e__ != cudaSuccess) return nttb200_trace_error((int)e__, __FILE__, __LINE__);        \
     } while (0)
 
+#define NTTB200_TRY(x) do { int r__ = (x); if (r__) return nttb200_trace_error(r__, __FILE__, __LINE__); } while (0)
+#define KCHECK() do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return nttb200_trace_error((int)e__, __FILE__, __LINE__); } while (0)
+
 struct nttb200_ctx {
     unsigned n = 0, logn = 0, limbs = 0;
     int device = 0;
@@ -65,6 +68,9 @@ int launch_fused_mul(bool lazy, unsigned logn, const NttArgsHost &h, const u64 *
 
 int launch_polymul(bool lazy, unsigned logn, const NttArgsHost &ha, const u64 *twi, const u64 *twis, const u64 *b, unsigned b_group_polys,
                    size_t b_group_stride, bool fwd, u64 *out, cudaStream_t st);
+
+struct EpiArgs;
+int launch_strided_inv_epi(unsigned logn, const NttArgsHost &h, int mode, const EpiArgs &E, cudaStream_t st);
 
 int get_tma_default();
 

@@ -21,6 +21,7 @@
 #pragma once
 #include "modarith.cuh"
 #include "tile_io.cuh"
+#include "epi.cuh"
 
 #ifdef NTTB200_EMU
 struct TensorMap { unsigned char opaque[128]; };
@@ -452,8 +453,9 @@ __device__ __forceinline__ void regs_row(u64 *tile, u32 row, u64 (&v)[16])
 }
 
 // One round of the strided pass: stages [J0, J0+S) of K1 on thread-in-tile index u in [0, 2^K1).
-template <class P, int K1, int J0, int S, bool INV>
-__device__ __forceinline__ void strided_round(u64 *tile, u32 u, const P &pol)
+// EPI (final inverse round only): applied to the canonical outputs; coefficient index of (row, col) = row * C + cbase + col
+template <class P, int K1, int J0, int S, bool INV, class EPI = NoEpi>
+__device__ __forceinline__ void strided_round(u64 *tile, u32 u, const P &pol, const EPI *epi = nullptr, u32 C = 0, u32 cbase = 0)
 {
     constexpr int NC = 16 >> S;
     constexpr int LOB = K1 - J0 - S;  // row bits below the round's bits
@@ -465,6 +467,14 @@ __device__ __forceinline__ void strided_round(u64 *tile, u32 u, const P &pol)
     regs_rows<S, false, true>(tile, rbase, LOB, cg * NC, v);
     if (!INV) ct_stages<S, NC>(v, (1u << J0) + hi, pol);
     else gs_stages<S, NC, J0 == 0>(v, (1u << J0) + hi, pol);
+    if constexpr (INV && J0 == 0 && EPI::kMode != kEpiNone) {
+        NTT_UNROLL
+        for (int i = 0; i < (1 << S); i++) {
+            const u32 j = (rbase + ((u32)i << LOB)) * C + cbase + cg * NC;
+            NTT_UNROLL
+            for (int c = 0; c < NC; c++) v[i * NC + c] = epi->apply(v[i * NC + c], j + c);
+        }
+    }
     regs_rows<S, false, false>(tile, rbase, LOB, cg * NC, v);
 }
 
@@ -490,9 +500,9 @@ __device__ __forceinline__ u64 *align_1024(unsigned char *p)
 __host__ __device__ constexpr int tiles_per_cta(u32 tiles_per_poly) { return tiles_per_poly % NTT_TPC == 0 ? NTT_TPC : 1; }
 
 // ---- pass "strided": grid (num * tiles / TPC), tiles = n / 2^K1 / 16 / NT column tiles per polynomial; 2^K1 * NT threads ----------------------
-template <class P, int LOGN, bool INV>
+template <class P, int LOGN, bool INV, class EPI = NoEpi>
 __global__ void __launch_bounds__((1 << Sched<LOGN>::K1) * Sched<LOGN>::NT, ((1 << Sched<LOGN>::K1) * Sched<LOGN>::NT) > 256 ? 2 : NTT_MINB_S)
-ntt_strided_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
+ntt_strided_pass(const __grid_constant__ TensorMap tmap, NttArgs A, EpiArgs E)
 {
     using SC = Sched<LOGN>;
     constexpr int K1 = SC::K1, R = 1 << K1, NT = SC::NT, THREADS = R * NT;
@@ -596,7 +606,13 @@ ntt_strided_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
         } else {
             if constexpr (SC::S3 != 0) { strided_round<P, K1, SC::S1 + SC::S2, SC::S3, true>(tile, u, pol); __syncthreads(); }
             if constexpr (SC::S2 != 0) { strided_round<P, K1, SC::S1, SC::S2, true>(tile, u, pol); __syncthreads(); }
-            strided_round<P, K1, 0, SC::S1, true>(tile, u, pol);
+            if constexpr (EPI::kMode != kEpiNone) {
+                EPI epi;
+                epi.init(E, grp, idx, n);
+                strided_round<P, K1, 0, SC::S1, true, EPI>(tile, u, pol, &epi, C, colbase + ((u32)tt * NT + (tid >> K1)) * 16u);
+            } else {
+                strided_round<P, K1, 0, SC::S1, true>(tile, u, pol);
+            }
         }
 
         if (dbg_nomem) {
@@ -762,9 +778,7 @@ struct FusedArgs {
 };
 
 template <class PF, class PI, int LOGN, int NOUT>
-// two outputs: 168 registers and three CTAs per SM; parking the forward row in shared memory to reach 128 registers / four CTAs
-// spilled and measured 3 % slower (profiles/r01_experiments.md)
-__global__ void __launch_bounds__(kContigRows, NOUT == 2 ? 3 : 4)
+__global__ void __launch_bounds__(kContigRows, 4)
 ntt_contig_fused_mul(const __grid_constant__ TensorMap tmap, FusedArgs F)
 {
     using SC = Sched<LOGN>;
@@ -818,27 +832,33 @@ ntt_contig_fused_mul(const __grid_constant__ TensorMap tmap, FusedArgs F)
     __syncwarp();
     regs_row<true, true>(tile, tid, v);
     ct_stages<4, 1>(v, twB, pf);
-    // (.) key, inverse row round, per output
+    // (.) key, inverse row round, per output.  Two outputs: the lazy forward row is PARKED in the thread's own tile row and re-read
+    // per output (the __syncwarp keeps the compiler from forwarding the stored registers), so no 16-coefficient vector stays live
+    // across an output: 128 registers / four CTAs per SM instead of 168 / three.  Output 0 goes to tile2, output 1 overwrites the
+    // parked row in place (only this lane touches its row before the next __syncwarp).
+    if (NOUT == 2) { regs_row<true, false>(tile, tid, v); __syncwarp(); }
+    u64 *const out_tile0 = NOUT == 2 ? tile2 : tile, *const out_tile1 = tile;
     const size_t krow = (size_t)item * F.key_item_stride + ((size_t)limb << LOGN) + ((size_t)(rip0 + tid) << 4);
     NTT_UNROLL
     for (int o = 0; o < NOUT; o++) {
         const u64 *kp = F.key + krow + (size_t)o * F.key_half_stride, *ks = F.key_s + krow + (size_t)o * F.key_half_stride;
-        u64 x[16];        NTT_UNROLL
+        if (NOUT == 2) regs_row<true, true>(tile, tid, v);
+        u64 x[16];
+        NTT_UNROLL
         for (int c = 0; c < 8; c++) {
             const ulonglong2 kv = __ldg(reinterpret_cast<const ulonglong2 *>(kp) + c), sv = __ldg(reinterpret_cast<const ulonglong2 *>(ks) + c);
             x[2 * c] = pi.mul_key(v[2 * c], kv.x, sv.x);
             x[2 * c + 1] = pi.mul_key(v[2 * c + 1], kv.y, sv.y);
         }
         gs_stages<4, 1, false>(x, twB, pi);
-        u64 *dst = o == 0 ? tile : tile2;
-        if (NOUT == 2 && o == 0) __syncwarp();            // every lane has read its forward row before rows are overwritten
-        regs_row<true, false>(dst, tid, x);
+        regs_row<true, false>(o == 0 ? out_tile0 : out_tile1, tid, x);
+        if (NOUT == 2 && o == 0) __syncwarp();
     }
     __syncwarp();
     // inverse column round on each output tile
     NTT_UNROLL
     for (int o = 0; o < NOUT; o++) {
-        u64 *dst = o == 0 ? tile : tile2;
+        u64 *dst = o == 0 ? out_tile0 : out_tile1;
         regs_rows<SA, true, true>(dst, bl << SA, 0, t * NC, v);
         gs_stages<SA, NC, false>(v, twA, pi);
         regs_rows<SA, true, false>(dst, bl << SA, 0, t * NC, v);
@@ -848,23 +868,23 @@ ntt_contig_fused_mul(const __grid_constant__ TensorMap tmap, FusedArgs F)
 #ifdef NTTB200_EMU
         __syncthreads();
         if (tid == 0) {
-            emu_tma_3d(false, &tmap, tile, 0, row_o0, (int)item);
-            if (NOUT == 2) emu_tma_3d(false, &tmap, tile2, 0, row_o1, (int)item);
+            emu_tma_3d(false, &tmap, out_tile0, 0, row_o0, (int)item);
+            if (NOUT == 2) emu_tma_3d(false, &tmap, out_tile1, 0, row_o1, (int)item);
         }
 #else
         fence_proxy_async();
         __syncthreads();
         if (tid == 0) {
-            tma_store_3d(&tmap, tile, 0, row_o0, (int)item);
-            if (NOUT == 2) tma_store_3d(&tmap, tile2, 0, row_o1, (int)item);
+            tma_store_3d(&tmap, out_tile0, 0, row_o0, (int)item);
+            if (NOUT == 2) tma_store_3d(&tmap, out_tile1, 0, row_o1, (int)item);
             tma_store_commit();
             tma_store_wait_read<0>();
         }
 #endif
     } else {
         __syncthreads();
-        tile_copy_coop<true, false>(tile, gbase + (size_t)row_o0 * 16, 16, RT, tid, RT);
-        if (NOUT == 2) tile_copy_coop<true, false>(tile2, gbase + (size_t)row_o1 * 16, 16, RT, tid, RT);
+        tile_copy_coop<true, false>(out_tile0, gbase + (size_t)row_o0 * 16, 16, RT, tid, RT);
+        if (NOUT == 2) tile_copy_coop<true, false>(out_tile1, gbase + (size_t)row_o1 * 16, 16, RT, tid, RT);
     }
     (void)bar;
 }

@@ -1,0 +1,393 @@
+// sharded.cu -- limb-sharded BFV encryption / decryption across the GPUs of one NVSwitch box (BASELINE configs 4-5).
+//
+// The reference is single-GPU.  Units (ciphertext, limb) are independent everywhere except
+//   * encryption's modulus switch: every limb needs the DROPPED limb's rounded value (bfv_encryption.cuh:146-149), and
+//   * decryption's base conversion: one sum over the limbs (fast_convert_array_kernel_t / _gamma, poly_arithmetic.cuh:217-251).
+// Partition (nttb200_shard_plan): the batch is cut into `world` item blocks; unit (limb l, block j) has flat index l * world + j and
+// rank g owns flat indices [g * rp, (g + 1) * rp) -- exactly rp (limb, block) tiles per rank whatever rp and world are (15 limbs on 8
+// GPUs: no idle rank), and for a fixed block the limbs a rank owns are a contiguous range.  The dropped limb of block j is computed by
+// rank j, once, and all-gathered (it is 1/r of the work: recomputing it on every rank, as round 1 did, costs 8/15 extra at 8 GPUs).
+// Decryption: per block, partial base-conversion sums packed to 10 bytes per coefficient -> ncclReduce to the block's owner (or a
+// chunked ncclReduceScatter) on a second stream while the next block's transforms run -> rounding on the owner -> ONE all-gather of
+// 16-bit plaintext words.  Bit-identical to the single-GPU calls (tests/test_gpu_sharded.py, scripts/multigpu_check.py).
+//
+// NCCL is bound at run time (dlopen of the libnccl already in the process, e.g. PyTorch's, else the system one): libnttb200.so
+// itself has no NCCL link dependency and single-GPU users never load it.
+#include "bfv_internal.h"
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+using namespace nttb200;
+
+// ---- NCCL, bound at run time ---------------------------------------------------------------------------------------------------
+namespace {
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*CommCount)(const ncclComm_t, int *) = nullptr;
+    ncclResult_t (*CommUserRank)(const ncclComm_t, int *) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*ReduceScatter)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Reduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+NcclApi &nccl()
+{
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api;
+    tried = true;
+    // the library that created the caller's communicator must be the one we call: prefer what the process already holds
+    const char *names[] = {getenv("NTTB200_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (int pass = 0; pass < 2 && !api.handle; pass++)
+        for (const char *nm : names) {
+            if (!nm) continue;
+            api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL | (pass == 0 ? RTLD_NOLOAD : 0));
+            if (api.handle) break;
+        }
+    if (!api.handle) return api;
+#define NTTB200_SYM(f) *(void **)(&api.f) = dlsym(api.handle, "nccl" #f)
+    NTTB200_SYM(GetUniqueId); NTTB200_SYM(CommInitRank); NTTB200_SYM(CommDestroy); NTTB200_SYM(CommCount); NTTB200_SYM(CommUserRank);
+    NTTB200_SYM(AllGather); NTTB200_SYM(ReduceScatter); NTTB200_SYM(Reduce); NTTB200_SYM(GroupStart); NTTB200_SYM(GroupEnd);
+    NTTB200_SYM(GetErrorString);
+#undef NTTB200_SYM
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.ReduceScatter && api.Reduce && api.GroupStart &&
+             api.GroupEnd;
+    return api;
+}
+int nccl_fail(ncclResult_t r, const char *file, int line)
+{
+    const char *e = getenv("NTTB200_DEBUG");
+    if (e && e[0] == '1') fprintf(stderr, "nttb200: NCCL error %d (%s) at %s:%d\n", (int)r, nccl().GetErrorString ? nccl().GetErrorString(r) : "?", file, line);
+    return NTTB200_ENCCL;
+}
+}  // namespace
+#define NCCLCHECK(x) do { ncclResult_t r__ = (x); if (r__ != ncclSuccess) return nccl_fail(r__, __FILE__, __LINE__); } while (0)
+#define TRY(x) do { int r__ = (x); if (r__) return nttb200_trace_error(r__, __FILE__, __LINE__); } while (0)
+
+struct nttb200_comm {
+    ncclComm_t comm = nullptr;
+    int world = 1, rank = 0;
+    bool owned = false;
+};
+
+// scratch + second stream of the sharded entry points, owned by the BFV context (grow-only: warm up before graph capture)
+struct nttb200_shard_state {
+    cudaStream_t cs = nullptr;                    // collectives (and the owner's rounding) run here, next to the transforms
+    std::vector<cudaEvent_t> ev;
+    unsigned char *buf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t cap[6] = {0, 0, 0, 0, 0, 0};
+    int mode = 0;                                 // 0: per-block ncclReduce to the owner; 1: chunked ncclReduceScatter
+    unsigned chunks = 4;
+};
+enum { kBufUb = 0, kBufEs, kBufCl, kBufPartial, kBufRecv, kBufPlain };
+
+void nttb200_shard_state_destroy(nttb200_shard_state *s)
+{
+    if (!s) return;
+    for (auto e : s->ev) cudaEventDestroy(e);
+    for (auto p : s->buf) if (p) cudaFree(p);
+    if (s->cs) cudaStreamDestroy(s->cs);
+    delete s;
+}
+static int shard_state(nttb200_bfv *b, nttb200_shard_state **out, size_t events)
+{
+    if (!b->shard) {
+        b->shard = new nttb200_shard_state();
+        if (const char *e = getenv("NTTB200_SHARD_MODE")) b->shard->mode = atoi(e);
+        if (const char *e = getenv("NTTB200_SHARD_CHUNKS")) b->shard->chunks = (unsigned)atoi(e) ? (unsigned)atoi(e) : 1u;
+        NTTB200_CHECK(cudaStreamCreateWithFlags(&b->shard->cs, cudaStreamNonBlocking));
+    }
+    nttb200_shard_state *s = b->shard;
+    while (s->ev.size() < events) {
+        cudaEvent_t e;
+        NTTB200_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        s->ev.push_back(e);
+    }
+    *out = s;
+    return 0;
+}
+static int shard_buf(nttb200_shard_state *s, int which, size_t bytes, void **p)
+{
+    if (s->cap[which] < bytes) {
+        if (s->buf[which]) NTTB200_CHECK(cudaFree(s->buf[which]));
+        s->buf[which] = nullptr; s->cap[which] = 0;
+        NTTB200_CHECK(cudaMalloc(&s->buf[which], bytes));
+        s->cap[which] = bytes;
+    }
+    *p = s->buf[which];
+    return 0;
+}
+
+static void plan_blocks(unsigned rp, unsigned n, unsigned batch, unsigned world, unsigned rank, nttb200_shard_block *blk, size_t *words)
+{
+    const unsigned per = batch / world;
+    size_t off = 0;
+    for (unsigned j = 0; j < world; j++) {
+        // limbs l with rank * rp <= l * world + j < (rank + 1) * rp
+        const long lo_num = (long)rank * rp - (long)j, hi_num = (long)(rank + 1) * rp - 1 - (long)j;
+        long lmin = lo_num <= 0 ? 0 : (lo_num + world - 1) / world;
+        long lmax = hi_num < 0 ? -1 : hi_num / (long)world;
+        if (lmax > (long)rp - 1) lmax = (long)rp - 1;
+        const unsigned cnt = lmax >= lmin ? (unsigned)(lmax - lmin + 1) : 0u;
+        blk[j].first_item = j * per; blk[j].items = per;
+        blk[j].first_limb = cnt ? (unsigned)lmin : 0u; blk[j].limb_count = cnt;
+        blk[j].offset = off;
+        off += (size_t)per * 2 * cnt * n;
+    }
+    if (words) *words = off;
+}
+
+extern "C" {
+
+int nttb200_shard_plan(unsigned rp, unsigned n, unsigned batch, unsigned world, unsigned rank, nttb200_shard_block *blocks, size_t *shard_words)
+{
+    if (!blocks || !rp || !world || rank >= world || !batch || batch % world) return NTTB200_EINVAL;
+    plan_blocks(rp, n, batch, world, rank, blocks, shard_words);
+    return 0;
+}
+
+int nttb200_comm_unique_id(unsigned char id[128])
+{
+    if (!id || !nccl().ok) return NTTB200_ENCCL;
+    ncclUniqueId u;
+    NCCLCHECK(nccl().GetUniqueId(&u));
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(id, &u, 128);
+    return 0;
+}
+int nttb200_comm_create(nttb200_comm **out, const unsigned char id[128], int world, int rank)
+{
+    if (!out || !id || world < 1 || rank < 0 || rank >= world) return NTTB200_EINVAL;
+    nttb200_comm *c = new nttb200_comm();
+    c->world = world; c->rank = rank;
+    if (world > 1) {
+        if (!nccl().ok) { delete c; return NTTB200_ENCCL; }
+        ncclUniqueId u;
+        memcpy(&u, id, 128);
+        ncclResult_t r = nccl().CommInitRank(&c->comm, world, u, rank);
+        if (r != ncclSuccess) { delete c; return nccl_fail(r, __FILE__, __LINE__); }
+        c->owned = true;
+    }
+    *out = c;
+    return 0;
+}
+int nttb200_comm_adopt(nttb200_comm **out, void *nccl_comm, int world, int rank)
+{
+    if (!out || world < 1 || rank < 0 || rank >= world || (world > 1 && !nccl_comm)) return NTTB200_EINVAL;
+    if (world > 1 && !nccl().ok) return NTTB200_ENCCL;
+    nttb200_comm *c = new nttb200_comm();
+    c->comm = (ncclComm_t)nccl_comm; c->world = world; c->rank = rank; c->owned = false;
+    if (world > 1 && nccl().CommCount && nccl().CommUserRank) {
+        int w = 0, r = 0;
+        if (nccl().CommCount(c->comm, &w) != ncclSuccess || nccl().CommUserRank(c->comm, &r) != ncclSuccess || w != world || r != rank) {
+            delete c;
+            return NTTB200_EINVAL;
+        }
+    }
+    *out = c;
+    return 0;
+}
+void nttb200_comm_destroy(nttb200_comm *c)
+{
+    if (!c) return;
+    if (c->owned && c->comm && nccl().ok) nccl().CommDestroy(c->comm);
+    delete c;
+}
+int nttb200_comm_world(const nttb200_comm *c) { return c ? c->world : 0; }
+int nttb200_comm_rank(const nttb200_comm *c) { return c ? c->rank : -1; }
+
+int nttb200_bfv_shard_config(nttb200_bfv *b, int mode, unsigned chunks)
+{
+    if (!b || mode < 0 || mode > 1) return NTTB200_EINVAL;
+    nttb200_shard_state *s;
+    TRY(shard_state(b, &s, 0));
+    s->mode = mode;
+    s->chunks = chunks ? chunks : 1u;
+    return 0;
+}
+
+// reference layout c[batch][2][r][n] (this device) <-> the calling rank's shard (nttb200_shard_plan), device-local copies
+static int shard_copy(nttb200_bfv *b, unsigned world, unsigned rank, nttb200_u64 *c_shard, nttb200_u64 *c_full, unsigned batch, bool to_shard, cudaStream_t st)
+{
+    if (!b || !c_shard || !c_full || !world || rank >= world || !batch || batch % world) return NTTB200_EINVAL;
+    const unsigned n = b->n, r = b->r;
+    std::vector<nttb200_shard_block> blk(world);
+    plan_blocks(r - 1, n, batch, world, rank, blk.data(), nullptr);
+    for (unsigned j = 0; j < world; j++) {
+        const unsigned cnt = blk[j].limb_count;
+        if (!cnt) continue;
+        for (unsigned h = 0; h < 2; h++) {
+            u64 *full = c_full + ((size_t)blk[j].first_item * 2 + h) * r * n + (size_t)blk[j].first_limb * n;
+            u64 *sh = c_shard + blk[j].offset + (size_t)h * cnt * n;
+            const size_t fp = (size_t)2 * r * n * 8, sp = (size_t)2 * cnt * n * 8, w = (size_t)cnt * n * 8;
+            if (to_shard) NTTB200_CHECK(cudaMemcpy2DAsync(sh, sp, full, fp, w, blk[j].items, cudaMemcpyDeviceToDevice, st));
+            else NTTB200_CHECK(cudaMemcpy2DAsync(full, fp, sh, sp, w, blk[j].items, cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    return 0;
+}
+int nttb200_bfv_shard_from_full(nttb200_bfv *b, unsigned world, unsigned rank, nttb200_u64 *c_shard, const nttb200_u64 *c_full, unsigned batch, void *stream)
+{
+    return shard_copy(b, world, rank, c_shard, const_cast<nttb200_u64 *>(c_full), batch, true, (cudaStream_t)stream);
+}
+int nttb200_bfv_shard_to_full(nttb200_bfv *b, unsigned world, unsigned rank, nttb200_u64 *c_full, const nttb200_u64 *c_shard, unsigned batch, void *stream)
+{
+    return shard_copy(b, world, rank, const_cast<nttb200_u64 *>(c_shard), c_full, batch, false, (cudaStream_t)stream);
+}
+
+// ---- building blocks for callers that run their own collectives (and for single-GPU tests with virtual ranks) ------------------------
+// limbs [first_limb, first_limb + limb_count) of `batch` ciphertexts, c_tile[batch][2][limb_count][n] (one tile of nttb200_shard_plan),
+// loaded secret key, fused NTT (.) sk -> INTT kernel.  packed = 1: partial[batch][n + n/4] (gamma sums, then 16-bit t sums; needs
+// (r-1) * (t-1) < 2^16), packed = 0: partial[batch][2][n] as nttb200_bfv_decrypt_partial writes it.  SUM-reduce over the limb windows.
+int nttb200_bfv_decrypt_partial_tile(nttb200_bfv *b, nttb200_u64 *partial, int packed, nttb200_u64 *c_tile, unsigned first_limb, unsigned limb_count,
+                                     unsigned batch, void *stream)
+{
+    if (!b || !partial || !c_tile || !batch || batch > 65535 || !limb_count || first_limb + limb_count > b->r - 1 || !b->sk_l) return NTTB200_EINVAL;
+    if (packed && (u64)(b->r - 1) * (b->t - 1) >= 65536) return NTTB200_EINVAL;
+    Pipe P = pipe_from_bfv(b, (cudaStream_t)stream);
+    return dec_partial(b, P, partial, packed, c_tile, limb_count, first_limb, limb_count, batch);
+}
+// out16 = 1: m_out is unsigned short[batch][n] (t <= 2^16), else nttb200_u64[batch][n]
+int nttb200_bfv_decrypt_finish_tile(nttb200_bfv *b, void *m_out, int out16, const nttb200_u64 *partial_sum, int packed, unsigned batch, void *stream)
+{
+    if (!b || !m_out || !partial_sum || !batch || batch > 65535 || (out16 && b->t > 65536)) return NTTB200_EINVAL;
+    return dec_finish(b, m_out, out16, partial_sum, packed, batch, (cudaStream_t)stream);
+}
+
+// ---- limb-sharded encryption --------------------------------------------------------------------------------------------------------
+// Every rank passes the same m[batch][n] and nonce0; c_shard receives the rank's (limb, block) tiles.  The loaded public key is used.
+int nttb200_bfv_encrypt_sharded(nttb200_bfv *b, nttb200_comm *comm, nttb200_u64 *c_shard, const nttb200_u64 *m, unsigned batch, nttb200_u64 nonce0,
+                                void *stream)
+{
+    if (!b || !comm || !c_shard || !m || !batch || batch % (unsigned)comm->world || !b->pk_l) return NTTB200_EINVAL;
+    if (!b->ctx->lazy_ok || !b->enc_lazy) return NTTB200_EINVAL;          // fused-epilogue path only (every reference parameter set qualifies)
+    const unsigned G = (unsigned)comm->world, g = (unsigned)comm->rank, n = b->n, r = b->r, per = batch / G;
+    if (per > 65535) return NTTB200_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    nttb200_shard_state *s;
+    TRY(shard_state(b, &s, 4));
+    std::vector<nttb200_shard_block> blk(G);
+    plan_blocks(r - 1, n, batch, G, g, blk.data(), nullptr);
+    unsigned char *ub; signed char *es; u64 *cl;
+    TRY(shard_buf(s, kBufUb, (size_t)batch * n, (void **)&ub));
+    TRY(shard_buf(s, kBufEs, (size_t)batch * 2 * n, (void **)&es));
+    TRY(shard_buf(s, kBufCl, (size_t)batch * 2 * n * 8, (void **)&cl));
+    Pipe P = pipe_from_bfv(b, st);
+    const size_t own = (size_t)g * per;
+    // scratch reuse across calls: the previous call's collectives (comm stream) must be done before this call overwrites their buffers
+    NTTB200_CHECK(cudaEventRecord(s->ev[0], s->cs));
+    NTTB200_CHECK(cudaStreamWaitEvent(st, s->ev[0], 0));
+    // 1. randomness: u bytes of every item (every rank transforms u on its limbs), gaussian draws of the block this rank finishes
+    TRY(enc_sample(b, ub, nullptr, batch, nonce0, 1, 0, st));
+    TRY(enc_sample(b, nullptr, es + own * 2 * n, per, nonce0 + own, 0, 1, st));
+    // 2. dropped limb of the own block, finished (+ e, rounding offset)
+    u64 *cl_own = cl + own * 2 * n;
+    TRY(enc_front(b, P, cl_own, 1, r - 1, 1, per, ub + own * n));
+    TRY(enc_finish_last(b, P, cl_own, (size_t)2 * n, (size_t)n, es + own * 2 * n, per));
+    // 3. all-gather of the finished dropped limbs and the draws, on the comm stream, under the transforms of step 4
+    if (G > 1) {
+        NTTB200_CHECK(cudaEventRecord(s->ev[1], st));
+        NTTB200_CHECK(cudaStreamWaitEvent(s->cs, s->ev[1], 0));
+        NCCLCHECK(nccl().GroupStart());
+        NCCLCHECK(nccl().AllGather(cl_own, cl, (size_t)per * 2 * n, ncclUint64, comm->comm, s->cs));
+        NCCLCHECK(nccl().AllGather(es + own * 2 * n, es, (size_t)per * 2 * n, ncclInt8, comm->comm, s->cs));
+        NCCLCHECK(nccl().GroupEnd());
+        NTTB200_CHECK(cudaEventRecord(s->ev[2], s->cs));
+    }
+    // 4. forward transform of u, (.) pk, contiguous inverse pass on the owned (limb, block) tiles
+    for (unsigned j = 0; j < G; j++)
+        if (blk[j].limb_count)
+            TRY(enc_front(b, P, c_shard + blk[j].offset, blk[j].limb_count, blk[j].first_limb, blk[j].limb_count, per, ub + (size_t)blk[j].first_item * n));
+    if (G > 1) NTTB200_CHECK(cudaStreamWaitEvent(st, s->ev[2], 0));
+    // 5. last inverse kernel with mod-switch + Delta*m in its store
+    for (unsigned j = 0; j < G; j++)
+        if (blk[j].limb_count) {
+            const size_t it = blk[j].first_item;
+            TRY(enc_finish_limbs(b, P, c_shard + blk[j].offset, blk[j].limb_count, blk[j].first_limb, blk[j].limb_count, per, cl + it * 2 * n,
+                                 (size_t)2 * n, (size_t)n, es + it * 2 * n, m + it * n, (size_t)n));
+        }
+    return 0;
+}
+
+// ---- limb-sharded decryption --------------------------------------------------------------------------------------------------------
+// c_shard is overwritten (as c1 is in the reference); m_out[batch][n] is complete on EVERY rank when the call's stream work is done.
+int nttb200_bfv_decrypt_sharded(nttb200_bfv *b, nttb200_comm *comm, nttb200_u64 *m_out, nttb200_u64 *c_shard, unsigned batch, void *stream)
+{
+    if (!b || !comm || !c_shard || !m_out || !batch || batch % (unsigned)comm->world || !b->sk_l) return NTTB200_EINVAL;
+    const unsigned G = (unsigned)comm->world, g = (unsigned)comm->rank, n = b->n, r = b->r, rp = r - 1, per = batch / G;
+    if (per > 65535) return NTTB200_EINVAL;
+    if (G > 1 && (~0ull / b->gamma) < G) return NTTB200_EINVAL;          // the 64-bit SUM of G partial sums below gamma must not wrap
+    const bool packed = (u64)rp * (b->t - 1) < 65536, out16 = b->t <= 65536;
+    const size_t pw = packed ? (size_t)n + n / 4 : (size_t)2 * n;        // words per item of partial sums
+    cudaStream_t st = (cudaStream_t)stream;
+    nttb200_shard_state *s;
+    TRY(shard_state(b, &s, 1));
+    std::vector<nttb200_shard_block> blk(G);
+    plan_blocks(rp, n, batch, G, g, blk.data(), nullptr);
+    unsigned chunks = (G > 1 && s->mode == 1) ? s->chunks : 1u;
+    while (chunks > 1 && per % chunks) chunks--;
+    TRY(shard_state(b, &s, (size_t)G + chunks + 4));
+    const unsigned sub = per / chunks;                                   // items of one block in one chunk
+    u64 *partial, *recv; unsigned short *plain;
+    TRY(shard_buf(s, kBufPartial, (size_t)batch * pw * 8, (void **)&partial));
+    TRY(shard_buf(s, kBufRecv, (size_t)per * pw * 8, (void **)&recv));
+    TRY(shard_buf(s, kBufPlain, (size_t)batch * n * 2, (void **)&plain));
+    Pipe P = pipe_from_bfv(b, st);
+    NTTB200_CHECK(cudaEventRecord(s->ev[0], s->cs));                     // scratch reuse across calls (see encrypt)
+    NTTB200_CHECK(cudaStreamWaitEvent(st, s->ev[0], 0));
+    size_t evi = 1;
+    const bool scatter = G > 1 && s->mode == 1;
+    // partial layout: mode 0 -> [block][item][pw]; mode 1 -> [chunk][block][sub items][pw] (what ncclReduceScatter wants)
+    for (unsigned c = 0; c < chunks; c++) {
+        for (unsigned j = 0; j < G; j++) {
+            const unsigned cnt = blk[j].limb_count;
+            u64 *pj = partial + ((size_t)c * G + j) * sub * pw;
+            if (cnt) TRY(dec_partial(b, P, pj, packed, c_shard + blk[j].offset + (size_t)c * sub * 2 * cnt * n, cnt, blk[j].first_limb, cnt, sub));
+            else NTTB200_CHECK(cudaMemsetAsync(pj, 0, (size_t)sub * pw * 8, st));
+            if (G > 1 && !scatter) {       // this block's sums -> its owner, while the next block's transforms run
+                NTTB200_CHECK(cudaEventRecord(s->ev[evi], st));
+                NTTB200_CHECK(cudaStreamWaitEvent(s->cs, s->ev[evi], 0));
+                evi++;
+                NCCLCHECK(nccl().Reduce(pj, recv, (size_t)sub * pw, ncclUint64, ncclSum, (int)j, comm->comm, s->cs));
+            }
+        }
+        if (scatter) {
+            NTTB200_CHECK(cudaEventRecord(s->ev[evi], st));
+            NTTB200_CHECK(cudaStreamWaitEvent(s->cs, s->ev[evi], 0));
+            evi++;
+            NCCLCHECK(nccl().ReduceScatter(partial + (size_t)c * G * sub * pw, recv + (size_t)c * sub * pw, (size_t)sub * pw, ncclUint64, ncclSum,
+                                           comm->comm, s->cs));
+        }
+    }
+    if (G == 1) {
+        TRY(dec_finish(b, m_out, 0, partial, packed, batch, st));
+        return 0;
+    }
+    // owner: rounding of the own block on the comm stream (after its reduce), then the path's final gather
+    const size_t own = (size_t)g * per;
+    if (out16) {
+        TRY(dec_finish(b, plain + own * n, 1, recv, packed, per, s->cs));
+        NCCLCHECK(nccl().AllGather(plain + own * n, plain, (size_t)per * n * 2, ncclInt8, comm->comm, s->cs));
+        TRY(dec_expand16(plain, m_out, (size_t)batch * n, s->cs));
+    } else {
+        TRY(dec_finish(b, m_out + own * n, 0, recv, packed, per, s->cs));
+        NCCLCHECK(nccl().AllGather(m_out + own * n, m_out, (size_t)per * n, ncclUint64, comm->comm, s->cs));
+    }
+    NTTB200_CHECK(cudaEventRecord(s->ev[evi], s->cs));
+    NTTB200_CHECK(cudaStreamWaitEvent(st, s->ev[evi], 0));
+    return 0;
+}
+
+}  // extern "C"

@@ -329,6 +329,31 @@ class Bfv:
     def unpack(self, c, packed, batch=1, stream=None):
         check(lib().nttb200_bfv_unpack(self._h, vp(ptr(c)), vp(ptr(packed)), C.c_uint(batch), vp(_stream(stream))))
 
+    def key_packed_words(self, polys) -> int:
+        lib().nttb200_bfv_key_packed_words.restype = C.c_size_t
+        return int(lib().nttb200_bfv_key_packed_words(self._h, C.c_uint(polys)))
+
+    def pack_key(self, packed, key, polys, batch=1, stream=None):
+        """sk[batch][r][n] (polys = r) / pk[batch][2][r][n] (polys = 2r) -> bit-packed words, all r limbs."""
+        check(lib().nttb200_bfv_pack_key(self._h, vp(ptr(packed)), vp(ptr(key)), C.c_uint(polys), C.c_uint(batch), vp(_stream(stream))))
+
+    def unpack_key(self, key, packed, polys, batch=1, stream=None):
+        check(lib().nttb200_bfv_unpack_key(self._h, vp(ptr(key)), vp(ptr(packed)), C.c_uint(polys), C.c_uint(batch), vp(_stream(stream))))
+
+    def pack_host(self, packed_host, c, batch=1, stream=None):
+        """device ciphertexts -> packed numpy / pinned host buffer (synchronous)"""
+        check(lib().nttb200_bfv_pack_host(self._h, vp(ptr(packed_host)), vp(ptr(c)), C.c_uint(batch), vp(_stream(stream))))
+
+    def unpack_host(self, c, packed_host, batch=1, stream=None):
+        check(lib().nttb200_bfv_unpack_host(self._h, vp(ptr(c)), vp(ptr(packed_host)), C.c_uint(batch), vp(_stream(stream))))
+
+    def encrypt_host(self, c_host, m_host, batch, nonce0=0, packed=True):
+        """m_host[batch][n] -> ciphertexts in host memory (wire format when packed); loaded public key; synchronous."""
+        check(lib().nttb200_bfv_encrypt_host(self._h, vp(ptr(c_host)), C.c_int(int(packed)), vp(ptr(m_host)), C.c_uint(batch), u64(nonce0)))
+
+    def decrypt_host(self, m_host, c_host, batch, packed=True):
+        check(lib().nttb200_bfv_decrypt_host(self._h, vp(ptr(m_host)), vp(ptr(c_host)), C.c_int(int(packed)), C.c_uint(batch)))
+
     def add(self, c_a, c_b, batch=1, stream=None):
         """c_a <- c_a + c_b (homomorphic addition: Dec = m_a + m_b mod t)."""
         check(lib().nttb200_bfv_add(self._h, vp(ptr(c_a)), vp(ptr(c_b)), C.c_uint(batch), vp(_stream(stream))))
@@ -353,6 +378,108 @@ class Bfv:
 
     def decrypt_finish(self, m_out, partial_sum, batch=1, stream=None):
         check(lib().nttb200_bfv_decrypt_finish(self._h, vp(ptr(m_out)), vp(ptr(partial_sum)), C.c_uint(batch), vp(_stream(stream))))
+
+    # ---- round 2: sampling key, fused-epilogue knob, limb-sharded calls with the collectives inside the library -------------------
+    def set_sampling_key(self, key: bytes):
+        """32-byte Salsa20 key of keygen / encrypt (default: the reference's 32 x 0x01 -- parity tests only)."""
+        assert len(key) == 32
+        check(lib().nttb200_bfv_set_sampling_key(self._h, (C.c_ubyte * 32).from_buffer_copy(key)))
+
+    def set_fused_epilogue(self, enable: bool):
+        check(lib().nttb200_bfv_set_fused_epilogue(self._h, C.c_int(int(enable))))
+
+    def shard_config(self, mode=0, chunks=4):
+        check(lib().nttb200_bfv_shard_config(self._h, C.c_int(mode), C.c_uint(chunks)))
+
+    def shard_words(self, comm, batch):
+        return shard_plan(self.r - 1, self.n, batch, comm.world, comm.rank)[1]
+
+    def encrypt_sharded(self, comm, c_shard, m, batch, nonce0=0, stream=None):
+        """Limb-sharded encryption_rns over comm's ranks (loaded public key); c_shard: this rank's tiles (shard_plan)."""
+        check(lib().nttb200_bfv_encrypt_sharded(self._h, comm._h, vp(ptr(c_shard)), vp(ptr(m)), C.c_uint(batch), u64(nonce0), vp(_stream(stream))))
+
+    def decrypt_sharded(self, comm, m_out, c_shard, batch, stream=None):
+        """Limb-sharded decryption_rns (loaded secret key); m_out[batch][n] complete on every rank; c_shard is consumed."""
+        check(lib().nttb200_bfv_decrypt_sharded(self._h, comm._h, vp(ptr(m_out)), vp(ptr(c_shard)), C.c_uint(batch), vp(_stream(stream))))
+
+    def shard_from_full(self, world, rank, c_shard, c_full, batch, stream=None):
+        check(lib().nttb200_bfv_shard_from_full(self._h, C.c_uint(world), C.c_uint(rank), vp(ptr(c_shard)), vp(ptr(c_full)), C.c_uint(batch),
+                                                vp(_stream(stream))))
+
+    def shard_to_full(self, world, rank, c_full, c_shard, batch, stream=None):
+        check(lib().nttb200_bfv_shard_to_full(self._h, C.c_uint(world), C.c_uint(rank), vp(ptr(c_full)), vp(ptr(c_shard)), C.c_uint(batch),
+                                              vp(_stream(stream))))
+
+    def decrypt_partial_tile(self, partial, packed, c_tile, first_limb, limb_count, batch=1, stream=None):
+        check(lib().nttb200_bfv_decrypt_partial_tile(self._h, vp(ptr(partial)), C.c_int(int(packed)), vp(ptr(c_tile)), C.c_uint(first_limb),
+                                                     C.c_uint(limb_count), C.c_uint(batch), vp(_stream(stream))))
+
+    def decrypt_finish_tile(self, m_out, out16, partial_sum, packed, batch=1, stream=None):
+        check(lib().nttb200_bfv_decrypt_finish_tile(self._h, vp(ptr(m_out)), C.c_int(int(out16)), vp(ptr(partial_sum)), C.c_int(int(packed)),
+                                                    C.c_uint(batch), vp(_stream(stream))))
+
+
+class ShardBlock(C.Structure):
+    """nttb200_shard_block (include/nttb200.h)"""
+    _fields_ = [("first_item", C.c_uint), ("items", C.c_uint), ("first_limb", C.c_uint), ("limb_count", C.c_uint), ("offset", C.c_size_t)]
+
+
+def shard_plan(rp: int, n: int, batch: int, world: int, rank: int):
+    """The calling rank's tiles: [(first_item, items, first_limb, limb_count, offset)] * world and the size of its shard buffer in words.
+    Host-only (works without a GPU)."""
+    blocks = (ShardBlock * world)()
+    words = C.c_size_t(0)
+    check(lib().nttb200_shard_plan(C.c_uint(rp), C.c_uint(n), C.c_uint(batch), C.c_uint(world), C.c_uint(rank), blocks, C.byref(words)))
+    return [(b.first_item, b.items, b.first_limb, b.limb_count, b.offset) for b in blocks], int(words.value)
+
+
+class Comm:
+    """Communicator of the sharded BFV calls.  Comm.from_torch() adopts the NCCL communicator of the default torch.distributed
+    process group (one process per GPU); Comm.single() is world size 1 (no NCCL).  A C++ host uses nttb200_comm_unique_id /
+    nttb200_comm_create instead."""
+
+    def __init__(self, handle, world, rank):
+        self._h, self.world, self.rank = handle, world, rank
+
+    @classmethod
+    def single(cls):
+        h = vp()
+        check(lib().nttb200_comm_adopt(C.byref(h), vp(0), C.c_int(1), C.c_int(0)))
+        return cls(h, 1, 0)
+
+    @classmethod
+    def from_torch(cls, group=None):
+        import torch
+        import torch.distributed as dist
+        if not dist.is_initialized() or dist.get_world_size(group) == 1:
+            return cls.single()
+        pg = group if group is not None else dist.distributed_c10d._get_default_group()
+        backend = pg._get_backend(torch.device("cuda"))
+        # the communicator is created lazily by the first collective
+        t = torch.zeros(1, device="cuda")
+        dist.all_reduce(t, group=group)
+        torch.cuda.synchronize()
+        ptr_ = int(backend._comm_ptr())
+        h = vp()
+        check(lib().nttb200_comm_adopt(C.byref(h), vp(ptr_), C.c_int(dist.get_world_size(group)), C.c_int(dist.get_rank(group))))
+        return cls(h, dist.get_world_size(group), dist.get_rank(group))
+
+    @classmethod
+    def create(cls, world, rank, broadcast_bytes):
+        """Own NCCL communicator: rank 0 draws the unique id, `broadcast_bytes(bytes_or_None) -> bytes` ships it."""
+        buf = (C.c_ubyte * 128)()
+        if rank == 0:
+            check(lib().nttb200_comm_unique_id(buf))
+        raw = broadcast_bytes(bytes(buf) if rank == 0 else None)
+        idb = (C.c_ubyte * 128).from_buffer_copy(raw)
+        h = vp()
+        check(lib().nttb200_comm_create(C.byref(h), idb, C.c_int(world), C.c_int(rank)))
+        return cls(h, world, rank)
+
+    def close(self):
+        if self._h:
+            lib().nttb200_comm_destroy(self._h)
+            self._h = vp()
 
 
 def keygen_rns(inp, q_amount, n, secret_key, public_key, temp, psi_table, psiinv_table, q_cons, mu_cons, q_bit_cons, stream=None):

@@ -6,6 +6,7 @@
 //   ref_dump ntt   <set> <num> <outdir>     forwardNTT_batch / inverseNTT_batch on `num` seeded polynomials
 //   ref_dump bfv   <set> <outdir>           keygen_rns -> encryption_rns -> decryption_rns, every buffer dumped
 //   ref_dump bench <set> <num> <iters>      CUDA-event timings (JSON on stdout)
+//   ref_dump c1    <iters>                  single-polynomial latency, N = 4096, 58-bit prime (BASELINE config 1)
 //
 // Inputs are generated here with the same splitmix64 recipe as oracle/ntt_oracle.c:orc_fill_uniform, so no input files
 // are needed.  Twiddle tables are produced by walking the exponents (identical values to fillTablePsi128, which the
@@ -144,6 +145,47 @@ int main(int argc, char **argv)
 {
     if (argc < 3) { fprintf(stderr, "usage: see source header\n"); return 2; }
     std::string mode = argv[1], setname = argv[2];
+    if (mode == "c1") {
+        // BASELINE config 1: ONE polynomial, N = 4096, the 58-bit prime of parameter.h:43-47 -- latency of the reference's single
+        // forwardNTT / inverseNTT calls (ntt_60bit.cuh:314, :350), CUDA events over a back-to-back loop after warm-up, plus the
+        // forwardNTT -> barrett -> inverseNTT flow of 60bit_ntt_test.cu:70-80.
+        const unsigned n = 4096; const int iters = atoi(argv[2]) > 0 ? atoi(argv[2]) : 200;
+        const u64 q = 288230376135196673ull, psi = 60193018759093ull, psiinv = 236271020333049746ull;
+        const int qbit = 58;
+        const u64 mu = (uint128_t::exp2(2 * qbit) / q).low;
+        vector<u64> t(n), ti(n), a(n);
+        fast_tables(psi, q, psiinv, t.data(), ti.data(), n);
+        fill_uniform(a.data(), n, q, 0xC1);
+        u64 *d, *d2, *td, *tid;
+        cudaMalloc(&d, 8 * n); cudaMalloc(&d2, 8 * n); cudaMalloc(&td, 8 * n); cudaMalloc(&tid, 8 * n);
+        cudaMemcpy(d, a.data(), 8 * n, cudaMemcpyHostToDevice); cudaMemcpy(d2, a.data(), 8 * n, cudaMemcpyHostToDevice);
+        cudaMemcpy(td, t.data(), 8 * n, cudaMemcpyHostToDevice); cudaMemcpy(tid, ti.data(), 8 * n, cudaMemcpyHostToDevice);
+        cudaStream_t s1, s2; cudaStreamCreate(&s1); cudaStreamCreate(&s2);
+        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+        float f_ms, i_ms, mul_ms;
+        for (int i = 0; i < 10; i++) { forwardNTT(d, n, s1, q, mu, qbit, td); inverseNTT(d, n, s1, q, mu, qbit, tid); }
+        cudaDeviceSynchronize();
+        cudaEventRecord(e0, s1); for (int i = 0; i < iters; i++) forwardNTT(d, n, s1, q, mu, qbit, td); cudaEventRecord(e1, s1);
+        cudaEventSynchronize(e1); cudaEventElapsedTime(&f_ms, e0, e1);
+        cudaEventRecord(e0, s1); for (int i = 0; i < iters; i++) inverseNTT(d, n, s1, q, mu, qbit, tid); cudaEventRecord(e1, s1);
+        cudaEventSynchronize(e1); cudaEventElapsedTime(&i_ms, e0, e1);
+        cudaDeviceSynchronize();
+        cudaEventRecord(e0, s1);
+        for (int i = 0; i < iters; i++) {
+            forwardNTT(d, n, s1, q, mu, qbit, td); forwardNTT(d2, n, s1, q, mu, qbit, td);
+            barrett<<<n / 256, 256, 0, s1>>>(d, d2, q, mu, qbit);
+            inverseNTT(d, n, s1, q, mu, qbit, tid);
+        }
+        cudaEventRecord(e1, s1); cudaEventSynchronize(e1); cudaEventElapsedTime(&mul_ms, e0, e1);
+        vector<u64> back(n);
+        cudaMemcpy(d, a.data(), 8 * n, cudaMemcpyHostToDevice);
+        forwardNTT(d, n, s1, q, mu, qbit, td); inverseNTT(d, n, s1, q, mu, qbit, tid);
+        cudaDeviceSynchronize();
+        cudaMemcpy(back.data(), d, 8 * n, cudaMemcpyDeviceToHost);
+        printf("{\"c1\": true, \"n\": %u, \"iters\": %d, \"fwd_us\": %.3f, \"inv_us\": %.3f, \"polymul_us\": %.3f, \"roundtrip_ok\": %s, \"err\": \"%s\"}\n",
+               n, iters, 1e3 * f_ms / iters, 1e3 * i_ms / iters, 1e3 * mul_ms / iters, back == a ? "true" : "false", cudaGetErrorString(cudaGetLastError()));
+        return 0;
+    }
     const Set *S = nullptr;
     static vector<Set> all = sets();
     for (auto &s : all) if (setname == s.name) S = &s;

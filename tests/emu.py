@@ -183,3 +183,82 @@ class EmuBfv:
 
     def decrypt_finish(self, m_out, partial_sum, batch=1):
         self._call(1, None, None, partial_sum, m_out, batch, 0, 0)
+
+
+# ---- building blocks of the fused-epilogue encryption / fused sharded decryption (mirror csrc/bfv.cu enc_* / dec_*) --------------------
+def enc_epi_limbs(R):
+    """EncEpiLimb[r-1] exactly as nttb200_bfv_create builds it (csrc/bfv.cu)."""
+    r = R.r
+    qs = [int(x) for x in R.q]
+    out = np.zeros((r - 1, 8), dtype=np.uint64)
+    for i in range(r - 1):
+        q, iql = qs[i], int(R.inv_q_last_mod_q[i])
+        out[i] = [q, 2 * q, iql, (iql << 64) // q, int(R.qi_div_t[i]), (qs[r - 1] >> 1) % q + 3 * q, ((1 << 64) - 1) // q, 0]
+    assert lib().emu_sizeof_encepilimb() == 64
+    return out
+
+
+class EmuBlocks:
+    """enc_sample / enc_front / enc_finish_last / enc_finish_limbs / dec_partial / dec_finish / dec_expand16 on the emulator, with a key
+    pair loaded (companions built here, as nttb200_bfv_load_keys does)."""
+
+    def __init__(self, er: EmuRing, sk=None, pk=None):
+        self.er, self.R = er, er.ring
+        R = self.R
+        self.n, self.r = R.n, R.r
+        qs = [int(x) for x in R.q]
+        self.K = enc_epi_limbs(R)
+        self.tsh = int(R.t).bit_length() - 1
+        self.sk = self.sk_s = self.pk = self.pk_s = None
+        if sk is not None:
+            self.sk = np.ascontiguousarray(sk, dtype=np.uint64)
+            self.sk_s = np.concatenate([shoup(self.sk[l * R.n:(l + 1) * R.n], qs[l]) for l in range(R.r)])
+        if pk is not None:
+            self.pk = np.ascontiguousarray(pk, dtype=np.uint64)
+            self.pk_s = np.concatenate([shoup(self.pk[i * R.n:(i + 1) * R.n], qs[i % R.r]) for i in range(2 * R.r)])
+
+    def _ring(self):
+        R, er, u = self.R, self.er, C.c_ulonglong
+        return (R.n, R.r, p(R.qa, u), p(R.mu, u), p(R.qbit, C.c_uint), p(er.psi, u), p(er.psiinv, u), p(er.psi_s, u), p(er.psiinv_s, u),
+                er.lc.ctypes.data_as(C.c_void_p))
+
+    def _enc(self, op, first=0, count=0, slots=0, items=0, c=None, ub=None, es8=None, cl=None, cl_is=0, cl_hs=0, m=None, nonce0=0, i0=0, i1=0):
+        u = C.c_ulonglong
+        z = np.zeros(1, dtype=np.uint64)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None   # noqa: E731
+        rc = lib().emu_enc_blocks(op, *self._ring(), first, count, slots, items, vp(c), vp(ub), vp(es8),
+                                  p(self.pk if self.pk is not None else z, u), p(self.pk_s if self.pk_s is not None else z, u), vp(cl),
+                                  C.c_size_t(cl_is), C.c_size_t(cl_hs), vp(m), self.K.ctypes.data_as(C.c_void_p), u(self.R.t), self.tsh,
+                                  u(nonce0), i0, i1)
+        assert rc == 0, rc
+
+    def enc_sample(self, ub, es8, items, nonce0, want_u, want_e):
+        self._enc(0, items=items, ub=ub, es8=es8, nonce0=nonce0, i0=int(want_u), i1=int(want_e))
+
+    def enc_front(self, c, slots, first, count, items, ub):
+        self._enc(1, first, count, slots, items, c=c, ub=ub)
+
+    def enc_finish_last(self, cl, cl_is, cl_hs, es8, items):
+        self._enc(2, items=items, cl=cl, cl_is=cl_is, cl_hs=cl_hs, es8=es8)
+
+    def enc_finish_limbs(self, c, slots, first, count, items, cl, cl_is, cl_hs, es8, m):
+        self._enc(3, first, count, slots, items, c=c, cl=cl, cl_is=cl_is, cl_hs=cl_hs, es8=es8, m=m)
+
+    def _dec(self, op, first=0, count=0, slots=0, items=0, c=None, part=None, out=None, packed=0, out16=0):
+        R, u = self.R, C.c_ulonglong
+        z = np.zeros(1, dtype=np.uint64)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None   # noqa: E731
+        rc = lib().emu_dec_blocks(op, *self._ring(), first, count, slots, items, vp(c), p(self.sk if self.sk is not None else z, u),
+                                  p(self.sk_s if self.sk_s is not None else z, u), vp(part), vp(out), int(packed), int(out16),
+                                  p(R.prod_t_gamma_mod_q, u), p(R.inv_punctured_q, u), p(R.bcm, u), u(R.t), u(R.gamma), u(R.mu_gamma),
+                                  int(R.gamma_bits), u(int(R.neg_inv[0])), u(int(R.neg_inv[1])))
+        assert rc == 0, rc
+
+    def dec_partial(self, part, packed, c_shard, slots, first, count, items):
+        self._dec(0, first, count, slots, items, c=c_shard, part=part, packed=packed)
+
+    def dec_finish(self, out, out16, part, packed, items):
+        self._dec(1, items=items, part=part, out=out, packed=packed, out16=out16)
+
+    def dec_expand16(self, plain16, out, items):
+        self._dec(2, items=items, part=plain16, out=out)
