@@ -238,9 +238,9 @@ def bfv_throughput(nttb200, params, torch, T, world, batch=64, reps=5):
 
     dec_l = T.ms(dec_loaded, reps) - copy_ms
     ok = ok and same and bool(torch.equal(out, m))
+    bfv.set_fused_epilogue(True)              # A/B: epilogue fused into the store of the last inverse kernel (slower: DESIGN.md 3.4)
+    enc_l_fus = T.ms(lambda: bfv.encrypt(c, None, m, batch=batch), reps)
     bfv.set_fused_epilogue(False)
-    enc_l_sep = T.ms(lambda: bfv.encrypt(c, None, m, batch=batch), reps)
-    bfv.set_fused_epilogue(True)
     # end to end through host buffers: m (pinned) -> H2D -> encrypt -> pack -> D2H ciphertexts; ciphertexts -> H2D -> unpack -> decrypt -> D2H m
     pw = bfv.packed_words()
     mh = torch.empty(batch * n, dtype=torch.int64).pin_memory()
@@ -268,8 +268,8 @@ def bfv_throughput(nttb200, params, torch, T, world, batch=64, reps=5):
     return {"workload": "BFV encrypt + decrypt, n=32768, 16-limb q (demo.cu), t=1024, batch %d per GPU" % batch,
             "loaded_keys": {"enc_plus_dec_per_s": world * batch / ((enc_l + dec_l) * 1e-3), "encrypt_per_s": world * batch / (enc_l * 1e-3),
                             "decrypt_per_s": world * batch / (dec_l * 1e-3),
-                            "encrypt_per_s_separate_epilogue": world * batch / (enc_l_sep * 1e-3),
-                            "api": "nttb200_bfv_load_keys + encrypt / decrypt with NULL key (5 / 4 launches)"},
+                            "encrypt_per_s_epilogue_in_ntt_store": world * batch / (enc_l_fus * 1e-3),
+                            "api": "nttb200_bfv_load_keys + encrypt / decrypt with NULL key (7 / 4 launches)"},
             "enc_plus_dec_per_s": world * batch / ((enc + dec_ms) * 1e-3), "encrypt_per_s": world * batch / (enc * 1e-3),
             "decrypt_per_s": world * batch / (dec_ms * 1e-3), "unit": "ops/s", "roundtrip_ok": ok,
             "e2e": {"value": world * batch / e2e_s, "unit": "enc+dec ops/s", "h2d_bytes_per_step": batch * (n * 8 + pw * 8),

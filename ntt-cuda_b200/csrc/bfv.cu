@@ -141,8 +141,10 @@ static int run_encrypt_epilogue(const Pipe &P, u64 *c, const int *es, const u64 
     const unsigned n = P.n, r = P.r;
     if (r > 1) {
         const unsigned rows = 2 * ((r - 1 + kEncChunk - 1) / kEncChunk);
-        if (P.enc_lazy) k_encrypt_epilogue<true><<<pair_grid(n, rows, batch), pair_block(n, rows, batch), 0, P.st>>>(c, es, m, m_stride, n, r, batch, t, P.qi_div_t, P.L);
-        else k_encrypt_epilogue<false><<<pair_grid(n, rows, batch), pair_block(n, rows, batch), 0, P.st>>>(c, es, m, m_stride, n, r, batch, t, P.qi_div_t, P.L);
+        const size_t rn = (size_t)r * n;
+        const u64 *cl = c + (size_t)(r - 1) * n;      // the padding slot still holds the RAW inverse-transform output here
+        if (P.enc_lazy) k_encrypt_epilogue<true, int, false><<<pair_grid(n, rows, batch), pair_block(n, rows, batch), 0, P.st>>>(c, 2 * rn, rn, es, m, m_stride, n, r, 0, r - 1, cl, 2 * rn, rn, t, P.qi_div_t, P.L);
+        else k_encrypt_epilogue<false, int, false><<<pair_grid(n, rows, batch), pair_block(n, rows, batch), 0, P.st>>>(c, 2 * rn, rn, es, m, m_stride, n, r, 0, r - 1, cl, 2 * rn, rn, t, P.qi_div_t, P.L);
     }
     k_encrypt_last_limb<<<pair_grid(n, 2, batch), pair_block(n, 2, batch), 0, P.st>>>(c, es, n, r, batch, P.L);
     KCHECK();
@@ -315,10 +317,24 @@ int enc_finish_limbs(const nttb200_bfv *b, const Pipe &P0, u64 *c, unsigned slot
                      size_t cl_item_stride, size_t cl_half_stride, const signed char *es8, const u64 *m, size_t m_stride)
 {
     Pipe P = pipe_limb_window(P0, b->ctx, first);
-    EpiArgs E = epi_args(b, es8);
-    E.cl = cl; E.cl_item_stride = cl_item_stride; E.cl_half_stride = cl_half_stride;
-    E.m = m; E.m_stride = m_stride; E.first_limb = first;
-    return launch_strided_inv_epi(P.logn, pipe_args(P, true, c, items * 2 * count, count, count, (size_t)slots * P.n), kEpiEncLimb, E, P.st);
+    const unsigned n = P.n;
+    if (!b->no_fused_epilogue) {          // A/B variant: mod-switch + Delta*m in the store of the last inverse kernel
+        EpiArgs E = epi_args(b, es8);
+        E.cl = cl; E.cl_item_stride = cl_item_stride; E.cl_half_stride = cl_half_stride;
+        E.m = m; E.m_stride = m_stride; E.first_limb = first;
+        return launch_strided_inv_epi(P.logn, pipe_args(P, true, c, items * 2 * count, count, count, (size_t)slots * n), kEpiEncLimb, E, P.st);
+    }
+    // default: plain strided inverse pass, then the HBM-bound epilogue pass (its arithmetic hides under its memory time, whereas inside
+    // the issue-bound NTT kernel the same arithmetic costs more than the pass it saves: profiles/r02_experiments.md)
+    NTTB200_TRY(launch_ntt_pass(true, P.policy_inv, P.logn, pipe_args(P, true, c, items * 2 * count, count, count, (size_t)slots * n), 1, P.st));
+    const unsigned rows = 2 * ((count + kEncChunk - 1) / kEncChunk);
+    const dim3 g = pair_grid(n, rows, items);
+    const unsigned tb = pair_block(n, rows, items);
+    const size_t item = (size_t)2 * slots * n, half = (size_t)slots * n;
+    if (b->enc_lazy) k_encrypt_epilogue<true, signed char, true><<<g, tb, 0, P.st>>>(c, item, half, es8, m, m_stride, n, b->r, first, count, cl, cl_item_stride, cl_half_stride, b->t, b->qi_div_t, P0.L);
+    else k_encrypt_epilogue<false, signed char, true><<<g, tb, 0, P.st>>>(c, item, half, es8, m, m_stride, n, b->r, first, count, cl, cl_item_stride, cl_half_stride, b->t, b->qi_div_t, P0.L);
+    KCHECK();
+    return 0;
 }
 int dec_partial(const nttb200_bfv *b, const Pipe &P0, u64 *partial, int packed, u64 *c_shard, unsigned slots, unsigned first, unsigned count,
                 unsigned items)
@@ -433,12 +449,13 @@ int nttb200_bfv_create(nttb200_bfv **out, unsigned n, unsigned limbs, const nttb
         return 0;
     };
     // epilogue flavours (bfv_kernels.cuh): the same predicates the kernels evaluate per limb, checked here for ALL limbs
-    b->enc_lazy = true; b->dec_fast = barrett_is_exact(gamma, b->mu_gamma, b->gamma_bits);
+    b->enc_lazy = true; b->epi_ok = true; b->dec_fast = barrett_is_exact(gamma, b->mu_gamma, b->gamma_bits);
     b->all_exact = true;
     for (unsigned i = 0; i < r; i++) b->all_exact = b->all_exact && barrett_is_exact(q[i], ctx->mu[i], (int)ctx->qbit[i]);
     for (unsigned i = 0; i < rp; i++) {
         const bool exact = barrett_is_exact(q[i], ctx->mu[i], (int)ctx->qbit[i]);
         b->enc_lazy = b->enc_lazy && exact && iql[i] < q[i] && q[r - 1] <= 2 * q[i] && q[i] < (1ull << 60);
+        b->epi_ok = b->epi_ok && exact && iql[i] < q[i] && q[i] < (1ull << 60);       // the fused epilogue reduces c_last itself when q_last > 2 q_i
         b->dec_fast = b->dec_fast && exact && ptg[i] < q[i] && ipq[i] < q[i] && bcm[rp + i] < gamma;
     }
     {   // wire format offsets (bfv_kernels.cuh: k_ct_pack)
@@ -465,7 +482,7 @@ int nttb200_bfv_create(nttb200_bfv **out, unsigned n, unsigned limbs, const nttb
         for (unsigned i = 0; i < rp; i++) {
             EncEpiLimb &e = ek[i];
             e.q = q[i]; e.twoq = 2 * q[i]; e.inv_q_last = iql[i]; e.inv_q_last_s = shoup_companion(iql[i], q[i]);
-            e.qdt = qdt[i]; e.bias = (q[r - 1] >> 1) % q[i] + 3 * q[i]; e.ratio = ratio_of(q[i]); e.pad = 0;
+            e.qdt = qdt[i]; e.bias = (q[r - 1] >> 1) % q[i] + 3 * q[i]; e.ratio = ratio_of(q[i]); e.reduce_cl = q[r - 1] > 2 * q[i];
         }
         if (cudaMalloc(&b->enc_epi, rp * sizeof(EncEpiLimb)) != cudaSuccess ||
             cudaMemcpy(b->enc_epi, ek.data(), rp * sizeof(EncEpiLimb), cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -555,11 +572,11 @@ int nttb200_bfv_encrypt(nttb200_bfv *b, nttb200_u64 *c, const nttb200_u64 *pk, i
                         nttb200_u64 nonce0, void *stream)
 {
     if (!b || !c || !m || !batch || batch > 65535 || (!pk && !b->pk_l)) return NTTB200_EINVAL;
-    const bool v2 = !pk && b->ctx->lazy_ok && b->enc_lazy && !b->no_fused_epilogue;
+    const bool v2 = !pk && b->ctx->lazy_ok && b->epi_ok && !b->no_fused_epilogue;
     if (!v2) NTTB200_TRY(ensure_scratch(b, 9 * (size_t)b->n * batch, (size_t)2 * b->n * batch));      // encryption draws 9n bytes per item
     const size_t rn = (size_t)b->r * b->n;
     Pipe P = pipe_from_bfv(b, (cudaStream_t)stream);
-    if (!pk && b->ctx->lazy_ok && b->enc_lazy && !b->no_fused_epilogue) return run_encrypt_v2(b, P, c, m, batch, nonce0);
+    if (!pk && b->ctx->lazy_ok && b->epi_ok && !b->no_fused_epilogue) return run_encrypt_v2(b, P, c, m, batch, nonce0);
     if (!pk) return run_encrypt_fused(P, b->ctx->lazy_ok != 0, b->ks, 9 * (size_t)b->n, b->es, c, b->pk_l, b->pk_ls, m, b->n, b->t, batch, nonce0);
     return run_encrypt(P, b->ks, 9 * (size_t)b->n, b->es, c, pk, pk_per_item ? 2 * rn : 0, m, b->n, b->t, batch, nonce0);
 }

@@ -29,7 +29,8 @@ struct nttb200_bfv {
     unsigned *key_word_off = nullptr; unsigned key_half_words = 0;   // same for keys (all r limbs)
     struct nttb200_host_state *host = nullptr;        // staging + streams of the host-buffer entry points (bfv_host.cu)
     bool enc_lazy = false, dec_fast = false, all_exact = false;
-    bool no_fused_epilogue = false;                   // debugging / A-B knob: keep the separate epilogue kernels
+    bool epi_ok = false;                              // every limb qualifies for the epilogue fused into the last inverse kernel
+    bool no_fused_epilogue = true;                    // default: separate (HBM-bound) epilogue kernels; false = epilogue in the last inverse kernel's store (A/B, slower)
 };
 void nttb200_shard_state_destroy(struct nttb200_shard_state *s);
 void nttb200_host_state_destroy(struct nttb200_host_state *s);

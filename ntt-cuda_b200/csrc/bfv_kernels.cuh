@@ -335,18 +335,22 @@ __host__ __device__ __forceinline__ u64 enc_last_limb(u64 v, int d, u64 last, u6
 // which is therefore left untouched here and finalised by k_encrypt_last_limb afterwards.
 // ALL_LAZY (decided on the host for context-owned parameter sets): every limb takes the lazy path, the literal reference
 // sequence is compiled out and the kernel fits four 256-thread CTAs per SM -- the pass is bound by loads in flight.
-template <bool ALL_LAZY>
+// Generalised for limb windows (sharded runs): the launch covers `cnt` limbs, local limb l = global limb first + l, stored at
+// c[item][half][l][n] with the given strides; the dropped limb's values come from clp[item][half][n] -- RAW inverse-transform outputs
+// (CL_FINISHED = false: `+ e` and the rounding offset are applied here, as the single-GPU path does on the padding slot) or the
+// finished values an earlier launch left there (CL_FINISHED = true).  ES: int (reference-style scratch) or signed char draws.
+template <bool ALL_LAZY, class ES, bool CL_FINISHED>
 NTT_KERNEL void __launch_bounds__(256, ALL_LAZY ? 4 : 2)
-k_encrypt_epilogue(u64 *c, const int *es, const u64 *m_poly, size_t m_stride, unsigned n, unsigned r, unsigned batch, u64 t,
-                   const u64 *qi_div_t, LimbArrays L)
+k_encrypt_epilogue(u64 *c, size_t item_stride, size_t half_stride, const ES *es, const u64 *m_poly, size_t m_stride, unsigned n, unsigned r,
+                   unsigned first, unsigned cnt, const u64 *clp, size_t cl_item_stride, size_t cl_half_stride, u64 t, const u64 *qi_div_t,
+                   LimbArrays L)
 {
-    (void)batch;
     NTT_SHARED EncLimb K[kEncChunk];
     const u64 last = L.q[r - 1], half_last = last >> 1;
-    const unsigned chunks = (r - 1 + kEncChunk - 1) / kEncChunk;
+    const unsigned chunks = (cnt + kEncChunk - 1) / kEncChunk;
     const unsigned h = blockIdx.y / chunks, l0 = (blockIdx.y % chunks) * kEncChunk;
-    if (threadIdx.x < kEncChunk && l0 + threadIdx.x + 1 < r) {
-        const unsigned l = l0 + threadIdx.x;
+    if (threadIdx.x < kEncChunk && l0 + threadIdx.x < cnt) {
+        const unsigned l = first + l0 + threadIdx.x;
         EncLimb e;
         e.q = L.q[l]; e.mu = L.mu[l]; e.qbit = (int)L.qbit[l];
         e.ratio = ratio_of(e.q);
@@ -363,9 +367,10 @@ k_encrypt_epilogue(u64 *c, const int *es, const u64 *m_poly, size_t m_stride, un
         K[threadIdx.x] = e;
     }
     __syncthreads();
-    const size_t rn = (size_t)r * n, k = blockIdx.z;
-    u64 *ch = c + k * 2 * rn + (size_t)h * rn;
-    const int *e = es + k * 2 * n + (size_t)h * n;
+    const size_t k = blockIdx.z;
+    u64 *ch = c + k * item_stride + (size_t)h * half_stride;
+    const u64 *clh = clp + k * cl_item_stride + (size_t)h * cl_half_stride;
+    const ES *e = es + k * 2 * n + (size_t)h * n;
     const u64 *mp = m_poly + k * m_stride;
     const u64 tfix = (t + 1) >> 1;
     // t is a power of two in every reference parameter set; keep the general division for anything else
@@ -376,10 +381,10 @@ k_encrypt_epilogue(u64 *c, const int *es, const u64 *m_poly, size_t m_stride, un
         ulonglong2 xv[kEncChunk];
         NTT_UNROLL
         for (unsigned i = 0; i < kEncChunk; i++)
-            if (l0 + i + 1 < r) xv[i] = ld2(ch + (size_t)(l0 + i) * n + j);
-        const int d0 = e[j], d1 = e[j + 1];
-        const ulonglong2 lv = ld2(ch + (size_t)(r - 1) * n + j);
-        const u64 cl0 = enc_last_limb(lv.x, d0, last, half_last), cl1 = enc_last_limb(lv.y, d1, last, half_last);
+            if (l0 + i < cnt) xv[i] = ld2(ch + (size_t)(l0 + i) * n + j);
+        const int d0 = (int)e[j], d1 = (int)e[j + 1];
+        const ulonglong2 lv = ld2(clh + j);
+        const u64 cl0 = CL_FINISHED ? lv.x : enc_last_limb(lv.x, d0, last, half_last), cl1 = CL_FINISHED ? lv.y : enc_last_limb(lv.y, d1, last, half_last);
         u64 m0 = 0, m1 = 0, f0 = 0, f1 = 0;
         if (h == 0) {
             const ulonglong2 mv = ld2(mp + j);
@@ -389,7 +394,7 @@ k_encrypt_epilogue(u64 *c, const int *es, const u64 *m_poly, size_t m_stride, un
         }
         NTT_UNROLL
         for (unsigned i = 0; i < kEncChunk; i++) {
-            if (l0 + i + 1 >= r) break;
+            if (l0 + i >= cnt) break;
             const EncLimb &P = K[i];
             if (ALL_LAZY || P.lazy) {
                 // (c_i + e - (c_last - half)) * q_last^-1: sum in (q - 20, 5q), Shoup product in [0, 2q)

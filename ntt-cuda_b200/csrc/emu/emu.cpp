@@ -298,7 +298,7 @@ EXPORT int emu_bfv(int op, unsigned n, unsigned r, const u64 *q, const u64 *mu, 
         }
         ew3(r, batch, [&] { k_encrypt_mul(c, pk, per_item_keys ? 2 * rn : 0, n, r, batch, L); });
         ring_ntt(R, true, c, batch * 2 * r, r, 0, 0);
-        if (r > 1) ew3(2 * ((r - 1 + kEncChunk - 1) / kEncChunk), batch, [&] { if (g_epi_fast) k_encrypt_epilogue<true>(c, es, m, (size_t)n, n, r, batch, t, qi_div_t, L); else k_encrypt_epilogue<false>(c, es, m, (size_t)n, n, r, batch, t, qi_div_t, L); });
+        if (r > 1) ew3(2 * ((r - 1 + kEncChunk - 1) / kEncChunk), batch, [&] { if (g_epi_fast) k_encrypt_epilogue<true, int, false>(c, 2 * rn, rn, es, m, (size_t)n, n, r, 0, r - 1, c + (size_t)(r - 1) * n, 2 * rn, rn, t, qi_div_t, L); else k_encrypt_epilogue<false, int, false>(c, 2 * rn, rn, es, m, (size_t)n, n, r, 0, r - 1, c + (size_t)(r - 1) * n, 2 * rn, rn, t, qi_div_t, L); });
         ew3(2, batch, [&] { k_encrypt_last_limb(c, es, n, r, batch, L); });
     } else if (op == 3 || op == 5) {   // encrypt through the fused kernel, key loaded (op 5: non-lazy policies); companions built here
         const size_t stride = 9 * (size_t)n; const u64 nblk = stride / 64;
@@ -312,7 +312,7 @@ EXPORT int emu_bfv(int op, unsigned n, unsigned r, const u64 *q, const u64 *mu, 
         g_gen_src = nullptr;
         ring_fused(R, op == 3, c, 2 * r, 2 * rn, pk, pk_s, rn, r, 0, 0, r, batch, 2);
         ring_ntt(R, true, c, batch * 2 * r, r, 0, 0, 1);
-        if (r > 1) ew3(2 * ((r - 1 + kEncChunk - 1) / kEncChunk), batch, [&] { if (g_epi_fast) k_encrypt_epilogue<true>(c, es, m, (size_t)n, n, r, batch, t, qi_div_t, L); else k_encrypt_epilogue<false>(c, es, m, (size_t)n, n, r, batch, t, qi_div_t, L); });
+        if (r > 1) ew3(2 * ((r - 1 + kEncChunk - 1) / kEncChunk), batch, [&] { if (g_epi_fast) k_encrypt_epilogue<true, int, false>(c, 2 * rn, rn, es, m, (size_t)n, n, r, 0, r - 1, c + (size_t)(r - 1) * n, 2 * rn, rn, t, qi_div_t, L); else k_encrypt_epilogue<false, int, false>(c, 2 * rn, rn, es, m, (size_t)n, n, r, 0, r - 1, c + (size_t)(r - 1) * n, 2 * rn, rn, t, qi_div_t, L); });
         ew3(2, batch, [&] { k_encrypt_last_limb(c, es, n, r, batch, L); });
         delete[] pk_s;
     } else if (op == 4 || op == 6) {   // decrypt through the fused kernel
@@ -450,7 +450,9 @@ EmuRing ring_window(const EmuRing &R, unsigned first, unsigned count)
 }
 }  // namespace
 
-// op 0: sample (want_u = i0, want_e = i1; items, nonce0) | 1: front | 2: finish_last | 3: finish_limbs
+static const u64 *g_inv_q_last = nullptr, *g_qi_div_t = nullptr;     // per-limb arrays of the separate epilogue kernel (set by emu_set_enc_arrays)
+EXPORT void emu_set_enc_arrays(const u64 *inv_q_last, const u64 *qi_div_t) { g_inv_q_last = inv_q_last; g_qi_div_t = qi_div_t; }
+// op 0: sample (want_u = i0, want_e = i1; items, nonce0) | 1: front | 2: finish_last | 3: finish_limbs (i0: fused epilogue, i1: ALL_LAZY)
 EXPORT int emu_enc_blocks(int op, unsigned n, unsigned r, const u64 *q, const u64 *mu, const u32 *qbit, const u64 *psi, const u64 *psiinv,
                           const u64 *psi_s, const u64 *psiinv_s, const LimbConst *lc, unsigned first, unsigned count, unsigned slots, unsigned items,
                           u64 *c, unsigned char *ub, signed char *es8, const u64 *pk, const u64 *pk_s, u64 *cl, size_t cl_item_stride,
@@ -484,7 +486,13 @@ EXPORT int emu_enc_blocks(int op, unsigned n, unsigned r, const u64 *q, const u6
         A.a = c; A.tw = W.psiinv; A.tws = W.psiinv_s; A.lc = W.lc; A.num = items * 2 * count; A.division = count; A.use_tma = 1;
         A.group_polys = count; A.group_stride = (size_t)slots * n;
         E.cl = cl; E.cl_item_stride = cl_item_stride; E.cl_half_stride = cl_half_stride; E.m = m; E.m_stride = n; E.first_limb = first;
-        return run_strided_inv_epi<EncLimbEpi>((int)R.logn, A, E);
+        if (i0) return run_strided_inv_epi<EncLimbEpi>((int)R.logn, A, E);          // A/B variant: epilogue in the kernel's store
+        ring_ntt(W, true, c, items * 2 * count, count, count, (size_t)slots * n, 1);  // default: plain strided inverse pass + epilogue kernel
+        LimbArrays L{q, mu, qbit, g_inv_q_last, nullptr, nullptr};
+        const size_t item = (size_t)2 * slots * n, half = (size_t)slots * n;
+        const unsigned rows = 2 * ((count + kEncChunk - 1) / kEncChunk);
+        if (i1) ew3(rows, items, [&] { k_encrypt_epilogue<true, signed char, true>(c, item, half, es8, m, (size_t)n, n, r, first, count, cl, cl_item_stride, cl_half_stride, t, g_qi_div_t, L); });
+        else ew3(rows, items, [&] { k_encrypt_epilogue<false, signed char, true>(c, item, half, es8, m, (size_t)n, n, r, first, count, cl, cl_item_stride, cl_half_stride, t, g_qi_div_t, L); });
     } else {
         return 1;
     }

@@ -10,7 +10,7 @@ namespace nttb200 {
 // coefficients in registers, so those steps run there and the ciphertext is written ONCE (the separate epilogue pass re-read
 // and re-wrote all of c: 15.5 MiB of the 49 MiB an encryption at (32768, 16 limbs) moved).  Ordering: the dropped limb is
 // finished by an earlier launch (mode kEpiEncLast), the other limbs read its finished values `cl` (mode kEpiEncLimb).
-struct EncEpiLimb { u64 q, twoq, inv_q_last, inv_q_last_s, qdt, bias, ratio, pad; };   // per limb below the dropped one
+struct EncEpiLimb { u64 q, twoq, inv_q_last, inv_q_last_s, qdt, bias, ratio, reduce_cl; };   // per limb below the dropped one; reduce_cl: q_last > 2 q
 enum { kEpiNone = 0, kEpiEncLast = 1, kEpiEncLimb = 2 };
 struct EpiArgs {
     const signed char *es;        // gaussian draws es[item][2][n] (signed, |e| <= 19)
@@ -53,7 +53,7 @@ struct EncLimbEpi {
     const signed char *e;
     const u64 *cl, *m;
     u64 q, twoq, c, cs, qdt, bias, ratio, t, tfix;
-    u32 tsh;
+    u32 tsh, reduce_cl;
     __device__ __forceinline__ void init(const EpiArgs &E, u32 grp, u32 limb, u32 n)
     {
         const u32 item = grp >> 1, half = grp & 1u;
@@ -61,14 +61,16 @@ struct EncLimbEpi {
         cl = E.cl + (size_t)item * E.cl_item_stride + (size_t)half * E.cl_half_stride;
         m = half == 0 ? E.m + (size_t)item * E.m_stride : nullptr;
         const EncEpiLimb &k = E.K[E.first_limb + limb];
-        q = k.q; twoq = k.twoq; c = k.inv_q_last; cs = k.inv_q_last_s; qdt = k.qdt; bias = k.bias; ratio = k.ratio;
+        q = k.q; twoq = k.twoq; c = k.inv_q_last; cs = k.inv_q_last_s; qdt = k.qdt; bias = k.bias; ratio = k.ratio; reduce_cl = (u32)k.reduce_cl;
         t = E.t; tfix = E.tfix; tsh = E.tsh;
     }
     // (c_i + e - (c_last - half)) * q_last^-1 [+ Delta*m + round-fix]: k_encrypt_epilogue's ALL_LAZY arithmetic (bfv_kernels.cuh)
     __device__ __forceinline__ u64 apply(u64 v, u32 j) const
     {
         const int d = (int)e[j];
-        u64 x = shoup_mul(v + bias + (u64)(long long)d - cl[j], c, cs, q);          // [0, 2q)
+        u64 last = cl[j];
+        if (reduce_cl) last -= mulhi64(last, ratio) * q;          // q_last > 2 q_i (mixed-size sets such as 16k_9q): bring c_last below 2 q_i first
+        u64 x = shoup_mul(v + bias + (u64)(long long)d - last, c, cs, q);          // [0, 2q)
         if (m) {
             const u64 mj = m[j], f = (mj + tfix) >> tsh;
             if (mj < t) x = csub(x + (mj * qdt + f), twoq);

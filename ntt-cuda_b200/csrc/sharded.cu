@@ -37,6 +37,7 @@ struct NcclApi {
     ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*ReduceScatter)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Reduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -59,10 +60,10 @@ NcclApi &nccl()
     if (!api.handle) return api;
 #define NTTB200_SYM(f) *(void **)(&api.f) = dlsym(api.handle, "nccl" #f)
     NTTB200_SYM(GetUniqueId); NTTB200_SYM(CommInitRank); NTTB200_SYM(CommDestroy); NTTB200_SYM(CommCount); NTTB200_SYM(CommUserRank);
-    NTTB200_SYM(AllGather); NTTB200_SYM(ReduceScatter); NTTB200_SYM(Reduce); NTTB200_SYM(GroupStart); NTTB200_SYM(GroupEnd);
+    NTTB200_SYM(AllGather); NTTB200_SYM(ReduceScatter); NTTB200_SYM(Reduce); NTTB200_SYM(Broadcast); NTTB200_SYM(GroupStart); NTTB200_SYM(GroupEnd);
     NTTB200_SYM(GetErrorString);
 #undef NTTB200_SYM
-    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.ReduceScatter && api.Reduce && api.GroupStart &&
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.ReduceScatter && api.Reduce && api.Broadcast && api.GroupStart &&
              api.GroupEnd;
     return api;
 }
@@ -272,7 +273,7 @@ int nttb200_bfv_encrypt_sharded(nttb200_bfv *b, nttb200_comm *comm, nttb200_u64 
                                 void *stream)
 {
     if (!b || !comm || !c_shard || !m || !batch || batch % (unsigned)comm->world || !b->pk_l) return NTTB200_EINVAL;
-    if (!b->ctx->lazy_ok || !b->enc_lazy) return NTTB200_EINVAL;          // fused-epilogue path only (every reference parameter set qualifies)
+    if (!b->ctx->lazy_ok || !b->epi_ok) return NTTB200_EINVAL;            // every q_i < 2^57 with an exact reference Barrett (all reference sets but 4k_3q / 8k_3q)
     const unsigned G = (unsigned)comm->world, g = (unsigned)comm->rank, n = b->n, r = b->r, per = batch / G;
     if (per > 65535) return NTTB200_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
@@ -336,9 +337,9 @@ int nttb200_bfv_decrypt_sharded(nttb200_bfv *b, nttb200_comm *comm, nttb200_u64 
     TRY(shard_state(b, &s, 1));
     std::vector<nttb200_shard_block> blk(G);
     plan_blocks(rp, n, batch, G, g, blk.data(), nullptr);
-    unsigned chunks = (G > 1 && s->mode == 1) ? s->chunks : 1u;
+    unsigned chunks = G > 1 ? s->chunks : 1u;
     while (chunks > 1 && per % chunks) chunks--;
-    TRY(shard_state(b, &s, (size_t)G + chunks + 4));
+    TRY(shard_state(b, &s, (size_t)G * chunks + 4));
     const unsigned sub = per / chunks;                                   // items of one block in one chunk
     u64 *partial, *recv; unsigned short *plain;
     TRY(shard_buf(s, kBufPartial, (size_t)batch * pw * 8, (void **)&partial));
@@ -348,42 +349,62 @@ int nttb200_bfv_decrypt_sharded(nttb200_bfv *b, nttb200_comm *comm, nttb200_u64 
     NTTB200_CHECK(cudaEventRecord(s->ev[0], s->cs));                     // scratch reuse across calls (see encrypt)
     NTTB200_CHECK(cudaStreamWaitEvent(st, s->ev[0], 0));
     size_t evi = 1;
-    const bool scatter = G > 1 && s->mode == 1;
-    // partial layout: mode 0 -> [block][item][pw]; mode 1 -> [chunk][block][sub items][pw] (what ncclReduceScatter wants)
-    for (unsigned c = 0; c < chunks; c++) {
+    const size_t own = (size_t)g * per;
+    if (G == 1) {
+        TRY(dec_partial(b, P, partial, packed, c_shard, blk[0].limb_count, blk[0].first_limb, blk[0].limb_count, batch));
+        TRY(dec_finish(b, m_out, 0, partial, packed, batch, st));
+        return 0;
+    }
+    if (s->mode == 0) {
+        // Block by block, each in `chunks` pieces: transforms + partial sums of a piece on the caller's stream; on the comm stream,
+        // behind them, the piece's sums go to the block's owner (ncclReduce), the owner rounds it, and when a block is complete its
+        // owner broadcasts the 16-bit plaintext words -- so the only exposed communication is the LAST piece's reduce + broadcast.
         for (unsigned j = 0; j < G; j++) {
             const unsigned cnt = blk[j].limb_count;
-            u64 *pj = partial + ((size_t)c * G + j) * sub * pw;
-            if (cnt) TRY(dec_partial(b, P, pj, packed, c_shard + blk[j].offset + (size_t)c * sub * 2 * cnt * n, cnt, blk[j].first_limb, cnt, sub));
-            else NTTB200_CHECK(cudaMemsetAsync(pj, 0, (size_t)sub * pw * 8, st));
-            if (G > 1 && !scatter) {       // this block's sums -> its owner, while the next block's transforms run
+            for (unsigned c = 0; c < chunks; c++) {
+                u64 *pj = partial + ((size_t)j * per + (size_t)c * sub) * pw;
+                if (cnt) TRY(dec_partial(b, P, pj, packed, c_shard + blk[j].offset + (size_t)c * sub * 2 * cnt * n, cnt, blk[j].first_limb, cnt, sub));
+                else NTTB200_CHECK(cudaMemsetAsync(pj, 0, (size_t)sub * pw * 8, st));
                 NTTB200_CHECK(cudaEventRecord(s->ev[evi], st));
                 NTTB200_CHECK(cudaStreamWaitEvent(s->cs, s->ev[evi], 0));
                 evi++;
-                NCCLCHECK(nccl().Reduce(pj, recv, (size_t)sub * pw, ncclUint64, ncclSum, (int)j, comm->comm, s->cs));
+                NCCLCHECK(nccl().Reduce(pj, recv + (size_t)c * sub * pw, (size_t)sub * pw, ncclUint64, ncclSum, (int)j, comm->comm, s->cs));
+                if (j == g) {
+                    if (out16) TRY(dec_finish(b, plain + (own + (size_t)c * sub) * n, 1, recv + (size_t)c * sub * pw, packed, sub, s->cs));
+                    else TRY(dec_finish(b, m_out + (own + (size_t)c * sub) * n, 0, recv + (size_t)c * sub * pw, packed, sub, s->cs));
+                }
+            }
+            const size_t it = (size_t)j * per;
+            if (out16) {
+                NCCLCHECK(nccl().Broadcast(plain + it * n, plain + it * n, (size_t)per * n * 2, ncclInt8, (int)j, comm->comm, s->cs));
+                TRY(dec_expand16(plain + it * n, m_out + it * n, (size_t)per * n, s->cs));
+            } else {
+                NCCLCHECK(nccl().Broadcast(m_out + it * n, m_out + it * n, (size_t)per * n, ncclUint64, (int)j, comm->comm, s->cs));
             }
         }
-        if (scatter) {
+    } else {
+        // mode 1: partial layout [chunk][block][sub items][pw], one ncclReduceScatter per chunk, rounding and ONE all-gather at the end
+        for (unsigned c = 0; c < chunks; c++) {
+            for (unsigned j = 0; j < G; j++) {
+                const unsigned cnt = blk[j].limb_count;
+                u64 *pj = partial + ((size_t)c * G + j) * sub * pw;
+                if (cnt) TRY(dec_partial(b, P, pj, packed, c_shard + blk[j].offset + (size_t)c * sub * 2 * cnt * n, cnt, blk[j].first_limb, cnt, sub));
+                else NTTB200_CHECK(cudaMemsetAsync(pj, 0, (size_t)sub * pw * 8, st));
+            }
             NTTB200_CHECK(cudaEventRecord(s->ev[evi], st));
             NTTB200_CHECK(cudaStreamWaitEvent(s->cs, s->ev[evi], 0));
             evi++;
             NCCLCHECK(nccl().ReduceScatter(partial + (size_t)c * G * sub * pw, recv + (size_t)c * sub * pw, (size_t)sub * pw, ncclUint64, ncclSum,
                                            comm->comm, s->cs));
         }
-    }
-    if (G == 1) {
-        TRY(dec_finish(b, m_out, 0, partial, packed, batch, st));
-        return 0;
-    }
-    // owner: rounding of the own block on the comm stream (after its reduce), then the path's final gather
-    const size_t own = (size_t)g * per;
-    if (out16) {
-        TRY(dec_finish(b, plain + own * n, 1, recv, packed, per, s->cs));
-        NCCLCHECK(nccl().AllGather(plain + own * n, plain, (size_t)per * n * 2, ncclInt8, comm->comm, s->cs));
-        TRY(dec_expand16(plain, m_out, (size_t)batch * n, s->cs));
-    } else {
-        TRY(dec_finish(b, m_out + own * n, 0, recv, packed, per, s->cs));
-        NCCLCHECK(nccl().AllGather(m_out + own * n, m_out, (size_t)per * n, ncclUint64, comm->comm, s->cs));
+        if (out16) {
+            TRY(dec_finish(b, plain + own * n, 1, recv, packed, per, s->cs));
+            NCCLCHECK(nccl().AllGather(plain + own * n, plain, (size_t)per * n * 2, ncclInt8, comm->comm, s->cs));
+            TRY(dec_expand16(plain, m_out, (size_t)batch * n, s->cs));
+        } else {
+            TRY(dec_finish(b, m_out + own * n, 0, recv, packed, per, s->cs));
+            NCCLCHECK(nccl().AllGather(m_out + own * n, m_out, (size_t)per * n, ncclUint64, comm->comm, s->cs));
+        }
     }
     NTTB200_CHECK(cudaEventRecord(s->ev[evi], s->cs));
     NTTB200_CHECK(cudaStreamWaitEvent(st, s->ev[evi], 0));

@@ -193,7 +193,7 @@ def enc_epi_limbs(R):
     out = np.zeros((r - 1, 8), dtype=np.uint64)
     for i in range(r - 1):
         q, iql = qs[i], int(R.inv_q_last_mod_q[i])
-        out[i] = [q, 2 * q, iql, (iql << 64) // q, int(R.qi_div_t[i]), (qs[r - 1] >> 1) % q + 3 * q, ((1 << 64) - 1) // q, 0]
+        out[i] = [q, 2 * q, iql, (iql << 64) // q, int(R.qi_div_t[i]), (qs[r - 1] >> 1) % q + 3 * q, ((1 << 64) - 1) // q, int(qs[r - 1] > 2 * q)]
     assert lib().emu_sizeof_encepilimb() == 64
     return out
 
@@ -210,6 +210,7 @@ class EmuBlocks:
         self.K = enc_epi_limbs(R)
         self.tsh = int(R.t).bit_length() - 1
         self.sk = self.sk_s = self.pk = self.pk_s = None
+        self.fused = False
         if sk is not None:
             self.sk = np.ascontiguousarray(sk, dtype=np.uint64)
             self.sk_s = np.concatenate([shoup(self.sk[l * R.n:(l + 1) * R.n], qs[l]) for l in range(R.r)])
@@ -241,8 +242,14 @@ class EmuBlocks:
     def enc_finish_last(self, cl, cl_is, cl_hs, es8, items):
         self._enc(2, items=items, cl=cl, cl_is=cl_is, cl_hs=cl_hs, es8=es8)
 
-    def enc_finish_limbs(self, c, slots, first, count, items, cl, cl_is, cl_hs, es8, m):
-        self._enc(3, first, count, slots, items, c=c, cl=cl, cl_is=cl_is, cl_hs=cl_hs, es8=es8, m=m)
+    def enc_finish_limbs(self, c, slots, first, count, items, cl, cl_is, cl_hs, es8, m, fused=None):
+        """fused: epilogue in the store of the last inverse kernel (A/B variant); default (the product's): plain pass + epilogue kernel"""
+        R, u = self.R, C.c_ulonglong
+        fused = self.fused if fused is None else fused
+        qs = [int(x) for x in R.q]
+        lazy = all(qs[-1] <= 2 * q for q in qs[:-1])
+        lib().emu_set_enc_arrays(p(R.inv_q_last_mod_q, u), p(R.qi_div_t, u))
+        self._enc(3, first, count, slots, items, c=c, cl=cl, cl_is=cl_is, cl_hs=cl_hs, es8=es8, m=m, i0=int(fused), i1=int(lazy))
 
     def _dec(self, op, first=0, count=0, slots=0, items=0, c=None, part=None, out=None, packed=0, out16=0):
         R, u = self.R, C.c_ulonglong

@@ -31,6 +31,9 @@ class NoColl:
     def reduce_sum_u64(self, send, recv, root):
         recv[:] = send
 
+    def broadcast_inplace(self, buf, root):
+        pass
+
 
 class GlooColl:
     def __init__(self, dist, world, rank):
@@ -49,6 +52,12 @@ class GlooColl:
         self.dist.reduce(t, dst=root, op=self.dist.ReduceOp.SUM)
         if self.rank == root:
             recv[:] = t.numpy().view(np.uint64)
+
+
+    def broadcast_inplace(self, buf, root):
+        import torch
+        t = torch.from_numpy(buf.view(np.uint8))
+        self.dist.broadcast(t, src=root)
 
 
 def encrypt_sharded(blocks, coll, m, batch, nonce0):
@@ -77,8 +86,9 @@ def encrypt_sharded(blocks, coll, m, batch, nonce0):
     return c_shard, es
 
 
-def decrypt_sharded(blocks, coll, c_shard, batch):
-    """blocks: EmuBlocks with the secret key loaded.  Returns m_out[batch * n] (complete on every rank).  Mode 0 of csrc/sharded.cu."""
+def decrypt_sharded(blocks, coll, c_shard, batch, chunks=2):
+    """blocks: EmuBlocks with the secret key loaded.  Returns m_out[batch * n] (complete on every rank).  Mode 0 of csrc/sharded.cu:
+    block by block in `chunks` pieces -- partial sums -> reduce to the owner -> the owner rounds -> the owner broadcasts the block."""
     n, r, G, g = blocks.n, blocks.r, coll.world, coll.rank
     R = blocks.R
     rp, per = r - 1, batch // G
@@ -86,23 +96,32 @@ def decrypt_sharded(blocks, coll, c_shard, batch):
     out16 = int(R.t) <= 65536
     pw = n + n // 4 if packed else 2 * n
     plan, _ = shard_plan(rp, n, batch, G, g)
+    while chunks > 1 and per % chunks:
+        chunks -= 1
+    sub = per // chunks
     partial = np.zeros(batch * pw, dtype=np.uint64)
     recv = np.zeros(per * pw, dtype=np.uint64)
-    for j, (it, items, f, cnt, off) in enumerate(plan):
-        pj = partial[j * per * pw:(j + 1) * per * pw]
-        if cnt:
-            blocks.dec_partial(pj, packed, c_shard[off:], cnt, f, cnt, items)
-        coll.reduce_sum_u64(pj, recv, j)
     own = g * per
     m_out = np.zeros(batch * n, dtype=np.uint64)
-    if out16:
-        plain = np.zeros(batch * n, dtype=np.uint16)
-        blocks.dec_finish(plain[own * n:], 1, recv, packed, per)
-        coll.all_gather_inplace(plain, per * n)
-        blocks.dec_expand16(plain, m_out, batch)
-    else:
-        blocks.dec_finish(m_out[own * n:], 0, recv, packed, per)
-        coll.all_gather_inplace(m_out, per * n)
+    plain = np.zeros(batch * n, dtype=np.uint16)
+    for j, (it, items, f, cnt, off) in enumerate(plan):
+        for c in range(chunks):
+            pj = partial[(j * per + c * sub) * pw:(j * per + (c + 1) * sub) * pw]
+            if cnt:
+                blocks.dec_partial(pj, packed, c_shard[off + c * sub * 2 * cnt * n:], cnt, f, cnt, sub)
+            rc = recv[c * sub * pw:(c + 1) * sub * pw]
+            coll.reduce_sum_u64(pj, rc, j)
+            if j == g:
+                if out16:
+                    blocks.dec_finish(plain[(own + c * sub) * n:], 1, rc, packed, sub)
+                else:
+                    blocks.dec_finish(m_out[(own + c * sub) * n:], 0, rc, packed, sub)
+        if out16:
+            blk = plain[it * n:(it + per) * n]
+            coll.broadcast_inplace(blk, j)
+            blocks.dec_expand16(blk, m_out[it * n:], per)
+        else:
+            coll.broadcast_inplace(m_out[it * n:(it + per) * n], j)
     return m_out
 
 

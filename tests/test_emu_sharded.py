@@ -44,7 +44,8 @@ def test_shard_plan_partition():
             assert (seen == 1).all(), (rp, world)
 
 
-def test_fused_epilogue_encryption_matches_oracle(oracle):
+@pytest.mark.parametrize("fused", [False, True], ids=["epilogue_kernel", "epilogue_in_store"])
+def test_fused_epilogue_encryption_matches_oracle(oracle, fused):
     """run_encrypt_v2's launch sequence (csrc/bfv.cu) on the emulator: sampling as signed bytes, strided forward pass generating u,
     fused contig kernel, strided inverse of the dropped limb with `+ e` / rounding in its store, strided inverse of the other limbs
     with mod-switch + Delta*m in its store -- ciphertext INCLUDING the padding limb == oracle, extremes of m included."""
@@ -57,6 +58,7 @@ def test_fused_epilogue_encryption_matches_oracle(oracle):
     m = np.concatenate([oracle.fill_uniform(n, R.t, 0xE1 + k) for k in range(B)])
     m[:4] = [0, R.t - 1, 1, R.t - 1]
     blk = emu.EmuBlocks(er, sk=sk, pk=pk)
+    blk.fused = fused
     ub = np.zeros(B * n, dtype=np.uint8)
     es = np.zeros(B * 2 * n, dtype=np.int8)
     c = np.zeros(B * 2 * r * n, dtype=np.uint64)
@@ -114,6 +116,27 @@ def test_unpacked_partials_when_t_is_large(oracle, tbits):
     assert np.array_equal(sharded_sim.decrypt_sharded(blk, sharded_sim.NoColl(), shard, 1), m)
 
 
+@pytest.mark.parametrize("fused", [False, True], ids=["epilogue_kernel", "epilogue_in_store"])
+def test_fused_epilogue_with_a_much_larger_dropped_limb(oracle, fused):
+    """q_last > 2 q_i (mixed-size sets such as 16k_9q: 48 / 49 / 50-bit primes): the fused epilogue reduces c_last mod q_i itself."""
+    n = 2048
+    qa, ra = params.find_ntt_primes(48, n, 2)
+    qb, rb = params.find_ntt_primes(51, n, 1)
+    qs, roots = qa + qb, ra + rb
+    assert qs[-1] > 2 * qs[0]
+    R = oracle.Ring(n, qs, roots)
+    er = emu.EmuRing(R)
+    sk, pk, _ = emu.bfv(0, er, 0)
+    B = 2
+    m = np.concatenate([oracle.fill_uniform(n, R.t, 0x3C + k) for k in range(B)])
+    blk = emu.EmuBlocks(er, sk=sk, pk=pk)
+    blk.fused = fused
+    shard, es = sharded_sim.encrypt_sharded(blk, sharded_sim.NoColl(), m, B, 0)
+    oc = _oracle_ciphertexts(oracle, R, pk, m, es, B, 0)
+    assert np.array_equal(shard, _drop_padding(oc, n, R.r, B))
+    assert np.array_equal(sharded_sim.decrypt_sharded(blk, sharded_sim.NoColl(), shard, B), m)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -134,7 +157,7 @@ def _worker(rank, world, port, q):
         R = orc.Ring(n, qs, roots)
         er = emu.EmuRing(R)
         r = R.r
-        B = world                                     # one item per block
+        B = 2 * world                                 # two items per block: two pieces per block in the decryption
         sk, pk, _, _ = orc.keygen_rns(R)
         m = np.concatenate([orc.fill_uniform(n, R.t, 0x900 + k) for k in range(B)])
         blk = emu.EmuBlocks(er, sk=sk, pk=pk)

@@ -34,7 +34,7 @@ def _setup(oracle, name, B, seed=0x5A):
     return R, bfv, sk, pk, m
 
 
-@pytest.mark.parametrize("name", ["4k_3q", "8k_4q", "16k_5q", "32k_16q"])
+@pytest.mark.parametrize("name", ["4k_3q", "8k_4q", "16k_5q", "16k_9q", "32k_16q"])
 def test_fused_epilogue_encryption(oracle, name):
     import torch
     import nttb200  # noqa: F401
@@ -45,10 +45,10 @@ def test_fused_epilogue_encryption(oracle, name):
     md = to_dev(m)
     c_new = torch.zeros(B * 2 * rn, dtype=torch.int64, device="cuda")
     c_old = torch.zeros_like(c_new)
-    bfv.encrypt(c_new, None, md, batch=B, nonce0=21)             # loaded key, fused epilogue (default)
-    bfv.set_fused_epilogue(False)
-    bfv.encrypt(c_old, None, md, batch=B, nonce0=21)             # loaded key, separate epilogue kernels (round 1 path)
     bfv.set_fused_epilogue(True)
+    bfv.encrypt(c_new, None, md, batch=B, nonce0=21)             # loaded key, epilogue in the store of the last inverse kernel (A/B variant)
+    bfv.set_fused_epilogue(False)
+    bfv.encrypt(c_old, None, md, batch=B, nonce0=21)             # loaded key, separate epilogue kernels (default)
     assert torch.equal(c_new, c_old), "fused-epilogue ciphertext (padding limb included) != separate-epilogue ciphertext"
     c_pk = torch.zeros_like(c_new)
     bfv.encrypt(c_pk, pk, md, batch=B, nonce0=21)                # explicit key: unfused kernels
@@ -82,6 +82,11 @@ def test_sharded_calls_world1(oracle, name):
     full = torch.zeros(B * 2 * rn, dtype=torch.int64, device="cuda")
     bfv.encrypt(full, None, md, batch=B, nonce0=5)
     assert torch.equal(shard.view(B, 2, r - 1, n), full.view(B, 2, r, n)[:, :, :r - 1, :])
+    bfv.set_fused_epilogue(True)                                 # the A/B variant of the sharded call's last inverse kernel
+    shard2 = torch.zeros_like(shard)
+    bfv.encrypt_sharded(comm, shard2, md, B, nonce0=5)
+    bfv.set_fused_epilogue(False)
+    assert torch.equal(shard2, shard)
     back = torch.zeros_like(full)
     bfv.shard_to_full(1, 0, back, shard, B)
     assert torch.equal(back.view(B, 2, r, n)[:, :, :r - 1, :], full.view(B, 2, r, n)[:, :, :r - 1, :])
