@@ -244,6 +244,29 @@ NTTB200_API int nttb200_bfv_add_plain(nttb200_bfv *bfv, nttb200_u64 *c, const nt
 NTTB200_API int nttb200_bfv_mul_plain(nttb200_bfv *bfv, nttb200_u64 *c, const nttb200_u64 *p_poly, int plain_per_item, unsigned batch,
                                       void *stream);
 
+/* Ciphertext x ciphertext multiplication and relinearisation (the paper's stated future work, Article.pdf p.29; the
+ * natural caller of the batched NTT and of half_poly_mul_device, poly_arithmetic.cuh:303).  RNS variant of Halevi-Polyakov-Shoup
+ * (CT-RSA 2019): base extension to an auxiliary base of r fresh NTT primes, tensor product in the NTT domain, round(t/Q .) in the
+ * auxiliary base, conversion back; relinearisation by RNS digits.  Ciphertexts in the reference layout c[batch][2][r][n] (limb r-1 =
+ * padding, left alone).  Parity is semantic (the reference has no such operation): Dec(nttb200_bfv_mul(c_a, c_b)) = m_a * m_b mod
+ * (X^n + 1, t), and exact against the big-integer oracle (oracle/bfv_mul_oracle.py) up to the documented rounding slack.
+ *   nttb200_bfv_relin_keygen   evk_i = (-(a_i s + e_i) + g_i s^2, a_i), i < r-1, from sk[r][n]; digit i samples nonce nonce0 + i
+ *   nttb200_bfv_mul_tensor     y[batch][3][r-1][n]: the degree-2 ciphertext, Dec = y0 + y1 s + y2 s^2
+ *   nttb200_bfv_relinearize    y -> c_out[batch][2][r][n]
+ *   nttb200_bfv_mul            both; c_out may alias an input
+ * Work buffers are grow-only (the first call at a batch size allocates).  batch <= 10000. */
+NTTB200_API int nttb200_bfv_relin_keygen(nttb200_bfv *bfv, const nttb200_u64 *sk, nttb200_u64 nonce0, void *stream);
+NTTB200_API int nttb200_bfv_relin_key(nttb200_bfv *bfv, const nttb200_u64 **evk_dev, size_t *words);   /* evk[r-1][2][r-1][n], NTT domain */
+NTTB200_API int nttb200_bfv_mul_tensor(nttb200_bfv *bfv, nttb200_u64 *y, const nttb200_u64 *c_a, const nttb200_u64 *c_b, unsigned batch, void *stream);
+NTTB200_API int nttb200_bfv_relinearize(nttb200_bfv *bfv, nttb200_u64 *c_out, const nttb200_u64 *y, unsigned batch, void *stream);
+NTTB200_API int nttb200_bfv_mul(nttb200_bfv *bfv, nttb200_u64 *c_out, const nttb200_u64 *c_a, const nttb200_u64 *c_b, unsigned batch, void *stream);
+NTTB200_API int nttb200_bfv_mul_aux_base(nttb200_bfv *bfv, nttb200_u64 *p_out, unsigned *count);
+/* NTT-friendly primes (parameter generation for ring degrees the reference has no constants for, BASELINE config 5): `count` primes
+ * below 2^bits with q = 1 (mod 2n), largest first, skipping `exclude`, and for each the primitive 2n-th root psi = g^((q-1)/2n) of
+ * the smallest base g with psi^n = -1.  Host-only. */
+NTTB200_API int nttb200_find_ntt_primes(unsigned bits, unsigned n, unsigned count, const nttb200_u64 *exclude, unsigned nexclude,
+                                        nttb200_u64 *q_out, nttb200_u64 *psi_out);
+
 /* Limb-sharded encryption needs no extra entry point: create a context for the sub-ring {owned limbs..., last limb}
  * and call nttb200_bfv_encrypt on it -- a limb of the ciphertext depends only on itself, the dropped last limb and the
  * nonce-addressed randomness (whose layout does not depend on the limb count), so the shard equals the same limbs of the

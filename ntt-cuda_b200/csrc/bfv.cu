@@ -507,6 +507,7 @@ void nttb200_bfv_destroy(nttb200_bfv *b)
     if (b->word_off) cudaFree(b->word_off);
     if (b->key_word_off) cudaFree(b->key_word_off);
     nttb200_host_state_destroy(b->host);
+    nttb200_mul_state_destroy(b->mul);
     if (b->ub) cudaFree(b->ub);
     if (b->es8) cudaFree(b->es8);
     if (b->enc_epi) cudaFree(b->enc_epi);

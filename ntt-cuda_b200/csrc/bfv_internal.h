@@ -28,12 +28,14 @@ struct nttb200_bfv {
     unsigned *word_off = nullptr; unsigned half_words = 0;   // compact wire format: first word of each limb inside a half, words per half
     unsigned *key_word_off = nullptr; unsigned key_half_words = 0;   // same for keys (all r limbs)
     struct nttb200_host_state *host = nullptr;        // staging + streams of the host-buffer entry points (bfv_host.cu)
+    struct nttb200_mul_state *mul = nullptr;          // auxiliary base, constants, relinearisation key, work buffers (bfv_mul.cu)
     bool enc_lazy = false, dec_fast = false, all_exact = false;
     bool epi_ok = false;                              // every limb qualifies for the epilogue fused into the last inverse kernel
     bool no_fused_epilogue = true;                    // default: separate (HBM-bound) epilogue kernels; false = epilogue in the last inverse kernel's store (A/B, slower)
 };
 void nttb200_shard_state_destroy(struct nttb200_shard_state *s);
 void nttb200_host_state_destroy(struct nttb200_host_state *s);
+void nttb200_mul_state_destroy(struct nttb200_mul_state *s);
 
 
 namespace nttb200 {

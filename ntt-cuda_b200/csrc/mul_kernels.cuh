@@ -1,0 +1,232 @@
+// mul_kernels.cuh -- kernels of BFV ciphertext x ciphertext multiplication and relinearisation (the paper's stated
+// future work, Article.pdf p.29; the natural next caller of the batched NTT and of half_poly_mul_device, poly_arithmetic.cuh:303).
+// The reference has no such operation: the arithmetic follows the published RNS variant of Halevi, Polyakov and Shoup
+// ("An Improved RNS Variant of the BFV Homomorphic Encryption Scheme", CT-RSA 2019): base extension Q -> P and P -> Q with a
+// floating-point estimate of the CRT overflow, and the "simple scaling" round(t/Q * d) computed limb-wise in the auxiliary base P;
+// relinearisation is the RNS-digit key switch (one digit per limb of Q).
+// All floating-point steps use explicit round-to-nearest multiplies / adds in a fixed order (no FMA contraction), so the CPU oracle
+// (oracle/bfv_mul_oracle.py) reproduces them bit for bit.
+#pragma once
+#include "modarith.cuh"
+#include "bfv_kernels.cuh"
+
+namespace nttb200 {
+
+struct ModC { u64 q, ratio, mu; u32 qbit, pad; };  // modulus, floor(2^64 / q), Barrett mu = floor(2^(2 qbit) / q), bit length
+struct ShoupC { u64 c, cs; };                      // constant below q and its companion floor(c * 2^64 / q)
+
+__host__ __device__ __forceinline__ double dmul_rn(double a, double b)
+{
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+__host__ __device__ __forceinline__ double dadd_rn(double a, double b)
+{
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+// canonical product of two canonical residues, no companion: the reference's Barrett estimate (at most 2 short) + corrections
+__host__ __device__ __forceinline__ u64 mulmod_canon(u64 x, u64 y, const ModC &m)
+{
+    return csub(csub(barrett_lazy(x, y, m.q, m.mu, (int)m.qbit), 2 * m.q), m.q);
+}
+__host__ __device__ __forceinline__ u64 shoup_canon(u64 x, const ShoupC &c, u64 q) { return csub(shoup_mul(x, c.c, c.cs, q), q); }
+
+constexpr int kBaseMax = 32;                 // limbs of one base
+
+// ---- fast base conversion with overflow estimate (HPS eq. 2-3) ------------------------------------------------------------------
+// x[item][lin][n] (canonical residues mod the input base) -> out[item][lout][n] mod the output base:
+//   y_i = [x_i * (B/b_i)^-1]_{b_i};  v = round(sum_i y_i / b_i);  out_j = (sum_i y_i * [B/b_i]_{o_j} - v * [B]_{o_j}) mod o_j
+// i.e. the residues of the CENTRED representative of x (or of one shifted by B when the estimate v is off by one, which only happens
+// within 2^-48 of the boundary and is harmless: any representative below B in magnitude works downstream).
+struct BconvArgs {
+    const u64 *x; size_t in_item;            // input, [lin][n] per item
+    u64 *out; size_t out_item;               // output, [lout][n] per item
+    const ShoupC *pre;                       // [lin]   (B/b_i)^-1 mod b_i
+    const ModC *bin;                         // [lin]   input moduli
+    const double *binv;                      // [lin]   1 / b_i
+    const ShoupC *M;                         // [lout][lin]  B/b_i mod o_j
+    const u64 *corr;                         // [lout]  B mod o_j
+    const ModC *bout;                        // [lout]  output moduli
+    unsigned lin, lout, n;
+};
+NTT_KERNEL void __launch_bounds__(128) k_bconv(BconvArgs A)
+{
+    const size_t k = blockIdx.y;
+    const u64 *x = A.x + k * A.in_item;
+    u64 *o = A.out + k * A.out_item;
+    for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < A.n; j += gridDim.x * blockDim.x) {
+        u64 y[kBaseMax];
+        double s = 0.0;
+        for (unsigned i = 0; i < A.lin; i++) {
+            y[i] = shoup_canon(x[(size_t)i * A.n + j], A.pre[i], A.bin[i].q);
+            s = dadd_rn(s, dmul_rn((double)y[i], A.binv[i]));
+        }
+        const u64 v = (u64)(long long)floor(dadd_rn(s, 0.5));
+        for (unsigned l = 0; l < A.lout; l++) {
+            const ModC m = A.bout[l];
+            const ShoupC *row = A.M + (size_t)l * A.lin;
+            u64 acc = 0;
+            for (unsigned i = 0; i < A.lin; i++) acc += shoup_mul(y[i], row[i].c, row[i].cs, m.q);        // each < 2 o_j: sum < 2^6 * 2^58
+            acc += (u64)(A.lin + 1) * m.q - v * A.corr[l];                                                // v <= lin, corr < o_j
+            o[(size_t)l * A.n + j] = mod_exact(acc, m.q, m.ratio);
+        }
+    }
+}
+
+// ---- HPS "simple scaling": y = round(t/Q * d) in base P from d in base Q u P ------------------------------------------------------
+// d[item][comp][rp + k][n] (coefficient domain, canonical; Q limbs first) -> y[item][comp][k][n]:
+//   yt_i = [d_i * (QP/q_i)^-1]_{q_i};  y_j = ( sum_i yt_i * [omega_i]_{p_j} + d'_j * lambda_j + round(sum_i yt_i * theta_i) ) mod p_j
+// with t*P/q_i = omega_i + theta_i (integer + fraction) and lambda_j = [(QP/p_j)^-1 * t * P/p_j]_{p_j}.
+struct ScaleArgs {
+    const u64 *d; u64 *y;
+    const ShoupC *preQ;                      // [rp]     (QP/q_i)^-1 mod q_i
+    const ModC *modQ, *modP;                 // [rp], [k]
+    const double *theta;                     // [rp]     frac(t * P / q_i)
+    const ShoupC *W;                         // [k][rp]  floor(t * P / q_i) mod p_j
+    const ShoupC *lam;                       // [k]
+    unsigned rp, k, n;
+};
+NTT_KERNEL void __launch_bounds__(128) k_scale(ScaleArgs A)
+{
+    const size_t kc = blockIdx.y;             // item * comps + comp
+    const size_t L = (size_t)A.rp + A.k;
+    const u64 *d = A.d + kc * L * A.n;
+    u64 *y = A.y + kc * (size_t)A.k * A.n;
+    for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < A.n; j += gridDim.x * blockDim.x) {
+        u64 yt[kBaseMax];
+        double f = 0.0;
+        for (unsigned i = 0; i < A.rp; i++) {
+            yt[i] = shoup_canon(d[(size_t)i * A.n + j], A.preQ[i], A.modQ[i].q);
+            f = dadd_rn(f, dmul_rn((double)yt[i], A.theta[i]));
+        }
+        const u64 v = (u64)(long long)floor(dadd_rn(f, 0.5));
+        for (unsigned l = 0; l < A.k; l++) {
+            const ModC m = A.modP[l];
+            const ShoupC *row = A.W + (size_t)l * A.rp;
+            u64 acc = shoup_mul(d[((size_t)A.rp + l) * A.n + j], A.lam[l].c, A.lam[l].cs, m.q);
+            for (unsigned i = 0; i < A.rp; i++) acc += shoup_mul(yt[i], row[i].c, row[i].cs, m.q);
+            acc += mod_exact(v, m.q, m.ratio);
+            y[(size_t)l * A.n + j] = mod_exact(acc, m.q, m.ratio);
+        }
+    }
+}
+
+// ---- tensor product in the NTT domain ---------------------------------------------------------------------------------------------
+// a, b: [item][2][L][n] (component, limb); d: [item][3][L][n]:  d0 = a0 b0, d1 = a0 b1 + a1 b0, d2 = a1 b1, limb l modulo mods[l].
+// Inputs canonical.  grid (x, L, items)
+NTT_KERNEL void k_tensor(const u64 *a, const u64 *b, u64 *d, unsigned n, unsigned L, const ModC *mods)
+{
+    const unsigned l = blockIdx.y;
+    const size_t k = blockIdx.z, Ln = (size_t)L * n;
+    const ModC m = mods[l];
+    const u64 *a0 = a + k * 2 * Ln + (size_t)l * n, *a1 = a0 + Ln, *b0 = b + k * 2 * Ln + (size_t)l * n, *b1 = b0 + Ln;
+    u64 *d0 = d + k * 3 * Ln + (size_t)l * n;
+    NTT_PAIR_STRIDE(j, n) {
+        const ulonglong2 x0 = ld2(a0 + j), x1 = ld2(a1 + j), y0 = ld2(b0 + j), y1 = ld2(b1 + j);
+        st2(d0 + j, mulmod_canon(x0.x, y0.x, m), mulmod_canon(x0.y, y0.y, m));
+        st2(d0 + Ln + j, csub(mulmod_canon(x0.x, y1.x, m) + mulmod_canon(x1.x, y0.x, m), m.q),
+            csub(mulmod_canon(x0.y, y1.y, m) + mulmod_canon(x1.y, y0.y, m), m.q));
+        st2(d0 + 2 * Ln + j, mulmod_canon(x1.x, y1.x, m), mulmod_canon(x1.y, y1.y, m));
+    }
+}
+
+// gathers the rp limbs of both halves of reference-layout ciphertexts c[item][2][r][n] into w[item][2][L][n] slots [0, rp)
+// (the P slots [rp, L) are filled by k_bconv).  grid (x, rp, 2 * items)
+NTT_KERNEL void k_gather_q(const u64 *c, u64 *w, unsigned n, unsigned r, unsigned L)
+{
+    const unsigned l = blockIdx.y;
+    const size_t kh = blockIdx.z;
+    const u64 *src = c + kh * r * n + (size_t)l * n;
+    u64 *dst = w + kh * L * n + (size_t)l * n;
+    NTT_PAIR_STRIDE(j, n) { const ulonglong2 v = ld2(src + j); st2(dst + j, v.x, v.y); }
+}
+
+// ---- relinearisation (RNS-digit key switch) ------------------------------------------------------------------------------------------
+// digits: D[item][i][j][n] = [y2_i]_{q_j}, y2[item][rp][n] canonical mod q_i.  grid (x, rp * rp, items)
+NTT_KERNEL void k_relin_lift(const u64 *y2, size_t y2_item, u64 *D, unsigned n, unsigned rp, const ModC *modQ)
+{
+    const unsigned i = blockIdx.y / rp, jl = blockIdx.y % rp;
+    const size_t k = blockIdx.z;
+    const ModC m = modQ[jl];
+    const u64 *src = y2 + k * y2_item + (size_t)i * n;
+    u64 *dst = D + ((k * rp + i) * rp + jl) * (size_t)n;
+    NTT_PAIR_STRIDE(j, n) {
+        const ulonglong2 v = ld2(src + j);
+        st2(dst + j, mod_exact(v.x, m.q, m.ratio), mod_exact(v.y, m.q, m.ratio));
+    }
+}
+// acc[item][h][j][n] = sum_i D[item][i][j][n] * evk[i][h][j][n] mod q_j (NTT domain, canonical).  grid (x, rp, 2 * items)
+NTT_KERNEL void k_relin_accum(const u64 *D, const u64 *evk, const u64 *evk_s, u64 *acc, unsigned n, unsigned rp, const ModC *modQ)
+{
+    const unsigned jl = blockIdx.y, h = blockIdx.z & 1u;
+    const size_t k = blockIdx.z >> 1;
+    const ModC m = modQ[jl];
+    u64 *dst = acc + ((k * 2 + h) * rp + jl) * (size_t)n;
+    NTT_PAIR_STRIDE(j, n) {
+        u64 s0 = 0, s1 = 0;
+        for (unsigned i = 0; i < rp; i++) {
+            const ulonglong2 d = ld2(D + ((k * rp + i) * rp + jl) * (size_t)n + j);
+            const size_t eo = (((size_t)i * 2 + h) * rp + jl) * (size_t)n + j;
+            const ulonglong2 e = ld2(evk + eo), es = ld2(evk_s + eo);
+            s0 += shoup_mul(d.x, e.x, es.x, m.q);          // each < 2 q_j; rp <= 32 terms of < 2^59
+            s1 += shoup_mul(d.y, e.y, es.y, m.q);
+        }
+        st2(dst + j, mod_exact(s0, m.q, m.ratio), mod_exact(s1, m.q, m.ratio));
+    }
+}
+// out[item][h][r slots][n] limb j = (y[item][h][rp][n] + acc[item][h][rp][n]) mod q_j (coefficient domain).  grid (x, rp, 2 * items)
+NTT_KERNEL void k_relin_add(const u64 *y, size_t y_item, const u64 *acc, u64 *out, unsigned n, unsigned rp, unsigned r, const ModC *modQ)
+{
+    const unsigned jl = blockIdx.y, h = blockIdx.z & 1u;
+    const size_t k = blockIdx.z >> 1;
+    const u64 q = modQ[jl].q;
+    const u64 *a = y + k * y_item + ((size_t)h * rp + jl) * n, *b = acc + ((k * 2 + h) * rp + jl) * (size_t)n;
+    u64 *o = out + ((k * 2 + h) * r + jl) * (size_t)n;
+    NTT_PAIR_STRIDE(j, n) {
+        const ulonglong2 u = ld2(a + j), v = ld2(b + j);
+        st2(o + j, csub(u.x + v.x, q), csub(u.y + v.y, q));
+    }
+}
+
+// ---- relinearisation key generation ---------------------------------------------------------------------------------------------
+// evk[i][1][j][n] = a_ij uniform mod q_j (taken as NTT-domain values), from 64-bit keystream words (uniform_value, the reference's
+// converter bfv_keygen.cuh:37-44); E[i][j][n] = e_i lifted to limb j, e_i gaussian from 32-bit words.  Keystream of digit i:
+// [a words: rp * n u64][e words: n u32].  grid (x, rp * rp)
+NTT_KERNEL void k_relin_sample(const unsigned char *ks, size_t ks_stride, u64 *evk, u64 *E, unsigned n, unsigned rp, const ModC *modQ)
+{
+    const unsigned i = blockIdx.y / rp, jl = blockIdx.y % rp;
+    const u64 q = modQ[jl].q;
+    const unsigned char *s = ks + (size_t)i * ks_stride;
+    const u64 *aw = reinterpret_cast<const u64 *>(s) + (size_t)jl * n;
+    const u32 *ew = reinterpret_cast<const u32 *>(s + (size_t)rp * n * 8);
+    u64 *a = evk + (((size_t)i * 2 + 1) * rp + jl) * (size_t)n, *e = E + ((size_t)i * rp + jl) * (size_t)n;
+    NTT_PAIR_STRIDE(j, n) {
+        const ulonglong2 w = ld2(aw + j);
+        st2(a + j, uniform_value(w.x, q), uniform_value(w.y, q));
+        st2(e + j, signed_to_residue(gaussian_value(ew[j]), q), signed_to_residue(gaussian_value(ew[j + 1]), q));
+    }
+}
+// evk[i][0][j] = -(a_ij * s_j + NTT(e_i)_j) + [i == j] * s_j^2   (NTT domain; sk[r][n] canonical).  grid (x, rp * rp)
+NTT_KERNEL void k_relin_combine(u64 *evk, const u64 *Ehat, const u64 *sk, unsigned n, unsigned rp, const ModC *modQ)
+{
+    const unsigned i = blockIdx.y / rp, jl = blockIdx.y % rp;
+    const ModC m = modQ[jl];
+    const u64 *a = evk + (((size_t)i * 2 + 1) * rp + jl) * (size_t)n, *e = Ehat + ((size_t)i * rp + jl) * (size_t)n, *s = sk + (size_t)jl * n;
+    u64 *o = evk + (((size_t)i * 2) * rp + jl) * (size_t)n;
+    NTT_PAIR_STRIDE(j, n) {
+        const ulonglong2 av = ld2(a + j), ev = ld2(e + j), sv = ld2(s + j);
+        u64 r0 = csub(mulmod_canon(av.x, sv.x, m) + ev.x, m.q), r1 = csub(mulmod_canon(av.y, sv.y, m) + ev.y, m.q);
+        r0 = r0 ? m.q - r0 : 0; r1 = r1 ? m.q - r1 : 0;
+        if (i == jl) { r0 = csub(r0 + mulmod_canon(sv.x, sv.x, m), m.q); r1 = csub(r1 + mulmod_canon(sv.y, sv.y, m), m.q); }
+        st2(o + j, r0, r1);
+    }
+}
+
+}  // namespace nttb200

@@ -354,6 +354,34 @@ class Bfv:
     def decrypt_host(self, m_host, c_host, batch, packed=True):
         check(lib().nttb200_bfv_decrypt_host(self._h, vp(ptr(m_host)), vp(ptr(c_host)), C.c_int(int(packed)), C.c_uint(batch)))
 
+    # ---- ciphertext x ciphertext multiplication + relinearisation -------------------------------------------------
+    def relin_keygen(self, sk, nonce0=1 << 62, stream=None):
+        """evk from sk[r][n] (NTT domain); digit i samples nonce nonce0 + i (default: a nonce range keygen / encrypt do not use)."""
+        check(lib().nttb200_bfv_relin_keygen(self._h, vp(ptr(sk)), u64(nonce0), vp(_stream(stream))))
+
+    def relin_key(self):
+        """(device address, words) of evk[r-1][2][r-1][n]"""
+        a, w = vp(), C.c_size_t(0)
+        check(lib().nttb200_bfv_relin_key(self._h, C.byref(a), C.byref(w)))
+        return a.value, int(w.value)
+
+    def mul_tensor(self, y, c_a, c_b, batch=1, stream=None):
+        """y[batch][3][r-1][n] = round(t/Q * (c_a (x) c_b)): degree-2 ciphertext (coefficient domain)."""
+        check(lib().nttb200_bfv_mul_tensor(self._h, vp(ptr(y)), vp(ptr(c_a)), vp(ptr(c_b)), C.c_uint(batch), vp(_stream(stream))))
+
+    def relinearize(self, c_out, y, batch=1, stream=None):
+        check(lib().nttb200_bfv_relinearize(self._h, vp(ptr(c_out)), vp(ptr(y)), C.c_uint(batch), vp(_stream(stream))))
+
+    def mul(self, c_out, c_a, c_b, batch=1, stream=None):
+        """c_out <- relin(c_a * c_b): Dec = m_a * m_b mod (X^n + 1, t)."""
+        check(lib().nttb200_bfv_mul(self._h, vp(ptr(c_out)), vp(ptr(c_a)), vp(ptr(c_b)), C.c_uint(batch), vp(_stream(stream))))
+
+    def mul_aux_base(self):
+        cnt = C.c_uint(0)
+        buf = (u64 * 64)()
+        check(lib().nttb200_bfv_mul_aux_base(self._h, buf, C.byref(cnt)))
+        return [int(buf[i]) for i in range(cnt.value)]
+
     def add(self, c_a, c_b, batch=1, stream=None):
         """c_a <- c_a + c_b (homomorphic addition: Dec = m_a + m_b mod t)."""
         check(lib().nttb200_bfv_add(self._h, vp(ptr(c_a)), vp(ptr(c_b)), C.c_uint(batch), vp(_stream(stream))))
@@ -417,6 +445,14 @@ class Bfv:
     def decrypt_finish_tile(self, m_out, out16, partial_sum, packed, batch=1, stream=None):
         check(lib().nttb200_bfv_decrypt_finish_tile(self._h, vp(ptr(m_out)), C.c_int(int(out16)), vp(ptr(partial_sum)), C.c_int(int(packed)),
                                                     C.c_uint(batch), vp(_stream(stream))))
+
+
+def find_ntt_primes(bits: int, n: int, count: int, exclude=()):
+    """C-ABI prime search (nttb200_find_ntt_primes): (primes, psi roots), largest prime first.  Host-only."""
+    q, psi = (u64 * count)(), (u64 * count)()
+    ex = _arr64(exclude) if exclude else None
+    check(lib().nttb200_find_ntt_primes(C.c_uint(bits), C.c_uint(n), C.c_uint(count), ex, C.c_uint(len(exclude)), q, psi))
+    return [int(v) for v in q], [int(v) for v in psi]
 
 
 class ShardBlock(C.Structure):
