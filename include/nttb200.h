@@ -316,11 +316,14 @@ NTTB200_API int nttb200_comm_rank(const nttb200_comm *comm);
 NTTB200_API int nttb200_bfv_encrypt_sharded(nttb200_bfv *bfv, nttb200_comm *comm, nttb200_u64 *c_shard, const nttb200_u64 *m, unsigned batch,
                                             nttb200_u64 nonce0, void *stream);
 /* decryption_rns bfv_decryption.cuh:76, limb-sharded: c_shard is consumed; m_out[batch][n] is complete on every rank.  Uses the
- * loaded secret key.  Collectives (mode 0): block by block, each in `chunks` pieces, the partial base-conversion sums
- * (poly_arithmetic.cuh:217-251) packed to 10 bytes per coefficient go to the block's owner (ncclReduce) on a second stream while the
- * next piece's transforms run; the owner rounds (dec_round :253-263) and broadcasts the block's plaintext as 16-bit words -- the
- * path's final gather, pipelined block by block, so only the last piece's reduce + broadcast is exposed.  Mode 1: `chunks`
- * ncclReduceScatter calls, rounding, one ncclAllGather. */
+ * loaded secret key.  The cross-limb sum (poly_arithmetic.cuh:217-251) is the path's one real exchange; block by block:
+ *   mode 2 (default): the kernel that forms a rank's partial base-conversion sums (packed to 10 bytes per coefficient) stores them
+ *           straight into that rank's slot of a buffer at the block's OWNER, mapped through CUDA IPC (NVLink peer stores: compute and
+ *           transfer are one kernel, no collective kernel takes SMs); a 4-byte all-reduce per block is the barrier; the owner sums
+ *           the slots while rounding (dec_round :253-263) and broadcasts the block's plaintext as 16-bit words -- the path's final
+ *           gather, pipelined block by block.  Falls back to mode 0 on all ranks when CUDA IPC is unavailable.
+ *   mode 0: ncclReduce of the sums to the owner, each block in `chunks` pieces, on a second stream next to the transforms.
+ *   mode 1: `chunks` ncclReduceScatter calls, rounding, one ncclAllGather. */
 NTTB200_API int nttb200_bfv_decrypt_sharded(nttb200_bfv *bfv, nttb200_comm *comm, nttb200_u64 *m_out, nttb200_u64 *c_shard, unsigned batch,
                                             void *stream);
 /* Building blocks for callers that run their own collectives: one (limb window, item block) tile of the plan through the fused
@@ -331,7 +334,7 @@ NTTB200_API int nttb200_bfv_decrypt_partial_tile(nttb200_bfv *bfv, nttb200_u64 *
                                                  unsigned limb_count, unsigned batch, void *stream);
 NTTB200_API int nttb200_bfv_decrypt_finish_tile(nttb200_bfv *bfv, void *m_out, int out16, const nttb200_u64 *partial_sum, int packed,
                                                 unsigned batch, void *stream);
-/* mode 0 (default) / 1 as above; chunks default 4.  Env NTTB200_SHARD_MODE / NTTB200_SHARD_CHUNKS set the defaults of new contexts. */
+/* modes as above; chunks default 4.  Env NTTB200_SHARD_MODE / NTTB200_SHARD_CHUNKS set the defaults of new contexts. */
 NTTB200_API int nttb200_bfv_shard_config(nttb200_bfv *bfv, int mode, unsigned chunks);
 /* device-local conversion between the reference layout c[batch][2][r][n] and the calling rank's shard */
 NTTB200_API int nttb200_bfv_shard_from_full(nttb200_bfv *bfv, unsigned world, unsigned rank, nttb200_u64 *c_shard, const nttb200_u64 *c_full,

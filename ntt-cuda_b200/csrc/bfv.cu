@@ -353,16 +353,17 @@ int dec_partial(const nttb200_bfv *b, const Pipe &P0, u64 *partial, int packed, 
     return 0;
 }
 // partial sums -> plaintext (16-bit words or u64 coefficients); expansion of gathered 16-bit plaintexts
-int dec_finish(const nttb200_bfv *b, void *out, int out16, const u64 *partial_sum, int packed, unsigned items, cudaStream_t st)
+int dec_finish(const nttb200_bfv *b, void *out, int out16, const u64 *partial_sum, int packed, unsigned items, cudaStream_t st, unsigned slots,
+               size_t slot_stride)
 {
     DecryptConsts D{b->t, b->gamma, b->mu_gamma, b->gamma_div_2, b->neg_inv_t, b->neg_inv_gamma, b->gamma_bits, b->r - 1, b->bcm};
     const unsigned n = b->n;
     const dim3 g = pair_grid(n, items, 1);
     const unsigned tb = pair_block(n, items, 1);
-    if (packed && out16) k_decrypt_finish<true, true><<<g, tb, 0, st>>>(partial_sum, out, (size_t)n, n, items, D);
-    else if (packed) k_decrypt_finish<true, false><<<g, tb, 0, st>>>(partial_sum, out, (size_t)n, n, items, D);
-    else if (out16) k_decrypt_finish<false, true><<<g, tb, 0, st>>>(partial_sum, out, (size_t)n, n, items, D);
-    else k_decrypt_finish<false, false><<<g, tb, 0, st>>>(partial_sum, out, (size_t)n, n, items, D);
+    if (packed && out16) k_decrypt_finish<true, true><<<g, tb, 0, st>>>(partial_sum, out, (size_t)n, n, items, D, slots, slot_stride);
+    else if (packed) k_decrypt_finish<true, false><<<g, tb, 0, st>>>(partial_sum, out, (size_t)n, n, items, D, slots, slot_stride);
+    else if (out16) k_decrypt_finish<false, true><<<g, tb, 0, st>>>(partial_sum, out, (size_t)n, n, items, D, slots, slot_stride);
+    else k_decrypt_finish<false, false><<<g, tb, 0, st>>>(partial_sum, out, (size_t)n, n, items, D, slots, slot_stride);
     KCHECK();
     return 0;
 }
@@ -747,7 +748,7 @@ int nttb200_bfv_decrypt_finish(nttb200_bfv *b, nttb200_u64 *m_out, const nttb200
 {
     if (!b || !m_out || !partial_sum || !batch) return NTTB200_EINVAL;
     DecryptConsts D{b->t, b->gamma, b->mu_gamma, b->gamma_div_2, b->neg_inv_t, b->neg_inv_gamma, b->gamma_bits, b->r - 1, b->bcm};
-    k_decrypt_finish<false, false><<<pair_grid(b->n, batch, 1), pair_block(b->n, batch, 1), 0, (cudaStream_t)stream>>>(partial_sum, m_out, b->n, b->n, batch, D);
+    k_decrypt_finish<false, false><<<pair_grid(b->n, batch, 1), pair_block(b->n, batch, 1), 0, (cudaStream_t)stream>>>(partial_sum, m_out, b->n, b->n, batch, D, 1, 0);
     KCHECK();
     return 0;
 }

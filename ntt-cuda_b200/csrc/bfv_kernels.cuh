@@ -600,27 +600,31 @@ NTT_KERNEL void k_decrypt_partial(const u64 *c, size_t item_stride, size_t c1_of
         }
     }
 }
-// OUT16: plaintext coefficients as 16-bit words (t <= 2^16; what the final gather of a sharded decryption moves)
+// OUT16: plaintext coefficients as 16-bit words (t <= 2^16; what the final gather of a sharded decryption moves).
+// slots > 1: part_sum holds `slots` contributions slot_stride words apart (the peer-to-peer exchange deposits every rank's partial sums
+// in its own slot at the block's owner) and the 64-bit SUM a collective would have formed is taken here.
 template <bool PACKED, bool OUT16>
-NTT_KERNEL void k_decrypt_finish(const u64 *part_sum, void *out, size_t out_stride, unsigned n, unsigned batch, DecryptConsts D)
+NTT_KERNEL void k_decrypt_finish(const u64 *part_sum, void *out, size_t out_stride, unsigned n, unsigned batch, DecryptConsts D, unsigned slots,
+                                 size_t slot_stride)
 {
     (void)batch;
     const u32 mask32 = (u32)(D.t - 1);
     const size_t k = blockIdx.y;
     NTT_PAIR_STRIDE(j, n) {
-        u64 t0, t1;
-        ulonglong2 pg;
-        if (PACKED) {
-            const u64 *p = part_sum + k * (size_t)(n + n / 4);
-            pg = ld2(p + j);
-            const u32 w = reinterpret_cast<const u32 *>(p + n)[j >> 1];
-            t0 = w & 0xffffu; t1 = w >> 16;
-        } else {
-            const ulonglong2 pt = ld2(part_sum + k * 2 * n + j);
-            pg = ld2(part_sum + k * 2 * n + n + j);
-            t0 = pt.x; t1 = pt.y;
+        u64 t0 = 0, t1 = 0, g0 = 0, g1 = 0;
+        for (unsigned sl = 0; sl < slots; sl++) {
+            const u64 *base = part_sum + (size_t)sl * slot_stride;
+            if (PACKED) {
+                const u64 *p = base + k * (size_t)(n + n / 4);
+                const ulonglong2 pg = ld2(p + j);
+                const u32 w = reinterpret_cast<const u32 *>(p + n)[j >> 1];
+                t0 += w & 0xffffu; t1 += w >> 16; g0 += pg.x; g1 += pg.y;
+            } else {
+                const ulonglong2 pt = ld2(base + k * 2 * n + j), pg = ld2(base + k * 2 * n + n + j);
+                t0 += pt.x; t1 += pt.y; g0 += pg.x; g1 += pg.y;
+            }
         }
-        const u64 r0 = dec_finish_one(t0, pg.x % D.gamma, mask32, D), r1 = dec_finish_one(t1, pg.y % D.gamma, mask32, D);
+        const u64 r0 = dec_finish_one(t0, g0 % D.gamma, mask32, D), r1 = dec_finish_one(t1, g1 % D.gamma, mask32, D);
         if (OUT16) reinterpret_cast<u32 *>(reinterpret_cast<unsigned short *>(out) + k * out_stride)[j >> 1] = (u32)r0 | ((u32)r1 << 16);
         else st2(reinterpret_cast<u64 *>(out) + k * out_stride + j, r0, r1);
     }

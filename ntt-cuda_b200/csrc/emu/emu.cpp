@@ -396,7 +396,7 @@ EXPORT int emu_bfv_sharded(int op, unsigned n, unsigned r, const u64 *q, const u
         ring_ntt(R, true, c_shard + c1_off, batch * count, count, count, item);
         ew3(batch, 1, [&] { k_decrypt_partial<false>(c_shard, item, c1_off, part, n, batch, first, count, D, Lglob); });
     } else {
-        ew3(batch, 1, [&] { k_decrypt_finish<false, false>(part, out, (size_t)n, n, batch, D); });
+        ew3(batch, 1, [&] { k_decrypt_finish<false, false>(part, out, (size_t)n, n, batch, D, 1, 0); });
     }
     return 0;
 }
@@ -518,10 +518,10 @@ EXPORT int emu_dec_blocks(int op, unsigned n, unsigned r, const u64 *q, const u6
         if (packed) ew3(items, 1, [&] { k_decrypt_partial<true>(c_shard, item, c1_off, part, n, items, first, count, D, Lglob); });
         else ew3(items, 1, [&] { k_decrypt_partial<false>(c_shard, item, c1_off, part, n, items, first, count, D, Lglob); });
     } else if (op == 1) {
-        if (packed && out16) ew3(items, 1, [&] { k_decrypt_finish<true, true>(part, out, (size_t)n, n, items, D); });
-        else if (packed) ew3(items, 1, [&] { k_decrypt_finish<true, false>(part, out, (size_t)n, n, items, D); });
-        else if (out16) ew3(items, 1, [&] { k_decrypt_finish<false, true>(part, out, (size_t)n, n, items, D); });
-        else ew3(items, 1, [&] { k_decrypt_finish<false, false>(part, out, (size_t)n, n, items, D); });
+        if (packed && out16) ew3(items, 1, [&] { k_decrypt_finish<true, true>(part, out, (size_t)n, n, items, D, 1, 0); });
+        else if (packed) ew3(items, 1, [&] { k_decrypt_finish<true, false>(part, out, (size_t)n, n, items, D, 1, 0); });
+        else if (out16) ew3(items, 1, [&] { k_decrypt_finish<false, true>(part, out, (size_t)n, n, items, D, 1, 0); });
+        else ew3(items, 1, [&] { k_decrypt_finish<false, false>(part, out, (size_t)n, n, items, D, 1, 0); });
     } else if (op == 2) {
         ew([&] { k_expand16((const unsigned short *)part, (u64 *)out, (size_t)items * n); });
     } else {

@@ -38,6 +38,7 @@ struct NcclApi {
     ncclResult_t (*ReduceScatter)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Reduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -60,10 +61,10 @@ NcclApi &nccl()
     if (!api.handle) return api;
 #define NTTB200_SYM(f) *(void **)(&api.f) = dlsym(api.handle, "nccl" #f)
     NTTB200_SYM(GetUniqueId); NTTB200_SYM(CommInitRank); NTTB200_SYM(CommDestroy); NTTB200_SYM(CommCount); NTTB200_SYM(CommUserRank);
-    NTTB200_SYM(AllGather); NTTB200_SYM(ReduceScatter); NTTB200_SYM(Reduce); NTTB200_SYM(Broadcast); NTTB200_SYM(GroupStart); NTTB200_SYM(GroupEnd);
+    NTTB200_SYM(AllGather); NTTB200_SYM(ReduceScatter); NTTB200_SYM(Reduce); NTTB200_SYM(Broadcast); NTTB200_SYM(AllReduce); NTTB200_SYM(GroupStart); NTTB200_SYM(GroupEnd);
     NTTB200_SYM(GetErrorString);
 #undef NTTB200_SYM
-    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.ReduceScatter && api.Reduce && api.Broadcast && api.GroupStart &&
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.ReduceScatter && api.Reduce && api.Broadcast && api.AllReduce && api.GroupStart &&
              api.GroupEnd;
     return api;
 }
@@ -89,14 +90,31 @@ struct nttb200_shard_state {
     std::vector<cudaEvent_t> ev;
     unsigned char *buf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t cap[6] = {0, 0, 0, 0, 0, 0};
-    int mode = 0;                                 // 0: per-block ncclReduce to the owner; 1: chunked ncclReduceScatter
+    int mode = 2;                                 // 2: peer-to-peer deposit of the partial sums at the block's owner (falls back to 0 when
+                                                  //    CUDA IPC is unavailable); 0: per-block ncclReduce to the owner; 1: chunked ncclReduceScatter
     unsigned chunks = 4;
+    // mode 2: every rank's slots buffer [world][items per block][pw] is mapped into every other rank (CUDA IPC)
+    u64 *slots = nullptr;                         // this rank's own buffer (cudaMalloc)
+    size_t slots_words = 0;
+    std::vector<u64 *> peer;                      // peer[g] = rank g's slots buffer as mapped here (peer[rank] = slots)
+    int p2p_failed = 0;
+    int *flag = nullptr;                          // 1-int device buffer of the barrier all-reduce
 };
 enum { kBufUb = 0, kBufEs, kBufCl, kBufPartial, kBufRecv, kBufPlain };
 
+static void p2p_release(nttb200_shard_state *s)
+{
+    for (size_t g = 0; g < s->peer.size(); g++)
+        if (s->peer[g] && s->peer[g] != s->slots) cudaIpcCloseMemHandle(s->peer[g]);
+    s->peer.clear();
+    if (s->slots) cudaFree(s->slots);
+    s->slots = nullptr; s->slots_words = 0;
+}
 void nttb200_shard_state_destroy(nttb200_shard_state *s)
 {
     if (!s) return;
+    p2p_release(s);
+    if (s->flag) cudaFree(s->flag);
     for (auto e : s->ev) cudaEventDestroy(e);
     for (auto p : s->buf) if (p) cudaFree(p);
     if (s->cs) cudaStreamDestroy(s->cs);
@@ -211,7 +229,7 @@ int nttb200_comm_rank(const nttb200_comm *c) { return c ? c->rank : -1; }
 
 int nttb200_bfv_shard_config(nttb200_bfv *b, int mode, unsigned chunks)
 {
-    if (!b || mode < 0 || mode > 1) return NTTB200_EINVAL;
+    if (!b || mode < 0 || mode > 2) return NTTB200_EINVAL;
     nttb200_shard_state *s;
     TRY(shard_state(b, &s, 0));
     s->mode = mode;
@@ -322,6 +340,53 @@ int nttb200_bfv_encrypt_sharded(nttb200_bfv *b, nttb200_comm *comm, nttb200_u64 
     return 0;
 }
 
+// mode 2 set-up (collective: every rank calls it with the same size): allocate this rank's slots buffer, exchange CUDA IPC handles
+// through an NCCL all-gather, map every peer's buffer.  Any failure (IPC unsupported in this environment) disables the mode on ALL
+// ranks -- the outcome is agreed through an all-reduce so that no rank is left waiting in a different protocol.
+static int p2p_setup(nttb200_bfv *b, nttb200_shard_state *s, nttb200_comm *comm, size_t words)
+{
+    (void)b;
+    const unsigned G = (unsigned)comm->world, g = (unsigned)comm->rank;
+    if (!s->flag) { NTTB200_CHECK(cudaMalloc(&s->flag, 2 * sizeof(int))); NTTB200_CHECK(cudaMemset(s->flag, 0, 2 * sizeof(int))); }
+    if (s->slots_words >= words && s->peer.size() == G) return 0;
+    NTTB200_CHECK(cudaStreamSynchronize(s->cs));
+    p2p_release(s);
+    int bad = 0;
+    if (cudaMalloc(&s->slots, words * 8) != cudaSuccess) { bad = 1; s->slots = nullptr; cudaGetLastError(); }
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof mine);
+    if (!bad && cudaIpcGetMemHandle(&mine, s->slots) != cudaSuccess) { bad = 1; cudaGetLastError(); }
+    unsigned char *dev = nullptr;
+    NTTB200_CHECK(cudaMalloc(&dev, (size_t)G * sizeof mine));
+    NTTB200_CHECK(cudaMemcpy(dev + (size_t)g * sizeof mine, &mine, sizeof mine, cudaMemcpyHostToDevice));
+    NCCLCHECK(nccl().AllGather(dev + (size_t)g * sizeof mine, dev, sizeof mine, ncclInt8, comm->comm, s->cs));
+    NTTB200_CHECK(cudaStreamSynchronize(s->cs));
+    std::vector<cudaIpcMemHandle_t> all(G);
+    NTTB200_CHECK(cudaMemcpy(all.data(), dev, (size_t)G * sizeof mine, cudaMemcpyDeviceToHost));
+    cudaFree(dev);
+    s->peer.assign(G, nullptr);
+    for (unsigned k = 0; k < G && !bad; k++) {
+        if (k == g) { s->peer[k] = s->slots; continue; }
+        void *p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, all[k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { bad = 1; cudaGetLastError(); break; }
+        s->peer[k] = (u64 *)p;
+    }
+    // agree on the outcome
+    int h = bad;
+    NTTB200_CHECK(cudaMemcpy(s->flag + 1, &h, sizeof h, cudaMemcpyHostToDevice));
+    NCCLCHECK(nccl().AllReduce(s->flag + 1, s->flag + 1, 1, ncclInt32, ncclSum, comm->comm, s->cs));
+    NTTB200_CHECK(cudaStreamSynchronize(s->cs));
+    NTTB200_CHECK(cudaMemcpy(&h, s->flag + 1, sizeof h, cudaMemcpyDeviceToHost));
+    if (h) {
+        p2p_release(s);
+        s->p2p_failed = 1;
+        if (const char *e = getenv("NTTB200_DEBUG")) if (e[0] == '1') fprintf(stderr, "nttb200: CUDA IPC unavailable on %d rank(s): sharded decryption falls back to ncclReduce\n", h);
+        return 0;
+    }
+    s->slots_words = words;
+    return 0;
+}
+
 // ---- limb-sharded decryption --------------------------------------------------------------------------------------------------------
 // c_shard is overwritten (as c1 is in the reference); m_out[batch][n] is complete on EVERY rank when the call's stream work is done.
 int nttb200_bfv_decrypt_sharded(nttb200_bfv *b, nttb200_comm *comm, nttb200_u64 *m_out, nttb200_u64 *c_shard, unsigned batch, void *stream)
@@ -355,7 +420,37 @@ int nttb200_bfv_decrypt_sharded(nttb200_bfv *b, nttb200_comm *comm, nttb200_u64 
         TRY(dec_finish(b, m_out, 0, partial, packed, batch, st));
         return 0;
     }
-    if (s->mode == 0) {
+    if (s->mode == 2 && !s->p2p_failed) {
+        // Peer-to-peer: the partial-sum kernel of block j writes straight into slot `rank` of the buffer of the block's OWNER (rank j),
+        // mapped here through CUDA IPC -- NVLink stores issued by the kernel that produces the sums, no collective kernel competing for
+        // SMs, no staging copy.  A 4-byte all-reduce per block is the "everybody has deposited block j" barrier; the owner then sums the
+        // world slots while rounding (k_decrypt_finish) and broadcasts the block's 16-bit plaintext words.
+        const int rc = p2p_setup(b, s, comm, (size_t)batch * pw);
+        if (rc) return rc;
+    }
+    if (s->mode == 2 && !s->p2p_failed) {
+        for (unsigned j = 0; j < G; j++) {
+            const unsigned cnt = blk[j].limb_count;
+            u64 *dst = s->peer[j] + (size_t)g * per * pw;                                   // my slot at the owner of block j
+            if (cnt) TRY(dec_partial(b, P, dst, packed, c_shard + blk[j].offset, cnt, blk[j].first_limb, cnt, per));
+            else NTTB200_CHECK(cudaMemsetAsync(dst, 0, (size_t)per * pw * 8, st));
+            NTTB200_CHECK(cudaEventRecord(s->ev[evi], st));
+            NTTB200_CHECK(cudaStreamWaitEvent(s->cs, s->ev[evi], 0));
+            evi++;
+            NCCLCHECK(nccl().AllReduce(s->flag, s->flag, 1, ncclInt32, ncclSum, comm->comm, s->cs));      // barrier: all deposits of block j are complete
+            const size_t it = (size_t)j * per;
+            if (j == g) {
+                if (out16) TRY(dec_finish(b, plain + it * n, 1, s->slots, packed, per, s->cs, G, (size_t)per * pw));
+                else TRY(dec_finish(b, m_out + it * n, 0, s->slots, packed, per, s->cs, G, (size_t)per * pw));
+            }
+            if (out16) {
+                NCCLCHECK(nccl().Broadcast(plain + it * n, plain + it * n, (size_t)per * n * 2, ncclInt8, (int)j, comm->comm, s->cs));
+                TRY(dec_expand16(plain + it * n, m_out + it * n, (size_t)per * n, s->cs));
+            } else {
+                NCCLCHECK(nccl().Broadcast(m_out + it * n, m_out + it * n, (size_t)per * n, ncclUint64, (int)j, comm->comm, s->cs));
+            }
+        }
+    } else if (s->mode == 0 || s->mode == 2) {
         // Block by block, each in `chunks` pieces: transforms + partial sums of a piece on the caller's stream; on the comm stream,
         // behind them, the piece's sums go to the block's owner (ncclReduce), the owner rounds it, and when a block is complete its
         // owner broadcasts the 16-bit plaintext words -- so the only exposed communication is the LAST piece's reduce + broadcast.
