@@ -307,6 +307,8 @@ NTTB200_API int nttb200_shard_plan(unsigned rp, unsigned n, unsigned batch, unsi
 NTTB200_API int nttb200_comm_unique_id(unsigned char id[128]);
 NTTB200_API int nttb200_comm_create(nttb200_comm **comm, const unsigned char id[128], int world, int rank);
 NTTB200_API int nttb200_comm_adopt(nttb200_comm **comm, void *nccl_comm, int world, int rank);
+/* profiling only: rank `rank` of a world of `world` with every collective skipped (one rank's compute share; results meaningless) */
+NTTB200_API int nttb200_comm_fake(nttb200_comm **comm, int world, int rank);
 NTTB200_API void nttb200_comm_destroy(nttb200_comm *comm);
 NTTB200_API int nttb200_comm_world(const nttb200_comm *comm);
 NTTB200_API int nttb200_comm_rank(const nttb200_comm *comm);

@@ -14,6 +14,7 @@
 #include "table_kernels.cuh"
 #include "bfv_internal.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -367,9 +368,11 @@ int dec_finish(const nttb200_bfv *b, void *out, int out16, const u64 *partial_su
     KCHECK();
     return 0;
 }
-int dec_expand16(const unsigned short *in, u64 *out, size_t total, cudaStream_t st)
+int dec_expand16(const unsigned short *in, u64 *out, size_t total, cudaStream_t st, unsigned blocks, size_t out_block_stride)
 {
-    k_expand16<<<grid_for(total / 2, 256), 256, 0, st>>>(in, out, total);
+    dim3 g = grid_for(total / 2, 256);
+    if (blocks > 1) { g.x = std::max(1u, g.x / blocks); g.y = blocks; }
+    k_expand16<<<g, 256, 0, st>>>(in, out, total, out_block_stride);
     KCHECK();
     return 0;
 }

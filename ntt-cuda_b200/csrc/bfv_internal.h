@@ -74,7 +74,7 @@ int dec_partial(const nttb200_bfv *b, const Pipe &P, u64 *partial, int packed, u
                 unsigned items);
 int dec_finish(const nttb200_bfv *b, void *out, int out16, const u64 *partial_sum, int packed, unsigned items, cudaStream_t st, unsigned slots = 1,
                size_t slot_stride = 0);
-int dec_expand16(const unsigned short *in, u64 *out, size_t total, cudaStream_t st);
+int dec_expand16(const unsigned short *in, u64 *out, size_t total, cudaStream_t st, unsigned blocks = 1, size_t out_block_stride = 0);
 int enc_sample(const nttb200_bfv *b, unsigned char *ub, signed char *es8, unsigned items, u64 nonce0, int want_u, int want_e, cudaStream_t st);
 SalsaKey bfv_salsa_key(const nttb200_bfv *b);
 dim3 grid_for(size_t total, int threads);

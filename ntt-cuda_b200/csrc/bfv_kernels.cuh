@@ -629,12 +629,15 @@ NTT_KERNEL void k_decrypt_finish(const u64 *part_sum, void *out, size_t out_stri
         else st2(reinterpret_cast<u64 *>(out) + k * out_stride + j, r0, r1);
     }
 }
-// 16-bit plaintext words -> the u64 coefficients of the reference layout
-NTT_KERNEL void k_expand16(const unsigned short *in, u64 *out, size_t total)
+// 16-bit plaintext words -> the u64 coefficients of the reference layout.  blocks > 1 (grid y): block b reads `total` words at
+// in + b * total and writes them at out + b * out_block_stride (the chunk-major staging of the sharded decryption back to item order).
+NTT_KERNEL void k_expand16(const unsigned short *in, u64 *out, size_t total, size_t out_block_stride)
 {
+    const unsigned short *src = in + (size_t)blockIdx.y * total;
+    u64 *dst = out + (size_t)blockIdx.y * out_block_stride;
     NTT_GRID_STRIDE(i, total / 2) {
-        const u32 w = reinterpret_cast<const u32 *>(in)[i];
-        st2(out + 2 * i, (u64)(w & 0xffffu), (u64)(w >> 16));
+        const u32 w = reinterpret_cast<const u32 *>(src)[i];
+        st2(dst + 2 * i, (u64)(w & 0xffffu), (u64)(w >> 16));
     }
 }
 

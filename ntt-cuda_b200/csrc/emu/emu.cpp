@@ -523,7 +523,7 @@ EXPORT int emu_dec_blocks(int op, unsigned n, unsigned r, const u64 *q, const u6
         else if (out16) ew3(items, 1, [&] { k_decrypt_finish<false, true>(part, out, (size_t)n, n, items, D, 1, 0); });
         else ew3(items, 1, [&] { k_decrypt_finish<false, false>(part, out, (size_t)n, n, items, D, 1, 0); });
     } else if (op == 2) {
-        ew([&] { k_expand16((const unsigned short *)part, (u64 *)out, (size_t)items * n); });
+        ew([&] { k_expand16((const unsigned short *)part, (u64 *)out, (size_t)items * n, 0); });
     } else {
         return 1;
     }

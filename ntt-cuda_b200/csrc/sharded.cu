@@ -76,12 +76,15 @@ int nccl_fail(ncclResult_t r, const char *file, int line)
 }
 }  // namespace
 #define NCCLCHECK(x) do { ncclResult_t r__ = (x); if (r__ != ncclSuccess) return nccl_fail(r__, __FILE__, __LINE__); } while (0)
+// collectives of the sharded calls: skipped for a fake communicator (compute-only profiling of one rank's share)
+#define COLL(x) do { if (!comm->fake) NCCLCHECK(x); } while (0)
 #define TRY(x) do { int r__ = (x); if (r__) return nttb200_trace_error(r__, __FILE__, __LINE__); } while (0)
 
 struct nttb200_comm {
     ncclComm_t comm = nullptr;
     int world = 1, rank = 0;
     bool owned = false;
+    bool fake = false;        // profiling only (nttb200_comm_fake): one rank's share of the work with every collective skipped
 };
 
 // scratch + second stream of the sharded entry points, owned by the BFV context (grow-only: warm up before graph capture)
@@ -93,28 +96,33 @@ struct nttb200_shard_state {
     int mode = 2;                                 // 2: peer-to-peer deposit of the partial sums at the block's owner (falls back to 0 when
                                                   //    CUDA IPC is unavailable); 0: per-block ncclReduce to the owner; 1: chunked ncclReduceScatter
     unsigned chunks = 4;
-    // mode 2: every rank's slots buffer [world][items per block][pw] is mapped into every other rank (CUDA IPC)
-    u64 *slots = nullptr;                         // this rank's own buffer (cudaMalloc)
-    size_t slots_words = 0;
-    std::vector<u64 *> peer;                      // peer[g] = rank g's slots buffer as mapped here (peer[rank] = slots)
+    // symmetric buffers: one cudaMalloc per rank, mapped into every other rank through CUDA IPC (peer stores / copy-engine pushes)
+    struct Sym {
+        unsigned char *local = nullptr;
+        size_t bytes = 0;
+        std::vector<unsigned char *> peer;        // peer[g] = rank g's buffer as mapped here (peer[rank] = local)
+    } sym[3];
     int p2p_failed = 0;
-    int *flag = nullptr;                          // 1-int device buffer of the barrier all-reduce
+    int *flag = nullptr;                          // device ints of the barrier / agreement all-reduces
+    cudaStream_t st2 = nullptr;                   // second compute stream: independent tiles overlap their launch tails
 };
+enum { kSymSlots = 0, kSymCl, kSymEs };
 enum { kBufUb = 0, kBufEs, kBufCl, kBufPartial, kBufRecv, kBufPlain };
 
-static void p2p_release(nttb200_shard_state *s)
+static void sym_release(nttb200_shard_state::Sym &y)
 {
-    for (size_t g = 0; g < s->peer.size(); g++)
-        if (s->peer[g] && s->peer[g] != s->slots) cudaIpcCloseMemHandle(s->peer[g]);
-    s->peer.clear();
-    if (s->slots) cudaFree(s->slots);
-    s->slots = nullptr; s->slots_words = 0;
+    for (size_t g = 0; g < y.peer.size(); g++)
+        if (y.peer[g] && y.peer[g] != y.local) cudaIpcCloseMemHandle(y.peer[g]);
+    y.peer.clear();
+    if (y.local) cudaFree(y.local);
+    y.local = nullptr; y.bytes = 0;
 }
 void nttb200_shard_state_destroy(nttb200_shard_state *s)
 {
     if (!s) return;
-    p2p_release(s);
+    for (auto &y : s->sym) sym_release(y);
     if (s->flag) cudaFree(s->flag);
+    if (s->st2) cudaStreamDestroy(s->st2);
     for (auto e : s->ev) cudaEventDestroy(e);
     for (auto p : s->buf) if (p) cudaFree(p);
     if (s->cs) cudaStreamDestroy(s->cs);
@@ -126,7 +134,10 @@ static int shard_state(nttb200_bfv *b, nttb200_shard_state **out, size_t events)
         b->shard = new nttb200_shard_state();
         if (const char *e = getenv("NTTB200_SHARD_MODE")) b->shard->mode = atoi(e);
         if (const char *e = getenv("NTTB200_SHARD_CHUNKS")) b->shard->chunks = (unsigned)atoi(e) ? (unsigned)atoi(e) : 1u;
-        NTTB200_CHECK(cudaStreamCreateWithFlags(&b->shard->cs, cudaStreamNonBlocking));
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);          // collectives / rounding of finished pieces go ahead of queued transforms
+        NTTB200_CHECK(cudaStreamCreateWithPriority(&b->shard->cs, cudaStreamNonBlocking, hi));
+        NTTB200_CHECK(cudaStreamCreateWithFlags(&b->shard->st2, cudaStreamNonBlocking));
     }
     nttb200_shard_state *s = b->shard;
     while (s->ev.size() < events) {
@@ -167,6 +178,55 @@ static void plan_blocks(unsigned rp, unsigned n, unsigned batch, unsigned world,
     }
     if (words) *words = off;
 }
+
+// Symmetric-buffer set-up (collective: every rank calls it with the same index and size): allocate this rank's buffer, exchange
+// CUDA IPC handles through an NCCL all-gather, map every peer's buffer.  Any failure (IPC unsupported in this environment) disables
+// the peer-to-peer paths on ALL ranks -- the outcome is agreed through an all-reduce so that no rank is left in a different protocol.
+static int sym_setup(nttb200_shard_state *s, nttb200_comm *comm, int which, size_t bytes)
+{
+    const unsigned G = (unsigned)comm->world, g = (unsigned)comm->rank;
+    nttb200_shard_state::Sym &y = s->sym[which];
+    if (!s->flag) { NTTB200_CHECK(cudaMalloc(&s->flag, 4 * sizeof(int))); NTTB200_CHECK(cudaMemset(s->flag, 0, 4 * sizeof(int))); }
+    if (s->p2p_failed) return 0;
+    if (y.bytes >= bytes && y.peer.size() == G) return 0;
+    NTTB200_CHECK(cudaStreamSynchronize(s->cs));
+    sym_release(y);
+    int bad = 0;
+    if (cudaMalloc(&y.local, bytes) != cudaSuccess) { bad = 1; y.local = nullptr; cudaGetLastError(); }
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof mine);
+    if (!bad && cudaIpcGetMemHandle(&mine, y.local) != cudaSuccess) { bad = 1; cudaGetLastError(); }
+    unsigned char *dev = nullptr;
+    NTTB200_CHECK(cudaMalloc(&dev, (size_t)G * sizeof mine));
+    NTTB200_CHECK(cudaMemcpy(dev + (size_t)g * sizeof mine, &mine, sizeof mine, cudaMemcpyHostToDevice));
+    NCCLCHECK(nccl().AllGather(dev + (size_t)g * sizeof mine, dev, sizeof mine, ncclInt8, comm->comm, s->cs));
+    NTTB200_CHECK(cudaStreamSynchronize(s->cs));
+    std::vector<cudaIpcMemHandle_t> all(G);
+    NTTB200_CHECK(cudaMemcpy(all.data(), dev, (size_t)G * sizeof mine, cudaMemcpyDeviceToHost));
+    cudaFree(dev);
+    y.peer.assign(G, nullptr);
+    for (unsigned k = 0; k < G && !bad; k++) {
+        if (k == g) { y.peer[k] = y.local; continue; }
+        void *p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, all[k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { bad = 1; cudaGetLastError(); break; }
+        y.peer[k] = (unsigned char *)p;
+    }
+    int h = bad;                                      // agree on the outcome
+    NTTB200_CHECK(cudaMemcpy(s->flag + 1, &h, sizeof h, cudaMemcpyHostToDevice));
+    NCCLCHECK(nccl().AllReduce(s->flag + 1, s->flag + 1, 1, ncclInt32, ncclSum, comm->comm, s->cs));
+    NTTB200_CHECK(cudaStreamSynchronize(s->cs));
+    NTTB200_CHECK(cudaMemcpy(&h, s->flag + 1, sizeof h, cudaMemcpyDeviceToHost));
+    if (h) {
+        for (auto &z : s->sym) sym_release(z);
+        s->p2p_failed = 1;
+        if (const char *e = getenv("NTTB200_DEBUG")) if (e[0] == '1') fprintf(stderr, "nttb200: CUDA IPC unavailable on %d rank(s): the sharded calls fall back to NCCL collectives\n", h);
+        return 0;
+    }
+    y.bytes = bytes;
+    return 0;
+}
+// "every rank has reached this point of its stream": a 4-byte all-reduce
+#define BARRIER() COLL(nccl().AllReduce(s->flag, s->flag, 1, ncclInt32, ncclSum, comm->comm, s->cs))
 
 extern "C" {
 
@@ -218,6 +278,15 @@ int nttb200_comm_adopt(nttb200_comm **out, void *nccl_comm, int world, int rank)
     *out = c;
     return 0;
 }
+// profiling only: behaves as rank `rank` of `world` but skips every collective (results are meaningless; timings are one rank's compute)
+int nttb200_comm_fake(nttb200_comm **out, int world, int rank)
+{
+    if (!out || world < 1 || rank < 0 || rank >= world) return NTTB200_EINVAL;
+    nttb200_comm *c = new nttb200_comm();
+    c->world = world; c->rank = rank; c->fake = true;
+    *out = c;
+    return 0;
+}
 void nttb200_comm_destroy(nttb200_comm *c)
 {
     if (!c) return;
@@ -229,7 +298,7 @@ int nttb200_comm_rank(const nttb200_comm *c) { return c ? c->rank : -1; }
 
 int nttb200_bfv_shard_config(nttb200_bfv *b, int mode, unsigned chunks)
 {
-    if (!b || mode < 0 || mode > 2) return NTTB200_EINVAL;
+    if (!b || mode < 0 || mode > 3) return NTTB200_EINVAL;
     nttb200_shard_state *s;
     TRY(shard_state(b, &s, 0));
     s->mode = mode;
@@ -287,6 +356,8 @@ int nttb200_bfv_decrypt_finish_tile(nttb200_bfv *b, void *m_out, int out16, cons
 
 // ---- limb-sharded encryption --------------------------------------------------------------------------------------------------------
 // Every rank passes the same m[batch][n] and nonce0; c_shard receives the rank's (limb, block) tiles.  The loaded public key is used.
+// Independent tiles alternate between the caller's stream and a second compute stream so that the launch tails of one tile's kernels
+// overlap the next tile's (a tile is 512 items x 1-3 limbs at 8 GPUs: 9-28 waves per kernel).
 int nttb200_bfv_encrypt_sharded(nttb200_bfv *b, nttb200_comm *comm, nttb200_u64 *c_shard, const nttb200_u64 *m, unsigned batch, nttb200_u64 nonce0,
                                 void *stream)
 {
@@ -296,18 +367,28 @@ int nttb200_bfv_encrypt_sharded(nttb200_bfv *b, nttb200_comm *comm, nttb200_u64 
     if (per > 65535) return NTTB200_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     nttb200_shard_state *s;
-    TRY(shard_state(b, &s, 4));
+    TRY(shard_state(b, &s, 8));
     std::vector<nttb200_shard_block> blk(G);
     plan_blocks(r - 1, n, batch, G, g, blk.data(), nullptr);
     unsigned char *ub; signed char *es; u64 *cl;
     TRY(shard_buf(s, kBufUb, (size_t)batch * n, (void **)&ub));
-    TRY(shard_buf(s, kBufEs, (size_t)batch * 2 * n, (void **)&es));
-    TRY(shard_buf(s, kBufCl, (size_t)batch * 2 * n * 8, (void **)&cl));
-    Pipe P = pipe_from_bfv(b, st);
+    // finished dropped limbs cl[batch][2][n] and signed-byte draws es[batch][2][n]: symmetric buffers when CUDA IPC is available (every
+    // rank PUSHES its block into the peers' buffers with copy-engine copies: no collective kernel takes SMs from the transforms),
+    // plain scratch + ncclAllGather otherwise
+    const bool want_p2p = G > 1 && !comm->fake && s->mode >= 2;
+    if (want_p2p) { TRY(sym_setup(s, comm, kSymCl, (size_t)batch * 2 * n * 8)); TRY(sym_setup(s, comm, kSymEs, (size_t)batch * 2 * n)); }
+    const bool p2p = want_p2p && !s->p2p_failed;
+    if (p2p) { cl = (u64 *)s->sym[kSymCl].local; es = (signed char *)s->sym[kSymEs].local; }
+    else { TRY(shard_buf(s, kBufEs, (size_t)batch * 2 * n, (void **)&es)); TRY(shard_buf(s, kBufCl, (size_t)batch * 2 * n * 8, (void **)&cl)); }
+    Pipe P = pipe_from_bfv(b, st), P2 = pipe_from_bfv(b, s->st2);
     const size_t own = (size_t)g * per;
-    // scratch reuse across calls: the previous call's collectives (comm stream) must be done before this call overwrites their buffers
-    NTTB200_CHECK(cudaEventRecord(s->ev[0], s->cs));
-    NTTB200_CHECK(cudaStreamWaitEvent(st, s->ev[0], 0));
+    // the previous call's exchange (comm stream) must be done before this call overwrites its buffers; with one-sided pushes every
+    // rank must also have finished READING the previous call's cl / es before anybody overwrites them: a barrier at entry
+    NTTB200_CHECK(cudaEventRecord(s->ev[0], st));
+    NTTB200_CHECK(cudaStreamWaitEvent(s->cs, s->ev[0], 0));
+    if (p2p) BARRIER();
+    NTTB200_CHECK(cudaEventRecord(s->ev[1], s->cs));
+    NTTB200_CHECK(cudaStreamWaitEvent(st, s->ev[1], 0));
     // 1. randomness: u bytes of every item (every rank transforms u on its limbs), gaussian draws of the block this rank finishes
     TRY(enc_sample(b, ub, nullptr, batch, nonce0, 1, 0, st));
     TRY(enc_sample(b, nullptr, es + own * 2 * n, per, nonce0 + own, 0, 1, st));
@@ -315,75 +396,41 @@ int nttb200_bfv_encrypt_sharded(nttb200_bfv *b, nttb200_comm *comm, nttb200_u64 
     u64 *cl_own = cl + own * 2 * n;
     TRY(enc_front(b, P, cl_own, 1, r - 1, 1, per, ub + own * n));
     TRY(enc_finish_last(b, P, cl_own, (size_t)2 * n, (size_t)n, es + own * 2 * n, per));
-    // 3. all-gather of the finished dropped limbs and the draws, on the comm stream, under the transforms of step 4
+    NTTB200_CHECK(cudaEventRecord(s->ev[2], st));
+    // 3. exchange of the finished dropped limbs and the draws, on the comm stream, under the transforms of step 4
     if (G > 1) {
-        NTTB200_CHECK(cudaEventRecord(s->ev[1], st));
-        NTTB200_CHECK(cudaStreamWaitEvent(s->cs, s->ev[1], 0));
-        NCCLCHECK(nccl().GroupStart());
-        NCCLCHECK(nccl().AllGather(cl_own, cl, (size_t)per * 2 * n, ncclUint64, comm->comm, s->cs));
-        NCCLCHECK(nccl().AllGather(es + own * 2 * n, es, (size_t)per * 2 * n, ncclInt8, comm->comm, s->cs));
-        NCCLCHECK(nccl().GroupEnd());
-        NTTB200_CHECK(cudaEventRecord(s->ev[2], s->cs));
+        NTTB200_CHECK(cudaStreamWaitEvent(s->cs, s->ev[2], 0));
+        if (p2p) {
+            for (unsigned tau = 1; tau < G; tau++) {          // rotated order: one incoming copy per rank at a time
+                const unsigned k = (g + tau) % G;
+                NTTB200_CHECK(cudaMemcpyAsync((u64 *)s->sym[kSymCl].peer[k] + own * 2 * n, cl_own, (size_t)per * 2 * n * 8, cudaMemcpyDeviceToDevice, s->cs));
+                NTTB200_CHECK(cudaMemcpyAsync(s->sym[kSymEs].peer[k] + own * 2 * n, es + own * 2 * n, (size_t)per * 2 * n, cudaMemcpyDeviceToDevice, s->cs));
+            }
+            BARRIER();                                         // every push has landed everywhere
+        } else {
+            COLL(nccl().GroupStart());
+            COLL(nccl().AllGather(cl_own, cl, (size_t)per * 2 * n, ncclUint64, comm->comm, s->cs));
+            COLL(nccl().AllGather(es + own * 2 * n, es, (size_t)per * 2 * n, ncclInt8, comm->comm, s->cs));
+            COLL(nccl().GroupEnd());
+        }
+        NTTB200_CHECK(cudaEventRecord(s->ev[3], s->cs));
     }
-    // 4. forward transform of u, (.) pk, contiguous inverse pass on the owned (limb, block) tiles
+    // 4. forward transform of u, (.) pk, contiguous inverse pass on the owned (limb, block) tiles; tiles alternate between two streams
+    NTTB200_CHECK(cudaStreamWaitEvent(s->st2, s->ev[2], 0));   // ub is ready; the second stream joins here
     for (unsigned j = 0; j < G; j++)
         if (blk[j].limb_count)
-            TRY(enc_front(b, P, c_shard + blk[j].offset, blk[j].limb_count, blk[j].first_limb, blk[j].limb_count, per, ub + (size_t)blk[j].first_item * n));
-    if (G > 1) NTTB200_CHECK(cudaStreamWaitEvent(st, s->ev[2], 0));
-    // 5. last inverse kernel with mod-switch + Delta*m in its store
+            TRY(enc_front(b, (j & 1) ? P2 : P, c_shard + blk[j].offset, blk[j].limb_count, blk[j].first_limb, blk[j].limb_count, per,
+                          ub + (size_t)blk[j].first_item * n));
+    if (G > 1) { NTTB200_CHECK(cudaStreamWaitEvent(st, s->ev[3], 0)); NTTB200_CHECK(cudaStreamWaitEvent(s->st2, s->ev[3], 0)); }
+    // 5. last inverse kernel + mod-switch + Delta*m (same stream as the tile's front: no cross-stream dependency)
     for (unsigned j = 0; j < G; j++)
         if (blk[j].limb_count) {
             const size_t it = blk[j].first_item;
-            TRY(enc_finish_limbs(b, P, c_shard + blk[j].offset, blk[j].limb_count, blk[j].first_limb, blk[j].limb_count, per, cl + it * 2 * n,
+            TRY(enc_finish_limbs(b, (j & 1) ? P2 : P, c_shard + blk[j].offset, blk[j].limb_count, blk[j].first_limb, blk[j].limb_count, per, cl + it * 2 * n,
                                  (size_t)2 * n, (size_t)n, es + it * 2 * n, m + it * n, (size_t)n));
         }
-    return 0;
-}
-
-// mode 2 set-up (collective: every rank calls it with the same size): allocate this rank's slots buffer, exchange CUDA IPC handles
-// through an NCCL all-gather, map every peer's buffer.  Any failure (IPC unsupported in this environment) disables the mode on ALL
-// ranks -- the outcome is agreed through an all-reduce so that no rank is left waiting in a different protocol.
-static int p2p_setup(nttb200_bfv *b, nttb200_shard_state *s, nttb200_comm *comm, size_t words)
-{
-    (void)b;
-    const unsigned G = (unsigned)comm->world, g = (unsigned)comm->rank;
-    if (!s->flag) { NTTB200_CHECK(cudaMalloc(&s->flag, 2 * sizeof(int))); NTTB200_CHECK(cudaMemset(s->flag, 0, 2 * sizeof(int))); }
-    if (s->slots_words >= words && s->peer.size() == G) return 0;
-    NTTB200_CHECK(cudaStreamSynchronize(s->cs));
-    p2p_release(s);
-    int bad = 0;
-    if (cudaMalloc(&s->slots, words * 8) != cudaSuccess) { bad = 1; s->slots = nullptr; cudaGetLastError(); }
-    cudaIpcMemHandle_t mine;
-    memset(&mine, 0, sizeof mine);
-    if (!bad && cudaIpcGetMemHandle(&mine, s->slots) != cudaSuccess) { bad = 1; cudaGetLastError(); }
-    unsigned char *dev = nullptr;
-    NTTB200_CHECK(cudaMalloc(&dev, (size_t)G * sizeof mine));
-    NTTB200_CHECK(cudaMemcpy(dev + (size_t)g * sizeof mine, &mine, sizeof mine, cudaMemcpyHostToDevice));
-    NCCLCHECK(nccl().AllGather(dev + (size_t)g * sizeof mine, dev, sizeof mine, ncclInt8, comm->comm, s->cs));
-    NTTB200_CHECK(cudaStreamSynchronize(s->cs));
-    std::vector<cudaIpcMemHandle_t> all(G);
-    NTTB200_CHECK(cudaMemcpy(all.data(), dev, (size_t)G * sizeof mine, cudaMemcpyDeviceToHost));
-    cudaFree(dev);
-    s->peer.assign(G, nullptr);
-    for (unsigned k = 0; k < G && !bad; k++) {
-        if (k == g) { s->peer[k] = s->slots; continue; }
-        void *p = nullptr;
-        if (cudaIpcOpenMemHandle(&p, all[k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { bad = 1; cudaGetLastError(); break; }
-        s->peer[k] = (u64 *)p;
-    }
-    // agree on the outcome
-    int h = bad;
-    NTTB200_CHECK(cudaMemcpy(s->flag + 1, &h, sizeof h, cudaMemcpyHostToDevice));
-    NCCLCHECK(nccl().AllReduce(s->flag + 1, s->flag + 1, 1, ncclInt32, ncclSum, comm->comm, s->cs));
-    NTTB200_CHECK(cudaStreamSynchronize(s->cs));
-    NTTB200_CHECK(cudaMemcpy(&h, s->flag + 1, sizeof h, cudaMemcpyDeviceToHost));
-    if (h) {
-        p2p_release(s);
-        s->p2p_failed = 1;
-        if (const char *e = getenv("NTTB200_DEBUG")) if (e[0] == '1') fprintf(stderr, "nttb200: CUDA IPC unavailable on %d rank(s): sharded decryption falls back to ncclReduce\n", h);
-        return 0;
-    }
-    s->slots_words = words;
+    NTTB200_CHECK(cudaEventRecord(s->ev[4], s->st2));          // the second stream rejoins the caller's
+    NTTB200_CHECK(cudaStreamWaitEvent(st, s->ev[4], 0));
     return 0;
 }
 
@@ -404,53 +451,71 @@ int nttb200_bfv_decrypt_sharded(nttb200_bfv *b, nttb200_comm *comm, nttb200_u64 
     plan_blocks(rp, n, batch, G, g, blk.data(), nullptr);
     unsigned chunks = G > 1 ? s->chunks : 1u;
     while (chunks > 1 && per % chunks) chunks--;
-    TRY(shard_state(b, &s, (size_t)G * chunks + 4));
+    TRY(shard_state(b, &s, (size_t)2 * G * chunks + 8));
     const unsigned sub = per / chunks;                                   // items of one block in one chunk
     u64 *partial, *recv; unsigned short *plain;
     TRY(shard_buf(s, kBufPartial, (size_t)batch * pw * 8, (void **)&partial));
     TRY(shard_buf(s, kBufRecv, (size_t)per * pw * 8, (void **)&recv));
     TRY(shard_buf(s, kBufPlain, (size_t)batch * n * 2, (void **)&plain));
-    Pipe P = pipe_from_bfv(b, st);
+    Pipe P = pipe_from_bfv(b, st), P2 = pipe_from_bfv(b, s->st2);
     NTTB200_CHECK(cudaEventRecord(s->ev[0], s->cs));                     // scratch reuse across calls (see encrypt)
     NTTB200_CHECK(cudaStreamWaitEvent(st, s->ev[0], 0));
-    size_t evi = 1;
+    NTTB200_CHECK(cudaEventRecord(s->ev[1], st));                        // the second compute stream joins (c_shard is ready at this point)
+    NTTB200_CHECK(cudaStreamWaitEvent(s->st2, s->ev[1], 0));
+    size_t evi = 2;
     const size_t own = (size_t)g * per;
     if (G == 1) {
         TRY(dec_partial(b, P, partial, packed, c_shard, blk[0].limb_count, blk[0].first_limb, blk[0].limb_count, batch));
         TRY(dec_finish(b, m_out, 0, partial, packed, batch, st));
         return 0;
     }
-    if (s->mode == 2 && !s->p2p_failed) {
-        // Peer-to-peer: the partial-sum kernel of block j writes straight into slot `rank` of the buffer of the block's OWNER (rank j),
-        // mapped here through CUDA IPC -- NVLink stores issued by the kernel that produces the sums, no collective kernel competing for
-        // SMs, no staging copy.  A 4-byte all-reduce per block is the "everybody has deposited block j" barrier; the owner then sums the
-        // world slots while rounding (k_decrypt_finish) and broadcasts the block's 16-bit plaintext words.
-        const int rc = p2p_setup(b, s, comm, (size_t)batch * pw);
+    const bool p2p_mode = (s->mode == 2 || s->mode == 3) && !comm->fake;
+    if (p2p_mode && !s->p2p_failed) {
+        // Peer-to-peer: the partial-sum kernel of a tile writes straight into slot `rank` of the buffer of the items' OWNER, mapped
+        // here through CUDA IPC -- NVLink stores issued by the kernel that produces the sums: compute and transfer are one kernel, no
+        // collective kernel competes for SMs, no staging copy.  A 4-byte all-reduce is the "everybody has deposited" barrier; the
+        // owner then sums the world slots while rounding (k_decrypt_finish) and the 16-bit plaintext words are all-gathered.
+        const int rc = sym_setup(s, comm, kSymSlots, (size_t)batch * pw * 8);
         if (rc) return rc;
     }
-    if (s->mode == 2 && !s->p2p_failed) {
-        for (unsigned j = 0; j < G; j++) {
-            const unsigned cnt = blk[j].limb_count;
-            u64 *dst = s->peer[j] + (size_t)g * per * pw;                                   // my slot at the owner of block j
-            if (cnt) TRY(dec_partial(b, P, dst, packed, c_shard + blk[j].offset, cnt, blk[j].first_limb, cnt, per));
-            else NTTB200_CHECK(cudaMemsetAsync(dst, 0, (size_t)per * pw * 8, st));
-            NTTB200_CHECK(cudaEventRecord(s->ev[evi], st));
-            NTTB200_CHECK(cudaStreamWaitEvent(s->cs, s->ev[evi], 0));
-            evi++;
-            NCCLCHECK(nccl().AllReduce(s->flag, s->flag, 1, ncclInt32, ncclSum, comm->comm, s->cs));      // barrier: all deposits of block j are complete
-            const size_t it = (size_t)j * per;
-            if (j == g) {
-                if (out16) TRY(dec_finish(b, plain + it * n, 1, s->slots, packed, per, s->cs, G, (size_t)per * pw));
-                else TRY(dec_finish(b, m_out + it * n, 0, s->slots, packed, per, s->cs, G, (size_t)per * pw));
+    if (p2p_mode && !s->p2p_failed) {
+        // Every rank visits the owners in ROTATED order (rank g starts with owner g + 1): at any moment each owner receives from one
+        // sender -- a balanced all-to-all; in lock-step order all 7 peers would store into the same GPU at once (measured: 12.8 ms
+        // instead of 9.8 for 4096 ciphertexts on 8 GPUs).
+        // mode 2: `chunks` rounds, round c covering piece c of EVERY owner's block, so the owners round and gather piece c while the
+        //         next round's transforms run; mode 3: one round (largest launches, everything after the last transform is exposed).
+        const unsigned rounds = s->mode == 2 ? chunks : 1u;
+        const unsigned piece = per / rounds;
+        for (unsigned c = 0; c < rounds; c++) {
+            for (unsigned tau = 0; tau < G; tau++) {
+                const unsigned j = (g + 1 + tau) % G;
+                const unsigned cnt = blk[j].limb_count;
+                u64 *dst = (u64 *)s->sym[kSymSlots].peer[j] + ((size_t)g * per + (size_t)c * piece) * pw;   // my slot at owner j, piece c
+                const bool alt = (tau & 1) != 0;
+                if (cnt) TRY(dec_partial(b, alt ? P2 : P, dst, packed, c_shard + blk[j].offset + (size_t)c * piece * 2 * cnt * n, cnt, blk[j].first_limb, cnt, piece));
+                else NTTB200_CHECK(cudaMemsetAsync(dst, 0, (size_t)piece * pw * 8, alt ? s->st2 : st));
             }
+            for (cudaStream_t cst : {st, s->st2}) {              // both compute streams have deposited round c
+                NTTB200_CHECK(cudaEventRecord(s->ev[evi], cst));
+                NTTB200_CHECK(cudaStreamWaitEvent(s->cs, s->ev[evi], 0));
+                evi++;
+            }
+            BARRIER();                                                                            // round c is deposited everywhere
+            const u64 *mine = (const u64 *)s->sym[kSymSlots].local + (size_t)c * piece * pw;     // piece c of every slot of my buffer
             if (out16) {
-                NCCLCHECK(nccl().Broadcast(plain + it * n, plain + it * n, (size_t)per * n * 2, ncclInt8, (int)j, comm->comm, s->cs));
-                TRY(dec_expand16(plain + it * n, m_out + it * n, (size_t)per * n, s->cs));
+                // staging is round-major: plain[c][owner][piece][n]
+                unsigned short *stg = plain + (size_t)c * G * piece * n;
+                TRY(dec_finish(b, stg + (size_t)g * piece * n, 1, mine, packed, piece, s->cs, G, (size_t)per * pw));
+                COLL(nccl().AllGather(stg + (size_t)g * piece * n, stg, (size_t)piece * n * 2, ncclInt8, comm->comm, s->cs));
+                TRY(dec_expand16(stg, m_out + (size_t)c * piece * n, (size_t)piece * n, s->cs, G, (size_t)per * n));
             } else {
-                NCCLCHECK(nccl().Broadcast(m_out + it * n, m_out + it * n, (size_t)per * n, ncclUint64, (int)j, comm->comm, s->cs));
+                TRY(dec_finish(b, m_out + (own + (size_t)c * piece) * n, 0, mine, packed, piece, s->cs, G, (size_t)per * pw));
+                for (unsigned j = 0; j < G; j++)
+                    COLL(nccl().Broadcast(m_out + ((size_t)j * per + (size_t)c * piece) * n, m_out + ((size_t)j * per + (size_t)c * piece) * n,
+                                               (size_t)piece * n, ncclUint64, (int)j, comm->comm, s->cs));
             }
         }
-    } else if (s->mode == 0 || s->mode == 2) {
+    } else if (s->mode != 1) {
         // Block by block, each in `chunks` pieces: transforms + partial sums of a piece on the caller's stream; on the comm stream,
         // behind them, the piece's sums go to the block's owner (ncclReduce), the owner rounds it, and when a block is complete its
         // owner broadcasts the 16-bit plaintext words -- so the only exposed communication is the LAST piece's reduce + broadcast.
@@ -463,7 +528,7 @@ int nttb200_bfv_decrypt_sharded(nttb200_bfv *b, nttb200_comm *comm, nttb200_u64 
                 NTTB200_CHECK(cudaEventRecord(s->ev[evi], st));
                 NTTB200_CHECK(cudaStreamWaitEvent(s->cs, s->ev[evi], 0));
                 evi++;
-                NCCLCHECK(nccl().Reduce(pj, recv + (size_t)c * sub * pw, (size_t)sub * pw, ncclUint64, ncclSum, (int)j, comm->comm, s->cs));
+                COLL(nccl().Reduce(pj, recv + (size_t)c * sub * pw, (size_t)sub * pw, ncclUint64, ncclSum, (int)j, comm->comm, s->cs));
                 if (j == g) {
                     if (out16) TRY(dec_finish(b, plain + (own + (size_t)c * sub) * n, 1, recv + (size_t)c * sub * pw, packed, sub, s->cs));
                     else TRY(dec_finish(b, m_out + (own + (size_t)c * sub) * n, 0, recv + (size_t)c * sub * pw, packed, sub, s->cs));
@@ -471,10 +536,10 @@ int nttb200_bfv_decrypt_sharded(nttb200_bfv *b, nttb200_comm *comm, nttb200_u64 
             }
             const size_t it = (size_t)j * per;
             if (out16) {
-                NCCLCHECK(nccl().Broadcast(plain + it * n, plain + it * n, (size_t)per * n * 2, ncclInt8, (int)j, comm->comm, s->cs));
+                COLL(nccl().Broadcast(plain + it * n, plain + it * n, (size_t)per * n * 2, ncclInt8, (int)j, comm->comm, s->cs));
                 TRY(dec_expand16(plain + it * n, m_out + it * n, (size_t)per * n, s->cs));
             } else {
-                NCCLCHECK(nccl().Broadcast(m_out + it * n, m_out + it * n, (size_t)per * n, ncclUint64, (int)j, comm->comm, s->cs));
+                COLL(nccl().Broadcast(m_out + it * n, m_out + it * n, (size_t)per * n, ncclUint64, (int)j, comm->comm, s->cs));
             }
         }
     } else {
@@ -489,16 +554,16 @@ int nttb200_bfv_decrypt_sharded(nttb200_bfv *b, nttb200_comm *comm, nttb200_u64 
             NTTB200_CHECK(cudaEventRecord(s->ev[evi], st));
             NTTB200_CHECK(cudaStreamWaitEvent(s->cs, s->ev[evi], 0));
             evi++;
-            NCCLCHECK(nccl().ReduceScatter(partial + (size_t)c * G * sub * pw, recv + (size_t)c * sub * pw, (size_t)sub * pw, ncclUint64, ncclSum,
+            COLL(nccl().ReduceScatter(partial + (size_t)c * G * sub * pw, recv + (size_t)c * sub * pw, (size_t)sub * pw, ncclUint64, ncclSum,
                                            comm->comm, s->cs));
         }
         if (out16) {
             TRY(dec_finish(b, plain + own * n, 1, recv, packed, per, s->cs));
-            NCCLCHECK(nccl().AllGather(plain + own * n, plain, (size_t)per * n * 2, ncclInt8, comm->comm, s->cs));
+            COLL(nccl().AllGather(plain + own * n, plain, (size_t)per * n * 2, ncclInt8, comm->comm, s->cs));
             TRY(dec_expand16(plain, m_out, (size_t)batch * n, s->cs));
         } else {
             TRY(dec_finish(b, m_out + own * n, 0, recv, packed, per, s->cs));
-            NCCLCHECK(nccl().AllGather(m_out + own * n, m_out, (size_t)per * n, ncclUint64, comm->comm, s->cs));
+            COLL(nccl().AllGather(m_out + own * n, m_out, (size_t)per * n, ncclUint64, comm->comm, s->cs));
         }
     }
     NTTB200_CHECK(cudaEventRecord(s->ev[evi], s->cs));

@@ -484,6 +484,13 @@ class Comm:
         return cls(h, 1, 0)
 
     @classmethod
+    def fake(cls, world, rank):
+        """profiling only: one rank's compute share, collectives skipped"""
+        h = vp()
+        check(lib().nttb200_comm_fake(C.byref(h), C.c_int(world), C.c_int(rank)))
+        return cls(h, world, rank)
+
+    @classmethod
     def from_torch(cls, group=None):
         import torch
         import torch.distributed as dist
