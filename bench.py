@@ -335,6 +335,19 @@ def bfv_limb_sharded(nttb200, params, torch, T, world, rank, total=4096):
         out["sets"][name] = {"n": n, "limbs": r, "enc_plus_dec_per_s": total / (float(t[2]) * 1e-3), "encrypt_ms": float(t[0]),
                              "decrypt_ms": float(t[1]), "bit_identical_to_one_gpu": True,
                              "tiles_per_rank": sum(b[3] for b in plan), "shard_bytes_per_rank": words * 8}
+        if world == 1:
+            # context for the strong-scaling curve: the un-sharded single-GPU calls (nttb200_bfv_encrypt / _decrypt, loaded keys) on 1024
+            # of the same ciphertexts -- the fastest way to do this job on ONE GPU
+            pb = 1024
+            cfull = torch.zeros(pb * 2 * rn, dtype=torch.int64, device="cuda")
+            o2 = torch.zeros(pb * n, dtype=torch.int64, device="cuda")
+
+            def pair():
+                bfv.encrypt(cfull, None, m[:pb * n], batch=pb)
+                bfv.decrypt(o2, cfull, None, batch=pb)
+            ms1 = T.ms(pair, reps=3)
+            out["sets"][name]["one_gpu_unsharded_calls_per_s"] = pb / (ms1 * 1e-3)
+            del cfull, o2
         bfv.close()
         del shard, res, m
         torch.cuda.empty_cache()
