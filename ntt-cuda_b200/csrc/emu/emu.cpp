@@ -57,9 +57,21 @@ static int g_which = -1;   // -1: whole transform, 0 / 1: only the first / secon
 static const unsigned char *g_gen_src = nullptr;   // next forward strided pass generates its input (NttArgs::gen_src)
 static size_t g_gen_stride = 0;
 
+static int g_single_pass = 1;          // n <= 4096: whole transform in one kernel, as csrc/ntt_launch.cu dispatches it
+extern "C" __attribute__((visibility("default"))) void emu_set_single_pass(int on) { g_single_pass = on; }
+
 template <class P, int LOGN, bool INV>
 static void run_one(const NttArgs &A)
 {
+    if constexpr (LOGN <= 12) {
+        if (g_which < 0 && !A.gen_src && g_single_pass) {
+            constexpr int R1 = 1 << (LOGN - 4);
+            emu_dim3 g1;
+            g1.x = A.num;
+            emu_launch(g1, R1, (size_t)R1 * 128 + 1024, [&] { ntt_single_pass<P, LOGN, INV>(A); });
+            return;
+        }
+    }
     using SC = Sched<LOGN>;
     constexpr int R = 1 << SC::K1;
     const size_t n = (size_t)1 << LOGN;

@@ -454,7 +454,7 @@ __device__ __forceinline__ void regs_row(u64 *tile, u32 row, u64 (&v)[16])
 
 // One round of the strided pass: stages [J0, J0+S) of K1 on thread-in-tile index u in [0, 2^K1).
 // EPI (final inverse round only): applied to the canonical outputs; coefficient index of (row, col) = row * C + cbase + col
-template <class P, int K1, int J0, int S, bool INV, class EPI = NoEpi>
+template <class P, int K1, int J0, int S, bool INV, class EPI = NoEpi, bool SWZ = false>
 __device__ __forceinline__ void strided_round(u64 *tile, u32 u, const P &pol, const EPI *epi = nullptr, u32 C = 0, u32 cbase = 0)
 {
     constexpr int NC = 16 >> S;
@@ -464,7 +464,7 @@ __device__ __forceinline__ void strided_round(u64 *tile, u32 u, const P &pol, co
     const u32 lo = rest & ((1u << LOB) - 1u), hi = rest >> LOB;
     const u32 rbase = (hi << (K1 - J0)) + lo;
     u64 v[16];
-    regs_rows<S, false, true>(tile, rbase, LOB, cg * NC, v);
+    regs_rows<S, SWZ, true>(tile, rbase, LOB, cg * NC, v);
     if (!INV) ct_stages<S, NC>(v, (1u << J0) + hi, pol);
     else gs_stages<S, NC, J0 == 0>(v, (1u << J0) + hi, pol);
     if constexpr (INV && J0 == 0 && EPI::kMode != kEpiNone) {
@@ -475,7 +475,7 @@ __device__ __forceinline__ void strided_round(u64 *tile, u32 u, const P &pol, co
             for (int c = 0; c < NC; c++) v[i * NC + c] = epi->apply(v[i * NC + c], j + c);
         }
     }
-    regs_rows<S, false, false>(tile, rbase, LOB, cg * NC, v);
+    regs_rows<S, SWZ, false>(tile, rbase, LOB, cg * NC, v);
 }
 
 // Dynamic shared memory is only guaranteed 16-byte aligned; the swizzled TMA image needs 1024.  The pad is added
@@ -759,6 +759,53 @@ ntt_contig_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
     if (!dbg_nomem && tma && tid == 0) tma_store_wait_read<0>();
 #endif
     (void)bar;
+}
+
+// ---- whole transform in ONE kernel for n <= 4096: one CTA per polynomial, the polynomial (<= 32 KiB) stays in shared memory ---------------
+// BASELINE config 1 (a single N = 4096 transform, ntt_60bit.cuh:314-386: forwardNTT = one <<<1,1024>>> launch, inverseNTT = two) is pure
+// launch latency; with two kernels per transform this library lost to the rebuilt reference there (20 us against 16).  The polynomial
+// is viewed as [R = n/16 rows][16 columns]: the first log2(R) stages pair rows (the strided rounds of ntt_strided_pass, on a swizzled
+// image), the last four stages are one row per thread (the row round of ntt_contig_pass).  One HBM round trip, one launch.
+template <int LOGN> struct SmallSched;
+template <> struct SmallSched<11> { static constexpr int S1 = 4, S2 = 3; };
+template <> struct SmallSched<12> { static constexpr int S1 = 4, S2 = 4; };
+template <class P, int LOGN, bool INV>
+__global__ void __launch_bounds__(1 << (LOGN - 4)) ntt_single_pass(NttArgs A)
+{
+    using SS = SmallSched<LOGN>;
+    constexpr int K1 = LOGN - 4, R = 1 << K1, S1 = SS::S1, S2 = SS::S2;
+    static_assert(S1 + S2 == K1, "bad split");
+    constexpr u32 n = 1u << LOGN;
+    NTT_DYN_SMEM(raw);
+    u64 *tile = align_1024(raw);
+    const u32 tid = threadIdx.x, p = blockIdx.x;
+    const u32 grp = p / A.group_polys, idx = p - grp * A.group_polys;
+    P pol;
+    pol.init(A, p % A.division, n);
+    u64 *g = A.a + (size_t)grp * A.group_stride + ((size_t)idx << LOGN);
+    tile_copy_coop<true, true>(tile, g, 16, R, tid, R);
+    __syncthreads();
+    u64 v[16];
+    if (!INV) {
+        strided_round<P, K1, 0, S1, false, NoEpi, true>(tile, tid, pol);
+        __syncthreads();
+        strided_round<P, K1, S1, S2, false, NoEpi, true>(tile, tid, pol);
+        __syncthreads();
+        regs_row<true, true>(tile, tid, v);
+        ct_stages<4, 1>(v, (n >> 4) + tid, pol);
+        pol.fwd_final_all(v);
+        regs_row<true, false>(tile, tid, v);
+    } else {
+        regs_row<true, true>(tile, tid, v);
+        gs_stages<4, 1, false>(v, (n >> 4) + tid, pol);
+        regs_row<true, false>(tile, tid, v);
+        __syncthreads();
+        strided_round<P, K1, S1, S2, true, NoEpi, true>(tile, tid, pol);
+        __syncthreads();
+        strided_round<P, K1, 0, S1, true, NoEpi, true>(tile, tid, pol);
+    }
+    __syncthreads();
+    tile_copy_coop<true, false>(tile, g, 16, R, tid, R);
 }
 
 // ---- fused "contig forward pass  (.) key  ->  contig inverse pass" ----------------------------------------------------

@@ -36,6 +36,14 @@ unsigned pf_dist_for(int dev, int resident)
     return (unsigned)(waves * (float)(sms[dev] * resident));
 }
 
+// NTTB200_SINGLE_PASS=0 keeps the two-kernel schedule for n <= 4096 (A/B)
+static bool use_single_pass()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("NTTB200_SINGLE_PASS"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v != 0;
+}
+
 int get_tma_default()
 {
     const char *e = getenv("NTTB200_NO_TMA");
@@ -120,6 +128,20 @@ static int launch_one(const NttArgs &A, int which, unsigned cnt, const CUtensorM
     { const int e__ = (int)cudaGetLastError(); return e__ ? nttb200_trace_error(e__, __FILE__, __LINE__) : 0; }
 }
 
+// n <= 4096: the whole transform in one kernel, one CTA per polynomial (ntt_single_pass)
+template <class P, int LOGN, bool INV>
+static int launch_single(const NttArgs &A, cudaStream_t st)
+{
+    constexpr int R = 1 << (LOGN - 4);
+    ntt_single_pass<P, LOGN, INV><<<A.num, R, (size_t)R * 128 + 1024, st>>>(A);
+    { const int e__ = (int)cudaGetLastError(); return e__ ? nttb200_trace_error(e__, __FILE__, __LINE__) : 0; }
+}
+template <class P, bool INV>
+static int launch_single_logn(unsigned logn, const NttArgs &A, cudaStream_t st)
+{
+    return logn == 11 ? launch_single<P, 11, INV>(A, st) : launch_single<P, 12, INV>(A, st);
+}
+
 template <class P, bool INV>
 static int launch_logn(unsigned logn, const NttArgs &A, int p0, unsigned cnt, const CUtensorMap &ms, const CUtensorMap &mc,
                        cudaStream_t st)
@@ -162,6 +184,12 @@ int launch_ntt_pass(bool inverse, int policy, unsigned logn, const NttArgsHost &
     A.group_polys = h.group_polys ? h.group_polys : h.num;
     A.group_stride = h.group_polys ? h.group_stride : ((size_t)h.num << logn);
     const unsigned groups = (h.num + A.group_polys - 1) / A.group_polys;
+    if (which < 0 && logn <= 12 && !h.gen_src && !(h.use_tma & 6) && use_single_pass()) {      // whole transform, small ring: one kernel, no tensor maps
+        if (policy == kPolicyShoupLazy && !inverse) return launch_single_logn<ShoupLazyPolicy, false>(logn, A, st);
+        if (policy == kPolicyShoupLazy && inverse) return launch_single_logn<ShoupLazyInvPolicy, true>(logn, A, st);
+        if (policy != kPolicyBarrett) return inverse ? launch_single_logn<ShoupPolicy, true>(logn, A, st) : launch_single_logn<ShoupPolicy, false>(logn, A, st);
+        return inverse ? launch_single_logn<BarrettPolicy, true>(logn, A, st) : launch_single_logn<BarrettPolicy, false>(logn, A, st);
+    }
     CUtensorMap ms, mc;
     if (h.use_tma & 1) {
         int r = make_tmap_strided(&ms, A.a, logn, sched_k1(logn), A.group_polys, A.group_stride, groups);

@@ -8,7 +8,7 @@
 #include <cstring>
 #include <vector>
 #include <cuda_runtime.h>
-#include "bfly_variants.cuh"
+#include "../csrc/ntt_kernels.cuh"
 using namespace nttb200;
 
 // twiddles from registers instead of the L1-resident table: isolates the arithmetic from the LDG stream
@@ -107,11 +107,6 @@ int main(int argc, char **argv)
     run<P, INV, 4>(nm "_4cta", s, A, data, false);
     RUN3(ShoupPolicy, false, "fwd_shoup_exact")
     RUN3(ShoupLazyPolicy, false, "fwd_lazy_approx")
-    RUN3(ShoupLazy2Policy, false, "fwd_lazy_v2")
-    RUN3(ShoupLazyHPolicy, false, "fwd_lazy_h")
-    RUN3(ShoupLazyFPolicy, false, "fwd_lazy_f")
-    RUN3(RegTw<ShoupLazyFPolicy>, false, "fwd_lazy_f_regtw")
-    RUN3(ShoupLazyInv2Policy, true, "inv_lazy_v2")
     RUN3(RegTw<ShoupLazyPolicy>, false, "fwd_lazy_approx_regtw")
     RUN3(RegTw<ShoupLazyInvPolicy>, true, "inv_lazy_approx_regtw")
     RUN3(ShoupLazyInvPolicy, true, "inv_lazy_approx")

@@ -206,3 +206,27 @@ def test_emu_final_reduction_arms(oracle):
     fwd = emu.ntt(a, n, qs, psi, psiinv, num, 3, inverse=False, barrett=2, use_tma=1)
     assert np.array_equal(fwd, _expect(oracle, a, n, qs, psi, psiinv, num, 3, False))
     assert np.array_equal(emu.ntt(fwd, n, qs, psi, psiinv, num, 3, inverse=True, barrett=2, use_tma=1), a)
+
+
+@pytest.mark.parametrize("logn,limbs,num,barrett", [(11, 3, 4, 0), (11, 2, 3, 1), (11, 3, 3, 2), (12, 3, 5, 0), (12, 1, 2, 1), (12, 3, 4, 2)])
+@pytest.mark.parametrize("single", [1, 0], ids=["one_kernel", "two_kernels"])
+def test_emu_small_rings_both_schedules(oracle, logn, limbs, num, barrett, single):
+    """n <= 4096: the whole transform in ONE kernel (ntt_single_pass, what the library launches) and the two-kernel schedule kept for
+    A/B (NTTB200_SINGLE_PASS=0) give the oracle's bits for all three arithmetic policies, several limbs, grouped polynomials."""
+    if barrett == 2:                       # the lazy policies need q < 2^57
+        n = 1 << logn
+        qs, roots = params.find_ntt_primes(55, n, limbs)
+        tabs = [oracle.fill_psi_tables(r, q, n) for q, r in zip(qs, roots)]
+        psi, psiinv = np.stack([t[0] for t in tabs]), np.stack([t[1] for t in tabs])
+    else:
+        n, qs, psi, psiinv = _ring(oracle, logn, limbs)
+    a = np.concatenate([oracle.fill_uniform(n, qs[pidx % limbs], 0xABCD00 + pidx) for pidx in range(num)])
+    a[0], a[1], a[2] = 0, 1, qs[0] - 1
+    emu.lib().emu_set_single_pass(single)
+    try:
+        fwd = emu.ntt(a, n, qs, psi, psiinv, num, limbs, inverse=False, barrett=barrett, use_tma=1)
+        assert np.array_equal(fwd, _expect(oracle, a, n, qs, psi, psiinv, num, limbs, False))
+        inv = emu.ntt(fwd, n, qs, psi, psiinv, num, limbs, inverse=True, barrett=barrett, use_tma=1)
+        assert np.array_equal(inv, a)
+    finally:
+        emu.lib().emu_set_single_pass(1)
