@@ -63,12 +63,11 @@ extern "C" __attribute__((visibility("default"))) void emu_set_single_pass(int o
 template <class P, int LOGN, bool INV>
 static void run_one(const NttArgs &A)
 {
-    if constexpr (LOGN <= 12) {
-        if (g_which < 0 && !A.gen_src && g_single_pass) {
-            constexpr int R1 = 1 << (LOGN - 4);
+    if constexpr (LOGN <= 12 && !P::kLazyGS) {
+        if (g_which < 0 && !A.gen_src && g_single_pass && A.num <= kSmallNttMaxPolys) {
             emu_dim3 g1;
             g1.x = A.num;
-            emu_launch(g1, R1, (size_t)R1 * 128 + 1024, [&] { ntt_single_pass<P, LOGN, INV>(A); });
+            emu_launch(g1, 1 << (LOGN - 2), (size_t)8 << LOGN, [&] { ntt_single_pass<P, LOGN, INV>(A); });
             return;
         }
     }
@@ -155,6 +154,8 @@ int emu_ntt(int inverse, int barrett, int use_tma, int logn, u64 *a, const u64 *
     A.a = a; A.tw = tw; A.tws = tws; A.lc = lc; A.qv = qv; A.muv = muv; A.qbitv = qbitv;
     A.num = num; A.division = division; A.use_tma = (u32)use_tma;
     A.gen_src = inverse ? nullptr : g_gen_src; A.gen_stride = g_gen_stride;
+    // the library sends small rings with few polynomials to the latency kernel under the general Shoup policy (csrc/ntt_launch.cu)
+    if (barrett == 2 && logn <= 12 && num <= kSmallNttMaxPolys && g_single_pass && g_which < 0 && !A.gen_src) barrett = 0;
     if (barrett == 2 && !inverse) return run_logn<ShoupLazyPolicy, false>(logn, A);
     if (barrett == 2 && inverse) return run_logn<ShoupLazyInvPolicy, true>(logn, A);
     if (barrett != 1) return inverse ? run_logn<ShoupPolicy, true>(logn, A) : run_logn<ShoupPolicy, false>(logn, A);

@@ -761,51 +761,84 @@ ntt_contig_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
     (void)bar;
 }
 
-// ---- whole transform in ONE kernel for n <= 4096: one CTA per polynomial, the polynomial (<= 32 KiB) stays in shared memory ---------------
+// ---- whole transform in ONE kernel for n <= 4096 and FEW polynomials: the latency path -----------------------------------------------
 // BASELINE config 1 (a single N = 4096 transform, ntt_60bit.cuh:314-386: forwardNTT = one <<<1,1024>>> launch, inverseNTT = two) is pure
-// launch latency; with two kernels per transform this library lost to the rebuilt reference there (20 us against 16).  The polynomial
-// is viewed as [R = n/16 rows][16 columns]: the first log2(R) stages pair rows (the strided rounds of ntt_strided_pass, on a swizzled
-// image), the last four stages are one row per thread (the row round of ntt_contig_pass).  One HBM round trip, one launch.
-template <int LOGN> struct SmallSched;
-template <> struct SmallSched<11> { static constexpr int S1 = 4, S2 = 3; };
-template <> struct SmallSched<12> { static constexpr int S1 = 4, S2 = 4; };
+// latency.  The two-kernel schedule gives one small polynomial to four 128-thread CTAs with 96 dependent butterflies per thread (20 us
+// against the rebuilt reference's 16); a first one-kernel version with 16 coefficients per thread was no faster (profiles/
+// r02_experiments.md).  Here one CTA of n/4 threads keeps the polynomial in shared memory and every thread owns FOUR coefficients per
+// round = two stages in registers (24 butterflies per thread at n = 4096, five CTA barriers), which is what latency wants.
+// Round k (stages 2k, 2k+1): groups {i, i + d, i + 2d, i + 3d}, d = n >> (2k + 2); table entries as in the reference
+// (stage `length = m` reads psi[m + block]).  Used when the call has at most kSmallNttMaxPolys polynomials; batches keep the two-kernel path.
+constexpr unsigned kSmallNttMaxPolys = 64;
 template <class P, int LOGN, bool INV>
-__global__ void __launch_bounds__(1 << (LOGN - 4)) ntt_single_pass(NttArgs A)
+__global__ void __launch_bounds__(1 << (LOGN - 2)) ntt_single_pass(NttArgs A)
 {
-    using SS = SmallSched<LOGN>;
-    constexpr int K1 = LOGN - 4, R = 1 << K1, S1 = SS::S1, S2 = SS::S2;
-    static_assert(S1 + S2 == K1, "bad split");
-    constexpr u32 n = 1u << LOGN;
+    static_assert(!P::kLazyGS, "the latency kernel uses the per-butterfly-corrected policies");
+    constexpr u32 n = 1u << LOGN, T = n >> 2;
+    constexpr int PAIRS = LOGN / 2;                 // rounds of two stages; LOGN odd: one single-stage round more
     NTT_DYN_SMEM(raw);
-    u64 *tile = align_1024(raw);
-    const u32 tid = threadIdx.x, p = blockIdx.x;
+    u64 *tile = reinterpret_cast<u64 *>(raw);
+    const u32 t = threadIdx.x, p = blockIdx.x;
     const u32 grp = p / A.group_polys, idx = p - grp * A.group_polys;
     P pol;
     pol.init(A, p % A.division, n);
     u64 *g = A.a + (size_t)grp * A.group_stride + ((size_t)idx << LOGN);
-    tile_copy_coop<true, true>(tile, g, 16, R, tid, R);
-    __syncthreads();
-    u64 v[16];
-    if (!INV) {
-        strided_round<P, K1, 0, S1, false, NoEpi, true>(tile, tid, pol);
-        __syncthreads();
-        strided_round<P, K1, S1, S2, false, NoEpi, true>(tile, tid, pol);
-        __syncthreads();
-        regs_row<true, true>(tile, tid, v);
-        ct_stages<4, 1>(v, (n >> 4) + tid, pol);
-        pol.fwd_final_all(v);
-        regs_row<true, false>(tile, tid, v);
-    } else {
-        regs_row<true, true>(tile, tid, v);
-        gs_stages<4, 1, false>(v, (n >> 4) + tid, pol);
-        regs_row<true, false>(tile, tid, v);
-        __syncthreads();
-        strided_round<P, K1, S1, S2, true, NoEpi, true>(tile, tid, pol);
-        __syncthreads();
-        strided_round<P, K1, 0, S1, true, NoEpi, true>(tile, tid, pol);
+    {   // 32 bytes per thread, coalesced
+        const ulonglong2 x0 = reinterpret_cast<const ulonglong2 *>(g)[t], x1 = reinterpret_cast<const ulonglong2 *>(g)[t + T];
+        reinterpret_cast<ulonglong2 *>(tile)[t] = x0;
+        reinterpret_cast<ulonglong2 *>(tile)[t + T] = x1;
     }
     __syncthreads();
-    tile_copy_coop<true, false>(tile, g, 16, R, tid, R);
+    if (!INV) {
+        NTT_UNROLL
+        for (int k = 0; k < PAIRS; k++) {
+            const u32 d = n >> (2 * k + 2), b0 = t / d, i = b0 * 4 * d + (t % d), m0 = 1u << (2 * k);
+            u64 x0 = tile[i], x1 = tile[i + d], x2 = tile[i + 2 * d], x3 = tile[i + 3 * d];
+            const typename P::Tw w0 = pol.load(m0 + b0);
+            typename P::Tw w1a, w1b;
+            pol.load2(2 * m0 + 2 * b0, w1a, w1b);
+            pol.ct(x0, x2, w0); pol.ct(x1, x3, w0);
+            pol.ct(x0, x1, w1a); pol.ct(x2, x3, w1b);
+            if (2 * k + 2 == LOGN) { x0 = pol.fwd_final(x0); x1 = pol.fwd_final(x1); x2 = pol.fwd_final(x2); x3 = pol.fwd_final(x3); }
+            tile[i] = x0; tile[i + d] = x1; tile[i + 2 * d] = x2; tile[i + 3 * d] = x3;
+            __syncthreads();
+        }
+        if constexpr (LOGN & 1) {                   // last stage alone: length n/2, pairs (2j, 2j + 1), two butterflies per thread
+            NTT_UNROLL
+            for (int h = 0; h < 2; h++) {
+                const u32 j = t + h * T;
+                u64 x0 = tile[2 * j], x1 = tile[2 * j + 1];
+                pol.ct(x0, x1, pol.load((n >> 1) + j));
+                tile[2 * j] = pol.fwd_final(x0); tile[2 * j + 1] = pol.fwd_final(x1);
+            }
+            __syncthreads();
+        }
+    } else {
+        if constexpr (LOGN & 1) {
+            NTT_UNROLL
+            for (int h = 0; h < 2; h++) {
+                const u32 j = t + h * T;
+                u64 x0 = tile[2 * j], x1 = tile[2 * j + 1];
+                pol.gs(x0, x1, pol.load((n >> 1) + j));
+                tile[2 * j] = x0; tile[2 * j + 1] = x1;
+            }
+            __syncthreads();
+        }
+        NTT_UNROLL
+        for (int k = PAIRS - 1; k >= 0; k--) {
+            const u32 d = n >> (2 * k + 2), b0 = t / d, i = b0 * 4 * d + (t % d), m0 = 1u << (2 * k);
+            u64 x0 = tile[i], x1 = tile[i + d], x2 = tile[i + 2 * d], x3 = tile[i + 3 * d];
+            typename P::Tw w1a, w1b;
+            pol.load2(2 * m0 + 2 * b0, w1a, w1b);
+            pol.gs(x0, x1, w1a); pol.gs(x2, x3, w1b);
+            if (k == 0) { pol.gs_last(x0, x2); pol.gs_last(x1, x3); }
+            else { const typename P::Tw w0 = pol.load(m0 + b0); pol.gs(x0, x2, w0); pol.gs(x1, x3, w0); }
+            tile[i] = x0; tile[i + d] = x1; tile[i + 2 * d] = x2; tile[i + 3 * d] = x3;
+            __syncthreads();
+        }
+    }
+    reinterpret_cast<ulonglong2 *>(g)[t] = reinterpret_cast<const ulonglong2 *>(tile)[t];
+    reinterpret_cast<ulonglong2 *>(g)[t + T] = reinterpret_cast<const ulonglong2 *>(tile)[t + T];
 }
 
 // ---- fused "contig forward pass  (.) key  ->  contig inverse pass" ----------------------------------------------------

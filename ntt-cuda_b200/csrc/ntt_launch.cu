@@ -128,12 +128,11 @@ static int launch_one(const NttArgs &A, int which, unsigned cnt, const CUtensorM
     { const int e__ = (int)cudaGetLastError(); return e__ ? nttb200_trace_error(e__, __FILE__, __LINE__) : 0; }
 }
 
-// n <= 4096: the whole transform in one kernel, one CTA per polynomial (ntt_single_pass)
+// n <= 4096, few polynomials: the whole transform in one kernel, one CTA of n/4 threads per polynomial (ntt_single_pass)
 template <class P, int LOGN, bool INV>
 static int launch_single(const NttArgs &A, cudaStream_t st)
 {
-    constexpr int R = 1 << (LOGN - 4);
-    ntt_single_pass<P, LOGN, INV><<<A.num, R, (size_t)R * 128 + 1024, st>>>(A);
+    ntt_single_pass<P, LOGN, INV><<<A.num, 1 << (LOGN - 2), (size_t)8 << LOGN, st>>>(A);
     { const int e__ = (int)cudaGetLastError(); return e__ ? nttb200_trace_error(e__, __FILE__, __LINE__) : 0; }
 }
 template <class P, bool INV>
@@ -184,9 +183,8 @@ int launch_ntt_pass(bool inverse, int policy, unsigned logn, const NttArgsHost &
     A.group_polys = h.group_polys ? h.group_polys : h.num;
     A.group_stride = h.group_polys ? h.group_stride : ((size_t)h.num << logn);
     const unsigned groups = (h.num + A.group_polys - 1) / A.group_polys;
-    if (which < 0 && logn <= 12 && !h.gen_src && !(h.use_tma & 6) && use_single_pass()) {      // whole transform, small ring: one kernel, no tensor maps
-        if (policy == kPolicyShoupLazy && !inverse) return launch_single_logn<ShoupLazyPolicy, false>(logn, A, st);
-        if (policy == kPolicyShoupLazy && inverse) return launch_single_logn<ShoupLazyInvPolicy, true>(logn, A, st);
+    if (which < 0 && logn <= 12 && h.num <= kSmallNttMaxPolys && !h.gen_src && !(h.use_tma & 6) && use_single_pass()) {   // latency path, no tensor maps
+        // (the lazy policies track bounds over 16-coefficient rounds; here every butterfly is corrected: general Shoup policy)
         if (policy != kPolicyBarrett) return inverse ? launch_single_logn<ShoupPolicy, true>(logn, A, st) : launch_single_logn<ShoupPolicy, false>(logn, A, st);
         return inverse ? launch_single_logn<BarrettPolicy, true>(logn, A, st) : launch_single_logn<BarrettPolicy, false>(logn, A, st);
     }
