@@ -154,6 +154,7 @@ int emu_ntt(int inverse, int barrett, int use_tma, int logn, u64 *a, const u64 *
     A.a = a; A.tw = tw; A.tws = tws; A.lc = lc; A.qv = qv; A.muv = muv; A.qbitv = qbitv;
     A.num = num; A.division = division; A.use_tma = (u32)use_tma;
     A.gen_src = inverse ? nullptr : g_gen_src; A.gen_stride = g_gen_stride;
+    ntt_args_finish(A);
     // the library sends small rings with few polynomials to the latency kernel under the general Shoup policy (csrc/ntt_launch.cu)
     if (barrett == 2 && logn <= 12 && num <= kSmallNttMaxPolys && g_single_pass && g_which < 0 && !A.gen_src) barrett = 0;
     if (barrett == 2 && !inverse) return run_logn<ShoupLazyPolicy, false>(logn, A);

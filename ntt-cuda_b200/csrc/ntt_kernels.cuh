@@ -54,7 +54,25 @@ struct NttArgs {
     // group g is ternary_value(gen_src[g * gen_stride + j], q_limb)  (encryption's u, bfv_encryption.cuh:23-36)
     const unsigned char *gen_src;
     size_t gen_stride;
+    // p / group_polys and p / division as multiply-shift (ntt_args_finish): exact for p < 2^31; mul == 0 -> plain division.  The two
+    // runtime divisions cost every CTA ~60 uniform-datapath instructions (I2F / MUFU.RCP sequences) before its first butterfly.
+    u32 gp_mul, gp_sh, div_mul, div_sh;
 };
+__host__ __device__ __forceinline__ void fastdiv_make(u32 d, u32 &mul, u32 &sh)
+{
+    u32 lg = 0;
+    while ((1ull << lg) < d) lg++;
+    sh = 31 + lg;
+    mul = (u32)((((u64)1 << sh) + d - 1) / d);          // ceil(2^sh / d) < 2^32 for d >= 1
+    if (d <= 1) { mul = 0; sh = 0; }
+}
+__host__ __device__ __forceinline__ u32 fastdiv(u32 p, u32 d, u32 mul, u32 sh) { return mul ? (u32)(((u64)p * mul) >> sh) : (d <= 1 ? p : p / d); }
+__host__ __device__ __forceinline__ void ntt_args_finish(NttArgs &A)
+{
+    fastdiv_make(A.group_polys, A.gp_mul, A.gp_sh);
+    fastdiv_make(A.division, A.div_mul, A.div_sh);
+}
+__device__ __forceinline__ u32 ntt_limb_of(const NttArgs &A, u32 p) { return p - fastdiv(p, A.division, A.div_mul, A.div_sh) * A.division; }
 
 // ---- stage split per ring degree: K1 = S1+S2+S3 strided stages (rounds of 3 or 4), K2 contiguous stages -------
 template <int LOGN> struct Sched;
@@ -517,7 +535,7 @@ ntt_strided_pass(const __grid_constant__ TensorMap tmap, NttArgs A, EpiArgs E)
     u64 *bar = tiles0 + TPC * TILE_ELEMS;
     const u32 tid = threadIdx.x, p = blockIdx.x / TG;
     const u32 colbase = (blockIdx.x % TG) * (TPC * NT * 16);
-    const u32 grp = p / A.group_polys, idx = p - grp * A.group_polys;   // polynomial idx of group grp
+    const u32 grp = fastdiv(p, A.group_polys, A.gp_mul, A.gp_sh), idx = p - grp * A.group_polys;   // polynomial idx of group grp
     const bool dbg_nocompute = (A.use_tma & 2u) != 0, dbg_nomem = (A.use_tma & 4u) != 0;
     const bool tma = (A.use_tma & 1u) != 0;
 #ifndef NTTB200_EMU
@@ -537,7 +555,7 @@ ntt_strided_pass(const __grid_constant__ TensorMap tmap, NttArgs A, EpiArgs E)
         const u32 fb = blockIdx.x + A.pf_dist;           // the CTA that will run here about one wave later
         if (A.pf_dist != 0 && fb < gridDim.x) {
             const u32 fp = fb / TG, fcol = (fb % TG) * (TPC * NT * 16);
-            const u32 fgrp = fp / A.group_polys, fidx = fp - fgrp * A.group_polys;
+            const u32 fgrp = fastdiv(fp, A.group_polys, A.gp_mul, A.gp_sh), fidx = fp - fgrp * A.group_polys;
             for (int k = 0; k < TPC * NT; k++)
                 for (int rc = 0; rc < R / RB; rc++) tma_prefetch_4d(&tmap, (int)fcol + k * 16, rc * RB, (int)fidx, (int)fgrp);
         }
@@ -546,7 +564,7 @@ ntt_strided_pass(const __grid_constant__ TensorMap tmap, NttArgs A, EpiArgs E)
     const bool gen = !INV && A.gen_src != nullptr;
 #endif
     P pol;
-    pol.init(A, p % A.division, n);
+    pol.init(A, ntt_limb_of(A, p), n);
     u64 *g = A.a + (size_t)grp * A.group_stride + ((size_t)idx << LOGN) + colbase;
     {   // twiddle lines of every round of this thread, requested before the tile wait so they arrive under it
         const u32 uu = tid & (R - 1);
@@ -562,11 +580,19 @@ ntt_strided_pass(const __grid_constant__ TensorMap tmap, NttArgs A, EpiArgs E)
         // 128-byte tile row, so the stores of a warp are 512 contiguous bytes (no bank conflicts; the row-per-thread version had
         // 8-way conflicts and ran the pass at 207 us instead of 148)
         const unsigned char *src = A.gen_src + (size_t)grp * A.gen_stride + colbase;
-        for (u32 e = tid; e < (u32)(TPC * NT) * R * 8; e += THREADS) {
-            const u32 seg = e >> 3, c = e & 7u, k = seg / R, row = seg % R;
-            const u32 b2 = *reinterpret_cast<const unsigned short *>(src + (size_t)row * C + k * 16 + 2 * c);
+        constexpr u32 GEN_ITERS = (u32)(TPC * NT) * R * 8 / THREADS;        // = 8: every thread converts eight 2-byte chunks
+        static_assert(GEN_ITERS * THREADS == (u32)(TPC * NT) * R * 8, "tile is a whole number of chunk sweeps");
+        u32 b2[GEN_ITERS];
+        NTT_UNROLL
+        for (u32 it = 0; it < GEN_ITERS; it++) {                            // all keystream loads in flight before the first conversion
+            const u32 e = tid + it * THREADS, seg = e >> 3, c = e & 7u, k = seg / R, row = seg % R;
+            b2[it] = *reinterpret_cast<const unsigned short *>(src + (size_t)row * C + k * 16 + 2 * c);
+        }
+        NTT_UNROLL
+        for (u32 it = 0; it < GEN_ITERS; it++) {
+            const u32 e = tid + it * THREADS, seg = e >> 3, c = e & 7u;
             *reinterpret_cast<ulonglong2 *>(tiles0 + (size_t)seg * 16 + 2 * c) =
-                make_ulonglong2(ternary_value((unsigned char)(b2 & 0xffu), pol.q), ternary_value((unsigned char)(b2 >> 8), pol.q));
+                make_ulonglong2(ternary_value((unsigned char)(b2[it] & 0xffu), pol.q), ternary_value((unsigned char)(b2[it] >> 8), pol.q));
         }
         __syncthreads();
     } else if (tma) {
@@ -661,7 +687,7 @@ ntt_contig_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
     const u32 tid = threadIdx.x;
     const u32 p = blockIdx.x / TG;
     const u32 ripbase = (blockIdx.x % TG) * (TPC * RT);      // first row (of 16 coefficients) inside the polynomial
-    const u32 grp = p / A.group_polys, idx = p - grp * A.group_polys;
+    const u32 grp = fastdiv(p, A.group_polys, A.gp_mul, A.gp_sh), idx = p - grp * A.group_polys;
     const int growbase = (int)(idx * (n >> 4) + ripbase);    // row inside the group
     const bool dbg_nocompute = (A.use_tma & 2u) != 0, dbg_nomem = (A.use_tma & 4u) != 0;
     const bool tma = (A.use_tma & 1u) != 0;
@@ -676,13 +702,13 @@ ntt_contig_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
         const u32 fb = blockIdx.x + A.pf_dist;
         if (A.pf_dist != 0 && fb < gridDim.x) {
             const u32 fp = fb / TG, frip = (fb % TG) * (TPC * RT);
-            const u32 fgrp = fp / A.group_polys, fidx = fp - fgrp * A.group_polys;
+            const u32 fgrp = fastdiv(fp, A.group_polys, A.gp_mul, A.gp_sh), fidx = fp - fgrp * A.group_polys;
             for (int tt = 0; tt < TPC; tt++) tma_prefetch_3d(&tmap, 0, (int)(fidx * (n >> 4) + frip) + tt * RT, (int)fgrp);
         }
     }
 #endif
     P pol;
-    pol.init(A, p % A.division, n);
+    pol.init(A, ntt_limb_of(A, p), n);
     u64 *g = A.a + (size_t)grp * A.group_stride + ((size_t)idx << LOGN) + (size_t)ripbase * 16;
     prefetch_round<4>(pol, (n >> 4) + ripbase + tid);
     prefetch_round<SA>(pol, (1u << K1) + (ripbase >> SA) + (tid >> SA));
@@ -781,10 +807,19 @@ __global__ void __launch_bounds__(1 << (LOGN - 2)) ntt_single_pass(NttArgs A)
     const u32 t = threadIdx.x, p = blockIdx.x;
     const u32 grp = p / A.group_polys, idx = p - grp * A.group_polys;
     P pol;
-    pol.init(A, p % A.division, n);
+    pol.init(A, ntt_limb_of(A, p), n);
     u64 *g = A.a + (size_t)grp * A.group_stride + ((size_t)idx << LOGN);
     {   // 32 bytes per thread, coalesced
         const ulonglong2 x0 = reinterpret_cast<const ulonglong2 *>(g)[t], x1 = reinterpret_cast<const ulonglong2 *>(g)[t + T];
+        // every round's table lines are requested now (real loads, results discarded: prefetch_l1) so that the loads inside the rounds hit
+        // L1 (measured: no change at n = 4096 -- one SM's issue rate, not table latency, bounds this kernel: profiles/r02_experiments.md)
+        NTT_UNROLL
+        for (int k = 0; k < PAIRS; k++) {
+            const u32 d = n >> (2 * k + 2), b0 = t / d, m0 = 1u << (2 * k);
+            if (k > 0 || !INV) pol.prefetch(m0 + b0);
+            pol.prefetch(2 * m0 + 2 * b0);
+        }
+        if constexpr (LOGN & 1) { pol.prefetch((n >> 1) + t); pol.prefetch((n >> 1) + t + T); }
         reinterpret_cast<ulonglong2 *>(tile)[t] = x0;
         reinterpret_cast<ulonglong2 *>(tile)[t + T] = x1;
     }

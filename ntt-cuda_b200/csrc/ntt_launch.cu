@@ -182,6 +182,7 @@ int launch_ntt_pass(bool inverse, int policy, unsigned logn, const NttArgsHost &
     A.gen_src = h.gen_src; A.gen_stride = h.gen_stride;
     A.group_polys = h.group_polys ? h.group_polys : h.num;
     A.group_stride = h.group_polys ? h.group_stride : ((size_t)h.num << logn);
+    ntt_args_finish(A);
     const unsigned groups = (h.num + A.group_polys - 1) / A.group_polys;
     if (which < 0 && logn <= 12 && h.num <= kSmallNttMaxPolys && !h.gen_src && !(h.use_tma & 6) && use_single_pass()) {   // latency path, no tensor maps
         // (the lazy policies track bounds over 16-coefficient rounds; here every butterfly is corrected: general Shoup policy)

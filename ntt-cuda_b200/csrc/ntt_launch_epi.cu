@@ -61,6 +61,7 @@ int launch_strided_inv_epi(unsigned logn, const NttArgsHost &h, int mode, const 
     A.qv = nullptr; A.muv = nullptr; A.qbitv = nullptr; A.q = 0; A.mu = 0; A.qbit = 0;
     A.num = h.num; A.division = h.division; A.use_tma = (u32)h.use_tma; A.pf_dist = 0; A.gen_src = nullptr; A.gen_stride = 0;
     A.group_polys = h.group_polys; A.group_stride = h.group_stride;
+    ntt_args_finish(A);
     const unsigned groups = (h.num + A.group_polys - 1) / A.group_polys;
     CUtensorMap ms;
     if (h.use_tma & 1) {

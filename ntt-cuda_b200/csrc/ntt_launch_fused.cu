@@ -50,6 +50,7 @@ int launch_fused_mul(bool lazy, unsigned logn, const NttArgsHost &h, const u64 *
     A.qv = nullptr; A.muv = nullptr; A.qbitv = nullptr; A.q = 0; A.mu = 0; A.qbit = 0;
     A.num = items * r; A.division = r; A.use_tma = (u32)h.use_tma; A.pf_dist = 0; A.gen_src = nullptr; A.gen_stride = 0;
     A.group_polys = h.group_polys; A.group_stride = h.group_stride;
+    ntt_args_finish(A);
     F.twi = twi; F.twis = twis; F.key = key; F.key_s = key_s;
     F.key_item_stride = key_item_stride; F.key_half_stride = key_half_stride;
     F.r = r; F.in_off = in_off; F.out_off[0] = out_off0; F.out_off[1] = out_off1; F.items = items;
@@ -110,6 +111,7 @@ int launch_polymul(bool lazy, unsigned logn, const NttArgsHost &ha, const u64 *t
     A.num = ha.num; A.division = ha.division; A.use_tma = (u32)ha.use_tma; A.pf_dist = 0; A.gen_src = nullptr; A.gen_stride = 0;
     A.group_polys = ha.group_polys ? ha.group_polys : ha.num;
     A.group_stride = ha.group_polys ? ha.group_stride : ((size_t)ha.num << logn);
+    ntt_args_finish(A);
     F.b = b; F.twi = twi; F.twis = twis; F.out = out ? out : A.a;
     F.b_group_polys = b_group_polys ? b_group_polys : ha.num;
     F.b_group_stride = b_group_polys ? b_group_stride : ((size_t)ha.num << logn);
