@@ -66,13 +66,22 @@ __host__ __device__ __forceinline__ void fastdiv_make(u32 d, u32 &mul, u32 &sh)
     mul = (u32)((((u64)1 << sh) + d - 1) / d);          // ceil(2^sh / d) < 2^32 for d >= 1
     if (d <= 1) { mul = 0; sh = 0; }
 }
-__host__ __device__ __forceinline__ u32 fastdiv(u32 p, u32 d, u32 mul, u32 sh) { return mul ? (u32)(((u64)p * mul) >> sh) : (d <= 1 ? p : p / d); }
+// FD = false: plain runtime division.  Measured per kernel on one box (scripts/ab_ntt.py, profiles/r02_experiments.md): the multiply-shift
+// form wins 5 % in the inverse strided pass and LOSES 1-6 % in the other three (ptxas schedules the uniform-datapath division under the
+// tile wait; the shorter form perturbs its register allocation), so each kernel picks its own.
+template <bool FD>
+__host__ __device__ __forceinline__ u32 fastdiv(u32 p, u32 d, u32 mul, u32 sh)
+{
+    if (FD) return mul ? (u32)(((u64)p * mul) >> sh) : (d <= 1 ? p : p / d);
+    return p / d;
+}
 __host__ __device__ __forceinline__ void ntt_args_finish(NttArgs &A)
 {
     fastdiv_make(A.group_polys, A.gp_mul, A.gp_sh);
     fastdiv_make(A.division, A.div_mul, A.div_sh);
 }
-__device__ __forceinline__ u32 ntt_limb_of(const NttArgs &A, u32 p) { return p - fastdiv(p, A.division, A.div_mul, A.div_sh) * A.division; }
+template <bool FD>
+__device__ __forceinline__ u32 ntt_limb_of(const NttArgs &A, u32 p) { return p - fastdiv<FD>(p, A.division, A.div_mul, A.div_sh) * A.division; }
 
 // ---- stage split per ring degree: K1 = S1+S2+S3 strided stages (rounds of 3 or 4), K2 contiguous stages -------
 template <int LOGN> struct Sched;
@@ -535,7 +544,7 @@ ntt_strided_pass(const __grid_constant__ TensorMap tmap, NttArgs A, EpiArgs E)
     u64 *bar = tiles0 + TPC * TILE_ELEMS;
     const u32 tid = threadIdx.x, p = blockIdx.x / TG;
     const u32 colbase = (blockIdx.x % TG) * (TPC * NT * 16);
-    const u32 grp = fastdiv(p, A.group_polys, A.gp_mul, A.gp_sh), idx = p - grp * A.group_polys;   // polynomial idx of group grp
+    const u32 grp = fastdiv<INV>(p, A.group_polys, A.gp_mul, A.gp_sh), idx = p - grp * A.group_polys;   // polynomial idx of group grp
     const bool dbg_nocompute = (A.use_tma & 2u) != 0, dbg_nomem = (A.use_tma & 4u) != 0;
     const bool tma = (A.use_tma & 1u) != 0;
 #ifndef NTTB200_EMU
@@ -555,7 +564,7 @@ ntt_strided_pass(const __grid_constant__ TensorMap tmap, NttArgs A, EpiArgs E)
         const u32 fb = blockIdx.x + A.pf_dist;           // the CTA that will run here about one wave later
         if (A.pf_dist != 0 && fb < gridDim.x) {
             const u32 fp = fb / TG, fcol = (fb % TG) * (TPC * NT * 16);
-            const u32 fgrp = fastdiv(fp, A.group_polys, A.gp_mul, A.gp_sh), fidx = fp - fgrp * A.group_polys;
+            const u32 fgrp = fastdiv<INV>(fp, A.group_polys, A.gp_mul, A.gp_sh), fidx = fp - fgrp * A.group_polys;
             for (int k = 0; k < TPC * NT; k++)
                 for (int rc = 0; rc < R / RB; rc++) tma_prefetch_4d(&tmap, (int)fcol + k * 16, rc * RB, (int)fidx, (int)fgrp);
         }
@@ -564,7 +573,7 @@ ntt_strided_pass(const __grid_constant__ TensorMap tmap, NttArgs A, EpiArgs E)
     const bool gen = !INV && A.gen_src != nullptr;
 #endif
     P pol;
-    pol.init(A, ntt_limb_of(A, p), n);
+    pol.init(A, ntt_limb_of<INV>(A, p), n);
     u64 *g = A.a + (size_t)grp * A.group_stride + ((size_t)idx << LOGN) + colbase;
     {   // twiddle lines of every round of this thread, requested before the tile wait so they arrive under it
         const u32 uu = tid & (R - 1);
@@ -687,7 +696,7 @@ ntt_contig_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
     const u32 tid = threadIdx.x;
     const u32 p = blockIdx.x / TG;
     const u32 ripbase = (blockIdx.x % TG) * (TPC * RT);      // first row (of 16 coefficients) inside the polynomial
-    const u32 grp = fastdiv(p, A.group_polys, A.gp_mul, A.gp_sh), idx = p - grp * A.group_polys;
+    const u32 grp = fastdiv<false>(p, A.group_polys, A.gp_mul, A.gp_sh), idx = p - grp * A.group_polys;
     const int growbase = (int)(idx * (n >> 4) + ripbase);    // row inside the group
     const bool dbg_nocompute = (A.use_tma & 2u) != 0, dbg_nomem = (A.use_tma & 4u) != 0;
     const bool tma = (A.use_tma & 1u) != 0;
@@ -702,13 +711,13 @@ ntt_contig_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
         const u32 fb = blockIdx.x + A.pf_dist;
         if (A.pf_dist != 0 && fb < gridDim.x) {
             const u32 fp = fb / TG, frip = (fb % TG) * (TPC * RT);
-            const u32 fgrp = fastdiv(fp, A.group_polys, A.gp_mul, A.gp_sh), fidx = fp - fgrp * A.group_polys;
+            const u32 fgrp = fastdiv<false>(fp, A.group_polys, A.gp_mul, A.gp_sh), fidx = fp - fgrp * A.group_polys;
             for (int tt = 0; tt < TPC; tt++) tma_prefetch_3d(&tmap, 0, (int)(fidx * (n >> 4) + frip) + tt * RT, (int)fgrp);
         }
     }
 #endif
     P pol;
-    pol.init(A, ntt_limb_of(A, p), n);
+    pol.init(A, ntt_limb_of<false>(A, p), n);
     u64 *g = A.a + (size_t)grp * A.group_stride + ((size_t)idx << LOGN) + (size_t)ripbase * 16;
     prefetch_round<4>(pol, (n >> 4) + ripbase + tid);
     prefetch_round<SA>(pol, (1u << K1) + (ripbase >> SA) + (tid >> SA));
@@ -807,7 +816,7 @@ __global__ void __launch_bounds__(1 << (LOGN - 2)) ntt_single_pass(NttArgs A)
     const u32 t = threadIdx.x, p = blockIdx.x;
     const u32 grp = p / A.group_polys, idx = p - grp * A.group_polys;
     P pol;
-    pol.init(A, ntt_limb_of(A, p), n);
+    pol.init(A, p % A.division, n);
     u64 *g = A.a + (size_t)grp * A.group_stride + ((size_t)idx << LOGN);
     {   // 32 bytes per thread, coalesced
         const ulonglong2 x0 = reinterpret_cast<const ulonglong2 *>(g)[t], x1 = reinterpret_cast<const ulonglong2 *>(g)[t + T];
