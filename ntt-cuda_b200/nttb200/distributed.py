@@ -1,5 +1,10 @@
 """Multi-GPU orchestration: one process per GPU, torch.distributed (NCCL over NVLink) for the plumbing.
 
+Round 2: the limb-sharded BFV calls live in the C library (nttb200_bfv_encrypt_sharded / _decrypt_sharded, csrc/sharded.cu: balanced
+(limb, block) tiles, peer-to-peer exchange over CUDA IPC with NCCL fallback); from Python they are `Bfv.encrypt_sharded` /
+`Bfv.decrypt_sharded` with a `nttb200.Comm` (Comm.from_torch() adopts the process group's NCCL communicator).  The helpers below are
+the round-1 building blocks (contiguous limb ranges, caller-side all-reduce) kept for callers that run their own collectives.
+
 The hot path shards with NO data-path collective for NTT / INTT / pointwise / keygen / encryption (units = (batch item,
 limb) are independent) and with exactly ONE collective for decryption: the cross-limb base-conversion sum.
 
@@ -68,6 +73,9 @@ def decrypt_limb_sharded(bfv, c_shard, sk_shard, first: int, count: int, batch: 
     new_u64        callable(count) -> zero-initialised device buffer of `count` 64-bit words
     Returns the plaintext buffer m_out[batch][n] (identical on every rank)."""
     n = bfv.n
+    gamma, world = getattr(bfv, "gamma", None), getattr(bfv, "world", None)
+    if gamma and world:          # the 64-bit SUM of `world` partial sums below gamma must not wrap (ADVICE r1)
+        assert world * gamma < 1 << 64, "all_reduce(SUM) of the gamma partials would wrap: reduce in two levels"
     partial = new_u64(batch * 2 * n)
     if count > 0:
         bfv.decrypt_partial(partial, c_shard, sk_shard, first, count, batch=batch, sk_per_item=sk_per_item, shard_half_limbs=shard_half_limbs)
