@@ -647,7 +647,8 @@ def run_ours(args):
                     "steps": e2e_steps, "api": "nttb200_forward_ntt_batch_host (pinned host buffers, 3-stage stream pipeline)"},
             "gpu_launches": 2 * args.steps,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": ncu_traffic(dom), "peak_source": peak_src,
+                         "traffic": ncu_traffic(dom), "traffic_source": "profiles/r02_pipe_util.json: ncu --set full of this command on another box of the pool (null when absent)",
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": dom_ms},
             "roofline_int_pipe": int_pipe,
             "kernels_ms": {"ntt_strided_pass": p1, "ntt_contig_pass": p2},

@@ -2,6 +2,8 @@
 // Replaces the host schedulers forwardNTT / inverseNTT / *_batch (ntt_60bit.cuh:267-386, 608-697): instead of
 // log2(n)-11 single-stage global passes plus one shared-memory pass, every size runs exactly two kernels.
 #include "internal.h"
+
+#include <atomic>
 #include "ntt_kernels.cuh"
 #include "launch_util.h"
 
@@ -28,11 +30,11 @@ EncodeTiledFn get_encode()
 // L2 prefetch distance in CTAs for a kernel with `resident` CTAs per SM (NTTB200_PF_WAVES: 0 = off; default 1 wave)
 unsigned pf_dist_for(int dev, int resident)
 {
-    static int sms[64] = {0};
+    static std::atomic<int> sms[64];
     static float waves = -1.f;
     if (waves < 0.f) { const char *e = getenv("NTTB200_PF_WAVES"); waves = e ? (float)atof(e) : 1.0f; }
     if (dev < 0 || dev >= 64) return 0;
-    if (!sms[dev]) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (!sms[dev]) { int v = 0; cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); sms[dev] = v; }
     return (unsigned)(waves * (float)(sms[dev] * resident));
 }
 
@@ -91,7 +93,7 @@ static int launch_one(const NttArgs &A, int which, unsigned cnt, const CUtensorM
     constexpr size_t smem_s = (size_t)tpc_s * SC::NT * R * 128 + 1024 + 64;
     constexpr size_t smem_c = (size_t)tpc_c * kContigRows * 128 + 1024 + 64;
     // the dynamic shared-memory opt-in is a per-device function attribute: remember it per (instantiation, device)
-    static bool attr_done[64] = {false};
+    static std::atomic<bool> attr_done[64];      // idempotent per-(instantiation, device) set-up: racing threads both do it
     int dev = 0;
     NTTB200_CHECK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_done[dev]) {
@@ -110,10 +112,12 @@ static int launch_one(const NttArgs &A, int which, unsigned cnt, const CUtensorM
     // which: -1 = whole transform, 0 / 1 = only the first / second kernel in execution order (profiling hook)
     const bool do_strided = which < 0 || (which == 0) == !INV;
     const bool do_contig = which < 0 || (which == 1) == !INV;
-    static int occ_s[64] = {0}, occ_c[64] = {0};      // resident CTAs per SM of the two kernels (prefetch distance = one wave)
+    static std::atomic<int> occ_s[64], occ_c[64];      // resident CTAs per SM of the two kernels (prefetch distance = one wave)
     if (dev >= 0 && dev < 64 && !occ_s[dev]) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s[dev], ntt_strided_pass<P, LOGN, INV>, R * SC::NT, smem_s);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c[dev], ntt_contig_pass<P, LOGN, INV>, kContigRows, smem_c);
+        int os_ = 0, oc_ = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&os_, ntt_strided_pass<P, LOGN, INV>, R * SC::NT, smem_s);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc_, ntt_contig_pass<P, LOGN, INV>, kContigRows, smem_c);
+        occ_s[dev] = os_; occ_c[dev] = oc_;
     }
     NttArgs As = A, Ac = A;
     As.pf_dist = (dev >= 0 && dev < 64) ? pf_dist_for(dev, occ_s[dev]) : 0;

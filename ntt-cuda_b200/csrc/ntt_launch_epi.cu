@@ -2,6 +2,8 @@
 // into its store (epi.cuh).  Lazy-policy moduli only (q < 2^57: every reference parameter set); other rings keep the separate
 // epilogue kernels of bfv_kernels.cuh.
 #include "internal.h"
+
+#include <atomic>
 #include "ntt_kernels.cuh"
 #include "launch_util.h"
 
@@ -18,14 +20,16 @@ static int launch_epi_one(const NttArgs &A, const EpiArgs &E, const CUtensorMap 
     constexpr unsigned tiles_s1 = (((1u << LOGN) >> SC::K1) >> 4) / SC::NT;
     constexpr int tpc_s = tiles_per_cta(tiles_s1);
     constexpr size_t smem_s = (size_t)tpc_s * SC::NT * R * 128 + 1024 + 64;
-    static bool attr_done[64] = {false};
-    static int occ[64] = {0};
+    static std::atomic<bool> attr_done[64];      // idempotent per-(instantiation, device) set-up: racing threads both do it
+    static std::atomic<int> occ[64];
     int dev = 0;
     NTTB200_CHECK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_done[dev]) {
         NTTB200_CHECK(cudaFuncSetAttribute(ntt_strided_pass<P, LOGN, true, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
         if (dev >= 0 && dev < 64) {
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[dev], ntt_strided_pass<P, LOGN, true, EPI>, R * SC::NT, smem_s);
+            int o_ = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o_, ntt_strided_pass<P, LOGN, true, EPI>, R * SC::NT, smem_s);
+            occ[dev] = o_;
             attr_done[dev] = true;
         }
     }

@@ -1,6 +1,8 @@
 // ntt_launch_fused.cu -- launchers of the fused transforms: contig-forward (.) key -> contig-inverse (BFV with loaded keys)
 // and the fused polynomial product (full_poly_mul_device / half_poly_mul_device, poly_arithmetic.cuh:296-310).
 #include "internal.h"
+
+#include <atomic>
 #include "ntt_kernels.cuh"
 #include "launch_util.h"
 
@@ -13,7 +15,7 @@ template <class PF, class PI, int LOGN, int NOUT>
 static int launch_fused_one(const FusedArgs &F, const CUtensorMap &mc, cudaStream_t st)
 {
     constexpr size_t smem = (size_t)kContigRows * 128 * NOUT + 1024 + 16;
-    static bool attr_done[64] = {false};
+    static std::atomic<bool> attr_done[64];      // idempotent per-(instantiation, device) set-up: racing threads both do it
     int dev = 0;
     NTTB200_CHECK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_done[dev]) {
@@ -71,7 +73,7 @@ template <class PF, class PI, int LOGN, bool A_FWD, bool B_FWD>
 static int launch_polymul_one(const PolymulArgs &F, const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mo, cudaStream_t st)
 {
     constexpr size_t smem = (size_t)kContigRows * 128 * 2 + 1024 + 16;
-    static bool attr_done[64] = {false};
+    static std::atomic<bool> attr_done[64];      // idempotent per-(instantiation, device) set-up: racing threads both do it
     int dev = 0;
     NTTB200_CHECK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_done[dev]) {

@@ -1,6 +1,8 @@
 // pointwise.cu -- C ABI of the coefficient-wise kernels and the stand-alone sampling entry points
 // (drop-in targets for poly_arithmetic.cuh:265-353 and distributions.cuh:220-297).
 #include "internal.h"
+
+#include <atomic>
 #include "bfv_kernels.cuh"
 
 #include <cstring>
@@ -11,11 +13,12 @@ namespace nttb200 {
 // grid-stride launch geometry: enough CTAs to fill the machine (multiple of the SM count), never more than the work
 dim3 grid_for(size_t total, int threads)
 {
-    static int sms = 0;      // one process drives GPUs of one kind: the SM count is read once
+    static std::atomic<int> sms{0};      // one process drives GPUs of one kind: the SM count is read once (racing readers store the same value)
     if (!sms) {
-        int dev = 0;
+        int dev = 0, v = 0;
         cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        sms = v;
     }
     size_t need = (total + threads - 1) / threads;
     size_t cap = (size_t)sms * 8;

@@ -49,3 +49,15 @@ def test_exact_multiply_and_relinearize_decrypt_to_the_product(oracle):
     full[:, :rp] = c2
     plain, _ = oracle.decryption_rns(R, full.reshape(-1), sk)
     assert np.array_equal(plain, expect)
+
+
+def test_find_ntt_primes_c_entry_on_the_host():
+    """nttb200_find_ntt_primes is host-only: the library's search equals the Python search used since round 1, roots are primitive."""
+    import nttb200
+    for bits, n, cnt in ((55, 65536, 3), (40, 2048, 4)):
+        q, psi = nttb200.find_ntt_primes(bits, n, cnt)
+        assert (q, psi) == params.find_ntt_primes(bits, n, cnt)
+        for qq, pp in zip(q, psi):
+            assert qq % (2 * n) == 1 and pow(pp, n, qq) == qq - 1
+    q, _ = nttb200.find_ntt_primes(55, 32768, 2, exclude=[36028797017456641])
+    assert 36028797017456641 not in q
