@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 using namespace nttb200;
@@ -404,6 +405,30 @@ static int ensure_scratch(nttb200_bfv *b, size_t ks_bytes, size_t es_count)
     return 0;
 }
 
+// Runs part(stream, first item, count) for the two halves of a batch on two streams when the batch is large enough to fill the GPU
+// twice: every pipeline alternates issue-bound transforms with HBM-bound element-wise kernels, and with two independent halves in
+// flight one half's memory-bound kernels run under the other half's transforms (measured on the sharded calls, where tiles alternate
+// streams: 12 % on encryption).  Fork / join with events, so the caller's stream semantics are unchanged (and it is graph-capturable).
+template <class F>
+static int run_split(nttb200_bfv *b, unsigned batch, cudaStream_t st, F part)
+{
+    const bool worth = b->split && batch >= 2 && (size_t)batch * b->r * b->n >= ((size_t)1 << 24);
+    if (!worth) return part(st, 0u, batch);
+    if (!b->st2) {
+        NTTB200_CHECK(cudaStreamCreateWithFlags(&b->st2, cudaStreamNonBlocking));
+        NTTB200_CHECK(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
+        NTTB200_CHECK(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming));
+    }
+    const unsigned h = batch / 2;
+    NTTB200_CHECK(cudaEventRecord(b->ev_fork, st));
+    NTTB200_CHECK(cudaStreamWaitEvent(b->st2, b->ev_fork, 0));
+    NTTB200_TRY(part(st, 0u, h));
+    NTTB200_TRY(part(b->st2, h, batch - h));
+    NTTB200_CHECK(cudaEventRecord(b->ev_join, b->st2));
+    NTTB200_CHECK(cudaStreamWaitEvent(st, b->ev_join, 0));
+    return 0;
+}
+
 extern "C" {
 
 int nttb200_bfv_create(nttb200_bfv **out, unsigned n, unsigned limbs, const nttb200_u64 *q, const nttb200_u64 *psi_roots, nttb200_u64 t,
@@ -480,6 +505,7 @@ int nttb200_bfv_create(nttb200_bfv **out, unsigned n, unsigned limbs, const nttb
         }
     }
     memset(b->salsa_key, 1, 32);                                                        // distributions.cuh:249 generate_random_default
+    if (const char *e = getenv("NTTB200_BFV_SPLIT")) b->split = atoi(e) != 0;
     while ((1ull << b->tsh) < t) b->tsh++;
     {   // per-limb constants of the epilogue fused into the last inverse kernel (epi.cuh)
         std::vector<EncEpiLimb> ek(rp);
@@ -512,6 +538,9 @@ void nttb200_bfv_destroy(nttb200_bfv *b)
     if (b->key_word_off) cudaFree(b->key_word_off);
     nttb200_host_state_destroy(b->host);
     nttb200_mul_state_destroy(b->mul);
+    if (b->st2) cudaStreamDestroy(b->st2);
+    if (b->ev_fork) cudaEventDestroy(b->ev_fork);
+    if (b->ev_join) cudaEventDestroy(b->ev_join);
     if (b->ub) cudaFree(b->ub);
     if (b->es8) cudaFree(b->es8);
     if (b->enc_epi) cudaFree(b->enc_epi);
@@ -568,9 +597,12 @@ int nttb200_bfv_keygen(nttb200_bfv *b, nttb200_u64 *sk, nttb200_u64 *pk, unsigne
 {
     if (!b || !sk || !pk || !batch || batch > 65535) return NTTB200_EINVAL;
     NTTB200_TRY(nttb200_bfv_reserve(b, batch));
-    const size_t rn = (size_t)b->r * b->n;
-    Pipe P = pipe_from_bfv(b, (cudaStream_t)stream);
-    return run_keygen(P, b->ks, 9 * rn + 4 * (size_t)b->n, b->es, sk, pk, batch, nonce0);
+    const size_t rn = (size_t)b->r * b->n, ks_stride = 9 * rn + 4 * (size_t)b->n;
+    return run_split(b, batch, (cudaStream_t)stream, [&](cudaStream_t s, unsigned first, unsigned cnt) {
+        Pipe P = pipe_from_bfv(b, s);
+        return run_keygen(P, b->ks + (size_t)first * ks_stride, ks_stride, b->es + (size_t)first * b->n, sk + (size_t)first * rn, pk + (size_t)first * 2 * rn, cnt,
+                          nonce0 + first);
+    });
 }
 
 int nttb200_bfv_encrypt(nttb200_bfv *b, nttb200_u64 *c, const nttb200_u64 *pk, int pk_per_item, const nttb200_u64 *m, unsigned batch,
@@ -579,20 +611,29 @@ int nttb200_bfv_encrypt(nttb200_bfv *b, nttb200_u64 *c, const nttb200_u64 *pk, i
     if (!b || !c || !m || !batch || batch > 65535 || (!pk && !b->pk_l)) return NTTB200_EINVAL;
     const bool v2 = !pk && b->ctx->lazy_ok && b->epi_ok && !b->no_fused_epilogue;
     if (!v2) NTTB200_TRY(ensure_scratch(b, 9 * (size_t)b->n * batch, (size_t)2 * b->n * batch));      // encryption draws 9n bytes per item
-    const size_t rn = (size_t)b->r * b->n;
-    Pipe P = pipe_from_bfv(b, (cudaStream_t)stream);
-    if (!pk && b->ctx->lazy_ok && b->epi_ok && !b->no_fused_epilogue) return run_encrypt_v2(b, P, c, m, batch, nonce0);
-    if (!pk) return run_encrypt_fused(P, b->ctx->lazy_ok != 0, b->ks, 9 * (size_t)b->n, b->es, c, b->pk_l, b->pk_ls, m, b->n, b->t, batch, nonce0);
-    return run_encrypt(P, b->ks, 9 * (size_t)b->n, b->es, c, pk, pk_per_item ? 2 * rn : 0, m, b->n, b->t, batch, nonce0);
+    const size_t rn = (size_t)b->r * b->n, n = b->n;
+    if (v2) { Pipe P = pipe_from_bfv(b, (cudaStream_t)stream); return run_encrypt_v2(b, P, c, m, batch, nonce0); }
+    return run_split(b, batch, (cudaStream_t)stream, [&](cudaStream_t s, unsigned first, unsigned cnt) {
+        Pipe P = pipe_from_bfv(b, s);
+        unsigned char *ks = b->ks + (size_t)first * 9 * n;
+        int *es = b->es + (size_t)first * 2 * n;
+        if (!pk) return run_encrypt_fused(P, b->ctx->lazy_ok != 0, ks, 9 * n, es, c + (size_t)first * 2 * rn, b->pk_l, b->pk_ls, m + (size_t)first * n, n, b->t, cnt,
+                                          nonce0 + first);
+        return run_encrypt(P, ks, 9 * n, es, c + (size_t)first * 2 * rn, pk + (pk_per_item ? (size_t)first * 2 * rn : 0), pk_per_item ? 2 * rn : 0,
+                           m + (size_t)first * n, n, b->t, cnt, nonce0 + first);
+    });
 }
 
 int nttb200_bfv_decrypt(nttb200_bfv *b, nttb200_u64 *m_out, nttb200_u64 *c, const nttb200_u64 *sk, int sk_per_item, unsigned batch, void *stream)
 {
     if (!b || !c || !m_out || !batch || batch > 65535 || (!sk && !b->sk_l)) return NTTB200_EINVAL;
-    Pipe P = pipe_from_bfv(b, (cudaStream_t)stream);
+    const size_t rn = (size_t)b->r * b->n, n = b->n;
     DecryptConsts D{b->t, b->gamma, b->mu_gamma, b->gamma_div_2, b->neg_inv_t, b->neg_inv_gamma, b->gamma_bits, b->r - 1, b->bcm};
-    if (!sk) return run_decrypt_fused(P, b->ctx->lazy_ok != 0, c, b->sk_l, b->sk_ls, m_out, b->n, D, batch);
-    return run_decrypt(P, c, sk, sk_per_item ? (size_t)b->r * b->n : 0, m_out, b->n, D, batch);
+    return run_split(b, batch, (cudaStream_t)stream, [&](cudaStream_t s, unsigned first, unsigned cnt) {
+        Pipe P = pipe_from_bfv(b, s);
+        if (!sk) return run_decrypt_fused(P, b->ctx->lazy_ok != 0, c + (size_t)first * 2 * rn, b->sk_l, b->sk_ls, m_out + (size_t)first * n, n, D, cnt);
+        return run_decrypt(P, c + (size_t)first * 2 * rn, sk + (sk_per_item ? (size_t)first * rn : 0), sk_per_item ? rn : 0, m_out + (size_t)first * n, n, D, cnt);
+    });
 }
 
 // ---- homomorphic add and plaintext multiply (the reference stops at decryption) ------------------------------------

@@ -29,6 +29,11 @@ struct nttb200_bfv {
     unsigned *key_word_off = nullptr; unsigned key_half_words = 0;   // same for keys (all r limbs)
     struct nttb200_host_state *host = nullptr;        // staging + streams of the host-buffer entry points (bfv_host.cu)
     struct nttb200_mul_state *mul = nullptr;          // auxiliary base, constants, relinearisation key, work buffers (bfv_mul.cu)
+    // batched calls run their two halves on two streams (fork / join with events): the HBM-bound element-wise kernels of one half
+    // overlap the issue-bound transforms of the other
+    cudaStream_t st2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int split = 1;                                    // 0: never split (A/B knob, NTTB200_BFV_SPLIT=0)
     bool enc_lazy = false, dec_fast = false, all_exact = false;
     bool epi_ok = false;                              // every limb qualifies for the epilogue fused into the last inverse kernel
     bool no_fused_epilogue = true;                    // default: separate (HBM-bound) epilogue kernels; false = epilogue in the last inverse kernel's store (A/B, slower)

@@ -417,16 +417,26 @@ int nttb200_bfv_encrypt_sharded(nttb200_bfv *b, nttb200_comm *comm, nttb200_u64 
     }
     // 4. forward transform of u, (.) pk, contiguous inverse pass on the owned (limb, block) tiles; tiles alternate between two streams
     NTTB200_CHECK(cudaStreamWaitEvent(s->st2, s->ev[2], 0));   // ub is ready; the second stream joins here
+    // (one rank: the single block is cut in two pieces so that both streams have work)
+    const unsigned pieces = (G == 1 && per >= 2) ? 2u : 1u;
+    auto piece_range = [&](unsigned pc, unsigned &first, unsigned &cnt_items) { first = pc * (per / pieces); cnt_items = pc + 1 == pieces ? per - first : per / pieces; };
     for (unsigned j = 0; j < G; j++)
-        if (blk[j].limb_count)
-            TRY(enc_front(b, (j & 1) ? P2 : P, c_shard + blk[j].offset, blk[j].limb_count, blk[j].first_limb, blk[j].limb_count, per,
-                          ub + (size_t)blk[j].first_item * n));
+        for (unsigned pc = 0; pc < pieces && blk[j].limb_count; pc++) {
+            unsigned f0, ci;
+            piece_range(pc, f0, ci);
+            const unsigned cnt = blk[j].limb_count;
+            TRY(enc_front(b, ((j + pc) & 1) ? P2 : P, c_shard + blk[j].offset + (size_t)f0 * 2 * cnt * n, cnt, blk[j].first_limb, cnt, ci,
+                          ub + ((size_t)blk[j].first_item + f0) * n));
+        }
     if (G > 1) { NTTB200_CHECK(cudaStreamWaitEvent(st, s->ev[3], 0)); NTTB200_CHECK(cudaStreamWaitEvent(s->st2, s->ev[3], 0)); }
     // 5. last inverse kernel + mod-switch + Delta*m (same stream as the tile's front: no cross-stream dependency)
     for (unsigned j = 0; j < G; j++)
-        if (blk[j].limb_count) {
-            const size_t it = blk[j].first_item;
-            TRY(enc_finish_limbs(b, (j & 1) ? P2 : P, c_shard + blk[j].offset, blk[j].limb_count, blk[j].first_limb, blk[j].limb_count, per, cl + it * 2 * n,
+        for (unsigned pc = 0; pc < pieces && blk[j].limb_count; pc++) {
+            unsigned f0, ci;
+            piece_range(pc, f0, ci);
+            const unsigned cnt = blk[j].limb_count;
+            const size_t it = (size_t)blk[j].first_item + f0;
+            TRY(enc_finish_limbs(b, ((j + pc) & 1) ? P2 : P, c_shard + blk[j].offset + (size_t)f0 * 2 * cnt * n, cnt, blk[j].first_limb, cnt, ci, cl + it * 2 * n,
                                  (size_t)2 * n, (size_t)n, es + it * 2 * n, m + it * n, (size_t)n));
         }
     NTTB200_CHECK(cudaEventRecord(s->ev[4], s->st2));          // the second stream rejoins the caller's
@@ -464,9 +474,16 @@ int nttb200_bfv_decrypt_sharded(nttb200_bfv *b, nttb200_comm *comm, nttb200_u64 
     NTTB200_CHECK(cudaStreamWaitEvent(s->st2, s->ev[1], 0));
     size_t evi = 2;
     const size_t own = (size_t)g * per;
-    if (G == 1) {
-        TRY(dec_partial(b, P, partial, packed, c_shard, blk[0].limb_count, blk[0].first_limb, blk[0].limb_count, batch));
-        TRY(dec_finish(b, m_out, 0, partial, packed, batch, st));
+    if (G == 1) {          // one rank: the two halves of the batch on the two compute streams (HBM-bound kernels under issue-bound ones)
+        const unsigned cnt = blk[0].limb_count, h0 = batch >= 2 ? batch / 2 : batch;
+        TRY(dec_partial(b, P, partial, packed, c_shard, cnt, blk[0].first_limb, cnt, h0));
+        TRY(dec_finish(b, m_out, 0, partial, packed, h0, st));
+        if (batch > h0) {
+            TRY(dec_partial(b, P2, partial + (size_t)h0 * pw, packed, c_shard + (size_t)h0 * 2 * cnt * n, cnt, blk[0].first_limb, cnt, batch - h0));
+            TRY(dec_finish(b, m_out + (size_t)h0 * n, 0, partial + (size_t)h0 * pw, packed, batch - h0, s->st2));
+        }
+        NTTB200_CHECK(cudaEventRecord(s->ev[evi], s->st2));
+        NTTB200_CHECK(cudaStreamWaitEvent(st, s->ev[evi], 0));
         return 0;
     }
     const bool p2p_mode = (s->mode == 2 || s->mode == 3) && !comm->fake;
