@@ -474,14 +474,9 @@ int nttb200_bfv_decrypt_sharded(nttb200_bfv *b, nttb200_comm *comm, nttb200_u64 
     NTTB200_CHECK(cudaStreamWaitEvent(s->st2, s->ev[1], 0));
     size_t evi = 2;
     const size_t own = (size_t)g * per;
-    if (G == 1) {          // one rank: the two halves of the batch on the two compute streams (HBM-bound kernels under issue-bound ones)
-        const unsigned cnt = blk[0].limb_count, h0 = batch >= 2 ? batch / 2 : batch;
-        TRY(dec_partial(b, P, partial, packed, c_shard, cnt, blk[0].first_limb, cnt, h0));
-        TRY(dec_finish(b, m_out, 0, partial, packed, h0, st));
-        if (batch > h0) {
-            TRY(dec_partial(b, P2, partial + (size_t)h0 * pw, packed, c_shard + (size_t)h0 * 2 * cnt * n, cnt, blk[0].first_limb, cnt, batch - h0));
-            TRY(dec_finish(b, m_out + (size_t)h0 * n, 0, partial + (size_t)h0 * pw, packed, batch - h0, s->st2));
-        }
+    if (G == 1) {          // one rank, one block (two halves on two streams were measured 3 % SLOWER here: decryption's epilogue is multiplier-bound, not HBM-bound)
+        TRY(dec_partial(b, P, partial, packed, c_shard, blk[0].limb_count, blk[0].first_limb, blk[0].limb_count, batch));
+        TRY(dec_finish(b, m_out, 0, partial, packed, batch, st));
         NTTB200_CHECK(cudaEventRecord(s->ev[evi], s->st2));
         NTTB200_CHECK(cudaStreamWaitEvent(st, s->ev[evi], 0));
         return 0;
