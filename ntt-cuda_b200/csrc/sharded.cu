@@ -101,12 +101,12 @@ struct nttb200_shard_state {
         unsigned char *local = nullptr;
         size_t bytes = 0;
         std::vector<unsigned char *> peer;        // peer[g] = rank g's buffer as mapped here (peer[rank] = local)
-    } sym[3];
+    } sym[4];
     int p2p_failed = 0;
     int *flag = nullptr;                          // device ints of the barrier / agreement all-reduces
     cudaStream_t st2 = nullptr;                   // second compute stream: independent tiles overlap their launch tails
 };
-enum { kSymSlots = 0, kSymCl, kSymEs };
+enum { kSymSlots = 0, kSymCl, kSymEs, kSymUb };
 enum { kBufUb = 0, kBufEs, kBufCl, kBufPartial, kBufRecv, kBufPlain };
 
 static void sym_release(nttb200_shard_state::Sym &y)
@@ -367,7 +367,7 @@ int nttb200_bfv_encrypt_sharded(nttb200_bfv *b, nttb200_comm *comm, nttb200_u64 
     if (per > 65535) return NTTB200_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     nttb200_shard_state *s;
-    TRY(shard_state(b, &s, 8));
+    TRY(shard_state(b, &s, 10));
     std::vector<nttb200_shard_block> blk(G);
     plan_blocks(r - 1, n, batch, G, g, blk.data(), nullptr);
     unsigned char *ub; signed char *es; u64 *cl;
@@ -376,9 +376,12 @@ int nttb200_bfv_encrypt_sharded(nttb200_bfv *b, nttb200_comm *comm, nttb200_u64 
     // rank PUSHES its block into the peers' buffers with copy-engine copies: no collective kernel takes SMs from the transforms),
     // plain scratch + ncclAllGather otherwise
     const bool want_p2p = G > 1 && !comm->fake && s->mode >= 2;
-    if (want_p2p) { TRY(sym_setup(s, comm, kSymCl, (size_t)batch * 2 * n * 8)); TRY(sym_setup(s, comm, kSymEs, (size_t)batch * 2 * n)); }
+    if (want_p2p) {
+        TRY(sym_setup(s, comm, kSymCl, (size_t)batch * 2 * n * 8)); TRY(sym_setup(s, comm, kSymEs, (size_t)batch * 2 * n));
+        TRY(sym_setup(s, comm, kSymUb, (size_t)batch * n));
+    }
     const bool p2p = want_p2p && !s->p2p_failed;
-    if (p2p) { cl = (u64 *)s->sym[kSymCl].local; es = (signed char *)s->sym[kSymEs].local; }
+    if (p2p) { cl = (u64 *)s->sym[kSymCl].local; es = (signed char *)s->sym[kSymEs].local; ub = s->sym[kSymUb].local; }
     else { TRY(shard_buf(s, kBufEs, (size_t)batch * 2 * n, (void **)&es)); TRY(shard_buf(s, kBufCl, (size_t)batch * 2 * n * 8, (void **)&cl)); }
     Pipe P = pipe_from_bfv(b, st), P2 = pipe_from_bfv(b, s->st2);
     const size_t own = (size_t)g * per;
@@ -389,9 +392,23 @@ int nttb200_bfv_encrypt_sharded(nttb200_bfv *b, nttb200_comm *comm, nttb200_u64 
     if (p2p) BARRIER();
     NTTB200_CHECK(cudaEventRecord(s->ev[1], s->cs));
     NTTB200_CHECK(cudaStreamWaitEvent(st, s->ev[1], 0));
-    // 1. randomness: u bytes of every item (every rank transforms u on its limbs), gaussian draws of the block this rank finishes
-    TRY(enc_sample(b, ub, nullptr, batch, nonce0, 1, 0, st));
-    TRY(enc_sample(b, nullptr, es + own * 2 * n, per, nonce0 + own, 0, 1, st));
+    // 1. randomness.  Every rank transforms u on its limbs of EVERY item, but drawing all of it on every rank costs world x the
+    //    sampling (0.25 ms per rank at 4096 ciphertexts): with peer-to-peer buffers each rank draws u and e of its own block only and
+    //    pushes the u bytes (n per item) to the peers; otherwise it draws every item's u itself.
+    if (p2p) {
+        TRY(enc_sample(b, ub + own * n, es + own * 2 * n, per, nonce0 + own, 1, 1, st));
+        NTTB200_CHECK(cudaEventRecord(s->ev[5], st));
+        NTTB200_CHECK(cudaStreamWaitEvent(s->cs, s->ev[5], 0));
+        for (unsigned tau = 1; tau < G; tau++) {
+            const unsigned k = (g + tau) % G;
+            NTTB200_CHECK(cudaMemcpyAsync(s->sym[kSymUb].peer[k] + own * n, ub + own * n, (size_t)per * n, cudaMemcpyDeviceToDevice, s->cs));
+        }
+        BARRIER();
+        NTTB200_CHECK(cudaEventRecord(s->ev[6], s->cs));           // every block's u bytes have arrived
+    } else {
+        TRY(enc_sample(b, ub, nullptr, batch, nonce0, 1, 0, st));
+        TRY(enc_sample(b, nullptr, es + own * 2 * n, per, nonce0 + own, 0, 1, st));
+    }
     // 2. dropped limb of the own block, finished (+ e, rounding offset)
     u64 *cl_own = cl + own * 2 * n;
     TRY(enc_front(b, P, cl_own, 1, r - 1, 1, per, ub + own * n));
@@ -416,7 +433,8 @@ int nttb200_bfv_encrypt_sharded(nttb200_bfv *b, nttb200_comm *comm, nttb200_u64 
         NTTB200_CHECK(cudaEventRecord(s->ev[3], s->cs));
     }
     // 4. forward transform of u, (.) pk, contiguous inverse pass on the owned (limb, block) tiles; tiles alternate between two streams
-    NTTB200_CHECK(cudaStreamWaitEvent(s->st2, s->ev[2], 0));   // ub is ready; the second stream joins here
+    NTTB200_CHECK(cudaStreamWaitEvent(s->st2, s->ev[2], 0));   // the second stream joins here
+    if (p2p) { NTTB200_CHECK(cudaStreamWaitEvent(st, s->ev[6], 0)); NTTB200_CHECK(cudaStreamWaitEvent(s->st2, s->ev[6], 0)); }   // the peers' u bytes
     // (one rank: the single block is cut in two pieces so that both streams have work)
     const unsigned pieces = (G == 1 && per >= 2) ? 2u : 1u;
     auto piece_range = [&](unsigned pc, unsigned &first, unsigned &cnt_items) { first = pc * (per / pieces); cnt_items = pc + 1 == pieces ? per - first : per / pieces; };
@@ -481,8 +499,8 @@ int nttb200_bfv_decrypt_sharded(nttb200_bfv *b, nttb200_comm *comm, nttb200_u64 
         NTTB200_CHECK(cudaStreamWaitEvent(st, s->ev[evi], 0));
         return 0;
     }
-    const bool p2p_mode = (s->mode == 2 || s->mode == 3) && !comm->fake;
-    if (p2p_mode && !s->p2p_failed) {
+    const bool p2p_mode = s->mode == 2 || s->mode == 3;
+    if (p2p_mode && !s->p2p_failed && !comm->fake) {
         // Peer-to-peer: the partial-sum kernel of a tile writes straight into slot `rank` of the buffer of the items' OWNER, mapped
         // here through CUDA IPC -- NVLink stores issued by the kernel that produces the sums: compute and transfer are one kernel, no
         // collective kernel competes for SMs, no staging copy.  A 4-byte all-reduce is the "everybody has deposited" barrier; the
@@ -490,7 +508,7 @@ int nttb200_bfv_decrypt_sharded(nttb200_bfv *b, nttb200_comm *comm, nttb200_u64 
         const int rc = sym_setup(s, comm, kSymSlots, (size_t)batch * pw * 8);
         if (rc) return rc;
     }
-    if (p2p_mode && !s->p2p_failed) {
+    if (p2p_mode && (comm->fake || !s->p2p_failed)) {
         // Every rank visits the owners in ROTATED order (rank g starts with owner g + 1): at any moment each owner receives from one
         // sender -- a balanced all-to-all; in lock-step order all 7 peers would store into the same GPU at once (measured: 12.8 ms
         // instead of 9.8 for 4096 ciphertexts on 8 GPUs).
@@ -502,7 +520,9 @@ int nttb200_bfv_decrypt_sharded(nttb200_bfv *b, nttb200_comm *comm, nttb200_u64 
             for (unsigned tau = 0; tau < G; tau++) {
                 const unsigned j = (g + 1 + tau) % G;
                 const unsigned cnt = blk[j].limb_count;
-                u64 *dst = (u64 *)s->sym[kSymSlots].peer[j] + ((size_t)g * per + (size_t)c * piece) * pw;   // my slot at owner j, piece c
+                // my slot at owner j, piece c (profiling with a fake communicator: the same volume into local scratch)
+                u64 *dst = comm->fake ? partial + ((size_t)j * per + (size_t)c * piece) * pw
+                                      : (u64 *)s->sym[kSymSlots].peer[j] + ((size_t)g * per + (size_t)c * piece) * pw;
                 const bool alt = (tau & 1) != 0;
                 if (cnt) TRY(dec_partial(b, alt ? P2 : P, dst, packed, c_shard + blk[j].offset + (size_t)c * piece * 2 * cnt * n, cnt, blk[j].first_limb, cnt, piece));
                 else NTTB200_CHECK(cudaMemsetAsync(dst, 0, (size_t)piece * pw * 8, alt ? s->st2 : st));
@@ -513,7 +533,7 @@ int nttb200_bfv_decrypt_sharded(nttb200_bfv *b, nttb200_comm *comm, nttb200_u64 
                 evi++;
             }
             BARRIER();                                                                            // round c is deposited everywhere
-            const u64 *mine = (const u64 *)s->sym[kSymSlots].local + (size_t)c * piece * pw;     // piece c of every slot of my buffer
+            const u64 *mine = (comm->fake ? partial : (const u64 *)s->sym[kSymSlots].local) + (size_t)c * piece * pw;     // piece c of every slot of my buffer
             if (out16) {
                 // staging is round-major: plain[c][owner][piece][n]
                 unsigned short *stg = plain + (size_t)c * G * piece * n;
