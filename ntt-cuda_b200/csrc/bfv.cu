@@ -338,8 +338,8 @@ int enc_finish_limbs(const nttb200_bfv *b, const Pipe &P0, u64 *c, unsigned slot
     KCHECK();
     return 0;
 }
-int dec_partial(const nttb200_bfv *b, const Pipe &P0, u64 *partial, int packed, u64 *c_shard, unsigned slots, unsigned first, unsigned count,
-                unsigned items)
+// decryption of a limb window, step 1: NTT(c1) (.) sk -> INTT on `items` ciphertext tiles c_shard[item][2][slots][n] (fused key kernel)
+int dec_transforms(const nttb200_bfv *b, const Pipe &P0, u64 *c_shard, unsigned slots, unsigned first, unsigned count, unsigned items)
 {
     const unsigned n = P0.n;
     const size_t item = (size_t)2 * slots * n, c1_off = (size_t)slots * n;
@@ -348,11 +348,25 @@ int dec_partial(const nttb200_bfv *b, const Pipe &P0, u64 *partial, int packed, 
     NTTB200_TRY(launch_fused_mul(b->ctx->lazy_ok != 0, P.logn, pipe_args(P, false, c_shard, items * 2 * slots, count, 2 * slots, item), P.psiinv,
                                  P.psiinv_s, b->sk_l + (size_t)first * n, b->sk_ls + (size_t)first * n, 0, 0, count, slots, slots, slots, items, 1, P.st));
     NTTB200_TRY(pipe_ntt_pass(P, true, 1, c_shard + c1_off, items * count, count, count, item));
+    return 0;
+}
+// step 2: the window's partial base-conversion sums of `items` tiles (packed: 1.25 n words per item, else 2 n)
+int dec_partial_sums(const nttb200_bfv *b, const Pipe &P0, u64 *partial, int packed, const u64 *c_shard, unsigned slots, unsigned first, unsigned count,
+                     unsigned items)
+{
+    const unsigned n = P0.n;
+    const size_t item = (size_t)2 * slots * n, c1_off = (size_t)slots * n;
     DecryptConsts D{b->t, b->gamma, b->mu_gamma, b->gamma_div_2, b->neg_inv_t, b->neg_inv_gamma, b->gamma_bits, b->r - 1, b->bcm};
-    if (packed) k_decrypt_partial<true><<<pair_grid(n, items, 1), pair_block(n, items, 1), 0, P.st>>>(c_shard, item, c1_off, partial, n, items, first, count, D, P0.L);
-    else k_decrypt_partial<false><<<pair_grid(n, items, 1), pair_block(n, items, 1), 0, P.st>>>(c_shard, item, c1_off, partial, n, items, first, count, D, P0.L);
+    if (packed) k_decrypt_partial<true><<<pair_grid(n, items, 1), pair_block(n, items, 1), 0, P0.st>>>(c_shard, item, c1_off, partial, n, items, first, count, D, P0.L);
+    else k_decrypt_partial<false><<<pair_grid(n, items, 1), pair_block(n, items, 1), 0, P0.st>>>(c_shard, item, c1_off, partial, n, items, first, count, D, P0.L);
     KCHECK();
     return 0;
+}
+int dec_partial(const nttb200_bfv *b, const Pipe &P0, u64 *partial, int packed, u64 *c_shard, unsigned slots, unsigned first, unsigned count,
+                unsigned items)
+{
+    NTTB200_TRY(dec_transforms(b, P0, c_shard, slots, first, count, items));
+    return dec_partial_sums(b, P0, partial, packed, c_shard, slots, first, count, items);
 }
 // partial sums -> plaintext (16-bit words or u64 coefficients); expansion of gathered 16-bit plaintexts
 int dec_finish(const nttb200_bfv *b, void *out, int out16, const u64 *partial_sum, int packed, unsigned items, cudaStream_t st, unsigned slots,

@@ -77,6 +77,9 @@ int enc_finish_limbs(const nttb200_bfv *b, const Pipe &P, u64 *c, unsigned slots
 // decryption of limbs [first, first + count) up to the cross-limb sums (loaded secret key: fused kernel); c_shard[item][2][slots][n]
 int dec_partial(const nttb200_bfv *b, const Pipe &P, u64 *partial, int packed, u64 *c_shard, unsigned slots, unsigned first, unsigned count,
                 unsigned items);
+int dec_transforms(const nttb200_bfv *b, const Pipe &P, u64 *c_shard, unsigned slots, unsigned first, unsigned count, unsigned items);
+int dec_partial_sums(const nttb200_bfv *b, const Pipe &P, u64 *partial, int packed, const u64 *c_shard, unsigned slots, unsigned first, unsigned count,
+                     unsigned items);
 int dec_finish(const nttb200_bfv *b, void *out, int out16, const u64 *partial_sum, int packed, unsigned items, cudaStream_t st, unsigned slots = 1,
                size_t slot_stride = 0);
 int dec_expand16(const unsigned short *in, u64 *out, size_t total, cudaStream_t st, unsigned blocks = 1, size_t out_block_stride = 0);

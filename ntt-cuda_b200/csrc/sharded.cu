@@ -179,6 +179,37 @@ static void plan_blocks(unsigned rp, unsigned n, unsigned batch, unsigned world,
     if (words) *words = off;
 }
 
+// Consecutive item blocks in which the rank holds the SAME limb window are contiguous in its shard buffer (and in every per-item
+// array), so their transforms run as one launch set: at (16384, 9 limbs) on 8 GPUs a rank owns one limb of every block = ONE run of
+// 4096 items instead of eight launch sets of 512; at (32768, 16 limbs) three runs.  Large runs are cut in two so that both compute
+// streams have work.
+struct ShardRun { unsigned j0, j1, first_limb, cnt, first_item, items; size_t offset; int stream; };
+static std::vector<ShardRun> shard_runs(const std::vector<nttb200_shard_block> &blk, unsigned per, unsigned n)
+{
+    std::vector<ShardRun> runs;
+    const unsigned G = (unsigned)blk.size();
+    for (unsigned j = 0; j < G;) {
+        if (!blk[j].limb_count) { j++; continue; }
+        unsigned k = j + 1;
+        while (k < G && blk[k].limb_count == blk[j].limb_count && blk[k].first_limb == blk[j].first_limb) k++;
+        runs.push_back(ShardRun{j, k, blk[j].first_limb, blk[j].limb_count, j * per, (k - j) * per, blk[j].offset, 0});
+        j = k;
+    }
+    // at least two parts of comparable size: cut the largest run until there are >= 2 (whole blocks when possible)
+    while (runs.size() == 1 && runs[0].items >= 2) {
+        ShardRun a = runs[0], c = runs[0];
+        const unsigned blocks = a.j1 - a.j0;
+        const unsigned cut_items = blocks >= 2 ? (blocks / 2) * per : a.items / 2;
+        a.items = cut_items; a.j1 = a.j0 + (blocks >= 2 ? blocks / 2 : blocks);
+        c.first_item = a.first_item + cut_items; c.items = runs[0].items - cut_items; c.j0 = blocks >= 2 ? a.j1 : a.j0;
+        c.offset = a.offset + (size_t)cut_items * 2 * a.cnt * n;
+        runs.clear(); runs.push_back(a); runs.push_back(c);
+    }
+    // alternate streams, largest first on the caller's stream
+    for (size_t i = 0; i < runs.size(); i++) runs[i].stream = (int)(i & 1);
+    return runs;
+}
+
 // Symmetric-buffer set-up (collective: every rank calls it with the same index and size): allocate this rank's buffer, exchange
 // CUDA IPC handles through an NCCL all-gather, map every peer's buffer.  Any failure (IPC unsupported in this environment) disables
 // the peer-to-peer paths on ALL ranks -- the outcome is agreed through an all-reduce so that no rank is left in a different protocol.
@@ -435,28 +466,16 @@ int nttb200_bfv_encrypt_sharded(nttb200_bfv *b, nttb200_comm *comm, nttb200_u64 
     // 4. forward transform of u, (.) pk, contiguous inverse pass on the owned (limb, block) tiles; tiles alternate between two streams
     NTTB200_CHECK(cudaStreamWaitEvent(s->st2, s->ev[2], 0));   // the second stream joins here
     if (p2p) { NTTB200_CHECK(cudaStreamWaitEvent(st, s->ev[6], 0)); NTTB200_CHECK(cudaStreamWaitEvent(s->st2, s->ev[6], 0)); }   // the peers' u bytes
-    // (one rank: the single block is cut in two pieces so that both streams have work)
-    const unsigned pieces = (G == 1 && per >= 2) ? 2u : 1u;
-    auto piece_range = [&](unsigned pc, unsigned &first, unsigned &cnt_items) { first = pc * (per / pieces); cnt_items = pc + 1 == pieces ? per - first : per / pieces; };
-    for (unsigned j = 0; j < G; j++)
-        for (unsigned pc = 0; pc < pieces && blk[j].limb_count; pc++) {
-            unsigned f0, ci;
-            piece_range(pc, f0, ci);
-            const unsigned cnt = blk[j].limb_count;
-            TRY(enc_front(b, ((j + pc) & 1) ? P2 : P, c_shard + blk[j].offset + (size_t)f0 * 2 * cnt * n, cnt, blk[j].first_limb, cnt, ci,
-                          ub + ((size_t)blk[j].first_item + f0) * n));
-        }
+    const std::vector<ShardRun> runs = shard_runs(blk, per, n);
+    for (const ShardRun &R : runs)
+        TRY(enc_front(b, R.stream ? P2 : P, c_shard + R.offset, R.cnt, R.first_limb, R.cnt, R.items, ub + (size_t)R.first_item * n));
     if (G > 1) { NTTB200_CHECK(cudaStreamWaitEvent(st, s->ev[3], 0)); NTTB200_CHECK(cudaStreamWaitEvent(s->st2, s->ev[3], 0)); }
-    // 5. last inverse kernel + mod-switch + Delta*m (same stream as the tile's front: no cross-stream dependency)
-    for (unsigned j = 0; j < G; j++)
-        for (unsigned pc = 0; pc < pieces && blk[j].limb_count; pc++) {
-            unsigned f0, ci;
-            piece_range(pc, f0, ci);
-            const unsigned cnt = blk[j].limb_count;
-            const size_t it = (size_t)blk[j].first_item + f0;
-            TRY(enc_finish_limbs(b, ((j + pc) & 1) ? P2 : P, c_shard + blk[j].offset + (size_t)f0 * 2 * cnt * n, cnt, blk[j].first_limb, cnt, ci, cl + it * 2 * n,
-                                 (size_t)2 * n, (size_t)n, es + it * 2 * n, m + it * n, (size_t)n));
-        }
+    // 5. last inverse kernel + mod-switch + Delta*m (same stream as the run's front: no cross-stream dependency)
+    for (const ShardRun &R : runs) {
+        const size_t it = R.first_item;
+        TRY(enc_finish_limbs(b, R.stream ? P2 : P, c_shard + R.offset, R.cnt, R.first_limb, R.cnt, R.items, cl + it * 2 * n, (size_t)2 * n, (size_t)n,
+                             es + it * 2 * n, m + it * n, (size_t)n));
+    }
     NTTB200_CHECK(cudaEventRecord(s->ev[4], s->st2));          // the second stream rejoins the caller's
     NTTB200_CHECK(cudaStreamWaitEvent(st, s->ev[4], 0));
     return 0;
@@ -516,6 +535,20 @@ int nttb200_bfv_decrypt_sharded(nttb200_bfv *b, nttb200_comm *comm, nttb200_u64 
         //         next round's transforms run; mode 3: one round (largest launches, everything after the last transform is exposed).
         const unsigned rounds = s->mode == 2 ? chunks : 1u;
         const unsigned piece = per / rounds;
+        // phase A: the transforms of the rank's whole share, run by run (large launches)
+        const std::vector<ShardRun> runs = shard_runs(blk, per, n);
+        std::vector<int> stream_of(G, 0);
+        for (const ShardRun &R : runs) {
+            TRY(dec_transforms(b, R.stream ? P2 : P, c_shard + R.offset, R.cnt, R.first_limb, R.cnt, R.items));
+            for (unsigned j = R.j0; j < R.j1; j++) stream_of[j] = R.stream;
+        }
+        if (runs.size() == 2 && runs[0].j0 == runs[1].j0) {      // one block cut in two (one owner): its sums need both halves
+            NTTB200_CHECK(cudaEventRecord(s->ev[evi], s->st2));
+            NTTB200_CHECK(cudaStreamWaitEvent(st, s->ev[evi], 0));
+            evi++;
+            stream_of[runs[0].j0] = 0;
+        }
+        // phase B: partial sums of (owner j, piece c), deposited at the owner, round by round
         for (unsigned c = 0; c < rounds; c++) {
             for (unsigned tau = 0; tau < G; tau++) {
                 const unsigned j = (g + 1 + tau) % G;
@@ -523,9 +556,9 @@ int nttb200_bfv_decrypt_sharded(nttb200_bfv *b, nttb200_comm *comm, nttb200_u64 
                 // my slot at owner j, piece c (profiling with a fake communicator: the same volume into local scratch)
                 u64 *dst = comm->fake ? partial + ((size_t)j * per + (size_t)c * piece) * pw
                                       : (u64 *)s->sym[kSymSlots].peer[j] + ((size_t)g * per + (size_t)c * piece) * pw;
-                const bool alt = (tau & 1) != 0;
-                if (cnt) TRY(dec_partial(b, alt ? P2 : P, dst, packed, c_shard + blk[j].offset + (size_t)c * piece * 2 * cnt * n, cnt, blk[j].first_limb, cnt, piece));
-                else NTTB200_CHECK(cudaMemsetAsync(dst, 0, (size_t)piece * pw * 8, alt ? s->st2 : st));
+                const bool alt = stream_of[j] != 0;
+                if (cnt) TRY(dec_partial_sums(b, alt ? P2 : P, dst, packed, c_shard + blk[j].offset + (size_t)c * piece * 2 * cnt * n, cnt, blk[j].first_limb, cnt, piece));
+                else NTTB200_CHECK(cudaMemsetAsync(dst, 0, (size_t)piece * pw * 8, st));
             }
             for (cudaStream_t cst : {st, s->st2}) {              // both compute streams have deposited round c
                 NTTB200_CHECK(cudaEventRecord(s->ev[evi], cst));
