@@ -319,11 +319,13 @@ NTTB200_API int nttb200_bfv_encrypt_sharded(nttb200_bfv *bfv, nttb200_comm *comm
                                             nttb200_u64 nonce0, void *stream);
 /* decryption_rns bfv_decryption.cuh:76, limb-sharded: c_shard is consumed; m_out[batch][n] is complete on every rank.  Uses the
  * loaded secret key.  The cross-limb sum (poly_arithmetic.cuh:217-251) is the path's one real exchange; block by block:
- *   mode 2 (default): the kernel that forms a rank's partial base-conversion sums (packed to 10 bytes per coefficient) stores them
- *           straight into that rank's slot of a buffer at the block's OWNER, mapped through CUDA IPC (NVLink peer stores: compute and
- *           transfer are one kernel, no collective kernel takes SMs); a 4-byte all-reduce per block is the barrier; the owner sums
- *           the slots while rounding (dec_round :253-263) and broadcasts the block's plaintext as 16-bit words -- the path's final
- *           gather, pipelined block by block.  Falls back to mode 0 on all ranks when CUDA IPC is unavailable.
+ *   mode 4 (default): a rank's partial base-conversion sums of a tile (packed to 10 bytes per coefficient) are pushed by the copy
+ *           engines into that rank's slot of a buffer at the items' OWNER, mapped through CUDA IPC (no collective kernel takes SMs from
+ *           the transforms); owners are visited in rotated order (one incoming stream per GPU at a time); a 4-byte all-reduce per
+ *           round is the barrier; the owner sums the slots while rounding (dec_round :253-263) and the round's plaintext is
+ *           all-gathered as 16-bit words -- the path's final gather -- under the next round's transforms.
+ *   mode 2 / 3: the same with the sums stored into the owner's slot directly by the kernel that forms them (3: one round).
+ *           Modes 2-4 fall back to mode 0 on all ranks when CUDA IPC is unavailable.
  *   mode 0: ncclReduce of the sums to the owner, each block in `chunks` pieces, on a second stream next to the transforms.
  *   mode 1: `chunks` ncclReduceScatter calls, rounding, one ncclAllGather. */
 NTTB200_API int nttb200_bfv_decrypt_sharded(nttb200_bfv *bfv, nttb200_comm *comm, nttb200_u64 *m_out, nttb200_u64 *c_shard, unsigned batch,
@@ -336,7 +338,7 @@ NTTB200_API int nttb200_bfv_decrypt_partial_tile(nttb200_bfv *bfv, nttb200_u64 *
                                                  unsigned limb_count, unsigned batch, void *stream);
 NTTB200_API int nttb200_bfv_decrypt_finish_tile(nttb200_bfv *bfv, void *m_out, int out16, const nttb200_u64 *partial_sum, int packed,
                                                 unsigned batch, void *stream);
-/* modes as above; chunks default 4.  Env NTTB200_SHARD_MODE / NTTB200_SHARD_CHUNKS set the defaults of new contexts. */
+/* modes as above; chunks = 0: the measured best of the mode.  Env NTTB200_SHARD_MODE / NTTB200_SHARD_CHUNKS set the defaults of new contexts. */
 NTTB200_API int nttb200_bfv_shard_config(nttb200_bfv *bfv, int mode, unsigned chunks);
 /* device-local conversion between the reference layout c[batch][2][r][n] and the calling rank's shard */
 NTTB200_API int nttb200_bfv_shard_from_full(nttb200_bfv *bfv, unsigned world, unsigned rank, nttb200_u64 *c_shard, const nttb200_u64 *c_full,

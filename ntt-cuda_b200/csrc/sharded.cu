@@ -93,9 +93,11 @@ struct nttb200_shard_state {
     std::vector<cudaEvent_t> ev;
     unsigned char *buf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t cap[6] = {0, 0, 0, 0, 0, 0};
-    int mode = 2;                                 // 2: peer-to-peer deposit of the partial sums at the block's owner (falls back to 0 when
-                                                  //    CUDA IPC is unavailable); 0: per-block ncclReduce to the owner; 1: chunked ncclReduceScatter
-    unsigned chunks = 4;
+    int mode = 4;                                 // decryption's exchange.  4 (default): partial sums into local scratch, pushed into the owner's
+                                                  //    slot by the copy engines; 2 / 3: stored there directly by the kernel (3: one round);
+                                                  //    0: per-piece ncclReduce to the owner; 1: chunked ncclReduceScatter.  2-4 need CUDA IPC and
+                                                  //    fall back to 0 on all ranks without it.
+    unsigned chunks = 0;                          // rounds / pieces per block; 0 = the measured best of the mode (4: 2, others: 4)
     // symmetric buffers: one cudaMalloc per rank, mapped into every other rank through CUDA IPC (peer stores / copy-engine pushes)
     struct Sym {
         unsigned char *local = nullptr;
@@ -133,7 +135,7 @@ static int shard_state(nttb200_bfv *b, nttb200_shard_state **out, size_t events)
     if (!b->shard) {
         b->shard = new nttb200_shard_state();
         if (const char *e = getenv("NTTB200_SHARD_MODE")) b->shard->mode = atoi(e);
-        if (const char *e = getenv("NTTB200_SHARD_CHUNKS")) b->shard->chunks = (unsigned)atoi(e) ? (unsigned)atoi(e) : 1u;
+        if (const char *e = getenv("NTTB200_SHARD_CHUNKS")) b->shard->chunks = (unsigned)atoi(e);
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);          // collectives / rounding of finished pieces go ahead of queued transforms
         NTTB200_CHECK(cudaStreamCreateWithPriority(&b->shard->cs, cudaStreamNonBlocking, hi));
@@ -329,11 +331,11 @@ int nttb200_comm_rank(const nttb200_comm *c) { return c ? c->rank : -1; }
 
 int nttb200_bfv_shard_config(nttb200_bfv *b, int mode, unsigned chunks)
 {
-    if (!b || mode < 0 || mode > 3) return NTTB200_EINVAL;
+    if (!b || mode < 0 || mode > 4) return NTTB200_EINVAL;
     nttb200_shard_state *s;
     TRY(shard_state(b, &s, 0));
     s->mode = mode;
-    s->chunks = chunks ? chunks : 1u;
+    s->chunks = chunks;
     return 0;
 }
 
@@ -496,9 +498,9 @@ int nttb200_bfv_decrypt_sharded(nttb200_bfv *b, nttb200_comm *comm, nttb200_u64 
     TRY(shard_state(b, &s, 1));
     std::vector<nttb200_shard_block> blk(G);
     plan_blocks(rp, n, batch, G, g, blk.data(), nullptr);
-    unsigned chunks = G > 1 ? s->chunks : 1u;
+    unsigned chunks = G > 1 ? (s->chunks ? s->chunks : (s->mode == 4 ? 2u : 4u)) : 1u;
     while (chunks > 1 && per % chunks) chunks--;
-    TRY(shard_state(b, &s, (size_t)2 * G * chunks + 8));
+    TRY(shard_state(b, &s, (size_t)3 * G * chunks + 8));
     const unsigned sub = per / chunks;                                   // items of one block in one chunk
     u64 *partial, *recv; unsigned short *plain;
     TRY(shard_buf(s, kBufPartial, (size_t)batch * pw * 8, (void **)&partial));
@@ -518,7 +520,7 @@ int nttb200_bfv_decrypt_sharded(nttb200_bfv *b, nttb200_comm *comm, nttb200_u64 
         NTTB200_CHECK(cudaStreamWaitEvent(st, s->ev[evi], 0));
         return 0;
     }
-    const bool p2p_mode = s->mode == 2 || s->mode == 3;
+    const bool p2p_mode = s->mode >= 2;          // 2 / 3: peer stores by the kernel; 4: local sums pushed by the copy engines
     if (p2p_mode && !s->p2p_failed && !comm->fake) {
         // Peer-to-peer: the partial-sum kernel of a tile writes straight into slot `rank` of the buffer of the items' OWNER, mapped
         // here through CUDA IPC -- NVLink stores issued by the kernel that produces the sums: compute and transfer are one kernel, no
@@ -533,7 +535,7 @@ int nttb200_bfv_decrypt_sharded(nttb200_bfv *b, nttb200_comm *comm, nttb200_u64 
         // instead of 9.8 for 4096 ciphertexts on 8 GPUs).
         // mode 2: `chunks` rounds, round c covering piece c of EVERY owner's block, so the owners round and gather piece c while the
         //         next round's transforms run; mode 3: one round (largest launches, everything after the last transform is exposed).
-        const unsigned rounds = s->mode == 2 ? chunks : 1u;
+        const unsigned rounds = s->mode == 3 ? 1u : chunks;
         const unsigned piece = per / rounds;
         // (Running all transforms first -- same-window blocks merged into large launches -- and depositing afterwards was measured
         // SLOWER, 8.8 ms against 7.5: the peer stores then come in one burst with nothing to overlap them.  Tile by tile, the
@@ -546,8 +548,16 @@ int nttb200_bfv_decrypt_sharded(nttb200_bfv *b, nttb200_comm *comm, nttb200_u64 
                 u64 *dst = comm->fake ? partial + ((size_t)j * per + (size_t)c * piece) * pw
                                       : (u64 *)s->sym[kSymSlots].peer[j] + ((size_t)g * per + (size_t)c * piece) * pw;
                 const bool alt = (tau & 1) != 0;
-                if (cnt) TRY(dec_partial(b, alt ? P2 : P, dst, packed, c_shard + blk[j].offset + (size_t)c * piece * 2 * cnt * n, cnt, blk[j].first_limb, cnt, piece));
-                else NTTB200_CHECK(cudaMemsetAsync(dst, 0, (size_t)piece * pw * 8, alt ? s->st2 : st));
+                const bool ce = s->mode == 4 && !comm->fake && j != g;          // sums into local scratch, pushed by a copy engine afterwards
+                u64 *loc = partial + ((size_t)j * per + (size_t)c * piece) * pw;
+                if (cnt) TRY(dec_partial(b, alt ? P2 : P, ce ? loc : dst, packed, c_shard + blk[j].offset + (size_t)c * piece * 2 * cnt * n, cnt, blk[j].first_limb, cnt, piece));
+                else NTTB200_CHECK(cudaMemsetAsync(ce ? loc : dst, 0, (size_t)piece * pw * 8, alt ? s->st2 : st));
+                if (ce) {
+                    NTTB200_CHECK(cudaEventRecord(s->ev[evi], alt ? s->st2 : st));
+                    NTTB200_CHECK(cudaStreamWaitEvent(s->cs, s->ev[evi], 0));
+                    evi++;
+                    NTTB200_CHECK(cudaMemcpyAsync(dst, loc, (size_t)piece * pw * 8, cudaMemcpyDeviceToDevice, s->cs));
+                }
             }
             for (cudaStream_t cst : {st, s->st2}) {              // both compute streams have deposited round c
                 NTTB200_CHECK(cudaEventRecord(s->ev[evi], cst));

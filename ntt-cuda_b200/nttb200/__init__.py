@@ -416,7 +416,7 @@ class Bfv:
     def set_fused_epilogue(self, enable: bool):
         check(lib().nttb200_bfv_set_fused_epilogue(self._h, C.c_int(int(enable))))
 
-    def shard_config(self, mode=0, chunks=4):
+    def shard_config(self, mode=4, chunks=0):
         check(lib().nttb200_bfv_shard_config(self._h, C.c_int(mode), C.c_uint(chunks)))
 
     def shard_words(self, comm, batch):
