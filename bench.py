@@ -14,6 +14,7 @@ Extra blocks on the same JSON line (BASELINE.json's other configs; none of them 
                        _decrypt_sharded (NCCL inside the library), strong scaling, bit-identity re-checked every run
   ntt_limb_sharded     config 5: N = 2^16 / 2^17, 16 limbs, each rank owns its limbs' tables only, strong scaling
   keygen_c3            config 3: 8192 x 3 limbs, 256 keys per call
+  bfv_mul              ciphertext x ciphertext multiply + relinearise, batch 8 per GPU
   latency_c1           config 1: one N = 4096 transform (58-bit prime), ours vs the rebuilt reference
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
@@ -413,6 +414,37 @@ def keygen_c3(nttb200, params, torch, T, world):
             "ms_per_call": ms, "us_per_key": 1e3 * ms / B}
 
 
+def bfv_mul(nttb200, params, torch, T, world, batch=8):
+    """SURVEY.md 8f-4's last row: ciphertext x ciphertext multiplication + relinearisation (the paper's future work), per GPU."""
+    n, qs, roots = params.RNS_SETS["32k_16q"]
+    rn = len(qs) * n
+    bfv = nttb200.Bfv(n, qs, roots)
+    sk = torch.zeros(rn, dtype=torch.int64, device="cuda")
+    pk = torch.zeros(2 * rn, dtype=torch.int64, device="cuda")
+    bfv.keygen(sk, pk)
+    bfv.load_keys(sk, pk)
+    bfv.relin_keygen(sk)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    ma = torch.randint(0, params.T, (batch * n,), dtype=torch.int64, device="cuda", generator=g)
+    mb = torch.randint(0, params.T, (batch * n,), dtype=torch.int64, device="cuda", generator=g)
+    ca = torch.zeros(batch * 2 * rn, dtype=torch.int64, device="cuda")
+    cb = torch.zeros_like(ca)
+    bfv.encrypt(ca, None, ma, batch=batch, nonce0=1)
+    bfv.encrypt(cb, None, mb, batch=batch, nonce0=1000)
+    out = torch.zeros_like(ca)
+    ms = T.ms(lambda: bfv.mul(out, ca, cb, batch=batch), reps=5)
+    # correctness inside the bench: the constant coefficient of Dec(c_a * c_b) of item 0 against a 64-bit dot product mod t
+    dec = torch.zeros(batch * n, dtype=torch.int64, device="cuda")
+    bfv.decrypt(dec, out.clone(), None, batch=batch)
+    a0, b0 = ma[:n], mb[:n]
+    want = (int(a0[0]) * int(b0[0]) - int((a0[1:] * b0[1:].flip(0)).sum().item())) % params.T    # X^n = -1
+    ok = int(dec[0].item()) == want
+    bfv.close()
+    torch.cuda.empty_cache()
+    return {"workload": f"BFV ciphertext x ciphertext multiply + relinearise, N=32768, 16-limb q, batch {batch} per GPU",
+            "products_per_s": world * batch / (ms * 1e-3), "ms_per_call": ms, "decrypts_to_product": bool(ok)}
+
+
 def latency_c1(nttb200, params, torch):
     """BASELINE config 1: ONE polynomial, N = 4096, 58-bit prime: microseconds per call (back-to-back launches, CUDA events)."""
     n = 4096
@@ -611,6 +643,7 @@ def run_ours(args):
         extras["bfv_limb_sharded"] = bfv_limb_sharded(nttb200, params, torch, T, world, rank, total=args.sharded_total)
         extras["ntt_limb_sharded"] = ntt_limb_sharded(nttb200, params, torch, T, world, rank)
         extras["keygen_c3"] = keygen_c3(nttb200, params, torch, T, world)
+        extras["bfv_mul"] = bfv_mul(nttb200, params, torch, T, world)
         if rank == 0 and world == 1:
             extras["latency_c1"] = latency_c1(nttb200, params, torch)
 
