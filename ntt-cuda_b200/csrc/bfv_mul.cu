@@ -91,8 +91,10 @@ struct nttb200_mul_state {
     std::vector<u64> p, psi_p;
     // device constants
     ModC *modQ = nullptr, *modP = nullptr, *modQP = nullptr;
-    ShoupC *preQ = nullptr, *M_QP = nullptr, *preP = nullptr, *M_PQ = nullptr, *preQs = nullptr, *W = nullptr, *lam = nullptr;
+    ShoupC *preQ = nullptr, *preP = nullptr, *preQs = nullptr, *r64Q = nullptr, *r64P = nullptr;
+    SplitC *M_QP = nullptr, *M_PQ = nullptr, *W = nullptr, *lam = nullptr;
     u64 *corr_QP = nullptr, *corr_PQ = nullptr;
+    unsigned h = 0;                          // split position of the lazy sums (mul_kernels.cuh)
     double *binvQ = nullptr, *binvP = nullptr, *theta = nullptr;
     // relinearisation key evk[rp][2][rp][n] (NTT domain) + companions
     u64 *evk = nullptr, *evk_s = nullptr;
@@ -107,7 +109,7 @@ void nttb200_mul_state_destroy(nttb200_mul_state *s)
     if (!s) return;
     cudaFree(s->modQ); cudaFree(s->modP); cudaFree(s->modQP); cudaFree(s->preQ); cudaFree(s->M_QP); cudaFree(s->preP); cudaFree(s->M_PQ);
     cudaFree(s->preQs); cudaFree(s->W); cudaFree(s->lam); cudaFree(s->corr_QP); cudaFree(s->corr_PQ); cudaFree(s->binvQ); cudaFree(s->binvP);
-    cudaFree(s->theta); cudaFree(s->evk); cudaFree(s->evk_s);
+    cudaFree(s->theta); cudaFree(s->evk); cudaFree(s->evk_s); cudaFree(s->r64Q); cudaFree(s->r64P);
     for (auto b : s->buf) cudaFree(b);
     if (s->ctxP) nttb200_ctx_destroy(s->ctxP);
     delete s;
@@ -148,8 +150,14 @@ static int mul_state(nttb200_bfv *b, nttb200_mul_state **out)
     s->rp = rp; s->k = k;
     unsigned bits = 0;
     for (unsigned i = 0; i < r; i++) bits = std::max(bits, c->qbit[i]);
-    // (3 lin + 1) * max modulus must stay below 2^64 in the lazy sums of k_bconv / k_scale
-    if ((u128)(3 * k + 1) * ((u128)1 << bits) >= ((u128)1 << 64)) { delete s; return NTTB200_EINVAL; }
+    // the three partial sums of k_bconv / k_scale (<= k + 1 terms, two products of < 2^(2h) each in the cross sum) must not carry,
+    // and neither may relinearisation's sum of r - 1 lazy Shoup products
+    s->h = (bits + 1) / 2;
+    if ((u128)(2 * (k + 1)) * ((u128)1 << (2 * s->h)) >= ((u128)1 << 64) || (u128)(2 * k) * ((u128)1 << bits) >= ((u128)1 << 64)) {
+        delete s; return NTTB200_EINVAL;
+    }
+    const unsigned h = s->h;
+    auto splitc = [h](u64 c) { SplitC r; r.c0 = (u32)(c & ((1ull << h) - 1)); r.c1 = (u32)(c >> h); return r; };
     s->p.resize(k); s->psi_p.resize(k);
     std::vector<u64> excl(c->q.begin(), c->q.end());
     excl.push_back(b->gamma);
@@ -164,7 +172,8 @@ static int mul_state(nttb200_bfv *b, nttb200_mul_state **out)
     std::vector<ModC> modQ(rp), modP(k), modQP(rp + k);
     for (unsigned i = 0; i < rp; i++) modQP[i] = modQ[i] = modc(q[i]);
     for (unsigned j = 0; j < k; j++) modQP[rp + j] = modP[j] = modc(p[j]);
-    std::vector<ShoupC> preQ(rp), M_QP((size_t)k * rp), preP(k), M_PQ((size_t)rp * k), preQs(rp), W((size_t)k * rp), lam(k);
+    std::vector<ShoupC> preQ(rp), preP(k), preQs(rp), r64Q(rp), r64P(k);
+    std::vector<SplitC> M_QP((size_t)k * rp), M_PQ((size_t)rp * k), W((size_t)k * rp), lam(k);
     std::vector<u64> corr_QP(k), corr_PQ(rp);
     std::vector<double> binvQ(rp), binvP(k), theta(rp);
     std::vector<Big> Qi(rp), Pj(k);        // Q / q_i, P / p_j
@@ -176,24 +185,27 @@ static int mul_state(nttb200_bfv *b, nttb200_mul_state **out)
         preQ[i] = shoupc(qi_inv, q[i]);
         preQs[i] = shoupc(mulmod(qi_inv, invmod_prime(big_mod_small(Pb, q[i]), q[i]), q[i]), q[i]);   // (QP/q_i)^-1 mod q_i
         corr_PQ[i] = big_mod_small(Pb, q[i]);
+        r64Q[i] = shoupc((u64)(((u128)1 << 64) % q[i]), q[i]);
         Big omega;
         const u64 rem = big_divmod_small(tP, q[i], &omega);                                  // t P / q_i = omega + rem / q_i
         theta[i] = (double)rem / (double)q[i];
         for (unsigned j = 0; j < k; j++) {
-            M_QP[(size_t)j * rp + i] = shoupc(big_mod_small(Qi[i], p[j]), p[j]);
-            W[(size_t)j * rp + i] = shoupc(big_mod_small(omega, p[j]), p[j]);
-            M_PQ[(size_t)i * k + j] = shoupc(big_mod_small(Pj[j], q[i]), q[i]);
+            M_QP[(size_t)j * rp + i] = splitc(big_mod_small(Qi[i], p[j]));
+            W[(size_t)j * rp + i] = splitc(big_mod_small(omega, p[j]));
+            M_PQ[(size_t)i * k + j] = splitc(big_mod_small(Pj[j], q[i]));
         }
     }
     for (unsigned j = 0; j < k; j++) {
         preP[j] = shoupc(invmod_prime(big_mod_small(Pj[j], p[j]), p[j]), p[j]);
         corr_QP[j] = big_mod_small(Qb, p[j]);
-        lam[j] = shoupc(mulmod(b->t % p[j], invmod_prime(big_mod_small(Qb, p[j]), p[j]), p[j]), p[j]);   // t Q^-1 mod p_j
+        lam[j] = splitc(mulmod(b->t % p[j], invmod_prime(big_mod_small(Qb, p[j]), p[j]), p[j]));         // t Q^-1 mod p_j
+        r64P[j] = shoupc((u64)(((u128)1 << 64) % p[j]), p[j]);
     }
     rc = upload(&s->modQ, modQ); if (!rc) rc = upload(&s->modP, modP); if (!rc) rc = upload(&s->modQP, modQP);
     if (!rc) rc = upload(&s->preQ, preQ); if (!rc) rc = upload(&s->M_QP, M_QP); if (!rc) rc = upload(&s->preP, preP);
     if (!rc) rc = upload(&s->M_PQ, M_PQ); if (!rc) rc = upload(&s->preQs, preQs); if (!rc) rc = upload(&s->W, W); if (!rc) rc = upload(&s->lam, lam);
     if (!rc) rc = upload(&s->corr_QP, corr_QP); if (!rc) rc = upload(&s->corr_PQ, corr_PQ);
+    if (!rc) rc = upload(&s->r64Q, r64Q); if (!rc) rc = upload(&s->r64P, r64P);
     if (!rc) rc = upload(&s->binvQ, binvQ); if (!rc) rc = upload(&s->binvP, binvP); if (!rc) rc = upload(&s->theta, theta);
     if (rc) { nttb200_mul_state_destroy(s); return rc; }
     b->mul = s;
@@ -219,13 +231,7 @@ static int ntt_call(const nttb200_ctx *c, bool inverse, u64 *a, unsigned num, un
                   c->use_tma, group_polys, group_stride};
     return launch_ntt(inverse, c->lazy_ok ? kPolicyShoupLazy : kPolicyShoup, c->logn, h, st);
 }
-static dim3 grid1(unsigned n, unsigned y)
-{
-    unsigned x = (n + 127) / 128;
-    const unsigned cap = 148 * 8;
-    if ((unsigned long long)x * y > cap) x = std::max(1u, cap / std::max(1u, y));
-    return dim3(x, y);
-}
+static dim3 grid1(unsigned n, unsigned y) { return dim3((n + 127) / 128, y); }    // one coefficient per thread
 static dim3 pair_grid3(unsigned n, unsigned y, unsigned z)
 {
     unsigned x = (n + 511) / 512;
@@ -248,8 +254,8 @@ static int run_tensor(nttb200_bfv *b, nttb200_mul_state *s, u64 *y, const u64 *c
     for (int op = 0; op < (square ? 1 : 2); op++) {
         u64 *Wx = op == 0 ? WA : WB;
         k_gather_q<<<pair_grid3(n, rp, 2 * batch), 256, 0, st>>>(op == 0 ? ca : cb, Wx, n, r, L);
-        BconvArgs A{Wx, Ln, Wx + (size_t)rp * n, Ln, s->preQ, s->modQ, s->binvQ, s->M_QP, s->corr_QP, s->modP, rp, k, n};
-        k_bconv<<<grid1(n, 2 * batch), 128, 0, st>>>(A);
+        BconvArgs A{Wx, Ln, Wx + (size_t)rp * n, Ln, s->preQ, s->modQ, s->binvQ, s->M_QP, s->corr_QP, s->r64P, s->modP, rp, k, n, s->h};
+        k_bconv<<<grid1(n, 2 * batch), 128, (size_t)rp * k * 8, st>>>(A);
         KCHECK();
         NTTB200_TRY(ntt_call(b->ctx, false, Wx, 2 * batch * rp, rp, rp, Ln, st));
         NTTB200_TRY(ntt_call(s->ctxP, false, Wx + (size_t)rp * n, 2 * batch * k, k, k, Ln, st));
@@ -258,10 +264,10 @@ static int run_tensor(nttb200_bfv *b, nttb200_mul_state *s, u64 *y, const u64 *c
     KCHECK();
     NTTB200_TRY(ntt_call(b->ctx, true, D, 3 * batch * rp, rp, rp, Ln, st));
     NTTB200_TRY(ntt_call(s->ctxP, true, D + (size_t)rp * n, 3 * batch * k, k, k, Ln, st));
-    ScaleArgs S{D, YP, s->preQs, s->modQ, s->modP, s->theta, s->W, s->lam, rp, k, n};
-    k_scale<<<grid1(n, 3 * batch), 128, 0, st>>>(S);
-    BconvArgs Bk{YP, (size_t)k * n, y, (size_t)rp * n, s->preP, s->modP, s->binvP, s->M_PQ, s->corr_PQ, s->modQ, k, rp, n};
-    k_bconv<<<grid1(n, 3 * batch), 128, 0, st>>>(Bk);
+    ScaleArgs S{D, YP, s->preQs, s->modQ, s->modP, s->theta, s->W, s->lam, s->r64P, rp, k, n, s->h};
+    k_scale<<<grid1(n, 3 * batch), 128, (size_t)rp * k * 8, st>>>(S);
+    BconvArgs Bk{YP, (size_t)k * n, y, (size_t)rp * n, s->preP, s->modP, s->binvP, s->M_PQ, s->corr_PQ, s->r64Q, s->modQ, k, rp, n, s->h};
+    k_bconv<<<grid1(n, 3 * batch), 128, (size_t)rp * k * 8, st>>>(Bk);
     KCHECK();
     return 0;
 }

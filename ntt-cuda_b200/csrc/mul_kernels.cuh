@@ -40,81 +40,143 @@ __host__ __device__ __forceinline__ u64 shoup_canon(u64 x, const ShoupC &c, u64 
 
 constexpr int kBaseMax = 32;                 // limbs of one base
 
+// ---- lazy accumulation of products of residues ---------------------------------------------------------------------------------------
+// sum of y_i * c_i over <= kBaseMax + 1 terms, every factor below 2^bits.  Both factors are split at h = ceil(bits / 2) bits -- y in the
+// kernel, once per coefficient; constants on the host (SplitC) -- so that each of the four partial products is below 2^(2h) and the
+// three partial SUMS (low, cross, high) cannot carry: 2 * terms * 2^(2h) < 2^64 is checked in mul_state.  A term is then four
+// 32x32->64 multiply-adds (an exact Shoup product: six wide multiplies, four narrow ones and the carry chain of a mul.hi), and ONE
+// reduction per sum replaces one per term.  Exact: the reduced value is the canonical residue of the true sum.
+struct SplitC { u32 c0, c1; };               // c = c1 * 2^h + c0
+struct Acc3 { u64 ll, mid, hh; };
+__host__ __device__ __forceinline__ void acc_init(Acc3 &a, u64 v) { a.ll = v; a.mid = 0; a.hh = 0; }
+__host__ __device__ __forceinline__ void acc_mac(Acc3 &a, u32 y0, u32 y1, const SplitC c)
+{
+#if defined(__CUDA_ARCH__)
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a.ll) : "r"(y0), "r"(c.c0));
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a.mid) : "r"(y0), "r"(c.c1));
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a.mid) : "r"(y1), "r"(c.c0));
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a.hh) : "r"(y1), "r"(c.c1));
+#else
+    a.ll += (u64)y0 * c.c0;
+    a.mid += (u64)y0 * c.c1;
+    a.mid += (u64)y1 * c.c0;
+    a.hh += (u64)y1 * c.c1;
+#endif
+}
+// value = ll + mid * 2^h + hh * 2^(2h) (below 2^128), reduced with r64 = 2^64 mod q and its companion
+__host__ __device__ __forceinline__ u64 acc_reduce(const Acc3 &a, unsigned h, const ModC &m, const ShoupC &r64)
+{
+    const u64 m_lo = a.mid << h, h_lo = a.hh << (2 * h);
+    u64 lo = a.ll + m_lo;
+    u64 hi = (a.mid >> (64 - h)) + (a.hh >> (64 - 2 * h)) + (lo < m_lo ? 1u : 0u);
+    lo += h_lo;
+    hi += lo < h_lo ? 1u : 0u;
+    return csub(csub(shoup_mul(hi, r64.c, r64.cs, m.q) + mod_exact(lo, m.q, m.ratio), 2 * m.q), m.q);
+}
+
 // ---- fast base conversion with overflow estimate (HPS eq. 2-3) ------------------------------------------------------------------
 // x[item][lin][n] (canonical residues mod the input base) -> out[item][lout][n] mod the output base:
 //   y_i = [x_i * (B/b_i)^-1]_{b_i};  v = round(sum_i y_i / b_i);  out_j = (sum_i y_i * [B/b_i]_{o_j} - v * [B]_{o_j}) mod o_j
 // i.e. the residues of the CENTRED representative of x (or of one shifted by B when the estimate v is off by one, which only happens
 // within 2^-48 of the boundary and is harmless: any representative below B in magnitude works downstream).
+// One thread per coefficient: the lin residues stay in registers (loops fully unrolled, uniform early exit), the lout x lin matrix
+// is staged in shared memory; per output limb one lazy sum.
 struct BconvArgs {
     const u64 *x; size_t in_item;            // input, [lin][n] per item
     u64 *out; size_t out_item;               // output, [lout][n] per item
     const ShoupC *pre;                       // [lin]   (B/b_i)^-1 mod b_i
     const ModC *bin;                         // [lin]   input moduli
     const double *binv;                      // [lin]   1 / b_i
-    const ShoupC *M;                         // [lout][lin]  B/b_i mod o_j
+    const SplitC *M;                         // [lout][lin]  B/b_i mod o_j
     const u64 *corr;                         // [lout]  B mod o_j
+    const ShoupC *r64;                       // [lout]  2^64 mod o_j
     const ModC *bout;                        // [lout]  output moduli
-    unsigned lin, lout, n;
+    unsigned lin, lout, n, h;                // h: split position of the lazy sums
 };
 NTT_KERNEL void __launch_bounds__(128) k_bconv(BconvArgs A)
 {
+    extern __shared__ SplitC mul_smem[];
+    for (unsigned i = threadIdx.x; i < A.lin * A.lout; i += blockDim.x) mul_smem[i] = A.M[i];
+    __syncthreads();
     const size_t k = blockIdx.y;
-    const u64 *x = A.x + k * A.in_item;
-    u64 *o = A.out + k * A.out_item;
-    for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < A.n; j += gridDim.x * blockDim.x) {
-        u64 y[kBaseMax];
-        double s = 0.0;
-        for (unsigned i = 0; i < A.lin; i++) {
-            y[i] = shoup_canon(x[(size_t)i * A.n + j], A.pre[i], A.bin[i].q);
-            s = dadd_rn(s, dmul_rn((double)y[i], A.binv[i]));
+    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= A.n) return;
+    const u64 *x = A.x + k * A.in_item + j;
+    u64 *o = A.out + k * A.out_item + j;
+    u32 y0[kBaseMax], y1[kBaseMax];
+    const u64 mask = (1ull << A.h) - 1;
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < kBaseMax; i++) {
+        if (i >= (int)A.lin) break;
+        const u64 y = shoup_canon(x[(size_t)i * A.n], A.pre[i], A.bin[i].q);
+        s = dadd_rn(s, dmul_rn((double)y, A.binv[i]));
+        y0[i] = (u32)(y & mask); y1[i] = (u32)(y >> A.h);
+    }
+    const u64 v = (u64)(long long)floor(dadd_rn(s, 0.5));
+    for (unsigned l = 0; l < A.lout; l++) {
+        const ModC m = A.bout[l];
+        const SplitC *row = mul_smem + (size_t)l * A.lin;
+        Acc3 acc;
+        acc_init(acc, (u64)(A.lin + 1) * m.q - v * A.corr[l]);                                            // v <= lin, corr < o_j
+#pragma unroll
+        for (int i = 0; i < kBaseMax; i++) {
+            if (i >= (int)A.lin) break;
+            acc_mac(acc, y0[i], y1[i], row[i]);
         }
-        const u64 v = (u64)(long long)floor(dadd_rn(s, 0.5));
-        for (unsigned l = 0; l < A.lout; l++) {
-            const ModC m = A.bout[l];
-            const ShoupC *row = A.M + (size_t)l * A.lin;
-            u64 acc = 0;
-            for (unsigned i = 0; i < A.lin; i++) acc += shoup_mul(y[i], row[i].c, row[i].cs, m.q);        // each < 2 o_j: sum < 2^6 * 2^58
-            acc += (u64)(A.lin + 1) * m.q - v * A.corr[l];                                                // v <= lin, corr < o_j
-            o[(size_t)l * A.n + j] = mod_exact(acc, m.q, m.ratio);
-        }
+        o[(size_t)l * A.n] = acc_reduce(acc, A.h, m, A.r64[l]);
     }
 }
 
 // ---- HPS "simple scaling": y = round(t/Q * d) in base P from d in base Q u P ------------------------------------------------------
 // d[item][comp][rp + k][n] (coefficient domain, canonical; Q limbs first) -> y[item][comp][k][n]:
 //   yt_i = [d_i * (QP/q_i)^-1]_{q_i};  y_j = ( sum_i yt_i * [omega_i]_{p_j} + d'_j * lambda_j + round(sum_i yt_i * theta_i) ) mod p_j
-// with t*P/q_i = omega_i + theta_i (integer + fraction) and lambda_j = [(QP/p_j)^-1 * t * P/p_j]_{p_j}.
+// with t*P/q_i = omega_i + theta_i (integer + fraction) and lambda_j = [(QP/p_j)^-1 * t * P/p_j]_{p_j}.  Same thread layout as k_bconv.
 struct ScaleArgs {
     const u64 *d; u64 *y;
     const ShoupC *preQ;                      // [rp]     (QP/q_i)^-1 mod q_i
     const ModC *modQ, *modP;                 // [rp], [k]
     const double *theta;                     // [rp]     frac(t * P / q_i)
-    const ShoupC *W;                         // [k][rp]  floor(t * P / q_i) mod p_j
-    const ShoupC *lam;                       // [k]
-    unsigned rp, k, n;
+    const SplitC *W;                         // [k][rp]  floor(t * P / q_i) mod p_j
+    const SplitC *lam;                       // [k]
+    const ShoupC *r64;                       // [k]      2^64 mod p_j
+    unsigned rp, k, n, h;
 };
 NTT_KERNEL void __launch_bounds__(128) k_scale(ScaleArgs A)
 {
+    extern __shared__ SplitC mul_smem[];
+    for (unsigned i = threadIdx.x; i < A.rp * A.k; i += blockDim.x) mul_smem[i] = A.W[i];
+    __syncthreads();
     const size_t kc = blockIdx.y;             // item * comps + comp
     const size_t L = (size_t)A.rp + A.k;
-    const u64 *d = A.d + kc * L * A.n;
-    u64 *y = A.y + kc * (size_t)A.k * A.n;
-    for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < A.n; j += gridDim.x * blockDim.x) {
-        u64 yt[kBaseMax];
-        double f = 0.0;
-        for (unsigned i = 0; i < A.rp; i++) {
-            yt[i] = shoup_canon(d[(size_t)i * A.n + j], A.preQ[i], A.modQ[i].q);
-            f = dadd_rn(f, dmul_rn((double)yt[i], A.theta[i]));
+    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= A.n) return;
+    const u64 *d = A.d + kc * L * A.n + j;
+    u64 *y = A.y + kc * (size_t)A.k * A.n + j;
+    u32 y0[kBaseMax], y1[kBaseMax];
+    const u64 mask = (1ull << A.h) - 1;
+    double f = 0.0;
+#pragma unroll
+    for (int i = 0; i < kBaseMax; i++) {
+        if (i >= (int)A.rp) break;
+        const u64 yt = shoup_canon(d[(size_t)i * A.n], A.preQ[i], A.modQ[i].q);
+        f = dadd_rn(f, dmul_rn((double)yt, A.theta[i]));
+        y0[i] = (u32)(yt & mask); y1[i] = (u32)(yt >> A.h);
+    }
+    const u64 v = (u64)(long long)floor(dadd_rn(f, 0.5));
+    for (unsigned l = 0; l < A.k; l++) {
+        const ModC m = A.modP[l];
+        const SplitC *row = mul_smem + (size_t)l * A.rp;
+        const u64 dp = d[((size_t)A.rp + l) * A.n];
+        Acc3 acc;
+        acc_init(acc, v);                                                                                 // v <= rp
+        acc_mac(acc, (u32)(dp & mask), (u32)(dp >> A.h), A.lam[l]);
+#pragma unroll
+        for (int i = 0; i < kBaseMax; i++) {
+            if (i >= (int)A.rp) break;
+            acc_mac(acc, y0[i], y1[i], row[i]);
         }
-        const u64 v = (u64)(long long)floor(dadd_rn(f, 0.5));
-        for (unsigned l = 0; l < A.k; l++) {
-            const ModC m = A.modP[l];
-            const ShoupC *row = A.W + (size_t)l * A.rp;
-            u64 acc = shoup_mul(d[((size_t)A.rp + l) * A.n + j], A.lam[l].c, A.lam[l].cs, m.q);
-            for (unsigned i = 0; i < A.rp; i++) acc += shoup_mul(yt[i], row[i].c, row[i].cs, m.q);
-            acc += mod_exact(v, m.q, m.ratio);
-            y[(size_t)l * A.n + j] = mod_exact(acc, m.q, m.ratio);
-        }
+        y[(size_t)l * A.n] = acc_reduce(acc, A.h, m, A.r64[l]);
     }
 }
 
