@@ -87,7 +87,8 @@ template <class T> int upload(T **d, const std::vector<T> &h)
 // state of the multiplication entry points, owned by the BFV context
 struct nttb200_mul_state {
     unsigned rp = 0, k = 0;
-    nttb200_ctx *ctxP = nullptr;
+    nttb200_ctx *ctxP = nullptr;            // base P alone (its tables are the source of ctxQP's second part)
+    nttb200_ctx *ctxQP = nullptr;           // tables of Q's r - 1 limbs followed by P's: one launch transforms a whole [..][rp + k][n] array
     std::vector<u64> p, psi_p;
     // device constants
     ModC *modQ = nullptr, *modP = nullptr, *modQP = nullptr;
@@ -96,23 +97,46 @@ struct nttb200_mul_state {
     u64 *corr_QP = nullptr, *corr_PQ = nullptr;
     unsigned h = 0;                          // split position of the lazy sums (mul_kernels.cuh)
     double *binvQ = nullptr, *binvP = nullptr, *theta = nullptr;
-    // relinearisation key evk[rp][2][rp][n] (NTT domain) + companions
-    u64 *evk = nullptr, *evk_s = nullptr;
+    // relinearisation key evk[rp][2][rp][n] (NTT domain, canonical; no companions: k_relin_accum multiplies by split words)
+    u64 *evk = nullptr;
     // grow-only work buffers
     u64 *buf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t cap[6] = {0, 0, 0, 0, 0, 0};
 };
-enum { kWA = 0, kWB, kD, kYP, kY, kDd };
+enum { kWA = 0, kWB /* unused since the operands share kWA */, kD, kYP, kY, kDd };
 
 void nttb200_mul_state_destroy(nttb200_mul_state *s)
 {
     if (!s) return;
     cudaFree(s->modQ); cudaFree(s->modP); cudaFree(s->modQP); cudaFree(s->preQ); cudaFree(s->M_QP); cudaFree(s->preP); cudaFree(s->M_PQ);
     cudaFree(s->preQs); cudaFree(s->W); cudaFree(s->lam); cudaFree(s->corr_QP); cudaFree(s->corr_PQ); cudaFree(s->binvQ); cudaFree(s->binvP);
-    cudaFree(s->theta); cudaFree(s->evk); cudaFree(s->evk_s); cudaFree(s->r64Q); cudaFree(s->r64P);
+    cudaFree(s->theta); cudaFree(s->evk); cudaFree(s->r64Q); cudaFree(s->r64P);
     for (auto b : s->buf) cudaFree(b);
     if (s->ctxP) nttb200_ctx_destroy(s->ctxP);
+    if (s->ctxQP) nttb200_ctx_destroy(s->ctxQP);
     delete s;
+}
+
+// a context whose limbs are the first `la` limbs of `a` followed by all limbs of `b` (device-to-device copies of the tables)
+static int ctx_concat(nttb200_ctx **out, const nttb200_ctx *a, unsigned la, const nttb200_ctx *b)
+{
+    nttb200_ctx *c = new nttb200_ctx();
+    *out = c;
+    c->n = a->n; c->logn = a->logn; c->limbs = la + b->limbs; c->device = a->device; c->use_tma = a->use_tma;
+    c->lazy_ok = a->lazy_ok && b->lazy_ok;
+    const size_t ta = (size_t)la * a->n * 8, tb = (size_t)b->limbs * b->n * 8;
+    u64 **dst[4] = {&c->psi, &c->psiinv, &c->psi_s, &c->psiinv_s};
+    u64 *const srca[4] = {a->psi, a->psiinv, a->psi_s, a->psiinv_s}, *const srcb[4] = {b->psi, b->psiinv, b->psi_s, b->psiinv_s};
+    for (int i = 0; i < 4; i++) {
+        NTTB200_CHECK(cudaMalloc(dst[i], ta + tb));
+        NTTB200_CHECK(cudaMemcpy(*dst[i], srca[i], ta, cudaMemcpyDeviceToDevice));
+        NTTB200_CHECK(cudaMemcpy(reinterpret_cast<char *>(*dst[i]) + ta, srcb[i], tb, cudaMemcpyDeviceToDevice));
+    }
+    NTTB200_CHECK(cudaMalloc(&c->lc, c->limbs * sizeof(LimbConst)));
+    NTTB200_CHECK(cudaMemcpy(c->lc, a->lc, la * sizeof(LimbConst), cudaMemcpyDeviceToDevice));
+    NTTB200_CHECK(cudaMemcpy(c->lc + la, b->lc, b->limbs * sizeof(LimbConst), cudaMemcpyDeviceToDevice));
+    c->q.assign(a->q.begin(), a->q.begin() + la); c->q.insert(c->q.end(), b->q.begin(), b->q.end());
+    return 0;
 }
 
 static int find_primes(unsigned bits, unsigned n, unsigned count, const u64 *exclude, unsigned nexclude, u64 *q_out, u64 *psi_out)
@@ -163,6 +187,7 @@ static int mul_state(nttb200_bfv *b, nttb200_mul_state **out)
     excl.push_back(b->gamma);
     int rc = find_primes(bits, n, k, excl.data(), (unsigned)excl.size(), s->p.data(), s->psi_p.data());
     if (!rc) rc = nttb200_ctx_create(&s->ctxP, n, k, s->p.data(), s->psi_p.data());
+    if (!rc) rc = ctx_concat(&s->ctxQP, c, rp, s->ctxP);
     if (rc) { nttb200_mul_state_destroy(s); return rc; }
     const std::vector<u64> &q = c->q;      // first rp entries = base Q
     const std::vector<u64> &p = s->p;
@@ -246,24 +271,22 @@ static int run_tensor(nttb200_bfv *b, nttb200_mul_state *s, u64 *y, const u64 *c
     const unsigned n = b->n, r = b->r, rp = s->rp, k = s->k, L = rp + k;
     const size_t Ln = (size_t)L * n;
     u64 *WA, *WB, *D, *YP;
-    NTTB200_TRY(mul_buf(s, kWA, (size_t)batch * 2 * Ln, &WA));
-    NTTB200_TRY(mul_buf(s, kWB, (size_t)batch * 2 * Ln, &WB));
+    const bool square = ca == cb;
+    NTTB200_TRY(mul_buf(s, kWA, (size_t)batch * 2 * Ln * (square ? 1 : 2), &WA));      // both operands in one array: one transform call
+    WB = WA + (size_t)batch * 2 * Ln;
     NTTB200_TRY(mul_buf(s, kD, (size_t)batch * 3 * Ln, &D));
     NTTB200_TRY(mul_buf(s, kYP, (size_t)batch * 3 * k * n, &YP));
-    const bool square = ca == cb;
     for (int op = 0; op < (square ? 1 : 2); op++) {
         u64 *Wx = op == 0 ? WA : WB;
         k_gather_q<<<pair_grid3(n, rp, 2 * batch), 256, 0, st>>>(op == 0 ? ca : cb, Wx, n, r, L);
         BconvArgs A{Wx, Ln, Wx + (size_t)rp * n, Ln, s->preQ, s->modQ, s->binvQ, s->M_QP, s->corr_QP, s->r64P, s->modP, rp, k, n, s->h};
         k_bconv<<<grid1(n, 2 * batch), 128, (size_t)rp * k * 8, st>>>(A);
         KCHECK();
-        NTTB200_TRY(ntt_call(b->ctx, false, Wx, 2 * batch * rp, rp, rp, Ln, st));
-        NTTB200_TRY(ntt_call(s->ctxP, false, Wx + (size_t)rp * n, 2 * batch * k, k, k, Ln, st));
     }
+    NTTB200_TRY(ntt_call(s->ctxQP, false, WA, (square ? 2 : 4) * batch * L, L, 0, 0, st));
     k_tensor<<<pair_grid3(n, L, batch), 256, 0, st>>>(WA, square ? WA : WB, D, n, L, s->modQP);
     KCHECK();
-    NTTB200_TRY(ntt_call(b->ctx, true, D, 3 * batch * rp, rp, rp, Ln, st));
-    NTTB200_TRY(ntt_call(s->ctxP, true, D + (size_t)rp * n, 3 * batch * k, k, k, Ln, st));
+    NTTB200_TRY(ntt_call(s->ctxQP, true, D, 3 * batch * L, L, 0, 0, st));
     ScaleArgs S{D, YP, s->preQs, s->modQ, s->modP, s->theta, s->W, s->lam, s->r64P, rp, k, n, s->h};
     k_scale<<<grid1(n, 3 * batch), 128, (size_t)rp * k * 8, st>>>(S);
     BconvArgs Bk{YP, (size_t)k * n, y, (size_t)rp * n, s->preP, s->modP, s->binvP, s->M_PQ, s->corr_PQ, s->r64Q, s->modQ, k, rp, n, s->h};
@@ -282,7 +305,8 @@ static int run_relin(nttb200_bfv *b, nttb200_mul_state *s, u64 *c_out, const u64
     k_relin_lift<<<pair_grid3(n, rp * rp, batch), 256, 0, st>>>(y + (size_t)2 * rp * n, (size_t)3 * rp * n, Dd, n, rp, s->modQ);
     KCHECK();
     NTTB200_TRY(ntt_call(b->ctx, false, Dd, batch * rp * rp, rp, 0, 0, st));
-    k_relin_accum<<<pair_grid3(n, rp, 2 * batch), 256, 0, st>>>(Dd, s->evk, s->evk_s, acc, n, rp, s->modQ);
+    k_relin_accum<<<dim3((batch + kAccumItems - 1) / kAccumItems, (n + 255) / 256, rp), 128, 0, st>>>(Dd, s->evk, acc, n, rp, batch, s->h,
+                                                                                                       s->modQ, s->r64Q);
     KCHECK();
     NTTB200_TRY(ntt_call(b->ctx, true, acc, batch * 2 * rp, rp, 0, 0, st));
     k_relin_add<<<pair_grid3(n, rp, 2 * batch), 256, 0, st>>>(y, (size_t)3 * rp * n, acc, c_out, n, rp, r, s->modQ);
@@ -308,7 +332,7 @@ int nttb200_bfv_relin_keygen(nttb200_bfv *b, const nttb200_u64 *sk, nttb200_u64 
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned n = b->n, rp = s->rp;
     const size_t words = (size_t)rp * 2 * rp * n;
-    if (!s->evk) { NTTB200_CHECK(cudaMalloc(&s->evk, words * 8)); NTTB200_CHECK(cudaMalloc(&s->evk_s, words * 8)); }
+    if (!s->evk) NTTB200_CHECK(cudaMalloc(&s->evk, words * 8));
     const size_t ks_stride = (size_t)rp * n * 8 + (size_t)n * 4;
     unsigned char *ks = nullptr;
     u64 *E = nullptr;
@@ -321,7 +345,6 @@ int nttb200_bfv_relin_keygen(nttb200_bfv *b, const nttb200_u64 *sk, nttb200_u64 
     if (!rc) rc = ntt_call(b->ctx, false, E, rp * rp, rp, 0, 0, st);
     if (!rc) {
         k_relin_combine<<<pair_grid3(n, rp * rp, 1), 256, 0, st>>>(s->evk, E, sk, n, rp, s->modQ);
-        k_build_companions<<<grid_for(words, 256), 256, 0, st>>>(s->evk, s->evk_s, b->ctx->q_dev, b->ctx->logn, rp, 2 * rp * rp);
         rc = (int)cudaGetLastError();
     }
     if (!rc) rc = (int)cudaStreamSynchronize(st);

@@ -224,23 +224,61 @@ NTT_KERNEL void k_relin_lift(const u64 *y2, size_t y2_item, u64 *D, unsigned n, 
         st2(dst + j, mod_exact(v.x, m.q, m.ratio), mod_exact(v.y, m.q, m.ratio));
     }
 }
-// acc[item][h][j][n] = sum_i D[item][i][j][n] * evk[i][h][j][n] mod q_j (NTT domain, canonical).  grid (x, rp, 2 * items)
-NTT_KERNEL void k_relin_accum(const u64 *D, const u64 *evk, const u64 *evk_s, u64 *acc, unsigned n, unsigned rp, const ModC *modQ)
+// acc[item][h][j][n] = sum_i D[item][i][j][n] * evk[i][h][j][n] mod q_j (NTT domain, canonical).  grid (ceil(items / kAccumItems), x, rp): the item
+// groups of one (coefficient range, limb) are neighbours in launch order, so the key words the first one pulls from HBM are L2 hits for the
+// others.  One thread = one PAIR of coefficients of limb j for BOTH halves and kAccumItems items: every digit word is read once (round-2
+// first version: once per half, plus a Shoup companion per key word); the loads of digit i + 1 are issued before the products of digit i;
+// the products are the lazy split-word sums of k_bconv, one reduction per output word.
+constexpr int kAccumItems = 2;
+struct AccumLoads { ulonglong2 e0, e1, d[kAccumItems]; };
+NTT_KERNEL void __launch_bounds__(128) k_relin_accum(const u64 *D, const u64 *evk, u64 *acc, unsigned n, unsigned rp, unsigned items,
+                                                     unsigned h, const ModC *modQ, const ShoupC *r64)
 {
-    const unsigned jl = blockIdx.y, h = blockIdx.z & 1u;
-    const size_t k = blockIdx.z >> 1;
+    const unsigned jl = blockIdx.z;
+    const unsigned k0 = blockIdx.x * kAccumItems;
+    const unsigned cnt = items - k0 < (unsigned)kAccumItems ? items - k0 : (unsigned)kAccumItems;
     const ModC m = modQ[jl];
-    u64 *dst = acc + ((k * 2 + h) * rp + jl) * (size_t)n;
-    NTT_PAIR_STRIDE(j, n) {
-        u64 s0 = 0, s1 = 0;
+    const ShoupC r = r64[jl];
+    const u64 mask = (1ull << h) - 1;
+    const size_t limb = (size_t)jl * n, rpn = (size_t)rp * n;
+    auto split = [&](u64 v) { SplitC c; c.c0 = (u32)(v & mask); c.c1 = (u32)(v >> h); return c; };
+    for (u32 j = 2 * (blockIdx.y * blockDim.x + threadIdx.x); j < n; j += 2 * gridDim.y * blockDim.x) {
+        auto fetch = [&](unsigned i) {
+            AccumLoads L;
+            L.e0 = ld2(evk + ((size_t)i * 2) * rpn + limb + j);
+            L.e1 = ld2(evk + ((size_t)i * 2 + 1) * rpn + limb + j);
+#pragma unroll
+            for (int t = 0; t < kAccumItems; t++) {
+                const unsigned it = t < (int)cnt ? k0 + t : k0;               // a short last group re-reads its first item (not stored)
+                L.d[t] = ld2(D + ((size_t)it * rp + i) * rpn + limb + j);
+            }
+            return L;
+        };
+        Acc3 a[kAccumItems][2][2];                                            // [item][half][coefficient of the pair]
+#pragma unroll
+        for (int t = 0; t < kAccumItems; t++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) acc_init(a[t][q >> 1][q & 1], 0);
+        AccumLoads cur = fetch(0);
         for (unsigned i = 0; i < rp; i++) {
-            const ulonglong2 d = ld2(D + ((k * rp + i) * rp + jl) * (size_t)n + j);
-            const size_t eo = (((size_t)i * 2 + h) * rp + jl) * (size_t)n + j;
-            const ulonglong2 e = ld2(evk + eo), es = ld2(evk_s + eo);
-            s0 += shoup_mul(d.x, e.x, es.x, m.q);          // each < 2 q_j; rp <= 32 terms of < 2^59
-            s1 += shoup_mul(d.y, e.y, es.y, m.q);
+            const AccumLoads nxt = fetch(i + 1 < rp ? i + 1 : i);
+            const SplitC e0x = split(cur.e0.x), e0y = split(cur.e0.y), e1x = split(cur.e1.x), e1y = split(cur.e1.y);
+#pragma unroll
+            for (int t = 0; t < kAccumItems; t++) {
+                const SplitC dx = split(cur.d[t].x), dy = split(cur.d[t].y);
+                acc_mac(a[t][0][0], dx.c0, dx.c1, e0x);
+                acc_mac(a[t][0][1], dy.c0, dy.c1, e0y);
+                acc_mac(a[t][1][0], dx.c0, dx.c1, e1x);
+                acc_mac(a[t][1][1], dy.c0, dy.c1, e1y);
+            }
+            cur = nxt;
         }
-        st2(dst + j, mod_exact(s0, m.q, m.ratio), mod_exact(s1, m.q, m.ratio));
+#pragma unroll
+        for (int t = 0; t < kAccumItems; t++) {
+            if (t >= (int)cnt) break;
+            st2(acc + ((size_t)(k0 + t) * 2) * rpn + limb + j, acc_reduce(a[t][0][0], h, m, r), acc_reduce(a[t][0][1], h, m, r));
+            st2(acc + ((size_t)(k0 + t) * 2 + 1) * rpn + limb + j, acc_reduce(a[t][1][0], h, m, r), acc_reduce(a[t][1][1], h, m, r));
+        }
     }
 }
 // out[item][h][r slots][n] limb j = (y[item][h][rp][n] + acc[item][h][rp][n]) mod q_j (coefficient domain).  grid (x, rp, 2 * items)
