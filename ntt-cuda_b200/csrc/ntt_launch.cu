@@ -5,6 +5,7 @@
 
 #include <atomic>
 #include "ntt_kernels.cuh"
+#include "ntt_cluster.cuh"
 #include "launch_util.h"
 
 #include <cstdlib>
@@ -139,9 +140,25 @@ static int launch_single(const NttArgs &A, cudaStream_t st)
     ntt_single_pass<P, LOGN, INV><<<A.num, 1 << (LOGN - 2), (size_t)8 << LOGN, st>>>(A);
     { const int e__ = (int)cudaGetLastError(); return e__ ? nttb200_trace_error(e__, __FILE__, __LINE__) : 0; }
 }
+// NTTB200_CLUSTER_NTT=0 keeps the one-CTA latency kernel (A/B)
+static bool use_cluster_ntt()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("NTTB200_CLUSTER_NTT"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v != 0;
+}
+// n <= 4096, at most kClusterNttMaxPolys polynomials: one transform per cluster of n / 1024 CTAs (ntt_cluster_pass)
+template <class P, int LOGN, bool INV>
+static int launch_cluster(const NttArgs &A, cudaStream_t st)
+{
+    ntt_cluster_pass<P, LOGN, INV><<<A.num << (LOGN - 10), kClusterThreads, 0, st>>>(A);
+    { const int e__ = (int)cudaGetLastError(); return e__ ? nttb200_trace_error(e__, __FILE__, __LINE__) : 0; }
+}
 template <class P, bool INV>
 static int launch_single_logn(unsigned logn, const NttArgs &A, cudaStream_t st)
 {
+    if (A.num <= kClusterNttMaxPolys && use_cluster_ntt())
+        return logn == 11 ? launch_cluster<P, 11, INV>(A, st) : launch_cluster<P, 12, INV>(A, st);
     return logn == 11 ? launch_single<P, 11, INV>(A, st) : launch_single<P, 12, INV>(A, st);
 }
 
