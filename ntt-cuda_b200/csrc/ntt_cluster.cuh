@@ -54,10 +54,15 @@ __global__ void __cluster_dims__(1 << (LOGN - 10), 1, 1) __launch_bounds__(kClus
     __shared__ __align__(16) u64 xt[BL];             // inverse: cross-round input, [m][column of this CTA]
     const u32 t = threadIdx.x, c = cluster_ctarank(), p = blockIdx.x / CS;
     const u32 grp = p / A.group_polys, idx = p - grp * A.group_polys;
+    // Programmatic dependent launch (the launcher sets cudaLaunchAttributeProgrammaticStreamSerialization): the NEXT kernel of the stream
+    // may be scheduled while this one runs, and this one may have been scheduled while its predecessor was still running -- nothing
+    // before griddepcontrol.wait touches global memory; after it, everything the predecessor wrote is visible (stream order is kept).
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    cluster_arrive();                                // #1: after the matching wait every CTA of the cluster is resident (its shared memory exists)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     P pol;
     pol.init(A, p % A.division, n);
     u64 *g = A.a + (size_t)grp * A.group_stride + ((size_t)idx << LOGN);
-    cluster_arrive();                                // #1: after the matching wait every CTA of the cluster is resident (its shared memory exists)
     u64 v[4];
     // The 1023 table entries of block c's ten local stages -- stage s, entries [2^s + c 2^(s-XS), + 2^(s-XS)) -- are staged in shared
     // memory NOW, as a heap (entry L = 2^(s-XS) + j), while the coefficients are on their way: loads issued inside the rounds would each

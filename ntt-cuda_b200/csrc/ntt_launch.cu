@@ -147,11 +147,27 @@ static bool use_cluster_ntt()
     if (v < 0) { const char *e = getenv("NTTB200_CLUSTER_NTT"); v = (e && e[0] == '0') ? 0 : 1; }
     return v != 0;
 }
+// NTTB200_PDL=0: plain stream serialisation for the cluster kernel (A/B)
+static bool use_pdl()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("NTTB200_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v != 0;
+}
 // n <= 4096, at most kClusterNttMaxPolys polynomials: one transform per cluster of n / 1024 CTAs (ntt_cluster_pass)
 template <class P, int LOGN, bool INV>
 static int launch_cluster(const NttArgs &A, cudaStream_t st)
 {
-    ntt_cluster_pass<P, LOGN, INV><<<A.num << (LOGN - 10), kClusterThreads, 0, st>>>(A);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(A.num << (LOGN - 10));
+    cfg.blockDim = dim3(kClusterThreads);
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // see the kernel: griddepcontrol.wait precedes its first global access
+    at[0].val.programmaticStreamSerializationAllowed = use_pdl() ? 1 : 0;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    NTTB200_CHECK(cudaLaunchKernelEx(&cfg, ntt_cluster_pass<P, LOGN, INV>, A));
     { const int e__ = (int)cudaGetLastError(); return e__ ? nttb200_trace_error(e__, __FILE__, __LINE__) : 0; }
 }
 template <class P, bool INV>

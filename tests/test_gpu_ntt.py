@@ -40,7 +40,10 @@ def _expect(oracle, a, n, qs, psi, psiinv, num, division, inverse, literal=False
 
 
 @pytest.mark.parametrize("tma", [1, 0])
-@pytest.mark.parametrize("logn,limbs,num", [(11, 1, 3), (12, 1, 2), (12, 3, 5), (13, 1, 2), (14, 9, 11), (15, 16, 40), (16, 3, 4), (17, 2, 3)])
+# n <= 4096 has three schedules by polynomial count: <= 32 one cluster per transform (ntt_cluster.cuh), <= 64 one CTA per transform
+# (ntt_single_pass), more: the two batched passes -- (11, 2, 40), (12, 3, 33), (12, 2, 70), (11, 1, 32) pin the boundaries.
+@pytest.mark.parametrize("logn,limbs,num", [(11, 1, 3), (12, 1, 2), (12, 3, 5), (13, 1, 2), (14, 9, 11), (15, 16, 40), (16, 3, 4), (17, 2, 3),
+                                            (11, 2, 40), (12, 3, 33), (12, 2, 70), (11, 1, 32)])
 def test_ctx_forward_inverse_vs_oracle(oracle, logn, limbs, num, tma):
     import nttb200
     from tests.gpu_util import to_dev, to_host
