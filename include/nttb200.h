@@ -325,6 +325,8 @@ NTTB200_API int nttb200_bfv_encrypt_sharded(nttb200_bfv *bfv, nttb200_comm *comm
  *           round is the barrier; the owner sums the slots while rounding (dec_round :253-263) and the round's plaintext is
  *           all-gathered as 16-bit words -- the path's final gather -- under the next round's transforms.
  *   mode 2 / 3: the same with the sums stored into the owner's slot directly by the kernel that forms them (3: one round).
+ *           With the default configuration (mode 4, chunks 0) a SMALL call -- a block below 2^24 coefficient-limbs, e.g. 64 ciphertexts
+ *           on 8 GPUs -- runs as mode 3: it is latency-bound and one round of direct stores is the shortest chain.
  *           Modes 2-4 fall back to mode 0 on all ranks when CUDA IPC is unavailable.
  *   mode 0: ncclReduce of the sums to the owner, each block in `chunks` pieces, on a second stream next to the transforms.
  *   mode 1: `chunks` ncclReduceScatter calls, rounding, one ncclAllGather. */

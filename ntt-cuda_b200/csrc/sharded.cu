@@ -498,7 +498,12 @@ int nttb200_bfv_decrypt_sharded(nttb200_bfv *b, nttb200_comm *comm, nttb200_u64 
     TRY(shard_state(b, &s, 1));
     std::vector<nttb200_shard_block> blk(G);
     plan_blocks(rp, n, batch, G, g, blk.data(), nullptr);
-    unsigned chunks = G > 1 ? (s->chunks ? s->chunks : (s->mode == 4 ? 2u : 4u)) : 1u;
+    // Default schedule (mode 4, chunks 0) by the size of the call: large batches push their sums with the copy engines in two rounds;
+    // a small one (a block below 2^24 coefficient-limbs, e.g. 64 ciphertexts on 8 GPUs) is latency-bound, and one round of direct
+    // stores by the kernel is the shortest chain (measured at batch 64, 8 GPUs: 0.30 ms against 0.40).
+    int mode = s->mode;
+    if (mode == 4 && !s->chunks && (size_t)per * n * rp < ((size_t)1 << 24)) mode = 3;
+    unsigned chunks = G > 1 ? (s->chunks ? s->chunks : (mode == 4 ? 2u : 4u)) : 1u;
     while (chunks > 1 && per % chunks) chunks--;
     TRY(shard_state(b, &s, (size_t)3 * G * chunks + 8));
     const unsigned sub = per / chunks;                                   // items of one block in one chunk
@@ -520,7 +525,7 @@ int nttb200_bfv_decrypt_sharded(nttb200_bfv *b, nttb200_comm *comm, nttb200_u64 
         NTTB200_CHECK(cudaStreamWaitEvent(st, s->ev[evi], 0));
         return 0;
     }
-    const bool p2p_mode = s->mode >= 2;          // 2 / 3: peer stores by the kernel; 4: local sums pushed by the copy engines
+    const bool p2p_mode = mode >= 2;          // 2 / 3: peer stores by the kernel; 4: local sums pushed by the copy engines
     if (p2p_mode && !s->p2p_failed && !comm->fake) {
         // Peer-to-peer: the partial-sum kernel of a tile writes straight into slot `rank` of the buffer of the items' OWNER, mapped
         // here through CUDA IPC -- NVLink stores issued by the kernel that produces the sums: compute and transfer are one kernel, no
@@ -535,7 +540,7 @@ int nttb200_bfv_decrypt_sharded(nttb200_bfv *b, nttb200_comm *comm, nttb200_u64 
         // instead of 9.8 for 4096 ciphertexts on 8 GPUs).
         // mode 2: `chunks` rounds, round c covering piece c of EVERY owner's block, so the owners round and gather piece c while the
         //         next round's transforms run; mode 3: one round (largest launches, everything after the last transform is exposed).
-        const unsigned rounds = s->mode == 3 ? 1u : chunks;
+        const unsigned rounds = mode == 3 ? 1u : chunks;
         const unsigned piece = per / rounds;
         // (Running all transforms first -- same-window blocks merged into large launches -- and depositing afterwards was measured
         // SLOWER, 8.8 ms against 7.5: the peer stores then come in one burst with nothing to overlap them.  Tile by tile, the
@@ -548,7 +553,7 @@ int nttb200_bfv_decrypt_sharded(nttb200_bfv *b, nttb200_comm *comm, nttb200_u64 
                 u64 *dst = comm->fake ? partial + ((size_t)j * per + (size_t)c * piece) * pw
                                       : (u64 *)s->sym[kSymSlots].peer[j] + ((size_t)g * per + (size_t)c * piece) * pw;
                 const bool alt = (tau & 1) != 0;
-                const bool ce = s->mode == 4 && !comm->fake && j != g;          // sums into local scratch, pushed by a copy engine afterwards
+                const bool ce = mode == 4 && !comm->fake && j != g;          // sums into local scratch, pushed by a copy engine afterwards
                 u64 *loc = partial + ((size_t)j * per + (size_t)c * piece) * pw;
                 if (cnt) TRY(dec_partial(b, alt ? P2 : P, ce ? loc : dst, packed, c_shard + blk[j].offset + (size_t)c * piece * 2 * cnt * n, cnt, blk[j].first_limb, cnt, piece));
                 else NTTB200_CHECK(cudaMemsetAsync(ce ? loc : dst, 0, (size_t)piece * pw * 8, alt ? s->st2 : st));
@@ -579,7 +584,7 @@ int nttb200_bfv_decrypt_sharded(nttb200_bfv *b, nttb200_comm *comm, nttb200_u64 
                                                (size_t)piece * n, ncclUint64, (int)j, comm->comm, s->cs));
             }
         }
-    } else if (s->mode != 1) {
+    } else if (mode != 1) {
         // Block by block, each in `chunks` pieces: transforms + partial sums of a piece on the caller's stream; on the comm stream,
         // behind them, the piece's sums go to the block's owner (ncclReduce), the owner rounds it, and when a block is complete its
         // owner broadcasts the 16-bit plaintext words -- so the only exposed communication is the LAST piece's reduce + broadcast.

@@ -60,7 +60,7 @@ def main():
     shard = torch.zeros_like(expect_shard)
     res = {}
     ok_enc = ok_dec = True
-    for mode, chunks in ((4, 2), (2, 4), (3, 1), (0, 4), (1, 4)):
+    for mode, chunks in ((4, 0), (4, 2), (2, 4), (3, 1), (0, 4), (1, 4)):      # (4, 0) = the library's default schedule
         bfv.shard_config(mode, chunks)
         shard.zero_()
         bfv.encrypt_sharded(comm, shard, m, B, nonce0=3)
