@@ -576,3 +576,64 @@ EXPORT int emu_build_tables(u64 *psi, u64 *psi_s, u64 *psiinv, u64 *psiinv_s, co
     emu_launch(g, 128, 0, [&] { k_build_tables(psi, psi_s, psiinv, psiinv_s, q, roots, roots_inv, logn); });
     return 0;
 }
+
+// ---- BFV multiplication kernels (csrc/mul_kernels.cuh) on the emulator: plain constants in, the device structures are built here -----
+#include "../mul_kernels.cuh"
+namespace {
+ModC emu_modc(u64 q)
+{
+    ModC m; m.q = q; m.ratio = ~0ull / q; m.qbit = 0; while ((q >> m.qbit) != 0) m.qbit++;
+    m.mu = (u64)(((unsigned __int128)1 << (2 * m.qbit)) / q); m.pad = 0;
+    return m;
+}
+ShoupC emu_shoupc(u64 c, u64 q) { ShoupC s; s.c = c; s.cs = (u64)(((unsigned __int128)c << 64) / q); return s; }
+SplitC emu_splitc(u64 c, unsigned h) { SplitC r; r.c0 = (u32)(c & ((1ull << h) - 1)); r.c1 = (u32)(c >> h); return r; }
+}  // namespace
+
+// x[items][lin][n] -> out[items][lout][n]; pre[lin] = (B/b_i)^-1 mod b_i, M[lout][lin] = B/b_i mod o_j, corr[lout] = B mod o_j
+EXPORT int emu_mul_bconv(const u64 *x, u64 *out, unsigned items, unsigned lin, unsigned lout, unsigned n, unsigned h, const u64 *bin,
+                         const u64 *bout, const u64 *pre, const double *binv, const u64 *M, const u64 *corr)
+{
+    std::vector<ShoupC> preS(lin), r64(lout);
+    std::vector<ModC> min_(lin), mout(lout);
+    std::vector<SplitC> Ms((size_t)lin * lout);
+    for (unsigned i = 0; i < lin; i++) { min_[i] = emu_modc(bin[i]); preS[i] = emu_shoupc(pre[i], bin[i]); }
+    for (unsigned j = 0; j < lout; j++) {
+        mout[j] = emu_modc(bout[j]);
+        r64[j] = emu_shoupc((u64)(((unsigned __int128)1 << 64) % bout[j]), bout[j]);
+        for (unsigned i = 0; i < lin; i++) Ms[(size_t)j * lin + i] = emu_splitc(M[(size_t)j * lin + i], h);
+    }
+    BconvArgs A{x, (size_t)lin * n, out, (size_t)lout * n, preS.data(), min_.data(), binv, Ms.data(), corr, r64.data(), mout.data(), lin, lout, n, h};
+    emu_dim3 g; g.x = (n + 127) / 128; g.y = items;
+    emu_launch(g, 128, (size_t)lin * lout * 8, [&] { k_bconv(A); });
+    return 0;
+}
+// d[kc][rp + k][n] -> y[kc][k][n]
+EXPORT int emu_mul_scale(const u64 *d, u64 *y, unsigned kc, unsigned rp, unsigned k, unsigned n, unsigned h, const u64 *qQ, const u64 *qP,
+                         const u64 *preQ, const double *theta, const u64 *W, const u64 *lam)
+{
+    std::vector<ShoupC> preS(rp), r64(k);
+    std::vector<ModC> mQ(rp), mP(k);
+    std::vector<SplitC> Ws((size_t)rp * k), lams(k);
+    for (unsigned i = 0; i < rp; i++) { mQ[i] = emu_modc(qQ[i]); preS[i] = emu_shoupc(preQ[i], qQ[i]); }
+    for (unsigned j = 0; j < k; j++) {
+        mP[j] = emu_modc(qP[j]);
+        r64[j] = emu_shoupc((u64)(((unsigned __int128)1 << 64) % qP[j]), qP[j]);
+        lams[j] = emu_splitc(lam[j], h);
+        for (unsigned i = 0; i < rp; i++) Ws[(size_t)j * rp + i] = emu_splitc(W[(size_t)j * rp + i], h);
+    }
+    ScaleArgs S{d, y, preS.data(), mQ.data(), mP.data(), theta, Ws.data(), lams.data(), r64.data(), rp, k, n, h};
+    emu_dim3 g; g.x = (n + 127) / 128; g.y = kc;
+    emu_launch(g, 128, (size_t)rp * k * 8, [&] { k_scale(S); });
+    return 0;
+}
+// D[items][rp][rp][n], evk[rp][2][rp][n] -> acc[items][2][rp][n]
+EXPORT int emu_mul_relin_accum(const u64 *D, const u64 *evk, u64 *acc, unsigned n, unsigned rp, unsigned items, unsigned h, const u64 *qQ)
+{
+    std::vector<ModC> mQ(rp);
+    std::vector<ShoupC> r64(rp);
+    for (unsigned i = 0; i < rp; i++) { mQ[i] = emu_modc(qQ[i]); r64[i] = emu_shoupc((u64)(((unsigned __int128)1 << 64) % qQ[i]), qQ[i]); }
+    emu_dim3 g; g.x = (items + kAccumItems - 1) / kAccumItems; g.y = (n + 255) / 256; g.z = rp;
+    emu_launch(g, 128, 0, [&] { k_relin_accum(D, evk, acc, n, rp, items, h, mQ.data(), r64.data()); });
+    return 0;
+}

@@ -95,7 +95,8 @@ struct BconvArgs {
 };
 NTT_KERNEL void __launch_bounds__(128) k_bconv(BconvArgs A)
 {
-    extern __shared__ SplitC mul_smem[];
+    NTT_DYN_SMEM(mul_raw);
+    SplitC *mul_smem = reinterpret_cast<SplitC *>(mul_raw);
     for (unsigned i = threadIdx.x; i < A.lin * A.lout; i += blockDim.x) mul_smem[i] = A.M[i];
     __syncthreads();
     const size_t k = blockIdx.y;
@@ -144,7 +145,8 @@ struct ScaleArgs {
 };
 NTT_KERNEL void __launch_bounds__(128) k_scale(ScaleArgs A)
 {
-    extern __shared__ SplitC mul_smem[];
+    NTT_DYN_SMEM(mul_raw);
+    SplitC *mul_smem = reinterpret_cast<SplitC *>(mul_raw);
     for (unsigned i = threadIdx.x; i < A.rp * A.k; i += blockDim.x) mul_smem[i] = A.W[i];
     __syncthreads();
     const size_t kc = blockIdx.y;             // item * comps + comp
