@@ -528,6 +528,31 @@ def reference_gpu_rebuilt():
         return {"error": str(e)[:200]}
 
 
+def bind_near_gpu(torch, local):
+    """Pin this process (and the pinned host buffers it is about to allocate: first touch) to the CPUs of the GPU's NUMA node, as any
+    multi-GPU host program does -- with one process per GPU and no binding, every rank's staging memory can land on one socket and the
+    other socket's GPUs copy across the inter-socket link.  Returns (description, original affinity); a no-op when the node's CPUs are
+    not in this process's cpuset."""
+    try:
+        allowed = os.sched_getaffinity(0)
+        pr = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        txt = open("/sys/bus/pci/devices/%s/local_cpulist" % bdf).read().strip()
+        node = open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if part:
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        want = cpus & allowed
+        if not want or want == allowed:
+            return {"gpu": bdf, "numa_node": node, "bound": False, "cpus_allowed": len(allowed), "cpus_local": len(want)}, allowed
+        os.sched_setaffinity(0, want)
+        return {"gpu": bdf, "numa_node": node, "bound": True, "cpus_allowed": len(allowed), "cpus_local": len(want)}, allowed
+    except Exception as e:  # pragma: no cover  (no sysfs entry, old torch: run unbound)
+        return {"bound": False, "error": str(e)[:120]}, None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -539,6 +564,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    numa, affinity0 = bind_near_gpu(torch, local) if os.environ.get("NTTB200_BENCH_NUMA", "1") != "0" else ({"bound": False}, None)
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -667,6 +693,8 @@ def run_ours(args):
             int_pipe["frac"] = int_pipe["kernels"][dom]["frac"]
         cb = None
         if world == 1 and not args.no_cpu_baseline:
+            if affinity0:
+                os.sched_setaffinity(0, affinity0)       # the CPU baseline uses every host thread of the cpuset
             cb, _, _ = cpu_ntt_rate(budget_s=12.0)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -691,6 +719,7 @@ def run_ours(args):
             "cpu_baseline": cb,
             "reference_gpu_rebuilt": reference_gpu_rebuilt() if world == 1 and not args.no_cpu_baseline else None,
         }
+        line["config"]["host_binding"] = numa             # rank 0's; every rank binds to its own GPU's NUMA node (bind_near_gpu)
         line.update(extras)
         print(json.dumps(line))
     if world > 1:
