@@ -89,6 +89,21 @@ NTTB200_API int nttb200_forward_ntt_batch_host(nttb200_ctx *ctx, const nttb200_u
                                                unsigned division);
 NTTB200_API int nttb200_inverse_ntt_batch_host(nttb200_ctx *ctx, const nttb200_u64 *in_host, nttb200_u64 *out_host, unsigned num,
                                                unsigned division);
+/* Compact host / wire format for residue polynomials (the reference's only serialisation is the text dump of
+ * decryption_test.cu:329-344): polynomial p (limb p % division) is stored as n * qbit_limb BITS -- coefficient j at bit offset
+ * j * qbit_limb, little-endian bits in little-endian 64-bit words -- polynomials back to back in the order of a[num][n].  55-bit
+ * residues take 14 % fewer bytes than 64-bit words.  num must be a multiple of division.
+ *   nttb200_polys_packed_words                    words of `num` packed polynomials
+ *   nttb200_pack_polys / _unpack_polys            device <-> device conversion (canonical residues in, canonical residues out)
+ *   nttb200_forward_/inverse_ntt_batch_host_packed  the host-buffer transforms with BOTH host arrays in the packed format: packed
+ *       H2D -> unpack -> transform -> pack -> packed D2H, chunks overlapped on internal streams; synchronous. */
+NTTB200_API int nttb200_polys_packed_words(const nttb200_ctx *ctx, unsigned num, unsigned division, size_t *words);
+NTTB200_API int nttb200_pack_polys(nttb200_ctx *ctx, nttb200_u64 *packed, const nttb200_u64 *a, unsigned num, unsigned division, void *stream);
+NTTB200_API int nttb200_unpack_polys(nttb200_ctx *ctx, nttb200_u64 *a, const nttb200_u64 *packed, unsigned num, unsigned division, void *stream);
+NTTB200_API int nttb200_forward_ntt_batch_host_packed(nttb200_ctx *ctx, const nttb200_u64 *in_packed_host, nttb200_u64 *out_packed_host,
+                                                      unsigned num, unsigned division);
+NTTB200_API int nttb200_inverse_ntt_batch_host_packed(nttb200_ctx *ctx, const nttb200_u64 *in_packed_host, nttb200_u64 *out_packed_host,
+                                                      unsigned num, unsigned division);
 
 /* ---------------------------------------------------------------------------------------------------
  * NTT / INTT, stateless reference-contract path: nothing but the reference's tables and (q, mu, qbit);

@@ -4,6 +4,7 @@
 // cudaMemcpyToSymbol into six 16-entry __constant__ tables).
 #include "internal.h"
 #include "table_kernels.cuh"
+#include "bfv_kernels.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -148,7 +149,9 @@ void nttb200_ctx_destroy(nttb200_ctx *c)
     if (!c) return;
     cudaFree(c->psi); cudaFree(c->psiinv); cudaFree(c->psi_s); cudaFree(c->psiinv_s);
     cudaFree(c->lc); cudaFree(c->q_dev); cudaFree(c->mu_dev); cudaFree(c->qbit_dev);
+    cudaFree(c->word_off_dev);
     for (int i = 0; i < nttb200_ctx::kStages; i++) {
+        if (c->stage_packed[i]) cudaFree(c->stage_packed[i]);
         if (c->stage_dev[i]) cudaFree(c->stage_dev[i]);
         if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
     }
@@ -233,6 +236,108 @@ static int host_pipeline(nttb200_ctx *c, bool inverse, const u64 *in, u64 *out, 
     }
     for (int i = 0; i < nttb200_ctx::kStages; i++) NTTB200_CHECK(cudaStreamSynchronize(c->streams[i]));
     return 0;
+}
+
+// ---- packed host / wire format ---------------------------------------------------------------------------------------------------
+static int packed_setup(nttb200_ctx *c)
+{
+    if (c->word_off_dev) return 0;
+    c->word_off.assign(c->limbs + 1, 0);
+    for (unsigned l = 0; l < c->limbs; l++) {
+        const unsigned long long w = (unsigned long long)c->word_off[l] + (unsigned long long)(c->n / 64) * c->qbit[l];
+        if (w >> 32) return NTTB200_EINVAL;
+        c->word_off[l + 1] = (unsigned)w;
+    }
+    NTTB200_CHECK(cudaMalloc(&c->word_off_dev, 4 * (c->limbs + 1)));
+    NTTB200_CHECK(cudaMemcpy(c->word_off_dev, c->word_off.data(), 4 * (c->limbs + 1), cudaMemcpyHostToDevice));
+    return 0;
+}
+static int packed_convert(nttb200_ctx *c, bool pack, u64 *packed, u64 *a, unsigned num, unsigned division, cudaStream_t st)
+{
+    const unsigned groups = num / division;
+    const unsigned x = (c->n / 64 + 127) / 128;
+    for (unsigned g0 = 0; g0 < groups; g0 += 65535) {                 // grid.z limit
+        const unsigned gz = groups - g0 < 65535 ? groups - g0 : 65535;
+        u64 *pk = packed + (size_t)g0 * c->word_off[division], *aa = a + (size_t)g0 * division * c->n;
+        if (pack) nttb200::k_ct_pack<<<dim3(x, division, gz), 128, 0, st>>>(aa, pk, c->n, division, gz, c->qbit_dev, c->word_off_dev, c->word_off[division]);
+        else nttb200::k_ct_unpack<<<dim3(x, division, gz), 128, 0, st>>>(pk, aa, c->n, division, gz, c->qbit_dev, c->word_off_dev, c->word_off[division]);
+    }
+    NTTB200_CHECK(cudaGetLastError());
+    return 0;
+}
+static int packed_args(nttb200_ctx *c, unsigned num, unsigned division)
+{
+    if (!c || division == 0 || division > c->limbs || num % division) return NTTB200_EINVAL;
+    return packed_setup(c);
+}
+int nttb200_polys_packed_words(const nttb200_ctx *c, unsigned num, unsigned division, size_t *words)
+{
+    if (!c || !words || division == 0 || division > c->limbs || num % division) return NTTB200_EINVAL;
+    size_t w = 0;
+    for (unsigned l = 0; l < division; l++) w += (size_t)(c->n / 64) * c->qbit[l];
+    *words = w * (num / division);
+    return 0;
+}
+int nttb200_pack_polys(nttb200_ctx *c, nttb200_u64 *packed, const nttb200_u64 *a, unsigned num, unsigned division, void *stream)
+{
+    if (!packed || !a) return NTTB200_EINVAL;
+    int r = packed_args(c, num, division);
+    return r ? r : packed_convert(c, true, packed, const_cast<u64 *>(a), num, division, (cudaStream_t)stream);
+}
+int nttb200_unpack_polys(nttb200_ctx *c, nttb200_u64 *a, const nttb200_u64 *packed, unsigned num, unsigned division, void *stream)
+{
+    if (!packed || !a) return NTTB200_EINVAL;
+    int r = packed_args(c, num, division);
+    return r ? r : packed_convert(c, false, const_cast<u64 *>(packed), a, num, division, (cudaStream_t)stream);
+}
+// host_pipeline with both host arrays in the packed format: per chunk packed H2D -> unpack -> transform -> pack -> packed D2H
+static int host_pipeline_packed(nttb200_ctx *c, bool inverse, const u64 *in, u64 *out, unsigned num, unsigned division)
+{
+    if (!in || !out) return NTTB200_EINVAL;
+    int r = packed_args(c, num, division);
+    if (r) return r;
+    if (num == 0) return 0;
+    static size_t chunk_mb = 0;
+    if (!chunk_mb) { const char *e = getenv("NTTB200_E2E_CHUNK_MB"); chunk_mb = e && atoi(e) > 0 ? (size_t)atoi(e) : 32; }
+    size_t per = (chunk_mb << 20) / ((size_t)c->n * 8) / division * division;          // polynomials per chunk, whole groups
+    if (per == 0) per = division;
+    const size_t gw = c->word_off[division];                                            // packed words per group
+    const size_t bytes = per * c->n * 8, pbytes = per / division * gw * 8;
+    if (c->stage_bytes < bytes || c->stage_packed_bytes < pbytes) {
+        for (int i = 0; i < nttb200_ctx::kStages; i++) {
+            if (c->stage_bytes < bytes) {
+                if (c->stage_dev[i]) { cudaFree(c->stage_dev[i]); c->stage_dev[i] = nullptr; }
+                NTTB200_CHECK(cudaMalloc(&c->stage_dev[i], bytes));
+            }
+            if (c->stage_packed[i]) { cudaFree(c->stage_packed[i]); c->stage_packed[i] = nullptr; }
+            NTTB200_CHECK(cudaMalloc(&c->stage_packed[i], pbytes));
+            if (!c->streams[i]) NTTB200_CHECK(cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking));
+        }
+        if (c->stage_bytes < bytes) c->stage_bytes = bytes;
+        c->stage_packed_bytes = pbytes;
+    }
+    int k = 0;
+    for (size_t p0 = 0; p0 < num; p0 += per, k = (k + 1) % nttb200_ctx::kStages) {
+        const unsigned cnt = (unsigned)(num - p0 < per ? num - p0 : per);
+        const size_t w0 = p0 / division * gw, w = (size_t)cnt / division * gw;
+        cudaStream_t st = c->streams[k];
+        NTTB200_CHECK(cudaMemcpyAsync(c->stage_packed[k], in + w0, w * 8, cudaMemcpyHostToDevice, st));
+        r = packed_convert(c, false, c->stage_packed[k], c->stage_dev[k], cnt, division, st);
+        if (!r) r = inverse ? nttb200_inverse_ntt_batch(c, c->stage_dev[k], cnt, division, st) : nttb200_forward_ntt_batch(c, c->stage_dev[k], cnt, division, st);
+        if (!r) r = packed_convert(c, true, c->stage_packed[k], c->stage_dev[k], cnt, division, st);
+        if (r) return r;
+        NTTB200_CHECK(cudaMemcpyAsync(out + w0, c->stage_packed[k], w * 8, cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < nttb200_ctx::kStages; i++) NTTB200_CHECK(cudaStreamSynchronize(c->streams[i]));
+    return 0;
+}
+int nttb200_forward_ntt_batch_host_packed(nttb200_ctx *c, const nttb200_u64 *in, nttb200_u64 *out, unsigned num, unsigned division)
+{
+    return host_pipeline_packed(c, false, in, out, num, division);
+}
+int nttb200_inverse_ntt_batch_host_packed(nttb200_ctx *c, const nttb200_u64 *in, nttb200_u64 *out, unsigned num, unsigned division)
+{
+    return host_pipeline_packed(c, true, in, out, num, division);
 }
 
 int nttb200_forward_ntt_batch_host(nttb200_ctx *c, const nttb200_u64 *in, nttb200_u64 *out, unsigned num, unsigned division)

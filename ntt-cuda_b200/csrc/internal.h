@@ -35,6 +35,11 @@ struct nttb200_ctx {
     cudaStream_t streams[kStages] = {nullptr, nullptr, nullptr};
     u64 *stage_dev[kStages] = {nullptr, nullptr, nullptr};
     size_t stage_bytes = 0;
+    // packed host / wire format (nttb200_pack_polys ...): word_off[l] = words of limbs < l of one group, device copy, packed staging
+    std::vector<unsigned> word_off;
+    unsigned *word_off_dev = nullptr;
+    u64 *stage_packed[kStages] = {nullptr, nullptr, nullptr};
+    size_t stage_packed_bytes = 0;
 };
 
 namespace nttb200 {

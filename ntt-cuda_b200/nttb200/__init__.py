@@ -142,6 +142,24 @@ class Context:
     def inverse_ntt_batch_host(self, a_in, a_out, num: int, division: int):
         check(lib().nttb200_inverse_ntt_batch_host(self._h, vp(ptr(a_in)), vp(ptr(a_out)), C.c_uint(num), C.c_uint(division)))
 
+    # compact wire format (n * qbit bits per polynomial; include/nttb200.h): sizes, device <-> device conversion, host-buffer transforms
+    def packed_words(self, num: int, division: int) -> int:
+        w = C.c_size_t()
+        check(lib().nttb200_polys_packed_words(self._h, C.c_uint(num), C.c_uint(division), C.byref(w)))
+        return int(w.value)
+
+    def pack_polys(self, packed, a, num: int, division: int, stream=None):
+        check(lib().nttb200_pack_polys(self._h, vp(ptr(packed)), vp(ptr(a)), C.c_uint(num), C.c_uint(division), vp(_stream(stream))))
+
+    def unpack_polys(self, a, packed, num: int, division: int, stream=None):
+        check(lib().nttb200_unpack_polys(self._h, vp(ptr(a)), vp(ptr(packed)), C.c_uint(num), C.c_uint(division), vp(_stream(stream))))
+
+    def forward_ntt_batch_host_packed(self, p_in, p_out, num: int, division: int):
+        check(lib().nttb200_forward_ntt_batch_host_packed(self._h, vp(ptr(p_in)), vp(ptr(p_out)), C.c_uint(num), C.c_uint(division)))
+
+    def inverse_ntt_batch_host_packed(self, p_in, p_out, num: int, division: int):
+        check(lib().nttb200_inverse_ntt_batch_host_packed(self._h, vp(ptr(p_in)), vp(ptr(p_out)), C.c_uint(num), C.c_uint(division)))
+
 
 # ---- stateless reference-contract entry points (what include/dropin/ntt_60bit.cuh forwards to) ----------------------
 def forwardNTT_batch(device_a, n, psi_powers, num, division, q_cons, mu_cons, q_bit_cons, stream=None):

@@ -144,6 +144,51 @@ def test_host_buffer_entry_point(oracle):
     ctx.close()
 
 
+def _pack_numpy(a, n, qbits, num, division):
+    """The wire format restated in numpy: polynomial p as n * qbit bits, coefficient j at bit offset j * qbit, little-endian."""
+    words = []
+    for p in range(num):
+        qb = qbits[p % division]
+        bits = ((a[p * n:(p + 1) * n, None] >> np.arange(qb, dtype=np.uint64)[None, :]) & np.uint64(1)).astype(np.uint8).reshape(-1)
+        words.append(np.packbits(bits, bitorder="little").view(np.uint64))
+    return np.concatenate(words)
+
+
+@pytest.mark.parametrize("name,num", [("8k_3q", 300), ("16k_9q", 18)])
+def test_packed_wire_format_and_host_packed_transforms(oracle, name, num):
+    """SURVEY.md 8f-3 on the transform path: device pack / unpack against a numpy restatement of the layout, and the host-buffer
+    transforms with both host arrays packed against the unpacked ones (several pipeline chunks, ragged last chunk)."""
+    import nttb200
+    from tests.gpu_util import to_dev, to_host
+    n, qs, roots = params.RNS_SETS[name]
+    L = len(qs)
+    qbits = [int(q).bit_length() for q in qs]
+    ctx = nttb200.Context(n, qs, roots)
+    a = np.concatenate([oracle.fill_uniform(n, qs[p % L], 900 + p) for p in range(num)])
+    a[0], a[1], a[2] = 0, 1, qs[0] - 1
+    words = ctx.packed_words(num, L)
+    assert words == sum(n // 64 * qbits[p % L] for p in range(num))
+    d, pk = to_dev(a), to_dev(np.zeros(words, dtype=np.uint64))
+    ctx.pack_polys(pk, d, num, L)
+    want = _pack_numpy(a, n, qbits, num, L)
+    assert np.array_equal(to_host(pk), want)
+    back = to_dev(np.zeros_like(a))
+    ctx.unpack_polys(back, pk, num, L)
+    assert np.array_equal(to_host(back), a)
+    # host-buffer transforms, packed in and out
+    plain = np.empty_like(a)
+    ctx.forward_ntt_batch_host(a, plain, num, L)
+    pout = np.zeros(words, dtype=np.uint64)
+    ctx.forward_ntt_batch_host_packed(want, pout, num, L)
+    assert np.array_equal(pout, _pack_numpy(plain, n, qbits, num, L))
+    pback = np.zeros(words, dtype=np.uint64)
+    ctx.inverse_ntt_batch_host_packed(pout, pback, num, L)
+    assert np.array_equal(pback, want)
+    with pytest.raises(nttb200.NttB200Error):
+        ctx.packed_words(num + 1, L)               # whole groups only
+    ctx.close()
+
+
 def test_invalid_arguments_fail_loudly():
     import nttb200
     with pytest.raises(nttb200.NttB200Error):
