@@ -280,7 +280,8 @@ static int run_tensor(nttb200_bfv *b, nttb200_mul_state *s, u64 *y, const u64 *c
         u64 *Wx = op == 0 ? WA : WB;
         k_gather_q<<<pair_grid3(n, rp, 2 * batch), 256, 0, st>>>(op == 0 ? ca : cb, Wx, n, r, L);
         BconvArgs A{Wx, Ln, Wx + (size_t)rp * n, Ln, s->preQ, s->modQ, s->binvQ, s->M_QP, s->corr_QP, s->r64P, s->modP, rp, k, n, s->h};
-        k_bconv<<<grid1(n, 2 * batch), 128, (size_t)rp * k * 8, st>>>(A);
+        if (rp <= 16) k_bconv<16><<<grid1(n, 2 * batch), 128, ((size_t)rp * k + 5 * k) * 8, st>>>(A);
+        else k_bconv<kBaseMax><<<grid1(n, 2 * batch), 128, ((size_t)rp * k + 5 * k) * 8, st>>>(A);
         KCHECK();
     }
     NTTB200_TRY(ntt_call(s->ctxQP, false, WA, (square ? 2 : 4) * batch * L, L, 0, 0, st));
@@ -288,9 +289,11 @@ static int run_tensor(nttb200_bfv *b, nttb200_mul_state *s, u64 *y, const u64 *c
     KCHECK();
     NTTB200_TRY(ntt_call(s->ctxQP, true, D, 3 * batch * L, L, 0, 0, st));
     ScaleArgs S{D, YP, s->preQs, s->modQ, s->modP, s->theta, s->W, s->lam, s->r64P, rp, k, n, s->h};
-    k_scale<<<grid1(n, 3 * batch), 128, (size_t)rp * k * 8, st>>>(S);
+    if (rp <= 16) k_scale<16><<<grid1(n, 3 * batch), 128, ((size_t)rp * k + 5 * k) * 8, st>>>(S);
+    else k_scale<kBaseMax><<<grid1(n, 3 * batch), 128, ((size_t)rp * k + 5 * k) * 8, st>>>(S);
     BconvArgs Bk{YP, (size_t)k * n, y, (size_t)rp * n, s->preP, s->modP, s->binvP, s->M_PQ, s->corr_PQ, s->r64Q, s->modQ, k, rp, n, s->h};
-    k_bconv<<<grid1(n, 3 * batch), 128, (size_t)rp * k * 8, st>>>(Bk);
+    if (k <= 16) k_bconv<16><<<grid1(n, 3 * batch), 128, ((size_t)rp * k + 5 * rp) * 8, st>>>(Bk);
+    else k_bconv<kBaseMax><<<grid1(n, 3 * batch), 128, ((size_t)rp * k + 5 * rp) * 8, st>>>(Bk);
     KCHECK();
     return 0;
 }

@@ -605,7 +605,7 @@ EXPORT int emu_mul_bconv(const u64 *x, u64 *out, unsigned items, unsigned lin, u
     }
     BconvArgs A{x, (size_t)lin * n, out, (size_t)lout * n, preS.data(), min_.data(), binv, Ms.data(), corr, r64.data(), mout.data(), lin, lout, n, h};
     emu_dim3 g; g.x = (n + 127) / 128; g.y = items;
-    emu_launch(g, 128, (size_t)lin * lout * 8, [&] { k_bconv(A); });
+    emu_launch(g, 128, ((size_t)lin * lout + 5 * lout) * 8, [&] { if (lin <= 16) k_bconv<16>(A); else k_bconv<kBaseMax>(A); });
     return 0;
 }
 // d[kc][rp + k][n] -> y[kc][k][n]
@@ -624,7 +624,7 @@ EXPORT int emu_mul_scale(const u64 *d, u64 *y, unsigned kc, unsigned rp, unsigne
     }
     ScaleArgs S{d, y, preS.data(), mQ.data(), mP.data(), theta, Ws.data(), lams.data(), r64.data(), rp, k, n, h};
     emu_dim3 g; g.x = (n + 127) / 128; g.y = kc;
-    emu_launch(g, 128, (size_t)rp * k * 8, [&] { k_scale(S); });
+    emu_launch(g, 128, ((size_t)rp * k + 5 * k) * 8, [&] { if (rp <= 16) k_scale<16>(S); else k_scale<kBaseMax>(S); });
     return 0;
 }
 // D[items][rp][rp][n], evk[rp][2][rp][n] -> acc[items][2][rp][n]

@@ -93,22 +93,28 @@ struct BconvArgs {
     const ModC *bout;                        // [lout]  output moduli
     unsigned lin, lout, n, h;                // h: split position of the lazy sums
 };
+template <int LMAX>      // register slots for the input residues: 16 (most parameter sets) or kBaseMax
 NTT_KERNEL void __launch_bounds__(128) k_bconv(BconvArgs A)
 {
     NTT_DYN_SMEM(mul_raw);
     SplitC *mul_smem = reinterpret_cast<SplitC *>(mul_raw);
+    u64 *outc = reinterpret_cast<u64 *>(mul_raw) + (size_t)A.lin * A.lout;      // per output limb: q, ratio, corr, r64.c, r64.cs
     for (unsigned i = threadIdx.x; i < A.lin * A.lout; i += blockDim.x) mul_smem[i] = A.M[i];
+    for (unsigned i = threadIdx.x; i < A.lout; i += blockDim.x) {
+        outc[5 * i] = A.bout[i].q; outc[5 * i + 1] = A.bout[i].ratio; outc[5 * i + 2] = A.corr[i];
+        outc[5 * i + 3] = A.r64[i].c; outc[5 * i + 4] = A.r64[i].cs;
+    }
     __syncthreads();
     const size_t k = blockIdx.y;
     const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= A.n) return;
     const u64 *x = A.x + k * A.in_item + j;
     u64 *o = A.out + k * A.out_item + j;
-    u32 y0[kBaseMax], y1[kBaseMax];
+    u32 y0[LMAX], y1[LMAX];
     const u64 mask = (1ull << A.h) - 1;
     double s = 0.0;
 #pragma unroll
-    for (int i = 0; i < kBaseMax; i++) {
+    for (int i = 0; i < LMAX; i++) {
         if (i >= (int)A.lin) break;
         const u64 y = shoup_canon(x[(size_t)i * A.n], A.pre[i], A.bin[i].q);
         s = dadd_rn(s, dmul_rn((double)y, A.binv[i]));
@@ -116,16 +122,17 @@ NTT_KERNEL void __launch_bounds__(128) k_bconv(BconvArgs A)
     }
     const u64 v = (u64)(long long)floor(dadd_rn(s, 0.5));
     for (unsigned l = 0; l < A.lout; l++) {
-        const ModC m = A.bout[l];
+        ModC m; m.q = outc[5 * l]; m.ratio = outc[5 * l + 1];
+        ShoupC r64; r64.c = outc[5 * l + 3]; r64.cs = outc[5 * l + 4];
         const SplitC *row = mul_smem + (size_t)l * A.lin;
         Acc3 acc;
-        acc_init(acc, (u64)(A.lin + 1) * m.q - v * A.corr[l]);                                            // v <= lin, corr < o_j
+        acc_init(acc, (u64)(A.lin + 1) * m.q - v * outc[5 * l + 2]);                                      // v <= lin, corr < o_j
 #pragma unroll
-        for (int i = 0; i < kBaseMax; i++) {
+        for (int i = 0; i < LMAX; i++) {
             if (i >= (int)A.lin) break;
             acc_mac(acc, y0[i], y1[i], row[i]);
         }
-        o[(size_t)l * A.n] = acc_reduce(acc, A.h, m, A.r64[l]);
+        o[(size_t)l * A.n] = acc_reduce(acc, A.h, m, r64);
     }
 }
 
@@ -143,11 +150,17 @@ struct ScaleArgs {
     const ShoupC *r64;                       // [k]      2^64 mod p_j
     unsigned rp, k, n, h;
 };
+template <int LMAX>
 NTT_KERNEL void __launch_bounds__(128) k_scale(ScaleArgs A)
 {
     NTT_DYN_SMEM(mul_raw);
     SplitC *mul_smem = reinterpret_cast<SplitC *>(mul_raw);
+    u64 *outc = reinterpret_cast<u64 *>(mul_raw) + (size_t)A.rp * A.k;          // per output limb: q, ratio, lambda (split), r64.c, r64.cs
     for (unsigned i = threadIdx.x; i < A.rp * A.k; i += blockDim.x) mul_smem[i] = A.W[i];
+    for (unsigned i = threadIdx.x; i < A.k; i += blockDim.x) {
+        outc[5 * i] = A.modP[i].q; outc[5 * i + 1] = A.modP[i].ratio; outc[5 * i + 2] = (u64)A.lam[i].c0 | ((u64)A.lam[i].c1 << 32);
+        outc[5 * i + 3] = A.r64[i].c; outc[5 * i + 4] = A.r64[i].cs;
+    }
     __syncthreads();
     const size_t kc = blockIdx.y;             // item * comps + comp
     const size_t L = (size_t)A.rp + A.k;
@@ -155,11 +168,11 @@ NTT_KERNEL void __launch_bounds__(128) k_scale(ScaleArgs A)
     if (j >= A.n) return;
     const u64 *d = A.d + kc * L * A.n + j;
     u64 *y = A.y + kc * (size_t)A.k * A.n + j;
-    u32 y0[kBaseMax], y1[kBaseMax];
+    u32 y0[LMAX], y1[LMAX];
     const u64 mask = (1ull << A.h) - 1;
     double f = 0.0;
 #pragma unroll
-    for (int i = 0; i < kBaseMax; i++) {
+    for (int i = 0; i < LMAX; i++) {
         if (i >= (int)A.rp) break;
         const u64 yt = shoup_canon(d[(size_t)i * A.n], A.preQ[i], A.modQ[i].q);
         f = dadd_rn(f, dmul_rn((double)yt, A.theta[i]));
@@ -167,18 +180,20 @@ NTT_KERNEL void __launch_bounds__(128) k_scale(ScaleArgs A)
     }
     const u64 v = (u64)(long long)floor(dadd_rn(f, 0.5));
     for (unsigned l = 0; l < A.k; l++) {
-        const ModC m = A.modP[l];
+        ModC m; m.q = outc[5 * l]; m.ratio = outc[5 * l + 1];
+        ShoupC r64; r64.c = outc[5 * l + 3]; r64.cs = outc[5 * l + 4];
+        SplitC lam; lam.c0 = (u32)outc[5 * l + 2]; lam.c1 = (u32)(outc[5 * l + 2] >> 32);
         const SplitC *row = mul_smem + (size_t)l * A.rp;
         const u64 dp = d[((size_t)A.rp + l) * A.n];
         Acc3 acc;
         acc_init(acc, v);                                                                                 // v <= rp
-        acc_mac(acc, (u32)(dp & mask), (u32)(dp >> A.h), A.lam[l]);
+        acc_mac(acc, (u32)(dp & mask), (u32)(dp >> A.h), lam);
 #pragma unroll
-        for (int i = 0; i < kBaseMax; i++) {
+        for (int i = 0; i < LMAX; i++) {
             if (i >= (int)A.rp) break;
             acc_mac(acc, y0[i], y1[i], row[i]);
         }
-        y[(size_t)l * A.n] = acc_reduce(acc, A.h, m, A.r64[l]);
+        y[(size_t)l * A.n] = acc_reduce(acc, A.h, m, r64);
     }
 }
 
