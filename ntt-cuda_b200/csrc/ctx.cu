@@ -82,6 +82,19 @@ static int ctx_finish(nttb200_ctx *c, const u64 *roots, const u64 *psi_h, const 
         k_build_companions<<<1184, 256>>>(c->psiinv, c->psiinv_s, c->q_dev, c->logn, c->limbs, c->limbs);
         NTTB200_CHECK(cudaDeviceSynchronize());
     }
+#ifdef NTT_TWZ   /* experiment: the companion tables become interleaved {w, companion} tables (only the plain transform entries are valid in this build) */
+    for (int which = 0; which < 2; which++) {
+        u64 **sp = which ? &c->psiinv_s : &c->psi_s;
+        const u64 *wsrc = which ? c->psiinv : c->psi;
+        std::vector<u64> hw(tot), hs(tot), hz(2 * tot);
+        NTTB200_CHECK(cudaMemcpy(hw.data(), wsrc, tot * 8, cudaMemcpyDeviceToHost));
+        NTTB200_CHECK(cudaMemcpy(hs.data(), *sp, tot * 8, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < tot; i++) { hz[2 * i] = hw[i]; hz[2 * i + 1] = hs[i]; }
+        NTTB200_CHECK(cudaFree(*sp));
+        NTTB200_CHECK(cudaMalloc(sp, 2 * tot * 8));
+        NTTB200_CHECK(cudaMemcpy(*sp, hz.data(), 2 * tot * 8, cudaMemcpyHostToDevice));
+    }
+#endif
     return 0;
 }
 

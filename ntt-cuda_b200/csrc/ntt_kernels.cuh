@@ -145,8 +145,29 @@ struct ShoupPolicy {
     {
         l = A.lc + limb;
         q = l->q; twoq = l->twoq; nq = l->negq;
-        w = A.tw + (size_t)limb * n; ws = A.tws + (size_t)limb * n;
+        w = A.tw + (size_t)limb * n;
+#ifdef NTT_TWZ   /* experiment (profiles/r02_experiments.md): A.tws is an INTERLEAVED table {w, floor(w 2^64 / q)}, 2n words per limb */
+        ws = A.tws + (size_t)limb * 2 * n;
+#else
+        ws = A.tws + (size_t)limb * n;
+#endif
     }
+#ifdef NTT_TWZ
+    __device__ __forceinline__ Tw load(u32 i) const
+    {
+        const ulonglong2 e = __ldg(reinterpret_cast<const ulonglong2 *>(ws) + i);
+        Tw t; t.w = e.x; t.ws = e.y; return t;
+    }
+    __device__ __forceinline__ void load2(u32 i, Tw &t0, Tw &t1) const
+    {
+#ifdef NTT_TWZ256
+        asm("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(t0.w), "=l"(t0.ws), "=l"(t1.w), "=l"(t1.ws) : "l"(ws + 2 * (size_t)i));
+#else
+        t0 = load(i); t1 = load(i + 1);
+#endif
+    }
+    __device__ __forceinline__ void prefetch(u32 i) const { prefetch_l1(ws + 2 * (size_t)i); }
+#else
 #ifdef NTT_DBG_REGTW   /* profiling only (wrong results): twiddles from registers, no table loads */
     __device__ __forceinline__ Tw load(u32 i) const { Tw t; t.w = q - 12345u; t.ws = nq; (void)i; return t; }
     __device__ __forceinline__ void load2(u32 i, Tw &t0, Tw &t1) const { t0 = load(i); t1.w = twoq - q - 777u; t1.ws = nq + 99u; }
@@ -162,6 +183,7 @@ struct ShoupPolicy {
     }
     // pull the line holding table entry i into L1 (no destination register: can be issued long before the use)
     __device__ __forceinline__ void prefetch(u32 i) const { prefetch_l1(w + i); prefetch_l1(ws + i); }
+#endif
     // forward (Cooley-Tukey), X,Y in [0,4q) -> [0,4q)
     __device__ __forceinline__ void ct(u64 &X, u64 &Y, const Tw &t) const
     {

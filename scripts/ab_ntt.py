@@ -17,6 +17,9 @@ P = 1024
 qv = torch.tensor(qs, dtype=torch.int64, device="cuda").repeat(P // 16).view(P, 1)
 a = torch.randint(0, 2**62, (P, n), dtype=torch.int64, device="cuda") %% qv
 out = {}
+b = a.clone()
+ctx.forward_ntt_batch(b, P, 16); ctx.inverse_ntt_batch(b, P, 16)
+out["roundtrip_ok"] = bool(torch.equal(a, b))
 for name, fn in (("fwd_strided", lambda: ctx.ntt_pass(a, P, 16, False, 0)), ("fwd_contig", lambda: ctx.ntt_pass(a, P, 16, False, 1)),
                  ("inv_contig", lambda: ctx.ntt_pass(a, P, 16, True, 0)), ("inv_strided", lambda: ctx.ntt_pass(a, P, 16, True, 1))):
     for _ in range(10): fn()
