@@ -266,16 +266,57 @@ static dim3 pair_grid3(unsigned n, unsigned y, unsigned z)
     return dim3(x, y, z);
 }
 
-static int run_tensor(nttb200_bfv *b, nttb200_mul_state *s, u64 *y, const u64 *ca, const u64 *cb, unsigned batch, cudaStream_t st)
+// work areas of one (part of a) batch, carved from the state's grow-only buffers
+struct MulWork { u64 *WA, *D, *YP, *Y, *Dd; };
+static int mul_reserve(nttb200_bfv *b, nttb200_mul_state *s, unsigned batch, bool square, bool want_y, bool want_relin)
+{
+    const unsigned n = b->n, rp = s->rp, k = s->k, L = rp + k;
+    u64 *p;
+    NTTB200_TRY(mul_buf(s, kWA, (size_t)batch * 2 * L * n * (square ? 1 : 2), &p));
+    NTTB200_TRY(mul_buf(s, kD, (size_t)batch * 3 * L * n, &p));
+    NTTB200_TRY(mul_buf(s, kYP, (size_t)batch * 3 * k * n, &p));
+    if (want_y) NTTB200_TRY(mul_buf(s, kY, (size_t)batch * 3 * rp * n, &p));
+    if (want_relin) NTTB200_TRY(mul_buf(s, kDd, (size_t)batch * ((size_t)rp * rp + 2 * rp) * n, &p));
+    return 0;
+}
+static MulWork mul_carve(nttb200_bfv *b, nttb200_mul_state *s, unsigned first, bool square)
+{
+    const size_t n = b->n, rp = s->rp, k = s->k, L = rp + k;
+    MulWork w;
+    w.WA = s->buf[kWA] ? s->buf[kWA] + (size_t)first * 2 * L * n * (square ? 1 : 2) : nullptr;
+    w.D = s->buf[kD] ? s->buf[kD] + (size_t)first * 3 * L * n : nullptr;
+    w.YP = s->buf[kYP] ? s->buf[kYP] + (size_t)first * 3 * k * n : nullptr;
+    w.Y = s->buf[kY] ? s->buf[kY] + (size_t)first * 3 * rp * n : nullptr;
+    w.Dd = s->buf[kDd] ? s->buf[kDd] + (size_t)first * (rp * rp + 2 * rp) * n : nullptr;
+    return w;
+}
+// Two halves of a batch on two streams (as run_split in bfv.cu): the memory-bound kernels of one half (tensor product, digit lift,
+// key accumulation) run under the issue-bound transforms and base conversions of the other.
+template <class F>
+static int mul_split(nttb200_bfv *b, unsigned batch, cudaStream_t st, F part)
+{
+    if (!b->split || batch < 2) return part(st, 0u, batch);
+    if (!b->st2) {
+        NTTB200_CHECK(cudaStreamCreateWithFlags(&b->st2, cudaStreamNonBlocking));
+        NTTB200_CHECK(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
+        NTTB200_CHECK(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming));
+    }
+    const unsigned h = batch / 2;
+    NTTB200_CHECK(cudaEventRecord(b->ev_fork, st));
+    NTTB200_CHECK(cudaStreamWaitEvent(b->st2, b->ev_fork, 0));
+    NTTB200_TRY(part(st, 0u, h));
+    NTTB200_TRY(part(b->st2, h, batch - h));
+    NTTB200_CHECK(cudaEventRecord(b->ev_join, b->st2));
+    NTTB200_CHECK(cudaStreamWaitEvent(st, b->ev_join, 0));
+    return 0;
+}
+
+static int run_tensor(nttb200_bfv *b, nttb200_mul_state *s, const MulWork &w, u64 *y, const u64 *ca, const u64 *cb, unsigned batch, cudaStream_t st)
 {
     const unsigned n = b->n, r = b->r, rp = s->rp, k = s->k, L = rp + k;
     const size_t Ln = (size_t)L * n;
-    u64 *WA, *WB, *D, *YP;
     const bool square = ca == cb;
-    NTTB200_TRY(mul_buf(s, kWA, (size_t)batch * 2 * Ln * (square ? 1 : 2), &WA));      // both operands in one array: one transform call
-    WB = WA + (size_t)batch * 2 * Ln;
-    NTTB200_TRY(mul_buf(s, kD, (size_t)batch * 3 * Ln, &D));
-    NTTB200_TRY(mul_buf(s, kYP, (size_t)batch * 3 * k * n, &YP));
+    u64 *WA = w.WA, *WB = WA + (size_t)batch * 2 * Ln, *D = w.D, *YP = w.YP;
     for (int op = 0; op < (square ? 1 : 2); op++) {
         u64 *Wx = op == 0 ? WA : WB;
         k_gather_q<<<pair_grid3(n, rp, 2 * batch), 256, 0, st>>>(op == 0 ? ca : cb, Wx, n, r, L);
@@ -298,13 +339,11 @@ static int run_tensor(nttb200_bfv *b, nttb200_mul_state *s, u64 *y, const u64 *c
     return 0;
 }
 
-static int run_relin(nttb200_bfv *b, nttb200_mul_state *s, u64 *c_out, const u64 *y, unsigned batch, cudaStream_t st)
+static int run_relin(nttb200_bfv *b, nttb200_mul_state *s, const MulWork &w, u64 *c_out, const u64 *y, unsigned batch, cudaStream_t st)
 {
     if (!s->evk) return NTTB200_EINVAL;
     const unsigned n = b->n, r = b->r, rp = s->rp;
-    u64 *Dd, *acc;
-    NTTB200_TRY(mul_buf(s, kDd, (size_t)batch * rp * rp * n + (size_t)batch * 2 * rp * n, &Dd));
-    acc = Dd + (size_t)batch * rp * rp * n;
+    u64 *Dd = w.Dd, *acc = Dd + (size_t)batch * rp * rp * n;
     k_relin_lift<<<pair_grid3(n, rp * rp, batch), 256, 0, st>>>(y + (size_t)2 * rp * n, (size_t)3 * rp * n, Dd, n, rp, s->modQ);
     KCHECK();
     NTTB200_TRY(ntt_call(b->ctx, false, Dd, batch * rp * rp, rp, 0, 0, st));
@@ -367,12 +406,24 @@ int nttb200_bfv_mul_tensor(nttb200_bfv *b, nttb200_u64 *y, const nttb200_u64 *c_
     if (!b || !y || !c_a || !c_b || !batch || batch > 10000) return NTTB200_EINVAL;
     nttb200_mul_state *s;
     NTTB200_TRY(mul_state(b, &s));
-    return run_tensor(b, s, y, c_a, c_b, batch, (cudaStream_t)stream);
+    const bool square = c_a == c_b;
+    NTTB200_TRY(mul_reserve(b, s, batch, square, false, false));
+    const size_t rn = (size_t)b->r * b->n, yn = (size_t)3 * s->rp * b->n;
+    return mul_split(b, batch, (cudaStream_t)stream, [&](cudaStream_t st, unsigned first, unsigned cnt) {
+        return run_tensor(b, s, mul_carve(b, s, first, square), y + first * yn, c_a + first * 2 * rn, square ? c_a + first * 2 * rn : c_b + first * 2 * rn, cnt, st);
+    });
 }
 int nttb200_bfv_relinearize(nttb200_bfv *b, nttb200_u64 *c_out, const nttb200_u64 *y, unsigned batch, void *stream)
 {
     if (!b || !y || !c_out || !batch || batch > 10000 || !b->mul) return NTTB200_EINVAL;
-    return run_relin(b, b->mul, c_out, y, batch, (cudaStream_t)stream);
+    nttb200_mul_state *s = b->mul;
+    if (!s->evk) return NTTB200_EINVAL;
+    u64 *p;
+    NTTB200_TRY(mul_buf(s, kDd, (size_t)batch * ((size_t)s->rp * s->rp + 2 * s->rp) * b->n, &p));
+    const size_t rn = (size_t)b->r * b->n, yn = (size_t)3 * s->rp * b->n;
+    return mul_split(b, batch, (cudaStream_t)stream, [&](cudaStream_t st, unsigned first, unsigned cnt) {
+        return run_relin(b, s, mul_carve(b, s, first, false), c_out + first * 2 * rn, y + first * yn, cnt, st);
+    });
 }
 // c_out <- relin(c_a * c_b): Dec(c_out) = m_a * m_b mod (X^n + 1, t).  c_out may alias an input.  Needs nttb200_bfv_relin_keygen.
 int nttb200_bfv_mul(nttb200_bfv *b, nttb200_u64 *c_out, const nttb200_u64 *c_a, const nttb200_u64 *c_b, unsigned batch, void *stream)
@@ -381,10 +432,15 @@ int nttb200_bfv_mul(nttb200_bfv *b, nttb200_u64 *c_out, const nttb200_u64 *c_a, 
     nttb200_mul_state *s;
     NTTB200_TRY(mul_state(b, &s));
     if (!s->evk) return NTTB200_EINVAL;
-    u64 *y;
-    NTTB200_TRY(mul_buf(s, kY, (size_t)batch * 3 * s->rp * b->n, &y));
-    NTTB200_TRY(run_tensor(b, s, y, c_a, c_b, batch, (cudaStream_t)stream));
-    return run_relin(b, s, c_out, y, batch, (cudaStream_t)stream);
+    const bool square = c_a == c_b;
+    NTTB200_TRY(mul_reserve(b, s, batch, square, true, true));
+    const size_t rn = (size_t)b->r * b->n;
+    return mul_split(b, batch, (cudaStream_t)stream, [&](cudaStream_t st, unsigned first, unsigned cnt) {
+        const MulWork w = mul_carve(b, s, first, square);
+        const u64 *a = c_a + first * 2 * rn, *bb = square ? a : c_b + first * 2 * rn;
+        NTTB200_TRY(run_tensor(b, s, w, w.Y, a, bb, cnt, st));
+        return run_relin(b, s, w, c_out + first * 2 * rn, w.Y, cnt, st);
+    });
 }
 // the auxiliary base of the multiplication (for tests / oracles): k = r primes
 int nttb200_bfv_mul_aux_base(nttb200_bfv *b, nttb200_u64 *p_out, unsigned *count)
