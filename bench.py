@@ -15,6 +15,7 @@ Extra blocks on the same JSON line (BASELINE.json's other configs; none of them 
   ntt_limb_sharded     config 5: N = 2^16 / 2^17, 16 limbs, each rank owns its limbs' tables only, strong scaling
   keygen_c3            config 3: 8192 x 3 limbs, 256 keys per call
   bfv_mul              ciphertext x ciphertext multiply + relinearise, batch 8 per GPU
+  bfv_single_item      one item per call (the reference's calling pattern), microseconds, beside reference_gpu_rebuilt
   latency_c1           config 1: one N = 4096 transform (58-bit prime), ours vs the rebuilt reference
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
@@ -445,6 +446,51 @@ def bfv_mul(nttb200, params, torch, T, world, batch=8):
             "products_per_s": world * batch / (ms * 1e-3), "ms_per_call": ms, "decrypts_to_product": bool(ok)}
 
 
+def bfv_single_item(nttb200, params, torch):
+    """The reference's own calling pattern -- ONE item per keygen_rns / encryption_rns / decryption_rns call (demo.cu:275-299) -- through
+    the batched entry points with batch = 1, microseconds per call (back-to-back calls, CUDA events); the rebuilt reference's numbers for
+    the same loops are in `reference_gpu_rebuilt` (keygen_us / encrypt_us / decrypt_us and c3_8k_3q)."""
+    out = {}
+    for name in ("32k_16q", "8k_3q"):
+        n, qs, roots = params.RNS_SETS[name]
+        rn = len(qs) * n
+        bfv = nttb200.Bfv(n, qs, roots)
+        sk = torch.zeros(rn, dtype=torch.int64, device="cuda")
+        pk = torch.zeros(2 * rn, dtype=torch.int64, device="cuda")
+        c = torch.zeros(2 * rn, dtype=torch.int64, device="cuda")
+        keep = torch.zeros_like(c)
+        m = torch.randint(0, params.T, (n,), dtype=torch.int64, device="cuda")
+        res = torch.zeros(n, dtype=torch.int64, device="cuda")
+
+        def timed(fn, iters=100):
+            for _ in range(5):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return 1e3 * e0.elapsed_time(e1) / iters
+
+        kg = timed(lambda: bfv.keygen(sk, pk))
+        enc = timed(lambda: bfv.encrypt(c, pk, m))
+        keep.copy_(c)
+        dec = timed(lambda: bfv.decrypt(res, c, sk))          # decryption consumes c: later iterations decrypt garbage, same work
+        c.copy_(keep)
+        bfv.decrypt(res, c, sk)
+        ok = bool(torch.equal(res, m))
+        bfv.load_keys(sk, pk)
+        enc_l = timed(lambda: bfv.encrypt(c, None, m))
+        dec_l = timed(lambda: bfv.decrypt(res, c, None))
+        out[name] = {"keygen_us": kg, "encrypt_us": enc, "decrypt_us": dec, "encrypt_loaded_key_us": enc_l, "decrypt_loaded_key_us": dec_l,
+                     "roundtrip_ok": ok}
+        bfv.close()
+    out["note"] = "batch = 1 through nttb200_bfv_keygen / _encrypt / _decrypt, Python/ctypes host (one C call per operation)"
+    return out
+
+
 def latency_c1(nttb200, params, torch):
     """BASELINE config 1: ONE polynomial, N = 4096, 58-bit prime: microseconds per call (back-to-back launches, CUDA events)."""
     n = 4096
@@ -698,6 +744,7 @@ def run_ours(args):
         extras["bfv_mul"] = bfv_mul(nttb200, params, torch, T, world)
         if rank == 0 and world == 1:
             extras["latency_c1"] = latency_c1(nttb200, params, torch)
+            extras["bfv_single_item"] = bfv_single_item(nttb200, params, torch)
 
     if rank == 0:
         peak, peak_src = peaks()
