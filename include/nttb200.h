@@ -269,7 +269,9 @@ NTTB200_API int nttb200_bfv_mul_plain(nttb200_bfv *bfv, nttb200_u64 *c, const nt
  *   nttb200_bfv_mul_tensor     y[batch][3][r-1][n]: the degree-2 ciphertext, Dec = y0 + y1 s + y2 s^2
  *   nttb200_bfv_relinearize    y -> c_out[batch][2][r][n]
  *   nttb200_bfv_mul            both; c_out may alias an input
- * Work buffers are grow-only (the first call at a batch size allocates).  batch <= 10000. */
+ * Work buffers are grow-only (the first call at a batch size allocates).  batch <= 10000.  A batch of two or more runs as two halves
+ * on the caller's stream and an internal one (joined before the call returns control of the stream; NTTB200_BFV_SPLIT=0: one stream).
+ * Moduli of at most 58 bits (EINVAL otherwise: the lazy sums of the base conversions must not carry). */
 NTTB200_API int nttb200_bfv_relin_keygen(nttb200_bfv *bfv, const nttb200_u64 *sk, nttb200_u64 nonce0, void *stream);
 NTTB200_API int nttb200_bfv_relin_key(nttb200_bfv *bfv, const nttb200_u64 **evk_dev, size_t *words);   /* evk[r-1][2][r-1][n], NTT domain */
 NTTB200_API int nttb200_bfv_mul_tensor(nttb200_bfv *bfv, nttb200_u64 *y, const nttb200_u64 *c_a, const nttb200_u64 *c_b, unsigned batch, void *stream);
