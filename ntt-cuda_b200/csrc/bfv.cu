@@ -13,6 +13,7 @@
 #include "epi.cuh"
 #include "table_kernels.cuh"
 #include "bfv_internal.h"
+#include "launch_util.h"
 
 #include <algorithm>
 #include <cmath>
@@ -110,14 +111,14 @@ static int run_keygen(const Pipe &P, unsigned char *in, size_t in_stride, int *e
     const unsigned n = P.n, r = P.r;
     const size_t rn = (size_t)r * n;
     const u64 nblk = (9 * rn + 4 * (size_t)n) / 64;                                   // bfv_keygen.cuh:99
-    k_salsa20_keystream<<<grid_for(nblk * batch, 256), 256, 0, P.st>>>(in, nblk, (u64)batch, in_stride, P.key, nonce0);
+    NTT_LAUNCH_PDL(k_salsa20_keystream, dim3(grid_for(nblk * batch, 256)), dim3(256), 0, P.st, in, nblk, (u64)batch, in_stride, P.key, nonce0, (u64)0);
     if (P.policy_fwd != kPolicyBarrett) {      // context path: the ternary secret is generated inside the first strided pass
-        k_keygen_sample<<<pair_grid(n, batch, 1), pair_block(n, batch, 1), 0, P.st>>>(in, in_stride, nullptr, pk, es, n, r, batch, P.L.q);   // :121-122
+        NTT_LAUNCH_PDL(k_keygen_sample, dim3(pair_grid(n, batch, 1)), dim3(pair_block(n, batch, 1)), 0, P.st, in, in_stride, nullptr, pk, es, n, r, batch, P.L.q);   // :121-122
         KCHECK();
         NTTB200_TRY(pipe_ntt_gen_pass(P, sk, batch * r, r, r, rn, in, in_stride));         // :120 + :129, first kernel
         NTTB200_TRY(pipe_ntt_pass(P, false, 1, sk, batch * r, r, r, rn));
     } else {
-        k_keygen_sample<<<pair_grid(n, batch, 1), pair_block(n, batch, 1), 0, P.st>>>(in, in_stride, sk, pk, es, n, r, batch, P.L.q);   // :120-122
+        NTT_LAUNCH_PDL(k_keygen_sample, dim3(pair_grid(n, batch, 1)), dim3(pair_block(n, batch, 1)), 0, P.st, in, in_stride, sk, pk, es, n, r, batch, P.L.q);   // :120-122
         KCHECK();
         NTTB200_TRY(pipe_ntt(P, false, sk, batch * r, r, 0, 0));                           // :129
     }
@@ -127,11 +128,11 @@ static int run_keygen(const Pipe &P, unsigned char *in, size_t in_stride, int *e
                                    P.psiinv_s, sk, 0, 0, false, pk, P.st));                // :132
         NTTB200_TRY(pipe_ntt_pass(P, true, 1, pk, batch * r, r, r, 2 * rn));               // :133 (second kernel)
     } else {
-        k_keygen_mul<<<pair_grid(n, r, batch), pair_block(n, r, batch), 0, P.st>>>(pk, sk, n, r, batch, P.L);                  // :132
+        NTT_LAUNCH_PDL(k_keygen_mul, dim3(pair_grid(n, r, batch)), dim3(pair_block(n, r, batch)), 0, P.st, pk, sk, n, r, batch, P.L);                  // :132
         KCHECK();
         NTTB200_TRY(pipe_ntt(P, true, pk, batch * r, r, r, 2 * rn));                       // :133
     }
-    k_keygen_add_negate<<<pair_grid(n, r, batch), pair_block(n, r, batch), 0, P.st>>>(pk, es, n, r, batch, P.L);               // :144
+    NTT_LAUNCH_PDL(k_keygen_add_negate, dim3(pair_grid(n, r, batch)), dim3(pair_block(n, r, batch)), 0, P.st, pk, es, n, r, batch, P.L);               // :144
     KCHECK();
     NTTB200_TRY(pipe_ntt(P, false, pk, batch * r, r, r, 2 * rn));                          // :145
     return 0;
@@ -145,10 +146,10 @@ static int run_encrypt_epilogue(const Pipe &P, u64 *c, const int *es, const u64 
         const unsigned rows = 2 * ((r - 1 + kEncChunk - 1) / kEncChunk);
         const size_t rn = (size_t)r * n;
         const u64 *cl = c + (size_t)(r - 1) * n;      // the padding slot still holds the RAW inverse-transform output here
-        if (P.enc_lazy) k_encrypt_epilogue<true, int, false><<<pair_grid(n, rows, batch), pair_block(n, rows, batch), 0, P.st>>>(c, 2 * rn, rn, es, m, m_stride, n, r, 0, r - 1, cl, 2 * rn, rn, t, P.qi_div_t, P.L);
-        else k_encrypt_epilogue<false, int, false><<<pair_grid(n, rows, batch), pair_block(n, rows, batch), 0, P.st>>>(c, 2 * rn, rn, es, m, m_stride, n, r, 0, r - 1, cl, 2 * rn, rn, t, P.qi_div_t, P.L);
+        if (P.enc_lazy) NTT_LAUNCH_PDL(k_encrypt_epilogue<true, int, false>, dim3(pair_grid(n, rows, batch)), dim3(pair_block(n, rows, batch)), 0, P.st, c, 2 * rn, rn, es, m, m_stride, n, r, 0, r - 1, cl, 2 * rn, rn, t, P.qi_div_t, P.L);
+        else NTT_LAUNCH_PDL(k_encrypt_epilogue<false, int, false>, dim3(pair_grid(n, rows, batch)), dim3(pair_block(n, rows, batch)), 0, P.st, c, 2 * rn, rn, es, m, m_stride, n, r, 0, r - 1, cl, 2 * rn, rn, t, P.qi_div_t, P.L);
     }
-    k_encrypt_last_limb<<<pair_grid(n, 2, batch), pair_block(n, 2, batch), 0, P.st>>>(c, es, n, r, batch, P.L);
+    NTT_LAUNCH_PDL(k_encrypt_last_limb, dim3(pair_grid(n, 2, batch)), dim3(pair_block(n, 2, batch)), 0, P.st, c, es, n, r, batch, P.L);
     KCHECK();
     return 0;
 }
@@ -159,18 +160,18 @@ static int run_encrypt(const Pipe &P, unsigned char *in, size_t in_stride, int *
     const unsigned n = P.n, r = P.r;
     const size_t rn = (size_t)r * n;
     const u64 nblk = (9 * (size_t)n) / 64;                                                // bfv_encryption.cuh:228
-    k_salsa20_keystream<<<grid_for(nblk * batch, 256), 256, 0, P.st>>>(in, nblk, (u64)batch, in_stride, P.key, nonce0);
+    NTT_LAUNCH_PDL(k_salsa20_keystream, dim3(grid_for(nblk * batch, 256)), dim3(256), 0, P.st, in, nblk, (u64)batch, in_stride, P.key, nonce0, (u64)0);
     if (P.policy_fwd != kPolicyBarrett) {
-        k_encrypt_gauss<<<pair_grid(n, batch, 1), pair_block(n, batch, 1), 0, P.st>>>(in, in_stride, es, n, batch, (size_t)n);               // :247 (e0, e1)
+        NTT_LAUNCH_PDL(k_encrypt_gauss, dim3(pair_grid(n, batch, 1)), dim3(pair_block(n, batch, 1)), 0, P.st, in, in_stride, es, n, batch, (size_t)n);               // :247 (e0, e1)
         KCHECK();
         NTTB200_TRY(pipe_ntt_gen_pass(P, c, batch * r, r, r, 2 * rn, in, in_stride));      // :247 (u) + :268 (once, not twice), first kernel
         NTTB200_TRY(pipe_ntt_pass(P, false, 1, c, batch * r, r, r, 2 * rn));
     } else {
-        k_encrypt_sample<<<pair_grid(n, batch, 1), pair_block(n, batch, 1), 0, P.st>>>(in, in_stride, c, es, n, r, batch, P.L.q);   // :247
+        NTT_LAUNCH_PDL(k_encrypt_sample, dim3(pair_grid(n, batch, 1)), dim3(pair_block(n, batch, 1)), 0, P.st, in, in_stride, c, es, n, r, batch, P.L.q);   // :247
         KCHECK();
         NTTB200_TRY(pipe_ntt(P, false, c, batch * r, r, r, 2 * rn));                       // :268 (once, not twice)
     }
-    k_encrypt_mul<<<pair_grid(n, r, batch), pair_block(n, r, batch), 0, P.st>>>(c, pk, pk_stride, n, r, batch, P.L);              // :270
+    NTT_LAUNCH_PDL(k_encrypt_mul, dim3(pair_grid(n, r, batch)), dim3(pair_block(n, r, batch)), 0, P.st, c, pk, pk_stride, n, r, batch, P.L);              // :270
     KCHECK();
     NTTB200_TRY(pipe_ntt(P, true, c, batch * 2 * r, r, 0, 0));                             // :271
     NTTB200_TRY(run_encrypt_epilogue(P, c, es, m, m_stride, t, batch));                    // :280-289
@@ -186,8 +187,8 @@ static int run_encrypt_fused(const Pipe &P, bool lazy, unsigned char *in, size_t
     const unsigned n = P.n, r = P.r;
     const size_t rn = (size_t)r * n;
     const u64 nblk = (9 * (size_t)n) / 64;
-    k_salsa20_keystream<<<grid_for(nblk * batch, 256), 256, 0, P.st>>>(in, nblk, (u64)batch, in_stride, P.key, nonce0);
-    k_encrypt_gauss<<<pair_grid(n, batch, 1), pair_block(n, batch, 1), 0, P.st>>>(in, in_stride, es, n, batch, (size_t)n);
+    NTT_LAUNCH_PDL(k_salsa20_keystream, dim3(grid_for(nblk * batch, 256)), dim3(256), 0, P.st, in, nblk, (u64)batch, in_stride, P.key, nonce0, (u64)0);
+    NTT_LAUNCH_PDL(k_encrypt_gauss, dim3(pair_grid(n, batch, 1)), dim3(pair_block(n, batch, 1)), 0, P.st, in, in_stride, es, n, batch, (size_t)n);
     KCHECK();
     NTTB200_TRY(pipe_ntt_gen_pass(P, c, batch * r, r, r, 2 * rn, in, in_stride));          // strided forward pass, u generated in the kernel
     NTTB200_TRY(launch_fused_mul(lazy, P.logn, pipe_args(P, false, c, batch * 2 * r, r, 2 * r, 2 * rn), P.psiinv, P.psiinv_s, pk, pk_s, 0, rn, r,
@@ -206,7 +207,7 @@ static int run_encrypt_v2(nttb200_bfv *b, const Pipe &P, u64 *c, const u64 *m, u
     const size_t rn = (size_t)r * n;
     NTTB200_TRY(ensure_enc_scratch(b, (size_t)batch * n, (size_t)batch * 2 * n));
     const u64 per = 9 * (u64)n / 64;
-    k_encrypt_sample_fused<<<grid_for(per * batch, 128), 128, 0, P.st>>>(b->ub, b->es8, n, (u64)batch, P.key, nonce0, 1, 1);
+    NTT_LAUNCH_PDL(k_encrypt_sample_fused, dim3(grid_for(per * batch, 128)), dim3(128), 0, P.st, b->ub, b->es8, n, (u64)batch, P.key, nonce0, 1, 1);
     KCHECK();
     NTTB200_TRY(enc_front(b, P, c, r, 0, r, batch, b->ub));
     u64 *cl = c + (size_t)(r - 1) * n;
@@ -224,8 +225,8 @@ static int run_decrypt_fused(const Pipe &P, bool lazy, u64 *c, const u64 *sk, co
     NTTB200_TRY(launch_fused_mul(lazy, P.logn, pipe_args(P, false, c, batch * 2 * (rp + 1), rp, 2 * (rp + 1), item), P.psiinv, P.psiinv_s, sk, sk_s,
                                  0, 0, rp, rp + 1, rp + 1, rp + 1, batch, 1, P.st));
     NTTB200_TRY(pipe_ntt_pass(P, true, 1, c + c1_off, batch * rp, rp, rp, item));
-    if (P.dec_fast) k_decrypt_epilogue<true><<<pair_grid(n, batch, 1), pair_block(n, batch, 1), 0, P.st>>>(c, item, c1_off, out, out_stride, n, batch, D, P.L);
-    else k_decrypt_epilogue<false><<<pair_grid(n, batch, 1), pair_block(n, batch, 1), 0, P.st>>>(c, item, c1_off, out, out_stride, n, batch, D, P.L);   // :103-137
+    if (P.dec_fast) NTT_LAUNCH_PDL(k_decrypt_epilogue<true>, dim3(pair_grid(n, batch, 1)), dim3(pair_block(n, batch, 1)), 0, P.st, c, item, c1_off, out, out_stride, n, batch, D, P.L);
+    else NTT_LAUNCH_PDL(k_decrypt_epilogue<false>, dim3(pair_grid(n, batch, 1)), dim3(pair_block(n, batch, 1)), 0, P.st, c, item, c1_off, out, out_stride, n, batch, D, P.L);   // :103-137
     KCHECK();
     return 0;
 }
@@ -236,11 +237,11 @@ static int run_decrypt(const Pipe &P, u64 *c, const u64 *sk, size_t sk_stride, u
     const unsigned n = P.n, rp = D.rp;
     const size_t item = (size_t)2 * (rp + 1) * n, c1_off = (size_t)(rp + 1) * n;
     NTTB200_TRY(pipe_ntt(P, false, c + c1_off, batch * rp, rp, rp, item));                 // bfv_decryption.cuh:98
-    k_decrypt_mul<<<pair_grid(n, rp, batch), pair_block(n, rp, batch), 0, P.st>>>(c, item, c1_off, sk, sk_stride, n, rp, batch, P.L);   // :100
+    NTT_LAUNCH_PDL(k_decrypt_mul, dim3(pair_grid(n, rp, batch)), dim3(pair_block(n, rp, batch)), 0, P.st, c, item, c1_off, sk, sk_stride, n, rp, batch, P.L);   // :100
     KCHECK();
     NTTB200_TRY(pipe_ntt(P, true, c + c1_off, batch * rp, rp, rp, item));                  // :101
-    if (P.dec_fast) k_decrypt_epilogue<true><<<pair_grid(n, batch, 1), pair_block(n, batch, 1), 0, P.st>>>(c, item, c1_off, out, out_stride, n, batch, D, P.L);
-    else k_decrypt_epilogue<false><<<pair_grid(n, batch, 1), pair_block(n, batch, 1), 0, P.st>>>(c, item, c1_off, out, out_stride, n, batch, D, P.L);   // :103-137
+    if (P.dec_fast) NTT_LAUNCH_PDL(k_decrypt_epilogue<true>, dim3(pair_grid(n, batch, 1)), dim3(pair_block(n, batch, 1)), 0, P.st, c, item, c1_off, out, out_stride, n, batch, D, P.L);
+    else NTT_LAUNCH_PDL(k_decrypt_epilogue<false>, dim3(pair_grid(n, batch, 1)), dim3(pair_block(n, batch, 1)), 0, P.st, c, item, c1_off, out, out_stride, n, batch, D, P.L);   // :103-137
     KCHECK();
     return 0;
 }

@@ -55,6 +55,7 @@ __host__ __device__ __forceinline__ void salsa20_block(u32 (&o)[16], const Salsa
 NTT_KERNEL void k_salsa20_keystream(unsigned char *out, u64 blocks_per_stream, u64 streams, size_t stream_stride, SalsaKey key, u64 nonce0,
                                     u64 blk0 = 0)
 {
+    NTT_PDL_ENTER();
     NTT_GRID_STRIDE(i, blocks_per_stream * streams) {
         const u64 s = i / blocks_per_stream, b = i - s * blocks_per_stream;
         u32 o[16];
@@ -181,6 +182,7 @@ __device__ __forceinline__ void st2(u64 *p, u64 a, u64 b) { *reinterpret_cast<ul
 NTT_KERNEL void k_keygen_sample(const unsigned char *in, size_t in_stride, u64 *sk, u64 *pk, int *es, unsigned n, unsigned r,
                                 unsigned batch, const u64 *q)
 {
+    NTT_PDL_ENTER();
     (void)batch;
     const size_t rn = (size_t)r * n, k = blockIdx.y;
     const unsigned char *s = in + k * in_stride;
@@ -200,6 +202,7 @@ NTT_KERNEL void k_keygen_sample(const unsigned char *in, size_t in_stride, u64 *
 // pk0 = pk1 (.) sk   (barrett_batch_3param, bfv_keygen.cuh:132).  grid (x, r, batch)
 NTT_KERNEL void k_keygen_mul(u64 *pk, const u64 *sk, unsigned n, unsigned r, unsigned batch, LimbArrays L)
 {
+    NTT_PDL_ENTER();
     (void)batch;
     const unsigned l = blockIdx.y;
     const size_t rn = (size_t)r * n, k = blockIdx.z;
@@ -215,6 +218,7 @@ NTT_KERNEL void k_keygen_mul(u64 *pk, const u64 *sk, unsigned n, unsigned r, uns
 // pk0 = -(pk0 + e)   (gaussian_dist_xq + poly_add_negate_xq, bfv_keygen.cuh:47-93).  grid (x, r, batch)
 NTT_KERNEL void k_keygen_add_negate(u64 *pk, const int *es, unsigned n, unsigned r, unsigned batch, LimbArrays L)
 {
+    NTT_PDL_ENTER();
     (void)batch;
     const unsigned l = blockIdx.y;
     const size_t rn = (size_t)r * n, k = blockIdx.z;
@@ -236,6 +240,7 @@ NTT_KERNEL void k_keygen_add_negate(u64 *pk, const int *es, unsigned n, unsigned
 NTT_KERNEL void k_encrypt_sample(const unsigned char *in, size_t in_stride, u64 *c, int *es, unsigned n, unsigned r, unsigned batch,
                                  const u64 *q)
 {
+    NTT_PDL_ENTER();
     (void)batch;
     const size_t rn = (size_t)r * n, k = blockIdx.y;
     const unsigned char *s = in + k * in_stride;
@@ -256,6 +261,7 @@ NTT_KERNEL void k_encrypt_sample(const unsigned char *in, size_t in_stride, u64 
 // e_off: byte offset of the e0 words inside an item's stream (n for the full 9n-byte stream; 0 when only blocks [n/64, 9n/64) were drawn)
 NTT_KERNEL void k_encrypt_gauss(const unsigned char *in, size_t in_stride, int *es, unsigned n, unsigned batch, size_t e_off)
 {
+    NTT_PDL_ENTER();
     (void)batch;
     const size_t k = blockIdx.y;
     const unsigned char *s = in + k * in_stride;
@@ -274,6 +280,7 @@ NTT_KERNEL void k_encrypt_gauss(const unsigned char *in, size_t in_stride, int *
 // every item gets its u part when `ub` is given.
 NTT_KERNEL void k_encrypt_sample_fused(unsigned char *ub, signed char *es8, unsigned n, u64 items, SalsaKey key, u64 nonce0, int want_u, int want_e)
 {
+    NTT_PDL_ENTER();
     const u64 ublk = n / 64, eblk = 8 * (u64)n / 64;
     const u64 per = (want_u ? ublk : 0) + (want_e ? eblk : 0);
     NTT_GRID_STRIDE(i, per * items) {
@@ -303,6 +310,7 @@ NTT_KERNEL void k_encrypt_sample_fused(unsigned char *ub, signed char *es8, unsi
 // half 0 and is read once.  pk_stride = 0: one public key for the whole batch.  grid (x, r, batch)
 NTT_KERNEL void k_encrypt_mul(u64 *c, const u64 *pk, size_t pk_stride, unsigned n, unsigned r, unsigned batch, LimbArrays L)
 {
+    NTT_PDL_ENTER();
     (void)batch;
     const unsigned l = blockIdx.y;
     const size_t rn = (size_t)r * n, k = blockIdx.z;
@@ -345,6 +353,7 @@ k_encrypt_epilogue(u64 *c, size_t item_stride, size_t half_stride, const ES *es,
                    unsigned first, unsigned cnt, const u64 *clp, size_t cl_item_stride, size_t cl_half_stride, u64 t, const u64 *qi_div_t,
                    LimbArrays L)
 {
+    NTT_PDL_ENTER();
     NTT_SHARED EncLimb K[kEncChunk];
     const u64 last = L.q[r - 1], half_last = last >> 1;
     const unsigned chunks = (cnt + kEncChunk - 1) / kEncChunk;
@@ -439,6 +448,7 @@ k_encrypt_epilogue(u64 *c, size_t item_stride, size_t half_stride, const ES *es,
 // the dropped limb r-1 keeps the value the reference leaves there (padding of the ciphertext layout).  grid (x, 2, batch)
 NTT_KERNEL void k_encrypt_last_limb(u64 *c, const int *es, unsigned n, unsigned r, unsigned batch, LimbArrays L)
 {
+    NTT_PDL_ENTER();
     (void)batch;
     const u64 last = L.q[r - 1], half_last = last >> 1;
     const unsigned h = blockIdx.y;
@@ -455,6 +465,7 @@ NTT_KERNEL void k_encrypt_last_limb(u64 *c, const int *es, unsigned n, unsigned 
 NTT_KERNEL void k_decrypt_mul(u64 *c, size_t item_stride, size_t c1_off, const u64 *sk, size_t sk_stride, unsigned n, unsigned rp,
                               unsigned batch, LimbArrays L)
 {
+    NTT_PDL_ENTER();
     (void)batch; (void)rp;
     const unsigned l = blockIdx.y;
     const size_t k = blockIdx.z;
@@ -556,6 +567,7 @@ NTT_KERNEL void __launch_bounds__(256, ALL_FAST ? 3 : 2)
 k_decrypt_epilogue(const u64 *c, size_t item_stride, size_t c1_off, u64 *out, size_t out_stride, unsigned n, unsigned batch,
                                    DecryptConsts D, LimbArrays L)
 {
+    NTT_PDL_ENTER();
     (void)batch;
     NTT_SHARED DecLimb K[kMaxLimbs];
     dec_stage_limbs(K, 0, D.rp, D, L);

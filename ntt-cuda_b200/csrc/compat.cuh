@@ -36,6 +36,7 @@ float emu_normcdfinvf(float x);   // double-precision stand-in; GPU parity for t
 #define NTT_KERNEL static
 #define NTT_SHARED static          /* the emulator runs one CTA at a time: a function-local static is CTA-shared */
 #define NTT_UNROLL _Pragma("GCC unroll 32")
+#define NTT_PDL_ENTER()
 #else
 // ---------------------------------------------------------------------------------------------
 #include <cuda_runtime.h>
@@ -44,4 +45,9 @@ float emu_normcdfinvf(float x);   // double-precision stand-in; GPU parity for t
 #define NTT_KERNEL static __global__   /* header-defined kernels: internal linkage per translation unit */
 #define NTT_SHARED __shared__
 #define NTT_UNROLL _Pragma("unroll")
+// Programmatic dependent launch (launch_pdl in launch_util.h sets the attribute): the NEXT kernel of the stream may be scheduled while
+// this one runs, and this one may have been scheduled while its predecessor was still running -- so the first statement of the kernel
+// releases its dependents and then waits for the predecessor's completion and memory flush.  Stream order is unchanged; without the
+// launch attribute both instructions are no-ops.
+#define NTT_PDL_ENTER() asm volatile("griddepcontrol.launch_dependents;\n\tgriddepcontrol.wait;" ::: "memory")
 #endif

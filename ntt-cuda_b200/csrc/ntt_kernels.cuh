@@ -553,6 +553,7 @@ template <class P, int LOGN, bool INV, class EPI = NoEpi>
 __global__ void __launch_bounds__((1 << Sched<LOGN>::K1) * Sched<LOGN>::NT, ((1 << Sched<LOGN>::K1) * Sched<LOGN>::NT) > 256 ? 2 : NTT_MINB_S)
 ntt_strided_pass(const __grid_constant__ TensorMap tmap, NttArgs A, EpiArgs E)
 {
+    NTT_PDL_ENTER();
     using SC = Sched<LOGN>;
     constexpr int K1 = SC::K1, R = 1 << K1, NT = SC::NT, THREADS = R * NT;
     constexpr u32 n = 1u << LOGN, C = n >> K1;          // C columns per row
@@ -706,6 +707,7 @@ template <class P, int LOGN, bool INV>
 __global__ void __launch_bounds__(kContigRows, Sched<LOGN>::K2 == 8 ? 4 : NTT_MINB_C)   // radix-16 first round needs > 80 registers
 ntt_contig_pass(const __grid_constant__ TensorMap tmap, NttArgs A)
 {
+    NTT_PDL_ENTER();
     using SC = Sched<LOGN>;
     constexpr int K1 = SC::K1, K2 = SC::K2, SA = K2 - 4, NC = 16 >> SA, RT = kContigRows;
     constexpr u32 n = 1u << LOGN;
@@ -830,6 +832,7 @@ constexpr unsigned kSmallNttMaxPolys = 64;
 template <class P, int LOGN, bool INV>
 __global__ void __launch_bounds__(1 << (LOGN - 2)) ntt_single_pass(NttArgs A)
 {
+    NTT_PDL_ENTER();
     static_assert(!P::kLazyGS, "the latency kernel uses the per-butterfly-corrected policies");
     constexpr u32 n = 1u << LOGN, T = n >> 2;
     constexpr int PAIRS = LOGN / 2;                 // rounds of two stages; LOGN odd: one single-stage round more
@@ -927,6 +930,7 @@ template <class PF, class PI, int LOGN, int NOUT>
 __global__ void __launch_bounds__(kContigRows, 4)
 ntt_contig_fused_mul(const __grid_constant__ TensorMap tmap, FusedArgs F)
 {
+    NTT_PDL_ENTER();
     using SC = Sched<LOGN>;
     constexpr int K1 = SC::K1, K2 = SC::K2, SA = K2 - 4, NC = 16 >> SA, RT = kContigRows;
     constexpr u32 n = 1u << LOGN, TILES = (n >> 4) / RT;

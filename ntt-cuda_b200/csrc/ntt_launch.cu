@@ -124,11 +124,11 @@ static int launch_one(const NttArgs &A, int which, unsigned cnt, const CUtensorM
     As.pf_dist = (dev >= 0 && dev < 64) ? pf_dist_for(dev, occ_s[dev]) : 0;
     Ac.pf_dist = (dev >= 0 && dev < 64) ? pf_dist_for(dev, occ_c[dev]) : 0;
     if (!INV) {
-        if (do_strided) ntt_strided_pass<P, LOGN, INV><<<gs, R * SC::NT, smem_s, st>>>(ms, As, EpiArgs{});
-        if (do_contig) ntt_contig_pass<P, LOGN, INV><<<gc, kContigRows, smem_c, st>>>(mc, Ac);
+        if (do_strided) NTT_LAUNCH_PDL(ntt_strided_pass<P, LOGN, INV>, gs, dim3(R * SC::NT), smem_s, st, ms, As, EpiArgs{});
+        if (do_contig) NTT_LAUNCH_PDL(ntt_contig_pass<P, LOGN, INV>, gc, dim3(kContigRows), smem_c, st, mc, Ac);
     } else {
-        if (do_contig) ntt_contig_pass<P, LOGN, INV><<<gc, kContigRows, smem_c, st>>>(mc, Ac);
-        if (do_strided) ntt_strided_pass<P, LOGN, INV><<<gs, R * SC::NT, smem_s, st>>>(ms, As, EpiArgs{});
+        if (do_contig) NTT_LAUNCH_PDL(ntt_contig_pass<P, LOGN, INV>, gc, dim3(kContigRows), smem_c, st, mc, Ac);
+        if (do_strided) NTT_LAUNCH_PDL(ntt_strided_pass<P, LOGN, INV>, gs, dim3(R * SC::NT), smem_s, st, ms, As, EpiArgs{});
     }
     { const int e__ = (int)cudaGetLastError(); return e__ ? nttb200_trace_error(e__, __FILE__, __LINE__) : 0; }
 }
@@ -137,7 +137,7 @@ static int launch_one(const NttArgs &A, int which, unsigned cnt, const CUtensorM
 template <class P, int LOGN, bool INV>
 static int launch_single(const NttArgs &A, cudaStream_t st)
 {
-    ntt_single_pass<P, LOGN, INV><<<A.num, 1 << (LOGN - 2), (size_t)8 << LOGN, st>>>(A);
+    NTT_LAUNCH_PDL(ntt_single_pass<P, LOGN, INV>, dim3(A.num), dim3(1 << (LOGN - 2)), (size_t)8 << LOGN, st, A);
     { const int e__ = (int)cudaGetLastError(); return e__ ? nttb200_trace_error(e__, __FILE__, __LINE__) : 0; }
 }
 // NTTB200_CLUSTER_NTT=0 keeps the one-CTA latency kernel (A/B)
@@ -145,13 +145,6 @@ static bool use_cluster_ntt()
 {
     static int v = -1;
     if (v < 0) { const char *e = getenv("NTTB200_CLUSTER_NTT"); v = (e && e[0] == '0') ? 0 : 1; }
-    return v != 0;
-}
-// NTTB200_PDL=0: plain stream serialisation for the cluster kernel (A/B)
-static bool use_pdl()
-{
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("NTTB200_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
     return v != 0;
 }
 // n <= 4096, at most kClusterNttMaxPolys polynomials: one transform per cluster of n / 1024 CTAs (ntt_cluster_pass)
@@ -164,7 +157,7 @@ static int launch_cluster(const NttArgs &A, cudaStream_t st)
     cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // see the kernel: griddepcontrol.wait precedes its first global access
-    at[0].val.programmaticStreamSerializationAllowed = use_pdl() ? 1 : 0;
+    at[0].val.programmaticStreamSerializationAllowed = pdl_allow(st, (unsigned long long)A.num << (LOGN - 10)) ? 1 : 0;
     cfg.attrs = at;
     cfg.numAttrs = 1;
     NTTB200_CHECK(cudaLaunchKernelEx(&cfg, ntt_cluster_pass<P, LOGN, INV>, A));

@@ -37,7 +37,7 @@ static int launch_epi_one(const NttArgs &A, const EpiArgs &E, const CUtensorMap 
     As.pf_dist = (dev >= 0 && dev < 64) ? pf_dist_for(dev, occ[dev]) : 0;
     const unsigned tiles_s = tiles_s1 / tpc_s;
     if ((size_t)A.num * tiles_s >= (1ull << 31)) return NTTB200_EINVAL;
-    ntt_strided_pass<P, LOGN, true, EPI><<<A.num * tiles_s, R * SC::NT, smem_s, st>>>(ms, As, E);
+    NTT_LAUNCH_PDL(ntt_strided_pass<P, LOGN, true, EPI>, dim3(A.num * tiles_s), dim3(R * SC::NT), smem_s, st, ms, As, E);
     { const int e__ = (int)cudaGetLastError(); return e__ ? nttb200_trace_error(e__, __FILE__, __LINE__) : 0; }
 }
 template <class EPI>

@@ -23,7 +23,7 @@ static int launch_fused_one(const FusedArgs &F, const CUtensorMap &mc, cudaStrea
         if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
     const unsigned tiles = ((1u << LOGN) >> 4) / kContigRows;
-    ntt_contig_fused_mul<PF, PI, LOGN, NOUT><<<F.items * F.r * tiles, kContigRows, smem, st>>>(mc, F);
+    NTT_LAUNCH_PDL(ntt_contig_fused_mul<PF, PI, LOGN, NOUT>, dim3(F.items * F.r * tiles), dim3(kContigRows), smem, st, mc, F);
     { const int e__ = (int)cudaGetLastError(); return e__ ? nttb200_trace_error(e__, __FILE__, __LINE__) : 0; }
 }
 template <class PF, class PI, int NOUT>
