@@ -379,7 +379,7 @@ int nttb200_bfv_relin_keygen(nttb200_bfv *b, const nttb200_u64 *sk, nttb200_u64 
     unsigned char *ks = nullptr;
     u64 *E = nullptr;
     NTTB200_CHECK(cudaMalloc(&ks, ks_stride * rp));
-    NTTB200_CHECK(cudaMalloc(&E, (size_t)rp * rp * n * 8));
+    if (cudaMalloc(&E, (size_t)rp * rp * n * 8) != cudaSuccess) { cudaFree(ks); return nttb200_trace_error((int)cudaErrorMemoryAllocation, __FILE__, __LINE__); }
     const u64 nblk = ks_stride / 64;
     k_salsa20_keystream<<<grid_for(nblk * rp, 256), 256, 0, st>>>(ks, nblk, (u64)rp, ks_stride, bfv_salsa_key(b), nonce0);
     k_relin_sample<<<pair_grid3(n, rp * rp, 1), 256, 0, st>>>(ks, ks_stride, s->evk, E, n, rp, s->modQ);
